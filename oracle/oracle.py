@@ -1,0 +1,190 @@
+"""ctypes loader for the CPU oracle (oracle/libgfs_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (geoflowslam_b200) never imports it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4")])
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libgfs_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith(".cpp")]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        L = _LIB
+        L.gfo_orb_create.restype = C.c_void_p
+        L.gfo_orb_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.gfo_orb_destroy.argtypes = [C.c_void_p]
+        L.gfo_orb_set_threads.argtypes = [C.c_void_p, C.c_int]
+        L.gfo_orb_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 3
+        L.gfo_orb_level_size.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.gfo_orb_extract.restype = C.c_int
+        L.gfo_orb_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.gfo_orb_get_level.restype = C.c_int
+        L.gfo_orb_get_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.gfo_orb_get_candidates.restype = C.c_int
+        L.gfo_orb_get_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.gfo_resize_area.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.gfo_blur7.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.gfo_fast_atan2.restype = C.c_float
+        L.gfo_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.gfo_fast.restype = C.c_int
+        L.gfo_fast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.gfo_distribute_octtree.restype = C.c_int
+        L.gfo_distribute_octtree.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_int]
+        for name, setup in _LATE_BINDERS:
+            if hasattr(L, name):
+                setup(L)
+    return _LIB
+
+
+_LATE_BINDERS = []  # (symbol, binder) pairs registered by the other oracle modules
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OrbOracle:
+    """Mirror of ORB_SLAM3::ORBextractor (include/ORBextractor.h:46-120) over the C oracle."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, threads=1):
+        self.L = lib()
+        self.h = self.L.gfo_orb_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self.L.gfo_orb_set_threads(self.h, threads)
+        self.cap = nfeatures + 4 * nlevels
+
+    def __del__(self):
+        try:
+            self.L.gfo_orb_destroy(self.h)
+        except Exception:
+            pass
+
+    def tables(self):
+        sf = np.zeros(self.nlevels, np.float32)
+        npl = np.zeros(self.nlevels, np.int32)
+        um = np.zeros(16, np.int32)
+        self.L.gfo_orb_tables(self.h, _p(sf), _p(npl), _p(um))
+        return sf, npl, um
+
+    def level_size(self, w, h, l):
+        lw, lh = C.c_int(), C.c_int()
+        self.L.gfo_orb_level_size(self.h, w, h, l, C.byref(lw), C.byref(lh))
+        return lw.value, lh.value
+
+    def extract(self, img, lapping=(0, 0)):
+        """-> (keypoints structured array, descriptors (n,32) u8, monoIndex)"""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        kps = np.zeros(self.cap, KP_DTYPE)
+        desc = np.zeros((self.cap, 32), np.uint8)
+        mono = C.c_int()
+        n = self.L.gfo_orb_extract(self.h, _p(img), w, h, w, lapping[0], lapping[1], _p(kps), _p(desc), self.cap,
+                                   C.byref(mono))
+        if n < 0:
+            return kps[:0], desc[:0], -1
+        assert n <= self.cap
+        self._wh = (w, h)
+        return kps[:n].copy(), desc[:n].copy(), mono.value
+
+    def level(self, l, blurred=False):
+        lw, lh = self.level_size(self._wh[0], self._wh[1], l)
+        out = np.zeros((lh, lw), np.uint8)
+        ok = self.L.gfo_orb_get_level(self.h, l, int(blurred), _p(out))
+        return out if ok else None
+
+    def candidates(self, l):
+        buf = np.zeros((200000, 3), np.float32)
+        n = self.L.gfo_orb_get_candidates(self.h, l, _p(buf), buf.shape[0])
+        return buf[:n].copy()
+
+
+def resize_area(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().gfo_resize_area(_p(src), src.shape[1], src.shape[0], _p(dst), dw, dh)
+    return dst
+
+
+def blur7(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros_like(src)
+    lib().gfo_blur7(_p(src), src.shape[1], src.shape[0], _p(dst))
+    return dst
+
+
+def fast_atan2(y, x):
+    return lib().gfo_fast_atan2(float(y), float(x))
+
+
+def fast(img, thr):
+    img = np.ascontiguousarray(img, np.uint8)
+    buf = np.zeros((img.size // 4 + 16, 3), np.int32)
+    n = lib().gfo_fast(_p(img), img.shape[1], img.shape[0], thr, _p(buf), buf.shape[0])
+    return buf[:n].copy()
+
+
+def distribute_octtree(xyr, minX, maxX, minY, maxY, N):
+    xyr = np.ascontiguousarray(xyr, np.float32)
+    out = np.zeros((max(N, 1) * 4 + 16, 3), np.float32)
+    n = lib().gfo_distribute_octtree(_p(xyr), xyr.shape[0], minX, maxX, minY, maxY, N, _p(out), out.shape[0])
+    return out[:n].copy()
+
+
+# ------------------------------------------------------------------------------ matching
+def _bind_match(L):
+    L.gfo_descriptor_distance.restype = C.c_int
+    L.gfo_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
+    L.gfo_bf_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.gfo_gms_filter.restype = C.c_int
+    L.gfo_gms_filter.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_int, C.c_void_p]
+
+
+_LATE_BINDERS.append(("gfo_bf_match", _bind_match))
+
+
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().gfo_descriptor_distance(_p(a), _p(b))
+
+
+def bf_match(dq, dt, threads=1):
+    """cv::BFMatcher(NORM_HAMMING).match(dq, dt) -> (trainIdx[nq], distance[nq])"""
+    dq = np.ascontiguousarray(dq, np.uint8).reshape(-1, 32)
+    dt = np.ascontiguousarray(dt, np.uint8).reshape(-1, 32)
+    idx = np.zeros(len(dq), np.int32); dist = np.zeros(len(dq), np.int32)
+    lib().gfo_bf_match(_p(dq), len(dq), _p(dt), len(dt), _p(idx), _p(dist), threads)
+    return idx, dist
+
+
+def gms_filter(pts1, size1, pts2, size2, matches):
+    """gms_matcher(kp1, size1, kp2, size2, matches).GetInlierMask(mask, false, false)"""
+    pts1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+    pts2 = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
+    matches = np.ascontiguousarray(matches, np.int32).reshape(-1, 2)
+    mask = np.zeros(max(len(matches), 1), np.uint8)
+    n = lib().gfo_gms_filter(_p(pts1), len(pts1), size1[0], size1[1], _p(pts2), len(pts2), size2[0], size2[1],
+                             _p(matches), len(matches), _p(mask))
+    return mask[:len(matches)].astype(bool), n
