@@ -1,0 +1,96 @@
+"""ctypes binding of libgfs_b200.so (the C ABI declared in include/gfs_b200.h).
+
+There is no CPU fallback: if the library cannot be built/loaded, or no CUDA device is present
+when a compute entry point is called, the call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libgfs_b200.so")
+_LIB = None
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4")])
+
+GFS_OK, GFS_ERR_INVALID, GFS_ERR_CUDA, GFS_ERR_CAPACITY, GFS_ERR_EMPTY, GFS_ERR_NODEVICE = 0, -1, -2, -3, -4, -5
+
+
+class GfsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libgfs_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _sig(L, name, argtypes, restype=C.c_int):
+    f = getattr(L, name)
+    f.argtypes = argtypes
+    f.restype = restype
+
+
+vp, ci, cf, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+
+# every symbol include/gfs_b200.h declares (tests/test_cabi.py checks the library exports them all)
+SIGNATURES = {
+    "gfs_last_error": ([], C.c_char_p),
+    "gfs_device_check": ([], ci),
+    "gfs_version": ([], C.c_char_p),
+    "gfs_orb_create": ([ci, cf, ci, ci, ci, ci, ci, ci, C.POINTER(vp)], ci),
+    "gfs_orb_destroy": ([vp], ci),
+    "gfs_orb_max_keypoints": ([vp], ci),
+    "gfs_orb_tables": ([vp, vp, vp], ci),
+    "gfs_orb_level_size": ([vp, ci, ci, ci, vp, vp], ci),
+    "gfs_orb_extract_batch_device": ([vp, vp, vp, ci, ci, ci, ci, sz, ci, ci, vp, vp, vp, vp], ci),
+    "gfs_orb_extract_batch": ([vp, vp, vp, ci, ci, ci, ci, sz, ci, ci, vp, vp, vp, vp], ci),
+    "gfs_orb_extract": ([vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp], ci),
+    "gfs_orb_get_level": ([vp, vp, ci, ci, ci, vp], ci),
+    "gfs_orb_get_candidates": ([vp, vp, ci, ci, vp, ci, vp], ci),
+    "gfs_orb_launches_per_call": ([vp, ci, ci], ci),
+    "gfs_match_bf_hamming_batch_device": ([vp, vp, vp, vp, vp, ci, ci, vp, vp], ci),
+    "gfs_match_bf_hamming": ([vp, vp, ci, vp, ci, vp, vp], ci),
+    "gfs_gms_filter_batch_device": ([vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp], ci),
+    "gfs_gms_filter": ([vp, vp, ci, ci, ci, vp, ci, ci, ci, vp, ci, vp, vp], ci),
+}
+DEBUG_SIGNATURES = {
+    "gfs_debug_gcc_sort": ([vp, vp, vp, ci, vp], ci),
+}
+
+
+def lib():
+    """Load (building if needed) the native library.  Raises if it cannot be had."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_SO):
+            from . import build
+            build.build_native()
+        L = C.CDLL(_SO)
+        for table in (SIGNATURES, DEBUG_SIGNATURES):
+            for name, (args, res) in table.items():
+                if hasattr(L, name):
+                    _sig(L, name, args, res)
+        _LIB = L
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        raise GfsError(rc, lib().gfs_last_error().decode("utf-8", "replace"))
+
+
+def require_device():
+    check(lib().gfs_device_check())
+
+
+def ptr(a):
+    """void* of a numpy array, torch tensor, int address or None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))

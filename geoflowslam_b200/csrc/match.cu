@@ -1,0 +1,376 @@
+// Descriptor matching on sm_100a: brute-force 256-bit Hamming argmin and the GMS grid filter.
+//
+// Replaces, for whole batches of frame pairs,
+//   * cv::BFMatcher(NORM_HAMMING).match(d1, d2)          reference call sites src/ORBmatcher.cc:755-756, 805-806, 888-889
+//   * ORBmatcher::DescriptorDistance                      src/ORBmatcher.cc:2536-2550
+//   * gms_matcher::GetInlierMask(mask, false, false)      Thirdparty/GMS/include/gms_matcher.h:236-246 -> run(1) :385-419
+// Integer work throughout: results are bit-exact against oracle/match_oracle.cpp.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gfs {
+
+// ------------------------------------------------------------------------------------------------
+// k_bf_hamming: CTA = 8 warps; the pair's train descriptors are staged once per CTA in shared
+// memory, word-major (T[w][row]) so a warp's 32 lanes read 32 consecutive words; each warp keeps
+// 4 query descriptors in registers and sweeps the train rows lane-strided.  Ties resolve to the
+// lowest train index (each lane scans its rows in increasing order with '<', the warp reduction
+// orders by (distance, index)).
+// ------------------------------------------------------------------------------------------------
+static const int BF_WARPS = 8;
+static const int BF_QPW = 4;                         // queries per warp per sweep
+static const int BF_QPB = BF_WARPS * BF_QPW * 2;     // queries per CTA (two sweeps)
+
+__global__ void __launch_bounds__(BF_WARPS * 32) k_bf_hamming(const uint8_t* __restrict__ dq, const int* __restrict__ nq,
+                                                              const uint8_t* __restrict__ dt, const int* __restrict__ nt,
+                                                              int stride, int* __restrict__ out_idx,
+                                                              int* __restrict__ out_dist) {
+  extern __shared__ uint32_t T[];  // [8][tp]
+  const int pair = blockIdx.y;
+  const int nQ = nq[pair], nT = nt[pair];
+  const int q0 = blockIdx.x * BF_QPB;
+  if (q0 >= nQ) return;
+  const int tp = (nT + 31) & ~31;
+  const uint32_t* gt = (const uint32_t*)(dt + (size_t)pair * stride * 32);
+  for (int i = threadIdx.x; i < tp * 8; i += blockDim.x) {
+    const int row = i >> 3, w = i & 7;
+    T[w * tp + row] = (row < nT) ? __ldg(gt + i) : 0u;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t* gq = (const uint32_t*)(dq + (size_t)pair * stride * 32);
+  for (int sweep = 0; sweep < 2; sweep++) {
+    const int qb = q0 + (sweep * BF_WARPS + warp) * BF_QPW;
+    if (qb >= nQ) continue;
+    uint32_t qw[BF_QPW][8];
+#pragma unroll
+    for (int j = 0; j < BF_QPW; j++) {
+      const int q = min(qb + j, nQ - 1);
+#pragma unroll
+      for (int w = 0; w < 8; w++) qw[j][w] = __ldg(gq + (size_t)q * 8 + w);
+    }
+    int best[BF_QPW], bidx[BF_QPW];
+#pragma unroll
+    for (int j = 0; j < BF_QPW; j++) { best[j] = 0x7fffffff; bidx[j] = -1; }
+    for (int t = lane; t < nT; t += 32) {
+      uint32_t tw[8];
+#pragma unroll
+      for (int w = 0; w < 8; w++) tw[w] = T[w * tp + t];
+#pragma unroll
+      for (int j = 0; j < BF_QPW; j++) {
+        int d = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) d += __popc(qw[j][w] ^ tw[w]);
+        if (d < best[j]) { best[j] = d; bidx[j] = t; }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < BF_QPW; j++) {
+      // (distance, index) packed so that min() prefers the smaller distance, then the lower index
+      unsigned long long v = ((unsigned long long)(unsigned)best[j] << 32) | (unsigned)(bidx[j] < 0 ? 0x7fffffff : bidx[j]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+      const int q = qb + j;
+      if (lane == 0 && q < nQ) {
+        const bool none = nT == 0;
+        out_idx[(size_t)pair * stride + q] = none ? -1 : (int)(v & 0xffffffffu);
+        out_dist[(size_t)pair * stride + q] = none ? -1 : (int)(v >> 32);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_gms: one CTA per frame pair.  The reference's dense 400x400 motion-statistics table (640 KB,
+// cleared four times per call) is replaced by the sorted list of the <= nm occupied (left cell,
+// right cell) keys; every table read becomes a binary-search count, which is exact.
+// ------------------------------------------------------------------------------------------------
+static const int GMS_G = 20, GMS_NG = 400, GMS_THREADS = 256;
+
+__device__ __forceinline__ int gms_nb9(int idx, int k) {
+  const int x = idx % GMS_G + (k % 3 - 1), y = idx / GMS_G + (k / 3 - 1);
+  if (x < 0 || x >= GMS_G || y < 0 || y >= GMS_G) return -1;
+  return x + y * GMS_G;
+}
+__device__ __forceinline__ int lower_bound_u32(const uint32_t* a, int n, uint32_t key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(GMS_THREADS) k_gms(const GfsKeyPoint* __restrict__ kp1, const int* __restrict__ n1,
+                                                     const GfsKeyPoint* __restrict__ kp2, const int* __restrict__ n2,
+                                                     const int* __restrict__ mq, const int* __restrict__ mt,
+                                                     const int* __restrict__ nmArr, int stride, int mstride, int pow2,
+                                                     int w1, int h1, int w2, int h2, uint8_t* __restrict__ out_inlier,
+                                                     int* __restrict__ out_count) {
+  extern __shared__ uint32_t gsm[];
+  uint32_t* keys = gsm;                          // [pow2]
+  short* ml = (short*)(keys + pow2);             // [mstride] left cell of match i (this grid type)
+  short* mr = ml + mstride;                      // [mstride] right cell (grid type 1)
+  int* nLeft = (int*)(mr + mstride + (mstride & 1));  // [400]
+  int* cellPair = nLeft + GMS_NG;                // [400]
+  __shared__ int s_cnt;
+  const int pair = blockIdx.x, tid = threadIdx.x;
+  const int nm = nmArr ? nmArr[pair] : n1[pair];
+  const int N1 = n1[pair], N2 = n2[pair];
+  const GfsKeyPoint* K1 = kp1 + (size_t)pair * stride;
+  const GfsKeyPoint* K2 = kp2 + (size_t)pair * stride;
+  const int* MQ = mq ? mq + (size_t)pair * mstride : nullptr;
+  const int* MT = mt + (size_t)pair * mstride;
+  uint8_t* mask = out_inlier + (size_t)pair * mstride;
+  for (int i = tid; i < nm; i += GMS_THREADS) mask[i] = 0;
+  if (tid == 0) s_cnt = 0;
+
+  for (int type = 1; type <= 4; type++) {
+    __syncthreads();
+    for (int i = tid; i < pow2; i += GMS_THREADS) {
+      uint32_t key = 0xffffffffu;
+      if (i < nm) {
+        const int q = MQ ? MQ[i] : i, t = MT[i];
+        int l = -1, r = -1;
+        if (q >= 0 && q < N1 && t >= 0 && t < N2) {
+          // NormalizePoints :104-115 and GetGridIndexLeft/Right :125-160
+          const float lx = __fmul_rn(__fdiv_rn(K1[q].x, (float)w1), (float)GMS_G);
+          const float ly = __fmul_rn(__fdiv_rn(K1[q].y, (float)h1), (float)GMS_G);
+          const int x = (type == 2 || type == 4) ? (int)floor((double)lx + 0.5) : (int)floorf(lx);
+          const int y = (type == 3 || type == 4) ? (int)floor((double)ly + 0.5) : (int)floorf(ly);
+          l = (x >= GMS_G || y >= GMS_G) ? -1 : x + y * GMS_G;
+          if (type == 1) {
+            const float rx = __fmul_rn(__fdiv_rn(K2[t].x, (float)w2), (float)GMS_G);
+            const float ry = __fmul_rn(__fdiv_rn(K2[t].y, (float)h2), (float)GMS_G);
+            r = (int)floorf(rx) + (int)floorf(ry) * GMS_G;
+            // keep -1 / -2 exact (the reference compares raw indices against mCellPairs, :406)
+            r = (r < -2) ? -3 : min(r, 32000);
+            mr[i] = (short)r;
+          } else {
+            r = mr[i];
+          }
+        } else if (type == 1) {
+          mr[i] = -1;
+        }
+        ml[i] = (short)max(-1, min(l, 32000));
+        if (l >= 0 && r >= 0 && l < GMS_NG && r < GMS_NG) key = (uint32_t)(l * GMS_NG + r);
+      }
+      keys[i] = key;
+    }
+    __syncthreads();
+    // bitonic sort of keys[0..pow2)
+    for (int k = 2; k <= pow2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < pow2; i += GMS_THREADS) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const uint32_t a = keys[i], b = keys[ixj];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    // per left cell: population, first-maximum right cell (VerifyCellPairs :338-356)
+    for (int c = tid; c < GMS_NG; c += GMS_THREADS) {
+      const int lo = lower_bound_u32(keys, pow2, (uint32_t)(c * GMS_NG));
+      const int hi = lower_bound_u32(keys, pow2, (uint32_t)((c + 1) * GMS_NG));
+      nLeft[c] = hi - lo;
+      int bestR = -1, bestN = 0, i = lo;
+      while (i < hi) {
+        const uint32_t k = keys[i];
+        int j = i + 1;
+        while (j < hi && keys[j] == k) j++;
+        if (j - i > bestN) { bestN = j - i; bestR = (int)(k - (uint32_t)(c * GMS_NG)); }
+        i = j;
+      }
+      cellPair[c] = bestR;  // -1 when the row is empty
+    }
+    __syncthreads();
+    // neighbourhood support test (:358-381); decisions are staged so every cell reads the
+    // unmodified nLeft / keys
+    int dec[(GMS_NG + GMS_THREADS - 1) / GMS_THREADS];
+    {
+      int u = 0;
+      for (int c = tid; c < GMS_NG; c += GMS_THREADS, u++) {
+        const int rt = cellPair[c];
+        dec[u] = rt;
+        if (rt < 0) continue;
+        int score = 0, numpair = 0;
+        double thresh = 0;
+        for (int k = 0; k < 9; k++) {
+          const int ll = gms_nb9(c, k), rr = gms_nb9(rt, k);
+          if (ll == -1 || rr == -1) continue;
+          const uint32_t key = (uint32_t)(ll * GMS_NG + rr);
+          const int lo = lower_bound_u32(keys, pow2, key);
+          const int hi = lower_bound_u32(keys, pow2, key + 1);
+          score += hi - lo;
+          thresh += nLeft[ll];
+          numpair++;
+        }
+        thresh = 6.0 * sqrt(thresh / numpair);
+        if (score < thresh) dec[u] = -2;
+      }
+    }
+    __syncthreads();
+    {
+      int u = 0;
+      for (int c = tid; c < GMS_NG; c += GMS_THREADS, u++) cellPair[c] = dec[u];
+    }
+    __syncthreads();
+    for (int i = tid; i < nm; i += GMS_THREADS) {
+      const int l = ml[i];
+      if (l >= 0 && l < GMS_NG && cellPair[l] == (int)mr[i]) mask[i] = 1;
+    }
+  }
+  __syncthreads();
+  int c = 0;
+  for (int i = tid; i < nm; i += GMS_THREADS) c += mask[i];
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((tid & 31) == 0 && c) atomicAdd(&s_cnt, c);
+  __syncthreads();
+  if (tid == 0) out_count[pair] = s_cnt;
+}
+
+static int next_pow2(int n) {
+  int p = 32;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+static int launch_gms(cudaStream_t st, const GfsKeyPoint* kp1, const int* n1, const GfsKeyPoint* kp2, const int* n2,
+                      const int* mq, const int* mt, const int* nm, int pairs, int stride, int mstride, int w1, int h1,
+                      int w2, int h2, uint8_t* inl, int* cnt) {
+  const int p2 = next_pow2(mstride);
+  const size_t smem = (size_t)p2 * 4 + ((size_t)mstride * 2 + (mstride & 1)) * 2 + 2 * GMS_NG * 4;
+  GFS_REQUIRE(smem <= 200 * 1024, GFS_ERR_CAPACITY, "too many matches per pair for the GMS kernel (max ~24k)");
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    GFS_CUDA(cudaFuncSetAttribute(k_gms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  k_gms<<<pairs, GMS_THREADS, smem, st>>>(kp1, n1, kp2, n2, mq, mt, nm, stride, mstride, p2, w1, h1, w2, h2, inl, cnt);
+  GFS_CUDA(cudaGetLastError());
+  return GFS_OK;
+}
+
+}  // namespace gfs
+
+using namespace gfs;
+
+extern "C" {
+
+int gfs_match_bf_hamming_batch_device(void* stream, const uint8_t* d_dq, const int* d_nq, const uint8_t* d_dt,
+                                      const int* d_nt, int pairs, int stride, int* d_out_idx, int* d_out_dist) {
+  GFS_REQUIRE(d_dq && d_nq && d_dt && d_nt && d_out_idx && d_out_dist, GFS_ERR_INVALID, "null pointer");
+  GFS_REQUIRE(pairs > 0 && stride > 0, GFS_ERR_INVALID, "bad pairs/stride");
+  const size_t smem = (size_t)((stride + 31) & ~31) * 32;
+  GFS_REQUIRE(smem <= 200 * 1024, GFS_ERR_CAPACITY, "train set too large for shared memory (max 6400 rows)");
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    GFS_CUDA(cudaFuncSetAttribute(k_bf_hamming, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  k_bf_hamming<<<dim3(div_up(stride, BF_QPB), pairs), BF_WARPS * 32, smem, (cudaStream_t)stream>>>(
+      d_dq, d_nq, d_dt, d_nt, stride, d_out_idx, d_out_dist);
+  GFS_CUDA(cudaGetLastError());
+  return GFS_OK;
+}
+
+int gfs_match_bf_hamming(void* stream, const uint8_t* dq, int nq, const uint8_t* dt, int nt, int* out_idx,
+                         int* out_dist) {
+  GFS_REQUIRE(nq >= 0 && nt >= 0, GFS_ERR_INVALID, "negative size");
+  GFS_REQUIRE((dq || nq == 0) && (dt || nt == 0), GFS_ERR_INVALID, "null descriptors");
+  if (nq == 0) return GFS_OK;
+  GFS_REQUIRE(out_idx && out_dist, GFS_ERR_INVALID, "null output");
+  int rc = gfs_device_check();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int stride = std::max(std::max(nq, nt), 1);
+  DevBuf b;
+  const size_t dsz = (size_t)stride * 32;
+  if ((rc = b.reserve(2 * dsz + 2 * sizeof(int) * (size_t)stride + 16))) return rc;
+  uint8_t* d_q = (uint8_t*)b.p;
+  uint8_t* d_t = d_q + dsz;
+  int* d_idx = (int*)(d_t + dsz);
+  int* d_dist = d_idx + stride;
+  int* d_n = d_dist + stride;
+  const int hn[2] = {nq, nt};
+  auto fail = [&](int code) { b.release(); return code; };
+  if (cudaMemcpyAsync(d_q, dq, (size_t)nq * 32, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      (nt && cudaMemcpyAsync(d_t, dt, (size_t)nt * 32, cudaMemcpyHostToDevice, st) != cudaSuccess) ||
+      cudaMemcpyAsync(d_n, hn, sizeof(hn), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+    set_error("H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(GFS_ERR_CUDA);
+  }
+  rc = gfs_match_bf_hamming_batch_device(stream, d_q, d_n, d_t, d_n + 1, 1, stride, d_idx, d_dist);
+  if (rc) return fail(rc);
+  if (cudaMemcpyAsync(out_idx, d_idx, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaMemcpyAsync(out_dist, d_dist, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess) {
+    set_error("D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(GFS_ERR_CUDA);
+  }
+  b.release();
+  return GFS_OK;
+}
+
+int gfs_gms_filter_batch_device(void* stream, const GfsKeyPoint* d_kp1, const int* d_n1, const GfsKeyPoint* d_kp2,
+                                const int* d_n2, const int* d_train_idx, int pairs, int stride, int w1, int h1,
+                                int w2, int h2, uint8_t* d_out_inlier, int* d_out_count) {
+  GFS_REQUIRE(d_kp1 && d_n1 && d_kp2 && d_n2 && d_train_idx && d_out_inlier && d_out_count, GFS_ERR_INVALID, "null pointer");
+  GFS_REQUIRE(pairs > 0 && stride > 0 && w1 > 0 && h1 > 0 && w2 > 0 && h2 > 0, GFS_ERR_INVALID, "bad sizes");
+  return launch_gms((cudaStream_t)stream, d_kp1, d_n1, d_kp2, d_n2, nullptr, d_train_idx, nullptr, pairs, stride, stride,
+                    w1, h1, w2, h2, d_out_inlier, d_out_count);
+}
+
+int gfs_gms_filter(void* stream, const GfsKeyPoint* kp1, int n1, int w1, int h1, const GfsKeyPoint* kp2, int n2,
+                   int w2, int h2, const int* matches_qt, int nm, uint8_t* out_inlier, int* out_count) {
+  GFS_REQUIRE(n1 >= 0 && n2 >= 0 && nm >= 0 && w1 > 0 && h1 > 0 && w2 > 0 && h2 > 0, GFS_ERR_INVALID, "bad sizes");
+  GFS_REQUIRE(out_count, GFS_ERR_INVALID, "null output");
+  *out_count = 0;
+  if (nm == 0) return GFS_OK;
+  GFS_REQUIRE(kp1 && kp2 && matches_qt && out_inlier, GFS_ERR_INVALID, "null pointer");
+  int rc = gfs_device_check();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int stride = std::max(std::max(n1, n2), 1);
+  std::vector<int> mq(nm), mt(nm);
+  for (int i = 0; i < nm; i++) { mq[i] = matches_qt[2 * i]; mt[i] = matches_qt[2 * i + 1]; }
+  DevBuf b;
+  const size_t ksz = (size_t)stride * sizeof(GfsKeyPoint);
+  if ((rc = b.reserve(2 * ksz + (size_t)nm * 8 + align_up((size_t)nm, 16) + 64))) return rc;
+  GfsKeyPoint* d_k1 = (GfsKeyPoint*)b.p;
+  GfsKeyPoint* d_k2 = d_k1 + stride;
+  int* d_mq = (int*)(d_k2 + stride);
+  int* d_mt = d_mq + nm;
+  int* d_n = d_mt + nm;  // n1, n2, nm, count
+  uint8_t* d_mask = (uint8_t*)(d_n + 4);
+  const int hn[4] = {n1, n2, nm, 0};
+  bool ok = true;
+  if (n1) ok &= cudaMemcpyAsync(d_k1, kp1, (size_t)n1 * sizeof(GfsKeyPoint), cudaMemcpyHostToDevice, st) == cudaSuccess;
+  if (n2) ok &= cudaMemcpyAsync(d_k2, kp2, (size_t)n2 * sizeof(GfsKeyPoint), cudaMemcpyHostToDevice, st) == cudaSuccess;
+  ok &= cudaMemcpyAsync(d_mq, mq.data(), (size_t)nm * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+  ok &= cudaMemcpyAsync(d_mt, mt.data(), (size_t)nm * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+  ok &= cudaMemcpyAsync(d_n, hn, sizeof(hn), cudaMemcpyHostToDevice, st) == cudaSuccess;
+  if (!ok) {
+    set_error("H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    b.release();
+    return GFS_ERR_CUDA;
+  }
+  rc = launch_gms(st, d_k1, d_n, d_k2, d_n + 1, d_mq, d_mt, d_n + 2, 1, stride, nm, w1, h1, w2, h2, d_mask, d_n + 3);
+  if (rc) { b.release(); return rc; }
+  ok = cudaMemcpyAsync(out_inlier, d_mask, nm, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+  ok &= cudaMemcpyAsync(out_count, d_n + 3, sizeof(int), cudaMemcpyDeviceToHost, st) == cudaSuccess;
+  ok &= cudaStreamSynchronize(st) == cudaSuccess;
+  b.release();
+  if (!ok) {
+    set_error("D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return GFS_ERR_CUDA;
+  }
+  return GFS_OK;
+}
+}

@@ -1,0 +1,1245 @@
+// ORB extractor for batches of frames on sm_100a.
+//
+// Replaces ORB_SLAM3::ORBextractor::operator() (reference src/ORBextractor.cc:1145-1225) and the
+// OpenCV primitives underneath it.  One launch sequence processes a whole batch of frames:
+//
+//   k_pyr_level   x (nlevels-1)  INTER_AREA pyramid (ComputePyramid :1227-1251, cv::resize)
+//   k_fast_cells                 per 35-px cell FAST-9/16 + 3x3 NMS + ini->min threshold retry
+//                                (ComputeKeyPointsOctTree cell loop :794-851, cv::FAST)
+//   k_octree                     quadtree keypoint distribution (DistributeOctTree :567-768), one
+//                                warp per (frame, level), exact std::list / std::sort semantics
+//   k_blur7                      7x7 sigma=2 fixed-point Gaussian per level (:1188-1189)
+//   k_orient_desc                IC_Angle (:71-95) + rBRIEF (:99-160) + output packing (:1196-1218),
+//                                one warp per keypoint
+//   k_pack_lapping               only when a lapping area is given (:1208-1217)
+//
+// All arithmetic follows the oracle (oracle/orb_oracle.cpp): integer stages exactly, float stages
+// with explicit _rn intrinsics so nvcc cannot contract them into FMAs.
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "gcc_sort.h"
+#include "../../include/gfs_orb_pattern.h"
+
+namespace gfs {
+
+static const int MAX_LEVELS = 12;
+static const int EDGE_THRESHOLD = 19;
+static const int HALF_PATCH = 15;
+static const int PATCH_SIZE = 31;
+static const int MIN_BORDER = EDGE_THRESHOLD - 3;  // 16
+
+struct LevelDev {
+  int w, h, pitch;
+  long long off;  // byte offset of this level inside a frame's pyramid / blur block
+  int nCols, nRows, wCell, hCell, cellBase;
+  int maxBorderX, maxBorderY;
+  int nFeat, nIni;
+  float hX;
+  int keyOff;          // offset (in keys) inside a frame's key buffers
+  int selOff, selCap;  // slot range inside a frame's selected-keypoint array
+  int tabX, tabY;      // first entry of this level's area tables
+  float scale;
+  int patchSize;
+};
+
+struct OrbDev {
+  int nlevels, iniTh, minTh;
+  int cellCap, totalCells, keysPerFrame, selPerFrame, kpStride, nodeCap;
+  int roiPitch, roiRows, scPitch;  // shared-memory geometry of k_fast_cells
+  long long pyrStride;
+  float p1, p3, p5, p7, factorPI;  // fastAtan2 polynomial (degrees) and deg->rad
+  int umax[16];
+  LevelDev lv[MAX_LEVELS];
+};
+
+struct AreaEntry {
+  int s0, n;
+  float a[4];
+};
+
+__constant__ signed char c_pattern[1024];
+
+// ------------------------------------------------------------------------------------------------
+// k_pyr_level: one thread per destination pixel.  OpenCV's area resize accumulates, per source
+// row, buf = S0*a0 (+ S1*a1 (+ S2*a2)) in float and then sum = b0*buf0 (+ b1*buf1 ...) -- the same
+// order is kept here, every product and sum rounded separately.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pyr_level(OrbDev P, int l, const uint8_t* __restrict__ src_base,
+                                                   long long src_stride, int src_pitch, uint8_t* __restrict__ pyr,
+                                                   const AreaEntry* __restrict__ tabs) {
+  const LevelDev& L = P.lv[l];
+  const int dx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int dy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (dx >= L.w || dy >= L.h) return;
+  const int frame = blockIdx.z;
+  const uint8_t* src = src_base + (long long)frame * src_stride;
+  const AreaEntry ex = tabs[L.tabX + dx];
+  const AreaEntry ey = tabs[L.tabY + dy];
+  float sum = 0.f;
+  for (int r = 0; r < ey.n; r++) {
+    const uint8_t* S = src + (long long)(ey.s0 + r) * src_pitch + ex.s0;
+    float buf = __fmul_rn((float)S[0], ex.a[0]);
+    for (int k = 1; k < ex.n; k++) buf = __fadd_rn(buf, __fmul_rn((float)S[k], ex.a[k]));
+    const float t = __fmul_rn(ey.a[r], buf);
+    sum = (r == 0) ? t : __fadd_rn(sum, t);
+  }
+  int v = __float2int_rn(sum);
+  v = min(255, max(0, v));
+  pyr[(long long)frame * P.pyrStride + L.off + (long long)dy * L.pitch + dx] = (uint8_t)v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fast_cells: one CTA per (cell, frame).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool has_arc9(unsigned m16) {
+  unsigned m = m16 | (m16 << 16);
+  unsigned r = m & (m >> 1);
+  r &= r >> 2;
+  r &= r >> 4;
+  r &= m >> 8;
+  return (r & 0xFFFFu) != 0;
+}
+
+// best = max over the 16 arcs of 9 contiguous ring pixels of max(min d, -max d)
+__device__ __forceinline__ int fast_best16(const int (&d)[16]) {
+  int mn2[16], mx2[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    mn2[k] = min(d[k], d[(k + 1) & 15]);
+    mx2[k] = max(d[k], d[(k + 1) & 15]);
+  }
+  int mn4[16], mx4[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    mn4[k] = min(mn2[k], mn2[(k + 2) & 15]);
+    mx4[k] = max(mx2[k], mx2[(k + 2) & 15]);
+  }
+  int best = -1000;
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    int mn = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
+    int mx = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
+    best = max(best, max(mn, -mx));
+  }
+  return best;
+}
+
+static const int FAST_THREADS = 128;
+static const int FAST_MAX_ROUNDS = 64;  // 64 * 128 px >= the largest cell (69 x 69)
+
+__global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbDev P, const uint8_t* __restrict__ img0,
+                                                              long long img_stride, int pitch0,
+                                                              const uint8_t* __restrict__ pyr,
+                                                              uint32_t* __restrict__ cellKeys,
+                                                              int* __restrict__ cellCount) {
+  extern __shared__ uint8_t sm[];
+  __shared__ int s_wcnt[FAST_MAX_ROUNDS * (FAST_THREADS / 32)];
+  __shared__ int s_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cell = blockIdx.x, frame = blockIdx.y;
+  int l = 0;
+  while (l + 1 < P.nlevels && cell >= P.lv[l + 1].cellBase) l++;
+  const LevelDev& L = P.lv[l];
+  const int c = cell - L.cellBase;
+  const int ci = c / L.nCols, cj = c - ci * L.nCols;
+  const int iniY = MIN_BORDER + ci * L.hCell, iniX = MIN_BORDER + cj * L.wCell;
+  int maxY = iniY + L.hCell + 6, maxX = iniX + L.wCell + 6;
+  const bool skip = (iniY >= L.maxBorderY - 3) || (iniX >= L.maxBorderX - 6);
+  maxY = min(maxY, L.maxBorderY);
+  maxX = min(maxX, L.maxBorderX);
+  const int rw = maxX - iniX, rh = maxY - iniY;
+  int* outCount = cellCount + (long long)frame * P.totalCells + cell;
+  if (skip || rw < 7 || rh < 7) {
+    if (tid == 0) *outCount = 0;
+    return;
+  }
+  const uint8_t* src;
+  int pitch;
+  if (l == 0) {
+    src = img0 + (long long)frame * img_stride;
+    pitch = pitch0;
+  } else {
+    src = pyr + (long long)frame * P.pyrStride + L.off;
+    pitch = L.pitch;
+  }
+  uint8_t* roi = sm;                            // [roiRows][roiPitch]
+  uint8_t* sc = sm + P.roiRows * P.roiPitch;    // [(dh+2)][scPitch], zero border
+  const int RP = P.roiPitch, SP = P.scPitch;
+  for (int idx = tid; idx < rw * rh; idx += FAST_THREADS) {
+    const int y = idx / rw, x = idx - y * rw;
+    roi[y * RP + x] = __ldg(src + (long long)(iniY + y) * pitch + iniX + x);
+  }
+  const int dw = rw - 6, dh = rh - 6;
+  for (int idx = tid; idx < (dh + 2) * SP; idx += FAST_THREADS) sc[idx] = 0;
+  __syncthreads();
+
+  const int npx = dw * dh;
+  const int thMin = P.minTh, thIni = P.iniTh;
+  for (int idx = tid; idx < npx; idx += FAST_THREADS) {
+    const int y = idx / dw, x = idx - y * dw;
+    const uint8_t* p = roi + (y + 3) * RP + (x + 3);
+    const int cval = p[0];
+    int v[16];
+    v[0] = p[3 * RP];       v[1] = p[3 * RP + 1];   v[2] = p[2 * RP + 2];   v[3] = p[RP + 3];
+    v[4] = p[3];            v[5] = p[-RP + 3];      v[6] = p[-2 * RP + 2];  v[7] = p[-3 * RP + 1];
+    v[8] = p[-3 * RP];      v[9] = p[-3 * RP - 1];  v[10] = p[-2 * RP - 2]; v[11] = p[-RP - 3];
+    v[12] = p[-3];          v[13] = p[RP - 3];      v[14] = p[2 * RP - 2];  v[15] = p[3 * RP - 1];
+    unsigned bright = 0, dark = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      bright |= (unsigned)(v[k] > cval + thMin) << k;
+      dark |= (unsigned)(v[k] < cval - thMin) << k;
+    }
+    if (has_arc9(bright) || has_arc9(dark)) {
+      int d[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) d[k] = cval - v[k];
+      const int best = fast_best16(d);
+      sc[(y + 1) * SP + (x + 1)] = (uint8_t)(best - 1);  // best > minTh >= 0, best <= 255
+    }
+  }
+  __syncthreads();
+
+  // 3x3 NMS with strict '>' at threshold t: a neighbour counts only if it is itself a corner at t
+  // (score >= t <=> best > t); pixels outside the cell's tested region score 0.
+  auto kept = [&](int idx, int t) -> int {
+    const int y = idx / dw, x = idx - y * dw;
+    const uint8_t* q = sc + (y + 1) * SP + (x + 1);
+    const int s = q[0];
+    if (s < t || s == 0) return 0;
+    int m = max(max(q[-SP - 1], q[-SP]), max(q[-SP + 1], q[-1]));
+    m = max(m, max(max(q[1], q[SP - 1]), max(q[SP], q[SP + 1])));
+    // neighbours below t count as 0; s >= t >= 0 so comparing against m is only wrong when
+    // m < t, in which case the neighbour is ignored: s > 0 suffices.
+    return (m >= t) ? (s > m) : 1;
+  };
+  int any = 0;
+  for (int idx = tid; idx < npx; idx += FAST_THREADS) any |= kept(idx, thIni);
+  any = __syncthreads_or(any);
+  const int thr = any ? thIni : thMin;
+
+  const int rounds = (npx + FAST_THREADS - 1) / FAST_THREADS;
+  unsigned long long mine = 0ull;
+  for (int r = 0; r < rounds; r++) {
+    const int idx = r * FAST_THREADS + tid;
+    const int k = (idx < npx) ? kept(idx, thr) : 0;
+    const unsigned b = __ballot_sync(0xffffffffu, k);
+    if (k) mine |= 1ull << r;
+    if (lane == 0) s_wcnt[r * (FAST_THREADS / 32) + warp] = __popc(b);
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of the (round, warp) counts, in output order
+    const int n = rounds * (FAST_THREADS / 32);
+    int carry = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const int vv = (i < n) ? s_wcnt[i] : 0;
+      int inc = vv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (i < n) s_wcnt[i] = carry + inc - vv;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) s_total = carry;
+  }
+  __syncthreads();
+  uint32_t* out = cellKeys + ((long long)frame * P.totalCells + cell) * P.cellCap;
+  for (int r = 0; r < rounds; r++) {
+    const int k = (int)((mine >> r) & 1ull);
+    const unsigned b = __ballot_sync(0xffffffffu, k);
+    if (k) {
+      const int idx = r * FAST_THREADS + tid;
+      const int y = idx / dw, x = idx - y * dw;
+      const int pos = s_wcnt[r * (FAST_THREADS / 32) + warp] + __popc(b & ((1u << lane) - 1u));
+      const unsigned s = sc[(y + 1) * SP + (x + 1)];
+      const unsigned kx = (unsigned)(x + 3 + cj * L.wCell), ky = (unsigned)(y + 3 + ci * L.hCell);
+      out[pos] = kx | (ky << 12) | (s << 24);
+    }
+  }
+  if (tid == 0) *outCount = s_total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_octree: DistributeOctTree with one warp per (frame, level).  Lane 0 owns the linked list and
+// the sort; all lanes cooperate on the stable 4-way key partition (DivideNode) and on the
+// per-node best-response pick.  Keys live in two ping-pong global buffers; a node's keys are a
+// contiguous range, children reuse the parent's range in the other buffer.
+// ------------------------------------------------------------------------------------------------
+static const int NIL = -1;
+struct OctNode {
+  short ulx, uly, brx, bry;
+  int begin, count;
+  short prev, next;
+  short buf, noMore;
+};
+struct OctState {
+  int head, tail, size, freeHead, nvsz, nprev, nToExpand, heapsorted;
+};
+struct NodeLess {
+  const OctNode* nodes;
+  GFS_HD bool operator()(int af, int as, int bf, int bs) const {
+    if (af < bf) return true;
+    if (af > bf) return false;
+    return nodes[as].ulx < nodes[bs].ulx;
+  }
+};
+
+static const int OCT_WARPS = 4;
+
+__device__ __forceinline__ int oct_alloc(OctState* S, OctNode* nodes) {
+  const int i = S->freeHead;
+  S->freeHead = nodes[i].next;
+  return i;
+}
+__device__ __forceinline__ void oct_free(OctState* S, OctNode* nodes, int i) {
+  nodes[i].next = (short)S->freeHead;
+  S->freeHead = i;
+}
+__device__ __forceinline__ void oct_push_front(OctState* S, OctNode* nodes, int i) {
+  nodes[i].prev = NIL;
+  nodes[i].next = (short)S->head;
+  if (S->head != NIL) nodes[S->head].prev = (short)i;
+  else S->tail = i;
+  S->head = i;
+  S->size++;
+}
+__device__ __forceinline__ void oct_push_back(OctState* S, OctNode* nodes, int i) {
+  nodes[i].next = NIL;
+  nodes[i].prev = (short)S->tail;
+  if (S->tail != NIL) nodes[S->tail].next = (short)i;
+  else S->head = i;
+  S->tail = i;
+  S->size++;
+}
+__device__ __forceinline__ void oct_erase(OctState* S, OctNode* nodes, int i) {
+  const int p = nodes[i].prev, n = nodes[i].next;
+  if (p != NIL) nodes[p].next = (short)n;
+  else S->head = n;
+  if (n != NIL) nodes[n].prev = (short)p;
+  else S->tail = p;
+  S->size--;
+}
+
+// ExtractorNode::DivideNode (:502-550) + the push_front / erase bookkeeping around it (:635-669).
+__device__ void oct_divide(OctState* S, OctNode* nodes, int* vszF, int* vszS, uint32_t* keys0, uint32_t* keys1,
+                           int cur, bool countExpand, int lane) {
+  const OctNode nd = nodes[cur];
+  const int halfX = (nd.brx - nd.ulx + 1) >> 1;  // ceil(float(w)/2), w >= 0
+  const int halfY = (nd.bry - nd.uly + 1) >> 1;
+  const int midX = nd.ulx + halfX, midY = nd.uly + halfY;
+  const uint32_t* src = (nd.buf ? keys1 : keys0) + nd.begin;
+  uint32_t* dst = (nd.buf ? keys0 : keys1) + nd.begin;
+  int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  for (int i = lane; i < nd.count; i += 32) {
+    const uint32_t k = src[i];
+    const int x = k & 0xFFF, y = (k >> 12) & 0xFFF;
+    const int q = (x < midX) ? ((y < midY) ? 0 : 2) : ((y < midY) ? 1 : 3);
+    c0 += (q == 0); c1 += (q == 1); c2 += (q == 2); c3 += (q == 3);
+  }
+  c0 = __reduce_add_sync(0xffffffffu, c0);
+  c1 = __reduce_add_sync(0xffffffffu, c1);
+  c2 = __reduce_add_sync(0xffffffffu, c2);
+  c3 = __reduce_add_sync(0xffffffffu, c3);
+  int b0 = 0, b1 = c0, b2 = c0 + c1, b3 = c0 + c1 + c2;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int s = 0; s < nd.count; s += 32) {
+    const int i = s + lane;
+    const bool valid = i < nd.count;
+    uint32_t k = 0;
+    int q = -1;
+    if (valid) {
+      k = src[i];
+      const int x = k & 0xFFF, y = (k >> 12) & 0xFFF;
+      q = (x < midX) ? ((y < midY) ? 0 : 2) : ((y < midY) ? 1 : 3);
+    }
+    const unsigned m0 = __ballot_sync(0xffffffffu, q == 0);
+    const unsigned m1 = __ballot_sync(0xffffffffu, q == 1);
+    const unsigned m2 = __ballot_sync(0xffffffffu, q == 2);
+    const unsigned m3 = __ballot_sync(0xffffffffu, q == 3);
+    if (q == 0) dst[b0 + __popc(m0 & lt)] = k;
+    else if (q == 1) dst[b1 + __popc(m1 & lt)] = k;
+    else if (q == 2) dst[b2 + __popc(m2 & lt)] = k;
+    else if (q == 3) dst[b3 + __popc(m3 & lt)] = k;
+    b0 += __popc(m0); b1 += __popc(m1); b2 += __popc(m2); b3 += __popc(m3);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const int cnt[4] = {c0, c1, c2, c3};
+    const int beg[4] = {nd.begin, nd.begin + c0, nd.begin + c0 + c1, nd.begin + c0 + c1 + c2};
+    const short ulx[4] = {nd.ulx, (short)midX, nd.ulx, (short)midX};
+    const short uly[4] = {nd.uly, nd.uly, (short)midY, (short)midY};
+    const short brx[4] = {(short)midX, nd.brx, (short)midX, nd.brx};
+    const short bry[4] = {(short)midY, (short)midY, nd.bry, nd.bry};
+    for (int q = 0; q < 4; q++) {
+      if (cnt[q] > 0) {
+        const int i = oct_alloc(S, nodes);
+        nodes[i].ulx = ulx[q]; nodes[i].uly = uly[q]; nodes[i].brx = brx[q]; nodes[i].bry = bry[q];
+        nodes[i].begin = beg[q]; nodes[i].count = cnt[q];
+        nodes[i].buf = (short)(nd.buf ^ 1);
+        nodes[i].noMore = (short)(cnt[q] == 1);
+        oct_push_front(S, nodes, i);
+        if (cnt[q] > 1) {
+          if (countExpand) S->nToExpand++;
+          vszF[S->nvsz] = cnt[q];
+          vszS[S->nvsz] = i;
+          S->nvsz++;
+        }
+      }
+    }
+    oct_erase(S, nodes, cur);
+    oct_free(S, nodes, cur);
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(OCT_WARPS * 32) k_octree(OrbDev P, int batch, const uint32_t* __restrict__ cellKeys,
+                                                           const int* __restrict__ cellCount, uint32_t* keysA,
+                                                           uint32_t* keysB, uint32_t* __restrict__ sel,
+                                                           int* __restrict__ selCount, int* __restrict__ status) {
+  extern __shared__ __align__(16) uint8_t osm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int inst = blockIdx.x * OCT_WARPS + warp;
+  if (inst >= batch * P.nlevels) return;
+  // heavy (fine) levels first so the tail of the grid is made of cheap instances
+  const int l = inst / batch, frame = inst - l * batch;
+  const LevelDev& L = P.lv[l];
+  const int nodeCap = P.nodeCap;
+  const size_t perWarp = sizeof(OctState) + (size_t)nodeCap * (sizeof(OctNode) + 4 * sizeof(int));
+  uint8_t* base = osm + warp * ((perWarp + 15) / 16 * 16);
+  OctState* S = (OctState*)base;
+  OctNode* nodes = (OctNode*)(base + sizeof(OctState));
+  int* vszF = (int*)(nodes + nodeCap);
+  int* vszS = vszF + nodeCap;
+  int* prvF = vszS + nodeCap;
+  int* prvS = prvF + nodeCap;
+
+  uint32_t* keys0 = keysA + (long long)frame * P.keysPerFrame + L.keyOff;
+  uint32_t* keys1 = keysB + (long long)frame * P.keysPerFrame + L.keyOff;
+  const int N = L.nFeat;
+
+  // ---- gather the level's candidates in reference order (cell row-major, in-cell row-major)
+  const int nCells = L.nCols * L.nRows;
+  const int* cc = cellCount + (long long)frame * P.totalCells + L.cellBase;
+  const uint32_t* ck = cellKeys + ((long long)frame * P.totalCells + L.cellBase) * P.cellCap;
+  int ncand = 0;
+  for (int cb = 0; cb < nCells; cb += 32) {
+    const int c = cb + lane;
+    const int n = (c < nCells) ? cc[c] : 0;
+    int inc = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const int excl = ncand + inc - n;
+    const int m = min(32, nCells - cb);
+    for (int j = 0; j < m; j++) {
+      const int nj = __shfl_sync(0xffffffffu, n, j);
+      const int oj = __shfl_sync(0xffffffffu, excl, j);
+      const uint32_t* s = ck + (long long)(cb + j) * P.cellCap;
+      for (int k = lane; k < nj; k += 32) keys1[oj + k] = s[k];
+    }
+    ncand += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  __syncwarp();
+
+  // ---- initial nodes (:573-612)
+  if (lane == 0) {
+    S->head = NIL; S->tail = NIL; S->size = 0; S->nvsz = 0; S->nprev = 0; S->nToExpand = 0; S->heapsorted = 0;
+    for (int i = 0; i < nodeCap; i++) nodes[i].next = (short)((i + 1 < nodeCap) ? i + 1 : NIL);
+    S->freeHead = 0;
+  }
+  __syncwarp();
+  {
+    int off = 0;
+    for (int i = 0; i < L.nIni; i++) {
+      // stable filter keys1 -> keys0 of the keys whose bucket (int)(x / hX) is i
+      int w = off;
+      for (int s = 0; s < ncand; s += 32) {
+        const int k = s + lane;
+        bool take = false;
+        uint32_t key = 0;
+        if (k < ncand) {
+          key = keys1[k];
+          take = (L.nIni == 1) || ((int)__fdiv_rn((float)(key & 0xFFF), L.hX) == i);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        if (take) keys0[w + __popc(m & ((1u << lane) - 1u))] = key;
+        w += __popc(m);
+      }
+      const int cnt = w - off;
+      if (lane == 0 && cnt > 0) {  // empty initial nodes are erased (:605-606)
+        const int n = oct_alloc(S, nodes);
+        nodes[n].ulx = (short)(int)__fmul_rn(L.hX, (float)i);
+        nodes[n].brx = (short)(int)__fmul_rn(L.hX, (float)(i + 1));
+        nodes[n].uly = 0;
+        nodes[n].bry = (short)(L.maxBorderY - MIN_BORDER);
+        nodes[n].begin = off; nodes[n].count = cnt; nodes[n].buf = 0;
+        nodes[n].noMore = (short)(cnt == 1);
+        oct_push_back(S, nodes, n);
+      }
+      off = w;
+    }
+  }
+  __syncwarp();
+
+  // ---- subdivision (:614-747)
+  bool finish = false;
+  while (!finish) {
+    int prevSize = S->size;
+    int cur = S->head;
+    __syncwarp();
+    if (lane == 0) { S->nvsz = 0; S->nToExpand = 0; }
+    __syncwarp();
+    while (cur != NIL) {
+      const int nxt = nodes[cur].next;
+      const bool nm = nodes[cur].noMore != 0;
+      __syncwarp();
+      if (!nm) oct_divide(S, nodes, vszF, vszS, keys0, keys1, cur, true, lane);
+      cur = nxt;
+    }
+    const int size = S->size;
+    if (size >= N || size == prevSize) {
+      finish = true;
+    } else if (size + S->nToExpand * 3 > N) {
+      while (!finish) {
+        prevSize = S->size;
+        __syncwarp();
+        if (lane == 0) {
+          const int n = S->nvsz;
+          for (int i = 0; i < n; i++) { prvF[i] = vszF[i]; prvS[i] = vszS[i]; }
+          S->nprev = n;
+          S->nvsz = 0;
+          GccSort<NodeLess> srt{{prvF, prvS}, NodeLess{nodes}};
+          srt.sort(n, &S->heapsorted);
+        }
+        __syncwarp();
+        const int np = S->nprev;
+        for (int j = np - 1; j >= 0; j--) {
+          oct_divide(S, nodes, vszF, vszS, keys0, keys1, prvS[j], false, lane);
+          if (S->size >= N) break;
+        }
+        if (S->size >= N || S->size == prevSize) finish = true;
+      }
+    }
+  }
+
+  // ---- best response per node, in list order (:749-767); first maximum wins
+  uint32_t* out = sel + (long long)frame * P.selPerFrame + L.selOff;
+  int nout = 0;
+  for (int cur = S->head; cur != NIL; cur = nodes[cur].next) {
+    const OctNode nd = nodes[cur];
+    const uint32_t* src = (nd.buf ? keys1 : keys0) + nd.begin;
+    // order by (score desc, index asc): pack score in the high bits, inverted index below
+    unsigned long long bestv = 0ull;
+    for (int i = lane; i < nd.count; i += 32) {
+      const uint32_t k = src[i];
+      const unsigned long long v = ((unsigned long long)(k >> 24) << 32) | (unsigned)(0x7fffffff - i);
+      bestv = max(bestv, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bestv = max(bestv, __shfl_xor_sync(0xffffffffu, bestv, o));
+    const int bi = 0x7fffffff - (int)(bestv & 0xffffffffu);
+    if (lane == 0 && nout < L.selCap) out[nout] = src[bi];
+    nout++;
+  }
+  if (lane == 0) {
+    selCount[frame * P.nlevels + l] = min(nout, L.selCap);
+    if (nout > L.selCap) atomicOr(status, 1);
+    if (S->heapsorted) atomicOr(status, 2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_blur7: cv::GaussianBlur 7x7 sigma 2 on u8 = fixed-point separable [18,34,48,56,48,34,18]/256.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int p, int n) {
+  if (n == 1) return 0;
+  while (p < 0 || p >= n) p = (p < 0) ? -p : 2 * (n - 1) - p;
+  return p;
+}
+
+static const int BL_TW = 64, BL_TH = 32;
+__global__ void __launch_bounds__(256) k_blur7(OrbDev P, int l, const uint8_t* __restrict__ img0, long long img_stride,
+                                               int pitch0, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
+  __shared__ uint8_t s_in[BL_TH + 6][BL_TW + 8];
+  __shared__ uint16_t s_h[BL_TH + 6][BL_TW];
+  const LevelDev& L = P.lv[l];
+  const int frame = blockIdx.z;
+  const uint8_t* src;
+  int pitch;
+  if (l == 0) { src = img0 + (long long)frame * img_stride; pitch = pitch0; }
+  else { src = pyr + (long long)frame * P.pyrStride + L.off; pitch = L.pitch; }
+  const int x0 = blockIdx.x * BL_TW, y0 = blockIdx.y * BL_TH;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < (BL_TH + 6) * (BL_TW + 6); idx += 256) {
+    const int yy = idx / (BL_TW + 6), xx = idx - yy * (BL_TW + 6);
+    const int gy = reflect101(y0 + yy - 3, L.h), gx = reflect101(x0 + xx - 3, L.w);
+    s_in[yy][xx] = __ldg(src + (long long)gy * pitch + gx);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < (BL_TH + 6) * BL_TW; idx += 256) {
+    const int yy = idx / BL_TW, xx = idx - yy * BL_TW;
+    const uint8_t* p = &s_in[yy][xx];
+    const int acc = 18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3];
+    s_h[yy][xx] = (uint16_t)acc;
+  }
+  __syncthreads();
+  uint8_t* dst = blur + (long long)frame * P.pyrStride + L.off;
+  for (int idx = tid; idx < BL_TH * BL_TW; idx += 256) {
+    const int yy = idx / BL_TW, xx = idx - yy * BL_TW;
+    const int gx = x0 + xx, gy = y0 + yy;
+    if (gx < L.w && gy < L.h) {
+      const unsigned acc = 18u * (s_h[yy][xx] + s_h[yy + 6][xx]) + 34u * (s_h[yy + 1][xx] + s_h[yy + 5][xx]) +
+                           48u * (s_h[yy + 2][xx] + s_h[yy + 4][xx]) + 56u * s_h[yy + 3][xx];
+      dst[(long long)gy * L.pitch + gx] = (uint8_t)((acc + 32768u) >> 16);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_orient_desc: one warp per selected keypoint slot.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_atan2_deg(const OrbDev& P, float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a;
+  if (ax >= ay) {
+    const float c = __fdiv_rn(ay, __fadd_rn(ax, (float)DBL_EPSILON));
+    const float c2 = __fmul_rn(c, c);
+    float t = __fadd_rn(__fmul_rn(P.p7, c2), P.p5);
+    t = __fadd_rn(__fmul_rn(t, c2), P.p3);
+    t = __fadd_rn(__fmul_rn(t, c2), P.p1);
+    a = __fmul_rn(t, c);
+  } else {
+    const float c = __fdiv_rn(ax, __fadd_rn(ay, (float)DBL_EPSILON));
+    const float c2 = __fmul_rn(c, c);
+    float t = __fadd_rn(__fmul_rn(P.p7, c2), P.p5);
+    t = __fadd_rn(__fmul_rn(t, c2), P.p3);
+    t = __fadd_rn(__fmul_rn(t, c2), P.p1);
+    a = __fsub_rn(90.f, __fmul_rn(t, c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+static const int OD_WARPS = 8;
+__global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(OrbDev P, const uint8_t* __restrict__ img0,
+                                                               long long img_stride, int pitch0,
+                                                               const uint8_t* __restrict__ pyr,
+                                                               const uint8_t* __restrict__ blur,
+                                                               const uint32_t* __restrict__ sel,
+                                                               const int* __restrict__ selCount,
+                                                               GfsKeyPoint* __restrict__ out_kp,
+                                                               uint8_t* __restrict__ out_desc, int* __restrict__ out_n,
+                                                               int* __restrict__ out_mono) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot = blockIdx.x * OD_WARPS + warp;
+  const int frame = blockIdx.y;
+  if (slot >= P.selPerFrame) return;
+  int l = 0;
+  while (l + 1 < P.nlevels && slot >= P.lv[l + 1].selOff) l++;
+  const LevelDev& L = P.lv[l];
+  const int i = slot - L.selOff;
+  const int* sc = selCount + frame * P.nlevels;
+  int base = 0, total = 0;
+  for (int k = 0; k < P.nlevels; k++) {
+    const int c = sc[k];
+    if (k < l) base += c;
+    total += c;
+  }
+  if (slot == 0 && lane == 0) { out_n[frame] = total; out_mono[frame] = total; }
+  if (i >= sc[l]) return;
+  const uint32_t key = sel[(long long)frame * P.selPerFrame + slot];
+  const int cx = (int)(key & 0xFFF) + MIN_BORDER, cy = (int)((key >> 12) & 0xFFF) + MIN_BORDER;
+  const int score = (int)(key >> 24);
+  const uint8_t* src;
+  int pitch;
+  if (l == 0) { src = img0 + (long long)frame * img_stride; pitch = pitch0; }
+  else { src = pyr + (long long)frame * P.pyrStride + L.off; pitch = L.pitch; }
+
+  // IC_Angle: integer moments over the radius-15 disc, one row per lane
+  int m10 = 0, m01 = 0;
+  if (lane < 2 * HALF_PATCH + 1) {
+    const int v = lane - HALF_PATCH;
+    const int d = P.umax[v < 0 ? -v : v];
+    const uint8_t* row = src + (long long)(cy + v) * pitch + cx;
+    int rs = 0;
+    for (int u = -d; u <= d; u++) {
+      const int val = __ldg(row + u);
+      m10 += u * val;
+      rs += val;
+    }
+    m01 = v * rs;
+  }
+  m10 = __reduce_add_sync(0xffffffffu, m10);
+  m01 = __reduce_add_sync(0xffffffffu, m01);
+  const float angle = fast_atan2_deg(P, (float)m01, (float)m10);
+
+  // rBRIEF: lane b computes descriptor byte b (tests 8b .. 8b+7)
+  const float ar = __fmul_rn(angle, P.factorPI);
+  double sd, cd;
+  sincos((double)ar, &sd, &cd);
+  const float a = (float)cd, b = (float)sd;
+  const uint8_t* bl = blur + (long long)frame * P.pyrStride + L.off + (long long)cy * L.pitch + cx;
+  const signed char* pat = c_pattern + lane * 32;
+  int val = 0;
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    int s[2];
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      const float px = (float)pat[4 * t + 2 * p], py = (float)pat[4 * t + 2 * p + 1];
+      const float r1 = __fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a));
+      const float r2 = __fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b));
+      const int ry = (int)roundf(r1), rx = (int)roundf(r2);
+      s[p] = __ldg(bl + ry * L.pitch + rx);
+    }
+    val |= (s[0] < s[1]) << t;
+  }
+  const long long o = (long long)frame * P.kpStride + base + i;
+  out_desc[o * 32 + lane] = (uint8_t)val;
+  if (lane == 0) {
+    GfsKeyPoint kp;
+    kp.x = (l == 0) ? (float)cx : __fmul_rn((float)cx, L.scale);
+    kp.y = (l == 0) ? (float)cy : __fmul_rn((float)cy, L.scale);
+    kp.size = (float)L.patchSize;
+    kp.angle = angle;
+    kp.response = (float)score;
+    kp.octave = l;
+    out_kp[o] = kp;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_pack_lapping: mono keypoints from the front, lapping-area keypoints from the back (:1208-1217).
+// One CTA per frame; in-place via a copy in global scratch.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_pack_lapping(int kpStride, int lap0, int lap1, const GfsKeyPoint* __restrict__ tkp,
+                                                       const uint8_t* __restrict__ tdesc, GfsKeyPoint* __restrict__ out_kp,
+                                                       uint8_t* __restrict__ out_desc, const int* __restrict__ out_n,
+                                                       int* __restrict__ out_mono) {
+  __shared__ int s_w[32];
+  __shared__ int s_carry;
+  const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = out_n[frame];
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int b = 0; b < n; b += 1024) {
+    const int i = b + tid;
+    GfsKeyPoint kp;
+    int lapf = 0;
+    if (i < n) {
+      kp = tkp[(long long)frame * kpStride + i];
+      lapf = (kp.x >= (float)lap0 && kp.x <= (float)lap1);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, lapf);
+    if (lane == 0) s_w[warp] = __popc(m);
+    __syncthreads();
+    int before = s_carry;
+    for (int w2 = 0; w2 < warp; w2++) before += s_w[w2];
+    before += __popc(m & ((1u << lane) - 1u));
+    if (i < n) {
+      const int dstI = lapf ? (n - 1 - before) : (i - before);
+      out_kp[(long long)frame * kpStride + dstI] = kp;
+      const uint4* s4 = (const uint4*)(tdesc + ((long long)frame * kpStride + i) * 32);
+      uint4* d4 = (uint4*)(out_desc + ((long long)frame * kpStride + dstI) * 32);
+      d4[0] = s4[0];
+      d4[1] = s4[1];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w2 = 0; w2 < 32; w2++) t += s_w[w2];
+      s_carry += t;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) out_mono[frame] = n - s_carry;
+}
+
+}  // namespace gfs
+
+// ================================================================================================
+// Host side
+// ================================================================================================
+using namespace gfs;
+
+struct GfsOrb {
+  int nfeatures, nlevels, iniTh, minTh;
+  double scaleFactor;
+  float sf[MAX_LEVELS], isf[MAX_LEVELS];
+  int nPerLevel[MAX_LEVELS];
+  int maxW, maxH, maxBatch;
+  int geomW = 0, geomH = 0;
+  OrbDev dev;
+  DevBuf d_pyr, d_blur, d_cellKeys, d_cellCount, d_keysA, d_keysB, d_sel, d_selCount, d_tabs, d_status;
+  DevBuf d_in, d_okp, d_odesc, d_on, d_omono, d_tkp, d_tdesc;
+  PinnedBuf h_in, h_okp, h_odesc, h_on;
+  size_t fastSmem = 0, octSmem = 0;
+  // last batch (debug hooks)
+  const uint8_t* lastImgs = nullptr;
+  long long lastStride = 0;
+  int lastPitch = 0, lastBatch = 0;
+};
+
+static inline int cv_round_f(double v) { return (int)std::nearbyint(v); }
+
+static void area_tab(int ssize, int dsize, std::vector<AreaEntry>& out) {
+  // cv::resize INTER_AREA table (oracle/orb_oracle.cpp area_tab)
+  const double scale = 1.0 / ((double)dsize / (double)ssize);
+  for (int dx = 0; dx < dsize; dx++) {
+    AreaEntry e{};
+    e.s0 = -1;
+    const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+    const double cw = std::min(scale, ssize - fsx1);
+    int sx1 = (int)std::ceil(fsx1), sx2 = (int)std::floor(fsx2);
+    sx2 = std::min(sx2, ssize - 1);
+    sx1 = std::min(sx1, sx2);
+    auto push = [&](int s, float a) {
+      if (e.n == 0) e.s0 = s;
+      if (e.n < 4) e.a[e.n] = a;
+      e.n++;
+    };
+    if (sx1 - fsx1 > 1e-3) push(sx1 - 1, (float)((sx1 - fsx1) / cw));
+    for (int sx = sx1; sx < sx2; sx++) push(sx, (float)(1.0 / cw));
+    if (fsx2 - sx2 > 1e-3) push(sx2, (float)(std::min(std::min(fsx2 - sx2, 1.), cw) / cw));
+    out.push_back(e);
+  }
+}
+
+static int orb_set_geometry(GfsOrb* h, int w, int ht) {
+  if (h->geomW == w && h->geomH == ht) return GFS_OK;
+  OrbDev& D = h->dev;
+  D.nlevels = h->nlevels;
+  D.iniTh = h->iniTh;
+  D.minTh = h->minTh;
+  std::vector<AreaEntry> tabs;
+  long long off = 0;
+  int cellBase = 0, keyOff = 0, selOff = 0, cellCap = 1, nodeCap = 8, maxWC = 0, maxHC = 0;
+  for (int l = 0; l < h->nlevels; l++) {
+    LevelDev& L = D.lv[l];
+    L.w = cv_round_f((float)w * h->isf[l]);
+    L.h = cv_round_f((float)ht * h->isf[l]);
+    L.pitch = (int)align_up(L.w, 16);
+    L.off = off;
+    off += (long long)L.pitch * L.h;
+    off = (long long)align_up((size_t)off, 256);
+    L.maxBorderX = L.w - EDGE_THRESHOLD + 3;
+    L.maxBorderY = L.h - EDGE_THRESHOLD + 3;
+    const float width = (float)(L.maxBorderX - MIN_BORDER), height = (float)(L.maxBorderY - MIN_BORDER);
+    L.nCols = (int)(width / 35.f);
+    L.nRows = (int)(height / 35.f);
+    if (L.nCols < 1 || L.nRows < 1) {
+      set_error("image %dx%d too small: pyramid level %d (%dx%d) has no 35-px FAST cell", w, ht, l, L.w, L.h);
+      return GFS_ERR_INVALID;
+    }
+    L.wCell = (int)std::ceil(width / L.nCols);
+    L.hCell = (int)std::ceil(height / L.nRows);
+    if (L.w > 4095 || L.h > 4095) {
+      set_error("level %d size %dx%d exceeds the 12-bit key range", l, L.w, L.h);
+      return GFS_ERR_INVALID;
+    }
+    maxWC = std::max(maxWC, L.wCell);
+    maxHC = std::max(maxHC, L.hCell);
+    L.cellBase = cellBase;
+    cellBase += L.nCols * L.nRows;
+    cellCap = std::max(cellCap, ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2));
+    L.nFeat = h->nPerLevel[l];
+    L.nIni = (int)std::round((float)(L.maxBorderX - MIN_BORDER) / (L.maxBorderY - MIN_BORDER));
+    if (L.nIni == 0) L.nIni = 1;
+    L.hX = (float)(L.maxBorderX - MIN_BORDER) / L.nIni;
+    L.selOff = selOff;
+    L.selCap = std::max(L.nFeat + 3, 4 * L.nIni);
+    selOff += L.selCap;
+    nodeCap = std::max(nodeCap, L.selCap + 8);
+    L.scale = h->sf[l];
+    L.patchSize = (int)(PATCH_SIZE * h->sf[l]);
+    if (l > 0) {
+      const LevelDev& Pv = D.lv[l - 1];
+      L.tabX = (int)tabs.size();
+      area_tab(Pv.w, L.w, tabs);
+      L.tabY = (int)tabs.size();
+      area_tab(Pv.h, L.h, tabs);
+    } else {
+      L.tabX = L.tabY = 0;
+    }
+  }
+  for (const AreaEntry& e : tabs)
+    if (e.n > 4 || e.n < 1) {
+      set_error("scale factor outside the supported (1, 3) range");
+      return GFS_ERR_INVALID;
+    }
+  for (int l = 0; l < h->nlevels; l++) {
+    LevelDev& L = D.lv[l];
+    L.keyOff = keyOff;
+    keyOff += L.nCols * L.nRows * cellCap;
+  }
+  D.pyrStride = off;
+  D.cellCap = cellCap;
+  D.totalCells = cellBase;
+  D.keysPerFrame = keyOff;
+  D.selPerFrame = selOff;
+  D.nodeCap = nodeCap;
+  D.roiPitch = (int)align_up(maxWC + 6, 4);
+  D.roiRows = maxHC + 6;
+  D.scPitch = (int)align_up(maxWC + 2, 4);
+  if (selOff > D.kpStride) {
+    set_error("internal: selected-slot count %d exceeds keypoint stride %d", selOff, D.kpStride);
+    return GFS_ERR_INVALID;
+  }
+  if (nodeCap > 32000) {
+    set_error("nfeatures too large for the quadtree node pool");
+    return GFS_ERR_CAPACITY;
+  }
+  const float scale = (float)(180.0 / M_PI);
+  D.p1 = 0.9997878412794807f * scale;
+  D.p3 = -0.3258083974640975f * scale;
+  D.p5 = 0.1555786518463281f * scale;
+  D.p7 = -0.04432655554792128f * scale;
+  D.factorPI = (float)(M_PI / 180.f);
+  {  // umax (ctor :464-478)
+    int v, v0, vmax = (int)std::floor(HALF_PATCH * std::sqrt(2.f) / 2 + 1);
+    int vmin = (int)std::ceil(HALF_PATCH * std::sqrt(2.f) / 2);
+    const double hp2 = HALF_PATCH * HALF_PATCH;
+    for (v = 0; v <= vmax; ++v) D.umax[v] = cv_round_f(std::sqrt(hp2 - v * v));
+    for (v = HALF_PATCH, v0 = 0; v >= vmin; --v) {
+      while (D.umax[v0] == D.umax[v0 + 1]) ++v0;
+      D.umax[v] = v0;
+      ++v0;
+    }
+  }
+  const size_t B = (size_t)h->maxBatch;
+  int rc;
+  if ((rc = h->d_pyr.reserve(B * D.pyrStride))) return rc;
+  if ((rc = h->d_blur.reserve(B * D.pyrStride))) return rc;
+  if ((rc = h->d_cellKeys.reserve(B * D.totalCells * (size_t)D.cellCap * 4))) return rc;
+  if ((rc = h->d_cellCount.reserve(B * D.totalCells * 4))) return rc;
+  if ((rc = h->d_keysA.reserve(B * (size_t)D.keysPerFrame * 4))) return rc;
+  if ((rc = h->d_keysB.reserve(B * (size_t)D.keysPerFrame * 4))) return rc;
+  if ((rc = h->d_sel.reserve(B * (size_t)D.selPerFrame * 4))) return rc;
+  if ((rc = h->d_selCount.reserve(B * MAX_LEVELS * 4))) return rc;
+  if ((rc = h->d_status.reserve(16))) return rc;
+  if ((rc = h->d_tabs.reserve(std::max<size_t>(tabs.size(), 1) * sizeof(AreaEntry)))) return rc;
+  if (!tabs.empty()) GFS_CUDA(cudaMemcpy(h->d_tabs.p, tabs.data(), tabs.size() * sizeof(AreaEntry), cudaMemcpyHostToDevice));
+  GFS_CUDA(cudaMemset(h->d_status.p, 0, 16));
+  GFS_CUDA(cudaMemcpyToSymbol(c_pattern, GFS_ORB_PATTERN, 1024));
+  h->fastSmem = (size_t)D.roiRows * D.roiPitch + (size_t)(maxHC + 2) * D.scPitch;
+  const size_t perWarp = align_up(sizeof(OctState) + (size_t)nodeCap * (sizeof(OctNode) + 4 * sizeof(int)), 16);
+  h->octSmem = perWarp * OCT_WARPS;
+  if (h->octSmem > 200 * 1024) {
+    set_error("nfeatures too large: quadtree needs %zu B shared memory", h->octSmem);
+    return GFS_ERR_CAPACITY;
+  }
+  GFS_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->octSmem));
+  GFS_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem));
+  h->geomW = w;
+  h->geomH = ht;
+  return GFS_OK;
+}
+
+extern "C" {
+
+int gfs_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, int max_w,
+                   int max_h, int max_batch, GfsOrb** out) {
+  GFS_REQUIRE(out, GFS_ERR_INVALID, "out is null");
+  *out = nullptr;
+  GFS_REQUIRE(nfeatures > 0 && nlevels >= 1 && nlevels <= MAX_LEVELS, GFS_ERR_INVALID, "bad nfeatures/nlevels");
+  GFS_REQUIRE(scale_factor > 1.0f && scale_factor < 3.0f, GFS_ERR_INVALID, "scale_factor must be in (1,3)");
+  GFS_REQUIRE(ini_th_fast >= 0 && ini_th_fast <= 255 && min_th_fast >= 0 && min_th_fast <= 255, GFS_ERR_INVALID,
+              "FAST thresholds must be in [0,255]");
+  GFS_REQUIRE(max_w > 0 && max_h > 0 && max_batch > 0, GFS_ERR_INVALID, "bad workspace size");
+  int rc = gfs_device_check();
+  if (rc) return rc;
+  GfsOrb* h = new GfsOrb();
+  h->nfeatures = nfeatures;
+  h->nlevels = nlevels;
+  h->iniTh = ini_th_fast;
+  h->minTh = min_th_fast;
+  h->scaleFactor = scale_factor;  // float -> double member, as the reference (ORBextractor.h:103)
+  h->maxW = max_w;
+  h->maxH = max_h;
+  h->maxBatch = max_batch;
+  // scale tables and per-level budgets, ctor :428-458
+  h->sf[0] = 1.0f;
+  for (int i = 1; i < nlevels; i++) h->sf[i] = (float)(h->sf[i - 1] * h->scaleFactor);
+  for (int i = 0; i < nlevels; i++) h->isf[i] = 1.0f / h->sf[i];
+  const float factor = (float)(1.0f / h->scaleFactor);
+  float nDesired = nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nlevels));
+  int sum = 0;
+  for (int l = 0; l < nlevels - 1; l++) {
+    h->nPerLevel[l] = cv_round_f(nDesired);
+    sum += h->nPerLevel[l];
+    nDesired *= factor;
+  }
+  h->nPerLevel[nlevels - 1] = std::max(nfeatures - sum, 0);
+  int total = 0;
+  for (int l = 0; l < nlevels; l++) total += std::max(h->nPerLevel[l] + 3, 16);
+  memset(&h->dev, 0, sizeof(h->dev));
+  h->dev.kpStride = (int)align_up((size_t)total, 32);
+  *out = h;
+  return GFS_OK;
+}
+
+int gfs_orb_destroy(GfsOrb* h) {
+  if (!h) return GFS_OK;
+  DevBuf* d[] = {&h->d_pyr, &h->d_blur, &h->d_cellKeys, &h->d_cellCount, &h->d_keysA, &h->d_keysB, &h->d_sel,
+                 &h->d_selCount, &h->d_tabs, &h->d_status, &h->d_in, &h->d_okp, &h->d_odesc, &h->d_on, &h->d_omono,
+                 &h->d_tkp, &h->d_tdesc};
+  for (DevBuf* b : d) b->release();
+  h->h_in.release(); h->h_okp.release(); h->h_odesc.release(); h->h_on.release();
+  delete h;
+  return GFS_OK;
+}
+
+int gfs_orb_max_keypoints(const GfsOrb* h) { return h ? h->dev.kpStride : GFS_ERR_INVALID; }
+
+int gfs_orb_tables(const GfsOrb* h, float* scale_factors, int* features_per_level) {
+  GFS_REQUIRE(h, GFS_ERR_INVALID, "null handle");
+  for (int i = 0; i < h->nlevels; i++) {
+    if (scale_factors) scale_factors[i] = h->sf[i];
+    if (features_per_level) features_per_level[i] = h->nPerLevel[i];
+  }
+  return GFS_OK;
+}
+
+int gfs_orb_level_size(const GfsOrb* h, int w, int h_img, int level, int* lw, int* lh) {
+  GFS_REQUIRE(h && level >= 0 && level < h->nlevels, GFS_ERR_INVALID, "bad handle/level");
+  if (lw) *lw = cv_round_f((float)w * h->isf[level]);
+  if (lh) *lh = cv_round_f((float)h_img * h->isf[level]);
+  return GFS_OK;
+}
+
+int gfs_orb_launches_per_call(const GfsOrb* h, int lap0, int lap1) {
+  if (!h) return GFS_ERR_INVALID;
+  // pyramid (nlevels-1) + fast + octree + blur (nlevels) + orient/desc (+ pack)
+  return (h->nlevels - 1) + 1 + 1 + h->nlevels + 1 + ((lap0 != 0 || lap1 != 0) ? 1 : 0);
+}
+
+static int orb_run_chunk(GfsOrb* h, cudaStream_t st, const uint8_t* d_imgs, int batch, int w, int ht, int pitch,
+                         size_t img_stride, int lap0, int lap1, GfsKeyPoint* d_kp, uint8_t* d_desc, int* d_n,
+                         int* d_mono) {
+  const OrbDev& D = h->dev;
+  uint8_t* pyr = (uint8_t*)h->d_pyr.p;
+  uint8_t* blur = (uint8_t*)h->d_blur.p;
+  for (int l = 1; l < h->nlevels; l++) {
+    const LevelDev& L = D.lv[l];
+    dim3 blk(32, 8), grd(div_up(L.w, 32), div_up(L.h, 8), batch);
+    const uint8_t* src = (l == 1) ? d_imgs : pyr + D.lv[l - 1].off;
+    const long long ss = (l == 1) ? (long long)img_stride : D.pyrStride;
+    const int sp = (l == 1) ? pitch : D.lv[l - 1].pitch;
+    k_pyr_level<<<grd, blk, 0, st>>>(D, l, src, ss, sp, pyr, (const AreaEntry*)h->d_tabs.p);
+  }
+  k_fast_cells<<<dim3(D.totalCells, batch), FAST_THREADS, h->fastSmem, st>>>(
+      D, d_imgs, (long long)img_stride, pitch, pyr, (uint32_t*)h->d_cellKeys.p, (int*)h->d_cellCount.p);
+  k_octree<<<div_up(batch * h->nlevels, OCT_WARPS), OCT_WARPS * 32, h->octSmem, st>>>(
+      D, batch, (const uint32_t*)h->d_cellKeys.p, (const int*)h->d_cellCount.p, (uint32_t*)h->d_keysA.p,
+      (uint32_t*)h->d_keysB.p, (uint32_t*)h->d_sel.p, (int*)h->d_selCount.p, (int*)h->d_status.p);
+  for (int l = 0; l < h->nlevels; l++) {
+    const LevelDev& L = D.lv[l];
+    k_blur7<<<dim3(div_up(L.w, BL_TW), div_up(L.h, BL_TH), batch), 256, 0, st>>>(D, l, d_imgs, (long long)img_stride,
+                                                                                pitch, pyr, blur);
+  }
+  const bool lapping = (lap0 != 0 || lap1 != 0);
+  GfsKeyPoint* kpDst = d_kp;
+  uint8_t* descDst = d_desc;
+  if (lapping) {
+    int rc;
+    if ((rc = h->d_tkp.reserve((size_t)h->maxBatch * D.kpStride * sizeof(GfsKeyPoint)))) return rc;
+    if ((rc = h->d_tdesc.reserve((size_t)h->maxBatch * D.kpStride * 32))) return rc;
+    kpDst = (GfsKeyPoint*)h->d_tkp.p;
+    descDst = (uint8_t*)h->d_tdesc.p;
+  }
+  k_orient_desc<<<dim3(div_up(D.selPerFrame, OD_WARPS), batch), OD_WARPS * 32, 0, st>>>(
+      D, d_imgs, (long long)img_stride, pitch, pyr, blur, (const uint32_t*)h->d_sel.p, (const int*)h->d_selCount.p,
+      kpDst, descDst, d_n, d_mono);
+  if (lapping)
+    k_pack_lapping<<<batch, 1024, 0, st>>>(D.kpStride, lap0, lap1, kpDst, descDst, d_kp, d_desc, d_n, d_mono);
+  GFS_CUDA(cudaGetLastError());
+  h->lastImgs = d_imgs;
+  h->lastStride = (long long)img_stride;
+  h->lastPitch = pitch;
+  h->lastBatch = batch;
+  return GFS_OK;
+}
+
+int gfs_orb_extract_batch_device(GfsOrb* h, void* stream, const uint8_t* d_imgs, int batch, int w, int h_img,
+                                 int pitch, size_t img_stride, int lap0, int lap1, GfsKeyPoint* d_out_kp,
+                                 uint8_t* d_out_desc, int* d_out_n, int* d_out_mono) {
+  GFS_REQUIRE(h, GFS_ERR_INVALID, "null handle");
+  GFS_REQUIRE(d_imgs && w > 0 && h_img > 0, GFS_ERR_EMPTY, "empty image");
+  GFS_REQUIRE(batch > 0 && pitch >= w, GFS_ERR_INVALID, "bad batch/pitch");
+  GFS_REQUIRE(d_out_kp && d_out_desc && d_out_n && d_out_mono, GFS_ERR_INVALID, "null output");
+  GFS_REQUIRE(w <= h->maxW && h_img <= h->maxH, GFS_ERR_CAPACITY, "image larger than the handle's max_w/max_h");
+  int rc = orb_set_geometry(h, w, h_img);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ks = h->dev.kpStride;
+  for (int b0 = 0; b0 < batch; b0 += h->maxBatch) {
+    const int nb = std::min(h->maxBatch, batch - b0);
+    rc = orb_run_chunk(h, st, d_imgs + (size_t)b0 * img_stride, nb, w, h_img, pitch, img_stride, lap0, lap1,
+                       d_out_kp + (size_t)b0 * ks, d_out_desc + (size_t)b0 * ks * 32, d_out_n + b0, d_out_mono + b0);
+    if (rc) return rc;
+  }
+  return GFS_OK;
+}
+
+int gfs_orb_extract_batch(GfsOrb* h, void* stream, const uint8_t* imgs, int batch, int w, int h_img, int pitch,
+                          size_t img_stride, int lap0, int lap1, GfsKeyPoint* out_kp, uint8_t* out_desc, int* out_n,
+                          int* out_mono) {
+  GFS_REQUIRE(h, GFS_ERR_INVALID, "null handle");
+  GFS_REQUIRE(imgs && w > 0 && h_img > 0, GFS_ERR_EMPTY, "empty image");
+  GFS_REQUIRE(batch > 0 && pitch >= w, GFS_ERR_INVALID, "bad batch/pitch");
+  GFS_REQUIRE(out_kp && out_desc && out_n && out_mono, GFS_ERR_INVALID, "null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ks = h->dev.kpStride;
+  const int cb = std::min(batch, h->maxBatch);
+  const size_t dpitch = align_up((size_t)w, 16), dstride = dpitch * h_img;
+  int rc;
+  if ((rc = h->d_in.reserve(cb * dstride))) return rc;
+  if ((rc = h->d_okp.reserve((size_t)cb * ks * sizeof(GfsKeyPoint)))) return rc;
+  if ((rc = h->d_odesc.reserve((size_t)cb * ks * 32))) return rc;
+  if ((rc = h->d_on.reserve((size_t)cb * 2 * sizeof(int)))) return rc;
+  const bool pin_in = is_pinned_host(imgs);
+  const bool pin_out = is_pinned_host(out_kp) && is_pinned_host(out_desc) && is_pinned_host(out_n) && is_pinned_host(out_mono);
+  if (!pin_in && (rc = h->h_in.reserve(cb * (size_t)w * h_img))) return rc;
+  if (!pin_out) {
+    if ((rc = h->h_okp.reserve((size_t)cb * ks * sizeof(GfsKeyPoint)))) return rc;
+    if ((rc = h->h_odesc.reserve((size_t)cb * ks * 32))) return rc;
+    if ((rc = h->h_on.reserve((size_t)cb * 2 * sizeof(int)))) return rc;
+  }
+  for (int b0 = 0; b0 < batch; b0 += cb) {
+    const int nb = std::min(cb, batch - b0);
+    const uint8_t* src = imgs + (size_t)b0 * img_stride;
+    if (pin_in) {
+      if (img_stride == (size_t)pitch * h_img) {
+        GFS_CUDA(cudaMemcpy2DAsync(h->d_in.p, dpitch, src, pitch, w, (size_t)h_img * nb, cudaMemcpyHostToDevice, st));
+      } else {
+        for (int i = 0; i < nb; i++)
+          GFS_CUDA(cudaMemcpy2DAsync((uint8_t*)h->d_in.p + i * dstride, dpitch, src + i * img_stride, pitch, w, h_img,
+                                     cudaMemcpyHostToDevice, st));
+      }
+    } else {
+      // a previous chunk's H2D from the staging buffer must have completed before it is reused
+      GFS_CUDA(cudaStreamSynchronize(st));
+      uint8_t* stg = (uint8_t*)h->h_in.p;
+      for (int i = 0; i < nb; i++)
+        for (int y = 0; y < h_img; y++) memcpy(stg + ((size_t)i * h_img + y) * w, src + i * img_stride + (size_t)y * pitch, w);
+      GFS_CUDA(cudaMemcpy2DAsync(h->d_in.p, dpitch, stg, w, w, (size_t)h_img * nb, cudaMemcpyHostToDevice, st));
+    }
+    int* d_n = (int*)h->d_on.p;
+    int* d_mono = d_n + cb;
+    rc = gfs_orb_extract_batch_device(h, stream, (const uint8_t*)h->d_in.p, nb, w, h_img, (int)dpitch, dstride, lap0,
+                                      lap1, (GfsKeyPoint*)h->d_okp.p, (uint8_t*)h->d_odesc.p, d_n, d_mono);
+    if (rc) return rc;
+    GfsKeyPoint* okp = pin_out ? out_kp + (size_t)b0 * ks : (GfsKeyPoint*)h->h_okp.p;
+    uint8_t* odesc = pin_out ? out_desc + (size_t)b0 * ks * 32 : (uint8_t*)h->h_odesc.p;
+    int* on = pin_out ? out_n + b0 : (int*)h->h_on.p;
+    int* omono = pin_out ? out_mono + b0 : (int*)h->h_on.p + cb;
+    GFS_CUDA(cudaMemcpyAsync(okp, h->d_okp.p, (size_t)nb * ks * sizeof(GfsKeyPoint), cudaMemcpyDeviceToHost, st));
+    GFS_CUDA(cudaMemcpyAsync(odesc, h->d_odesc.p, (size_t)nb * ks * 32, cudaMemcpyDeviceToHost, st));
+    GFS_CUDA(cudaMemcpyAsync(on, d_n, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+    GFS_CUDA(cudaMemcpyAsync(omono, d_mono, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+    GFS_CUDA(cudaStreamSynchronize(st));
+    if (!pin_out) {
+      memcpy(out_kp + (size_t)b0 * ks, okp, (size_t)nb * ks * sizeof(GfsKeyPoint));
+      memcpy(out_desc + (size_t)b0 * ks * 32, odesc, (size_t)nb * ks * 32);
+      memcpy(out_n + b0, on, (size_t)nb * sizeof(int));
+      memcpy(out_mono + b0, omono, (size_t)nb * sizeof(int));
+    }
+  }
+  int status = 0;
+  GFS_CUDA(cudaMemcpy(&status, h->d_status.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (status & 1) {
+    set_error("quadtree produced more keypoints than the per-level slot capacity");
+    return GFS_ERR_CAPACITY;
+  }
+  return GFS_OK;
+}
+
+int gfs_orb_extract(GfsOrb* h, void* stream, const uint8_t* img, int w, int h_img, int pitch, int lap0, int lap1,
+                    GfsKeyPoint* out_kp, uint8_t* out_desc, int* out_n, int* out_mono) {
+  if (!img || w <= 0 || h_img <= 0) {
+    if (out_n) *out_n = 0;
+    if (out_mono) *out_mono = -1;
+    set_error("empty image");
+    return GFS_ERR_EMPTY;
+  }
+  return gfs_orb_extract_batch(h, stream, img, 1, w, h_img, pitch, (size_t)pitch * h_img, lap0, lap1, out_kp, out_desc,
+                               out_n, out_mono);
+}
+
+int gfs_orb_get_level(GfsOrb* h, void* stream, int frame, int level, int blurred, uint8_t* out) {
+  GFS_REQUIRE(h && out && h->geomW > 0, GFS_ERR_INVALID, "no batch processed yet");
+  GFS_REQUIRE(frame >= 0 && frame < h->lastBatch && level >= 0 && level < h->nlevels, GFS_ERR_INVALID, "bad frame/level");
+  cudaStream_t st = (cudaStream_t)stream;
+  const LevelDev& L = h->dev.lv[level];
+  const uint8_t* src;
+  size_t sp;
+  if (blurred) {
+    src = (const uint8_t*)h->d_blur.p + (size_t)frame * h->dev.pyrStride + L.off;
+    sp = L.pitch;
+  } else if (level == 0) {
+    src = h->lastImgs + (size_t)frame * h->lastStride;
+    sp = h->lastPitch;
+  } else {
+    src = (const uint8_t*)h->d_pyr.p + (size_t)frame * h->dev.pyrStride + L.off;
+    sp = L.pitch;
+  }
+  GFS_CUDA(cudaMemcpy2DAsync(out, L.w, src, sp, L.w, L.h, cudaMemcpyDeviceToHost, st));
+  GFS_CUDA(cudaStreamSynchronize(st));
+  return GFS_OK;
+}
+
+int gfs_orb_get_candidates(GfsOrb* h, void* stream, int frame, int level, float* out_xyr, int cap, int* n) {
+  GFS_REQUIRE(h && n && h->geomW > 0, GFS_ERR_INVALID, "no batch processed yet");
+  GFS_REQUIRE(frame >= 0 && frame < h->lastBatch && level >= 0 && level < h->nlevels, GFS_ERR_INVALID, "bad frame/level");
+  cudaStream_t st = (cudaStream_t)stream;
+  const OrbDev& D = h->dev;
+  const LevelDev& L = D.lv[level];
+  const int nc = L.nCols * L.nRows;
+  std::vector<int> cnt(nc);
+  std::vector<uint32_t> keys((size_t)nc * D.cellCap);
+  GFS_CUDA(cudaStreamSynchronize(st));
+  GFS_CUDA(cudaMemcpy(cnt.data(), (int*)h->d_cellCount.p + (size_t)frame * D.totalCells + L.cellBase, nc * sizeof(int),
+                      cudaMemcpyDeviceToHost));
+  GFS_CUDA(cudaMemcpy(keys.data(), (uint32_t*)h->d_cellKeys.p + ((size_t)frame * D.totalCells + L.cellBase) * D.cellCap,
+                      keys.size() * 4, cudaMemcpyDeviceToHost));
+  int k = 0;
+  for (int c = 0; c < nc; c++)
+    for (int i = 0; i < cnt[c]; i++, k++) {
+      if (k < cap && out_xyr) {
+        const uint32_t key = keys[(size_t)c * D.cellCap + i];
+        out_xyr[3 * k] = (float)(key & 0xFFF);
+        out_xyr[3 * k + 1] = (float)((key >> 12) & 0xFFF);
+        out_xyr[3 * k + 2] = (float)(key >> 24);
+      }
+    }
+  *n = k;
+  return GFS_OK;
+}
+
+// Host-only debug hook: the libstdc++-introsort restatement used by k_octree, exposed so the CPU
+// test-suite can compare it against std::sort (tests/test_host_logic.py).  key: (first, ulx).
+int gfs_debug_gcc_sort(int* first, int* second, const int* ulx_by_second, int n, int* heapsorted) {
+  struct L {
+    const int* u;
+    GFS_HD bool operator()(int af, int as, int bf, int bs) const {
+      if (af < bf) return true;
+      if (af > bf) return false;
+      return u[as] < u[bs];
+    }
+  };
+  int hs = 0;
+  GccSort<L> s{{first, second}, L{ulx_by_second}};
+  s.sort(n, &hs);
+  if (heapsorted) *heapsorted = hs;
+  return GFS_OK;
+}
+}

@@ -1,0 +1,124 @@
+/* gfs_b200.h -- C ABI of the B200-native GeoFlow-SLAM hot path (libgfs_b200.so).
+ *
+ * The reference (HorizonRobotics/GeoFlowSlam) has no plugin/FFI layer: the drop-in boundary is
+ * four C++ call sites.  Each entry point below names the reference interface it
+ * replaces (file:line into the reference tree).  Plain pointers and sizes only; no C++/torch
+ * types.  All functions return 0 on success or a negative GFS_ERR_* code; none throws.
+ *
+ * Pointer-space convention: names ending in _device take DEVICE pointers and enqueue work on
+ * `stream` without synchronising (the caller owns synchronisation); the un-suffixed variants
+ * take HOST pointers, stage through pinned memory, and return after the results are on the host.
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *
+ * Threading: a handle owns its workspace; use one handle per calling thread (the reference calls
+ * the extractor from the tracking thread or two pool threads, System.cc:570-596).
+ */
+#ifndef GFS_B200_H_
+#define GFS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GFS_OK 0
+#define GFS_ERR_INVALID (-1)  /* bad argument */
+#define GFS_ERR_CUDA (-2)     /* CUDA runtime error, see gfs_last_error() */
+#define GFS_ERR_CAPACITY (-3) /* input exceeds the capacity the handle was created with */
+#define GFS_ERR_EMPTY (-4)    /* empty image: the reference returns -1 (ORBextractor.cc:1150) */
+#define GFS_ERR_NODEVICE (-5) /* no CUDA device: there is NO CPU fallback */
+
+const char* gfs_last_error(void);
+/* 0 when a CUDA device is usable, GFS_ERR_NODEVICE otherwise. */
+int gfs_device_check(void);
+/* library / build identification, e.g. "gfs_b200 0.1 sm_100a" */
+const char* gfs_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * ORB extractor -- replaces ORB_SLAM3::ORBextractor (include/ORBextractor.h:46-120,
+ * src/ORBextractor.cc:421-479 ctor, :1145-1225 operator()).
+ * ---------------------------------------------------------------------------------------- */
+
+/* cv::KeyPoint fields the reference fills (pt, size, angle, response, octave). 24 bytes. */
+typedef struct GfsKeyPoint {
+  float x, y;     /* level-0 pixel coordinates (pt *= scale, ORBextractor.cc:1204) */
+  float size;     /* PATCH_SIZE * mvScaleFactor[octave] truncated to int (:860) */
+  float angle;    /* degrees, cv::fastAtan2 convention (:94) */
+  float response; /* FAST score */
+  int32_t octave;
+} GfsKeyPoint;
+
+typedef struct GfsOrb GfsOrb;
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+ * (src/ORBextractor.cc:421).  max_w/max_h/max_batch size the device workspace. */
+int gfs_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, int max_w,
+                   int max_h, int max_batch, GfsOrb** out);
+int gfs_orb_destroy(GfsOrb* h);
+/* Row stride (in keypoints) of the per-frame output arrays: nfeatures + 3*nlevels rounded up to
+ * a multiple of 32 (the quadtree may return up to N+2 points per level, ORBextractor.cc:703-707). */
+int gfs_orb_max_keypoints(const GfsOrb* h);
+/* GetScaleFactors() / mnFeaturesPerLevel (include/ORBextractor.h:69-83, :108). arrays of nlevels. */
+int gfs_orb_tables(const GfsOrb* h, float* scale_factors, int* features_per_level);
+/* level size as ComputePyramid computes it (src/ORBextractor.cc:1229-1231) */
+int gfs_orb_level_size(const GfsOrb* h, int w, int h_img, int level, int* lw, int* lh);
+
+/* int ORBextractor::operator()(image, mask, keypoints, descriptors, vLappingArea)
+ * (include/ORBextractor.h:61-64).  Batched: `batch` gray images of w x h, row pitch `pitch`
+ * bytes, consecutive images `img_stride` bytes apart.
+ *   out_kp   [batch][gfs_orb_max_keypoints]       keypoints, mono from the front, lapping from the back
+ *   out_desc [batch][gfs_orb_max_keypoints][32]   rBRIEF descriptors, same order
+ *   out_n    [batch]  number of keypoints;  out_mono [batch]  monoIndex (the reference's return value)
+ */
+int gfs_orb_extract_batch_device(GfsOrb* h, void* stream, const uint8_t* d_imgs, int batch, int w, int h_img,
+                                 int pitch, size_t img_stride, int lap0, int lap1, GfsKeyPoint* d_out_kp,
+                                 uint8_t* d_out_desc, int* d_out_n, int* d_out_mono);
+int gfs_orb_extract_batch(GfsOrb* h, void* stream, const uint8_t* imgs, int batch, int w, int h_img, int pitch,
+                          size_t img_stride, int lap0, int lap1, GfsKeyPoint* out_kp, uint8_t* out_desc, int* out_n,
+                          int* out_mono);
+/* single frame, host pointers; returns GFS_ERR_EMPTY for a null/0-sized image. */
+int gfs_orb_extract(GfsOrb* h, void* stream, const uint8_t* img, int w, int h_img, int pitch, int lap0, int lap1,
+                    GfsKeyPoint* out_kp, uint8_t* out_desc, int* out_n, int* out_mono);
+
+/* mvImagePyramid (public member, include/ORBextractor.h:82) and the blurred working copy
+ * (ORBextractor.cc:1188-1189) of frame `frame` of the last batch, un-bordered, tightly packed
+ * lw x lh bytes, copied to the host.  Debug / parity hook. */
+int gfs_orb_get_level(GfsOrb* h, void* stream, int frame, int level, int blurred, uint8_t* out);
+/* FAST candidates (vToDistributeKeys, ORBextractor.cc:853-870) of (frame, level) of the last batch
+ * as (x, y, response) float triples relative to minBorder; returns the count through *n. */
+int gfs_orb_get_candidates(GfsOrb* h, void* stream, int frame, int level, float* out_xyr, int cap, int* n);
+/* number of kernels one gfs_orb_extract_batch_device call launches (for bench gpu_launches). */
+int gfs_orb_launches_per_call(const GfsOrb* h, int lap0, int lap1);
+
+/* ------------------------------------------------------------------------------------------
+ * Matcher -- replaces ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2536-2550), the
+ * cv::BFMatcher(NORM_HAMMING).match calls and gms_matcher::GetInlierMask(false,false) inside
+ * ORBmatcher::SearchWithGMS / SearchForInitializationWithGMS / SearchForTriangulationWithGMS
+ * (src/ORBmatcher.cc:744-778, 786-841, 852-913; Thirdparty/GMS/include/gms_matcher.h).
+ * ---------------------------------------------------------------------------------------- */
+
+/* Batched brute-force Hamming match: for pair p, query descriptors dq[p] (nq[p] rows of 32 B) vs
+ * train descriptors dt[p] (nt[p] rows).  out_idx[p][q] = argmin train index (ties -> lowest
+ * index, as cv::BFMatcher), out_dist[p][q] = Hamming distance; -1/-1 when nt[p] == 0.
+ * Descriptor arrays are [pairs][stride][32]; out arrays are [pairs][stride]. */
+int gfs_match_bf_hamming_batch_device(void* stream, const uint8_t* d_dq, const int* d_nq, const uint8_t* d_dt,
+                                      const int* d_nt, int pairs, int stride, int* d_out_idx, int* d_out_dist);
+int gfs_match_bf_hamming(void* stream, const uint8_t* dq, int nq, const uint8_t* dt, int nt, int* out_idx,
+                         int* out_dist);
+
+/* Batched GMS: matches of pair p are (q, out_idx[p][q]) for q < nq[p] (what BFMatcher::match
+ * returns).  kp1/kp2 are [pairs][stride] keypoints (only x, y are read), image sizes w x h.
+ * out_inlier[p][q] in {0,1}; out_count[p] = number of inliers (the reference's return value). */
+int gfs_gms_filter_batch_device(void* stream, const GfsKeyPoint* d_kp1, const int* d_n1, const GfsKeyPoint* d_kp2,
+                                const int* d_n2, const int* d_train_idx, int pairs, int stride, int w1, int h1,
+                                int w2, int h2, uint8_t* d_out_inlier, int* d_out_count);
+/* single pair, host pointers, explicit match list (query, train) pairs as cv::DMatch order */
+int gfs_gms_filter(void* stream, const GfsKeyPoint* kp1, int n1, int w1, int h1, const GfsKeyPoint* kp2, int n2,
+                   int w2, int h2, const int* matches_qt, int nm, uint8_t* out_inlier, int* out_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFS_B200_H_ */

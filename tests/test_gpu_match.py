@@ -1,0 +1,93 @@
+"""GPU parity: BF Hamming + GMS kernels (through the C ABI) vs the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("nq,nt,seed", [(1000, 1000, 0), (37, 1024, 1), (1, 1, 2), (513, 77, 3), (1024, 5, 4),
+                                        (3000, 2500, 5)])
+def test_bf_match_equals_oracle(nq, nt, seed):
+    from geoflowslam_b200 import ORBmatcher
+    from oracle import oracle as O
+    rng = np.random.default_rng(seed)
+    dq = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    dt = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    dt[rng.integers(0, nt, nt // 4)] = dt[rng.integers(0, nt, nt // 4)]  # duplicate rows -> ties
+    dq[: min(nq, nt) // 2] = dt[: min(nq, nt) // 2]                       # exact matches
+    gi, gd = ORBmatcher.bf_match(dq, dt)
+    oi, od = O.bf_match(dq, dt)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+
+
+def test_bf_empty_sets():
+    from geoflowslam_b200 import ORBmatcher
+    d = np.zeros((5, 32), np.uint8)
+    gi, gd = ORBmatcher.bf_match(d, np.zeros((0, 32), np.uint8))
+    assert (gi == -1).all() and (gd == -1).all()
+    gi, gd = ORBmatcher.bf_match(np.zeros((0, 32), np.uint8), d)
+    assert len(gi) == 0
+
+
+def test_descriptor_distance():
+    from geoflowslam_b200 import ORBmatcher
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        a = rng.integers(0, 256, 32, dtype=np.uint8); b = rng.integers(0, 256, 32, dtype=np.uint8)
+        assert ORBmatcher.DescriptorDistance(a, b) == int(np.unpackbits(a ^ b).sum())
+
+
+def _match_set(seed, n, frac):
+    rng = np.random.default_rng(seed)
+    p1 = np.stack([rng.uniform(19, 620, n), rng.uniform(19, 460, n)], 1).astype(np.float32)
+    p2 = np.clip(p1 + rng.normal(0, 1.0, p1.shape) + [6, -4], 0, [639, 479]).astype(np.float32)
+    tr = np.arange(n)
+    bad = rng.random(n) > frac
+    tr[bad] = rng.integers(0, n, bad.sum())
+    return p1, p2, np.stack([np.arange(n), tr], 1).astype(np.int32)
+
+
+@pytest.mark.parametrize("seed,n,frac", [(0, 1000, 0.6), (1, 1000, 0.1), (2, 300, 0.9), (3, 3000, 0.5), (4, 1, 1.0),
+                                         (5, 33, 1.0)])
+def test_gms_equals_oracle(seed, n, frac):
+    from geoflowslam_b200 import ORBmatcher
+    from oracle import oracle as O
+    p1, p2, m = _match_set(seed, n, frac)
+    gm, gc = ORBmatcher.gms_filter(p1, (640, 480), p2, (640, 480), m)
+    om, oc = O.gms_filter(p1, (640, 480), p2, (640, 480), m)
+    assert gc == oc and np.array_equal(gm, om)
+
+
+def test_gms_degenerate():
+    from geoflowslam_b200 import ORBmatcher
+    from oracle import oracle as O
+    p = np.zeros((0, 2), np.float32)
+    gm, gc = ORBmatcher.gms_filter(p, (640, 480), p, (640, 480), np.zeros((0, 2), np.int32))
+    assert gc == 0 and len(gm) == 0
+    p1 = np.full((500, 2), 100.0, np.float32)  # every match in one cell pair (count > 255)
+    m = np.stack([np.arange(500), np.arange(500)], 1).astype(np.int32)
+    gm, gc = ORBmatcher.gms_filter(p1, (640, 480), p1, (640, 480), m)
+    om, oc = O.gms_filter(p1, (640, 480), p1, (640, 480), m)
+    assert gc == oc == 500 and np.array_equal(gm, om)
+    # points on the image border (x == w -> right index wraps, left index out of range)
+    p2 = np.array([[640, 10], [639.9, 479.9], [0, 0], [630, 470]], np.float32)
+    m = np.array([[0, 1], [1, 0], [2, 2], [3, 3]], np.int32)
+    gm, gc = ORBmatcher.gms_filter(p2, (640, 480), p2, (640, 480), m)
+    om, oc = O.gms_filter(p2, (640, 480), p2, (640, 480), m)
+    assert gc == oc and np.array_equal(gm, om)
+
+
+def test_extract_match_gms_pipeline(frames4):
+    """configs[1] slice: extract two frames of one scene, BF + GMS, everything vs the oracle."""
+    from geoflowslam_b200 import ORBextractor, ORBmatcher
+    from oracle import oracle as O
+    e = ORBextractor(1000, 1.2, 8, 25, 7, max_size=(640, 480), max_batch=2)
+    kps, desc, n, _ = e.extract_batch(frames4[:2])
+    k1, d1, k2, d2 = kps[0, :n[0]], desc[0, :n[0]], kps[1, :n[1]], desc[1, :n[1]]
+    m, mask, cnt = ORBmatcher().SearchWithGMS(k1, d1, k2, d2, (640, 480))
+    oi, _ = O.bf_match(d1, d2)
+    assert np.array_equal(m[:, 1], oi)
+    p1 = np.stack([k1["x"], k1["y"]], 1); p2 = np.stack([k2["x"], k2["y"]], 1)
+    om, oc = O.gms_filter(p1, (640, 480), p2, (640, 480), m)
+    assert cnt == oc and np.array_equal(mask, om)
+    assert cnt > 100  # same scene under a small homography: most matches are coherent
