@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the GeoFlow-SLAM hot path on B200.
+
+Workload (BASELINE.json configs[1]): a batch of 1024 synthetic 640x480 gray frames, 1000 ORB
+features (scale 1.2, 8 levels, FAST 25/7), ORB extraction of every frame followed by BF-Hamming
++ GMS matching of every consecutive pair.  One "step" = one pass over the batch.  Metric:
+frames/s (whole job, all ranks).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...      (one rank per GPU, weak scaling)
+
+`value`  : inputs resident in HBM, timed with CUDA events on the launching stream.
+`e2e`    : the same step through the host-buffer C-ABI call (gfs_frontend_run): pinned host images
+           in, every result (keypoints, descriptors, matches, inlier masks) back on the host.
+`roofline`: dominant kernel, algorithmic bytes (DESIGN.md "Algorithmic bytes") / CUDA-event time.
+`cpu_baseline` / `--impl reference`: the restated reference CPU path (oracle/) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+W, H = 640, 480
+ORB_CFG = dict(nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=25, minThFAST=7)
+LEVELS = [(640, 480), (533, 400), (444, 333), (370, 278), (309, 231), (257, 193), (214, 161), (179, 134)]
+METRIC = "frames/sec VGA ORB(1k feats)+BF/GMS match, batch 1024 (BASELINE configs[1])"
+
+
+def _gen_chunk(args):
+    from geoflowslam_b200 import synth
+    start, n, seed0 = args
+    # frames of one 8-frame group share a scene; chunks start on group boundaries
+    return synth.orb_frames(n, W, H, group=8, seed0=seed0 + start)
+
+
+def make_frames(n, seed0, procs):
+    """n distinct synthetic frames (numpy generator, fork pool; call before CUDA is initialised)."""
+    from multiprocessing import get_context
+    chunk = 8
+    jobs = [(s, min(chunk, n - s), seed0) for s in range(0, n, chunk)]
+    if procs <= 1 or len(jobs) == 1:
+        parts = [_gen_chunk(j) for j in jobs]
+    else:
+        with get_context("fork").Pool(procs) as pool:
+            parts = pool.map(_gen_chunk, jobs)
+    return np.ascontiguousarray(np.concatenate(parts, 0))
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the restated reference path (oracle) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_frames_per_sec(frames, threads):
+    """ORB extract every frame + BF/GMS every consecutive pair with `threads` worker threads (each
+    worker runs the single-threaded oracle; ctypes releases the GIL).  Returns (fps, seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    O.lib()
+    tl = threading.local()
+
+    def ext(i):
+        if not hasattr(tl, "o"):
+            tl.o = O.OrbOracle(ORB_CFG["nfeatures"], ORB_CFG["scaleFactor"], ORB_CFG["nlevels"],
+                               ORB_CFG["iniThFAST"], ORB_CFG["minThFAST"], threads=1)
+        return tl.o.extract(frames[i])
+
+    def match(p):
+        (k1, d1, _), (k2, d2, _) = res[p], res[p + 1]
+        idx, _ = O.bf_match(d1, d2, threads=1)
+        m = np.stack([np.arange(len(idx), dtype=np.int32), idx], 1)
+        return O.gms_filter(np.stack([k1["x"], k1["y"]], 1), (W, H), np.stack([k2["x"], k2["y"]], 1), (W, H), m)[1]
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        res = list(ex.map(ext, range(len(frames))))
+        list(ex.map(match, range(len(frames) - 1)))
+    dt = time.perf_counter() - t0
+    return len(frames) / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = max(2 * cores, 32)
+    frames = make_frames(n, 1000, min(cores, 16))
+    for _ in range(args.warmup):
+        cpu_frames_per_sec(frames[:max(cores, 8)], cores)
+    t = []
+    for _ in range(args.steps):
+        fps, dt = cpu_frames_per_sec(frames, cores)
+        t.append(dt)
+    ms = 1e3 * sum(t) / len(t)
+    value = n / (ms / 1e3)
+    sample = "%d frames + %d pairs per step, %d steps" % (n, n - 1, args.steps)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[1]: ORB(1000 feats, 1.2, 8 levels, FAST 25/7) + BF-Hamming + GMS, 640x480",
+                       "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(stage, n_frames, n_kp, n_cand):
+    """Algorithmic bytes one launch group of `stage` moves for n_frames."""
+    px = [w * h for (w, h) in LEVELS]
+    per_frame = {
+        "pyramid": sum(px[:-1]) + sum(px[1:]),           # read levels 0..6, write levels 1..7
+        "fast_cells": sum(px) + 4 * n_cand,              # read every level once, write packed candidates
+        "octree": 4 * n_cand + 4 * n_kp,                 # read candidates, write selected keys
+        "blur": 2 * sum(px),                             # read + write every level
+        "orient_desc": n_kp * (749 + 512 + 24 + 32 + 4),  # disc + 512 samples + keypoint + descriptor + key
+        "pack_lapping": 0,
+        "bf_hamming": 2 * n_kp * 32 + n_kp * 8,          # both descriptor sets + (idx, dist)
+        "gms": 2 * n_kp * 8 + n_kp * 4 + n_kp,           # both point sets + train idx + mask
+    }
+    return per_frame[stage] * n_frames
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    B = args.batch
+    cores = os.cpu_count() or 1
+    # synthetic input first (fork pool), CUDA afterwards
+    frames = make_frames(B, 1000 + rank * 100000, max(1, min(16, cores // max(world, 1))))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from geoflowslam_b200 import TrackingFrontend
+    from geoflowslam_b200._lib import KP_DTYPE
+    fe = TrackingFrontend(max_size=(W, H), max_batch=B, **ORB_CFG)
+    S = fe.stride
+    dev = torch.device("cuda", local)
+    d_imgs = torch.from_numpy(frames).to(dev)
+    d_out = dict(kp=torch.empty((B, S, 6), dtype=torch.float32, device=dev),
+                 desc=torch.empty((B, S, 32), dtype=torch.uint8, device=dev),
+                 n=torch.zeros(B, dtype=torch.int32, device=dev), mono=torch.zeros(B, dtype=torch.int32, device=dev),
+                 train_idx=torch.empty((B, S), dtype=torch.int32, device=dev),
+                 dist=torch.empty((B, S), dtype=torch.int32, device=dev),
+                 inlier=torch.empty((B, S), dtype=torch.uint8, device=dev),
+                 inlier_count=torch.zeros(B, dtype=torch.int32, device=dev))
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_dev():
+        fe.run_device(d_imgs, B, W, H, W, W * H, d_out, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        """k calls of fn between two CUDA events on the current stream -> ms (max over ranks)."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_dev, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step / 1e3)
+
+    # per-kernel durations (CUDA events recorded inside the C-ABI call, on the same stream)
+    fe.set_profiling(True)
+    prof = {}
+    for _ in range(args.steps):
+        step_dev()
+        for k, v in fe.profile().items():
+            prof.setdefault(k, []).append(v)
+    fe.set_profiling(False)
+    prof = {k: sum(v) / len(v) for k, v in prof.items()}
+    n_host = d_out["n"].cpu().numpy()
+    mean_kp = float(n_host.mean())
+
+    # end to end through the host-buffer C-ABI call: pinned images in, all results out
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+    h_imgs_t = pin(frames.shape, torch.uint8)
+    h_imgs_t.copy_(torch.from_numpy(frames))
+    h_imgs = h_imgs_t.numpy()
+    keep = []
+
+    def pinned_np(shape, dt):
+        nbytes = int(np.prod(shape)) * np.dtype(dt).itemsize
+        t = torch.empty(max(nbytes, 1), dtype=torch.uint8).pin_memory()
+        keep.append(t)
+        return t.numpy()[:nbytes].view(dt).reshape(shape)
+
+    h_out = fe.alloc_host_outputs(B, pinned_np)
+
+    def step_e2e():
+        fe.run(h_imgs, out=h_out, stream=stream)
+
+    for _ in range(2):
+        step_e2e()
+    e2e_steps = max(1, min(args.steps, 5))
+    ms_e2e = timed(step_e2e, e2e_steps) / e2e_steps
+    e2e_value = world * B / (ms_e2e / 1e3)
+    h2d = int(frames.nbytes)
+    d2h = int(sum(v.nbytes for v in h_out.values()))
+    assert np.array_equal(h_out["n"], n_host), "host-path and device-path results differ"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
+    top = max(prof, key=prof.get)
+    cand_per_frame = 3400.0  # measured mean FAST candidates/frame on this workload (profiles/r01_stage_stats.md)
+    alg = algorithmic_bytes(top, B if top not in ("bf_hamming", "gms") else B - 1, mean_kp, cand_per_frame)
+    achieved = alg / (prof[top] / 1e3) / 1e9
+    roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "ms_per_launch_group": prof[top], "peak_source": peak_src,
+            "stage_ms": prof}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        ns = max(2 * cores, 32)
+        fps, dt = cpu_frames_per_sec(frames[:ns], cores)
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "first %d frames + %d pairs of the same batch, %.1f s wall, %d worker threads" % (ns, ns - 1, dt, cores)}
+
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[1]: ORB(1000 feats, 1.2, 8 levels, FAST 25/7) + BF-Hamming + GMS i->i+1",
+                       "frames_per_gpu": B, "width": W, "height": H, "mean_keypoints": mean_kp,
+                       "l2": "inputs larger than L2 (%.0f MB of frames per step)" % (frames.nbytes / 1e6),
+                       "parallelism": "frames sharded across ranks, no data-path collective"},
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": args.steps * fe.launches_per_call(B)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -3,3 +3,4 @@ behind the reference's own entry points.  See DESIGN.md / INTEGRATION.md."""
 from ._lib import GfsError, KP_DTYPE  # noqa: F401
 from .matcher import ORBmatcher  # noqa: F401
 from .orb import ORBextractor  # noqa: F401
+from .frontend import TrackingFrontend  # noqa: F401

@@ -48,6 +48,17 @@ SIGNATURES = {
     "gfs_orb_get_level": ([vp, vp, ci, ci, ci, vp], ci),
     "gfs_orb_get_candidates": ([vp, vp, ci, ci, vp, ci, vp], ci),
     "gfs_orb_launches_per_call": ([vp, ci, ci], ci),
+    "gfs_orb_set_profiling": ([vp, ci], ci),
+    "gfs_orb_get_profile": ([vp, vp], ci),
+    "gfs_frontend_create": ([ci, cf, ci, ci, ci, ci, ci, ci, C.POINTER(vp)], ci),
+    "gfs_frontend_destroy": ([vp], ci),
+    "gfs_frontend_max_keypoints": ([vp], ci),
+    "gfs_frontend_orb": ([vp], vp),
+    "gfs_frontend_run_device": ([vp, vp, vp, ci, ci, ci, ci, sz, vp, vp, vp, vp, vp, vp, vp, vp], ci),
+    "gfs_frontend_run": ([vp, vp, vp, ci, ci, ci, ci, sz, vp, vp, vp, vp, vp, vp, vp, vp], ci),
+    "gfs_frontend_set_profiling": ([vp, ci], ci),
+    "gfs_frontend_get_profile": ([vp, vp], ci),
+    "gfs_frontend_launches_per_call": ([vp, ci], ci),
     "gfs_match_bf_hamming_batch_device": ([vp, vp, vp, vp, vp, ci, ci, vp, vp], ci),
     "gfs_match_bf_hamming": ([vp, vp, ci, vp, ci, vp, vp], ci),
     "gfs_gms_filter_batch_device": ([vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp], ci),

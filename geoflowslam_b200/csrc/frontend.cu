@@ -1,0 +1,167 @@
+// Batched tracking front-end: ORB extraction of `batch` frames followed by BF-Hamming + GMS
+// between consecutive frames (frame i -> frame i+1).  This is the per-frame sequence
+// Frame::ExtractORB (reference src/Frame.cc:768-777 -> ORBextractor::operator()) then
+// ORBmatcher::SearchWithGMS (src/ORBmatcher.cc:744-778) of System::TrackRGBD, applied to a batch
+// of independent frames -- BASELINE.json configs[1].
+#include <algorithm>
+
+#include "common.cuh"
+
+using namespace gfs;
+
+struct GfsFrontend {
+  GfsOrb* orb = nullptr;
+  int maxBatch = 0, stride = 0;
+  DevBuf d_in, d_kp, d_desc, d_n, d_idx, d_dist, d_inl, d_cnt;
+  PinnedBuf h_in;
+  cudaStream_t copyStream = nullptr;
+  cudaEvent_t evIn[2] = {nullptr, nullptr}, evDone = nullptr;
+  bool profiling = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, after orb, after bf, after gms
+};
+
+extern "C" {
+
+int gfs_frontend_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, int max_w,
+                        int max_h, int max_batch, GfsFrontend** out) {
+  GFS_REQUIRE(out, GFS_ERR_INVALID, "out is null");
+  *out = nullptr;
+  GfsOrb* orb = nullptr;
+  int rc = gfs_orb_create(nfeatures, scale_factor, nlevels, ini_th_fast, min_th_fast, max_w, max_h, max_batch, &orb);
+  if (rc) return rc;
+  GfsFrontend* f = new GfsFrontend();
+  f->orb = orb;
+  f->maxBatch = max_batch;
+  f->stride = gfs_orb_max_keypoints(orb);
+  *out = f;
+  return GFS_OK;
+}
+
+int gfs_frontend_destroy(GfsFrontend* f) {
+  if (!f) return GFS_OK;
+  gfs_orb_destroy(f->orb);
+  DevBuf* d[] = {&f->d_in, &f->d_kp, &f->d_desc, &f->d_n, &f->d_idx, &f->d_dist, &f->d_inl, &f->d_cnt};
+  for (DevBuf* b : d) b->release();
+  f->h_in.release();
+  for (cudaEvent_t e : f->ev)
+    if (e) cudaEventDestroy(e);
+  delete f;
+  return GFS_OK;
+}
+
+int gfs_frontend_max_keypoints(const GfsFrontend* f) { return f ? f->stride : GFS_ERR_INVALID; }
+GfsOrb* gfs_frontend_orb(GfsFrontend* f) { return f ? f->orb : nullptr; }
+
+int gfs_frontend_set_profiling(GfsFrontend* f, int enable) {
+  GFS_REQUIRE(f, GFS_ERR_INVALID, "null handle");
+  if (enable && !f->ev[0])
+    for (int i = 0; i < 4; i++) GFS_CUDA(cudaEventCreate(&f->ev[i]));
+  f->profiling = enable != 0;
+  return gfs_orb_set_profiling(f->orb, enable);
+}
+
+// ms8 = {pyramid, fast_cells, octree, blur, orient_desc, pack_lapping, bf_hamming, gms}
+int gfs_frontend_get_profile(GfsFrontend* f, float* ms8) {
+  GFS_REQUIRE(f && ms8 && f->profiling, GFS_ERR_INVALID, "profiling not enabled");
+  int rc = gfs_orb_get_profile(f->orb, ms8);
+  if (rc) return rc;
+  GFS_CUDA(cudaEventSynchronize(f->ev[3]));
+  GFS_CUDA(cudaEventElapsedTime(&ms8[6], f->ev[1], f->ev[2]));
+  GFS_CUDA(cudaEventElapsedTime(&ms8[7], f->ev[2], f->ev[3]));
+  return GFS_OK;
+}
+
+int gfs_frontend_launches_per_call(const GfsFrontend* f, int batch) {
+  if (!f) return GFS_ERR_INVALID;
+  return gfs_orb_launches_per_call(f->orb, 0, 0) + (batch > 1 ? 2 : 0);
+}
+
+int gfs_frontend_run_device(GfsFrontend* f, void* stream, const uint8_t* d_imgs, int batch, int w, int h_img,
+                            int pitch, size_t img_stride, GfsKeyPoint* d_kp, uint8_t* d_desc, int* d_n, int* d_mono,
+                            int* d_train_idx, int* d_dist, uint8_t* d_inlier, int* d_inlier_count) {
+  GFS_REQUIRE(f, GFS_ERR_INVALID, "null handle");
+  GFS_REQUIRE(batch > 0 && batch <= f->maxBatch, GFS_ERR_CAPACITY, "batch exceeds the handle's max_batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f->profiling) cudaEventRecord(f->ev[0], st);
+  int rc = gfs_orb_extract_batch_device(f->orb, stream, d_imgs, batch, w, h_img, pitch, img_stride, 0, 0, d_kp, d_desc,
+                                        d_n, d_mono);
+  if (rc) return rc;
+  if (f->profiling) cudaEventRecord(f->ev[1], st);
+  if (batch > 1) {
+    const int s = f->stride;
+    // pair p: query = frame p, train = frame p + 1
+    rc = gfs_match_bf_hamming_batch_device(stream, d_desc, d_n, d_desc + (size_t)s * 32, d_n + 1, batch - 1, s,
+                                           d_train_idx, d_dist);
+    if (rc) return rc;
+    if (f->profiling) cudaEventRecord(f->ev[2], st);
+    rc = gfs_gms_filter_batch_device(stream, d_kp, d_n, d_kp + s, d_n + 1, d_train_idx, batch - 1, s, w, h_img, w,
+                                     h_img, d_inlier, d_inlier_count);
+    if (rc) return rc;
+  } else if (f->profiling) {
+    cudaEventRecord(f->ev[2], st);
+  }
+  if (f->profiling) cudaEventRecord(f->ev[3], st);
+  return GFS_OK;
+}
+
+// Host-pointer variant: H2D of the images, the device pipeline, D2H of every result.
+// Outputs: out_kp [batch][stride], out_desc [batch][stride][32], out_n/out_mono [batch],
+// out_train_idx/out_dist [batch-1][stride], out_inlier [batch-1][stride], out_inlier_count [batch-1].
+int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batch, int w, int h_img, int pitch,
+                     size_t img_stride, GfsKeyPoint* out_kp, uint8_t* out_desc, int* out_n, int* out_mono,
+                     int* out_train_idx, int* out_dist, uint8_t* out_inlier, int* out_inlier_count) {
+  GFS_REQUIRE(f, GFS_ERR_INVALID, "null handle");
+  GFS_REQUIRE(imgs && w > 0 && h_img > 0, GFS_ERR_EMPTY, "empty image");
+  GFS_REQUIRE(batch > 0 && batch <= f->maxBatch, GFS_ERR_CAPACITY, "batch exceeds the handle's max_batch");
+  GFS_REQUIRE(out_kp && out_desc && out_n && out_mono, GFS_ERR_INVALID, "null output");
+  GFS_REQUIRE(batch == 1 || (out_train_idx && out_dist && out_inlier && out_inlier_count), GFS_ERR_INVALID, "null match output");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int s = f->stride;
+  const size_t B = (size_t)batch, dpitch = align_up((size_t)w, 16), dstride = dpitch * h_img;
+  int rc;
+  if ((rc = f->d_in.reserve(B * dstride))) return rc;
+  if ((rc = f->d_kp.reserve(B * s * sizeof(GfsKeyPoint)))) return rc;
+  if ((rc = f->d_desc.reserve(B * s * 32))) return rc;
+  if ((rc = f->d_n.reserve(B * 2 * sizeof(int)))) return rc;
+  if ((rc = f->d_idx.reserve(B * s * sizeof(int)))) return rc;
+  if ((rc = f->d_dist.reserve(B * s * sizeof(int)))) return rc;
+  if ((rc = f->d_inl.reserve(B * s))) return rc;
+  if ((rc = f->d_cnt.reserve(B * sizeof(int)))) return rc;
+  const uint8_t* src = imgs;
+  size_t spitch = pitch;
+  if (!is_pinned_host(imgs)) {  // pageable input: stage once through pinned memory
+    if ((rc = f->h_in.reserve(B * (size_t)w * h_img))) return rc;
+    uint8_t* stg = (uint8_t*)f->h_in.p;
+    for (size_t i = 0; i < B; i++)
+      for (int y = 0; y < h_img; y++) memcpy(stg + (i * h_img + y) * w, imgs + i * img_stride + (size_t)y * pitch, w);
+    src = stg;
+    spitch = w;
+    img_stride = (size_t)w * h_img;
+  }
+  if (img_stride == spitch * h_img) {
+    GFS_CUDA(cudaMemcpy2DAsync(f->d_in.p, dpitch, src, spitch, w, (size_t)h_img * B, cudaMemcpyHostToDevice, st));
+  } else {
+    for (size_t i = 0; i < B; i++)
+      GFS_CUDA(cudaMemcpy2DAsync((uint8_t*)f->d_in.p + i * dstride, dpitch, src + i * img_stride, spitch, w, h_img,
+                                 cudaMemcpyHostToDevice, st));
+  }
+  int* d_n = (int*)f->d_n.p;
+  int* d_mono = d_n + batch;
+  rc = gfs_frontend_run_device(f, stream, (const uint8_t*)f->d_in.p, batch, w, h_img, (int)dpitch, dstride,
+                               (GfsKeyPoint*)f->d_kp.p, (uint8_t*)f->d_desc.p, d_n, d_mono, (int*)f->d_idx.p,
+                               (int*)f->d_dist.p, (uint8_t*)f->d_inl.p, (int*)f->d_cnt.p);
+  if (rc) return rc;
+  GFS_CUDA(cudaMemcpyAsync(out_kp, f->d_kp.p, B * s * sizeof(GfsKeyPoint), cudaMemcpyDeviceToHost, st));
+  GFS_CUDA(cudaMemcpyAsync(out_desc, f->d_desc.p, B * s * 32, cudaMemcpyDeviceToHost, st));
+  GFS_CUDA(cudaMemcpyAsync(out_n, d_n, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  GFS_CUDA(cudaMemcpyAsync(out_mono, d_mono, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (batch > 1) {
+    GFS_CUDA(cudaMemcpyAsync(out_train_idx, f->d_idx.p, (B - 1) * s * sizeof(int), cudaMemcpyDeviceToHost, st));
+    GFS_CUDA(cudaMemcpyAsync(out_dist, f->d_dist.p, (B - 1) * s * sizeof(int), cudaMemcpyDeviceToHost, st));
+    GFS_CUDA(cudaMemcpyAsync(out_inlier, f->d_inl.p, (B - 1) * s, cudaMemcpyDeviceToHost, st));
+    GFS_CUDA(cudaMemcpyAsync(out_inlier_count, f->d_cnt.p, (B - 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
+  GFS_CUDA(cudaStreamSynchronize(st));
+  return GFS_OK;
+}
+}

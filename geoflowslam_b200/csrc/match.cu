@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(GMS_THREADS) k_gms(const GfsKeyPoint* __restri
   uint32_t* keys = gsm;                          // [pow2]
   short* ml = (short*)(keys + pow2);             // [mstride] left cell of match i (this grid type)
   short* mr = ml + mstride;                      // [mstride] right cell (grid type 1)
-  int* nLeft = (int*)(mr + mstride + (mstride & 1));  // [400]
+  int* nLeft = (int*)(ml + 2 * mstride);        // [400] (2*mstride shorts keep 4-byte alignment)
   int* cellPair = nLeft + GMS_NG;                // [400]
   __shared__ int s_cnt;
   const int pair = blockIdx.x, tid = threadIdx.x;
@@ -245,7 +245,7 @@ static int launch_gms(cudaStream_t st, const GfsKeyPoint* kp1, const int* n1, co
                       const int* mq, const int* mt, const int* nm, int pairs, int stride, int mstride, int w1, int h1,
                       int w2, int h2, uint8_t* inl, int* cnt) {
   const int p2 = next_pow2(mstride);
-  const size_t smem = (size_t)p2 * 4 + ((size_t)mstride * 2 + (mstride & 1)) * 2 + 2 * GMS_NG * 4;
+  const size_t smem = (size_t)p2 * 4 + (size_t)mstride * 4 + 2 * GMS_NG * 4;
   GFS_REQUIRE(smem <= 200 * 1024, GFS_ERR_CAPACITY, "too many matches per pair for the GMS kernel (max ~24k)");
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {

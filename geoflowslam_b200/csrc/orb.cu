@@ -103,28 +103,36 @@ __device__ __forceinline__ bool has_arc9(unsigned m16) {
   return (r & 0xFFFFu) != 0;
 }
 
-// best = max over the 16 arcs of 9 contiguous ring pixels of max(min d, -max d)
+// best = max over the 16 arcs of 9 contiguous ring pixels of max(min d, min -d).
+// NOTE (toolchain): written with min-only networks over d and -d.  The equivalent
+// max(best, max(min d, -(max d))) form is MISCOMPILED by ptxas 12.9 for sm_100a at -O1 and above
+// (it returned max(d) for rings such as {33,32,30,29,31,27,30,20,-1,-1,0,-2,-2,7,36,37}; correct
+// at -Xptxas -O0) -- found by the oracle parity test, see DESIGN.md "ptxas min/max miscompile".
 __device__ __forceinline__ int fast_best16(const int (&d)[16]) {
-  int mn2[16], mx2[16];
+  int nd[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) nd[k] = -d[k];
+  int a2[16], b2[16];
 #pragma unroll
   for (int k = 0; k < 16; k++) {
-    mn2[k] = min(d[k], d[(k + 1) & 15]);
-    mx2[k] = max(d[k], d[(k + 1) & 15]);
+    a2[k] = min(d[k], d[(k + 1) & 15]);
+    b2[k] = min(nd[k], nd[(k + 1) & 15]);
   }
-  int mn4[16], mx4[16];
+  int a4[16], b4[16];
 #pragma unroll
   for (int k = 0; k < 16; k++) {
-    mn4[k] = min(mn2[k], mn2[(k + 2) & 15]);
-    mx4[k] = max(mx2[k], mx2[(k + 2) & 15]);
+    a4[k] = min(a2[k], a2[(k + 2) & 15]);
+    b4[k] = min(b2[k], b2[(k + 2) & 15]);
   }
-  int best = -1000;
+  int bestD = -1000, bestB = -1000;
 #pragma unroll
   for (int k = 0; k < 16; k++) {
-    int mn = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
-    int mx = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
-    best = max(best, max(mn, -mx));
+    const int a = min(min(a4[k], a4[(k + 4) & 15]), d[(k + 8) & 15]);
+    const int b = min(min(b4[k], b4[(k + 4) & 15]), nd[(k + 8) & 15]);
+    bestD = max(bestD, a);
+    bestB = max(bestB, b);
   }
-  return best;
+  return max(bestD, bestB);
 }
 
 static const int FAST_THREADS = 128;
@@ -783,6 +791,9 @@ struct GfsOrb {
   DevBuf d_in, d_okp, d_odesc, d_on, d_omono, d_tkp, d_tdesc;
   PinnedBuf h_in, h_okp, h_odesc, h_on;
   size_t fastSmem = 0, octSmem = 0;
+  // optional per-stage CUDA-event timing (bench roofline): pyramid, fast, octree, blur, orient/desc, pack
+  bool profiling = false;
+  cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // last batch (debug hooks)
   const uint8_t* lastImgs = nullptr;
   long long lastStride = 0;
@@ -816,7 +827,7 @@ static void area_tab(int ssize, int dsize, std::vector<AreaEntry>& out) {
 
 static int orb_set_geometry(GfsOrb* h, int w, int ht) {
   if (h->geomW == w && h->geomH == ht) return GFS_OK;
-  OrbDev& D = h->dev;
+  OrbDev D = h->dev;  // built on a copy; committed only when everything succeeded
   D.nlevels = h->nlevels;
   D.iniTh = h->iniTh;
   D.minTh = h->minTh;
@@ -937,8 +948,17 @@ static int orb_set_geometry(GfsOrb* h, int w, int ht) {
     set_error("nfeatures too large: quadtree needs %zu B shared memory", h->octSmem);
     return GFS_ERR_CAPACITY;
   }
-  GFS_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->octSmem));
-  GFS_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem));
+  // the attribute is per function (shared by every handle): only ever raise it
+  static size_t octMax = 48 * 1024, fastMax = 48 * 1024;
+  if (h->octSmem > octMax) {
+    GFS_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->octSmem));
+    octMax = h->octSmem;
+  }
+  if (h->fastSmem > fastMax) {
+    GFS_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem));
+    fastMax = h->fastSmem;
+  }
+  h->dev = D;
   h->geomW = w;
   h->geomH = ht;
   return GFS_OK;
@@ -994,6 +1014,8 @@ int gfs_orb_destroy(GfsOrb* h) {
                  &h->d_tkp, &h->d_tdesc};
   for (DevBuf* b : d) b->release();
   h->h_in.release(); h->h_okp.release(); h->h_odesc.release(); h->h_on.release();
+  for (int i = 0; i < 7; i++)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
   return GFS_OK;
 }
@@ -1016,6 +1038,21 @@ int gfs_orb_level_size(const GfsOrb* h, int w, int h_img, int level, int* lw, in
   return GFS_OK;
 }
 
+int gfs_orb_set_profiling(GfsOrb* h, int enable) {
+  GFS_REQUIRE(h, GFS_ERR_INVALID, "null handle");
+  if (enable && !h->ev[0])
+    for (int i = 0; i < 7; i++) GFS_CUDA(cudaEventCreate(&h->ev[i]));
+  h->profiling = enable != 0;
+  return GFS_OK;
+}
+
+int gfs_orb_get_profile(GfsOrb* h, float* ms6) {
+  GFS_REQUIRE(h && ms6 && h->profiling && h->ev[0], GFS_ERR_INVALID, "profiling not enabled");
+  GFS_CUDA(cudaEventSynchronize(h->ev[6]));
+  for (int i = 0; i < 6; i++) GFS_CUDA(cudaEventElapsedTime(&ms6[i], h->ev[i], h->ev[i + 1]));
+  return GFS_OK;
+}
+
 int gfs_orb_launches_per_call(const GfsOrb* h, int lap0, int lap1) {
   if (!h) return GFS_ERR_INVALID;
   // pyramid (nlevels-1) + fast + octree + blur (nlevels) + orient/desc (+ pack)
@@ -1028,6 +1065,8 @@ static int orb_run_chunk(GfsOrb* h, cudaStream_t st, const uint8_t* d_imgs, int 
   const OrbDev& D = h->dev;
   uint8_t* pyr = (uint8_t*)h->d_pyr.p;
   uint8_t* blur = (uint8_t*)h->d_blur.p;
+  auto mark = [&](int i) { if (h->profiling) cudaEventRecord(h->ev[i], st); };
+  mark(0);
   for (int l = 1; l < h->nlevels; l++) {
     const LevelDev& L = D.lv[l];
     dim3 blk(32, 8), grd(div_up(L.w, 32), div_up(L.h, 8), batch);
@@ -1036,16 +1075,20 @@ static int orb_run_chunk(GfsOrb* h, cudaStream_t st, const uint8_t* d_imgs, int 
     const int sp = (l == 1) ? pitch : D.lv[l - 1].pitch;
     k_pyr_level<<<grd, blk, 0, st>>>(D, l, src, ss, sp, pyr, (const AreaEntry*)h->d_tabs.p);
   }
+  mark(1);
   k_fast_cells<<<dim3(D.totalCells, batch), FAST_THREADS, h->fastSmem, st>>>(
       D, d_imgs, (long long)img_stride, pitch, pyr, (uint32_t*)h->d_cellKeys.p, (int*)h->d_cellCount.p);
+  mark(2);
   k_octree<<<div_up(batch * h->nlevels, OCT_WARPS), OCT_WARPS * 32, h->octSmem, st>>>(
       D, batch, (const uint32_t*)h->d_cellKeys.p, (const int*)h->d_cellCount.p, (uint32_t*)h->d_keysA.p,
       (uint32_t*)h->d_keysB.p, (uint32_t*)h->d_sel.p, (int*)h->d_selCount.p, (int*)h->d_status.p);
+  mark(3);
   for (int l = 0; l < h->nlevels; l++) {
     const LevelDev& L = D.lv[l];
     k_blur7<<<dim3(div_up(L.w, BL_TW), div_up(L.h, BL_TH), batch), 256, 0, st>>>(D, l, d_imgs, (long long)img_stride,
                                                                                 pitch, pyr, blur);
   }
+  mark(4);
   const bool lapping = (lap0 != 0 || lap1 != 0);
   GfsKeyPoint* kpDst = d_kp;
   uint8_t* descDst = d_desc;
@@ -1059,8 +1102,10 @@ static int orb_run_chunk(GfsOrb* h, cudaStream_t st, const uint8_t* d_imgs, int 
   k_orient_desc<<<dim3(div_up(D.selPerFrame, OD_WARPS), batch), OD_WARPS * 32, 0, st>>>(
       D, d_imgs, (long long)img_stride, pitch, pyr, blur, (const uint32_t*)h->d_sel.p, (const int*)h->d_selCount.p,
       kpDst, descDst, d_n, d_mono);
+  mark(5);
   if (lapping)
     k_pack_lapping<<<batch, 1024, 0, st>>>(D.kpStride, lap0, lap1, kpDst, descDst, d_kp, d_desc, d_n, d_mono);
+  mark(6);
   GFS_CUDA(cudaGetLastError());
   h->lastImgs = d_imgs;
   h->lastStride = (long long)img_stride;

@@ -89,6 +89,11 @@ int gfs_orb_get_level(GfsOrb* h, void* stream, int frame, int level, int blurred
 /* FAST candidates (vToDistributeKeys, ORBextractor.cc:853-870) of (frame, level) of the last batch
  * as (x, y, response) float triples relative to minBorder; returns the count through *n. */
 int gfs_orb_get_candidates(GfsOrb* h, void* stream, int frame, int level, float* out_xyr, int cap, int* n);
+/* Per-stage device timing of the last gfs_orb_extract_batch_device call (CUDA events on the call's
+ * stream): ms6 = {pyramid, fast_cells, octree, blur, orient_desc, pack_lapping}.  Measurement aid
+ * (bench.py roofline); the reference's analogue is REGISTER_TIMES (Frame.cc:352-365). */
+int gfs_orb_set_profiling(GfsOrb* h, int enable);
+int gfs_orb_get_profile(GfsOrb* h, float* ms6);
 /* number of kernels one gfs_orb_extract_batch_device call launches (for bench gpu_launches). */
 int gfs_orb_launches_per_call(const GfsOrb* h, int lap0, int lap1);
 
@@ -117,6 +122,29 @@ int gfs_gms_filter_batch_device(void* stream, const GfsKeyPoint* d_kp1, const in
 /* single pair, host pointers, explicit match list (query, train) pairs as cv::DMatch order */
 int gfs_gms_filter(void* stream, const GfsKeyPoint* kp1, int n1, int w1, int h1, const GfsKeyPoint* kp2, int n2,
                    int w2, int h2, const int* matches_qt, int nm, uint8_t* out_inlier, int* out_count);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched tracking front-end (BASELINE.json configs[1]): ORB extraction of `batch` independent
+ * frames, then BF-Hamming + GMS from frame i to frame i+1 -- the Frame::ExtractORB
+ * (src/Frame.cc:768-777) + ORBmatcher::SearchWithGMS (src/ORBmatcher.cc:744-778) sequence of
+ * System::TrackRGBD, for a whole batch per call.  Match outputs have batch-1 rows.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct GfsFrontend GfsFrontend;
+int gfs_frontend_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast, int max_w,
+                        int max_h, int max_batch, GfsFrontend** out);
+int gfs_frontend_destroy(GfsFrontend* f);
+int gfs_frontend_max_keypoints(const GfsFrontend* f);
+GfsOrb* gfs_frontend_orb(GfsFrontend* f);
+int gfs_frontend_run_device(GfsFrontend* f, void* stream, const uint8_t* d_imgs, int batch, int w, int h_img,
+                            int pitch, size_t img_stride, GfsKeyPoint* d_kp, uint8_t* d_desc, int* d_n, int* d_mono,
+                            int* d_train_idx, int* d_dist, uint8_t* d_inlier, int* d_inlier_count);
+int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batch, int w, int h_img, int pitch,
+                     size_t img_stride, GfsKeyPoint* out_kp, uint8_t* out_desc, int* out_n, int* out_mono,
+                     int* out_train_idx, int* out_dist, uint8_t* out_inlier, int* out_inlier_count);
+/* ms8 = {pyramid, fast_cells, octree, blur, orient_desc, pack_lapping, bf_hamming, gms} of the last call */
+int gfs_frontend_set_profiling(GfsFrontend* f, int enable);
+int gfs_frontend_get_profile(GfsFrontend* f, float* ms8);
+int gfs_frontend_launches_per_call(const GfsFrontend* f, int batch);
 
 #ifdef __cplusplus
 }

@@ -91,3 +91,32 @@ def test_extract_match_gms_pipeline(frames4):
     om, oc = O.gms_filter(p1, (640, 480), p2, (640, 480), m)
     assert cnt == oc and np.array_equal(mask, om)
     assert cnt > 100  # same scene under a small homography: most matches are coherent
+
+
+def test_frontend_batch_equals_oracle():
+    """gfs_frontend_run (host buffers) on 6 frames: every output vs the oracle, bit-exact."""
+    from geoflowslam_b200 import TrackingFrontend, synth
+    from oracle import oracle as O
+    frames = synth.orb_frames(6, group=3)
+    fe = TrackingFrontend(1000, 1.2, 8, 25, 7, max_size=(640, 480), max_batch=6)
+    out = fe.run(frames)
+    orc = O.OrbOracle(1000, 1.2, 8, 25, 7)
+    ref = [orc.extract(f) for f in frames]
+    for i, (ko, do, mo) in enumerate(ref):
+        n = out["n"][i]
+        assert n == len(ko) and out["mono"][i] == mo
+        for f in ("x", "y", "size", "angle", "response", "octave"):
+            assert np.array_equal(out["kp"][i, :n][f], ko[f])
+        assert np.array_equal(out["desc"][i, :n], do)
+    for p in range(5):
+        (k1, d1, _), (k2, d2, _) = ref[p], ref[p + 1]
+        oi, od = O.bf_match(d1, d2)
+        n1 = len(k1)
+        assert np.array_equal(out["train_idx"][p, :n1], oi) and np.array_equal(out["dist"][p, :n1], od)
+        m = np.stack([np.arange(n1), oi], 1)
+        om, oc = O.gms_filter(np.stack([k1["x"], k1["y"]], 1), (640, 480), np.stack([k2["x"], k2["y"]], 1),
+                              (640, 480), m)
+        assert out["inlier_count"][p] == oc
+        assert np.array_equal(out["inlier"][p, :n1].astype(bool), om)
+    # frames 2 -> 3 straddle two different scenes: GMS must reject (almost) everything
+    assert out["inlier_count"][2] < out["inlier_count"][0] // 4

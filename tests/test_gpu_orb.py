@@ -60,7 +60,7 @@ def test_edge_images(kind):
         yy, xx = np.mgrid[0:480, 0:640]
         img = (((yy // 8 + xx // 8) % 2) * 200 + 20).astype(np.uint8)  # score plateaus / ties
     else:
-        img = rng.integers(0, 256, (200, 752), dtype=np.uint8)        # nIni = 4 initial nodes
+        img = rng.integers(0, 256, (280, 752), dtype=np.uint8)        # several initial quadtree nodes
     h, w = img.shape
     e = ORBextractor(*ORB_CFG, max_size=(w, h), max_batch=1)
     mono, kg, dg = e(img)
