@@ -670,3 +670,16 @@ int gfo_distribute_octtree(const float* xyr, int n, int minX, int maxX, int minY
   return (int)r.size();
 }
 }
+
+// std::sort of (first, second) pairs with the compareNodes ordering (ORBextractor.cc:552-565),
+// key for ties = ulx[second].  Reference permutation for tests of csrc/gcc_sort.h.
+extern "C" void gfo_std_sort_pairs(int* first, int* second, const int* ulx, int n) {
+  std::vector<std::pair<int, int>> v(n);
+  for (int i = 0; i < n; i++) v[i] = std::make_pair(first[i], second[i]);
+  std::sort(v.begin(), v.end(), [ulx](std::pair<int, int>& a, std::pair<int, int>& b) {
+    if (a.first < b.first) return true;
+    if (a.first > b.first) return false;
+    return ulx[a.second] < ulx[b.second];
+  });
+  for (int i = 0; i < n; i++) { first[i] = v[i].first; second[i] = v[i].second; }
+}
