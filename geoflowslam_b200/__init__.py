@@ -4,3 +4,4 @@ from ._lib import GfsError, KP_DTYPE  # noqa: F401
 from .matcher import ORBmatcher  # noqa: F401
 from .orb import ORBextractor  # noqa: F401
 from .frontend import TrackingFrontend  # noqa: F401
+from .gicp import RegistrationGICP  # noqa: F401

@@ -59,6 +59,14 @@ SIGNATURES = {
     "gfs_frontend_set_profiling": ([vp, ci], ci),
     "gfs_frontend_get_profile": ([vp, vp], ci),
     "gfs_frontend_launches_per_call": ([vp, ci], ci),
+    "gfs_gicp_default_setting": ([vp], None),
+    "gfs_gicp_create": ([vp, ci, ci, C.POINTER(vp)], ci),
+    "gfs_gicp_destroy": ([vp], ci),
+    "gfs_gicp_align": ([vp, vp, vp, ci, vp, ci, vp, vp], ci),
+    "gfs_gicp_align_batch": ([vp, vp, vp, vp, vp, vp, ci, ci, vp, vp], ci),
+    "gfs_gicp_align_batch_device": ([vp, vp, vp, vp, vp, vp, ci, ci, vp, vp], ci),
+    "gfs_gicp_get_cloud": ([vp, vp, ci, vp, vp, ci, vp], ci),
+    "gfs_gicp_last_launches": ([vp], ci),
     "gfs_match_bf_hamming_batch_device": ([vp, vp, vp, vp, vp, ci, ci, vp, vp], ci),
     "gfs_match_bf_hamming": ([vp, vp, ci, vp, ci, vp, vp], ci),
     "gfs_gms_filter_batch_device": ([vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp], ci),

@@ -1,0 +1,1029 @@
+// Batched GICP alignment on sm_100a.
+//
+// Replaces RegistrationGICP::RegisterPointClouds (reference src/RegistrationGICP.cc:5-20) and the
+// small_gicp code behind it (Thirdparty/small_gicp/include/small_gicp: util/downsampling.hpp,
+// ann/kdtree.hpp, util/normal_estimation.hpp, factors/gicp_factor.hpp,
+// registration/reduction_omp.hpp, registration/optimizer.hpp, util/lie.hpp) for a batch of
+// independent cloud pairs.  All arithmetic is fp64 as in the reference.
+//
+//   k_group_insert / k_group_rank / k_group_fill   deterministic "group by 63-bit key" built on an
+//                      open-addressing hash table: voxels (leaf 0.02 m) for the downsampling, grid
+//                      cells (0.05 m) for the neighbour search.  Groups are numbered by first
+//                      occurrence and member lists are in input order, so every sum below has a
+//                      fixed order (results are run-to-run reproducible).
+//   k_voxel_mean       per-voxel mean in input order          (voxelgrid_sampling :23-78)
+//   k_knn_cov          exact 10-NN by expanding grid shells (KdTree::knn_search semantics: exact
+//                      k nearest) + covariance regularisation (normal_estimation.hpp:66-92)
+//   k_linearize        exact 1-NN within max_correspondence_distance, GICPFactor::linearize
+//                      (gicp_factor.hpp:34-73), block-reduced partial sums of H, b, e
+//   k_lm_begin / k_error / k_lm_decide              LevenbergMarquardtOptimizer (optimizer.hpp:83-148)
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gfs {
+
+static const unsigned long long KEY_EMPTY = 0xffffffffffffffffull;
+static const int RED_N = 29;  // 21 (H upper) + 6 (b) + 1 (e) + 1 (inlier count)
+
+struct GicpDev {
+  int nmax, hsize;  // points capacity per cloud, hash slots per cloud (power of two)
+  int nblk;         // partial-sum blocks per pair
+  double voxel, cell, max_dist, rot_eps, trans_eps;
+  int k, max_iter;
+  // per cloud (2 * pairs clouds; cloud 2p = target of pair p, 2p+1 = source)
+  unsigned long long* keys;  // [clouds][hsize]
+  int* minIdx;               // [clouds][hsize]
+  int* count;                // [clouds][hsize]
+  int* start;                // [clouds][hsize]
+  int* cursor;               // [clouds][hsize]
+  int* rank;                 // [clouds][hsize]
+  int* slotOf;               // [clouds][nmax]
+  int* members;              // [clouds][nmax]
+  int* nIn;                  // [clouds] input point count
+  int* nDown;                // [clouds] downsampled point count
+  int* nCells;               // [clouds] occupied grid cells
+  int* cellBox;              // [clouds][6] min/max cell coordinate of the grid
+  double* pts;               // [clouds][nmax][4]
+  double* cov;               // [clouds][nmax][6]
+  // per pair
+  int* corr;                 // [pairs][nmax] target index of source point (-1: none)
+  double* maha;              // [pairs][nmax][6]
+  double* partial;           // [pairs][nblk][RED_N]
+  double* partialE;          // [pairs][nblk]
+  double* state;             // [pairs][LM_STATE]
+  int* istate;               // [pairs][LM_ISTATE]
+  int* counters;             // [4]: needTrial, active
+};
+
+// per-pair LM state layout (doubles)
+enum { S_T = 0, S_NEWT = 12, S_H = 24, S_B = 45, S_E = 51, S_LAMBDA = 52, S_DELTA = 53, LM_STATE = 60 };
+// per-pair LM state layout (ints)
+enum { I_ACTIVE = 0, I_NEED = 1, I_CONV = 2, I_ITER = 3, I_TRIAL = 4, I_INL = 5, I_INNER = 6, I_SUCCESS = 7, LM_ISTATE = 8 };
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+__device__ __forceinline__ int fast_floor_d(double v) {  // util/fast_floor.hpp:12-15
+  const int n = (int)v;
+  return n - (v < (double)n);
+}
+// 63-bit key of a point for cell size 1/inv (downsampling.hpp:41-55); KEY_EMPTY if out of range
+__device__ __forceinline__ unsigned long long point_key(double x, double y, double z, double inv) {
+  const long long off = 1 << 20, mask = (1 << 21) - 1;
+  const long long cx = (long long)fast_floor_d(x * inv) + off, cy = (long long)fast_floor_d(y * inv) + off,
+                  cz = (long long)fast_floor_d(z * inv) + off;
+  if (cx < 0 || cy < 0 || cz < 0 || cx > mask || cy > mask || cz > mask) return KEY_EMPTY;
+  return (unsigned long long)cx | ((unsigned long long)cy << 21) | ((unsigned long long)cz << 42);
+}
+
+__global__ void k_group_clear(GicpDev D, int clouds) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)clouds * D.hsize;
+  if (i < n) {
+    D.keys[i] = KEY_EMPTY;
+    D.minIdx[i] = 0x7fffffff;
+    D.count[i] = 0;
+    D.cursor[i] = 0;
+  }
+  if (i < (long long)clouds * 6) D.cellBox[i] = ((i % 6) < 3) ? 0x7fffffff : -0x7fffffff;
+}
+
+// mode 0: keys of the raw float4 input points, voxel leaf; mode 1: keys of the downsampled points, grid cell
+__global__ void __launch_bounds__(256) k_group_insert(GicpDev D, int mode, const float* __restrict__ tgt,
+                                                      const float* __restrict__ src, int stride) {
+  const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = mode == 0 ? D.nIn[c] : D.nDown[c];
+  if (i >= n) return;
+  double x, y, z, inv;
+  if (mode == 0) {
+    const float* p = ((c & 1) ? src : tgt) + ((size_t)(c >> 1) * stride + i) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    x = (double)v.x; y = (double)v.y; z = (double)v.z;
+    inv = 1.0 / D.voxel;
+  } else {
+    const double* p = D.pts + ((size_t)c * D.nmax + i) * 4;
+    x = p[0]; y = p[1]; z = p[2];
+    inv = 1.0 / D.cell;
+  }
+  const unsigned long long key = point_key(x, y, z, inv);
+  int slot = -1;
+  if (key != KEY_EMPTY) {
+    const int hm = D.hsize - 1;
+    unsigned long long* keys = D.keys + (size_t)c * D.hsize;
+    int h = (int)(mix64(key) & hm);
+    while (true) {
+      const unsigned long long prev = atomicCAS(&keys[h], KEY_EMPTY, key);
+      if (prev == KEY_EMPTY || prev == key) break;
+      h = (h + 1) & hm;
+    }
+    slot = h;
+    atomicMin(&D.minIdx[(size_t)c * D.hsize + h], i);
+    atomicAdd(&D.count[(size_t)c * D.hsize + h], 1);
+    if (mode == 1) {
+      int* box = D.cellBox + c * 6;
+      const int cx = (int)(key & 0x1fffff), cy = (int)((key >> 21) & 0x1fffff), cz = (int)((key >> 42) & 0x1fffff);
+      atomicMin(&box[0], cx); atomicMin(&box[1], cy); atomicMin(&box[2], cz);
+      atomicMax(&box[3], cx); atomicMax(&box[4], cy); atomicMax(&box[5], cz);
+    }
+  }
+  D.slotOf[(size_t)c * D.nmax + i] = slot;
+}
+
+// One CTA per cloud: number the groups by first occurrence and lay their member lists out
+// contiguously (start = exclusive prefix of the group sizes in that order).
+__global__ void __launch_bounds__(1024) k_group_rank(GicpDev D, int mode, int* __restrict__ nGroups) {
+  __shared__ int s_a[32], s_b[32];
+  __shared__ int s_ca, s_cb;
+  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = mode == 0 ? D.nIn[c] : D.nDown[c];
+  const int* slotOf = D.slotOf + (size_t)c * D.nmax;
+  const size_t hb = (size_t)c * D.hsize;
+  if (tid == 0) { s_ca = 0; s_cb = 0; }
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    int lead = 0, cnt = 0, slot = -1;
+    if (i < n) {
+      slot = slotOf[i];
+      if (slot >= 0 && D.minIdx[hb + slot] == i) { lead = 1; cnt = D.count[hb + slot]; }
+    }
+    int a = lead, b = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int ta = __shfl_up_sync(0xffffffffu, a, o), tb = __shfl_up_sync(0xffffffffu, b, o);
+      if (lane >= o) { a += ta; b += tb; }
+    }
+    if (lane == 31) { s_a[warp] = a; s_b[warp] = b; }
+    __syncthreads();
+    if (warp == 0) {
+      int wa = s_a[lane], wb = s_b[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(0xffffffffu, wa, o), tb = __shfl_up_sync(0xffffffffu, wb, o);
+        if (lane >= o) { wa += ta; wb += tb; }
+      }
+      s_a[lane] = wa; s_b[lane] = wb;
+    }
+    __syncthreads();
+    const int pa = s_ca + (warp ? s_a[warp - 1] : 0) + a - lead;
+    const int pb = s_cb + (warp ? s_b[warp - 1] : 0) + b - cnt;
+    if (lead) { D.rank[hb + slot] = pa; D.start[hb + slot] = pb; }
+    __syncthreads();
+    if (tid == 0) { s_ca += s_a[31]; s_cb += s_b[31]; }
+    __syncthreads();
+  }
+  if (tid == 0) nGroups[c] = s_ca;
+}
+
+// One warp per cloud walks the points in input order and appends each to its group's member list;
+// lanes of one step that hit the same group are ordered by lane (= input order) via match_any.
+__global__ void __launch_bounds__(128) k_group_fill(GicpDev D, int mode, int clouds) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= clouds) return;
+  const int n = mode == 0 ? D.nIn[c] : D.nDown[c];
+  const int* slotOf = D.slotOf + (size_t)c * D.nmax;
+  int* members = D.members + (size_t)c * D.nmax;
+  const size_t hb = (size_t)c * D.hsize;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    const int slot = (i < n) ? slotOf[i] : -1;
+    const unsigned grp = __match_any_sync(0xffffffffu, slot);
+    if (slot >= 0) {
+      const int leader = __ffs(grp) - 1;
+      const int r = __popc(grp & ((1u << lane) - 1u));
+      int cur = 0;
+      if (lane == leader) cur = D.cursor[hb + slot];
+      cur = __shfl_sync(grp, cur, leader);
+      members[D.start[hb + slot] + cur + r] = i;
+      if (lane == leader) D.cursor[hb + slot] = cur + __popc(grp);
+    }
+    __syncwarp();
+  }
+}
+
+// voxelgrid_sampling: mean of each voxel's points, summed in input order (downsampling.hpp:60-75)
+__global__ void __launch_bounds__(256) k_voxel_mean(GicpDev D, const float* __restrict__ tgt, const float* __restrict__ src,
+                                                    int stride) {
+  const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D.nIn[c]) return;
+  const int slot = D.slotOf[(size_t)c * D.nmax + i];
+  if (slot < 0) return;
+  const size_t hb = (size_t)c * D.hsize;
+  if (D.minIdx[hb + slot] != i) return;
+  const float* base = ((c & 1) ? src : tgt) + (size_t)(c >> 1) * stride * 4;
+  const int* mem = D.members + (size_t)c * D.nmax + D.start[hb + slot];
+  const int cnt = D.count[hb + slot];
+  double sx = 0, sy = 0, sz = 0, w = 0;
+  for (int j = 0; j < cnt; j++) {
+    const float4 v = *reinterpret_cast<const float4*>(base + (size_t)mem[j] * 4);
+    sx += (double)v.x; sy += (double)v.y; sz += (double)v.z; w += 1.0;
+  }
+  double* o = D.pts + ((size_t)c * D.nmax + D.rank[hb + slot]) * 4;
+  o[0] = sx / w; o[1] = sy / w; o[2] = sz / w; o[3] = 1.0;
+}
+
+// ---- grid lookup
+struct Grid {
+  const unsigned long long* keys;
+  const int *count, *start, *members;
+  const double* pts;
+  int hm;
+};
+__device__ __forceinline__ Grid make_grid(const GicpDev& D, int c) {
+  Grid g;
+  g.keys = D.keys + (size_t)c * D.hsize;
+  g.count = D.count + (size_t)c * D.hsize;
+  g.start = D.start + (size_t)c * D.hsize;
+  g.members = D.members + (size_t)c * D.nmax;
+  g.pts = D.pts + (size_t)c * D.nmax * 4;
+  g.hm = D.hsize - 1;
+  return g;
+}
+__device__ __forceinline__ int grid_find(const Grid& g, int cx, int cy, int cz) {
+  if ((unsigned)cx > 0x1fffffu || (unsigned)cy > 0x1fffffu || (unsigned)cz > 0x1fffffu) return -1;
+  const unsigned long long key = (unsigned long long)cx | ((unsigned long long)cy << 21) | ((unsigned long long)cz << 42);
+  int h = (int)(mix64(key) & g.hm);
+  while (true) {
+    const unsigned long long k = g.keys[h];
+    if (k == key) return h;
+    if (k == KEY_EMPTY) return -1;
+    h = (h + 1) & g.hm;
+  }
+}
+__device__ __forceinline__ double sqdist3(const double* p, double qx, double qy, double qz) {
+  // Eigen Vector4d::squaredNorm with SSE2 packets: (dx^2 + dz^2) + dy^2
+  const double dx = p[0] - qx, dy = p[1] - qy, dz = p[2] - qz;
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz)), __dmul_rn(dy, dy));
+}
+
+// k nearest under the total order (distance, index): independent of the visiting order
+template <int K>
+struct KnnAcc {
+  double d[K];
+  int id[K];
+  int found;
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < K; i++) { d[i] = DBL_MAX; id[i] = 0x7fffffff; }
+    found = 0;
+  }
+  __device__ __forceinline__ void push(int index, double dist) {
+    if (dist > d[K - 1] || (dist == d[K - 1] && index >= id[K - 1])) return;
+    double cd = dist;
+    int ci = index;
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+      const bool before = cd < d[i] || (cd == d[i] && ci < id[i]);
+      if (before) {
+        const double td = d[i]; const int ti = id[i];
+        d[i] = cd; id[i] = ci;
+        cd = td; ci = ti;
+      }
+    }
+    if (found < K) found++;
+  }
+};
+
+template <int K>
+__device__ __forceinline__ void scan_cell(const Grid& g, int slot, double qx, double qy, double qz, KnnAcc<K>& acc) {
+  const int s = g.start[slot], n = g.count[slot];
+  for (int j = 0; j < n; j++) {
+    const int pi = g.members[s + j];
+    acc.push(pi, sqdist3(g.pts + (size_t)pi * 4, qx, qy, qz));
+  }
+}
+
+// Exact k-NN: shells of grid cells around the query until the k-th distance is provably final,
+// brute force over the cloud beyond MAX_SHELL.  If max_r2 >= 0 the search may stop as soon as no
+// unvisited point can be closer than sqrt(max_r2) (bounded 1-NN for correspondences).
+static const int MAX_SHELL = 4;
+template <int K>
+__device__ void grid_knn(const Grid& g, const int* box, int nPts, double cell, double qx, double qy, double qz,
+                         double max_r2, KnnAcc<K>& acc) {
+  acc.init();
+  const double inv = 1.0 / cell;
+  const int off = 1 << 20;
+  const int cx = fast_floor_d(qx * inv) + off, cy = fast_floor_d(qy * inv) + off, cz = fast_floor_d(qz * inv) + off;
+  // distance from the query to the nearest face of its own cell
+  const double fx = qx - (double)(cx - off) * cell, fy = qy - (double)(cy - off) * cell, fz = qz - (double)(cz - off) * cell;
+  double margin = fmin(fmin(fx, cell - fx), fmin(fmin(fy, cell - fy), fmin(fz, cell - fz)));
+  margin = fmax(margin, 0.0) * 0.999999;  // guard the bound against rounding in fx..fz
+  for (int r = 0; r <= MAX_SHELL; r++) {
+    const int x0 = max(cx - r, box[0]), x1 = min(cx + r, box[3]);
+    const int y0 = max(cy - r, box[1]), y1 = min(cy + r, box[4]);
+    const int z0 = max(cz - r, box[2]), z1 = min(cz + r, box[5]);
+    for (int z = z0; z <= z1; z++)
+      for (int y = y0; y <= y1; y++) {
+        const bool face = (z == cz - r) || (z == cz + r) || (y == cy - r) || (y == cy + r);
+        if (face) {
+          for (int x = x0; x <= x1; x++) {
+            const int s = grid_find(g, x, y, z);
+            if (s >= 0) scan_cell<K>(g, s, qx, qy, qz, acc);
+          }
+        } else {
+          if (cx - r >= x0) { const int s = grid_find(g, cx - r, y, z); if (s >= 0) scan_cell<K>(g, s, qx, qy, qz, acc); }
+          if (r > 0 && cx + r <= x1) { const int s = grid_find(g, cx + r, y, z); if (s >= 0) scan_cell<K>(g, s, qx, qy, qz, acc); }
+        }
+      }
+    const double bound = (double)r * cell + margin;  // every unvisited point is farther than this
+    const double b2 = bound * bound;
+    if (acc.found == K && acc.d[K - 1] <= b2) return;
+    if (max_r2 >= 0.0 && b2 >= max_r2) return;
+    // whole bounding box visited?
+    if (cx - r <= box[0] && cx + r >= box[3] && cy - r <= box[1] && cy + r >= box[4] && cz - r <= box[2] && cz + r >= box[5]) return;
+  }
+  // far / sparse query: exact brute force over the cloud
+  acc.init();
+  for (int i = 0; i < nPts; i++) acc.push(i, sqdist3(g.pts + (size_t)i * 4, qx, qy, qz));
+}
+
+// ---- Eigen SelfAdjointEigenSolver<Matrix3d>::computeDirect restated (see oracle/gicp_oracle.cpp)
+__device__ void sym3_roots(const double m[3][3], double roots[3]) {
+  const double s_inv3 = 1.0 / 3.0, s_sqrt3 = sqrt(3.0);
+  const double c0 = m[0][0] * m[1][1] * m[2][2] + 2.0 * m[1][0] * m[2][0] * m[2][1] - m[0][0] * m[2][1] * m[2][1] -
+                    m[1][1] * m[2][0] * m[2][0] - m[2][2] * m[1][0] * m[1][0];
+  const double c1 = m[0][0] * m[1][1] - m[1][0] * m[1][0] + m[0][0] * m[2][2] - m[2][0] * m[2][0] + m[1][1] * m[2][2] -
+                    m[2][1] * m[2][1];
+  const double c2 = m[0][0] + m[1][1] + m[2][2];
+  const double c2_over_3 = c2 * s_inv3;
+  double a_over_3 = (c2 * c2_over_3 - c1) * s_inv3;
+  a_over_3 = fmax(a_over_3, 0.0);
+  const double half_b = 0.5 * (c0 + c2_over_3 * (2.0 * c2_over_3 * c2_over_3 - c1));
+  double q = a_over_3 * a_over_3 * a_over_3 - half_b * half_b;
+  q = fmax(q, 0.0);
+  const double rho = sqrt(a_over_3);
+  const double theta = atan2(sqrt(q), half_b) * s_inv3;
+  double st, ct;
+  sincos(theta, &st, &ct);
+  roots[0] = c2_over_3 - rho * (ct + s_sqrt3 * st);
+  roots[1] = c2_over_3 - rho * (ct - s_sqrt3 * st);
+  roots[2] = c2_over_3 + 2.0 * rho * ct;
+}
+__device__ __forceinline__ void cross3(const double a[3], const double b[3], double c[3]) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ void extract_kernel(const double m[3][3], double res[3], double rep[3]) {
+  int i0 = 0;
+  double best = fabs(m[0][0]);
+  if (fabs(m[1][1]) > best) { best = fabs(m[1][1]); i0 = 1; }
+  if (fabs(m[2][2]) > best) { best = fabs(m[2][2]); i0 = 2; }
+  const int i1 = (i0 + 1) % 3, i2 = (i0 + 2) % 3;
+  double colA[3], colB[3];
+  for (int r = 0; r < 3; r++) { rep[r] = m[r][i0]; colA[r] = m[r][i1]; colB[r] = m[r][i2]; }
+  double c0[3], c1[3];
+  cross3(rep, colA, c0);
+  cross3(rep, colB, c1);
+  const double n0 = c0[0] * c0[0] + c0[1] * c0[1] + c0[2] * c0[2];
+  const double n1 = c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2];
+  if (n0 > n1) { const double s = sqrt(n0); for (int r = 0; r < 3; r++) res[r] = c0[r] / s; }
+  else { const double s = sqrt(n1); for (int r = 0; r < 3; r++) res[r] = c1[r] / s; }
+}
+__device__ void eig3_direct(const double A[3][3], double V[3][3]) {
+  const double eps = DBL_EPSILON;
+  double m[3][3], evals[3];
+  const double shift = (A[0][0] + A[1][1] + A[2][2]) / 3.0;
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) m[r][c] = (r >= c) ? A[r][c] : A[c][r];
+  for (int i = 0; i < 3; i++) m[i][i] -= shift;
+  double scale = 0;
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) scale = fmax(scale, fabs(m[r][c]));
+  if (scale > 0)
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) m[r][c] /= scale;
+  sym3_roots(m, evals);
+  double v[3][3];
+  if ((evals[2] - evals[0]) <= eps) {
+    for (int k = 0; k < 3; k++)
+      for (int r = 0; r < 3; r++) v[k][r] = (k == r) ? 1.0 : 0.0;
+  } else {
+    double tmp[3][3];
+    double d0 = evals[2] - evals[1], d1 = evals[1] - evals[0];
+    int k = 0, l = 2;
+    if (d0 > d1) { k = 2; l = 0; d0 = d1; }
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) tmp[r][c] = m[r][c];
+    for (int i = 0; i < 3; i++) tmp[i][i] -= evals[k];
+    extract_kernel(tmp, v[k], v[l]);
+    if (d0 <= 2 * eps * d1) {
+      const double dot = v[k][0] * v[l][0] + v[k][1] * v[l][1] + v[k][2] * v[l][2];
+      for (int r = 0; r < 3; r++) v[l][r] -= dot * v[l][r];
+      const double nn = sqrt(v[l][0] * v[l][0] + v[l][1] * v[l][1] + v[l][2] * v[l][2]);
+      for (int r = 0; r < 3; r++) v[l][r] /= nn;
+    } else {
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) tmp[r][c] = m[r][c];
+      for (int i = 0; i < 3; i++) tmp[i][i] -= evals[l];
+      double dummy[3];
+      extract_kernel(tmp, v[l], dummy);
+    }
+    double c[3];
+    cross3(v[2], v[0], c);
+    const double nn = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+    for (int r = 0; r < 3; r++) v[1][r] = c[r] / nn;
+  }
+  for (int k = 0; k < 3; k++)
+    for (int r = 0; r < 3; r++) V[r][k] = v[k][r];
+}
+
+// estimate_local_features<CovarianceSetter> (normal_estimation.hpp:66-92), K = 10
+__global__ void __launch_bounds__(128) k_knn_cov(GicpDev D) {
+  const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = D.nDown[c];
+  if (i >= n) return;
+  const Grid g = make_grid(D, c);
+  const double* q = g.pts + (size_t)i * 4;
+  KnnAcc<10> acc;
+  grid_knn<10>(g, D.cellBox + c * 6, n, D.cell, q[0], q[1], q[2], -1.0, acc);
+  double* out = D.cov + ((size_t)c * D.nmax + i) * 6;
+  const int nf = acc.found;
+  if (nf < 5) {
+    out[0] = 1; out[1] = 0; out[2] = 0; out[3] = 1; out[4] = 0; out[5] = 1;
+    return;
+  }
+  double s[3] = {0, 0, 0}, cr[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int j = 0; j < nf; j++) {
+    const double* p = g.pts + (size_t)acc.id[j] * 4;
+    const double v[3] = {p[0], p[1], p[2]};
+    for (int a = 0; a < 3; a++) {
+      s[a] += v[a];
+      for (int b = 0; b < 3; b++) cr[a][b] += v[a] * v[b];
+    }
+  }
+  double C[3][3], V[3][3];
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) C[a][b] = (cr[a][b] - (s[a] / nf) * s[b]) / nf;
+  eig3_direct(C, V);
+  const double val[3] = {1e-3, 1.0, 1.0};
+  double R[3][3];
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) {
+      double t = 0;
+      for (int k = 0; k < 3; k++) t += (V[a][k] * val[k]) * V[b][k];
+      R[a][b] = t;
+    }
+  out[0] = R[0][0]; out[1] = R[0][1]; out[2] = R[0][2]; out[3] = R[1][1]; out[4] = R[1][2]; out[5] = R[2][2];
+}
+
+// ---- block reduction of NV doubles per thread into out[NV] (fixed order: lanes, then warps)
+template <int NV, int THREADS>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* out) {
+  __shared__ double s_red[THREADS / 32][NV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    double x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) s_red[warp][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double x = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; w++) x += s_red[w][threadIdx.x];
+    out[threadIdx.x] = x;
+  }
+}
+
+__device__ __forceinline__ void xform(const double* T, const double* p, double o[3]) {
+  // T: rows of [R | t], 12 doubles
+  for (int r = 0; r < 3; r++) o[r] = ((T[4 * r] * p[0] + T[4 * r + 1] * p[1]) + T[4 * r + 2] * p[2]) + T[4 * r + 3];
+}
+
+static const int LIN_THREADS = 128;
+// GICPFactor::linearize for every source point of every active pair + partial sums
+__global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D) {
+  const int p = blockIdx.y;
+  if (!D.istate[p * LM_ISTATE + I_ACTIVE]) return;
+  const int ct = 2 * p, cs = 2 * p + 1;
+  const int ns = D.nDown[cs];
+  const int i = blockIdx.x * LIN_THREADS + threadIdx.x;
+  double acc[RED_N];
+#pragma unroll
+  for (int k = 0; k < RED_N; k++) acc[k] = 0.0;
+  if (i < ns) {
+    const double* T = D.state + (size_t)p * LM_STATE + S_T;
+    const double* ps = D.pts + ((size_t)cs * D.nmax + i) * 4;
+    double q[3];
+    xform(T, ps, q);
+    const Grid g = make_grid(D, ct);
+    KnnAcc<1> nn;
+    const double max_d2 = D.max_dist * D.max_dist;
+    grid_knn<1>(g, D.cellBox + ct * 6, D.nDown[ct], D.cell, q[0], q[1], q[2], max_d2 * 1.0000001, nn);
+    int tgt = -1;
+    if (nn.found == 1 && !(nn.d[0] > max_d2)) tgt = nn.id[0];  // DistanceRejector: sq_dist > max_dist_sq
+    D.corr[(size_t)p * D.nmax + i] = tgt;
+    if (tgt >= 0) {
+      const double* cS = D.cov + ((size_t)cs * D.nmax + i) * 6;
+      const double* cT = D.cov + ((size_t)ct * D.nmax + tgt) * 6;
+      const double Cs[3][3] = {{cS[0], cS[1], cS[2]}, {cS[1], cS[3], cS[4]}, {cS[2], cS[4], cS[5]}};
+      const double Ct[3][3] = {{cT[0], cT[1], cT[2]}, {cT[1], cT[3], cT[4]}, {cT[2], cT[4], cT[5]}};
+      double R[3][3];
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) R[r][c] = T[4 * r + c];
+      double RC[3][3], A[3][3];
+      for (int r = 0; r < 3; r++)
+        for (int k = 0; k < 3; k++) RC[r][k] = R[r][0] * Cs[0][k] + R[r][1] * Cs[1][k] + R[r][2] * Cs[2][k];
+      for (int r = 0; r < 3; r++)
+        for (int k = 0; k < 3; k++) A[r][k] = Ct[r][k] + (RC[r][0] * R[k][0] + RC[r][1] * R[k][1] + RC[r][2] * R[k][2]);
+      // 3x3 inverse by cofactors
+      const double c00 = A[1][1] * A[2][2] - A[1][2] * A[2][1], c01 = A[1][2] * A[2][0] - A[1][0] * A[2][2],
+                   c02 = A[1][0] * A[2][1] - A[1][1] * A[2][0];
+      const double id = 1.0 / (A[0][0] * c00 + A[0][1] * c01 + A[0][2] * c02);
+      double M[3][3];
+      M[0][0] = c00 * id; M[1][0] = c01 * id; M[2][0] = c02 * id;
+      M[0][1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) * id;
+      M[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) * id;
+      M[2][1] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) * id;
+      M[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) * id;
+      M[1][2] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) * id;
+      M[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) * id;
+      double* mo = D.maha + ((size_t)p * D.nmax + i) * 9;
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) mo[3 * r + c] = M[r][c];
+      const double* pt = g.pts + (size_t)tgt * 4;
+      const double res[3] = {pt[0] - q[0], pt[1] - q[1], pt[2] - q[2]};
+      const double S[3][3] = {{0, -ps[2], ps[1]}, {ps[2], 0, -ps[0]}, {-ps[1], ps[0], 0}};
+      double J[3][6];
+      for (int r = 0; r < 3; r++)
+        for (int k = 0; k < 3; k++) {
+          J[r][k] = R[r][0] * S[0][k] + R[r][1] * S[1][k] + R[r][2] * S[2][k];
+          J[r][3 + k] = -R[r][k];
+        }
+      double MJ[3][6], Mr[3];
+      for (int r = 0; r < 3; r++) {
+        for (int k = 0; k < 6; k++) MJ[r][k] = M[r][0] * J[0][k] + M[r][1] * J[1][k] + M[r][2] * J[2][k];
+        Mr[r] = M[r][0] * res[0] + M[r][1] * res[1] + M[r][2] * res[2];
+      }
+      int n = 0;
+#pragma unroll
+      for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int b = a; b < 6; b++) acc[n++] = J[0][a] * MJ[0][b] + J[1][a] * MJ[1][b] + J[2][a] * MJ[2][b];
+#pragma unroll
+      for (int a = 0; a < 6; a++) acc[21 + a] = J[0][a] * Mr[0] + J[1][a] * Mr[1] + J[2][a] * Mr[2];
+      acc[27] = 0.5 * (res[0] * Mr[0] + res[1] * Mr[1] + res[2] * Mr[2]);
+      acc[28] = 1.0;
+    }
+  }
+  block_reduce_store<RED_N, LIN_THREADS>(acc, D.partial + ((size_t)p * D.nblk + blockIdx.x) * RED_N);
+}
+
+// GICPFactor::error with the stored correspondences / Mahalanobis matrices
+__global__ void __launch_bounds__(LIN_THREADS) k_error(GicpDev D) {
+  const int p = blockIdx.y;
+  if (!D.istate[p * LM_ISTATE + I_NEED]) return;
+  const int ct = 2 * p, cs = 2 * p + 1;
+  const int ns = D.nDown[cs];
+  const int i = blockIdx.x * LIN_THREADS + threadIdx.x;
+  double acc[1] = {0.0};
+  if (i < ns) {
+    const int tgt = D.corr[(size_t)p * D.nmax + i];
+    if (tgt >= 0) {
+      const double* T = D.state + (size_t)p * LM_STATE + S_NEWT;
+      const double* ps = D.pts + ((size_t)cs * D.nmax + i) * 4;
+      double q[3];
+      xform(T, ps, q);
+      const double* pt = D.pts + ((size_t)ct * D.nmax + tgt) * 4;
+      const double res[3] = {pt[0] - q[0], pt[1] - q[1], pt[2] - q[2]};
+      const double* M = D.maha + ((size_t)p * D.nmax + i) * 9;
+      double Mr[3];
+      for (int r = 0; r < 3; r++) Mr[r] = M[3 * r] * res[0] + M[3 * r + 1] * res[1] + M[3 * r + 2] * res[2];
+      acc[0] = 0.5 * (res[0] * Mr[0] + res[1] * Mr[1] + res[2] * Mr[2]);
+    }
+  }
+  block_reduce_store<1, LIN_THREADS>(acc, D.partialE + (size_t)p * D.nblk + blockIdx.x);
+}
+
+// ---- 6x6 LDL^T solve, se3_exp, compose (one thread)
+__device__ void ldlt_solve6(const double Hin[6][6], const double rhs[6], double x[6]) {
+  double L[6][6], Dg[6];
+  for (int a = 0; a < 6; a++)
+    for (int b = 0; b < 6; b++) L[a][b] = 0;
+  for (int j = 0; j < 6; j++) {
+    double d = Hin[j][j];
+    for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k] * Dg[k];
+    Dg[j] = d;
+    L[j][j] = 1;
+    for (int i = j + 1; i < 6; i++) {
+      double v = Hin[i][j];
+      for (int k = 0; k < j; k++) v -= L[i][k] * L[j][k] * Dg[k];
+      L[i][j] = v / d;
+    }
+  }
+  double y[6];
+  for (int i = 0; i < 6; i++) {
+    double v = rhs[i];
+    for (int k = 0; k < i; k++) v -= L[i][k] * y[k];
+    y[i] = v;
+  }
+  for (int i = 0; i < 6; i++) y[i] /= Dg[i];
+  for (int i = 5; i >= 0; i--) {
+    double v = y[i];
+    for (int k = i + 1; k < 6; k++) v -= L[k][i] * x[k];
+    x[i] = v;
+  }
+}
+__device__ void se3_exp_dev(const double a[6], double T[12]) {  // util/lie.hpp:52-96
+  const double w[3] = {a[0], a[1], a[2]};
+  const double theta_sq = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  double imag, real;
+  if (theta_sq < 1e-10) {
+    const double tq = theta_sq * theta_sq;
+    imag = 0.5 - 1.0 / 48.0 * theta_sq + 1.0 / 3840.0 * tq;
+    real = 1.0 - 1.0 / 8.0 * theta_sq + 1.0 / 384.0 * tq;
+  } else {
+    const double theta = sqrt(theta_sq), half = 0.5 * theta;
+    imag = sin(half) / theta;
+    real = cos(half);
+  }
+  const double qw = real, qx = imag * w[0], qy = imag * w[1], qz = imag * w[2];
+  const double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
+  const double twx = tx * qw, twy = ty * qw, twz = tz * qw, txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy,
+               tyz = tz * qy, tzz = tz * qz;
+  double R[3][3];
+  R[0][0] = 1 - (tyy + tzz); R[0][1] = txy - twz; R[0][2] = txz + twy;
+  R[1][0] = txy + twz; R[1][1] = 1 - (txx + tzz); R[1][2] = tyz - twx;
+  R[2][0] = txz - twy; R[2][1] = tyz + twx; R[2][2] = 1 - (txx + tyy);
+  const double theta = sqrt(theta_sq);
+  const double tr[3] = {a[3], a[4], a[5]};
+  double t[3];
+  if (theta < 1e-10) {
+    for (int r = 0; r < 3; r++) t[r] = R[r][0] * tr[0] + R[r][1] * tr[1] + R[r][2] * tr[2];
+  } else {
+    const double O[3][3] = {{0, -w[2], w[1]}, {w[2], 0, -w[0]}, {-w[1], w[0], 0}};
+    const double k1 = (1.0 - cos(theta)) / theta_sq, k2 = (theta - sin(theta)) / (theta_sq * theta);
+    for (int r = 0; r < 3; r++) {
+      double Vr[3];
+      for (int c = 0; c < 3; c++) {
+        double oo = 0;
+        for (int k = 0; k < 3; k++) oo += O[r][k] * O[k][c];
+        Vr[c] = (r == c ? 1.0 : 0.0) + k1 * O[r][c] + k2 * oo;
+      }
+      t[r] = Vr[0] * tr[0] + Vr[1] * tr[1] + Vr[2] * tr[2];
+    }
+  }
+  for (int r = 0; r < 3; r++) { T[4 * r] = R[r][0]; T[4 * r + 1] = R[r][1]; T[4 * r + 2] = R[r][2]; T[4 * r + 3] = t[r]; }
+}
+__device__ void compose12(const double* A, const double* B, double* C) {
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) C[4 * r + c] = A[4 * r] * B[c] + A[4 * r + 1] * B[4 + c] + A[4 * r + 2] * B[8 + c];
+    C[4 * r + 3] = A[4 * r] * B[3] + A[4 * r + 1] * B[7] + A[4 * r + 2] * B[11] + A[4 * r + 3];
+  }
+}
+// delta = (H + lambda I)^-1 (-b); newT = T * se3_exp(delta)       (optimizer.hpp:107-112)
+__device__ void lm_trial(double* st) {
+  double H[6][6], nb[6], delta[6];
+  int n = 0;
+  for (int a = 0; a < 6; a++)
+    for (int b = a; b < 6; b++) { H[a][b] = H[b][a] = st[S_H + n]; n++; }
+  for (int a = 0; a < 6; a++) { H[a][a] += st[S_LAMBDA]; nb[a] = -st[S_B + a]; }
+  ldlt_solve6(H, nb, delta);
+  double dT[12];
+  se3_exp_dev(delta, dT);
+  compose12(st + S_T, dT, st + S_NEWT);
+  for (int a = 0; a < 6; a++) st[S_DELTA + a] = delta[a];
+}
+
+// one warp per pair: sum the partials in block order (lane v owns value v), start the first trial
+__global__ void __launch_bounds__(32) k_lm_begin(GicpDev D, int iter) {
+  const int p = blockIdx.x, lane = threadIdx.x;
+  int* is = D.istate + p * LM_ISTATE;
+  if (!is[I_ACTIVE]) return;
+  double* st = D.state + (size_t)p * LM_STATE;
+  const int nb = (D.nDown[2 * p + 1] + LIN_THREADS - 1) / LIN_THREADS;
+  double s = 0;
+  if (lane < RED_N)
+    for (int b = 0; b < nb; b++) s += D.partial[((size_t)p * D.nblk + b) * RED_N + lane];
+  if (lane < 21) st[S_H + lane] = s;
+  else if (lane < 27) st[S_B + lane - 21] = s;
+  else if (lane == 27) st[S_E] = s;
+  else if (lane == 28) is[I_INL] = (int)(s + 0.5);
+  __syncwarp();
+  if (lane == 0) {
+    is[I_ITER] = iter;
+    is[I_TRIAL] = 0;
+    is[I_SUCCESS] = 0;
+    is[I_NEED] = 1;
+    lm_trial(st);
+    atomicAdd(&D.counters[0], 1);
+  }
+}
+
+// one warp per pair: new_e, accept / reject, next trial or end of the outer iteration (:114-143)
+__global__ void __launch_bounds__(32) k_lm_decide(GicpDev D, int iter) {
+  const int p = blockIdx.x, lane = threadIdx.x;
+  int* is = D.istate + p * LM_ISTATE;
+  if (!is[I_NEED]) return;
+  double* st = D.state + (size_t)p * LM_STATE;
+  const int nb = (D.nDown[2 * p + 1] + LIN_THREADS - 1) / LIN_THREADS;
+  // fixed-order sum: lane-strided partial sums are NOT order-preserving, so lane 0 sums serially
+  double new_e = 0;
+  if (lane == 0) {
+    for (int b = 0; b < nb; b++) new_e += D.partialE[(size_t)p * D.nblk + b];
+    is[I_INNER]++;
+    if (new_e <= st[S_E]) {
+      const double* d = st + S_DELTA;
+      const double dr = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      const double dt = sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
+      is[I_CONV] = (dr <= D.rot_eps && dt <= D.trans_eps) ? 1 : 0;
+      for (int k = 0; k < 12; k++) st[S_T + k] = st[S_NEWT + k];
+      st[S_LAMBDA] /= 10.0;
+      is[I_SUCCESS] = 1;
+      is[I_NEED] = 0;
+    } else {
+      st[S_LAMBDA] *= 10.0;
+      is[I_TRIAL]++;
+      if (is[I_TRIAL] >= 10) is[I_NEED] = 0;
+      else { lm_trial(st); atomicAdd(&D.counters[0], 1); }
+    }
+    if (!is[I_NEED]) {  // the outer iteration is over for this pair
+      if (!is[I_SUCCESS] || is[I_CONV] || iter + 1 >= D.max_iter) is[I_ACTIVE] = 0;
+      else atomicAdd(&D.counters[1], 1);
+    }
+  }
+}
+
+__global__ void k_lm_init(GicpDev D, int pairs, const double* __restrict__ T0) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pairs) return;
+  double* st = D.state + (size_t)p * LM_STATE;
+  for (int k = 0; k < LM_STATE; k++) st[k] = 0;
+  for (int k = 0; k < 12; k++) st[S_T + k] = T0[(size_t)p * 16 + k];
+  st[S_LAMBDA] = 1e-3;
+  int* is = D.istate + p * LM_ISTATE;
+  for (int k = 0; k < LM_ISTATE; k++) is[k] = 0;
+  is[I_ACTIVE] = D.max_iter > 0 ? 1 : 0;
+}
+
+__global__ void k_gicp_result(GicpDev D, int pairs, GfsGicpResult* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pairs) return;
+  const double* st = D.state + (size_t)p * LM_STATE;
+  const int* is = D.istate + p * LM_ISTATE;
+  GfsGicpResult r;
+  for (int k = 0; k < 12; k++) r.T[k] = st[S_T + k];
+  r.T[12] = r.T[13] = r.T[14] = 0; r.T[15] = 1;
+  int n = 0;
+  for (int a = 0; a < 6; a++)
+    for (int b = a; b < 6; b++) { r.H[6 * a + b] = r.H[6 * b + a] = st[S_H + n]; n++; }
+  for (int a = 0; a < 6; a++) r.b[a] = st[S_B + a];
+  r.error = st[S_E];
+  r.iterations = is[I_ITER];
+  r.num_inliers = is[I_INL];
+  r.converged = is[I_CONV];
+  r.n_target = D.nDown[2 * p];
+  r.n_source = D.nDown[2 * p + 1];
+  r.inner_evals = is[I_INNER];
+  out[p] = r;
+}
+
+__global__ void k_set_counts(GicpDev D, int pairs, const int* __restrict__ nt, const int* __restrict__ ns) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pairs) return;
+  D.nIn[2 * p] = min(nt[p], D.nmax);
+  D.nIn[2 * p + 1] = min(ns[p], D.nmax);
+}
+
+}  // namespace gfs
+
+using namespace gfs;
+
+struct GfsGicp {
+  GicpDev dev;
+  int maxPairs = 0;
+  DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_box, b_pts, b_cov,
+      b_corr, b_maha, b_partial, b_partialE, b_state, b_istate, b_counters;
+  DevBuf b_tgt, b_src, b_n, b_T0, b_res;
+  PinnedBuf h_counters;
+  int launches = 0;
+};
+
+extern "C" {
+
+void gfs_gicp_default_setting(GfsGicpSetting* s) {
+  if (!s) return;
+  s->downsampling_resolution = 0.02;      // RegistrationGICP.cc:11
+  s->max_correspondence_distance = 0.1;   // RegistrationGICP.cc:12-14
+  s->rotation_eps = 0.1 * M_PI / 180.0;   // registration_helper.hpp:44
+  s->translation_eps = 1e-3;              // :45
+  s->num_neighbors = 10;                  // registration_helper.cpp:59-60
+  s->max_iterations = 20;                 // registration_helper.hpp:47
+  s->num_threads = 4;                     // RegistrationGICP.cc:10 (ignored on the GPU)
+}
+
+int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs, GfsGicp** out) {
+  GFS_REQUIRE(out, GFS_ERR_INVALID, "out is null");
+  *out = nullptr;
+  GFS_REQUIRE(max_points > 0 && max_pairs > 0, GFS_ERR_INVALID, "bad capacity");
+  GfsGicpSetting s;
+  gfs_gicp_default_setting(&s);
+  if (setting) s = *setting;
+  GFS_REQUIRE(s.downsampling_resolution > 0 && s.max_correspondence_distance > 0 && s.max_iterations >= 0, GFS_ERR_INVALID,
+              "bad setting");
+  GFS_REQUIRE(s.num_neighbors == 10, GFS_ERR_INVALID, "num_neighbors must be 10 (the value align() hard-codes)");
+  int rc = gfs_device_check();
+  if (rc) return rc;
+  GfsGicp* h = new GfsGicp();
+  GicpDev& D = h->dev;
+  memset(&D, 0, sizeof(D));
+  D.nmax = max_points;
+  int hs = 64;
+  while (hs < 2 * max_points) hs <<= 1;
+  D.hsize = hs;
+  D.nblk = div_up(max_points, LIN_THREADS);
+  D.voxel = s.downsampling_resolution;
+  // grid cell: half the correspondence radius, but never finer than 2.5 voxels (10-NN radius)
+  D.cell = std::max(0.5 * s.max_correspondence_distance, 2.5 * s.downsampling_resolution);
+  D.max_dist = s.max_correspondence_distance;
+  D.rot_eps = s.rotation_eps;
+  D.trans_eps = s.translation_eps;
+  D.k = s.num_neighbors;
+  D.max_iter = s.max_iterations;
+  h->maxPairs = max_pairs;
+  const size_t C = 2 * (size_t)max_pairs, P = max_pairs, N = max_points, H = hs;
+#define RES(buf, bytes, field, type)            \
+  if ((rc = h->buf.reserve(bytes))) {           \
+    delete h;                                   \
+    return rc;                                  \
+  }                                             \
+  D.field = (type)h->buf.p;
+  RES(b_keys, C * H * 8, keys, unsigned long long*)
+  RES(b_minIdx, C * H * 4, minIdx, int*)
+  RES(b_count, C * H * 4, count, int*)
+  RES(b_start, C * H * 4, start, int*)
+  RES(b_cursor, C * H * 4, cursor, int*)
+  RES(b_rank, C * H * 4, rank, int*)
+  RES(b_slotOf, C * N * 4, slotOf, int*)
+  RES(b_members, C * N * 4, members, int*)
+  RES(b_nIn, C * 4, nIn, int*)
+  RES(b_nDown, C * 4, nDown, int*)
+  RES(b_nCells, C * 4, nCells, int*)
+  RES(b_box, C * 6 * 4, cellBox, int*)
+  RES(b_pts, C * N * 32, pts, double*)
+  RES(b_cov, C * N * 48, cov, double*)
+  RES(b_corr, P * N * 4, corr, int*)
+  RES(b_maha, P * N * 72, maha, double*)
+  RES(b_partial, P * D.nblk * RED_N * 8, partial, double*)
+  RES(b_partialE, P * D.nblk * 8, partialE, double*)
+  RES(b_state, P * LM_STATE * 8, state, double*)
+  RES(b_istate, P * LM_ISTATE * 4, istate, int*)
+  RES(b_counters, 16, counters, int*)
+#undef RES
+  if ((rc = h->h_counters.reserve(16))) { delete h; return rc; }
+  *out = h;
+  return GFS_OK;
+}
+
+int gfs_gicp_destroy(GfsGicp* h) {
+  if (!h) return GFS_OK;
+  DevBuf* d[] = {&h->b_keys, &h->b_minIdx, &h->b_count, &h->b_start, &h->b_cursor, &h->b_rank, &h->b_slotOf, &h->b_members,
+                 &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_box, &h->b_pts, &h->b_cov, &h->b_corr, &h->b_maha, &h->b_partial,
+                 &h->b_partialE, &h->b_state, &h->b_istate, &h->b_counters, &h->b_tgt, &h->b_src, &h->b_n, &h->b_T0, &h->b_res};
+  for (DevBuf* b : d) b->release();
+  h->h_counters.release();
+  delete h;
+  return GFS_OK;
+}
+
+int gfs_gicp_last_launches(const GfsGicp* h) { return h ? h->launches : GFS_ERR_INVALID; }
+
+static int group_build(GfsGicp* h, cudaStream_t st, int mode, int clouds, const float* tgt, const float* src, int stride,
+                       int* nGroupsOut) {
+  const GicpDev& D = h->dev;
+  const long long slots = (long long)clouds * D.hsize;
+  k_group_clear<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(D, clouds);
+  k_group_insert<<<dim3(div_up(D.nmax, 256), clouds), 256, 0, st>>>(D, mode, tgt, src, stride);
+  k_group_rank<<<clouds, 1024, 0, st>>>(D, mode, nGroupsOut);
+  k_group_fill<<<div_up(clouds, 4), 128, 0, st>>>(D, mode, clouds);
+  h->launches += 4;
+  return GFS_OK;
+}
+
+int gfs_gicp_align_batch_device(GfsGicp* h, void* stream, const float* d_target, const int* d_nt, const float* d_source,
+                                const int* d_ns, int pairs, int stride, const double* d_T0, GfsGicpResult* d_out) {
+  GFS_REQUIRE(h, GFS_ERR_INVALID, "null handle");
+  GFS_REQUIRE(d_target && d_nt && d_source && d_ns && d_T0 && d_out, GFS_ERR_INVALID, "null pointer");
+  GFS_REQUIRE(pairs > 0 && pairs <= h->maxPairs, GFS_ERR_CAPACITY, "pairs exceeds the handle's max_pairs");
+  GFS_REQUIRE(stride > 0 && stride <= h->dev.nmax, GFS_ERR_CAPACITY, "stride exceeds the handle's max_points");
+  cudaStream_t st = (cudaStream_t)stream;
+  const GicpDev& D = h->dev;
+  const int clouds = 2 * pairs;
+  h->launches = 0;
+  k_set_counts<<<div_up(pairs, 128), 128, 0, st>>>(D, pairs, d_nt, d_ns);
+  group_build(h, st, 0, clouds, d_target, d_source, stride, D.nDown);
+  k_voxel_mean<<<dim3(div_up(D.nmax, 256), clouds), 256, 0, st>>>(D, d_target, d_source, stride);
+  // grid over the downsampled points (reuses the hash-table storage); group count is not needed
+  group_build(h, st, 1, clouds, nullptr, nullptr, 0, D.nCells);
+  k_knn_cov<<<dim3(div_up(D.nmax, 128), clouds), 128, 0, st>>>(D);
+  k_lm_init<<<div_up(pairs, 128), 128, 0, st>>>(D, pairs, d_T0);
+  h->launches += 4;
+  GFS_CUDA(cudaGetLastError());
+  int* hc = (int*)h->h_counters.p;
+  for (int it = 0; it < D.max_iter; it++) {
+    GFS_CUDA(cudaMemsetAsync(D.counters, 0, 8, st));
+    k_linearize<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D);
+    k_lm_begin<<<pairs, 32, 0, st>>>(D, it);
+    h->launches += 2;
+    for (int j = 0; j < 10; j++) {
+      k_error<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D);
+      GFS_CUDA(cudaMemsetAsync(D.counters, 0, 4, st));
+      k_lm_decide<<<pairs, 32, 0, st>>>(D, it);
+      h->launches += 2;
+      GFS_CUDA(cudaMemcpyAsync(hc, D.counters, 8, cudaMemcpyDeviceToHost, st));
+      GFS_CUDA(cudaStreamSynchronize(st));
+      if (hc[0] == 0) break;  // no pair needs another lambda trial
+    }
+    if (hc[1] == 0) break;  // every pair converged / failed / hit max_iterations
+  }
+  k_gicp_result<<<div_up(pairs, 128), 128, 0, st>>>(D, pairs, d_out);
+  h->launches += 1;
+  GFS_CUDA(cudaGetLastError());
+  return GFS_OK;
+}
+
+int gfs_gicp_align_batch(GfsGicp* h, void* stream, const float* target, const int* nt, const float* source, const int* ns,
+                         int pairs, int stride, const double* T0, GfsGicpResult* out) {
+  GFS_REQUIRE(h, GFS_ERR_INVALID, "null handle");
+  GFS_REQUIRE(target && nt && source && ns && T0 && out, GFS_ERR_INVALID, "null pointer");
+  GFS_REQUIRE(pairs > 0 && pairs <= h->maxPairs, GFS_ERR_CAPACITY, "pairs exceeds the handle's max_pairs");
+  GFS_REQUIRE(stride > 0 && stride <= h->dev.nmax, GFS_ERR_CAPACITY, "stride exceeds the handle's max_points");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t P = pairs, cb = P * stride * 16;
+  int rc;
+  if ((rc = h->b_tgt.reserve(cb))) return rc;
+  if ((rc = h->b_src.reserve(cb))) return rc;
+  if ((rc = h->b_n.reserve(P * 8))) return rc;
+  if ((rc = h->b_T0.reserve(P * 128))) return rc;
+  if ((rc = h->b_res.reserve(P * sizeof(GfsGicpResult)))) return rc;
+  GFS_CUDA(cudaMemcpyAsync(h->b_tgt.p, target, cb, cudaMemcpyHostToDevice, st));
+  GFS_CUDA(cudaMemcpyAsync(h->b_src.p, source, cb, cudaMemcpyHostToDevice, st));
+  GFS_CUDA(cudaMemcpyAsync(h->b_n.p, nt, P * 4, cudaMemcpyHostToDevice, st));
+  GFS_CUDA(cudaMemcpyAsync((int*)h->b_n.p + P, ns, P * 4, cudaMemcpyHostToDevice, st));
+  GFS_CUDA(cudaMemcpyAsync(h->b_T0.p, T0, P * 128, cudaMemcpyHostToDevice, st));
+  rc = gfs_gicp_align_batch_device(h, stream, (const float*)h->b_tgt.p, (const int*)h->b_n.p, (const float*)h->b_src.p,
+                                   (const int*)h->b_n.p + P, pairs, stride, (const double*)h->b_T0.p,
+                                   (GfsGicpResult*)h->b_res.p);
+  if (rc) return rc;
+  GFS_CUDA(cudaMemcpyAsync(out, h->b_res.p, P * sizeof(GfsGicpResult), cudaMemcpyDeviceToHost, st));
+  GFS_CUDA(cudaStreamSynchronize(st));
+  return GFS_OK;
+}
+
+int gfs_gicp_align(GfsGicp* h, void* stream, const float* target, int nt, const float* source, int ns, const double* T0,
+                   GfsGicpResult* out) {
+  GFS_REQUIRE(h && out, GFS_ERR_INVALID, "null handle/output");
+  GFS_REQUIRE(nt >= 0 && ns >= 0 && nt <= h->dev.nmax && ns <= h->dev.nmax, GFS_ERR_CAPACITY, "cloud larger than max_points");
+  GFS_REQUIRE((target || nt == 0) && (source || ns == 0) && T0, GFS_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int stride = std::max(std::max(nt, ns), 1);
+  int rc;
+  if ((rc = h->b_tgt.reserve((size_t)stride * 16))) return rc;
+  if ((rc = h->b_src.reserve((size_t)stride * 16))) return rc;
+  if ((rc = h->b_n.reserve(8))) return rc;
+  if ((rc = h->b_T0.reserve(128))) return rc;
+  if ((rc = h->b_res.reserve(sizeof(GfsGicpResult)))) return rc;
+  if (nt) GFS_CUDA(cudaMemcpyAsync(h->b_tgt.p, target, (size_t)nt * 16, cudaMemcpyHostToDevice, st));
+  if (ns) GFS_CUDA(cudaMemcpyAsync(h->b_src.p, source, (size_t)ns * 16, cudaMemcpyHostToDevice, st));
+  const int n2[2] = {nt, ns};
+  GFS_CUDA(cudaMemcpyAsync(h->b_n.p, n2, 8, cudaMemcpyHostToDevice, st));
+  GFS_CUDA(cudaMemcpyAsync(h->b_T0.p, T0, 128, cudaMemcpyHostToDevice, st));
+  rc = gfs_gicp_align_batch_device(h, stream, (const float*)h->b_tgt.p, (const int*)h->b_n.p, (const float*)h->b_src.p,
+                                   (const int*)h->b_n.p + 1, 1, stride, (const double*)h->b_T0.p, (GfsGicpResult*)h->b_res.p);
+  if (rc) return rc;
+  GFS_CUDA(cudaMemcpyAsync(out, h->b_res.p, sizeof(GfsGicpResult), cudaMemcpyDeviceToHost, st));
+  GFS_CUDA(cudaStreamSynchronize(st));
+  return GFS_OK;
+}
+
+// Parity hook: downsampled points (xyz) and covariances (xx xy xz yy yz zz) of one cloud of the last
+// batch (cloud = 2*pair for the target, 2*pair+1 for the source), copied to the host.
+int gfs_gicp_get_cloud(GfsGicp* h, void* stream, int cloud, double* out_xyz, double* out_cov6, int cap, int* n) {
+  GFS_REQUIRE(h && n && cloud >= 0 && cloud < 2 * h->maxPairs, GFS_ERR_INVALID, "bad handle/cloud");
+  cudaStream_t st = (cudaStream_t)stream;
+  GFS_CUDA(cudaStreamSynchronize(st));
+  int m = 0;
+  GFS_CUDA(cudaMemcpy(&m, h->dev.nDown + cloud, 4, cudaMemcpyDeviceToHost));
+  *n = m;
+  const int k = std::min(m, cap);
+  if (k > 0 && out_xyz) {
+    std::vector<double> tmp((size_t)k * 4);
+    GFS_CUDA(cudaMemcpy(tmp.data(), h->dev.pts + (size_t)cloud * h->dev.nmax * 4, tmp.size() * 8, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < k; i++) { out_xyz[3 * i] = tmp[4 * i]; out_xyz[3 * i + 1] = tmp[4 * i + 1]; out_xyz[3 * i + 2] = tmp[4 * i + 2]; }
+  }
+  if (k > 0 && out_cov6)
+    GFS_CUDA(cudaMemcpy(out_cov6, h->dev.cov + (size_t)cloud * h->dev.nmax * 6, (size_t)k * 48, cudaMemcpyDeviceToHost));
+  return GFS_OK;
+}
+}

@@ -1,0 +1,95 @@
+"""Host-side mirror of RegistrationGICP (reference include/RegistrationGICP.h:15-33,
+src/RegistrationGICP.cc:5-20) over the C ABI."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr
+
+
+class GicpSetting(C.Structure):
+    _fields_ = [("downsampling_resolution", C.c_double), ("max_correspondence_distance", C.c_double),
+                ("rotation_eps", C.c_double), ("translation_eps", C.c_double), ("num_neighbors", C.c_int),
+                ("max_iterations", C.c_int), ("num_threads", C.c_int)]
+
+
+class GicpResult(C.Structure):
+    _fields_ = [("T", C.c_double * 16), ("H", C.c_double * 36), ("b", C.c_double * 6), ("error", C.c_double),
+                ("iterations", C.c_int), ("num_inliers", C.c_int), ("converged", C.c_int), ("n_target", C.c_int),
+                ("n_source", C.c_int), ("inner_evals", C.c_int)]
+
+
+RESULT_DTYPE = np.dtype([("T", "<f8", (4, 4)), ("H", "<f8", (6, 6)), ("b", "<f8", (6,)), ("error", "<f8"),
+                         ("iterations", "<i4"), ("num_inliers", "<i4"), ("converged", "<i4"), ("n_target", "<i4"),
+                         ("n_source", "<i4"), ("inner_evals", "<i4")], align=True)
+assert RESULT_DTYPE.itemsize == C.sizeof(GicpResult)
+
+
+def _res_to_dict(r):
+    return dict(T=np.array(r["T"]), H=np.array(r["H"]), b=np.array(r["b"]), error=float(r["error"]),
+                iterations=int(r["iterations"]), num_inliers=int(r["num_inliers"]), converged=bool(r["converged"]),
+                n_target=int(r["n_target"]), n_source=int(r["n_source"]), inner_evals=int(r["inner_evals"]))
+
+
+class RegistrationGICP:
+    """RegistrationGICP().RegisterPointClouds(target_points, source_points, init_T_target_source).
+    The setting defaults are the ones the reference hard-codes (voxel 0.02, max dist 0.1, GICP)."""
+
+    def __init__(self, max_points=65536, max_pairs=1, **setting):
+        self._L = _lib.lib()
+        _lib.require_device()
+        s = GicpSetting()
+        self._L.gfs_gicp_default_setting(C.byref(s))
+        for k, v in setting.items():
+            setattr(s, k, v)
+        self.setting = s
+        h = C.c_void_p()
+        check(self._L.gfs_gicp_create(C.byref(s), int(max_points), int(max_pairs), C.byref(h)))
+        self._h = h
+        self.max_points, self.max_pairs = int(max_points), int(max_pairs)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.gfs_gicp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def RegisterPointClouds(self, target_points, source_points, init_T_target_source=None, stream=None):
+        t = np.ascontiguousarray(target_points, np.float32).reshape(-1, 4)
+        s = np.ascontiguousarray(source_points, np.float32).reshape(-1, 4)
+        T0 = np.ascontiguousarray(np.eye(4) if init_T_target_source is None else init_T_target_source, np.float64)
+        r = np.zeros(1, RESULT_DTYPE)
+        check(self._L.gfs_gicp_align(self._h, stream, ptr(t), len(t), ptr(s), len(s), ptr(T0), ptr(r)))
+        return _res_to_dict(r[0])
+
+    def align_batch(self, targets, nt, sources, ns, T0, stream=None):
+        """targets/sources: (P, stride, 4) float32 host arrays; nt/ns: (P,) int32; T0: (P,4,4)."""
+        targets = np.ascontiguousarray(targets, np.float32); sources = np.ascontiguousarray(sources, np.float32)
+        P, stride = targets.shape[0], targets.shape[1]
+        assert sources.shape[:2] == (P, stride)
+        nt = np.ascontiguousarray(nt, np.int32); ns = np.ascontiguousarray(ns, np.int32)
+        T0 = np.ascontiguousarray(T0, np.float64).reshape(P, 16)
+        r = np.zeros(P, RESULT_DTYPE)
+        check(self._L.gfs_gicp_align_batch(self._h, stream, ptr(targets), ptr(nt), ptr(sources), ptr(ns), P, stride,
+                                           ptr(T0), ptr(r)))
+        return r
+
+    def align_batch_device(self, d_targets, d_nt, d_sources, d_ns, pairs, stride, d_T0, d_out, stream=None):
+        check(self._L.gfs_gicp_align_batch_device(self._h, stream, ptr(d_targets), ptr(d_nt), ptr(d_sources), ptr(d_ns),
+                                                  int(pairs), int(stride), ptr(d_T0), ptr(d_out)))
+
+    def last_launches(self):
+        return self._L.gfs_gicp_last_launches(self._h)
+
+    def cloud(self, index, stream=None):
+        """(downsampled xyz (M,3), covariances (M,6)) of cloud `index` of the last batch."""
+        xyz = np.zeros((self.max_points, 3), np.float64); cov = np.zeros((self.max_points, 6), np.float64)
+        n = C.c_int()
+        check(self._L.gfs_gicp_get_cloud(self._h, stream, index, ptr(xyz), ptr(cov), self.max_points, C.byref(n)))
+        return xyz[:n.value].copy(), cov[:n.value].copy()

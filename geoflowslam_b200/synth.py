@@ -70,3 +70,71 @@ def orb_frames(n, w=640, h=480, group=8, seed0=1000):
             sc = scene(seed0 + i, h + 80, w + 80)
         out[i] = frame_from_scene(sc, np.random.default_rng(seed0 + i), w, h)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# RGB-D clouds for GICP (BASELINE configs[2]): a room (3 planes) + 5 boxes seen from two poses.
+# ------------------------------------------------------------------------------------------------
+def _rot(rv):
+    th = np.linalg.norm(rv)
+    if th < 1e-12:
+        return np.eye(3)
+    k = rv / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+
+
+def _raycast(o, d, boxes):
+    """o: (3,), d: (N,3) unit-z-normalised rays.  Returns depth along each ray to the nearest surface of
+    the room x in [-3,3], y in [-1.5,1.5], z in [..,6] or of the boxes."""
+    t = np.full(len(d), np.inf)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for axis, val in ((2, 6.0), (1, 1.5), (0, -3.0), (0, 3.0), (1, -1.5)):
+            tt = (val - o[axis]) / d[:, axis]
+            tt[~(tt > 1e-6)] = np.inf
+            t = np.minimum(t, tt)
+        for (lo, hi) in boxes:
+            t0 = (lo - o) / d
+            t1 = (hi - o) / d
+            tn = np.minimum(t0, t1).max(1)
+            tf = np.maximum(t0, t1).min(1)
+            hit = (tf >= tn) & (tn > 1e-6)
+            t = np.where(hit, np.minimum(t, tn), t)
+    return t
+
+
+def gicp_pair(seed, n_target=50000, max_rot_deg=3.0, max_trans=0.05, noise_z=0.002):
+    """-> (target float32 (N,4), source float32 (M,4), T_target_source_true (4,4) float64).
+    Both clouds are expressed in their own camera frame (x right, y down, z forward)."""
+    rng = np.random.default_rng(seed)
+    boxes = []
+    for _ in range(5):
+        c = np.array([rng.uniform(-2, 2), rng.uniform(0.3, 1.2), rng.uniform(1.5, 5.0)])
+        s = rng.uniform(0.2, 0.6, 3)
+        boxes.append((c - s, c + s))
+    w = int(round(np.sqrt(n_target * 4 / 3)))
+    h = int(round(w * 3 / 4))
+    fx = fy = 0.95 * w
+    cx, cy = w / 2 - 0.5, h / 2 - 0.5
+    us, vs = np.meshgrid(np.arange(w), np.arange(h))
+    dirs = np.stack([(us.ravel() - cx) / fx, (vs.ravel() - cy) / fy, np.ones(w * h)], 1)
+
+    def view(R, tvec):
+        # camera-to-world: Xw = R Xc + t
+        dw = dirs @ R.T
+        depth = _raycast(tvec, dw, boxes)  # parametrised so that Xc = depth * dirs (dirs has z = 1)
+        ok = np.isfinite(depth) & (depth > 0.3) & (depth < 10.0)
+        z = depth[ok] + rng.normal(0, noise_z, ok.sum())
+        pts = dirs[ok] * z[:, None]
+        return np.concatenate([pts, np.ones((len(pts), 1))], 1).astype(np.float32)
+
+    R1, t1 = np.eye(3), np.zeros(3)
+    rv = np.deg2rad(rng.uniform(-max_rot_deg, max_rot_deg, 3))
+    R2 = _rot(rv)
+    t2 = rng.uniform(-max_trans, max_trans, 3)
+    tgt = view(R1, t1)
+    src = view(R2, t2)
+    T = np.eye(4)
+    T[:3, :3] = R2  # X_target = R2 X_source + t2
+    T[:3, 3] = t2
+    return tgt, src, T

@@ -146,6 +146,54 @@ int gfs_frontend_set_profiling(GfsFrontend* f, int enable);
 int gfs_frontend_get_profile(GfsFrontend* f, float* ms8);
 int gfs_frontend_launches_per_call(const GfsFrontend* f, int batch);
 
+/* ------------------------------------------------------------------------------------------
+ * GICP -- replaces RegistrationGICP::RegisterPointClouds (include/RegistrationGICP.h:25-28,
+ * src/RegistrationGICP.cc:5-20) = small_gicp::align(target, source, init_T, setting) with
+ * type GICP (Thirdparty/small_gicp/src/small_gicp/registration/registration_helper.cpp:56-68,
+ * :111-120): voxel downsampling, 10-NN covariances, exact nearest-neighbour correspondences,
+ * Levenberg-Marquardt.  Points are float4 (x, y, z, 1) like std::vector<Eigen::Vector4f>.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct GfsGicpSetting {        /* small_gicp::RegistrationSetting (registration_helper.hpp:38-49) */
+  double downsampling_resolution;      /* 0.02  (RegistrationGICP.cc:11) */
+  double max_correspondence_distance;  /* 0.1   (RegistrationGICP.cc:12) */
+  double rotation_eps;                 /* 0.1 deg in rad */
+  double translation_eps;              /* 1e-3 */
+  int num_neighbors;                   /* 10 (registration_helper.cpp:59) */
+  int max_iterations;                  /* 20 */
+  int num_threads;                     /* 4 in the reference; ignored */
+} GfsGicpSetting;
+
+typedef struct GfsGicpResult {  /* small_gicp::RegistrationResult (registration_result.hpp:11-30) */
+  double T[16];                 /* T_target_source, row-major 4x4 */
+  double H[36];                 /* information matrix of the last linearisation */
+  double b[6];
+  double error;
+  int iterations;               /* zero-based index of the last outer iteration */
+  int num_inliers;
+  int converged;
+  int n_target, n_source;       /* points after downsampling (measurement aid) */
+  int inner_evals;              /* total lambda trials = error evaluations (measurement aid) */
+} GfsGicpResult;
+
+typedef struct GfsGicp GfsGicp;
+void gfs_gicp_default_setting(GfsGicpSetting* s);
+/* setting may be NULL (defaults above). max_points = per-cloud capacity, max_pairs = batch capacity. */
+int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs, GfsGicp** out);
+int gfs_gicp_destroy(GfsGicp* h);
+/* RegisterPointClouds(target, source, init_T_target_source) -> result; T0 row-major 4x4. */
+int gfs_gicp_align(GfsGicp* h, void* stream, const float* target, int nt, const float* source, int ns, const double* T0,
+                   GfsGicpResult* out);
+/* Batched: clouds are [pairs][stride][4] floats with nt[p] / ns[p] valid points, T0 is [pairs][16].
+ * The device variant enqueues on `stream` but synchronises it once per LM trial to read two
+ * control counters (the optimizer's data-dependent loop, optimizer.hpp:97-141). */
+int gfs_gicp_align_batch(GfsGicp* h, void* stream, const float* target, const int* nt, const float* source, const int* ns,
+                         int pairs, int stride, const double* T0, GfsGicpResult* out);
+int gfs_gicp_align_batch_device(GfsGicp* h, void* stream, const float* d_target, const int* d_nt, const float* d_source,
+                                const int* d_ns, int pairs, int stride, const double* d_T0, GfsGicpResult* d_out);
+/* parity hook: downsampled points + covariances of cloud (2*pair = target, 2*pair+1 = source) */
+int gfs_gicp_get_cloud(GfsGicp* h, void* stream, int cloud, double* out_xyz, double* out_cov6, int cap, int* n);
+int gfs_gicp_last_launches(const GfsGicp* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -188,3 +188,74 @@ def gms_filter(pts1, size1, pts2, size2, matches):
     n = lib().gfo_gms_filter(_p(pts1), len(pts1), size1[0], size1[1], _p(pts2), len(pts2), size2[0], size2[1],
                              _p(matches), len(matches), _p(mask))
     return mask[:len(matches)].astype(bool), n
+
+
+# ------------------------------------------------------------------------------ GICP
+class GicpResult(C.Structure):
+    _fields_ = [("T", C.c_double * 16), ("H", C.c_double * 36), ("b", C.c_double * 6), ("error", C.c_double),
+                ("iterations", C.c_int), ("num_inliers", C.c_int), ("converged", C.c_int), ("n_target", C.c_int),
+                ("n_source", C.c_int), ("inner_evals", C.c_int)]
+
+
+def _bind_gicp(L):
+    L.gfo_gicp_align.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int,
+                                 C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(GicpResult)]
+    L.gfo_voxelgrid.restype = C.c_int
+    L.gfo_voxelgrid.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int]
+    L.gfo_kdtree_knn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gfo_covariances.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.gfo_eig3.argtypes = [C.c_void_p] * 3
+    L.gfo_se3_exp.argtypes = [C.c_void_p] * 2
+
+
+_LATE_BINDERS.append(("gfo_gicp_align", _bind_gicp))
+
+
+def gicp_align(target, source, T0=None, voxel=0.02, max_dist=0.1, k=10, max_iter=20,
+               rot_eps=0.1 * np.pi / 180.0, trans_eps=1e-3, threads=4):
+    """RegistrationGICP::RegisterPointClouds -> dict(T, H, b, error, iterations, num_inliers, converged, ...)"""
+    target = np.ascontiguousarray(target, np.float32).reshape(-1, 4)
+    source = np.ascontiguousarray(source, np.float32).reshape(-1, 4)
+    T0 = np.ascontiguousarray(np.eye(4) if T0 is None else T0, np.float64)
+    r = GicpResult()
+    lib().gfo_gicp_align(_p(target), len(target), _p(source), len(source), _p(T0), voxel, max_dist, k, max_iter,
+                         rot_eps, trans_eps, threads, C.byref(r))
+    return dict(T=np.array(r.T).reshape(4, 4), H=np.array(r.H).reshape(6, 6), b=np.array(r.b), error=r.error,
+                iterations=r.iterations, num_inliers=r.num_inliers, converged=bool(r.converged), n_target=r.n_target,
+                n_source=r.n_source, inner_evals=r.inner_evals)
+
+
+def voxelgrid(pts4, leaf):
+    pts4 = np.ascontiguousarray(pts4, np.float32).reshape(-1, 4)
+    out = np.zeros((max(len(pts4), 1), 3), np.float64)
+    n = lib().gfo_voxelgrid(_p(pts4), len(pts4), leaf, _p(out), len(out))
+    return out[:n].copy()
+
+
+def kdtree_knn(pts, queries, k):
+    pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
+    q = np.ascontiguousarray(queries, np.float64).reshape(-1, 3)
+    idx = np.zeros((len(q), k), np.int64); d2 = np.zeros((len(q), k), np.float64); f = np.zeros(len(q), np.int32)
+    lib().gfo_kdtree_knn(_p(pts), len(pts), _p(q), len(q), k, _p(idx), _p(d2), _p(f))
+    return idx, d2, f
+
+
+def covariances(pts, k=10):
+    pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
+    out = np.zeros((len(pts), 6), np.float64)
+    lib().gfo_covariances(_p(pts), len(pts), k, _p(out))
+    return out
+
+
+def eig3(A):
+    A = np.ascontiguousarray(A, np.float64).reshape(3, 3)
+    ev = np.zeros(3); V = np.zeros((3, 3))
+    lib().gfo_eig3(_p(A), _p(ev), _p(V))
+    return ev, V
+
+
+def se3_exp(a):
+    a = np.ascontiguousarray(a, np.float64).reshape(6)
+    T = np.zeros((4, 4))
+    lib().gfo_se3_exp(_p(a), _p(T))
+    return T

@@ -1,0 +1,86 @@
+"""GPU parity: batched GICP (through the C ABI) vs the CPU oracle.  Integer results equal;
+floating point within 1e-4 relative (north_star), in practice ~1e-9."""
+import numpy as np
+import pytest
+
+from geoflowslam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def _check(g, o, tight=True):
+    assert g["converged"] == o["converged"] and g["iterations"] == o["iterations"]
+    assert g["num_inliers"] == o["num_inliers"] and g["inner_evals"] == o["inner_evals"]
+    assert g["n_target"] == o["n_target"] and g["n_source"] == o["n_source"]
+    tol = 1e-7 if tight else RTOL
+    assert np.allclose(g["T"], o["T"], rtol=tol, atol=tol)
+    assert np.allclose(g["H"], o["H"], rtol=tol, atol=tol * np.abs(o["H"]).max())
+    assert np.allclose(g["b"], o["b"], rtol=tol, atol=tol * max(np.abs(o["b"]).max(), 1.0))
+    assert np.isclose(g["error"], o["error"], rtol=tol, atol=1e-9)
+
+
+def test_preprocess_stage_parity():
+    from geoflowslam_b200 import RegistrationGICP
+    from oracle import oracle as O
+    tgt, src, _ = synth.gicp_pair(2003, n_target=12000)
+    reg = RegistrationGICP(max_points=16384, max_pairs=1)
+    reg.RegisterPointClouds(tgt, src)
+    for ci, cloud in enumerate((tgt, src)):
+        xyz, cov = reg.cloud(ci)
+        ref = O.voxelgrid(cloud, 0.02)
+        assert len(xyz) == len(ref)
+        og, orr = np.lexsort(xyz.T), np.lexsort(ref.T)
+        assert np.array_equal(xyz[og], ref[orr])            # per-voxel means are bit-exact (fixed sum order)
+        cref = O.covariances(ref, 10)
+        assert np.allclose(cov[og], cref[orr], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("seed,n", [(2000, 20000), (2004, 50000), (2005, 5000)])
+def test_align_matches_oracle(seed, n):
+    from geoflowslam_b200 import RegistrationGICP
+    from oracle import oracle as O
+    tgt, src, T = synth.gicp_pair(seed, n_target=n)
+    reg = RegistrationGICP(max_points=65536, max_pairs=1)
+    g = reg.RegisterPointClouds(tgt, src)
+    o = O.gicp_align(tgt, src)
+    _check(g, o)
+    assert np.abs(g["T"] - T).max() < 2e-3
+
+
+def test_batch_with_ragged_sizes_and_inits():
+    from geoflowslam_b200 import RegistrationGICP
+    from oracle import oracle as O
+    pairs = [synth.gicp_pair(2010 + i, n_target=[8000, 3000, 12000, 500][i]) for i in range(4)]
+    stride = max(max(len(t), len(s)) for t, s, _ in pairs)
+    P = len(pairs)
+    tg = np.zeros((P, stride, 4), np.float32); sr = np.zeros((P, stride, 4), np.float32)
+    nt = np.zeros(P, np.int32); ns = np.zeros(P, np.int32)
+    T0 = np.tile(np.eye(4), (P, 1, 1))
+    for i, (t, s, T) in enumerate(pairs):
+        tg[i, :len(t)] = t; sr[i, :len(s)] = s; nt[i] = len(t); ns[i] = len(s)
+    T0[1] = pairs[1][2]                                    # start one pair at the true pose
+    T0[2][:3, 3] += 0.3                                    # and one far enough to need several iterations
+    reg = RegistrationGICP(max_points=stride, max_pairs=P)
+    res = reg.align_batch(tg, nt, sr, ns, T0)
+    from geoflowslam_b200.gicp import _res_to_dict
+    for i, (t, s, _) in enumerate(pairs):
+        _check(_res_to_dict(res[i]), O.gicp_align(t, s, T0=T0[i]))
+
+
+def test_degenerate_inputs():
+    from geoflowslam_b200 import RegistrationGICP
+    from oracle import oracle as O
+    tgt, src, _ = synth.gicp_pair(2002, n_target=3000)
+    reg = RegistrationGICP(max_points=8192, max_pairs=1)
+    far = src.copy(); far[:, :3] += 50.0
+    _check(reg.RegisterPointClouds(tgt, far), O.gicp_align(tgt, far))       # zero inliers, LM stalls
+    _check(reg.RegisterPointClouds(tgt, tgt), O.gicp_align(tgt, tgt))       # identical clouds
+    few = tgt[:4]
+    _check(reg.RegisterPointClouds(few, few), O.gicp_align(few, few))       # < 5 points: identity covariances
+    sparse = tgt[::200]                                                     # neighbours beyond the shell limit
+    _check(reg.RegisterPointClouds(sparse, sparse + np.float32([0.01, 0, 0, 0])),
+           O.gicp_align(sparse, sparse + np.float32([0.01, 0, 0, 0])))
+    from geoflowslam_b200 import GfsError
+    with pytest.raises(GfsError):
+        reg.RegisterPointClouds(np.zeros((10000, 4), np.float32), src)      # beyond max_points
