@@ -138,3 +138,202 @@ def gicp_pair(seed, n_target=50000, max_rot_deg=3.0, max_trans=0.05, noise_z=0.0
     T[:3, :3] = R2  # X_target = R2 X_source + t2
     T[:3, 3] = t2
     return tgt, src, T
+
+
+# ------------------------------------------------------------------------------------------------
+# LocalInertialBA problem (BASELINE configs[3]): 20 KFs on an arc, 3000 points, ~15k stereo
+# observations, 200 Hz IMU preintegrated in float32 as IMU::Preintegrated does
+# (reference src/ImuTypes.cc:184-246), 1 fixed predecessor keyframe.
+# ------------------------------------------------------------------------------------------------
+PRE_STRIDE = 292  # dR9 dV3 dP3 JRg9 JVg9 JVa9 JPg9 JPa9 C225 dT1 b6(bax bay baz bwx bwy bwz)
+G1_CAM = dict(fx=606.986, fy=607.011, cx=311.519, cy=247.260, bf=606.986 * 0.0745)  # g1 yaml :25-28,54
+IMU_NOISE = dict(ng=2.443e-3, na=1.176e-2, ngw=1e-4, naw=1e-3, freq=200.0)         # g1 yaml :106-110
+
+
+def _f32(x):
+    return np.asarray(x, np.float32)
+
+
+def _hat32(v):
+    return _f32([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+
+
+def _polar32(R):
+    U, _, Vt = np.linalg.svd(R.astype(np.float32))
+    return (U @ Vt).astype(np.float32)
+
+
+def preintegrate(acc, gyr, dt, bias, noise=IMU_NOISE):
+    """IMU::Preintegrated::IntegrateNewMeasurement over the samples, float32 throughout.
+    bias = (bax, bay, baz, bwx, bwy, bwz).  Returns the packed PRE_STRIDE record."""
+    f = np.float32
+    sf = np.sqrt(f(noise["freq"]))
+    ng, na = f(noise["ng"]) * sf, f(noise["na"]) * sf
+    ngw, naw = f(noise["ngw"]) / sf, f(noise["naw"]) / sf
+    Nga = np.diag(_f32([ng * ng] * 3 + [na * na] * 3))
+    NgaWalk = np.diag(_f32([ngw * ngw] * 3 + [naw * naw] * 3))
+    dR = np.eye(3, dtype=f); dV = np.zeros(3, f); dP = np.zeros(3, f)
+    JRg = np.zeros((3, 3), f); JVg = np.zeros((3, 3), f); JVa = np.zeros((3, 3), f)
+    JPg = np.zeros((3, 3), f); JPa = np.zeros((3, 3), f)
+    C = np.zeros((15, 15), f)
+    dT = f(0)
+    b = _f32(bias)
+    dt = f(dt)
+    for a_m, w_m in zip(_f32(acc), _f32(gyr)):
+        A = np.eye(9, dtype=f); B = np.zeros((9, 6), f)
+        a = a_m - b[:3]
+        Wacc = _hat32(a)
+        dP = dP + dV * dt + f(0.5) * (dR @ a) * dt * dt
+        dV = dV + (dR @ a) * dt
+        A[3:6, 0:3] = -dR * dt @ Wacc
+        A[6:9, 0:3] = f(-0.5) * dR * dt * dt @ Wacc
+        A[6:9, 3:6] = np.eye(3, dtype=f) * dt
+        B[3:6, 3:6] = dR * dt
+        B[6:9, 3:6] = f(0.5) * dR * dt * dt
+        JPa = JPa + JVa * dt - f(0.5) * dR * dt * dt
+        JPg = JPg + JVg * dt - f(0.5) * dR * dt * dt @ Wacc @ JRg
+        JVa = JVa - dR * dt
+        JVg = JVg - dR * dt @ Wacc @ JRg
+        v = (w_m - b[3:]) * dt
+        d2 = f(v @ v); d = np.sqrt(d2)
+        W = _hat32(v)
+        if d < 1e-4:
+            dRi = np.eye(3, dtype=f) + W; rJ = np.eye(3, dtype=f)
+        else:
+            dRi = np.eye(3, dtype=f) + W * (np.sin(d) / d) + W @ W * ((f(1) - np.cos(d)) / d2)
+            rJ = np.eye(3, dtype=f) - W * ((f(1) - np.cos(d)) / d2) + W @ W * ((d - np.sin(d)) / (d2 * d))
+        dR = _polar32(dR @ dRi)
+        A[0:3, 0:3] = dRi.T
+        B[0:3, 0:3] = rJ * dt
+        C[0:9, 0:9] = A @ C[0:9, 0:9] @ A.T + B @ Nga @ B.T
+        C[9:15, 9:15] += NgaWalk
+        JRg = dRi.T @ JRg - rJ * dt
+        dT = dT + dt
+    rec = np.concatenate([dR.ravel(), dV, dP, JRg.ravel(), JVg.ravel(), JVa.ravel(), JPg.ravel(), JPa.ravel(),
+                          C.ravel(), [dT], b]).astype(np.float32)
+    assert rec.size == PRE_STRIDE
+    return rec
+
+
+def ba_problem(seed=3000, n_kf=20, n_points=3000, obs_per_point=5, kf_dt=0.5, imu_rate=200, b_large=True,
+               rot_noise_deg=1.0, trans_noise=0.02, point_noise=0.02, outlier_frac=0.01):
+    """Synthetic LocalInertialBA problem as plain arrays (the flattened export of the reference's
+    KeyFrame / MapPoint graph, see include/gfs_b200.h GfsBaProblem).  Keyframe 0 is the newest
+    (vpOptimizableKFs order, Optimizer.cc:3078-3086); the fixed predecessor is index n_kf."""
+    rng = np.random.default_rng(seed)
+    g = np.array([0, 0, -9.81])
+    Rbc = np.array([[0, 0, 1.0], [-1, 0, 0], [0, -1, 0]])  # camera z forward / x right / y down in a FLU body
+    tbc = np.array([0.05, 0.02, 0.01])
+    Rcb = Rbc.T; tcb = -Rcb @ tbc
+    nk = n_kf + 1
+    per = int(round(kf_dt * imu_rate))
+    dt = 1.0 / imu_rate
+    T_total = kf_dt * (nk - 1)
+    w_yaw = (2.0 / 5.0) / T_total  # 2 m arc on a 5 m radius circle
+
+    def pose(t):
+        yaw = w_yaw * t + 0.02 * np.sin(1.3 * t)
+        pitch = 0.03 * np.sin(0.9 * t); roll = 0.02 * np.cos(1.1 * t)
+        R = _rot(np.array([0, 0, yaw])) @ _rot(np.array([0, pitch, 0])) @ _rot(np.array([roll, 0, 0]))
+        p = np.array([5 * np.sin(w_yaw * t), 5 * (1 - np.cos(w_yaw * t)), 0.05 * np.sin(0.7 * t)])
+        return R, p
+
+    h = 1e-4
+    ts = np.arange(0, (nk - 1) * per) * dt + dt / 2  # mid-point samples
+    acc = np.zeros((len(ts), 3)); gyr = np.zeros((len(ts), 3))
+    bg_true = np.array([0.002, -0.001, 0.0015]); ba_true = np.array([0.02, -0.03, 0.01])
+    for i, t in enumerate(ts):
+        R0, p0 = pose(t); Rp, pp = pose(t + h); Rm, pm = pose(t - h)
+        a_w = (pp - 2 * p0 + pm) / (h * h)
+        dRm = R0.T @ (Rp - Rm) / (2 * h)
+        gyr[i] = [dRm[2, 1], dRm[0, 2], dRm[1, 0]]
+        acc[i] = R0.T @ (a_w - g)
+    ns = IMU_NOISE
+    gyr += bg_true + rng.normal(0, ns["ng"] * np.sqrt(imu_rate), gyr.shape)
+    acc += ba_true + rng.normal(0, ns["na"] * np.sqrt(imu_rate), acc.shape)
+
+    # chronological keyframes c = 0 (fixed predecessor) .. n_kf (newest); window index i = n_kf - c
+    Rwb_t, twb_t, vel_t = [], [], []
+    for c in range(nk):
+        t = c * kf_dt
+        R, p = pose(t); _, pp = pose(t + h); _, pm = pose(t - h)
+        Rwb_t.append(R); twb_t.append(p); vel_t.append((pp - pm) / (2 * h))
+    order = list(range(n_kf, 0, -1)) + [0]  # problem index -> chronological index
+    bias_est = np.concatenate([ba_true, bg_true]) + rng.normal(0, [2e-3] * 3 + [2e-4] * 3)
+    pre = np.zeros((n_kf, PRE_STRIDE), np.float32)
+    in_kf1 = np.zeros(n_kf, np.int32); in_kf2 = np.zeros(n_kf, np.int32); down = np.zeros(n_kf, np.uint8)
+    for i in range(n_kf):  # edge i links problem kf i (cur) with its predecessor
+        c = order[i]
+        seg = slice((c - 1) * per, c * per)
+        pre[i] = preintegrate(acc[seg], gyr[seg], dt, bias_est)
+        in_kf2[i] = i
+        in_kf1[i] = i + 1  # predecessor: next window index, or the fixed KF (index n_kf)
+        down[i] = 1 if i == n_kf - 1 else 0
+
+    # points in front of the trajectory
+    cam = G1_CAM
+    pts = np.zeros((n_points, 3))
+    for j in range(n_points):  # unproject a random pixel of a random keyframe at 2..8 m
+        c = int(rng.integers(0, nk))
+        u, v, z = rng.uniform(20, 620), rng.uniform(20, 460), rng.uniform(2.0, 8.0)
+        Xc = np.array([(u - cam["cx"]) / cam["fx"] * z, (v - cam["cy"]) / cam["fy"] * z, z])
+        pts[j] = Rwb_t[c] @ (Rbc @ Xc + tbc) + twb_t[c]
+    obs_kf, obs_pt, obs_uvr, obs_is2 = [], [], [], []
+    for j in range(n_points):
+        vis = []
+        for i in range(nk):
+            c = order[i]
+            Rcw = Rcb @ Rwb_t[c].T
+            Xc = Rcw @ (pts[j] - twb_t[c]) + tcb
+            if Xc[2] < 0.3:
+                continue
+            u = cam["fx"] * Xc[0] / Xc[2] + cam["cx"]; v = cam["fy"] * Xc[1] / Xc[2] + cam["cy"]
+            if 0 <= u < 640 and 0 <= v < 480:
+                vis.append((i, u, v, u - cam["bf"] / Xc[2]))
+        if len(vis) < 2:
+            continue
+        k = min(len(vis), obs_per_point + int(rng.integers(-1, 2)))
+        s = int(rng.integers(0, len(vis) - k + 1))
+        for (i, u, v, ur) in vis[s:s + k]:
+            octv = int(rng.integers(0, 4))
+            sig = 1.2 ** octv
+            nz = rng.normal(0, sig, 3)
+            if rng.random() < outlier_frac:
+                nz += rng.normal(0, 30.0, 3)
+            mono = rng.random() < 0.05  # a few depth-less observations -> EdgeMono
+            obs_kf.append(i); obs_pt.append(j)
+            obs_uvr.append([np.float32(u + nz[0]), np.float32(v + nz[1]), -1.0 if mono else np.float32(ur + nz[2])])
+            obs_is2.append(np.float32(1.0) / np.float32(np.float32(sig) * np.float32(sig)))
+
+    # initial estimates: float32 keyframe states, as the reference stores them
+    def f64(x):
+        return np.asarray(x, np.float32).astype(np.float64)
+    kf_Rwb = np.zeros((nk, 9)); kf_twb = np.zeros((nk, 3)); kf_Rcw = np.zeros((nk, 9)); kf_tcw = np.zeros((nk, 3))
+    kf_vel = np.zeros((nk, 3)); kf_bg = np.zeros((nk, 3)); kf_ba = np.zeros((nk, 3))
+    for i in range(nk):
+        c = order[i]
+        fixed = i == n_kf
+        R = Rwb_t[c] if fixed else Rwb_t[c] @ _rot(np.deg2rad(rng.uniform(-rot_noise_deg, rot_noise_deg, 3)))
+        p = twb_t[c] if fixed else twb_t[c] + rng.uniform(-trans_noise, trans_noise, 3)
+        R32 = _polar32(R.astype(np.float32)); p32 = p.astype(np.float32)
+        Rcw32 = (Rcb.astype(np.float32) @ R32.T).astype(np.float32)
+        tcw32 = (Rcb.astype(np.float32) @ (-(R32.T @ p32)) + tcb.astype(np.float32)).astype(np.float32)
+        kf_Rwb[i] = f64(R32).ravel(); kf_twb[i] = f64(p32)
+        kf_Rcw[i] = f64(Rcw32).ravel(); kf_tcw[i] = f64(tcw32)
+        kf_vel[i] = f64(vel_t[c] + (0 if fixed else rng.uniform(-0.02, 0.02, 3)))
+        kf_bg[i] = f64(bias_est[3:]); kf_ba[i] = f64(bias_est[:3])
+    pt_xyz = f64(pts + rng.normal(0, point_noise, pts.shape))
+    return dict(
+        n_opt_kf=n_kf, n_fixed_kf=1, n_points=n_points, n_obs=len(obs_kf), n_inertial=n_kf,
+        iterations=4 if b_large else 8, b_large=int(b_large), lambda_init=1e-2 if b_large else 1.0,
+        Rcb=f64(Rcb).ravel(), tcb=f64(tcb), Rbc=f64(Rbc).ravel(), tbc=f64(tbc),
+        fx=np.float32(cam["fx"]), fy=np.float32(cam["fy"]), cx=np.float32(cam["cx"]), cy=np.float32(cam["cy"]),
+        bf=float(np.float32(cam["bf"])),
+        kf_Rwb=kf_Rwb, kf_twb=kf_twb, kf_Rcw=kf_Rcw, kf_tcw=kf_tcw, kf_vel=kf_vel, kf_bg=kf_bg, kf_ba=kf_ba,
+        kf_has_imu=np.ones(nk, np.uint8),
+        pt_xyz=pt_xyz, pt_close=np.ones(n_points, np.uint8),
+        obs_kf=np.array(obs_kf, np.int32), obs_pt=np.array(obs_pt, np.int32),
+        obs_uvr=np.array(obs_uvr, np.float64).reshape(-1, 3), obs_inv_sigma2=np.array(obs_is2, np.float32),
+        in_kf1=in_kf1, in_kf2=in_kf2, in_pre=pre, in_downweight=down,
+        truth=dict(Rwb=np.array([Rwb_t[c] for c in order]), twb=np.array([twb_t[c] for c in order]), pts=pts,
+                   vel=np.array([vel_t[c] for c in order]), bg=bg_true, ba=ba_true))

@@ -194,6 +194,77 @@ int gfs_gicp_align_batch_device(GfsGicp* h, void* stream, const float* d_target,
 int gfs_gicp_get_cloud(GfsGicp* h, void* stream, int cloud, double* out_xyz, double* out_cov6, int cap, int* n);
 int gfs_gicp_last_launches(const GfsGicp* h);
 
+/* ------------------------------------------------------------------------------------------
+ * Local inertial bundle adjustment -- replaces the numerical core of
+ * Optimizer::LocalInertialBA (include/Optimizer.h:180-183, src/Optimizer.cc:3056-3702): the g2o
+ * problem it builds (VertexPose/Velocity/GyroBias/AccBias + VertexSBAPointXYZ, EdgeMono /
+ * EdgeStereo with Huber, EdgeInertial with Huber, EdgeGyroRW / EdgeAccRW; src/G2oTypes.cc,
+ * include/G2oTypes.h) and the Levenberg-Marquardt / Schur solve g2o runs on it
+ * (Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:59-164, block_solver.hpp:354-560).
+ * The pointer graph (KeyFrame*, MapPoint*, observations) is flattened by the shim into the plain
+ * arrays below; window selection, outlier erasure and write-back stay with the caller.
+ * ---------------------------------------------------------------------------------------- */
+#define GFS_BA_PRE_STRIDE 292 /* floats per inertial edge: dR9 dV3 dP3 JRg9 JVg9 JVa9 JPg9 JPa9 C225 dT1
+                                 b6 (bax bay baz bwx bwy bwz) -- IMU::Preintegrated members, ImuTypes.h */
+typedef struct GfsBaProblem {
+  int n_opt_kf;   /* optimizable keyframes (vpOptimizableKFs order, index 0 = pKF; Optimizer.cc:3078-3086) */
+  int n_fixed_kf; /* fixed keyframes (lFixedKeyFrames, :3106-3165); stored after the optimizable ones */
+  int n_points;   /* lLocalMapPoints */
+  int n_obs;      /* visual edges, in creation order (:3446-3577) */
+  int n_inertial; /* EdgeInertial (+ EdgeGyroRW + EdgeAccRW each), :3328-3401 */
+  int iterations; /* optimizer.optimize(opt_it): 4 if bLarge else 8 (:3063-3068) */
+  int b_large;
+  double lambda_init; /* setUserLambdaInit: 1e-2 if bLarge else 1e0 (:3178-3187) */
+  /* ImuCamPose calibration (G2oTypes.cc:48-56); Pinhole parameters are floats (Pinhole.cpp:36-42) */
+  double Rcb[9], tcb[3], Rbc[9], tbc[3];
+  float fx, fy, cx, cy;
+  double bf;
+  /* keyframe states [n_opt_kf + n_fixed_kf]; matrices row-major; float values widened like the
+   * reference does when it loads them (G2oTypes.cc:30-52) */
+  const double *kf_Rwb, *kf_twb, *kf_Rcw, *kf_tcw, *kf_vel, *kf_bg, *kf_ba;
+  const uint8_t* kf_has_imu;
+  const double* pt_xyz;    /* [n_points][3] */
+  const uint8_t* pt_close; /* pMP->mTrackDepth < 10 (:3607) */
+  const int *obs_kf, *obs_pt;
+  const double* obs_uvr;       /* [n_obs][3] u, v, u_right; u_right < 0 -> EdgeMono (:3477, :3509) */
+  const float* obs_inv_sigma2; /* mvInvLevelSigma2[octave] / unc2 (:3494, :3528) */
+  const int *in_kf1, *in_kf2;  /* keyframe indices of (prev, cur) */
+  const float* in_pre;         /* [n_inertial][GFS_BA_PRE_STRIDE] */
+  const uint8_t* in_downweight; /* 1 -> information * 1e-2 (i == N-1, :3371) */
+} GfsBaProblem;
+
+typedef struct GfsBaResult {
+  /* optimised states, same layout as the inputs ([n_opt_kf + n_fixed_kf] keyframes) */
+  double *kf_Rwb, *kf_twb, *kf_Rcw, *kf_tcw, *kf_vel, *kf_bg, *kf_ba, *pt_xyz;
+  double* obs_chi2;            /* [n_obs] e->chi2() as the reference reads it after optimize (:3611, :3624) */
+  uint8_t* obs_depth_positive; /* [n_obs] e->isDepthPositive() (mono edges; 1 for stereo) */
+  uint8_t* obs_outlier;        /* [n_obs] the vToErase decision (:3603-3626) */
+  float err, err_end;          /* activeRobustChi2 before / after (:3590-3592) */
+  int failed;                  /* "FAIL LOCAL-INERTIAL BA" guard (:3632-3636): no write-back */
+  int iterations_done;         /* g2o optimize() return value */
+  int lm_trials;               /* total LM trials (measurement aid) */
+  double lambda_final;
+} GfsBaResult;
+
+typedef struct GfsBa GfsBa;
+/* capacity: keyframes (optimizable + fixed), points, observations, inertial edges per problem, problems per batch */
+int gfs_ba_create(int max_kf, int max_points, int max_obs, int max_inertial, int max_batch, GfsBa** out);
+int gfs_ba_destroy(GfsBa* h);
+/* Solve `batch` independent problems (host pointers inside GfsBaProblem / GfsBaResult). */
+int gfs_ba_solve_batch(GfsBa* h, void* stream, const GfsBaProblem* problems, GfsBaResult* results, int batch);
+int gfs_ba_solve(GfsBa* h, void* stream, const GfsBaProblem* problem, GfsBaResult* result);
+/* Two-phase variant for resident problems: upload once, then solve (re-solve) on the device;
+ * gfs_ba_download copies the results of the last gfs_ba_solve_uploaded back. */
+int gfs_ba_upload(GfsBa* h, void* stream, const GfsBaProblem* problems, int batch);
+int gfs_ba_solve_uploaded(GfsBa* h, void* stream);
+int gfs_ba_download(GfsBa* h, void* stream, GfsBaResult* results, int batch);
+int gfs_ba_last_launches(const GfsBa* h);
+/* Edge-partitioned mode: this rank owns the landmarks p with p % world == rank; the
+ * reduced pose system is summed over ranks by `allreduce(buf, count_doubles, user)` (e.g. a
+ * thin wrapper over ncclAllReduce / torch.distributed.all_reduce) once per LM trial. */
+typedef int (*GfsAllReduceFn)(double* device_buf, int count, void* user);
+int gfs_ba_set_partition(GfsBa* h, int rank, int world, GfsAllReduceFn allreduce, void* user);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,856 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY. Not part of the product path.
+//
+// CPU restatement of the numerical core of Optimizer::LocalInertialBA (reference
+// src/Optimizer.cc:3056-3702) on a flattened problem (include/gfs_b200.h GfsBaProblem):
+//   vertices        ImuCamPose / VertexPose::oplusImpl        src/G2oTypes.cc:28-74,191-217
+//                   VertexVelocity / GyroBias / AccBias        include/G2oTypes.h:181-236
+//   EdgeMono/Stereo computeError, linearizeOplus              include/G2oTypes.h:317-332,399-405; src/G2oTypes.cc:335-360,385-416
+//   EdgeInertial    ctor, computeError, linearizeOplus        src/G2oTypes.cc:473-719
+//   EdgeGyroRW / EdgeAccRW                                     include/G2oTypes.h:782-852
+//   IMU::Preintegrated::GetDelta{Rotation,Velocity,Position}  src/ImuTypes.cc:283-313 (float32)
+//   Pinhole::project / projectJac                              src/CameraModels/Pinhole.cpp:36-42,73-83
+//   SO3 helpers                                                src/G2oTypes.cc:1007-1082
+//   g2o: Huber (robust_kernel_impl.cpp:77-91), constructQuadraticForm (base_binary_edge.hpp:56-118,
+//        base_multi_edge.hpp:36-48), BlockSolver Schur solve (block_solver.hpp:354-486),
+//        Levenberg (optimization_algorithm_levenberg.cpp:59-190), optimize loop (sparse_optimizer.cpp:354-420)
+// written without Eigen/g2o.  The reference has no tests for this path ("parity unpinned");
+// tests/test_oracle_ba.py pins the Jacobians by finite differences, the Schur solve against a dense
+// numpy solve, and the optimisation against ground truth.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "../include/gfs_b200.h"
+
+namespace gfo {
+namespace ba {
+
+typedef double M3[9];  // row-major 3x3
+
+static inline void mm3(const double* A, const double* B, double* C) {
+  double t[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) t[3 * r + c] = A[3 * r] * B[c] + A[3 * r + 1] * B[3 + c] + A[3 * r + 2] * B[6 + c];
+  memcpy(C, t, sizeof(t));
+}
+static inline void mt3(const double* A, double* T) {
+  double t[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) t[3 * r + c] = A[3 * c + r];
+  memcpy(T, t, sizeof(t));
+}
+static inline void mv3(const double* A, const double* v, double* o) {
+  double t[3];
+  for (int r = 0; r < 3; r++) t[r] = A[3 * r] * v[0] + A[3 * r + 1] * v[1] + A[3 * r + 2] * v[2];
+  memcpy(o, t, sizeof(t));
+}
+static inline void mtv3(const double* A, const double* v, double* o) {  // A^T v
+  double t[3];
+  for (int r = 0; r < 3; r++) t[r] = A[r] * v[0] + A[3 + r] * v[1] + A[6 + r] * v[2];
+  memcpy(o, t, sizeof(t));
+}
+static bool inv3(const double* A, double* I) {
+  const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+  const double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+  const double id = 1.0 / det;
+  double t[9];
+  t[0] = c00 * id; t[3] = c01 * id; t[6] = c02 * id;
+  t[1] = (A[2] * A[7] - A[1] * A[8]) * id; t[4] = (A[0] * A[8] - A[2] * A[6]) * id; t[7] = (A[1] * A[6] - A[0] * A[7]) * id;
+  t[2] = (A[1] * A[5] - A[2] * A[4]) * id; t[5] = (A[2] * A[3] - A[0] * A[5]) * id; t[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+  memcpy(I, t, sizeof(t));
+  return det != 0 && std::isfinite(id);
+}
+static inline void skew(const double* w, double* W) {
+  W[0] = 0; W[1] = -w[2]; W[2] = w[1]; W[3] = w[2]; W[4] = 0; W[5] = -w[0]; W[6] = -w[1]; W[7] = w[0]; W[8] = 0;
+}
+// NormalizeRotation (G2oTypes.h:69-74): U V^T of the SVD = orthogonal polar factor.  Computed by the
+// Newton iteration X <- (X + X^-T)/2, which converges quadratically to the same matrix.
+template <class T>
+static void normalize_rotation(T* R) {
+  for (int it = 0; it < 20; it++) {
+    double A[9], I[9];
+    for (int i = 0; i < 9; i++) A[i] = (double)R[i];
+    if (!inv3(A, I)) return;
+    double diff = 0;
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) {
+        const T n = (T)(0.5 * (A[3 * r + c] + I[3 * c + r]));
+        diff = std::max(diff, std::fabs((double)n - (double)R[3 * r + c]));
+        R[3 * r + c] = n;
+      }
+    if (diff < (sizeof(T) == 4 ? 1e-7 : 1e-15)) break;
+  }
+}
+// ExpSO3 (G2oTypes.cc:1011-1025)
+static void exp_so3(const double* w, double* R) {
+  const double d2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], d = std::sqrt(d2);
+  double W[9], W2[9];
+  skew(w, W);
+  mm3(W, W, W2);
+  if (d < 1e-5) {
+    for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0 ? 1.0 : 0.0) + W[i] + 0.5 * W2[i];
+  } else {
+    const double a = std::sin(d) / d, b = (1.0 - std::cos(d)) / d2;
+    for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0 ? 1.0 : 0.0) + W[i] * a + W2[i] * b;
+  }
+  normalize_rotation(R);
+}
+// LogSO3 (:1027-1041) -- note the float literal 0.5f and the early returns
+static void log_so3(const double* R, double* w) {
+  const double tr = R[0] + R[4] + R[8];
+  w[0] = (R[7] - R[5]) / 2; w[1] = (R[2] - R[6]) / 2; w[2] = (R[3] - R[1]) / 2;
+  const double costheta = (tr - 1.0) * 0.5f;
+  if (costheta > 1 || costheta < -1) return;
+  const double theta = std::acos(costheta), s = std::sin(theta);
+  if (std::fabs(s) < 1e-5) return;
+  for (int i = 0; i < 3; i++) w[i] = theta * w[i] / s;
+}
+// InverseRightJacobianSO3 (:1047-1061), RightJacobianSO3 (:1067-1082)
+static void inv_right_jac(const double* v, double* J) {
+  const double d2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2], d = std::sqrt(d2);
+  double W[9], W2[9];
+  skew(v, W);
+  mm3(W, W, W2);
+  if (d < 1e-5) { for (int i = 0; i < 9; i++) J[i] = (i % 4 == 0); return; }
+  const double k = 1.0 / d2 - (1.0 + std::cos(d)) / (2.0 * d * std::sin(d));
+  for (int i = 0; i < 9; i++) J[i] = (i % 4 == 0 ? 1.0 : 0.0) + W[i] / 2 + W2[i] * k;
+}
+static void right_jac(const double* v, double* J) {
+  const double d2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2], d = std::sqrt(d2);
+  double W[9], W2[9];
+  skew(v, W);
+  mm3(W, W, W2);
+  if (d < 1e-5) { for (int i = 0; i < 9; i++) J[i] = (i % 4 == 0); return; }
+  const double a = (1.0 - std::cos(d)) / d2, b = (d - std::sin(d)) / (d2 * d);
+  for (int i = 0; i < 9; i++) J[i] = (i % 4 == 0 ? 1.0 : 0.0) - W[i] * a + W2[i] * b;
+}
+
+// ---- float32 preintegration read side (ImuTypes.cc:283-313)
+struct Pre {
+  const float *dR, *dV, *dP, *JRg, *JVg, *JVa, *JPg, *JPa, *C;
+  float dT;
+  const float* b;  // bax bay baz bwx bwy bwz
+  explicit Pre(const float* r) {
+    dR = r; dV = r + 9; dP = r + 12; JRg = r + 15; JVg = r + 24; JVa = r + 33; JPg = r + 42; JPa = r + 51; C = r + 60;
+    dT = r[285]; b = r + 286;
+  }
+};
+static void so3f_exp(const float* w, float* R) {  // Sophus::SO3f::exp(w).matrix()
+  const float th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  float imag, real;
+  if (th2 < 1e-5f * 1e-5f) {
+    const float th4 = th2 * th2;
+    imag = 0.5f - (1.0f / 48.0f) * th2 + (1.0f / 3840.0f) * th4;
+    real = 1.0f - (1.0f / 8.0f) * th2 + (1.0f / 384.0f) * th4;
+  } else {
+    const float th = std::sqrt(th2), half = 0.5f * th;
+    imag = std::sin(half) / th;
+    real = std::cos(half);
+  }
+  const float qw = real, qx = imag * w[0], qy = imag * w[1], qz = imag * w[2];
+  const float tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
+  const float twx = tx * qw, twy = ty * qw, twz = tz * qw, txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy,
+              tyz = tz * qy, tzz = tz * qz;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+// corrected deltas for bias estimate (bg, ba) given as doubles, narrowed to float as IMU::Bias does
+static void delta_for_bias(const Pre& p, const double* bg, const double* ba, double* dR, double* dV, double* dP, double* dbg_out) {
+  const float dbg[3] = {(float)bg[0] - p.b[3], (float)bg[1] - p.b[4], (float)bg[2] - p.b[5]};
+  const float dba[3] = {(float)ba[0] - p.b[0], (float)ba[1] - p.b[1], (float)ba[2] - p.b[2]};
+  float w[3], E[9], R[9];
+  for (int r = 0; r < 3; r++) w[r] = p.JRg[3 * r] * dbg[0] + p.JRg[3 * r + 1] * dbg[1] + p.JRg[3 * r + 2] * dbg[2];
+  so3f_exp(w, E);
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) R[3 * r + c] = p.dR[3 * r] * E[c] + p.dR[3 * r + 1] * E[3 + c] + p.dR[3 * r + 2] * E[6 + c];
+  normalize_rotation(R);
+  for (int i = 0; i < 9; i++) dR[i] = (double)R[i];
+  for (int r = 0; r < 3; r++) {
+    const float v = p.dV[r] + (p.JVg[3 * r] * dbg[0] + p.JVg[3 * r + 1] * dbg[1] + p.JVg[3 * r + 2] * dbg[2]) +
+                    (p.JVa[3 * r] * dba[0] + p.JVa[3 * r + 1] * dba[1] + p.JVa[3 * r + 2] * dba[2]);
+    const float q = p.dP[r] + (p.JPg[3 * r] * dbg[0] + p.JPg[3 * r + 1] * dbg[1] + p.JPg[3 * r + 2] * dbg[2]) +
+                    (p.JPa[3 * r] * dba[0] + p.JPa[3 * r + 1] * dba[1] + p.JPa[3 * r + 2] * dba[2]);
+    dV[r] = (double)v;
+    dP[r] = (double)q;
+  }
+  if (dbg_out) for (int i = 0; i < 3; i++) dbg_out[i] = (double)dbg[i];
+}
+
+// ---- general dense helpers
+static bool invert_n(std::vector<double> A, int n, std::vector<double>& inv) {  // Gauss-Jordan, partial pivoting
+  inv.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; i++) inv[(size_t)i * n + i] = 1.0;
+  for (int c = 0; c < n; c++) {
+    int piv = c;
+    for (int r = c + 1; r < n; r++)
+      if (std::fabs(A[(size_t)r * n + c]) > std::fabs(A[(size_t)piv * n + c])) piv = r;
+    if (A[(size_t)piv * n + c] == 0.0) return false;
+    if (piv != c)
+      for (int k = 0; k < n; k++) { std::swap(A[(size_t)c * n + k], A[(size_t)piv * n + k]); std::swap(inv[(size_t)c * n + k], inv[(size_t)piv * n + k]); }
+    const double d = 1.0 / A[(size_t)c * n + c];
+    for (int k = 0; k < n; k++) { A[(size_t)c * n + k] *= d; inv[(size_t)c * n + k] *= d; }
+    for (int r = 0; r < n; r++) {
+      if (r == c) continue;
+      const double f = A[(size_t)r * n + c];
+      if (f == 0.0) continue;
+      for (int k = 0; k < n; k++) { A[(size_t)r * n + k] -= f * A[(size_t)c * n + k]; inv[(size_t)r * n + k] -= f * inv[(size_t)c * n + k]; }
+    }
+  }
+  return true;
+}
+// symmetric eigen-decomposition by cyclic Jacobi: A = V diag(e) V^T
+static void jacobi_eig(std::vector<double> A, int n, std::vector<double>& e, std::vector<double>& V) {
+  V.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; i++) V[(size_t)i * n + i] = 1.0;
+  for (int sweep = 0; sweep < 100; sweep++) {
+    double off = 0, diag = 0;
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) (i == j ? diag : off) += A[(size_t)i * n + j] * A[(size_t)i * n + j];
+    if (off <= 1e-32 * diag) break;
+    for (int p = 0; p < n; p++)
+      for (int q = p + 1; q < n; q++) {
+        const double apq = A[(size_t)p * n + q];
+        if (apq == 0.0) continue;
+        const double theta = (A[(size_t)q * n + q] - A[(size_t)p * n + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < n; k++) {
+          const double akp = A[(size_t)k * n + p], akq = A[(size_t)k * n + q];
+          A[(size_t)k * n + p] = c * akp - s * akq;
+          A[(size_t)k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; k++) {
+          const double apk = A[(size_t)p * n + k], aqk = A[(size_t)q * n + k];
+          A[(size_t)p * n + k] = c * apk - s * aqk;
+          A[(size_t)q * n + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; k++) {
+          const double vkp = V[(size_t)k * n + p], vkq = V[(size_t)k * n + q];
+          V[(size_t)k * n + p] = c * vkp - s * vkq;
+          V[(size_t)k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  e.resize(n);
+  for (int i = 0; i < n; i++) e[i] = A[(size_t)i * n + i];
+}
+// EdgeInertial information (G2oTypes.cc:487-494): inverse of C[0:9,0:9], symmetrised, eigenvalues < 1e-12 zeroed
+static void inertial_information(const float* C15, double* Info81) {
+  std::vector<double> C(81), Ci, e, V;
+  for (int r = 0; r < 9; r++)
+    for (int c = 0; c < 9; c++) C[9 * r + c] = (double)C15[15 * r + c];
+  invert_n(C, 9, Ci);
+  std::vector<double> S(81);
+  for (int r = 0; r < 9; r++)
+    for (int c = 0; c < 9; c++) S[9 * r + c] = (Ci[9 * r + c] + Ci[9 * c + r]) / 2;
+  jacobi_eig(S, 9, e, V);
+  for (int i = 0; i < 9; i++)
+    if (e[i] < 1e-12) e[i] = 0;
+  for (int r = 0; r < 9; r++)
+    for (int c = 0; c < 9; c++) {
+      double s = 0;
+      for (int k = 0; k < 9; k++) s += V[9 * r + k] * e[k] * V[9 * c + k];
+      Info81[9 * r + c] = s;
+    }
+}
+
+struct KF {
+  double Rwb[9], twb[3], Rcw[9], tcw[3], vel[3], bg[3], ba[3];
+};
+struct State {
+  std::vector<KF> kf;
+  std::vector<double> pt;
+};
+
+struct Problem {
+  const GfsBaProblem* P;
+  int nOpt, nKf, nPt, nObs, nIn, dimP;
+  std::vector<double> infoIn;  // [nIn][81]
+  std::vector<double> infoG, infoA;  // [nIn][9]
+  double deltaMono, deltaStereo, deltaIn;
+};
+
+// ImuCamPose::Update (G2oTypes.cc:191-217)
+static void kf_update(const GfsBaProblem& P, KF& k, const double* pu) {
+  double t[3], E[9];
+  mv3(k.Rwb, pu + 3, t);
+  for (int i = 0; i < 3; i++) k.twb[i] += t[i];
+  exp_so3(pu, E);
+  mm3(k.Rwb, E, k.Rwb);
+  // (NormalizeRotation(Rwb) every third update: its result is discarded in the reference, :203-207)
+  double Rbw[9], tbw[3];
+  mt3(k.Rwb, Rbw);
+  mv3(Rbw, k.twb, tbw);
+  for (int i = 0; i < 3; i++) tbw[i] = -tbw[i];
+  mm3(P.Rcb, Rbw, k.Rcw);
+  mv3(P.Rcb, tbw, k.tcw);
+  for (int i = 0; i < 3; i++) k.tcw[i] += P.tcb[i];
+}
+
+// visual edge error: obs - Project[Stereo](Xw)  (G2oTypes.cc:172-188)
+static int vis_error(const GfsBaProblem& P, const KF& k, const double* Xw, const double* obs, double* err, double* Xc_out) {
+  double Xc[3];
+  mv3(k.Rcw, Xw, Xc);
+  for (int i = 0; i < 3; i++) Xc[i] += k.tcw[i];
+  const double u = P.fx * Xc[0] / Xc[2] + P.cx, v = P.fy * Xc[1] / Xc[2] + P.cy;
+  if (Xc_out) memcpy(Xc_out, Xc, sizeof(Xc));
+  err[0] = obs[0] - u;
+  err[1] = obs[1] - v;
+  if (obs[2] < 0) return 2;
+  const double invZ = 1 / Xc[2];
+  err[2] = obs[2] - (u - P.bf * invZ);
+  return 3;
+}
+static inline void huber(double e, double delta, double* rho) {  // robust_kernel_impl.cpp:77-91
+  const double dsqr = delta * delta;
+  if (e <= dsqr) { rho[0] = e; rho[1] = 1.; rho[2] = 0.; }
+  else { const double sq = std::sqrt(e); rho[0] = 2 * sq * delta - dsqr; rho[1] = delta / sq; rho[2] = -0.5 * rho[1] / e; }
+}
+
+// EdgeInertial::computeError (G2oTypes.cc:495-522)
+static void inertial_error(const Problem& pr, const State& s, int e, double* err9) {
+  const GfsBaProblem& P = *pr.P;
+  const KF& k1 = s.kf[P.in_kf1[e]];
+  const KF& k2 = s.kf[P.in_kf2[e]];
+  const Pre pre(P.in_pre + (size_t)e * GFS_BA_PRE_STRIDE);
+  double dR[9], dV[3], dP[3];
+  delta_for_bias(pre, k1.bg, k1.ba, dR, dV, dP, nullptr);
+  const double dt = (double)pre.dT;
+  const double g[3] = {0, 0, -(double)9.81f};
+  double dRt[9], Rbw1[9], A[9], eR[9];
+  mt3(dR, dRt);
+  mt3(k1.Rwb, Rbw1);
+  mm3(dRt, Rbw1, A);
+  mm3(A, k2.Rwb, eR);
+  log_so3(eR, err9);
+  double tv[3], tp[3];
+  for (int i = 0; i < 3; i++) {
+    tv[i] = k2.vel[i] - k1.vel[i] - g[i] * dt;
+    tp[i] = k2.twb[i] - k1.twb[i] - k1.vel[i] * dt - g[i] * dt * dt / 2;
+  }
+  double rv[3], rp[3];
+  mv3(Rbw1, tv, rv);
+  mv3(Rbw1, tp, rp);
+  for (int i = 0; i < 3; i++) { err9[3 + i] = rv[i] - dV[i]; err9[6 + i] = rp[i] - dP[i]; }
+}
+// EdgeInertial::linearizeOplus (:524-719): J is 9 x 24, columns [pose1(6) vel1(3) bg1(3) ba1(3) pose2(6) vel2(3)]
+static void inertial_jacobian(const Problem& pr, const State& s, int e, double* J /*9x24*/) {
+  const GfsBaProblem& P = *pr.P;
+  const KF& k1 = s.kf[P.in_kf1[e]];
+  const KF& k2 = s.kf[P.in_kf2[e]];
+  const Pre pre(P.in_pre + (size_t)e * GFS_BA_PRE_STRIDE);
+  double dR[9], dV[3], dP[3], dbg[3];
+  delta_for_bias(pre, k1.bg, k1.ba, dR, dV, dP, dbg);
+  const double dt = (double)pre.dT;
+  const double g[3] = {0, 0, -(double)9.81f};
+  double JRg[9], JVg[9], JPg[9], JVa[9], JPa[9];
+  for (int i = 0; i < 9; i++) { JRg[i] = pre.JRg[i]; JVg[i] = pre.JVg[i]; JPg[i] = pre.JPg[i]; JVa[i] = pre.JVa[i]; JPa[i] = pre.JPa[i]; }
+  double Rbw1[9], dRt[9], A[9], eR[9], er[3], invJr[9];
+  mt3(k1.Rwb, Rbw1);
+  mt3(dR, dRt);
+  mm3(dRt, Rbw1, A);
+  mm3(A, k2.Rwb, eR);
+  log_so3(eR, er);
+  inv_right_jac(er, invJr);
+  memset(J, 0, sizeof(double) * 9 * 24);
+  auto put = [&](int r0, int c0, const double* M, double sgn) {
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) J[(r0 + r) * 24 + c0 + c] = sgn * M[3 * r + c];
+  };
+  double Rwb2t[9], T1[9], T2[9];
+  mt3(k2.Rwb, Rwb2t);
+  mm3(invJr, Rwb2t, T1);
+  mm3(T1, k1.Rwb, T2);
+  put(0, 0, T2, -1.0);  // -invJr * Rwb2^T * Rwb1
+  double tv[3], tp[3], v[3], W[9];
+  for (int i = 0; i < 3; i++) {
+    tv[i] = k2.vel[i] - k1.vel[i] - g[i] * dt;
+    tp[i] = k2.twb[i] - k1.twb[i] - k1.vel[i] * dt - 0.5 * g[i] * dt * dt;
+  }
+  mv3(Rbw1, tv, v); skew(v, W); put(3, 0, W, 1.0);
+  mv3(Rbw1, tp, v); skew(v, W); put(6, 0, W, 1.0);
+  const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  put(6, 3, I3, -1.0);
+  // velocity 1
+  put(3, 6, Rbw1, -1.0);
+  { double M[9]; for (int i = 0; i < 9; i++) M[i] = Rbw1[i] * dt; put(6, 6, M, -1.0); }
+  // gyro bias 1
+  {
+    double w[3], Jr[9], eRt[9], M1[9], M2[9], M3_[9];
+    mv3(JRg, dbg, w);
+    right_jac(w, Jr);
+    mt3(eR, eRt);
+    mm3(invJr, eRt, M1);
+    mm3(M1, Jr, M2);
+    mm3(M2, JRg, M3_);
+    put(0, 9, M3_, -1.0);
+    put(3, 9, JVg, -1.0);
+    put(6, 9, JPg, -1.0);
+  }
+  // acc bias 1
+  put(3, 12, JVa, -1.0);
+  put(6, 12, JPa, -1.0);
+  // pose 2
+  put(0, 15, invJr, 1.0);
+  { double M[9]; mm3(Rbw1, k2.Rwb, M); put(6, 18, M, 1.0); }
+  // velocity 2
+  put(3, 21, Rbw1, 1.0);
+}
+
+// pose-side layout: keyframe k (< nOpt) owns dofs [15k, 15k+15): pose 6, vel 3, bg 3, ba 3
+struct System {
+  int dimP, nPt;
+  std::vector<double> Hpp, bp;       // dimP x dimP, dimP
+  std::vector<double> Hll, bl;       // nPt x 9, nPt x 3
+  std::vector<double> Hpl;           // nObs x 18 (6x3, row-major), zero for fixed keyframes
+  std::vector<double> x;             // dimP + 3 nPt
+};
+
+static double robust_chi2(const Problem& pr, const State& s, std::vector<double>* chi2_vis) {
+  const GfsBaProblem& P = *pr.P;
+  double chi = 0, rho[3];
+  for (int e = 0; e < pr.nIn; e++) {
+    double r[9];
+    inertial_error(pr, s, e, r);
+    const double* I = &pr.infoIn[(size_t)e * 81];
+    double c2 = 0;
+    for (int a = 0; a < 9; a++)
+      for (int b = 0; b < 9; b++) c2 += r[a] * I[9 * a + b] * r[b];
+    huber(c2, pr.deltaIn, rho);
+    chi += rho[0];
+    const KF& k1 = s.kf[P.in_kf1[e]];
+    const KF& k2 = s.kf[P.in_kf2[e]];
+    double rg[3], ra[3];
+    for (int i = 0; i < 3; i++) { rg[i] = k2.bg[i] - k1.bg[i]; ra[i] = k2.ba[i] - k1.ba[i]; }
+    const double *G = &pr.infoG[(size_t)e * 9], *A = &pr.infoA[(size_t)e * 9];
+    double cg = 0, ca = 0;
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) { cg += rg[a] * G[3 * a + b] * rg[b]; ca += ra[a] * A[3 * a + b] * ra[b]; }
+    chi += cg + ca;
+  }
+  for (int e = 0; e < pr.nObs; e++) {
+    double r[3];
+    const int d = vis_error(P, s.kf[P.obs_kf[e]], &s.pt[3 * (size_t)P.obs_pt[e]], P.obs_uvr + 3 * (size_t)e, r, nullptr);
+    const double w = (double)P.obs_inv_sigma2[e];
+    double c2 = 0;
+    for (int a = 0; a < d; a++) c2 += r[a] * w * r[a];
+    if (chi2_vis) (*chi2_vis)[e] = c2;
+    huber(c2, d == 2 ? pr.deltaMono : pr.deltaStereo, rho);
+    chi += rho[0];
+  }
+  return chi;
+}
+
+static void build_system(const Problem& pr, const State& s, System& S) {
+  const GfsBaProblem& P = *pr.P;
+  const int dimP = pr.dimP;
+  S.dimP = dimP; S.nPt = pr.nPt;
+  S.Hpp.assign((size_t)dimP * dimP, 0.0); S.bp.assign(dimP, 0.0);
+  S.Hll.assign((size_t)pr.nPt * 9, 0.0); S.bl.assign((size_t)pr.nPt * 3, 0.0);
+  S.Hpl.assign((size_t)pr.nObs * 18, 0.0);
+  double rho[3];
+  // inertial + random-walk edges
+  for (int e = 0; e < pr.nIn; e++) {
+    const int k1 = P.in_kf1[e], k2 = P.in_kf2[e];
+    double J[9 * 24], r[9];
+    inertial_error(pr, s, e, r);
+    inertial_jacobian(pr, s, e, J);
+    const double* I = &pr.infoIn[(size_t)e * 81];
+    double c2 = 0;
+    for (int a = 0; a < 9; a++)
+      for (int b = 0; b < 9; b++) c2 += r[a] * I[9 * a + b] * r[b];
+    huber(c2, pr.deltaIn, rho);
+    // global dof of each of the 24 columns (-1: fixed)
+    int col[24];
+    for (int c = 0; c < 15; c++) col[c] = (k1 < pr.nOpt) ? 15 * k1 + c : -1;
+    for (int c = 0; c < 9; c++) col[15 + c] = (k2 < pr.nOpt) ? 15 * k2 + c : -1;
+    double WJ[9 * 24], Wr[9];
+    for (int a = 0; a < 9; a++) {
+      for (int c = 0; c < 24; c++) {
+        double t = 0;
+        for (int b = 0; b < 9; b++) t += I[9 * a + b] * J[b * 24 + c];
+        WJ[a * 24 + c] = rho[1] * t;
+      }
+      double t = 0;
+      for (int b = 0; b < 9; b++) t += I[9 * a + b] * r[b];
+      Wr[a] = -rho[1] * t;
+    }
+    for (int c1 = 0; c1 < 24; c1++) {
+      if (col[c1] < 0) continue;
+      double t = 0;
+      for (int a = 0; a < 9; a++) t += J[a * 24 + c1] * Wr[a];
+      S.bp[col[c1]] += t;
+      for (int c2i = 0; c2i < 24; c2i++) {
+        if (col[c2i] < 0) continue;
+        double h = 0;
+        for (int a = 0; a < 9; a++) h += J[a * 24 + c1] * WJ[a * 24 + c2i];
+        S.Hpp[(size_t)col[c1] * dimP + col[c2i]] += h;
+      }
+    }
+    // EdgeGyroRW / EdgeAccRW: r = b2 - b1, J = [-I, I], no robust kernel
+    const KF& a1 = s.kf[k1];
+    const KF& a2 = s.kf[k2];
+    for (int which = 0; which < 2; which++) {
+      const double* Om = which == 0 ? &pr.infoG[(size_t)e * 9] : &pr.infoA[(size_t)e * 9];
+      double rr[3];
+      for (int i = 0; i < 3; i++) rr[i] = which == 0 ? a2.bg[i] - a1.bg[i] : a2.ba[i] - a1.ba[i];
+      const int o1 = (k1 < pr.nOpt) ? 15 * k1 + 9 + 3 * which : -1, o2 = (k2 < pr.nOpt) ? 15 * k2 + 9 + 3 * which : -1;
+      double Or[3];
+      for (int a = 0; a < 3; a++) Or[a] = Om[3 * a] * rr[0] + Om[3 * a + 1] * rr[1] + Om[3 * a + 2] * rr[2];
+      for (int a = 0; a < 3; a++) {
+        if (o1 >= 0) S.bp[o1 + a] += Or[a];   // -J1^T Om r with J1 = -I
+        if (o2 >= 0) S.bp[o2 + a] += -Or[a];
+        for (int b = 0; b < 3; b++) {
+          if (o1 >= 0) S.Hpp[(size_t)(o1 + a) * dimP + o1 + b] += Om[3 * a + b];
+          if (o2 >= 0) S.Hpp[(size_t)(o2 + a) * dimP + o2 + b] += Om[3 * a + b];
+          if (o1 >= 0 && o2 >= 0) {
+            S.Hpp[(size_t)(o1 + a) * dimP + o2 + b] += -Om[3 * a + b];
+            S.Hpp[(size_t)(o2 + a) * dimP + o1 + b] += -Om[3 * b + a];
+          }
+        }
+      }
+    }
+  }
+  // visual edges (EdgeMono / EdgeStereo linearizeOplus + BaseBinaryEdge::constructQuadraticForm)
+  for (int e = 0; e < pr.nObs; e++) {
+    const int k = P.obs_kf[e], j = P.obs_pt[e];
+    const KF& kf = s.kf[k];
+    double r[3], Xc[3];
+    const int d = vis_error(P, kf, &s.pt[3 * (size_t)j], P.obs_uvr + 3 * (size_t)e, r, Xc);
+    const double w0 = (double)P.obs_inv_sigma2[e];
+    double c2 = 0;
+    for (int a = 0; a < d; a++) c2 += r[a] * w0 * r[a];
+    huber(c2, d == 2 ? pr.deltaMono : pr.deltaStereo, rho);
+    const double w = rho[1] * w0;
+    double pj[9] = {0};
+    pj[0] = P.fx / Xc[2]; pj[1] = 0.f; pj[2] = -P.fx * Xc[0] / (Xc[2] * Xc[2]);
+    pj[3] = 0.f; pj[4] = P.fy / Xc[2]; pj[5] = -P.fy * Xc[1] / (Xc[2] * Xc[2]);
+    if (d == 3) { pj[6] = pj[0]; pj[7] = pj[1]; pj[8] = pj[2] + P.bf * (1.0 / (Xc[2] * Xc[2])); }
+    double Jl[9] = {0};  // d x 3 = -proj_jac * Rcw
+    for (int a = 0; a < d; a++)
+      for (int c = 0; c < 3; c++) Jl[3 * a + c] = -(pj[3 * a] * kf.Rcw[c] + pj[3 * a + 1] * kf.Rcw[3 + c] + pj[3 * a + 2] * kf.Rcw[6 + c]);
+    double Xb[3];
+    mv3(P.Rbc, Xc, Xb);
+    for (int i = 0; i < 3; i++) Xb[i] += P.tbc[i];
+    const double D[18] = {0.0, Xb[2], -Xb[1], 1.0, 0.0, 0.0, -Xb[2], 0.0, Xb[0], 0.0, 1.0, 0.0, Xb[1], -Xb[0], 0.0, 0.0, 0.0, 1.0};
+    double PR[9] = {0}, Jp[18] = {0};  // d x 6 = proj_jac * Rcb * SE3deriv
+    for (int a = 0; a < d; a++)
+      for (int c = 0; c < 3; c++) PR[3 * a + c] = pj[3 * a] * P.Rcb[c] + pj[3 * a + 1] * P.Rcb[3 + c] + pj[3 * a + 2] * P.Rcb[6 + c];
+    for (int a = 0; a < d; a++)
+      for (int c = 0; c < 6; c++) Jp[6 * a + c] = PR[3 * a] * D[c] + PR[3 * a + 1] * D[6 + c] + PR[3 * a + 2] * D[12 + c];
+    // point block
+    for (int a = 0; a < 3; a++) {
+      double t = 0;
+      for (int q = 0; q < d; q++) t += Jl[3 * q + a] * (-w * r[q]);
+      S.bl[3 * (size_t)j + a] += t;
+      for (int b = 0; b < 3; b++) {
+        double h = 0;
+        for (int q = 0; q < d; q++) h += Jl[3 * q + a] * w * Jl[3 * q + b];
+        S.Hll[9 * (size_t)j + 3 * a + b] += h;
+      }
+    }
+    if (k < pr.nOpt) {
+      const int o = 15 * k;
+      for (int a = 0; a < 6; a++) {
+        double t = 0;
+        for (int q = 0; q < d; q++) t += Jp[6 * q + a] * (-w * r[q]);
+        S.bp[o + a] += t;
+        for (int b = 0; b < 6; b++) {
+          double h = 0;
+          for (int q = 0; q < d; q++) h += Jp[6 * q + a] * w * Jp[6 * q + b];
+          S.Hpp[(size_t)(o + a) * dimP + o + b] += h;
+        }
+        for (int b = 0; b < 3; b++) {
+          double h = 0;
+          for (int q = 0; q < d; q++) h += Jp[6 * q + a] * w * Jl[3 * q + b];
+          S.Hpl[18 * (size_t)e + 3 * a + b] = h;
+        }
+      }
+    }
+  }
+}
+
+// dense LDL^T without pivoting, in place on the lower triangle; false on a zero / non-finite pivot
+static bool ldlt_solve(std::vector<double>& A, int n, std::vector<double>& b) {
+  for (int j = 0; j < n; j++) {
+    double d = A[(size_t)j * n + j];
+    for (int k = 0; k < j; k++) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k] * A[(size_t)k * n + k];
+    if (d == 0.0 || !std::isfinite(d)) return false;
+    A[(size_t)j * n + j] = d;
+    for (int i = j + 1; i < n; i++) {
+      double v = A[(size_t)i * n + j];
+      for (int k = 0; k < j; k++) v -= A[(size_t)i * n + k] * A[(size_t)j * n + k] * A[(size_t)k * n + k];
+      A[(size_t)i * n + j] = v / d;
+    }
+  }
+  for (int i = 0; i < n; i++) {
+    double v = b[i];
+    for (int k = 0; k < i; k++) v -= A[(size_t)i * n + k] * b[k];
+    b[i] = v;
+  }
+  for (int i = 0; i < n; i++) b[i] /= A[(size_t)i * n + i];
+  for (int i = n - 1; i >= 0; i--) {
+    double v = b[i];
+    for (int k = i + 1; k < n; k++) v -= A[(size_t)k * n + i] * b[k];
+    b[i] = v;
+  }
+  return true;
+}
+
+// BlockSolver::solve with Schur complement (block_solver.hpp:354-486) for damping lambda
+static bool schur_solve(const Problem& pr, const System& S, double lambda, std::vector<double>& x) {
+  const GfsBaProblem& P = *pr.P;
+  const int n = S.dimP;
+  std::vector<double> Hs = S.Hpp, bs = S.bp;
+  std::vector<uint8_t> used(n, 0);
+  for (int k = 0; k < pr.nOpt; k++) {
+    const int nd = P.kf_has_imu[k] ? 15 : 6;
+    for (int d = 0; d < nd; d++) used[15 * k + d] = 1;
+  }
+  for (int i = 0; i < n; i++) {
+    if (used[i]) Hs[(size_t)i * n + i] += lambda;
+    else { Hs[(size_t)i * n + i] = 1.0; bs[i] = 0.0; }  // dofs that are not vertices (keyframe without IMU)
+  }
+  std::vector<double> Dinv((size_t)pr.nPt * 9), db((size_t)pr.nPt * 3);
+  std::vector<std::vector<int>> byPt(pr.nPt);
+  for (int e = 0; e < pr.nObs; e++)
+    if (P.obs_kf[e] < pr.nOpt) byPt[P.obs_pt[e]].push_back(e);
+  for (int j = 0; j < pr.nPt; j++) {
+    double D[9];
+    memcpy(D, &S.Hll[9 * (size_t)j], sizeof(D));
+    D[0] += lambda; D[4] += lambda; D[8] += lambda;
+    inv3(D, &Dinv[9 * (size_t)j]);
+    mv3(&Dinv[9 * (size_t)j], &S.bl[3 * (size_t)j], &db[3 * (size_t)j]);
+    for (int e1 : byPt[j]) {
+      const double* B1 = &S.Hpl[18 * (size_t)e1];
+      const int o1 = 15 * P.obs_kf[e1];
+      double BD[18];
+      for (int a = 0; a < 6; a++)
+        for (int c = 0; c < 3; c++)
+          BD[3 * a + c] = B1[3 * a] * Dinv[9 * (size_t)j + c] + B1[3 * a + 1] * Dinv[9 * (size_t)j + 3 + c] + B1[3 * a + 2] * Dinv[9 * (size_t)j + 6 + c];
+      for (int a = 0; a < 6; a++) bs[o1 + a] -= B1[3 * a] * db[3 * (size_t)j] + B1[3 * a + 1] * db[3 * (size_t)j + 1] + B1[3 * a + 2] * db[3 * (size_t)j + 2];
+      for (int e2 : byPt[j]) {
+        const double* B2 = &S.Hpl[18 * (size_t)e2];
+        const int o2 = 15 * P.obs_kf[e2];
+        for (int a = 0; a < 6; a++)
+          for (int b = 0; b < 6; b++)
+            Hs[(size_t)(o1 + a) * n + o2 + b] -= BD[3 * a] * B2[3 * b] + BD[3 * a + 1] * B2[3 * b + 1] + BD[3 * a + 2] * B2[3 * b + 2];
+      }
+    }
+  }
+  if (!ldlt_solve(Hs, n, bs)) return false;
+  x.assign((size_t)n + 3 * (size_t)pr.nPt, 0.0);
+  for (int i = 0; i < n; i++) x[i] = used[i] ? bs[i] : 0.0;
+  for (int j = 0; j < pr.nPt; j++) {
+    double c[3] = {S.bl[3 * (size_t)j], S.bl[3 * (size_t)j + 1], S.bl[3 * (size_t)j + 2]};
+    for (int e : byPt[j]) {
+      const double* B = &S.Hpl[18 * (size_t)e];
+      const double* xp = &x[15 * (size_t)P.obs_kf[e]];
+      for (int b = 0; b < 3; b++)
+        for (int a = 0; a < 6; a++) c[b] -= B[3 * a + b] * xp[a];
+    }
+    mv3(&Dinv[9 * (size_t)j], c, &x[(size_t)n + 3 * (size_t)j]);
+  }
+  return true;
+}
+
+static void apply_update(const Problem& pr, State& s, const std::vector<double>& x) {
+  const GfsBaProblem& P = *pr.P;
+  for (int k = 0; k < pr.nOpt; k++) {
+    const double* u = &x[15 * (size_t)k];
+    kf_update(P, s.kf[k], u);
+    if (P.kf_has_imu[k])
+      for (int i = 0; i < 3; i++) { s.kf[k].vel[i] += u[6 + i]; s.kf[k].bg[i] += u[9 + i]; s.kf[k].ba[i] += u[12 + i]; }
+  }
+  for (size_t i = 0; i < s.pt.size(); i++) s.pt[i] += x[(size_t)pr.dimP + i];
+}
+
+static void setup(const GfsBaProblem* P, Problem& pr, State& s) {
+  pr.P = P;
+  pr.nOpt = P->n_opt_kf; pr.nKf = P->n_opt_kf + P->n_fixed_kf; pr.nPt = P->n_points; pr.nObs = P->n_obs; pr.nIn = P->n_inertial;
+  pr.dimP = 15 * pr.nOpt;
+  pr.deltaMono = (double)(float)std::sqrt(5.991);    // const float thHuberMono = sqrt(5.991), Optimizer.cc:3427
+  pr.deltaStereo = (double)(float)std::sqrt(7.815);  // :3429
+  pr.deltaIn = std::sqrt(16.0);                      // :3372
+  pr.infoIn.resize((size_t)pr.nIn * 81); pr.infoG.resize((size_t)pr.nIn * 9); pr.infoA.resize((size_t)pr.nIn * 9);
+  for (int e = 0; e < pr.nIn; e++) {
+    const float* C = P->in_pre + (size_t)e * GFS_BA_PRE_STRIDE + 60;
+    inertial_information(C, &pr.infoIn[(size_t)e * 81]);
+    if (P->in_downweight[e])
+      for (int i = 0; i < 81; i++) pr.infoIn[(size_t)e * 81 + i] *= 1e-2;
+    double G[9], A[9];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) { G[3 * r + c] = (double)C[15 * (9 + r) + 9 + c]; A[3 * r + c] = (double)C[15 * (12 + r) + 12 + c]; }
+    inv3(G, &pr.infoG[(size_t)e * 9]);
+    inv3(A, &pr.infoA[(size_t)e * 9]);
+  }
+  s.kf.resize(pr.nKf);
+  for (int k = 0; k < pr.nKf; k++) {
+    memcpy(s.kf[k].Rwb, P->kf_Rwb + 9 * (size_t)k, 72); memcpy(s.kf[k].twb, P->kf_twb + 3 * (size_t)k, 24);
+    memcpy(s.kf[k].Rcw, P->kf_Rcw + 9 * (size_t)k, 72); memcpy(s.kf[k].tcw, P->kf_tcw + 3 * (size_t)k, 24);
+    memcpy(s.kf[k].vel, P->kf_vel + 3 * (size_t)k, 24); memcpy(s.kf[k].bg, P->kf_bg + 3 * (size_t)k, 24);
+    memcpy(s.kf[k].ba, P->kf_ba + 3 * (size_t)k, 24);
+  }
+  s.pt.assign(P->pt_xyz, P->pt_xyz + 3 * (size_t)pr.nPt);
+}
+
+static void solve(const GfsBaProblem* P, GfsBaResult* R) {
+  Problem pr;
+  State s;
+  setup(P, pr, s);
+  std::vector<double> chi2v(pr.nObs, 0.0);
+  // optimizer.computeActiveErrors(); err = activeRobustChi2()  (Optimizer.cc:3589-3590)
+  double lastChi = robust_chi2(pr, s, &chi2v);
+  R->err = (float)lastChi;
+  // optimizer.optimize(opt_it): sparse_optimizer.cpp:354-420 + optimization_algorithm_levenberg.cpp:59-164
+  double lambda = 0, ni = 2;
+  int nBad = 0, done = 0, trials = 0;
+  System S;
+  std::vector<double> x;
+  for (int it = 0; it < P->iterations; it++) {
+    double currentChi = robust_chi2(pr, s, &chi2v);
+    lastChi = currentChi;
+    const double iniChi = currentChi;
+    double tempChi = currentChi;
+    build_system(pr, s, S);
+    if (it == 0) { lambda = P->lambda_init; ni = 2; nBad = 0; }
+    double rho = 0;
+    int qmax = 0;
+    do {
+      State backup = s;
+      const bool ok2 = schur_solve(pr, S, lambda, x);
+      if (ok2) apply_update(pr, s, x);
+      else x.assign((size_t)pr.dimP + 3 * (size_t)pr.nPt, 0.0);
+      tempChi = robust_chi2(pr, s, &chi2v);
+      lastChi = tempChi;
+      if (!ok2) tempChi = std::numeric_limits<double>::max();
+      rho = currentChi - tempChi;
+      double scale = 0;
+      for (int j = 0; j < pr.dimP; j++) scale += x[j] * (lambda * x[j] + S.bp[j]);
+      for (size_t j = 0; j < 3 * (size_t)pr.nPt; j++) scale += x[(size_t)pr.dimP + j] * (lambda * x[(size_t)pr.dimP + j] + S.bl[j]);
+      scale += 1e-3;
+      rho /= scale;
+      if (rho > 0 && std::isfinite(tempChi)) {
+        double alpha = 1. - std::pow((2 * rho - 1), 3);
+        alpha = std::min(alpha, 2. / 3.);
+        const double sf = std::max(1. / 3., alpha);
+        lambda *= sf;
+        ni = 2;
+        currentChi = tempChi;
+      } else {
+        lambda *= ni;
+        ni *= 2;
+        s = backup;  // pop(): the per-edge errors keep the values of the rejected trial
+      }
+      qmax++;
+      trials++;
+    } while (rho < 0 && qmax < 10);
+    done++;
+    if (qmax == 10 || rho == 0) break;  // Terminate
+    if ((iniChi - currentChi) * 1e3 < iniChi) nBad++;
+    else nBad = 0;
+    if (nBad >= 3) break;
+  }
+  // err_end = activeRobustChi2() over the stored edge errors, i.e. those of the last evaluated LM
+  // trial, accepted or not (g2o does not recompute errors after pop(); Optimizer.cc:3592)
+  R->err_end = (float)lastChi;
+  R->iterations_done = done;
+  R->lm_trials = trials;
+  R->lambda_final = lambda;
+  R->failed = ((2 * R->err < R->err_end || std::isnan(R->err) || std::isnan(R->err_end)) && !P->b_large) ? 1 : 0;
+  const float chi2Mono2 = 5.991f, chi2Stereo2 = 7.815f;
+  for (int e = 0; e < pr.nObs; e++) {
+    const int k = P->obs_kf[e], j = P->obs_pt[e];
+    const bool mono = P->obs_uvr[3 * (size_t)e + 2] < 0;
+    const double c2 = chi2v[e];
+    R->obs_chi2[e] = c2;
+    const KF& kf = s.kf[k];
+    const double z = kf.Rcw[6] * s.pt[3 * (size_t)j] + kf.Rcw[7] * s.pt[3 * (size_t)j + 1] + kf.Rcw[8] * s.pt[3 * (size_t)j + 2] + kf.tcw[2];
+    const bool dpos = mono ? (z > 0.0) : true;
+    R->obs_depth_positive[e] = dpos;
+    bool out;
+    if (mono) {
+      const bool close = P->pt_close[j] != 0;
+      out = (c2 > chi2Mono2 && !close) || (c2 > 1.5f * chi2Mono2 && close) || !dpos;
+    } else {
+      out = c2 > chi2Stereo2;
+    }
+    R->obs_outlier[e] = out;
+  }
+  for (int k = 0; k < pr.nKf; k++) {
+    memcpy(R->kf_Rwb + 9 * (size_t)k, s.kf[k].Rwb, 72); memcpy(R->kf_twb + 3 * (size_t)k, s.kf[k].twb, 24);
+    memcpy(R->kf_Rcw + 9 * (size_t)k, s.kf[k].Rcw, 72); memcpy(R->kf_tcw + 3 * (size_t)k, s.kf[k].tcw, 24);
+    memcpy(R->kf_vel + 3 * (size_t)k, s.kf[k].vel, 24); memcpy(R->kf_bg + 3 * (size_t)k, s.kf[k].bg, 24);
+    memcpy(R->kf_ba + 3 * (size_t)k, s.kf[k].ba, 24);
+  }
+  memcpy(R->pt_xyz, s.pt.data(), sizeof(double) * s.pt.size());
+}
+
+}  // namespace ba
+}  // namespace gfo
+
+extern "C" {
+
+void gfo_ba_solve(const GfsBaProblem* P, GfsBaResult* R) { gfo::ba::solve(P, R); }
+
+// ---- stage hooks for the oracle's own validation
+// robust chi2 of the problem at its initial state
+double gfo_ba_chi2(const GfsBaProblem* P) {
+  gfo::ba::Problem pr;
+  gfo::ba::State s;
+  gfo::ba::setup(P, pr, s);
+  return gfo::ba::robust_chi2(pr, s, nullptr);
+}
+// 9-D inertial error and 9x24 Jacobian of edge e at the problem's initial state
+void gfo_ba_inertial(const GfsBaProblem* P, int e, double* err9, double* J216, double* info81) {
+  gfo::ba::Problem pr;
+  gfo::ba::State s;
+  gfo::ba::setup(P, pr, s);
+  gfo::ba::inertial_error(pr, s, e, err9);
+  gfo::ba::inertial_jacobian(pr, s, e, J216);
+  memcpy(info81, &pr.infoIn[(size_t)e * 81], 81 * sizeof(double));
+}
+// normal equations at the initial state: Hpp (dimP x dimP), bp, Hll (nPt x 9), bl (nPt x 3), Hpl (nObs x 18)
+void gfo_ba_system(const GfsBaProblem* P, double* Hpp, double* bp, double* Hll, double* bl, double* Hpl) {
+  gfo::ba::Problem pr;
+  gfo::ba::State s;
+  gfo::ba::System S;
+  gfo::ba::setup(P, pr, s);
+  gfo::ba::build_system(pr, s, S);
+  memcpy(Hpp, S.Hpp.data(), S.Hpp.size() * 8); memcpy(bp, S.bp.data(), S.bp.size() * 8);
+  memcpy(Hll, S.Hll.data(), S.Hll.size() * 8); memcpy(bl, S.bl.data(), S.bl.size() * 8);
+  memcpy(Hpl, S.Hpl.data(), S.Hpl.size() * 8);
+}
+// one damped Schur solve at the initial state: x (dimP + 3 nPt); returns 1 on success
+int gfo_ba_step(const GfsBaProblem* P, double lambda, double* x) {
+  gfo::ba::Problem pr;
+  gfo::ba::State s;
+  gfo::ba::System S;
+  gfo::ba::setup(P, pr, s);
+  gfo::ba::build_system(pr, s, S);
+  std::vector<double> xv;
+  const bool ok = gfo::ba::schur_solve(pr, S, lambda, xv);
+  if (ok) memcpy(x, xv.data(), xv.size() * 8);
+  return ok;
+}
+// apply an update vector to the initial state and return the robust chi2 there (for finite differences)
+double gfo_ba_chi2_at(const GfsBaProblem* P, const double* x, int robust) {
+  gfo::ba::Problem pr;
+  gfo::ba::State s;
+  gfo::ba::setup(P, pr, s);
+  std::vector<double> xv(x, x + pr.dimP + 3 * (size_t)pr.nPt);
+  gfo::ba::apply_update(pr, s, xv);
+  if (!robust) { pr.deltaMono = pr.deltaStereo = pr.deltaIn = 1e300; }
+  return gfo::ba::robust_chi2(pr, s, nullptr);
+}
+void gfo_so3(const double* w, double* R_exp, double* log_of_exp, double* Jr, double* Jrinv) {
+  gfo::ba::exp_so3(w, R_exp);
+  gfo::ba::log_so3(R_exp, log_of_exp);
+  gfo::ba::right_jac(w, Jr);
+  gfo::ba::inv_right_jac(w, Jrinv);
+}
+}

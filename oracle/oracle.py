@@ -259,3 +259,130 @@ def se3_exp(a):
     T = np.zeros((4, 4))
     lib().gfo_se3_exp(_p(a), _p(T))
     return T
+
+
+# ------------------------------------------------------------------------------ Local inertial BA
+dp, ip, fp, bp_ = C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_uint8)
+
+
+class BaProblem(C.Structure):  # mirrors GfsBaProblem (include/gfs_b200.h)
+    _fields_ = [("n_opt_kf", C.c_int), ("n_fixed_kf", C.c_int), ("n_points", C.c_int), ("n_obs", C.c_int),
+                ("n_inertial", C.c_int), ("iterations", C.c_int), ("b_large", C.c_int), ("lambda_init", C.c_double),
+                ("Rcb", C.c_double * 9), ("tcb", C.c_double * 3), ("Rbc", C.c_double * 9), ("tbc", C.c_double * 3),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_double),
+                ("kf_Rwb", dp), ("kf_twb", dp), ("kf_Rcw", dp), ("kf_tcw", dp), ("kf_vel", dp), ("kf_bg", dp),
+                ("kf_ba", dp), ("kf_has_imu", bp_), ("pt_xyz", dp), ("pt_close", bp_), ("obs_kf", ip), ("obs_pt", ip),
+                ("obs_uvr", dp), ("obs_inv_sigma2", fp), ("in_kf1", ip), ("in_kf2", ip), ("in_pre", fp),
+                ("in_downweight", bp_)]
+
+
+class BaResult(C.Structure):  # mirrors GfsBaResult
+    _fields_ = [("kf_Rwb", dp), ("kf_twb", dp), ("kf_Rcw", dp), ("kf_tcw", dp), ("kf_vel", dp), ("kf_bg", dp),
+                ("kf_ba", dp), ("pt_xyz", dp), ("obs_chi2", dp), ("obs_depth_positive", bp_), ("obs_outlier", bp_),
+                ("err", C.c_float), ("err_end", C.c_float), ("failed", C.c_int), ("iterations_done", C.c_int),
+                ("lm_trials", C.c_int), ("lambda_final", C.c_double)]
+
+
+_BA_ARRAYS = [("kf_Rwb", np.float64), ("kf_twb", np.float64), ("kf_Rcw", np.float64), ("kf_tcw", np.float64),
+              ("kf_vel", np.float64), ("kf_bg", np.float64), ("kf_ba", np.float64), ("kf_has_imu", np.uint8),
+              ("pt_xyz", np.float64), ("pt_close", np.uint8), ("obs_kf", np.int32), ("obs_pt", np.int32),
+              ("obs_uvr", np.float64), ("obs_inv_sigma2", np.float32), ("in_kf1", np.int32), ("in_kf2", np.int32),
+              ("in_pre", np.float32), ("in_downweight", np.uint8)]
+
+
+def ba_pack(prob, struct_cls=BaProblem):
+    """dict (geoflowslam_b200.synth.ba_problem layout) -> (ctypes struct, keep-alive list)"""
+    P = struct_cls()
+    keep = []
+    for k in ("n_opt_kf", "n_fixed_kf", "n_points", "n_obs", "n_inertial", "iterations", "b_large"):
+        setattr(P, k, int(prob[k]))
+    P.lambda_init = float(prob["lambda_init"])
+    for k, n in (("Rcb", 9), ("tcb", 3), ("Rbc", 9), ("tbc", 3)):
+        setattr(P, k, (C.c_double * n)(*np.asarray(prob[k], np.float64).ravel()))
+    for k in ("fx", "fy", "cx", "cy"):
+        setattr(P, k, float(prob[k]))
+    P.bf = float(prob["bf"])
+    for k, dt in _BA_ARRAYS:
+        a = np.ascontiguousarray(prob[k], dt)
+        keep.append(a)
+        setattr(P, k, a.ctypes.data_as(dict(P._fields_)[k]))
+    return P, keep
+
+
+def ba_alloc_result(prob, struct_cls=BaResult):
+    nk = prob["n_opt_kf"] + prob["n_fixed_kf"]
+    out = dict(kf_Rwb=np.zeros((nk, 9)), kf_twb=np.zeros((nk, 3)), kf_Rcw=np.zeros((nk, 9)), kf_tcw=np.zeros((nk, 3)),
+               kf_vel=np.zeros((nk, 3)), kf_bg=np.zeros((nk, 3)), kf_ba=np.zeros((nk, 3)),
+               pt_xyz=np.zeros((prob["n_points"], 3)), obs_chi2=np.zeros(max(prob["n_obs"], 1)),
+               obs_depth_positive=np.zeros(max(prob["n_obs"], 1), np.uint8),
+               obs_outlier=np.zeros(max(prob["n_obs"], 1), np.uint8))
+    R = struct_cls()
+    for k, a in out.items():
+        setattr(R, k, a.ctypes.data_as(dict(R._fields_)[k]))
+    return R, out
+
+
+def ba_unpack_result(R, out, prob):
+    res = {k: v[:prob["n_obs"]] if k.startswith("obs_") else v for k, v in out.items()}
+    res.update(err=R.err, err_end=R.err_end, failed=bool(R.failed), iterations_done=R.iterations_done,
+               lm_trials=R.lm_trials, lambda_final=R.lambda_final)
+    return res
+
+
+def _bind_ba(L):
+    L.gfo_ba_solve.argtypes = [C.POINTER(BaProblem), C.POINTER(BaResult)]
+    L.gfo_ba_chi2.restype = C.c_double
+    L.gfo_ba_chi2.argtypes = [C.POINTER(BaProblem)]
+    L.gfo_ba_inertial.argtypes = [C.POINTER(BaProblem), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gfo_ba_system.argtypes = [C.POINTER(BaProblem)] + [C.c_void_p] * 5
+    L.gfo_ba_step.restype = C.c_int
+    L.gfo_ba_step.argtypes = [C.POINTER(BaProblem), C.c_double, C.c_void_p]
+    L.gfo_ba_chi2_at.restype = C.c_double
+    L.gfo_ba_chi2_at.argtypes = [C.POINTER(BaProblem), C.c_void_p, C.c_int]
+    L.gfo_so3.argtypes = [C.c_void_p] * 5
+
+
+_LATE_BINDERS.append(("gfo_ba_solve", _bind_ba))
+
+
+def ba_solve(prob):
+    """Optimizer::LocalInertialBA numerical core -> dict of optimised states + per-edge outcomes"""
+    P, keep = ba_pack(prob)
+    R, out = ba_alloc_result(prob)
+    lib().gfo_ba_solve(C.byref(P), C.byref(R))
+    return ba_unpack_result(R, out, prob)
+
+
+def ba_system(prob):
+    P, keep = ba_pack(prob)
+    n, m, o = 15 * prob["n_opt_kf"], prob["n_points"], prob["n_obs"]
+    Hpp = np.zeros((n, n)); bpv = np.zeros(n); Hll = np.zeros((m, 3, 3)); bl = np.zeros((m, 3)); Hpl = np.zeros((o, 6, 3))
+    lib().gfo_ba_system(C.byref(P), _p(Hpp), _p(bpv), _p(Hll), _p(bl), _p(Hpl))
+    return Hpp, bpv, Hll, bl, Hpl
+
+
+def ba_step(prob, lam):
+    P, keep = ba_pack(prob)
+    x = np.zeros(15 * prob["n_opt_kf"] + 3 * prob["n_points"])
+    ok = lib().gfo_ba_step(C.byref(P), float(lam), _p(x))
+    return bool(ok), x
+
+
+def ba_chi2_at(prob, x, robust=True):
+    P, keep = ba_pack(prob)
+    x = np.ascontiguousarray(x, np.float64)
+    return lib().gfo_ba_chi2_at(C.byref(P), _p(x), int(robust))
+
+
+def ba_inertial(prob, e):
+    P, keep = ba_pack(prob)
+    err = np.zeros(9); J = np.zeros((9, 24)); info = np.zeros((9, 9))
+    lib().gfo_ba_inertial(C.byref(P), e, _p(err), _p(J), _p(info))
+    return err, J, info
+
+
+def so3(w):
+    w = np.ascontiguousarray(w, np.float64)
+    R = np.zeros((3, 3)); lg = np.zeros(3); Jr = np.zeros((3, 3)); Ji = np.zeros((3, 3))
+    lib().gfo_so3(_p(w), _p(R), _p(lg), _p(Jr), _p(Ji))
+    return R, lg, Jr, Ji
