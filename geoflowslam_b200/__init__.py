@@ -5,3 +5,4 @@ from .matcher import ORBmatcher  # noqa: F401
 from .orb import ORBextractor  # noqa: F401
 from .frontend import TrackingFrontend  # noqa: F401
 from .gicp import RegistrationGICP  # noqa: F401
+from .optimizer import Optimizer  # noqa: F401

@@ -67,6 +67,15 @@ SIGNATURES = {
     "gfs_gicp_align_batch_device": ([vp, vp, vp, vp, vp, vp, ci, ci, vp, vp], ci),
     "gfs_gicp_get_cloud": ([vp, vp, ci, vp, vp, ci, vp], ci),
     "gfs_gicp_last_launches": ([vp], ci),
+    "gfs_ba_create": ([ci, ci, ci, ci, ci, C.POINTER(vp)], ci),
+    "gfs_ba_destroy": ([vp], ci),
+    "gfs_ba_solve_batch": ([vp, vp, vp, vp, ci], ci),
+    "gfs_ba_solve": ([vp, vp, vp, vp], ci),
+    "gfs_ba_upload": ([vp, vp, vp, ci], ci),
+    "gfs_ba_solve_uploaded": ([vp, vp], ci),
+    "gfs_ba_download": ([vp, vp, vp, ci], ci),
+    "gfs_ba_last_launches": ([vp], ci),
+    "gfs_ba_set_partition": ([vp, ci, ci, vp, vp], ci),
     "gfs_match_bf_hamming_batch_device": ([vp, vp, vp, vp, vp, ci, ci, vp, vp], ci),
     "gfs_match_bf_hamming": ([vp, vp, ci, vp, ci, vp, vp], ci),
     "gfs_gms_filter_batch_device": ([vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp], ci),
