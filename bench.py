@@ -323,6 +323,124 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# Secondary workloads (BASELINE configs[2] GICP and configs[3] LocalInertialBA); same JSON contract
+# ------------------------------------------------------------------------------------------------
+def _clock_block(fn, local):
+    import torch
+    s = ClockSampler(local)
+    s.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), s.stop()
+
+
+def run_gicp(args):
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from geoflowslam_b200 import RegistrationGICP, synth
+    from geoflowslam_b200.gicp import RESULT_DTYPE
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    P = args.batch if args.batch != 1024 else 512
+    uniq = min(P, 32)  # distinct synthetic pairs; the batch tiles them (every pair is solved independently)
+    with ThreadPoolExecutor(min(16, os.cpu_count() or 1)) as ex:
+        pairs = list(ex.map(lambda i: synth.gicp_pair(2000 + i, n_target=50000), range(uniq)))
+    stride = max(max(len(t), len(s)) for t, s, _ in pairs)
+    tg = np.zeros((P, stride, 4), np.float32); sr = np.zeros((P, stride, 4), np.float32)
+    nt = np.zeros(P, np.int32); ns = np.zeros(P, np.int32)
+    for i in range(P):
+        t, s_, _ = pairs[i % uniq]
+        tg[i, :len(t)] = t; sr[i, :len(s_)] = s_; nt[i] = len(t); ns[i] = len(s_)
+    T0 = np.tile(np.eye(4), (P, 1, 1))
+    reg = RegistrationGICP(max_points=stride, max_pairs=P)
+    dev = torch.device("cuda", local)
+    d_tg, d_sr = torch.from_numpy(tg).to(dev), torch.from_numpy(sr).to(dev)
+    d_nt, d_ns, d_T0 = torch.from_numpy(nt).to(dev), torch.from_numpy(ns).to(dev), torch.from_numpy(T0).to(dev)
+    d_out = torch.zeros(P * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    step = lambda: reg.align_batch_device(d_tg, d_nt, d_sr, d_ns, P, stride, d_T0, d_out, stream=stream)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    ms, clocks = _clock_block(lambda: [step() for _ in range(args.steps)], local)
+    ms /= args.steps
+    res = d_out.cpu().numpy().view(RESULT_DTYPE)
+    M_t, M_s = float(res["n_target"].mean()), float(res["n_source"].mean())
+    I, J = float(res["iterations"].mean() + 1), float(res["inner_evals"].mean())
+    alg = P * (16 * (nt.mean() + ns.mean()) + 400 * (M_t + M_s) + M_s * (160 * I + 112 * J))  # SURVEY 8d A_gicp
+    t0 = time.perf_counter(); res_h = reg.align_batch(tg, nt, sr, ns, T0); e2e_s = time.perf_counter() - t0
+    assert np.array_equal(res_h["iterations"], res["iterations"])
+    from oracle import oracle as O
+    nsamp = min(uniq, 8)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max(1, (os.cpu_count() or 4) // 4)) as ex:  # 4 OpenMP threads per pair, as the reference
+        list(ex.map(lambda i: O.gicp_align(pairs[i][0], pairs[i][1], threads=4), range(nsamp)))
+    cpu_s = time.perf_counter() - t0
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    line = {"metric": "cloud pairs/sec GICP 50k-pt RGB-D pairs (BASELINE configs[2])", "value": P / (ms / 1e3), "unit": "pairs/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[2]: RegistrationGICP voxel 0.02, max dist 0.1, k=10, <=20 LM iterations",
+                       "pairs": P, "distinct_pairs": uniq, "points_per_cloud": int(nt.mean()), "downsampled": [M_t, M_s],
+                       "outer_iterations": I, "inner_evals": J},
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "whole align call", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg / (ms / 1e3) / 1e9 / peak, "traffic": None},
+            "cpu_baseline": {"value": nsamp / cpu_s, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": "%d pairs, 4 threads per pair" % nsamp},
+            "e2e": {"value": P / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": int(tg.nbytes + sr.nbytes),
+                    "d2h_bytes_per_step": int(res_h.nbytes)},
+            "gpu_launches": args.steps * reg.last_launches()}
+    print(json.dumps(line))
+
+
+def run_ba(args):
+    import torch
+    from geoflowslam_b200 import Optimizer, synth
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    B = args.batch if args.batch != 1024 else 256
+    uniq = min(B, 8)
+    probs = [synth.ba_problem(seed=3000 + i) for i in range(uniq)]
+    batch = [probs[i % uniq] for i in range(B)]
+    opt = Optimizer(max_kf=21, max_points=3000, max_obs=16384, max_inertial=20, max_batch=B)
+    stream = torch.cuda.current_stream().cuda_stream
+    opt.upload(batch, stream)
+    for _ in range(max(args.warmup, 1)):
+        opt.solve_uploaded(stream)
+    ms, clocks = _clock_block(lambda: [opt.solve_uploaded(stream) for _ in range(args.steps)], local)
+    ms /= args.steps
+    res = opt.download(stream)
+    t0 = time.perf_counter(); opt.LocalInertialBA_batch(batch, stream); e2e_s = time.perf_counter() - t0
+    one = Optimizer(max_kf=21, max_points=3000, max_obs=16384, max_inertial=20, max_batch=1)
+    one.upload(batch[:1], stream); one.solve_uploaded(stream)
+    ms1, _ = _clock_block(lambda: [one.solve_uploaded(stream) for _ in range(5)], local)
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    for p in probs[:4]:
+        O.ba_solve(p)
+    cpu_s = (time.perf_counter() - t0) / 4
+    trials = float(np.mean([r["lm_trials"] for r in res]))
+    alg = B * trials * 7.6e6  # A_ba ~ 7.6 MB per LM trial
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    line = {"metric": "problems/sec LocalInertialBA 20 KF x 3000 MP x 15k obs (BASELINE configs[3])", "value": B / (ms / 1e3),
+            "unit": "problems/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[3]: 20 KF, 3000 points, ~15k stereo/mono edges, 20 inertial edges, bLarge (4 its)",
+                       "batch": B, "distinct_problems": uniq, "lm_trials": trials, "single_problem_ms": ms1 / 5},
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "whole solve", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg / (ms / 1e3) / 1e9 / peak, "traffic": None},
+            "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "problems/s", "cores": 1, "kind": "port", "sample": "4 problems, 1 thread (g2o OpenMP is off)"},
+            "e2e": {"value": B / e2e_s, "unit": "problems/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None},
+            "gpu_launches": args.steps * opt.last_launches()}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -331,9 +449,15 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="orb", choices=["orb", "gicp", "ba"],
+                    help="orb = BASELINE configs[1] (the driver's default); gicp / ba = configs[2] / configs[3]")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "gicp":
+        run_gicp(args)
+    elif args.workload == "ba":
+        run_ba(args)
     else:
         run_ours(args)
 
