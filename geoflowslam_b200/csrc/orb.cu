@@ -48,7 +48,7 @@ struct LevelDev {
 struct OrbDev {
   int nlevels, iniTh, minTh;
   int cellCap, totalCells, keysPerFrame, selPerFrame, kpStride, nodeCap;
-  int roiPitch, roiRows, scPitch;  // shared-memory geometry of k_fast_cells
+  int roiPitch, roiRows, scPitch, offSc, offCorner, offCand, offKept;  // shared-memory geometry of k_fast_cells
   long long pyrStride;
   float p1, p3, p5, p7, factorPI;  // fastAtan2 polynomial (degrees) and deg->rad
   int umax[16];
@@ -60,35 +60,47 @@ struct AreaEntry {
   float a[4];
 };
 
-__constant__ signed char c_pattern[1024];
 
 // ------------------------------------------------------------------------------------------------
 // k_pyr_level: one thread per destination pixel.  OpenCV's area resize accumulates, per source
 // row, buf = S0*a0 (+ S1*a1 (+ S2*a2)) in float and then sum = b0*buf0 (+ b1*buf1 ...) -- the same
 // order is kept here, every product and sum rounded separately.
 // ------------------------------------------------------------------------------------------------
+static const int PYR_TW = 64, PYR_TH = 32;
 __global__ void __launch_bounds__(256) k_pyr_level(OrbDev P, int l, const uint8_t* __restrict__ src_base,
                                                    long long src_stride, int src_pitch, uint8_t* __restrict__ pyr,
                                                    const AreaEntry* __restrict__ tabs) {
+  // CTA = 64 x 32 destination tile.  Horizontal pass: one float per (source row, destination column)
+  // into shared memory (a source row feeds up to two destination rows); vertical pass from there.
+  extern __shared__ float s_buf[];  // [source rows of the tile][PYR_TW]
   const LevelDev& L = P.lv[l];
-  const int dx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int dy = blockIdx.y * blockDim.y + threadIdx.y;
-  if (dx >= L.w || dy >= L.h) return;
-  const int frame = blockIdx.z;
+  const int tid = threadIdx.x, frame = blockIdx.z;
+  const int dx0 = blockIdx.x * PYR_TW, dy0 = blockIdx.y * PYR_TH;
+  const int th = min(PYR_TH, L.h - dy0);
+  const int c = tid & (PYR_TW - 1), dx = dx0 + c;
   const uint8_t* src = src_base + (long long)frame * src_stride;
-  const AreaEntry ex = tabs[L.tabX + dx];
-  const AreaEntry ey = tabs[L.tabY + dy];
-  float sum = 0.f;
-  for (int r = 0; r < ey.n; r++) {
-    const uint8_t* S = src + (long long)(ey.s0 + r) * src_pitch + ex.s0;
-    float buf = __fmul_rn((float)S[0], ex.a[0]);
-    for (int k = 1; k < ex.n; k++) buf = __fadd_rn(buf, __fmul_rn((float)S[k], ex.a[k]));
-    const float t = __fmul_rn(ey.a[r], buf);
-    sum = (r == 0) ? t : __fadd_rn(sum, t);
+  const AreaEntry eyF = tabs[L.tabY + dy0], eyL = tabs[L.tabY + dy0 + th - 1];
+  const int r0 = eyF.s0, nr = eyL.s0 + eyL.n - r0;
+  if (dx < L.w) {
+    const AreaEntry ex = tabs[L.tabX + dx];
+    for (int r = tid >> 6; r < nr; r += 256 / PYR_TW) {
+      const uint8_t* S = src + (long long)(r0 + r) * src_pitch + ex.s0;
+      float buf = __fmul_rn((float)__ldg(S), ex.a[0]);
+      for (int k = 1; k < ex.n; k++) buf = __fadd_rn(buf, __fmul_rn((float)__ldg(S + k), ex.a[k]));
+      s_buf[r * PYR_TW + c] = buf;
+    }
   }
-  int v = __float2int_rn(sum);
-  v = min(255, max(0, v));
-  pyr[(long long)frame * P.pyrStride + L.off + (long long)dy * L.pitch + dx] = (uint8_t)v;
+  __syncthreads();
+  if (dx >= L.w) return;
+  for (int ry = tid >> 6; ry < th; ry += 256 / PYR_TW) {
+    const AreaEntry ey = tabs[L.tabY + dy0 + ry];
+    const float* bcol = s_buf + (ey.s0 - r0) * PYR_TW + c;
+    float sum = __fmul_rn(ey.a[0], bcol[0]);
+    for (int r = 1; r < ey.n; r++) sum = __fadd_rn(sum, __fmul_rn(ey.a[r], bcol[r * PYR_TW]));
+    int v = __float2int_rn(sum);
+    v = min(255, max(0, v));
+    pyr[(long long)frame * P.pyrStride + L.off + (long long)(dy0 + ry) * L.pitch + dx] = (uint8_t)v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -136,17 +148,18 @@ __device__ __forceinline__ int fast_best16(const int (&d)[16]) {
 }
 
 static const int FAST_THREADS = 128;
-static const int FAST_MAX_ROUNDS = 64;  // 64 * 128 px >= the largest cell (69 x 69)
 
+// Shared memory: ROI pixels (word-aligned rows), the score map with a zero border, the list of
+// detected corners and the list of NMS survivors.  Per-pixel work is the antipodal-pair reject
+// (4 loads); only the survivors pay for the 16-pixel ring test, only corners for score + NMS.
 __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbDev P, const uint8_t* __restrict__ img0,
                                                               long long img_stride, int pitch0,
                                                               const uint8_t* __restrict__ pyr,
                                                               uint32_t* __restrict__ cellKeys,
                                                               int* __restrict__ cellCount) {
-  extern __shared__ uint8_t sm[];
-  __shared__ int s_wcnt[FAST_MAX_ROUNDS * (FAST_THREADS / 32)];
-  __shared__ int s_total;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  extern __shared__ __align__(16) uint8_t sm[];
+  __shared__ int s_nCand, s_nCorner, s_nKept;
+  const int tid = threadIdx.x;
   const int cell = blockIdx.x, frame = blockIdx.y;
   int l = 0;
   while (l + 1 < P.nlevels && cell >= P.lv[l + 1].cellBase) l++;
@@ -173,104 +186,136 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbDev P, const uin
     src = pyr + (long long)frame * P.pyrStride + L.off;
     pitch = L.pitch;
   }
-  uint8_t* roi = sm;                            // [roiRows][roiPitch]
-  uint8_t* sc = sm + P.roiRows * P.roiPitch;    // [(dh+2)][scPitch], zero border
   const int RP = P.roiPitch, SP = P.scPitch;
-  for (int idx = tid; idx < rw * rh; idx += FAST_THREADS) {
-    const int y = idx / rw, x = idx - y * rw;
-    roi[y * RP + x] = __ldg(src + (long long)(iniY + y) * pitch + iniX + x);
-  }
+  uint8_t* sc = sm + P.offSc;                       // [(dh+2)][SP], zero border
+  uint16_t* corners = (uint16_t*)(sm + P.offCorner);
+  uint16_t* cand = (uint16_t*)(sm + P.offCand);
+  uint32_t* keptList = (uint32_t*)(sm + P.offKept);
   const int dw = rw - 6, dh = rh - 6;
-  for (int idx = tid; idx < (dh + 2) * SP; idx += FAST_THREADS) sc[idx] = 0;
+  const int shift = iniX & 3;
+  const uint8_t* roi = sm + shift;                  // pixel (y, x) of the ROI at roi[y * RP + x]
+  if (((pitch & 3) == 0) && ((((size_t)src) & 3) == 0)) {
+    const int nW = (shift + rw + 3) >> 2;
+    const uint32_t* s32 = (const uint32_t*)(src + (long long)iniY * pitch + (iniX - shift));
+    const int p32 = pitch >> 2, rp32 = RP >> 2;
+    uint32_t* d32 = (uint32_t*)sm;
+    for (int idx = tid; idx < nW * rh; idx += FAST_THREADS) {
+      const int y = idx / nW, x = idx - y * nW;
+      d32[y * rp32 + x] = __ldg(s32 + (long long)y * p32 + x);
+    }
+  } else {
+    for (int idx = tid; idx < rw * rh; idx += FAST_THREADS) {
+      const int y = idx / rw, x = idx - y * rw;
+      sm[shift + y * RP + x] = __ldg(src + (long long)(iniY + y) * pitch + iniX + x);
+    }
+  }
+  {
+    uint32_t* z = (uint32_t*)sc;
+    for (int idx = tid; idx < ((dh + 2) * SP) >> 2; idx += FAST_THREADS) z[idx] = 0u;
+  }
+  if (tid == 0) { s_nCorner = 0; s_nCand = 0; }
   __syncthreads();
 
   const int npx = dw * dh;
   const int thMin = P.minTh, thIni = P.iniTh;
-  for (int idx = tid; idx < npx; idx += FAST_THREADS) {
-    const int y = idx / dw, x = idx - y * dw;
-    const uint8_t* p = roi + (y + 3) * RP + (x + 3);
-    const int cval = p[0];
-    int v[16];
-    v[0] = p[3 * RP];       v[1] = p[3 * RP + 1];   v[2] = p[2 * RP + 2];   v[3] = p[RP + 3];
-    v[4] = p[3];            v[5] = p[-RP + 3];      v[6] = p[-2 * RP + 2];  v[7] = p[-3 * RP + 1];
-    v[8] = p[-3 * RP];      v[9] = p[-3 * RP - 1];  v[10] = p[-2 * RP - 2]; v[11] = p[-RP - 3];
-    v[12] = p[-3];          v[13] = p[RP - 3];      v[14] = p[2 * RP - 2];  v[15] = p[3 * RP - 1];
-    unsigned bright = 0, dark = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-      bright |= (unsigned)(v[k] > cval + thMin) << k;
-      dark |= (unsigned)(v[k] < cval - thMin) << k;
-    }
-    if (has_arc9(bright) || has_arc9(dark)) {
-      int d[16];
-#pragma unroll
-      for (int k = 0; k < 16; k++) d[k] = cval - v[k];
-      const int best = fast_best16(d);
-      sc[(y + 1) * SP + (x + 1)] = (uint8_t)(best - 1);  // best > minTh >= 0, best <= 255
-    }
-  }
-  __syncthreads();
-
-  // 3x3 NMS with strict '>' at threshold t: a neighbour counts only if it is itself a corner at t
-  // (score >= t <=> best > t); pixels outside the cell's tested region score 0.
-  auto kept = [&](int idx, int t) -> int {
-    const int y = idx / dw, x = idx - y * dw;
-    const uint8_t* q = sc + (y + 1) * SP + (x + 1);
-    const int s = q[0];
-    if (s < t || s == 0) return 0;
-    int m = max(max(q[-SP - 1], q[-SP]), max(q[-SP + 1], q[-1]));
-    m = max(m, max(max(q[1], q[SP - 1]), max(q[SP], q[SP + 1])));
-    // neighbours below t count as 0; s >= t >= 0 so comparing against m is only wrong when
-    // m < t, in which case the neighbour is ignored: s > 0 suffices.
-    return (m >= t) ? (s > m) : 1;
-  };
-  int any = 0;
-  for (int idx = tid; idx < npx; idx += FAST_THREADS) any |= kept(idx, thIni);
-  any = __syncthreads_or(any);
-  const int thr = any ? thIni : thMin;
-
-  const int rounds = (npx + FAST_THREADS - 1) / FAST_THREADS;
-  unsigned long long mine = 0ull;
-  for (int r = 0; r < rounds; r++) {
-    const int idx = r * FAST_THREADS + tid;
-    const int k = (idx < npx) ? kept(idx, thr) : 0;
-    const unsigned b = __ballot_sync(0xffffffffu, k);
-    if (k) mine |= 1ull << r;
-    if (lane == 0) s_wcnt[r * (FAST_THREADS / 32) + warp] = __popc(b);
-  }
-  __syncthreads();
-  if (warp == 0) {  // exclusive scan of the (round, warp) counts, in output order
-    const int n = rounds * (FAST_THREADS / 32);
-    int carry = 0;
-    for (int base = 0; base < n; base += 32) {
-      const int i = base + lane;
-      const int vv = (i < n) ? s_wcnt[i] : 0;
-      int inc = vv;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      if (i < n) s_wcnt[i] = carry + inc - vv;
-      carry += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    if (lane == 0) s_total = carry;
-  }
-  __syncthreads();
-  uint32_t* out = cellKeys + ((long long)frame * P.totalCells + cell) * P.cellCap;
-  for (int r = 0; r < rounds; r++) {
-    const int k = (int)((mine >> r) & 1ull);
-    const unsigned b = __ballot_sync(0xffffffffu, k);
-    if (k) {
+  const int lane = tid & 31;
+  // phase 1 (every pixel, all lanes busy): antipodal-pair reject.  Every 9-arc of the 16-ring holds
+  // one pixel of each antipodal pair, so both (0,8) and (4,12) must have a bright (dark) member.
+  {
+    int x = tid % dw, y = tid / dw;
+    const int sx = FAST_THREADS % dw, sy = FAST_THREADS / dw;
+    const int rounds = (npx + FAST_THREADS - 1) / FAST_THREADS;
+    for (int r = 0; r < rounds; r++) {
       const int idx = r * FAST_THREADS + tid;
-      const int y = idx / dw, x = idx - y * dw;
-      const int pos = s_wcnt[r * (FAST_THREADS / 32) + warp] + __popc(b & ((1u << lane) - 1u));
-      const unsigned s = sc[(y + 1) * SP + (x + 1)];
-      const unsigned kx = (unsigned)(x + 3 + cj * L.wCell), ky = (unsigned)(y + 3 + ci * L.hCell);
-      out[pos] = kx | (ky << 12) | (s << 24);
+      bool pass = false;
+      if (idx < npx) {
+        const uint8_t* p = roi + (y + 3) * RP + (x + 3);
+        const int cval = p[0];
+        const int hi = cval + thMin, lo = cval - thMin;
+        const int v0 = p[3 * RP], v8 = p[-3 * RP], v4 = p[3], v12 = p[-3];
+        const bool br = ((v0 > hi) | (v8 > hi)) & ((v4 > hi) | (v12 > hi));
+        const bool dk = ((v0 < lo) | (v8 < lo)) & ((v4 < lo) | (v12 < lo));
+        pass = br | dk;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, pass);
+      if (m) {
+        int basePos = 0;
+        if (lane == 0) basePos = atomicAdd(&s_nCand, __popc(m));
+        basePos = __shfl_sync(0xffffffffu, basePos, 0);
+        if (pass) cand[basePos + __popc(m & ((1u << lane) - 1u))] = (uint16_t)idx;
+      }
+      x += sx; y += sy;
+      if (x >= dw) { x -= dw; y++; }
     }
   }
-  if (tid == 0) *outCount = s_total;
+  __syncthreads();
+  // phase 2 (survivors only, densely packed): full ring test, score, corner list
+  {
+    const int nCand = s_nCand;
+    for (int i = tid; i < nCand; i += FAST_THREADS) {
+      const int idx = cand[i];
+      const int y = idx / dw, x = idx - y * dw;
+      const uint8_t* p = roi + (y + 3) * RP + (x + 3);
+      const int cval = p[0];
+      const int hi = cval + thMin, lo = cval - thMin;
+      int v[16];
+      v[0] = p[3 * RP];       v[1] = p[3 * RP + 1];   v[2] = p[2 * RP + 2];   v[3] = p[RP + 3];
+      v[4] = p[3];            v[5] = p[-RP + 3];      v[6] = p[-2 * RP + 2];  v[7] = p[-3 * RP + 1];
+      v[8] = p[-3 * RP];      v[9] = p[-3 * RP - 1];  v[10] = p[-2 * RP - 2]; v[11] = p[-RP - 3];
+      v[12] = p[-3];          v[13] = p[RP - 3];      v[14] = p[2 * RP - 2];  v[15] = p[3 * RP - 1];
+      unsigned bright = 0, dark = 0;
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        bright |= (unsigned)(v[k] > hi) << k;
+        dark |= (unsigned)(v[k] < lo) << k;
+      }
+      if (has_arc9(bright) || has_arc9(dark)) {
+        int d[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) d[k] = cval - v[k];
+        const int best = fast_best16(d);
+        sc[(y + 1) * SP + (x + 1)] = (uint8_t)(best - 1);  // best > minTh >= 0, best <= 255
+        corners[atomicAdd(&s_nCorner, 1)] = (uint16_t)idx;
+      }
+    }
+  }
+  __syncthreads();
+  const int nCorner = s_nCorner;
+
+  // 3x3 NMS with strict '>' at threshold t, on the detected corners only: a neighbour counts only
+  // if it is itself a corner at t (score >= t <=> best > t); pixels outside the cell's tested
+  // region score 0.  If nothing survives at iniTh the cell is redone at minTh (:809-826).
+  for (int pass = 0; pass < 2; pass++) {
+    const int t = pass == 0 ? thIni : thMin;
+    if (tid == 0) s_nKept = 0;
+    __syncthreads();
+    for (int i = tid; i < nCorner; i += FAST_THREADS) {
+      const int idx = corners[i];
+      const int y = idx / dw, x = idx - y * dw;
+      const uint8_t* q = sc + (y + 1) * SP + (x + 1);
+      const int s = q[0];
+      if (s < t || s == 0) continue;
+      int m = max(max(q[-SP - 1], q[-SP]), max(q[-SP + 1], q[-1]));
+      m = max(m, max(max(q[1], q[SP - 1]), max(q[SP], q[SP + 1])));
+      // neighbours below t count as 0, so the comparison only applies when m >= t
+      if ((m >= t) ? (s > m) : true) keptList[atomicAdd(&s_nKept, 1)] = (uint32_t)idx | ((uint32_t)s << 16);
+    }
+    __syncthreads();
+    if (s_nKept > 0 || thIni == thMin) break;
+  }
+  const int nKept = s_nKept;
+  // output in cv::FAST order (row-major): rank = number of survivors with a smaller pixel index
+  uint32_t* out = cellKeys + ((long long)frame * P.totalCells + cell) * P.cellCap;
+  for (int i = tid; i < nKept; i += FAST_THREADS) {
+    const uint32_t e = keptList[i];
+    const int idx = (int)(e & 0xffffu);
+    int rank = 0;
+    for (int j = 0; j < nKept; j++) rank += (int)(keptList[j] & 0xffffu) < idx;
+    const int y = idx / dw, x = idx - y * dw;
+    const unsigned kx = (unsigned)(x + 3 + cj * L.wCell), ky = (unsigned)(y + 3 + ci * L.hCell);
+    out[rank] = kx | (ky << 12) | ((e >> 16) << 24);
+  }
+  if (tid == 0) *outCount = nKept;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -638,15 +683,26 @@ __device__ __forceinline__ float fast_atan2_deg(const OrbDev& P, float y, float 
 }
 
 static const int OD_WARPS = 8;
+static const int PATCH_R = 21;                 // 18 (largest rounded rotated pattern radius) + 3 (blur taps)
+static const int PATCH_W = 2 * PATCH_R + 1;    // 43
+static const int RAW_PITCH = 52;               // 13 words per row: odd, so column walks hit distinct banks
+static const int HB_W = 37, HB_PITCH = 38;     // horizontally blurred rows, radius 18, u16
+
+// The warp stages the keypoint's 43x43 neighbourhood of the level image in shared memory (one
+// coalesced sweep), takes the IC_Angle moments from it, runs the horizontal pass of the 7x7 sigma-2
+// fixed-point Gaussian (ORBextractor.cc:1188-1189) over it and evaluates the vertical pass only at
+// the 512 rotated sample positions -- the blurred level image is never materialised in HBM.
 __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(OrbDev P, const uint8_t* __restrict__ img0,
                                                                long long img_stride, int pitch0,
                                                                const uint8_t* __restrict__ pyr,
-                                                               const uint8_t* __restrict__ blur,
+                                                               const uint4* __restrict__ pattern,
                                                                const uint32_t* __restrict__ sel,
                                                                const int* __restrict__ selCount,
                                                                GfsKeyPoint* __restrict__ out_kp,
                                                                uint8_t* __restrict__ out_desc, int* __restrict__ out_n,
                                                                int* __restrict__ out_mono) {
+  __shared__ __align__(16) uint8_t s_raw[OD_WARPS][PATCH_W * RAW_PITCH];
+  __shared__ __align__(16) uint16_t s_hb[OD_WARPS][PATCH_W * HB_PITCH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slot = blockIdx.x * OD_WARPS + warp;
   const int frame = blockIdx.y;
@@ -672,42 +728,98 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(OrbDev P, const u
   if (l == 0) { src = img0 + (long long)frame * img_stride; pitch = pitch0; }
   else { src = pyr + (long long)frame * P.pyrStride + L.off; pitch = L.pitch; }
 
-  // IC_Angle: integer moments over the radius-15 disc, one row per lane
+  // ---- stage the raw patch: rows cy-21..cy+21, columns cx-21..cx+21 (REFLECT_101 at the image border)
+  uint8_t* raw = s_raw[warp];
+  const int x0 = cx - PATCH_R, y0 = cy - PATCH_R;
+  int shift = 0;
+  const bool interior = x0 >= 0 && y0 >= 0 && cx + PATCH_R < L.w && cy + PATCH_R < L.h && ((pitch & 3) == 0) &&
+                        ((((size_t)src) & 3) == 0);
+  bool fast = false;
+  if (interior) {
+    shift = x0 & 3;
+    const int nW = (shift + PATCH_W + 3) >> 2;  // <= 12 words
+    if (x0 - shift + 4 * nW <= pitch) {
+      fast = true;
+      const uint32_t* s32 = (const uint32_t*)(src + (long long)y0 * pitch + (x0 - shift));
+      const int p32 = pitch >> 2;
+      uint32_t* d32 = (uint32_t*)raw;
+      for (int idx = lane; idx < PATCH_W * nW; idx += 32) {
+        const int r = idx / nW, c = idx - r * nW;
+        d32[r * (RAW_PITCH / 4) + c] = __ldg(s32 + (long long)r * p32 + c);
+      }
+    }
+  }
+  if (!fast) {
+    shift = 0;
+    for (int idx = lane; idx < PATCH_W * PATCH_W; idx += 32) {
+      const int r = idx / PATCH_W, c = idx - r * PATCH_W;
+      const int gy = reflect101(y0 + r, L.h), gx = reflect101(x0 + c, L.w);
+      raw[r * RAW_PITCH + c] = __ldg(src + (long long)gy * pitch + gx);
+    }
+  }
+  __syncwarp();
+  const uint8_t* rp = raw + shift;  // patch pixel (r, c) at rp[r * RAW_PITCH + c]
+
+  // ---- IC_Angle (:71-95): integer moments over the radius-15 disc, one column per lane
   int m10 = 0, m01 = 0;
   if (lane < 2 * HALF_PATCH + 1) {
-    const int v = lane - HALF_PATCH;
-    const int d = P.umax[v < 0 ? -v : v];
-    const uint8_t* row = src + (long long)(cy + v) * pitch + cx;
-    int rs = 0;
-    for (int u = -d; u <= d; u++) {
-      const int val = __ldg(row + u);
-      m10 += u * val;
-      rs += val;
+    const int u = lane - HALF_PATCH;
+    const int d = P.umax[u < 0 ? -u : u];  // the disc is symmetric: column u spans |v| <= umax[|u|]
+    const uint8_t* col = rp + PATCH_R * RAW_PITCH + PATCH_R + u;
+    int cs = 0;
+    for (int v = -d; v <= d; v++) {
+      const int val = col[v * RAW_PITCH];
+      m01 += v * val;
+      cs += val;
     }
-    m01 = v * rs;
+    m10 = u * cs;
   }
   m10 = __reduce_add_sync(0xffffffffu, m10);
   m01 = __reduce_add_sync(0xffffffffu, m01);
   const float angle = fast_atan2_deg(P, (float)m01, (float)m10);
 
-  // rBRIEF: lane b computes descriptor byte b (tests 8b .. 8b+7)
+  // ---- horizontal blur pass: hb[r][c] = sum_k K[k] * raw[r][c + k], c in [0, 37); 86 half-rows over 32 lanes
+  uint16_t* hb = s_hb[warp];
+  for (int item = lane; item < 2 * PATCH_W; item += 32) {
+    const int r = item >> 1, half = item & 1;
+    const int c0 = half ? 19 : 0, n = half ? 18 : 19;
+    const uint8_t* q = rp + r * RAW_PITCH + c0;
+    int a = q[0], b = q[1], c = q[2], d = q[3], e = q[4], f = q[5];
+    uint16_t* o = hb + r * HB_PITCH + c0;
+    for (int k = 0; k < n; k++) {
+      const int g = q[k + 6];
+      o[k] = (uint16_t)(18 * (a + g) + 34 * (b + f) + 48 * (c + e) + 56 * d);
+      a = b; b = c; c = d; d = e; e = f; f = g;
+    }
+  }
+  __syncwarp();
+
+  // ---- rBRIEF (:99-160): lane b computes descriptor byte b (tests 8b .. 8b+7); the vertical blur
+  // pass is evaluated at the sample positions only: ((sum_k K[k] * hb[y+k][x]) + 2^15) >> 16
   const float ar = __fmul_rn(angle, P.factorPI);
   double sd, cd;
   sincos((double)ar, &sd, &cd);
   const float a = (float)cd, b = (float)sd;
-  const uint8_t* bl = blur + (long long)frame * P.pyrStride + L.off + (long long)cy * L.pitch + cx;
-  const signed char* pat = c_pattern + lane * 32;
+  // the lane's 16 pattern points (32 signed bytes) live in 8 registers; a per-lane indexed
+  // __constant__ read would serialise in the address-divergence unit (ncu: adu pipe 88 %)
+  const uint4 pw0 = __ldg(pattern + 2 * lane), pw1 = __ldg(pattern + 2 * lane + 1);
+  const unsigned pw[8] = {pw0.x, pw0.y, pw0.z, pw0.w, pw1.x, pw1.y, pw1.z, pw1.w};
   int val = 0;
 #pragma unroll
   for (int t = 0; t < 8; t++) {
     int s[2];
 #pragma unroll
     for (int p = 0; p < 2; p++) {
-      const float px = (float)pat[4 * t + 2 * p], py = (float)pat[4 * t + 2 * p + 1];
+      // point index 2t+p -> bytes 4t+2p (x) and 4t+2p+1 (y) of the lane's record
+      const unsigned w = pw[t];
+      const float px = (float)((int)(w << (24 - 16 * p)) >> 24), py = (float)((int)(w << (16 - 16 * p)) >> 24);
       const float r1 = __fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a));
       const float r2 = __fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b));
       const int ry = (int)roundf(r1), rx = (int)roundf(r2);
-      s[p] = __ldg(bl + ry * L.pitch + rx);
+      const uint16_t* h = hb + (ry + 18) * HB_PITCH + (rx + 18);  // rows ry+18 .. ry+24 = blur taps -3 .. +3
+      const unsigned acc = 18u * (h[0] + h[6 * HB_PITCH]) + 34u * (h[HB_PITCH] + h[5 * HB_PITCH]) +
+                           48u * (h[2 * HB_PITCH] + h[4 * HB_PITCH]) + 56u * h[3 * HB_PITCH];
+      s[p] = (int)((acc + 32768u) >> 16);
     }
     val |= (s[0] < s[1]) << t;
   }
@@ -788,9 +900,9 @@ struct GfsOrb {
   int geomW = 0, geomH = 0;
   OrbDev dev;
   DevBuf d_pyr, d_blur, d_cellKeys, d_cellCount, d_keysA, d_keysB, d_sel, d_selCount, d_tabs, d_status;
-  DevBuf d_in, d_okp, d_odesc, d_on, d_omono, d_tkp, d_tdesc;
+  DevBuf d_in, d_okp, d_odesc, d_on, d_omono, d_tkp, d_tdesc, d_pattern;
   PinnedBuf h_in, h_okp, h_odesc, h_on;
-  size_t fastSmem = 0, octSmem = 0;
+  size_t fastSmem = 0, octSmem = 0, pyrSmem = 0;
   // optional per-stage CUDA-event timing (bench roofline): pyramid, fast, octree, blur, orient/desc, pack
   bool profiling = false;
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -882,6 +994,16 @@ static int orb_set_geometry(GfsOrb* h, int w, int ht) {
       L.tabX = L.tabY = 0;
     }
   }
+  int maxSrcRows = 1;
+  for (int l = 1; l < h->nlevels; l++) {
+    const LevelDev& L = D.lv[l];
+    for (int dy0 = 0; dy0 < L.h; dy0 += PYR_TH) {
+      const AreaEntry& f = tabs[L.tabY + dy0];
+      const AreaEntry& e = tabs[L.tabY + std::min(dy0 + PYR_TH, L.h) - 1];
+      maxSrcRows = std::max(maxSrcRows, e.s0 + e.n - f.s0);
+    }
+  }
+  h->pyrSmem = (size_t)maxSrcRows * PYR_TW * sizeof(float);
   for (const AreaEntry& e : tabs)
     if (e.n > 4 || e.n < 1) {
       set_error("scale factor outside the supported (1, 3) range");
@@ -898,9 +1020,13 @@ static int orb_set_geometry(GfsOrb* h, int w, int ht) {
   D.keysPerFrame = keyOff;
   D.selPerFrame = selOff;
   D.nodeCap = nodeCap;
-  D.roiPitch = (int)align_up(maxWC + 6, 4);
+  D.roiPitch = (int)align_up(maxWC + 6 + 3, 4) + 4;  // + word-alignment shift of the first column
   D.roiRows = maxHC + 6;
   D.scPitch = (int)align_up(maxWC + 2, 4);
+  D.offSc = (int)align_up((size_t)D.roiRows * D.roiPitch + 4, 16);
+  D.offCorner = D.offSc + (int)align_up((size_t)(maxHC + 2) * D.scPitch, 16);
+  D.offCand = D.offCorner + (int)align_up((size_t)2 * maxWC * maxHC, 16);
+  D.offKept = D.offCand + (int)align_up((size_t)2 * maxWC * maxHC, 16);
   if (selOff > D.kpStride) {
     set_error("internal: selected-slot count %d exceeds keypoint stride %d", selOff, D.kpStride);
     return GFS_ERR_INVALID;
@@ -929,7 +1055,6 @@ static int orb_set_geometry(GfsOrb* h, int w, int ht) {
   const size_t B = (size_t)h->maxBatch;
   int rc;
   if ((rc = h->d_pyr.reserve(B * D.pyrStride))) return rc;
-  if ((rc = h->d_blur.reserve(B * D.pyrStride))) return rc;
   if ((rc = h->d_cellKeys.reserve(B * D.totalCells * (size_t)D.cellCap * 4))) return rc;
   if ((rc = h->d_cellCount.reserve(B * D.totalCells * 4))) return rc;
   if ((rc = h->d_keysA.reserve(B * (size_t)D.keysPerFrame * 4))) return rc;
@@ -940,8 +1065,9 @@ static int orb_set_geometry(GfsOrb* h, int w, int ht) {
   if ((rc = h->d_tabs.reserve(std::max<size_t>(tabs.size(), 1) * sizeof(AreaEntry)))) return rc;
   if (!tabs.empty()) GFS_CUDA(cudaMemcpy(h->d_tabs.p, tabs.data(), tabs.size() * sizeof(AreaEntry), cudaMemcpyHostToDevice));
   GFS_CUDA(cudaMemset(h->d_status.p, 0, 16));
-  GFS_CUDA(cudaMemcpyToSymbol(c_pattern, GFS_ORB_PATTERN, 1024));
-  h->fastSmem = (size_t)D.roiRows * D.roiPitch + (size_t)(maxHC + 2) * D.scPitch;
+  if ((rc = h->d_pattern.reserve(1024))) return rc;
+  GFS_CUDA(cudaMemcpy(h->d_pattern.p, GFS_ORB_PATTERN, 1024, cudaMemcpyHostToDevice));
+  h->fastSmem = (size_t)D.offKept + (size_t)4 * cellCap + 16;
   const size_t perWarp = align_up(sizeof(OctState) + (size_t)nodeCap * (sizeof(OctNode) + 4 * sizeof(int)), 16);
   h->octSmem = perWarp * OCT_WARPS;
   if (h->octSmem > 200 * 1024) {
@@ -949,7 +1075,11 @@ static int orb_set_geometry(GfsOrb* h, int w, int ht) {
     return GFS_ERR_CAPACITY;
   }
   // the attribute is per function (shared by every handle): only ever raise it
-  static size_t octMax = 48 * 1024, fastMax = 48 * 1024;
+  static size_t octMax = 48 * 1024, fastMax = 48 * 1024, pyrMax = 48 * 1024;
+  if (h->pyrSmem > pyrMax) {
+    GFS_CUDA(cudaFuncSetAttribute(k_pyr_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pyrSmem));
+    pyrMax = h->pyrSmem;
+  }
   if (h->octSmem > octMax) {
     GFS_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->octSmem));
     octMax = h->octSmem;
@@ -1011,7 +1141,7 @@ int gfs_orb_destroy(GfsOrb* h) {
   if (!h) return GFS_OK;
   DevBuf* d[] = {&h->d_pyr, &h->d_blur, &h->d_cellKeys, &h->d_cellCount, &h->d_keysA, &h->d_keysB, &h->d_sel,
                  &h->d_selCount, &h->d_tabs, &h->d_status, &h->d_in, &h->d_okp, &h->d_odesc, &h->d_on, &h->d_omono,
-                 &h->d_tkp, &h->d_tdesc};
+                 &h->d_tkp, &h->d_tdesc, &h->d_pattern};
   for (DevBuf* b : d) b->release();
   h->h_in.release(); h->h_okp.release(); h->h_odesc.release(); h->h_on.release();
   for (int i = 0; i < 7; i++)
@@ -1055,8 +1185,8 @@ int gfs_orb_get_profile(GfsOrb* h, float* ms6) {
 
 int gfs_orb_launches_per_call(const GfsOrb* h, int lap0, int lap1) {
   if (!h) return GFS_ERR_INVALID;
-  // pyramid (nlevels-1) + fast + octree + blur (nlevels) + orient/desc (+ pack)
-  return (h->nlevels - 1) + 1 + 1 + h->nlevels + 1 + ((lap0 != 0 || lap1 != 0) ? 1 : 0);
+  // pyramid (nlevels-1) + fast + octree + orient/desc with the fused blur (+ pack)
+  return (h->nlevels - 1) + 1 + 1 + 1 + ((lap0 != 0 || lap1 != 0) ? 1 : 0);
 }
 
 static int orb_run_chunk(GfsOrb* h, cudaStream_t st, const uint8_t* d_imgs, int batch, int w, int ht, int pitch,
@@ -1064,16 +1194,15 @@ static int orb_run_chunk(GfsOrb* h, cudaStream_t st, const uint8_t* d_imgs, int 
                          int* d_mono) {
   const OrbDev& D = h->dev;
   uint8_t* pyr = (uint8_t*)h->d_pyr.p;
-  uint8_t* blur = (uint8_t*)h->d_blur.p;
   auto mark = [&](int i) { if (h->profiling) cudaEventRecord(h->ev[i], st); };
   mark(0);
   for (int l = 1; l < h->nlevels; l++) {
     const LevelDev& L = D.lv[l];
-    dim3 blk(32, 8), grd(div_up(L.w, 32), div_up(L.h, 8), batch);
+    dim3 blk(256), grd(div_up(L.w, PYR_TW), div_up(L.h, PYR_TH), batch);
     const uint8_t* src = (l == 1) ? d_imgs : pyr + D.lv[l - 1].off;
     const long long ss = (l == 1) ? (long long)img_stride : D.pyrStride;
     const int sp = (l == 1) ? pitch : D.lv[l - 1].pitch;
-    k_pyr_level<<<grd, blk, 0, st>>>(D, l, src, ss, sp, pyr, (const AreaEntry*)h->d_tabs.p);
+    k_pyr_level<<<grd, blk, h->pyrSmem, st>>>(D, l, src, ss, sp, pyr, (const AreaEntry*)h->d_tabs.p);
   }
   mark(1);
   k_fast_cells<<<dim3(D.totalCells, batch), FAST_THREADS, h->fastSmem, st>>>(
@@ -1083,12 +1212,7 @@ static int orb_run_chunk(GfsOrb* h, cudaStream_t st, const uint8_t* d_imgs, int 
       D, batch, (const uint32_t*)h->d_cellKeys.p, (const int*)h->d_cellCount.p, (uint32_t*)h->d_keysA.p,
       (uint32_t*)h->d_keysB.p, (uint32_t*)h->d_sel.p, (int*)h->d_selCount.p, (int*)h->d_status.p);
   mark(3);
-  for (int l = 0; l < h->nlevels; l++) {
-    const LevelDev& L = D.lv[l];
-    k_blur7<<<dim3(div_up(L.w, BL_TW), div_up(L.h, BL_TH), batch), 256, 0, st>>>(D, l, d_imgs, (long long)img_stride,
-                                                                                pitch, pyr, blur);
-  }
-  mark(4);
+  mark(4);  // (the 7x7 blur is fused into k_orient_desc; k_blur7 only serves gfs_orb_get_level)
   const bool lapping = (lap0 != 0 || lap1 != 0);
   GfsKeyPoint* kpDst = d_kp;
   uint8_t* descDst = d_desc;
@@ -1100,8 +1224,8 @@ static int orb_run_chunk(GfsOrb* h, cudaStream_t st, const uint8_t* d_imgs, int 
     descDst = (uint8_t*)h->d_tdesc.p;
   }
   k_orient_desc<<<dim3(div_up(D.selPerFrame, OD_WARPS), batch), OD_WARPS * 32, 0, st>>>(
-      D, d_imgs, (long long)img_stride, pitch, pyr, blur, (const uint32_t*)h->d_sel.p, (const int*)h->d_selCount.p,
-      kpDst, descDst, d_n, d_mono);
+      D, d_imgs, (long long)img_stride, pitch, pyr, (const uint4*)h->d_pattern.p, (const uint32_t*)h->d_sel.p,
+      (const int*)h->d_selCount.p, kpDst, descDst, d_n, d_mono);
   mark(5);
   if (lapping)
     k_pack_lapping<<<batch, 1024, 0, st>>>(D.kpStride, lap0, lap1, kpDst, descDst, d_kp, d_desc, d_n, d_mono);
@@ -1228,6 +1352,13 @@ int gfs_orb_get_level(GfsOrb* h, void* stream, int frame, int level, int blurred
   const uint8_t* src;
   size_t sp;
   if (blurred) {
+    // the blurred working copy (ORBextractor.cc:1188-1189) is not kept by the extraction path any more:
+    // materialise this level on demand with the stand-alone blur kernel
+    int rc = h->d_blur.reserve((size_t)h->maxBatch * h->dev.pyrStride);
+    if (rc) return rc;
+    k_blur7<<<dim3(div_up(L.w, BL_TW), div_up(L.h, BL_TH), h->lastBatch), 256, 0, st>>>(
+        h->dev, level, h->lastImgs, h->lastStride, h->lastPitch, (const uint8_t*)h->d_pyr.p, (uint8_t*)h->d_blur.p);
+    GFS_CUDA(cudaGetLastError());
     src = (const uint8_t*)h->d_blur.p + (size_t)frame * h->dev.pyrStride + L.off;
     sp = L.pitch;
   } else if (level == 0) {
