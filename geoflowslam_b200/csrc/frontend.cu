@@ -4,6 +4,7 @@
 // ORBmatcher::SearchWithGMS (src/ORBmatcher.cc:744-778) of System::TrackRGBD, applied to a batch
 // of independent frames -- BASELINE.json configs[1].
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -14,8 +15,10 @@ struct GfsFrontend {
   int maxBatch = 0, stride = 0;
   DevBuf d_in, d_kp, d_desc, d_n, d_idx, d_dist, d_inl, d_cnt;
   PinnedBuf h_in;
-  cudaStream_t copyStream = nullptr;
-  cudaEvent_t evIn[2] = {nullptr, nullptr}, evDone = nullptr;
+  // host-buffer path: H2D of chunk k+1 and D2H of chunk k-1 overlap the kernels of chunk k
+  cudaStream_t copyStream = nullptr, outStream = nullptr;
+  std::vector<cudaEvent_t> evIn, evDone;
+  int chunk = 128;
   bool profiling = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, after orb, after bf, after gms
 };
@@ -45,6 +48,10 @@ int gfs_frontend_destroy(GfsFrontend* f) {
   f->h_in.release();
   for (cudaEvent_t e : f->ev)
     if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : f->evIn) cudaEventDestroy(e);
+  for (cudaEvent_t e : f->evDone) cudaEventDestroy(e);
+  if (f->copyStream) cudaStreamDestroy(f->copyStream);
+  if (f->outStream) cudaStreamDestroy(f->outStream);
   delete f;
   return GFS_OK;
 }
@@ -127,32 +134,84 @@ int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batc
   if ((rc = f->d_dist.reserve(B * s * sizeof(int)))) return rc;
   if ((rc = f->d_inl.reserve(B * s))) return rc;
   if ((rc = f->d_cnt.reserve(B * sizeof(int)))) return rc;
-  const uint8_t* src = imgs;
-  size_t spitch = pitch;
-  if (!is_pinned_host(imgs)) {  // pageable input: stage once through pinned memory
-    if ((rc = f->h_in.reserve(B * (size_t)w * h_img))) return rc;
-    uint8_t* stg = (uint8_t*)f->h_in.p;
-    for (size_t i = 0; i < B; i++)
-      for (int y = 0; y < h_img; y++) memcpy(stg + (i * h_img + y) * w, imgs + i * img_stride + (size_t)y * pitch, w);
-    src = stg;
-    spitch = w;
-    img_stride = (size_t)w * h_img;
-  }
-  if (img_stride == spitch * h_img) {
-    GFS_CUDA(cudaMemcpy2DAsync(f->d_in.p, dpitch, src, spitch, w, (size_t)h_img * B, cudaMemcpyHostToDevice, st));
-  } else {
-    for (size_t i = 0; i < B; i++)
-      GFS_CUDA(cudaMemcpy2DAsync((uint8_t*)f->d_in.p + i * dstride, dpitch, src + i * img_stride, spitch, w, h_img,
-                                 cudaMemcpyHostToDevice, st));
-  }
   int* d_n = (int*)f->d_n.p;
   int* d_mono = d_n + batch;
-  rc = gfs_frontend_run_device(f, stream, (const uint8_t*)f->d_in.p, batch, w, h_img, (int)dpitch, dstride,
-                               (GfsKeyPoint*)f->d_kp.p, (uint8_t*)f->d_desc.p, d_n, d_mono, (int*)f->d_idx.p,
-                               (int*)f->d_dist.p, (uint8_t*)f->d_inl.p, (int*)f->d_cnt.p);
-  if (rc) return rc;
-  GFS_CUDA(cudaMemcpyAsync(out_kp, f->d_kp.p, B * s * sizeof(GfsKeyPoint), cudaMemcpyDeviceToHost, st));
-  GFS_CUDA(cudaMemcpyAsync(out_desc, f->d_desc.p, B * s * 32, cudaMemcpyDeviceToHost, st));
+  GfsKeyPoint* d_kp = (GfsKeyPoint*)f->d_kp.p;
+  uint8_t* d_desc = (uint8_t*)f->d_desc.p;
+  uint8_t* d_in = (uint8_t*)f->d_in.p;
+  const bool pinned = is_pinned_host(imgs) && is_pinned_host(out_kp) && is_pinned_host(out_desc);
+  f->chunk = std::max(64, div_up(batch, 4));  // 4 chunks: enough overlap, kernels stay large
+  if (pinned && batch > f->chunk) {
+    // ---- pipelined: chunked H2D on a copy stream, kernels on the caller's stream, D2H on a third
+    if (!f->copyStream) {
+      GFS_CUDA(cudaStreamCreateWithFlags(&f->copyStream, cudaStreamNonBlocking));
+      GFS_CUDA(cudaStreamCreateWithFlags(&f->outStream, cudaStreamNonBlocking));
+    }
+    const int nChunks = div_up(batch, f->chunk);
+    while ((int)f->evIn.size() < nChunks) {
+      cudaEvent_t a, b2;
+      GFS_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+      GFS_CUDA(cudaEventCreateWithFlags(&b2, cudaEventDisableTiming));
+      f->evIn.push_back(a);
+      f->evDone.push_back(b2);
+    }
+    // the copy stream must not run ahead of work already queued on the caller's stream
+    GFS_CUDA(cudaEventRecord(f->evDone[0], st));
+    GFS_CUDA(cudaStreamWaitEvent(f->copyStream, f->evDone[0], 0));
+    GFS_CUDA(cudaStreamWaitEvent(f->outStream, f->evDone[0], 0));
+    for (int c = 0; c < nChunks; c++) {
+      const size_t b0 = (size_t)c * f->chunk, nb = std::min<size_t>(f->chunk, B - b0);
+      if (img_stride == (size_t)pitch * h_img) {
+        GFS_CUDA(cudaMemcpy2DAsync(d_in + b0 * dstride, dpitch, imgs + b0 * img_stride, pitch, w, (size_t)h_img * nb,
+                                   cudaMemcpyHostToDevice, f->copyStream));
+      } else {
+        for (size_t i = 0; i < nb; i++)
+          GFS_CUDA(cudaMemcpy2DAsync(d_in + (b0 + i) * dstride, dpitch, imgs + (b0 + i) * img_stride, pitch, w, h_img,
+                                     cudaMemcpyHostToDevice, f->copyStream));
+      }
+      GFS_CUDA(cudaEventRecord(f->evIn[c], f->copyStream));
+      GFS_CUDA(cudaStreamWaitEvent(st, f->evIn[c], 0));
+      rc = gfs_orb_extract_batch_device(f->orb, stream, d_in + b0 * dstride, (int)nb, w, h_img, (int)dpitch, dstride, 0, 0,
+                                        d_kp + b0 * s, d_desc + b0 * s * 32, d_n + b0, d_mono + b0);
+      if (rc) return rc;
+      GFS_CUDA(cudaEventRecord(f->evDone[c], st));
+      GFS_CUDA(cudaStreamWaitEvent(f->outStream, f->evDone[c], 0));
+      GFS_CUDA(cudaMemcpyAsync(out_kp + b0 * s, d_kp + b0 * s, nb * s * sizeof(GfsKeyPoint), cudaMemcpyDeviceToHost, f->outStream));
+      GFS_CUDA(cudaMemcpyAsync(out_desc + b0 * s * 32, d_desc + b0 * s * 32, nb * s * 32, cudaMemcpyDeviceToHost, f->outStream));
+    }
+    if (f->profiling) { cudaEventRecord(f->ev[0], st); cudaEventRecord(f->ev[1], st); }
+    rc = gfs_match_bf_hamming_batch_device(stream, d_desc, d_n, d_desc + (size_t)s * 32, d_n + 1, batch - 1, s,
+                                           (int*)f->d_idx.p, (int*)f->d_dist.p);
+    if (rc) return rc;
+    if (f->profiling) cudaEventRecord(f->ev[2], st);
+    rc = gfs_gms_filter_batch_device(stream, d_kp, d_n, d_kp + s, d_n + 1, (int*)f->d_idx.p, batch - 1, s, w, h_img, w, h_img,
+                                     (uint8_t*)f->d_inl.p, (int*)f->d_cnt.p);
+    if (rc) return rc;
+    if (f->profiling) cudaEventRecord(f->ev[3], st);
+  } else {
+    const uint8_t* src = imgs;
+    size_t spitch = pitch;
+    if (!is_pinned_host(imgs)) {  // pageable input: stage once through pinned memory
+      if ((rc = f->h_in.reserve(B * (size_t)w * h_img))) return rc;
+      uint8_t* stg = (uint8_t*)f->h_in.p;
+      for (size_t i = 0; i < B; i++)
+        for (int y = 0; y < h_img; y++) memcpy(stg + (i * h_img + y) * w, imgs + i * img_stride + (size_t)y * pitch, w);
+      src = stg;
+      spitch = w;
+      img_stride = (size_t)w * h_img;
+    }
+    if (img_stride == spitch * h_img) {
+      GFS_CUDA(cudaMemcpy2DAsync(d_in, dpitch, src, spitch, w, (size_t)h_img * B, cudaMemcpyHostToDevice, st));
+    } else {
+      for (size_t i = 0; i < B; i++)
+        GFS_CUDA(cudaMemcpy2DAsync(d_in + i * dstride, dpitch, src + i * img_stride, spitch, w, h_img, cudaMemcpyHostToDevice, st));
+    }
+    rc = gfs_frontend_run_device(f, stream, d_in, batch, w, h_img, (int)dpitch, dstride, d_kp, d_desc, d_n, d_mono,
+                                 (int*)f->d_idx.p, (int*)f->d_dist.p, (uint8_t*)f->d_inl.p, (int*)f->d_cnt.p);
+    if (rc) return rc;
+    GFS_CUDA(cudaMemcpyAsync(out_kp, d_kp, B * s * sizeof(GfsKeyPoint), cudaMemcpyDeviceToHost, st));
+    GFS_CUDA(cudaMemcpyAsync(out_desc, d_desc, B * s * 32, cudaMemcpyDeviceToHost, st));
+  }
   GFS_CUDA(cudaMemcpyAsync(out_n, d_n, B * sizeof(int), cudaMemcpyDeviceToHost, st));
   GFS_CUDA(cudaMemcpyAsync(out_mono, d_mono, B * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (batch > 1) {
@@ -161,6 +220,7 @@ int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batc
     GFS_CUDA(cudaMemcpyAsync(out_inlier, f->d_inl.p, (B - 1) * s, cudaMemcpyDeviceToHost, st));
     GFS_CUDA(cudaMemcpyAsync(out_inlier_count, f->d_cnt.p, (B - 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
   }
+  if (f->outStream) GFS_CUDA(cudaStreamSynchronize(f->outStream));
   GFS_CUDA(cudaStreamSynchronize(st));
   return GFS_OK;
 }

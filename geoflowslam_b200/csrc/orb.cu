@@ -213,97 +213,106 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbDev P, const uin
     uint32_t* z = (uint32_t*)sc;
     for (int idx = tid; idx < ((dh + 2) * SP) >> 2; idx += FAST_THREADS) z[idx] = 0u;
   }
-  if (tid == 0) { s_nCorner = 0; s_nCand = 0; }
+  if (tid == 0) { s_nCorner = 0; s_nCand = 0; s_nKept = 0; }
   __syncthreads();
 
   const int npx = dw * dh;
   const int thMin = P.minTh, thIni = P.iniTh;
   const int lane = tid & 31;
-  // phase 1 (every pixel, all lanes busy): antipodal-pair reject.  Every 9-arc of the 16-ring holds
-  // one pixel of each antipodal pair, so both (0,8) and (4,12) must have a bright (dark) member.
-  {
-    int x = tid % dw, y = tid / dw;
-    const int sx = FAST_THREADS % dw, sy = FAST_THREADS / dw;
-    const int rounds = (npx + FAST_THREADS - 1) / FAST_THREADS;
-    for (int r = 0; r < rounds; r++) {
-      const int idx = r * FAST_THREADS + tid;
-      bool pass = false;
-      if (idx < npx) {
+  int nKept = 0;
+  // cv::FAST(cell, iniThFAST) first; only a cell without any surviving corner is redone at minThFAST
+  // (ORBextractor.cc:809-826).  At threshold th the score map only holds corners at th, which is all
+  // the 3x3 NMS of that FAST call ever sees.
+  for (int pass = 0; pass < 2; pass++) {
+    const int th = pass == 0 ? thIni : thMin;
+    // phase 1 (every pixel, all lanes busy): antipodal-pair reject.  Every 9-arc of the 16-ring holds
+    // one pixel of each antipodal pair, so both (0,8) and (4,12) must have a bright (dark) member.
+    {
+      int x = tid % dw, y = tid / dw;
+      const int sx = FAST_THREADS % dw, sy = FAST_THREADS / dw;
+      const int rounds = (npx + FAST_THREADS - 1) / FAST_THREADS;
+      for (int r = 0; r < rounds; r++) {
+        const int idx = r * FAST_THREADS + tid;
+        bool ok = false;
+        if (idx < npx) {
+          const uint8_t* p = roi + (y + 3) * RP + (x + 3);
+          const int cval = p[0];
+          const int hi = cval + th, lo = cval - th;
+          const int v0 = p[3 * RP], v8 = p[-3 * RP], v4 = p[3], v12 = p[-3];
+          const bool br = ((v0 > hi) | (v8 > hi)) & ((v4 > hi) | (v12 > hi));
+          const bool dk = ((v0 < lo) | (v8 < lo)) & ((v4 < lo) | (v12 < lo));
+          ok = br | dk;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (m) {
+          int basePos = 0;
+          if (lane == 0) basePos = atomicAdd(&s_nCand, __popc(m));
+          basePos = __shfl_sync(0xffffffffu, basePos, 0);
+          if (ok) cand[basePos + __popc(m & ((1u << lane) - 1u))] = (uint16_t)idx;
+        }
+        x += sx; y += sy;
+        if (x >= dw) { x -= dw; y++; }
+      }
+    }
+    __syncthreads();
+    // phase 2 (survivors only, densely packed): full ring test, score, corner list
+    {
+      const int nCand = s_nCand;
+      for (int i = tid; i < nCand; i += FAST_THREADS) {
+        const int idx = cand[i];
+        const int y = idx / dw, x = idx - y * dw;
         const uint8_t* p = roi + (y + 3) * RP + (x + 3);
         const int cval = p[0];
-        const int hi = cval + thMin, lo = cval - thMin;
-        const int v0 = p[3 * RP], v8 = p[-3 * RP], v4 = p[3], v12 = p[-3];
-        const bool br = ((v0 > hi) | (v8 > hi)) & ((v4 > hi) | (v12 > hi));
-        const bool dk = ((v0 < lo) | (v8 < lo)) & ((v4 < lo) | (v12 < lo));
-        pass = br | dk;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, pass);
-      if (m) {
-        int basePos = 0;
-        if (lane == 0) basePos = atomicAdd(&s_nCand, __popc(m));
-        basePos = __shfl_sync(0xffffffffu, basePos, 0);
-        if (pass) cand[basePos + __popc(m & ((1u << lane) - 1u))] = (uint16_t)idx;
-      }
-      x += sx; y += sy;
-      if (x >= dw) { x -= dw; y++; }
-    }
-  }
-  __syncthreads();
-  // phase 2 (survivors only, densely packed): full ring test, score, corner list
-  {
-    const int nCand = s_nCand;
-    for (int i = tid; i < nCand; i += FAST_THREADS) {
-      const int idx = cand[i];
-      const int y = idx / dw, x = idx - y * dw;
-      const uint8_t* p = roi + (y + 3) * RP + (x + 3);
-      const int cval = p[0];
-      const int hi = cval + thMin, lo = cval - thMin;
-      int v[16];
-      v[0] = p[3 * RP];       v[1] = p[3 * RP + 1];   v[2] = p[2 * RP + 2];   v[3] = p[RP + 3];
-      v[4] = p[3];            v[5] = p[-RP + 3];      v[6] = p[-2 * RP + 2];  v[7] = p[-3 * RP + 1];
-      v[8] = p[-3 * RP];      v[9] = p[-3 * RP - 1];  v[10] = p[-2 * RP - 2]; v[11] = p[-RP - 3];
-      v[12] = p[-3];          v[13] = p[RP - 3];      v[14] = p[2 * RP - 2];  v[15] = p[3 * RP - 1];
-      unsigned bright = 0, dark = 0;
+        const int hi = cval + th, lo = cval - th;
+        int v[16];
+        v[0] = p[3 * RP];       v[1] = p[3 * RP + 1];   v[2] = p[2 * RP + 2];   v[3] = p[RP + 3];
+        v[4] = p[3];            v[5] = p[-RP + 3];      v[6] = p[-2 * RP + 2];  v[7] = p[-3 * RP + 1];
+        v[8] = p[-3 * RP];      v[9] = p[-3 * RP - 1];  v[10] = p[-2 * RP - 2]; v[11] = p[-RP - 3];
+        v[12] = p[-3];          v[13] = p[RP - 3];      v[14] = p[2 * RP - 2];  v[15] = p[3 * RP - 1];
+        unsigned bright = 0, dark = 0;
 #pragma unroll
-      for (int k = 0; k < 16; k++) {
-        bright |= (unsigned)(v[k] > hi) << k;
-        dark |= (unsigned)(v[k] < lo) << k;
-      }
-      if (has_arc9(bright) || has_arc9(dark)) {
-        int d[16];
+        for (int k = 0; k < 16; k++) {
+          bright |= (unsigned)(v[k] > hi) << k;
+          dark |= (unsigned)(v[k] < lo) << k;
+        }
+        if (has_arc9(bright) || has_arc9(dark)) {
+          int d[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) d[k] = cval - v[k];
-        const int best = fast_best16(d);
-        sc[(y + 1) * SP + (x + 1)] = (uint8_t)(best - 1);  // best > minTh >= 0, best <= 255
-        corners[atomicAdd(&s_nCorner, 1)] = (uint16_t)idx;
+          for (int k = 0; k < 16; k++) d[k] = cval - v[k];
+          const int best = fast_best16(d);
+          sc[(y + 1) * SP + (x + 1)] = (uint8_t)(best - 1);  // best > th >= 0, best <= 255
+          corners[atomicAdd(&s_nCorner, 1)] = (uint16_t)idx;
+        }
       }
-    }
-  }
-  __syncthreads();
-  const int nCorner = s_nCorner;
-
-  // 3x3 NMS with strict '>' at threshold t, on the detected corners only: a neighbour counts only
-  // if it is itself a corner at t (score >= t <=> best > t); pixels outside the cell's tested
-  // region score 0.  If nothing survives at iniTh the cell is redone at minTh (:809-826).
-  for (int pass = 0; pass < 2; pass++) {
-    const int t = pass == 0 ? thIni : thMin;
-    if (tid == 0) s_nKept = 0;
-    __syncthreads();
-    for (int i = tid; i < nCorner; i += FAST_THREADS) {
-      const int idx = corners[i];
-      const int y = idx / dw, x = idx - y * dw;
-      const uint8_t* q = sc + (y + 1) * SP + (x + 1);
-      const int s = q[0];
-      if (s < t || s == 0) continue;
-      int m = max(max(q[-SP - 1], q[-SP]), max(q[-SP + 1], q[-1]));
-      m = max(m, max(max(q[1], q[SP - 1]), max(q[SP], q[SP + 1])));
-      // neighbours below t count as 0, so the comparison only applies when m >= t
-      if ((m >= t) ? (s > m) : true) keptList[atomicAdd(&s_nKept, 1)] = (uint32_t)idx | ((uint32_t)s << 16);
     }
     __syncthreads();
-    if (s_nKept > 0 || thIni == thMin) break;
+    // 3x3 NMS with strict '>' over the corners of this pass; pixels outside the cell's tested region
+    // (and non-corners) score 0
+    {
+      const int nCorner = s_nCorner;
+      for (int i = tid; i < nCorner; i += FAST_THREADS) {
+        const int idx = corners[i];
+        const int y = idx / dw, x = idx - y * dw;
+        const uint8_t* q = sc + (y + 1) * SP + (x + 1);
+        const int sv = q[0];
+        if (sv == 0) continue;
+        int m = max(max(q[-SP - 1], q[-SP]), max(q[-SP + 1], q[-1]));
+        m = max(m, max(max(q[1], q[SP - 1]), max(q[SP], q[SP + 1])));
+        if (sv > m) keptList[atomicAdd(&s_nKept, 1)] = (uint32_t)idx | ((uint32_t)sv << 16);
+      }
+    }
+    __syncthreads();
+    nKept = s_nKept;
+    if (nKept > 0 || thIni == thMin) break;
+    // nothing at iniTh: clear and redo the cell at minTh
+    __syncthreads();
+    {
+      uint32_t* z = (uint32_t*)sc;
+      for (int idx = tid; idx < ((dh + 2) * SP) >> 2; idx += FAST_THREADS) z[idx] = 0u;
+    }
+    if (tid == 0) { s_nCorner = 0; s_nCand = 0; s_nKept = 0; }
+    __syncthreads();
   }
-  const int nKept = s_nKept;
   // output in cv::FAST order (row-major): rank = number of survivors with a smaller pixel index
   uint32_t* out = cellKeys + ((long long)frame * P.totalCells + cell) * P.cellCap;
   for (int i = tid; i < nKept; i += FAST_THREADS) {

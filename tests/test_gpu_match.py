@@ -120,3 +120,33 @@ def test_frontend_batch_equals_oracle():
         assert np.array_equal(out["inlier"][p, :n1].astype(bool), om)
     # frames 2 -> 3 straddle two different scenes: GMS must reject (almost) everything
     assert out["inlier_count"][2] < out["inlier_count"][0] // 4
+
+
+def test_frontend_pipelined_host_path_equals_device_path():
+    """batch > chunk with pinned buffers takes the chunked, stream-overlapped path: same bits."""
+    import torch
+    from geoflowslam_b200 import TrackingFrontend, synth
+    frames = synth.orb_frames(144, group=8)                    # 144 > 64: three chunks
+    fe = TrackingFrontend(1000, 1.2, 8, 25, 7, max_size=(640, 480), max_batch=144)
+    ref = fe.run(frames)                                       # pageable buffers: single-shot path
+    keep = []
+
+    def pinned(shape, dt):
+        nb = int(np.prod(shape)) * np.dtype(dt).itemsize
+        t = torch.empty(max(nb, 1), dtype=torch.uint8).pin_memory(); keep.append(t)
+        return t.numpy()[:nb].view(dt).reshape(shape)
+
+    h_imgs = pinned(frames.shape, np.uint8); h_imgs[...] = frames
+    out = fe.alloc_host_outputs(144, pinned)
+    fe.run(h_imgs, out=out)
+    for k in ref:
+        if k in ("kp", "desc"):
+            for i in range(144):
+                n = ref["n"][i]
+                assert np.array_equal(ref[k][i, :n], out[k][i, :n]), (k, i)
+        elif k in ("train_idx", "dist", "inlier"):
+            for i in range(143):
+                n = ref["n"][i]
+                assert np.array_equal(ref[k][i, :n], out[k][i, :n]), (k, i)
+        else:
+            assert np.array_equal(ref[k], out[k]), k
