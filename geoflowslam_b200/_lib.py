@@ -50,6 +50,10 @@ SIGNATURES = {
     "gfs_orb_launches_per_call": ([vp, ci, ci], ci),
     "gfs_orb_set_profiling": ([vp, ci], ci),
     "gfs_orb_get_profile": ([vp, vp], ci),
+    "gfs_search_by_projection": ([vp, ci, cf, ci, vp, ci, vp, vp, vp, vp, ci, cf, cf, cf, cf, vp, vp], ci),
+    "gfs_search_by_projection_batch_device": ([vp, ci, cf, ci, vp, vp, ci, vp, vp, vp, vp, vp, ci, ci, cf, cf, cf, cf, vp, vp, vp], ci),
+    "gfs_depth_to_cloud": ([vp, vp, ci, ci, ci, cf, cf, cf, cf, vp, ci, vp], ci),
+    "gfs_depth_to_cloud_batch_device": ([vp, vp, ci, ci, ci, ci, sz, ci, cf, cf, cf, cf, vp, ci, vp], ci),
     "gfs_frontend_create": ([ci, cf, ci, ci, ci, ci, ci, ci, C.POINTER(vp)], ci),
     "gfs_frontend_destroy": ([vp], ci),
     "gfs_frontend_max_keypoints": ([vp], ci),

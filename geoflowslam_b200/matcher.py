@@ -64,3 +64,41 @@ def _as_kp(k):
     out = np.zeros(len(a), KP_DTYPE)
     out["x"], out["y"] = a[:, 0], a[:, 1]
     return out
+
+
+PROJ_QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("ur", "<f4"), ("angle", "<f4"),
+                             ("min_level", "<i4"), ("max_level", "<i4"), ("blocks", "<i4"), ("desc", "u1", (32,))])
+assert PROJ_QUERY_DTYPE.itemsize == 64
+
+
+def search_by_projection(mode, queries, kps_un, u_right, desc, occupied, grid, nnratio=0.9, check_orientation=True,
+                         stream=None):
+    """ORBmatcher::SearchByProjection on flattened inputs (include/gfs_b200.h GfsProjQuery).
+    mode 0 = (CurrentFrame, LastFrame, th) src/ORBmatcher.cc:1853; mode 1 = (Frame, vpMapPoints, th) :43.
+    grid = (mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv).
+    -> (assign[n] query index per keypoint or -1, nmatches)"""
+    L = _lib.lib()
+    q = np.ascontiguousarray(queries, PROJ_QUERY_DTYPE)
+    k = np.ascontiguousarray(kps_un, KP_DTYPE)
+    ur = np.ascontiguousarray(u_right, np.float32)
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    oc = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    assign = np.full(max(len(k), 1), -1, np.int32)
+    nm = C.c_int()
+    check(L.gfs_search_by_projection(stream, int(mode), float(nnratio), int(check_orientation), ptr(q), len(q), ptr(k),
+                                     ptr(ur), ptr(d), ptr(oc), len(k), float(grid[0]), float(grid[1]), float(grid[2]),
+                                     float(grid[3]), ptr(assign), C.byref(nm)))
+    return assign[:len(k)], nm.value
+
+
+def depth_to_cloud(depth, stride, fx, fy, cx, cy, stream=None):
+    """Frame::ConvertDepthToPointCloud (src/Frame.cc:590-623) -> (n, 4) float32 points (x, y, z, 1)."""
+    L = _lib.lib()
+    depth = np.ascontiguousarray(depth, np.float32)
+    h, w = depth.shape
+    cap = ((w + stride - 1) // stride) * ((h + stride - 1) // stride)
+    out = np.zeros((cap, 4), np.float32)
+    n = C.c_int()
+    check(L.gfs_depth_to_cloud(stream, ptr(depth), w, h, int(stride), float(fx), float(fy), float(cx), float(cy), ptr(out),
+                               cap, C.byref(n)))
+    return out[:n.value].copy()

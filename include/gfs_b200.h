@@ -123,6 +123,43 @@ int gfs_gms_filter_batch_device(void* stream, const GfsKeyPoint* d_kp1, const in
 int gfs_gms_filter(void* stream, const GfsKeyPoint* kp1, int n1, int w1, int h1, const GfsKeyPoint* kp2, int n2,
                    int w2, int h2, const int* matches_qt, int nm, uint8_t* out_inlier, int* out_count);
 
+/* Projection-window search -- replaces ORBmatcher::SearchByProjection(Frame&, const Frame&, th,
+ * bMono) (mode 0, src/ORBmatcher.cc:1853-2063) and SearchByProjection(Frame&, vector<MapPoint*>&,
+ * th, bFarPoints, thFarPoints) (mode 1, :43-207) for the RGB-D / monocular layout (Nleft == -1),
+ * including Frame::GetFeaturesInArea / AssignFeaturesToGrid (src/Frame.cc:1007-1071, 734-761).
+ * The shim flattens each candidate MapPoint into a query; the projection itself (Sophus / camera
+ * model) stays with the caller. */
+typedef struct GfsProjQuery {
+  float u, v;     /* projected position (uv / mTrackProjX,Y) */
+  float radius;   /* search radius (th * scale[octave], or r * scale[level]); < 0 = skip this map point */
+  float ur;       /* projected right coordinate (uv.x - bf * invz / mTrackProjXR) */
+  float angle;    /* keypoint angle in the last frame (rotation histogram, mode 0) */
+  int32_t min_level, max_level; /* GetFeaturesInArea level window (-1 = open) */
+  int32_t blocks; /* MapPoint::Observations() > 0: a keypoint it takes is skipped by later map points */
+  uint8_t desc[32];
+} GfsProjQuery;     /* 64 bytes */
+/* Frame side: undistorted keypoints (x, y, octave, angle), mvuRight, descriptors, occupied[i] =
+ * (mvpMapPoints[i] && Observations() > 0) before the call (may be NULL), grid parameters mnMinX,
+ * mnMinY, mfGridElementWidthInv, mfGridElementHeightInv.  out_assign[i] = index of the query now
+ * stored in mvpMapPoints[i] or -1 (untouched / cleared); *out_nmatches = the reference's return value. */
+int gfs_search_by_projection(void* stream, int mode, float nnratio, int check_orientation, const GfsProjQuery* queries, int nq,
+                             const GfsKeyPoint* kps_un, const float* u_right, const uint8_t* desc, const uint8_t* occupied,
+                             int n, float min_x, float min_y, float inv_w, float inv_h, int* out_assign, int* out_nmatches);
+int gfs_search_by_projection_batch_device(void* stream, int mode, float nnratio, int check_orientation,
+                                          const GfsProjQuery* d_queries, const int* d_nq, int qstride,
+                                          const GfsKeyPoint* d_kps_un, const float* d_u_right, const uint8_t* d_desc,
+                                          const uint8_t* d_occupied, const int* d_n, int kstride, int frames, float min_x,
+                                          float min_y, float inv_w, float inv_h, int* d_scratch_claim, int* d_out_assign,
+                                          int* d_out_nmatches);
+
+/* Frame::ConvertDepthToPointCloud (src/Frame.cc:590-623): every `stride`-th pixel with 0 < d < 10 m,
+ * scan order, float4 (x, y, z, 1) -- the clouds RegistrationGICP consumes. */
+int gfs_depth_to_cloud(void* stream, const float* depth, int w, int h, int stride, float fx, float fy, float cx, float cy,
+                       float* out_xyz1, int cap, int* out_n);
+int gfs_depth_to_cloud_batch_device(void* stream, const float* d_depth, int frames, int w, int h, int pitch_floats,
+                                    size_t frame_stride_floats, int stride, float fx, float fy, float cx, float cy,
+                                    float* d_out_xyz1, int cap, int* d_out_n);
+
 /* ------------------------------------------------------------------------------------------
  * Batched tracking front-end (BASELINE.json configs[1]): ORB extraction of `batch` independent
  * frames, then BF-Hamming + GMS from frame i to frame i+1 -- the Frame::ExtractORB

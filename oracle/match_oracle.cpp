@@ -156,3 +156,162 @@ int gfo_gms_filter(const float* pts1, int n1, int w1, int h1, const float* pts2,
   return n;
 }
 }
+
+// =================================================================================================
+// Projection-window search (ORBmatcher::SearchByProjection, both overloads) on flattened inputs,
+// with the Frame grid helpers it relies on.  RGB-D / monocular layout (Frame::Nleft == -1).
+//   Frame::AssignFeaturesToGrid / PosInGrid        src/Frame.cc:734-761, 1073-1084 (64 x 48 cells)
+//   Frame::GetFeaturesInArea                       src/Frame.cc:1007-1071
+//   SearchByProjection(Frame&, vector<MapPoint*>&) src/ORBmatcher.cc:43-207   (mode 1)
+//   SearchByProjection(Frame&, const Frame&, ...)  src/ORBmatcher.cc:1853-2063 (mode 0)
+//   ComputeThreeMaxima                             src/ORBmatcher.cc:2500-2532
+// =================================================================================================
+#include <algorithm>
+namespace gfo {
+
+struct ProjQuery {  // == GfsProjQuery (include/gfs_b200.h)
+  float u, v, radius, ur, angle;
+  int min_level, max_level, blocks;
+  uint8_t desc[32];
+};
+struct KeyPt {
+  float x, y, size, angle, response;
+  int octave;
+};
+static const int GRID_COLS = 64, GRID_ROWS = 48, TH_HIGH = 100, HISTO_LENGTH = 30;
+
+struct FrameGrid {
+  std::vector<int> cells[GRID_COLS][GRID_ROWS];
+  float minX, minY, invW, invH;
+  void build(const KeyPt* k, int n) {
+    for (int i = 0; i < n; i++) {
+      const int px = (int)std::round((k[i].x - minX) * invW), py = (int)std::round((k[i].y - minY) * invH);
+      if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
+      cells[px][py].push_back(i);
+    }
+  }
+  void in_area(const KeyPt* k, float x, float y, float r, int minLevel, int maxLevel, std::vector<int>& out) const {
+    out.clear();
+    const int nMinCellX = std::max(0, (int)std::floor((x - minX - r) * invW));
+    if (nMinCellX >= GRID_COLS) return;
+    const int nMaxCellX = std::min(GRID_COLS - 1, (int)std::ceil((x - minX + r) * invW));
+    if (nMaxCellX < 0) return;
+    const int nMinCellY = std::max(0, (int)std::floor((y - minY - r) * invH));
+    if (nMinCellY >= GRID_ROWS) return;
+    const int nMaxCellY = std::min(GRID_ROWS - 1, (int)std::ceil((y - minY + r) * invH));
+    if (nMaxCellY < 0) return;
+    const bool check = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+      for (int iy = nMinCellY; iy <= nMaxCellY; iy++)
+        for (int j : cells[ix][iy]) {
+          if (check) {
+            if (k[j].octave < minLevel) continue;
+            if (maxLevel >= 0 && k[j].octave > maxLevel) continue;
+          }
+          const float dx = k[j].x - x, dy = k[j].y - y;
+          if (std::fabs(dx) < r && std::fabs(dy) < r) out.push_back(j);
+        }
+  }
+};
+
+static int search_by_projection(int mode, float nnratio, int checkOri, const ProjQuery* q, int nq, const KeyPt* kps,
+                                const float* uRight, const uint8_t* desc, const uint8_t* occupied, int n, float minX,
+                                float minY, float invW, float invH, int* assign) {
+  FrameGrid* g = new FrameGrid();
+  g->minX = minX; g->minY = minY; g->invW = invW; g->invH = invH;
+  g->build(kps, n);
+  std::vector<int> blocked(n), cand;
+  for (int i = 0; i < n; i++) { assign[i] = -1; blocked[i] = occupied ? occupied[i] != 0 : 0; }
+  std::vector<std::vector<int>> rotHist(HISTO_LENGTH);
+  const float factor = 1.0f / HISTO_LENGTH;
+  int nmatches = 0;
+  for (int i = 0; i < nq; i++) {
+    const ProjQuery& Q = q[i];
+    if (Q.radius < 0) continue;  // query not in view / filtered by the caller
+    g->in_area(kps, Q.u, Q.v, Q.radius, Q.min_level, Q.max_level, cand);
+    if (cand.empty()) continue;
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+    for (int idx : cand) {
+      if (blocked[idx]) continue;
+      if (uRight[idx] > 0) {
+        const float er = std::fabs(Q.ur - uRight[idx]);
+        if (er > Q.radius) continue;
+      }
+      const int dist = descriptor_distance(Q.desc, desc + 32 * (size_t)idx);
+      if (dist < bestDist) {
+        bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = kps[idx].octave; bestIdx = idx;
+      } else if (mode == 1 && dist < bestDist2) {
+        bestLevel2 = kps[idx].octave; bestDist2 = dist;
+      }
+    }
+    if (bestDist <= TH_HIGH) {
+      if (mode == 1) {
+        if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+        if (bestLevel != bestLevel2 || bestDist <= nnratio * bestDist2) {
+          assign[bestIdx] = i;
+          blocked[bestIdx] = Q.blocks != 0;
+          nmatches++;
+        }
+      } else {
+        assign[bestIdx] = i;
+        blocked[bestIdx] = Q.blocks != 0;
+        nmatches++;
+        if (checkOri) {
+          float rot = Q.angle - kps[bestIdx].angle;
+          if (rot < 0.0) rot += 360.0f;
+          int bin = (int)std::round(rot * factor);
+          if (bin == HISTO_LENGTH) bin = 0;
+          rotHist[bin].push_back(bestIdx);
+        }
+      }
+    }
+  }
+  if (mode == 0 && checkOri) {
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      const int s = (int)rotHist[i].size();
+      if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+      else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+      else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+    for (int i = 0; i < HISTO_LENGTH; i++)
+      if (i != ind1 && i != ind2 && i != ind3)
+        for (int idx : rotHist[i]) { assign[idx] = -1; nmatches--; }
+  }
+  delete g;
+  return nmatches;
+}
+
+}  // namespace gfo
+
+extern "C" {
+int gfo_search_by_projection(int mode, float nnratio, int checkOri, const void* queries, int nq, const void* kps,
+                             const float* uRight, const uint8_t* desc, const uint8_t* occupied, int n, float minX, float minY,
+                             float invW, float invH, int* assign) {
+  return gfo::search_by_projection(mode, nnratio, checkOri, (const gfo::ProjQuery*)queries, nq, (const gfo::KeyPt*)kps, uRight,
+                                   desc, occupied, n, minX, minY, invW, invH, assign);
+}
+
+// Frame::ConvertDepthToPointCloud (src/Frame.cc:590-623): every `stride`-th pixel with 0 < d < 10,
+// scan order, float32 back-projection.  Returns the number of points.
+int gfo_depth_to_cloud(const float* depth, int w, int h, int stride, float fx, float fy, float cx, float cy, float* out4,
+                       int cap) {
+  int n = 0;
+  for (int v = 0; v < h; v += stride)
+    for (int u = 0; u < w; u += stride) {
+      const float d = depth[(size_t)v * w + u];
+      if (d > 0.0 && d < 10.0) {
+        if (n < cap) {
+          out4[4 * n] = (u - cx) * d / fx;
+          out4[4 * n + 1] = (v - cy) * d / fy;
+          out4[4 * n + 2] = d;
+          out4[4 * n + 3] = 1.0f;
+        }
+        n++;
+      }
+    }
+  return n;
+}
+}

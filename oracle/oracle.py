@@ -386,3 +386,43 @@ def so3(w):
     R = np.zeros((3, 3)); lg = np.zeros(3); Jr = np.zeros((3, 3)); Ji = np.zeros((3, 3))
     lib().gfo_so3(_p(w), _p(R), _p(lg), _p(Jr), _p(Ji))
     return R, lg, Jr, Ji
+
+
+# ------------------------------------------------------------------------------ projection search / depth
+PROJ_QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("ur", "<f4"), ("angle", "<f4"),
+                             ("min_level", "<i4"), ("max_level", "<i4"), ("blocks", "<i4"), ("desc", "u1", (32,))])
+
+
+def _bind_proj(L):
+    L.gfo_search_by_projection.restype = C.c_int
+    L.gfo_search_by_projection.argtypes = [C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                           C.c_void_p]
+    L.gfo_depth_to_cloud.restype = C.c_int
+    L.gfo_depth_to_cloud.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                     C.c_void_p, C.c_int]
+
+
+_LATE_BINDERS.append(("gfo_search_by_projection", _bind_proj))
+
+
+def search_by_projection(mode, queries, kps_un, u_right, desc, occupied, grid, nnratio=0.9, check_orientation=True):
+    q = np.ascontiguousarray(queries, PROJ_QUERY_DTYPE)
+    k = np.ascontiguousarray(kps_un, KP_DTYPE)
+    ur = np.ascontiguousarray(u_right, np.float32)
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    oc = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    assign = np.full(max(len(k), 1), -1, np.int32)
+    n = lib().gfo_search_by_projection(int(mode), float(nnratio), int(check_orientation), _p(q), len(q), _p(k), _p(ur), _p(d),
+                                       None if oc is None else _p(oc), len(k), float(grid[0]), float(grid[1]),
+                                       float(grid[2]), float(grid[3]), _p(assign))
+    return assign[:len(k)], n
+
+
+def depth_to_cloud(depth, stride, fx, fy, cx, cy):
+    depth = np.ascontiguousarray(depth, np.float32)
+    h, w = depth.shape
+    cap = ((w + stride - 1) // stride) * ((h + stride - 1) // stride)
+    out = np.zeros((cap, 4), np.float32)
+    n = lib().gfo_depth_to_cloud(_p(depth), w, h, int(stride), fx, fy, cx, cy, _p(out), cap)
+    return out[:n].copy()
