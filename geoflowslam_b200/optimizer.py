@@ -135,3 +135,10 @@ class Optimizer:
 
     def last_launches(self):
         return self._L.gfs_ba_last_launches(self._h)
+
+    def set_partition(self, rank, world, group=None):
+        """Edge-partitioned mode: this rank owns landmarks p % world == rank; the reduced pose system
+        is all-reduced over `group` (torch.distributed, NCCL) once per LM trial."""
+        from .parallel import ba_allreduce_callback
+        self._cb = ba_allreduce_callback(group) if world > 1 else None
+        check(self._L.gfs_ba_set_partition(self._h, int(rank), int(world), self._cb, None))
