@@ -169,8 +169,8 @@ def algorithmic_bytes(stage, n_frames, n_kp, n_cand):
         "pyramid": sum(px[:-1]) + sum(px[1:]),           # read levels 0..6, write levels 1..7
         "fast_cells": sum(px) + 4 * n_cand,              # read every level once, write packed candidates
         "octree": 4 * n_cand + 4 * n_kp,                 # read candidates, write selected keys
-        "blur": 2 * sum(px),                             # read + write every level
-        "orient_desc": n_kp * (749 + 512 + 24 + 32 + 4),  # disc + 512 samples + keypoint + descriptor + key
+        "blur": 0,                                       # fused into orient_desc (never materialised)
+        "orient_desc": n_kp * (43 * 43 + 24 + 32 + 4),   # 43x43 patch + keypoint + descriptor + key
         "pack_lapping": 0,
         "bf_hamming": 2 * n_kp * 32 + n_kp * 8,          # both descriptor sets + (idx, dist)
         "gms": 2 * n_kp * 8 + n_kp * 4 + n_kp,           # both point sets + train idx + mask
