@@ -42,7 +42,7 @@ struct BaCalib {
 };
 
 struct BaDev {
-  int maxKf, maxPt, maxObs, maxIn, maxDim, nblk;  // capacities (per problem)
+  int maxKf, maxOpt, maxPt, maxObs, maxIn, maxDim, nblk;  // capacities (per problem); maxOpt = optimizable keyframes
   int rank, world;                                 // landmark partition (p % world == rank), default 0 / 1
   BaCalib* calib;       // [B]
   double *kf, *kfBak;   // [B][maxKf][KF_STRIDE]
@@ -56,7 +56,7 @@ struct BaDev {
   const double *infoIn, *infoG, *infoA;    // [B][maxIn][81], [9], [9]
   const int *ptStart, *ptEdges;            // CSR landmarks -> edges: [B][maxPt+1], [B][maxObs]
   const int *kfStart, *kfEdges;            // CSR optimizable keyframes -> edges: [B][maxKf+1], [B][maxObs]
-  const int* ptKfEdge;                     // [B][maxPt][maxKf] edge id of (landmark, optimizable keyframe) or -1
+  const int* ptKfEdge;                     // [B][maxPt][maxOpt] edge id of (landmark, optimizable keyframe) or -1
   double* chi2;         // [B][maxObs] chi2 of every visual edge at the last evaluation
   double* inRho;        // [B][maxIn] robustified chi2 of inertial edge + its RW edges
   double* partChi;      // [B][nblk]
@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(128) k_schur_pairs(BaDev D) {
     const int e1 = D.kfEdges[(size_t)b * D.maxObs + q];
     const int j = D.obsPt[(size_t)b * D.maxObs + e1];
     if (!owned(D, j)) continue;
-    const int e2 = D.ptKfEdge[((size_t)b * D.maxPt + j) * D.maxKf + i2];
+    const int e2 = D.ptKfEdge[((size_t)b * D.maxPt + j) * D.maxOpt + i2];
     if (e2 < 0) continue;
     const double* B1 = D.E + ((size_t)b * D.maxObs + e1) * 18;
     const double* B2 = D.E + ((size_t)b * D.maxObs + e2) * 18;
@@ -1158,7 +1158,7 @@ int gfs_ba_create(int max_kf, int max_points, int max_obs, int max_inertial, int
   GFS_REQUIRE(out, GFS_ERR_INVALID, "out is null");
   *out = nullptr;
   GFS_REQUIRE(max_kf > 0 && max_points > 0 && max_obs > 0 && max_inertial >= 0 && max_batch > 0, GFS_ERR_INVALID, "bad capacity");
-  GFS_REQUIRE(15 * max_kf <= 320, GFS_ERR_CAPACITY, "at most 21 keyframes (optimizable + fixed) per problem");
+  // the reference optimises at most 20 keyframes (maxOpt, Optimizer.cc:3062-3068) next to up to 200 fixed ones
   int rc = gfs_device_check();
   if (rc) return rc;
   GfsBa* h = new GfsBa();
@@ -1166,7 +1166,8 @@ int gfs_ba_create(int max_kf, int max_points, int max_obs, int max_inertial, int
   BaDev& D = h->dev;
   memset(&D, 0, sizeof(D));
   D.maxKf = max_kf; D.maxPt = max_points; D.maxObs = max_obs; D.maxIn = std::max(max_inertial, 1);
-  D.maxDim = 15 * max_kf;
+  D.maxOpt = std::min(max_kf, 21);
+  D.maxDim = 15 * D.maxOpt;
   D.nblk = std::max(div_up(max_obs, ERR_THREADS), div_up(max_points + max_kf, 128)) + 1;
   D.rank = 0; D.world = 1;
   h->maxBatch = max_batch;
@@ -1185,7 +1186,7 @@ int gfs_ba_create(int max_kf, int max_points, int max_obs, int max_inertial, int
   AL(infoIn, double, B * D.maxIn * 81) AL(infoG, double, B * D.maxIn * 9) AL(infoA, double, B * D.maxIn * 9)
   AL(ptStart, int, B * (D.maxPt + 1)) AL(ptEdges, int, B * D.maxObs)
   AL(kfStart, int, B * (D.maxKf + 1)) AL(kfEdges, int, B * D.maxObs)
-  AL(ptKfEdge, int, B * D.maxPt * D.maxKf)
+  AL(ptKfEdge, int, B * D.maxPt * D.maxOpt)
   AL(chi2, double, B * D.maxObs) AL(inRho, double, B * D.maxIn) AL(partChi, double, B * D.nblk)
   AL(E, double, B * D.maxObs * 18) AL(Ae, double, B * D.maxObs * 27)
   AL(Hll, double, B * D.maxPt * 9) AL(bl, double, B * D.maxPt * 3) AL(Dinv, double, B * D.maxPt * 9) AL(db, double, B * D.maxPt * 3)
@@ -1244,10 +1245,11 @@ int gfs_ba_upload(GfsBa* h, void* stream, const GfsBaProblem* problems, int batc
   h->h_infoIn.assign(B * D.maxIn * 81, 0.0); h->h_infoG.assign(B * D.maxIn * 9, 0.0); h->h_infoA.assign(B * D.maxIn * 9, 0.0);
   h->h_ptStart.assign(B * (D.maxPt + 1), 0); h->h_ptEdges.assign(B * D.maxObs, 0);
   h->h_kfStart.assign(B * (D.maxKf + 1), 0); h->h_kfEdges.assign(B * D.maxObs, 0);
-  h->h_ptKfEdge.assign(B * D.maxPt * D.maxKf, -1);
+  h->h_ptKfEdge.assign(B * D.maxPt * D.maxOpt, -1);
   for (size_t b = 0; b < B; b++) {
     const GfsBaProblem& P = problems[b];
     const int nKf = P.n_opt_kf + P.n_fixed_kf;
+    GFS_REQUIRE(P.n_opt_kf <= D.maxOpt, GFS_ERR_CAPACITY, "more than 21 optimizable keyframes");
     GFS_REQUIRE(P.n_opt_kf >= 0 && P.n_fixed_kf >= 0 && nKf <= D.maxKf && P.n_points >= 0 && P.n_points <= D.maxPt &&
                     P.n_obs >= 0 && P.n_obs <= D.maxObs && P.n_inertial >= 0 && P.n_inertial <= D.maxIn,
                 GFS_ERR_CAPACITY, "problem exceeds the handle's capacity");
@@ -1280,7 +1282,7 @@ int gfs_ba_upload(GfsBa* h, void* stream, const GfsBaProblem* problems, int batc
       pc[j + 1]++;
       if (k < P.n_opt_kf) {
         kc[k + 1]++;
-        int& slot = h->h_ptKfEdge[(b * D.maxPt + j) * D.maxKf + k];
+        int& slot = h->h_ptKfEdge[(b * D.maxPt + j) * D.maxOpt + k];
         GFS_REQUIRE(slot < 0, GFS_ERR_INVALID, "two observations of one landmark in one keyframe are not supported");
         slot = e;
       }
@@ -1338,7 +1340,7 @@ int gfs_ba_solve_uploaded(GfsBa* h, void* stream) {
   BaDev& D = h->dev;
   const int B = h->batch;
   const dim3 gObs(div_up(D.maxObs, ERR_THREADS), B), gIn(div_up(D.maxIn, 32), B), gPt(div_up(D.maxPt, 128), B);
-  const dim3 gKfW(div_up(D.maxKf, 4), B), gPairs(div_up(D.maxKf * (D.maxKf + 1) / 2, 4), B);
+  const dim3 gKfW(div_up(D.maxOpt, 4), B), gPairs(div_up(D.maxOpt * (D.maxOpt + 1) / 2, 4), B);
   const dim3 gUpd(div_up(D.maxPt + D.maxKf, 128), B);
   const dim3 gCopy(div_up(std::max(D.maxKf * KF_STRIDE, D.maxPt * 3), 256), B);
   const dim3 gHs(std::min(64, div_up(D.maxDim * D.maxDim, 256)), B);

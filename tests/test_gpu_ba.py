@@ -74,3 +74,27 @@ def test_degenerate_problems():
     big = synth.ba_problem(seed=3003, n_kf=8, n_points=400)
     with pytest.raises(GfsError):
         opt.LocalInertialBA(big)                                # beyond max_points
+
+
+def test_many_fixed_keyframes():
+    """lFixedKeyFrames may hold up to 200 covisible observers (Optimizer.cc:3136-3165): only the
+    optimizable keyframes own unknowns, the fixed ones only contribute visual edges."""
+    from geoflowslam_b200 import Optimizer
+    from oracle import oracle as O
+    p = synth.ba_problem(seed=3030, n_kf=24, n_points=600, b_large=False)
+    n_opt = 6                                              # keyframes 6..24 become fixed observers
+    q = dict(p)
+    q["n_opt_kf"], q["n_fixed_kf"] = n_opt, p["n_opt_kf"] + p["n_fixed_kf"] - n_opt
+    keep = p["in_kf2"] < n_opt                             # inertial edges with an optimizable vertex
+    for k in ("in_kf1", "in_kf2", "in_pre", "in_downweight"):
+        q[k] = p[k][keep]
+    q["n_inertial"] = int(keep.sum())
+    q["in_downweight"] = (np.arange(q["n_inertial"]) == q["n_inertial"] - 1).astype(np.uint8)
+    opt = Optimizer(max_kf=40, max_points=600, max_obs=8192, max_inertial=24, max_batch=1)
+    g = opt.LocalInertialBA(q)
+    o = O.ba_solve(q)
+    _check(g, o, q)
+    assert np.array_equal(g["kf_twb"][n_opt:], p["kf_twb"][n_opt:])       # fixed keyframes untouched
+    from geoflowslam_b200 import GfsError
+    with pytest.raises(GfsError):
+        opt.LocalInertialBA(p)                              # 24 optimizable keyframes: beyond the 21 supported
