@@ -6,6 +6,7 @@
 //   * gms_matcher::GetInlierMask(mask, false, false)      Thirdparty/GMS/include/gms_matcher.h:236-246 -> run(1) :385-419
 // Integer work throughout: results are bit-exact against oracle/match_oracle.cpp.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -78,6 +79,75 @@ __global__ void __launch_bounds__(BF_WARPS * 32) k_bf_hamming(const uint8_t* __r
         out_idx[(size_t)pair * stride + q] = none ? -1 : (int)(v & 0xffffffffu);
         out_dist[(size_t)pair * stride + q] = none ? -1 : (int)(v >> 32);
       }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_bf_hamming_mma: the same argmin, with the 256-bit XOR-popcount done by the tensor-core binary MMA
+// (mma.sync m16n8k256 .b1 xor.popc: one warp instruction = 16 x 8 Hamming distances).  Experimental:
+// on sm_100a ptxas lowers the instruction onto IMMA.16832.U8 sequences and the kernel is slower than the
+// POPC one (2.73 vs 1.90 ms per 1023 pairs); kept, bit-exact, behind GFS_BF_MMA=1 for comparison.
+// CTA = 8 warps x 16 queries; train descriptors in shared memory, row-major.
+// ------------------------------------------------------------------------------------------------
+static const int BFM_WARPS = 8;
+static const int BFM_QPB = BFM_WARPS * 16;
+
+__global__ void __launch_bounds__(BFM_WARPS * 32) k_bf_hamming_mma(const uint8_t* __restrict__ dq, const int* __restrict__ nq,
+                                                                   const uint8_t* __restrict__ dt, const int* __restrict__ nt,
+                                                                   int stride, int* __restrict__ out_idx,
+                                                                   int* __restrict__ out_dist) {
+  extern __shared__ uint32_t T[];  // [tp][8]
+  const int pair = blockIdx.y;
+  const int nQ = nq[pair], nT = nt[pair];
+  const int q0 = blockIdx.x * BFM_QPB;
+  if (q0 >= nQ) return;
+  const int tp = (nT + 7) & ~7;
+  const uint32_t* gt = (const uint32_t*)(dt + (size_t)pair * stride * 32);
+  for (int i = threadIdx.x; i < tp * 8; i += blockDim.x) T[i] = ((i >> 3) < nT) ? __ldg(gt + i) : 0u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int qb = q0 + warp * 16;
+  if (qb >= nQ) return;
+  const uint32_t* gq = (const uint32_t*)(dq + (size_t)pair * stride * 32);
+  const int qa = min(qb + g, nQ - 1), qc = min(qb + g + 8, nQ - 1);
+  const uint32_t a0 = __ldg(gq + (size_t)qa * 8 + t), a1 = __ldg(gq + (size_t)qc * 8 + t);
+  const uint32_t a2 = __ldg(gq + (size_t)qa * 8 + t + 4), a3 = __ldg(gq + (size_t)qc * 8 + t + 4);
+  int bestA = 0x7fffffff, idxA = 0x7fffffff, bestB = 0x7fffffff, idxB = 0x7fffffff;
+  for (int c = 0; c < tp; c += 8) {
+    const uint32_t b0 = T[(c + g) * 8 + t], b1 = T[(c + g) * 8 + t + 4];
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    asm volatile(
+        "mma.sync.aligned.m16n8k256.row.col.s32.b1.b1.s32.xor.popc {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    const int j0 = c + 2 * t, j1 = j0 + 1;  // train rows of this thread's two columns (ascending)
+    if (j0 < nT) {
+      if (c0 < bestA) { bestA = c0; idxA = j0; }
+      if (c2 < bestB) { bestB = c2; idxB = j0; }
+    }
+    if (j1 < nT) {
+      if (c1 < bestA) { bestA = c1; idxA = j1; }
+      if (c3 < bestB) { bestB = c3; idxB = j1; }
+    }
+  }
+  unsigned long long va = ((unsigned long long)(unsigned)bestA << 32) | (unsigned)idxA;
+  unsigned long long vb = ((unsigned long long)(unsigned)bestB << 32) | (unsigned)idxB;
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    va = min(va, __shfl_xor_sync(0xffffffffu, va, o));
+    vb = min(vb, __shfl_xor_sync(0xffffffffu, vb, o));
+  }
+  if (t == 0) {
+    const bool none = nT == 0;
+    if (qb + g < nQ) {
+      out_idx[(size_t)pair * stride + qb + g] = none ? -1 : (int)(va & 0xffffffffu);
+      out_dist[(size_t)pair * stride + qb + g] = none ? -1 : (int)(va >> 32);
+    }
+    if (qb + g + 8 < nQ) {
+      out_idx[(size_t)pair * stride + qb + g + 8] = none ? -1 : (int)(vb & 0xffffffffu);
+      out_dist[(size_t)pair * stride + qb + g + 8] = none ? -1 : (int)(vb >> 32);
     }
   }
 }
@@ -274,8 +344,23 @@ int gfs_match_bf_hamming_batch_device(void* stream, const uint8_t* d_dq, const i
     GFS_CUDA(cudaFuncSetAttribute(k_bf_hamming, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  k_bf_hamming<<<dim3(div_up(stride, BF_QPB), pairs), BF_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      d_dq, d_nq, d_dt, d_nt, stride, d_out_idx, d_out_dist);
+  // GFS_BF_MMA=1 selects the binary-MMA kernel.  Measured on B200 (1023 pairs x 1000 x 1000): POPC kernel
+  // 1.90 ms, b1-MMA kernel 2.73 ms -- sm_100a has no native b1 MMA, ptxas emulates it with IMMA.16832.U8
+  // sequences, so the POPC-pipe kernel stays the default.
+  static int use_mma = -1;
+  if (use_mma < 0) use_mma = getenv("GFS_BF_MMA") ? 1 : 0;
+  if (use_mma) {
+    static size_t configured2 = 0;
+    if (smem > 48 * 1024 && smem > configured2) {
+      GFS_CUDA(cudaFuncSetAttribute(k_bf_hamming_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured2 = smem;
+    }
+    k_bf_hamming_mma<<<dim3(div_up(stride, BFM_QPB), pairs), BFM_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        d_dq, d_nq, d_dt, d_nt, stride, d_out_idx, d_out_dist);
+  } else {
+    k_bf_hamming<<<dim3(div_up(stride, BF_QPB), pairs), BF_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        d_dq, d_nq, d_dt, d_nt, stride, d_out_idx, d_out_dist);
+  }
   GFS_CUDA(cudaGetLastError());
   return GFS_OK;
 }
