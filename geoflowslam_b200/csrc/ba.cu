@@ -752,37 +752,127 @@ __global__ void __launch_bounds__(128) k_schur_rhs(BaDev D) {
     for (int a = 0; a < 6; a++) D.bs[(size_t)b * D.maxDim + 15 * k + a] -= acc[a];
 }
 
-// CTA per problem: in-place right-looking LDL^T (no pivoting) on the lower triangle, then the solve.
-static const int LDLT_THREADS = 512;
+// CTA per problem: blocked right-looking LDL^T (no pivoting) of the reduced pose system, then the
+// solve.  Block column of 32: (1) one warp factors the 32x32 diagonal block in shared memory, (2) every
+// thread solves one row of the panel below it, (3) the trailing lower triangle gets its rank-32 update
+// from the panel held in shared memory (8x8 register tiles), so the matrix in L2 is read-modify-written
+// once per 32 columns.  g2o solves this system with Eigen::SimplicialLDLT (linear_solver_eigen.h:60-76).
+static const int LDLT_THREADS = 512, LDLT_NB = 32, LDLT_PITCH = 33, LDLT_MAXN = 320;
 __global__ void __launch_bounds__(LDLT_THREADS) k_ldlt_solve(BaDev D) {
-  __shared__ double s_col[320];
+  extern __shared__ double s_ld[];
+  double* Lp = s_ld;                              // [LDLT_MAXN][33] panel: unit-lower L columns of this block
+  double* Wp = Lp + LDLT_MAXN * LDLT_PITCH;       // [LDLT_MAXN][33] panel times D
+  double* dv = Wp + LDLT_MAXN * LDLT_PITCH;       // [32] pivots of this block
+  double* y = dv + 32;                            // [LDLT_MAXN] right-hand side / solution
   __shared__ int s_ok;
   const int b = blockIdx.x;
   if (!problem_on(D, b, J_NEED)) return;
   const BaCalib& C = D.calib[b];
-  const int n = C.dimP, tid = threadIdx.x;
+  const int n = C.dimP, tid = threadIdx.x, lane = tid & 31;
   double* A = D.Hs + (size_t)b * D.maxDim * D.maxDim;
   double* x = D.x + (size_t)b * (D.maxDim + 3 * D.maxPt);
   if (tid == 0) s_ok = 1;
+  for (int i = tid; i < n; i += LDLT_THREADS) y[i] = D.bs[(size_t)b * D.maxDim + i];
   __syncthreads();
-  for (int j = 0; j < n; j++) {
-    const double d = A[(size_t)j * n + j];
-    if (d == 0.0 || !isfinite(d)) { if (tid == 0) s_ok = 0; break; }  // uniform: every thread reads the same d
-    for (int i = j + 1 + tid; i < n; i += LDLT_THREADS) {
-      const double l = A[(size_t)i * n + j] / d;
-      s_col[i] = l;
+  for (int kb = 0; kb < n; kb += LDLT_NB) {
+    const int w = min(LDLT_NB, n - kb);
+    const int rows = n - kb;  // panel rows kb .. n-1, local index r = i - kb
+    for (int idx = tid; idx < rows * LDLT_NB; idx += LDLT_THREADS) {
+      const int r = idx >> 5, c = idx & 31;
+      Lp[r * LDLT_PITCH + c] = (c < w) ? A[(size_t)(kb + r) * n + kb + c] : 0.0;
     }
     __syncthreads();
-    const int m = n - j - 1;
-    // trailing update of the lower triangle: A[i][k] -= l_i * d * l_k for j < k <= i
-    for (int idx = tid; idx < m * m; idx += LDLT_THREADS) {
-      const int ii = idx / m, kk = idx - ii * m;
-      if (kk <= ii) {
-        const int i = j + 1 + ii, k = j + 1 + kk;
-        A[(size_t)i * n + k] -= s_col[i] * d * s_col[k];
+    // (1) diagonal block: lane r owns row r (r < w)
+    if (tid < 32) {
+      for (int j = 0; j < w; j++) {
+        const double d = Lp[j * LDLT_PITCH + j];
+        if (d == 0.0 || !isfinite(d)) { if (lane == 0) s_ok = 0; break; }
+        if (lane == 0) dv[j] = d;
+        if (lane > j && lane < w) {
+          const double l = Lp[lane * LDLT_PITCH + j] / d;
+          for (int c = j + 1; c <= lane; c++) Lp[lane * LDLT_PITCH + c] -= l * Lp[c * LDLT_PITCH + j];  // column j still unscaled
+        }
+        __syncwarp();
+        if (lane > j && lane < w) Lp[lane * LDLT_PITCH + j] /= d;
+        __syncwarp();
       }
     }
-    for (int i = j + 1 + tid; i < n; i += LDLT_THREADS) A[(size_t)i * n + j] = s_col[i];
+    __syncthreads();
+    if (!s_ok) break;
+    // (2) panel rows below the diagonal block: L[r][c] = (A[r][c] - sum_{j<c} L[r][j] d_j L[c][j]) / d_c
+    for (int r = w + tid; r < rows; r += LDLT_THREADS) {
+      double* row = Lp + r * LDLT_PITCH;
+      for (int c = 0; c < w; c++) {
+        double v = row[c];
+        for (int j = 0; j < c; j++) v -= row[j] * dv[j] * Lp[c * LDLT_PITCH + j];
+        row[c] = v / dv[c];
+      }
+    }
+    __syncthreads();
+    // forward substitution with this block column: unit-lower solve on the diagonal block (warp 0),
+    // then y[rows below] -= L_panel * y_block
+    if (tid < 32) {
+      for (int j = 0; j < w; j++) {
+        const double yj = y[kb + j];
+        if (lane > j && lane < w) y[kb + lane] -= Lp[lane * LDLT_PITCH + j] * yj;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    for (int r = w + tid; r < rows; r += LDLT_THREADS) {
+      double v = 0;
+      for (int j = 0; j < w; j++) v += Lp[r * LDLT_PITCH + j] * y[kb + j];
+      y[kb + r] -= v;
+    }
+    // write the factor columns back (unit diagonal implied, pivots on the diagonal) and build W = L D
+    for (int idx = tid; idx < rows * LDLT_NB; idx += LDLT_THREADS) {
+      const int r = idx >> 5, c = idx & 31;
+      if (c < w) {
+        const double l = Lp[r * LDLT_PITCH + c];
+        if (r > c) A[(size_t)(kb + r) * n + kb + c] = l;
+        else if (r == c) A[(size_t)(kb + r) * n + kb + c] = dv[c];
+        Wp[r * LDLT_PITCH + c] = (r >= w) ? l * dv[c] : 0.0;
+      } else {
+        Wp[r * LDLT_PITCH + c] = 0.0;
+      }
+    }
+    __syncthreads();
+    // (3) trailing update on the lower triangle, rows/cols local index >= w, 8x8 tiles
+    const int m = rows - w;
+    if (m > 0) {
+      const int nt = (m + 7) >> 3;
+      const int ntiles = nt * (nt + 1) / 2;
+      for (int tile = tid; tile < ntiles; tile += LDLT_THREADS) {
+        int ti = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
+        while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
+        while (ti * (ti + 1) / 2 > tile) ti--;
+        const int tk = tile - ti * (ti + 1) / 2;
+        const int r0 = w + ti * 8, k0 = w + tk * 8;
+        double acc[8][8];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+          for (int v = 0; v < 8; v++) acc[u][v] = 0.0;
+        for (int j = 0; j < w; j++) {
+          double li[8], wk[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) li[u] = (r0 + u < rows) ? Lp[(r0 + u) * LDLT_PITCH + j] : 0.0;
+#pragma unroll
+          for (int v = 0; v < 8; v++) wk[v] = (k0 + v < rows) ? Wp[(k0 + v) * LDLT_PITCH + j] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int v = 0; v < 8; v++) acc[u][v] += li[u] * wk[v];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+          for (int v = 0; v < 8; v++) {
+            const int r = r0 + u, k = k0 + v;
+            if (r < rows && k <= r) A[(size_t)(kb + r) * n + kb + k] -= acc[u][v];
+          }
+      }
+    }
     __syncthreads();
   }
   __syncthreads();
@@ -792,29 +882,40 @@ __global__ void __launch_bounds__(LDLT_THREADS) k_ldlt_solve(BaDev D) {
     for (int i = tid; i < n; i += LDLT_THREADS) x[i] = 0.0;
     return;
   }
-  // forward / diagonal / backward substitution by one warp with a shared vector
-  double* y = s_col;
-  for (int i = tid; i < n; i += LDLT_THREADS) y[i] = D.bs[(size_t)b * D.maxDim + i];
+  // diagonal scaling, then blocked backward substitution with L^T: block columns from last to first,
+  // each panel re-read (coalesced) from the factor in L2
+  for (int i = tid; i < n; i += LDLT_THREADS) y[i] /= A[(size_t)i * n + i];
   __syncthreads();
-  if (tid < 32) {
-    for (int i = 0; i < n; i++) {
-      double v = 0;
-      for (int k = tid; k < i; k += 32) v += A[(size_t)i * n + k] * y[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-      if (tid == 0) y[i] -= v;
-      __syncwarp();
+  const int nblocks = (n + LDLT_NB - 1) / LDLT_NB;
+  for (int bi = nblocks - 1; bi >= 0; bi--) {
+    const int kb = bi * LDLT_NB;
+    const int w = min(LDLT_NB, n - kb), rows = n - kb;
+    for (int idx = tid; idx < rows * LDLT_NB; idx += LDLT_THREADS) {
+      const int r = idx >> 5, c = idx & 31;
+      Lp[r * LDLT_PITCH + c] = (c < w && r > c) ? A[(size_t)(kb + r) * n + kb + c] : 0.0;
     }
-    for (int i = tid; i < n; i += 32) y[i] /= A[(size_t)i * n + i];
-    __syncwarp();
-    for (int i = n - 1; i >= 0; i--) {
-      double v = 0;
-      for (int k = i + 1 + tid; k < n; k += 32) v += A[(size_t)k * n + i] * y[k];
+    __syncthreads();
+    // x[kb + c] -= sum_{r >= w} L[r][c] * x[kb + r]: warp per column group, lanes over rows
+    {
+      const int warp = tid >> 5;
+      for (int c = warp; c < w; c += LDLT_THREADS / 32) {
+        double v = 0;
+        for (int r = w + lane; r < rows; r += 32) v += Lp[r * LDLT_PITCH + c] * y[kb + r];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-      if (tid == 0) y[i] -= v;
-      __syncwarp();
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) y[kb + c] -= v;
+      }
     }
+    __syncthreads();
+    // unit-upper (L^T) solve inside the diagonal block, last column first
+    if (tid < 32) {
+      for (int j = w - 1; j >= 0; j--) {
+        const double xj = y[kb + j];
+        if (lane < j) y[kb + lane] -= Lp[j * LDLT_PITCH + lane] * xj;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
   }
   __syncthreads();
   for (int i = tid; i < n; i += LDLT_THREADS) {
@@ -1347,6 +1448,12 @@ int gfs_ba_solve_uploaded(GfsBa* h, void* stream) {
   int* hc = (int*)h->h_counters.p;
   h->launches = 0;
   const bool part = D.world > 1;
+  const size_t ldltSmem = (size_t)(2 * LDLT_MAXN * LDLT_PITCH + 32 + LDLT_MAXN) * sizeof(double);
+  static bool ldltConfigured = false;
+  if (!ldltConfigured) {
+    GFS_CUDA(cudaFuncSetAttribute(k_ldlt_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldltSmem));
+    ldltConfigured = true;
+  }
   k_ba_init<<<div_up(B, 128), 128, 0, st>>>(D, B);
   // reset the working state from the uploaded problem (re-solvable)
   GFS_CUDA(cudaMemcpyAsync(D.kf, h->h_kf.data(), h->h_kf.size() * 8, cudaMemcpyHostToDevice, st));
@@ -1390,7 +1497,7 @@ int gfs_ba_solve_uploaded(GfsBa* h, void* stream) {
         if ((rc = ba_allreduce(h, st, D.Hs, B * D.maxDim * D.maxDim))) return rc;
         if ((rc = ba_allreduce(h, st, D.bs, B * D.maxDim))) return rc;
       }
-      k_ldlt_solve<<<B, LDLT_THREADS, 0, st>>>(D);
+      k_ldlt_solve<<<B, LDLT_THREADS, ldltSmem, st>>>(D);
       k_backsub_update<<<gUpd, 128, 0, st>>>(D);
       errors(J_NEED);
       if (part) {
