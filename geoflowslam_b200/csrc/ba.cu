@@ -38,7 +38,7 @@ struct BaCalib {
   double Rcb[9], tcb[3], Rbc[9], tbc[3];
   double fx, fy, cx, cy, bf, lambda_init;
   double deltaMono, deltaStereo;  // (float)sqrt(5.991), (float)sqrt(7.815) widened (Optimizer.cc:3427-3429)
-  int nOpt, nKf, nPt, nObs, nIn, iterations, bLarge, dimP;
+  int nOpt, nKf, nPt, nObs, nIn, nIcp, iterations, bLarge, dimP;
 };
 
 struct BaDev {
@@ -54,6 +54,9 @@ struct BaDev {
   const int *inKf1, *inKf2;                // [B][maxIn]
   const float* inPre;                      // [B][maxIn][292]
   const double *infoIn, *infoG, *infoA;    // [B][maxIn][81], [9], [9]
+  const int *icpKf1, *icpKf2;              // [B][maxIn] EdgeICP vertices (previous keyframe, keyframe)
+  const double* icpRt;                     // [B][maxIn][12] measured T_c1_c2
+  double* icpRho;                          // [B][maxIn]
   const int *ptStart, *ptEdges;            // CSR landmarks -> edges: [B][maxPt+1], [B][maxObs]
   const int *kfStart, *kfEdges;            // CSR optimizable keyframes -> edges: [B][maxKf+1], [B][maxObs]
   const int* ptKfEdge;                     // [B][maxPt][maxOpt] edge id of (landmark, optimizable keyframe) or -1
@@ -224,6 +227,108 @@ __device__ void delta_for_bias(const float* pre, const double* bg, const double*
 
 #define BA_DELTA_INERTIAL 4.0 /* sqrt(16.0), Optimizer.cc:3372 */
 
+// ---- g2o::SE3Quat restated (Thirdparty/g2o/g2o/types/se3quat.h:40-215) for EdgeICP (include/G2oTypes.h:508-572)
+struct Quat { double w, x, y, z; };
+struct SE3Q { Quat r; double t[3]; };
+__device__ Quat quat_from_R(const double* m) {  // Eigen::Quaterniond(Matrix3d)
+  Quat q;
+  double t = m[0] + m[4] + m[8];
+  if (t > 0) {
+    t = sqrt(t + 1.0);
+    q.w = 0.5 * t;
+    t = 0.5 / t;
+    q.x = (m[7] - m[5]) * t; q.y = (m[2] - m[6]) * t; q.z = (m[3] - m[1]) * t;
+  } else {
+    int i = 0;
+    if (m[4] > m[0]) i = 1;
+    if (m[8] > m[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt(m[4 * i] - m[4 * j] - m[4 * k] + 1.0);
+    double v[3];
+    v[i] = 0.5 * t;
+    t = 0.5 / t;
+    q.w = (m[3 * k + j] - m[3 * j + k]) * t;
+    v[j] = (m[3 * j + i] + m[3 * i + j]) * t;
+    v[k] = (m[3 * k + i] + m[3 * i + k]) * t;
+    q.x = v[0]; q.y = v[1]; q.z = v[2];
+  }
+  return q;
+}
+__device__ void quat_normalize_rot(Quat& q) {
+  if (q.w < 0) { q.w = -q.w; q.x = -q.x; q.y = -q.y; q.z = -q.z; }
+  const double n = sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+  q.w /= n; q.x /= n; q.y /= n; q.z /= n;
+}
+__device__ Quat quat_mul(const Quat& a, const Quat& b) {
+  return Quat{a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+              a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z, a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x};
+}
+__device__ void quat_rot(const Quat& q, const double* v, double* o) {
+  const double ux = 2 * (q.y * v[2] - q.z * v[1]), uy = 2 * (q.z * v[0] - q.x * v[2]), uz = 2 * (q.x * v[1] - q.y * v[0]);
+  o[0] = v[0] + q.w * ux + (q.y * uz - q.z * uy);
+  o[1] = v[1] + q.w * uy + (q.z * ux - q.x * uz);
+  o[2] = v[2] + q.w * uz + (q.x * uy - q.y * ux);
+}
+__device__ void quat_to_R(const Quat& q, double* R) {
+  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w, txx = tx * q.x, txy = ty * q.x, txz = tz * q.x, tyy = ty * q.y,
+               tyz = tz * q.y, tzz = tz * q.z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+__device__ SE3Q se3q_make(const double* R, const double* t) {
+  SE3Q s; s.r = quat_from_R(R); quat_normalize_rot(s.r);
+  s.t[0] = t[0]; s.t[1] = t[1]; s.t[2] = t[2];
+  return s;
+}
+__device__ SE3Q se3q_mul(const SE3Q& a, const SE3Q& b) {
+  SE3Q r = a;
+  double rt[3];
+  quat_rot(a.r, b.t, rt);
+  for (int i = 0; i < 3; i++) r.t[i] += rt[i];
+  r.r = quat_mul(a.r, b.r);
+  quat_normalize_rot(r.r);
+  return r;
+}
+__device__ SE3Q se3q_inv(const SE3Q& a) {
+  SE3Q r;
+  r.r = Quat{a.r.w, -a.r.x, -a.r.y, -a.r.z};
+  const double nt[3] = {-a.t[0], -a.t[1], -a.t[2]};
+  quat_rot(r.r, nt, r.t);
+  return r;
+}
+__device__ void se3q_log(const SE3Q& a, double* res) {
+  double R[9];
+  quat_to_R(a.r, R);
+  const double d = 0.5 * (R[0] + R[4] + R[8] - 1);
+  const double dR[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
+  double omega[3], Om[9], Om2[9], Vi[9];
+  if (d > 0.99999) {
+    for (int i = 0; i < 3; i++) omega[i] = 0.5 * dR[i];
+    skew3(omega, Om);
+    mm3(Om, Om, Om2);
+    for (int i = 0; i < 9; i++) Vi[i] = (i % 4 == 0 ? 1.0 : 0.0) - 0.5 * Om[i] + (1. / 12.) * Om2[i];
+  } else {
+    const double theta = acos(d);
+    const double k = theta / (2 * sqrt(1 - d * d));
+    for (int i = 0; i < 3; i++) omega[i] = k * dR[i];
+    skew3(omega, Om);
+    mm3(Om, Om, Om2);
+    const double c = (1 - theta / (2 * tan(theta / 2))) / (theta * theta);
+    for (int i = 0; i < 9; i++) Vi[i] = (i % 4 == 0 ? 1.0 : 0.0) - 0.5 * Om[i] + c * Om2[i];
+  }
+  double ups[3];
+  mv3(Vi, a.t, ups);
+  for (int i = 0; i < 3; i++) { res[i] = omega[i]; res[3 + i] = ups[i]; }
+}
+// EdgeICP::computeError: log(T_c1c2^-1 * T_c1w * T_c2w^-1); s1, s2 = keyframe state records
+__device__ void icp_error(const double* Rt, const double* s1, const double* s2, double* err6) {
+  const SE3Q Tm = se3q_make(Rt, Rt + 9), T1 = se3q_make(s1 + K_RCW, s1 + K_TCW), T2 = se3q_make(s2 + K_RCW, s2 + K_TCW);
+  se3q_log(se3q_mul(se3q_mul(se3q_inv(Tm), T1), se3q_inv(T2)), err6);
+}
+#define BA_DELTA_ICP ((double)(float)0.632455532033675866) /* (float)sqrt(0.4), Optimizer.cc:3258 */
+
 // visual residual: obs - Project[Stereo](Xw) (G2oTypes.cc:172-188, Pinhole.cpp:36-42)
 __device__ __forceinline__ int vis_error(const BaCalib& C, const double* kf, const double* Xw, const double* obs, double* err,
                                          double* Xc) {
@@ -236,6 +341,23 @@ __device__ __forceinline__ int vis_error(const BaCalib& C, const double* kf, con
   const double invZ = 1 / Xc[2];
   err[2] = obs[2] - (u - C.bf * invZ);
   return 3;
+}
+
+// ImuCamPose::Update (G2oTypes.cc:191-217) on a keyframe state record (pose part)
+__device__ void kf_oplus(const BaCalib& C, double* st, const double* u) {
+  double t[3], E[9];
+  mv3(st + K_RWB, u + 3, t);
+  st[K_TWB] += t[0]; st[K_TWB + 1] += t[1]; st[K_TWB + 2] += t[2];
+  exp_so3(u, E);
+  mm3(st + K_RWB, E, st + K_RWB);
+  // (NormalizeRotation(Rwb) every third update: its result is discarded in the reference, :203-207)
+  double Rbw[9], tbw[3];
+  mt3(st + K_RWB, Rbw);
+  mv3(Rbw, st + K_TWB, tbw);
+  tbw[0] = -tbw[0]; tbw[1] = -tbw[1]; tbw[2] = -tbw[2];
+  mm3(C.Rcb, Rbw, st + K_RCW);
+  mv3(C.Rcb, tbw, st + K_TCW);
+  st[K_TCW] += C.tcb[0]; st[K_TCW + 1] += C.tcb[1]; st[K_TCW + 2] += C.tcb[2];
 }
 
 // fixed-order block sum of one double per thread -> out (thread 0 writes)
@@ -316,6 +438,19 @@ __global__ void k_in_error(BaDev D, int flag) {
   if (!problem_on(D, b, flag)) return;
   const BaCalib& C = D.calib[b];
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < C.nIcp) {  // EdgeICP: information 1e2 * I, Huber sqrt(0.4) (Optimizer.cc:3258, 3306-3314)
+    double v = 0;
+    if (D.rank == 0) {
+      double r[6], rho[2];
+      icp_error(D.icpRt + ((size_t)b * D.maxIn + e) * 12, D.kf + ((size_t)b * D.maxKf + D.icpKf1[(size_t)b * D.maxIn + e]) * KF_STRIDE,
+                D.kf + ((size_t)b * D.maxKf + D.icpKf2[(size_t)b * D.maxIn + e]) * KF_STRIDE, r);
+      double c2 = 0;
+      for (int a = 0; a < 6; a++) c2 += r[a] * 1e2 * r[a];
+      huber(c2, BA_DELTA_ICP, rho);
+      v = rho[0];
+    }
+    D.icpRho[(size_t)b * D.maxIn + e] = v;
+  }
   if (e >= C.nIn) return;
   double out = 0;
   if (D.rank == 0) {  // inertial edges belong to rank 0 in partitioned mode
@@ -618,6 +753,62 @@ __global__ void __launch_bounds__(INERTIAL_THREADS) k_lin_inertial(BaDev D) {
         const double Or = Om[3 * a] * rr[0] + Om[3 * a + 1] * rr[1] + Om[3 * a + 2] * rr[2];
         if (o1 >= 0) bp[o1 + a] += Or;
         if (o2 >= 0) bp[o2 + a] += -Or;
+      }
+    }
+    __syncthreads();
+  }
+  // EdgeICP: numeric Jacobians by central differences through the vertices' oplus, delta = 1e-9
+  // (BaseBinaryEdge::linearizeOplus, base_binary_edge.hpp:124-190), then the robust quadratic form
+  double* sJ = &s_J[0][0];   // [6][12]
+  double* sR = &s_Wr[0][0];  // r[6], then w
+  for (int e = 0; e < C.nIcp; e++) {
+    const int k1 = D.icpKf1[(size_t)b * D.maxIn + e], k2 = D.icpKf2[(size_t)b * D.maxIn + e];
+    const double* Rt = D.icpRt + ((size_t)b * D.maxIn + e) * 12;
+    const double* s1 = D.kf + ((size_t)b * D.maxKf + k1) * KF_STRIDE;
+    const double* s2 = D.kf + ((size_t)b * D.maxKf + k2) * KF_STRIDE;
+    if (threadIdx.x < 12) {
+      const int v = threadIdx.x / 6, d = threadIdx.x % 6;
+      const int k = v == 0 ? k1 : k2;
+      double col[6] = {0, 0, 0, 0, 0, 0};
+      if (k < C.nOpt) {
+        const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+        double sp[KF_STRIDE], sm[KF_STRIDE], add[6] = {0, 0, 0, 0, 0, 0}, ep[6], em[6];
+        const double* sv = v == 0 ? s1 : s2;
+        for (int q = 0; q < KF_STRIDE; q++) { sp[q] = sv[q]; sm[q] = sv[q]; }
+        add[d] = delta; kf_oplus(C, sp, add);
+        add[d] = -delta; kf_oplus(C, sm, add);
+        icp_error(Rt, v == 0 ? sp : s1, v == 0 ? s2 : sp, ep);
+        icp_error(Rt, v == 0 ? sm : s1, v == 0 ? s2 : sm, em);
+        for (int a = 0; a < 6; a++) col[a] = scalar * (ep[a] - em[a]);
+      }
+      for (int a = 0; a < 6; a++) sJ[a * 12 + threadIdx.x] = col[a];
+    } else if (threadIdx.x == 32) {
+      double r[6], rho[2];
+      icp_error(Rt, s1, s2, r);
+      double c2 = 0;
+      for (int a = 0; a < 6; a++) c2 += r[a] * 1e2 * r[a];
+      huber(c2, BA_DELTA_ICP, rho);
+      for (int a = 0; a < 6; a++) sR[a] = r[a];
+      sR[6] = rho[1] * 1e2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 156) {
+      const double w = sR[6];
+      const int c1 = threadIdx.x < 144 ? threadIdx.x / 12 : threadIdx.x - 144, c2 = threadIdx.x < 144 ? threadIdx.x % 12 : -1;
+      const int g1 = c1 < 6 ? (k1 < C.nOpt ? 15 * k1 + c1 : -1) : (k2 < C.nOpt ? 15 * k2 + c1 - 6 : -1);
+      if (g1 >= 0) {
+        if (c2 < 0) {
+          double t = 0;
+          for (int a = 0; a < 6; a++) t += sJ[a * 12 + c1] * (-w * sR[a]);
+          bp[g1] += t;
+        } else {
+          const int g2 = c2 < 6 ? (k1 < C.nOpt ? 15 * k1 + c2 : -1) : (k2 < C.nOpt ? 15 * k2 + c2 - 6 : -1);
+          if (g2 >= 0) {
+            double hh = 0;
+            for (int a = 0; a < 6; a++) hh += sJ[a * 12 + c1] * w * sJ[a * 12 + c2];
+            H[(size_t)g1 * n + g2] += hh;
+          }
+        }
       }
     }
     __syncthreads();
@@ -965,18 +1156,7 @@ __global__ void __launch_bounds__(128) k_backsub_update(BaDev D) {
     double st[KF_STRIDE];
     for (int q = 0; q < KF_STRIDE; q++) st[q] = sb[q];
     if (ok) {
-      double t[3], E[9];
-      mv3(st + K_RWB, u + 3, t);
-      st[K_TWB] += t[0]; st[K_TWB + 1] += t[1]; st[K_TWB + 2] += t[2];
-      exp_so3(u, E);
-      mm3(st + K_RWB, E, st + K_RWB);
-      double Rbw[9], tbw[3];
-      mt3(st + K_RWB, Rbw);
-      mv3(Rbw, st + K_TWB, tbw);
-      tbw[0] = -tbw[0]; tbw[1] = -tbw[1]; tbw[2] = -tbw[2];
-      mm3(C.Rcb, Rbw, st + K_RCW);
-      mv3(C.Rcb, tbw, st + K_TCW);
-      st[K_TCW] += C.tcb[0]; st[K_TCW + 1] += C.tcb[1]; st[K_TCW + 2] += C.tcb[2];
+      kf_oplus(C, st, u);
       if (D.kfImu[(size_t)b * D.maxKf + k])
         for (int a = 0; a < 3; a++) { st[K_VEL + a] += u[6 + a]; st[K_BG + a] += u[9 + a]; st[K_BA + a] += u[12 + a]; }
       if (D.rank == 0) {  // computeScale over the pose part, counted once
@@ -1012,6 +1192,7 @@ __global__ void k_restore(BaDev D) {  // pop() for the problems whose last trial
 __device__ double total_chi(const BaDev& D, int b, const BaCalib& C) {
   double s = 0;
   for (int e = 0; e < C.nIn; e++) s += D.inRho[(size_t)b * D.maxIn + e];
+  for (int e = 0; e < C.nIcp; e++) s += D.icpRho[(size_t)b * D.maxIn + e];
   const int nb = (C.nObs + ERR_THREADS - 1) / ERR_THREADS;
   for (int i = 0; i < nb; i++) s += D.partChi[(size_t)b * D.nblk + i];
   return s;
@@ -1235,7 +1416,8 @@ struct GfsBa {
   // host staging of the flattened batch
   std::vector<double> h_kf, h_pt, h_uvr, h_infoIn, h_infoG, h_infoA;
   std::vector<uint8_t> h_kfImu, h_ptClose;
-  std::vector<int> h_obsKf, h_obsPt, h_inKf1, h_inKf2, h_ptStart, h_ptEdges, h_kfStart, h_kfEdges, h_ptKfEdge;
+  std::vector<int> h_obsKf, h_obsPt, h_inKf1, h_inKf2, h_ptStart, h_ptEdges, h_kfStart, h_kfEdges, h_ptKfEdge, h_icpKf1, h_icpKf2;
+  std::vector<double> h_icpRt;
   std::vector<float> h_obsW, h_inPre;
   PinnedBuf h_counters;
   int launches = 0;
@@ -1285,6 +1467,7 @@ int gfs_ba_create(int max_kf, int max_points, int max_obs, int max_inertial, int
   AL(obsKf, int, B * D.maxObs) AL(obsPt, int, B * D.maxObs) AL(obsUvr, double, B * D.maxObs * 3) AL(obsW, float, B * D.maxObs)
   AL(inKf1, int, B * D.maxIn) AL(inKf2, int, B * D.maxIn) AL(inPre, float, B * D.maxIn * GFS_BA_PRE_STRIDE)
   AL(infoIn, double, B * D.maxIn * 81) AL(infoG, double, B * D.maxIn * 9) AL(infoA, double, B * D.maxIn * 9)
+  AL(icpKf1, int, B * D.maxIn) AL(icpKf2, int, B * D.maxIn) AL(icpRt, double, B * D.maxIn * 12) AL(icpRho, double, B * D.maxIn)
   AL(ptStart, int, B * (D.maxPt + 1)) AL(ptEdges, int, B * D.maxObs)
   AL(kfStart, int, B * (D.maxKf + 1)) AL(kfEdges, int, B * D.maxObs)
   AL(ptKfEdge, int, B * D.maxPt * D.maxOpt)
@@ -1344,6 +1527,7 @@ int gfs_ba_upload(GfsBa* h, void* stream, const GfsBaProblem* problems, int batc
   h->h_obsW.assign(B * D.maxObs, 0.f);
   h->h_inKf1.assign(B * D.maxIn, 0); h->h_inKf2.assign(B * D.maxIn, 0); h->h_inPre.assign(B * D.maxIn * GFS_BA_PRE_STRIDE, 0.f);
   h->h_infoIn.assign(B * D.maxIn * 81, 0.0); h->h_infoG.assign(B * D.maxIn * 9, 0.0); h->h_infoA.assign(B * D.maxIn * 9, 0.0);
+  h->h_icpKf1.assign(B * D.maxIn, 0); h->h_icpKf2.assign(B * D.maxIn, 0); h->h_icpRt.assign(B * D.maxIn * 12, 0.0);
   h->h_ptStart.assign(B * (D.maxPt + 1), 0); h->h_ptEdges.assign(B * D.maxObs, 0);
   h->h_kfStart.assign(B * (D.maxKf + 1), 0); h->h_kfEdges.assign(B * D.maxObs, 0);
   h->h_ptKfEdge.assign(B * D.maxPt * D.maxOpt, -1);
@@ -1359,7 +1543,13 @@ int gfs_ba_upload(GfsBa* h, void* stream, const GfsBaProblem* problems, int batc
     C.fx = P.fx; C.fy = P.fy; C.cx = P.cx; C.cy = P.cy; C.bf = P.bf; C.lambda_init = P.lambda_init;
     C.deltaMono = (double)(float)std::sqrt(5.991);
     C.deltaStereo = (double)(float)std::sqrt(7.815);
-    C.nOpt = P.n_opt_kf; C.nKf = nKf; C.nPt = P.n_points; C.nObs = P.n_obs; C.nIn = P.n_inertial;
+    C.nOpt = P.n_opt_kf; C.nKf = nKf; C.nPt = P.n_points; C.nObs = P.n_obs; C.nIn = P.n_inertial; C.nIcp = P.n_icp;
+    GFS_REQUIRE(P.n_icp >= 0 && P.n_icp <= D.maxIn, GFS_ERR_CAPACITY, "too many ICP edges");
+    for (int e = 0; e < P.n_icp; e++) {
+      GFS_REQUIRE(P.icp_kf1[e] >= 0 && P.icp_kf1[e] < nKf && P.icp_kf2[e] >= 0 && P.icp_kf2[e] < nKf, GFS_ERR_INVALID, "ICP edge index out of range");
+      h->h_icpKf1[b * D.maxIn + e] = P.icp_kf1[e]; h->h_icpKf2[b * D.maxIn + e] = P.icp_kf2[e];
+      memcpy(&h->h_icpRt[(b * D.maxIn + e) * 12], P.icp_Rt + 12 * (size_t)e, 96);
+    }
     C.iterations = P.iterations; C.bLarge = P.b_large; C.dimP = 15 * P.n_opt_kf;
     for (int k = 0; k < nKf; k++) {
       double* s = &h->h_kf[(b * D.maxKf + k) * KF_STRIDE];
@@ -1419,6 +1609,7 @@ int gfs_ba_upload(GfsBa* h, void* stream, const GfsBaProblem* problems, int batc
   GFS_CUDA(cudaMemcpyAsync(D.calib, h->calib.data(), B * sizeof(BaCalib), cudaMemcpyHostToDevice, st));
   UP(kf, h_kf); UP(pt, h_pt); UP(kfImu, h_kfImu); UP(ptClose, h_ptClose);
   UP(obsKf, h_obsKf); UP(obsPt, h_obsPt); UP(obsUvr, h_uvr); UP(obsW, h_obsW);
+  UP(icpKf1, h_icpKf1); UP(icpKf2, h_icpKf2); UP(icpRt, h_icpRt);
   UP(inKf1, h_inKf1); UP(inKf2, h_inKf2); UP(inPre, h_inPre); UP(infoIn, h_infoIn); UP(infoG, h_infoG); UP(infoA, h_infoA);
   UP(ptStart, h_ptStart); UP(ptEdges, h_ptEdges); UP(kfStart, h_kfStart); UP(kfEdges, h_kfEdges); UP(ptKfEdge, h_ptKfEdge);
 #undef UP
@@ -1467,6 +1658,7 @@ int gfs_ba_solve_uploaded(GfsBa* h, void* stream) {
     if (!part) return GFS_OK;
     int rc = ba_allreduce(h, st, D.partChi, B * D.nblk);
     if (rc) return rc;
+    if ((rc = ba_allreduce(h, st, D.icpRho, B * D.maxIn))) return rc;
     return ba_allreduce(h, st, D.inRho, B * D.maxIn);
   };
   int rc;

@@ -216,7 +216,7 @@ def preintegrate(acc, gyr, dt, bias, noise=IMU_NOISE):
 
 
 def ba_problem(seed=3000, n_kf=20, n_points=3000, obs_per_point=5, kf_dt=0.5, imu_rate=200, b_large=True,
-               rot_noise_deg=1.0, trans_noise=0.02, point_noise=0.02, outlier_frac=0.01):
+               rot_noise_deg=1.0, trans_noise=0.02, point_noise=0.02, outlier_frac=0.01, n_icp=0):
     """Synthetic LocalInertialBA problem as plain arrays (the flattened export of the reference's
     KeyFrame / MapPoint graph, see include/gfs_b200.h GfsBaProblem).  Keyframe 0 is the newest
     (vpOptimizableKFs order, Optimizer.cc:3078-3086); the fixed predecessor is index n_kf."""
@@ -323,7 +323,20 @@ def ba_problem(seed=3000, n_kf=20, n_points=3000, obs_per_point=5, kf_dt=0.5, im
         kf_vel[i] = f64(vel_t[c] + (0 if fixed else rng.uniform(-0.02, 0.02, 3)))
         kf_bg[i] = f64(bias_est[3:]); kf_ba[i] = f64(bias_est[:3])
     pt_xyz = f64(pts + rng.normal(0, point_noise, pts.shape))
-    return dict(
+    # optional EdgeICP factors between consecutive keyframes (vertex 0 = previous KF, vertex 1 = KF):
+    # T_c1_c2 = T_c1w * T_c2w^-1 from the true poses plus GICP-sized noise
+    icp_kf1, icp_kf2, icp_Rt = [], [], []
+    for i in range(min(n_icp, n_kf)):
+        c2, c1 = order[i], order[i + 1]
+        def Tcw(c):
+            R = Rcb @ Rwb_t[c].T
+            return R, R @ (-twb_t[c]) + tcb
+        R1, t1 = Tcw(c1); R2, t2 = Tcw(c2)
+        R12 = R1 @ R2.T @ _rot(rng.normal(0, 5e-4, 3)); t12 = t1 - R1 @ R2.T @ t2 + rng.normal(0, 2e-3, 3)
+        icp_kf1.append(i + 1); icp_kf2.append(i); icp_Rt.append(np.concatenate([R12.ravel(), t12]))
+    icp = dict(n_icp=len(icp_kf1), icp_kf1=np.array(icp_kf1, np.int32), icp_kf2=np.array(icp_kf2, np.int32),
+               icp_Rt=np.array(icp_Rt, np.float64).reshape(-1, 12))
+    return dict(icp, 
         n_opt_kf=n_kf, n_fixed_kf=1, n_points=n_points, n_obs=len(obs_kf), n_inertial=n_kf,
         iterations=4 if b_large else 8, b_large=int(b_large), lambda_init=1e-2 if b_large else 1.0,
         Rcb=f64(Rcb).ravel(), tcb=f64(tcb), Rbc=f64(Rbc).ravel(), tbc=f64(tbc),

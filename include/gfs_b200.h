@@ -268,6 +268,12 @@ typedef struct GfsBaProblem {
   const int *in_kf1, *in_kf2;  /* keyframe indices of (prev, cur) */
   const float* in_pre;         /* [n_inertial][GFS_BA_PRE_STRIDE] */
   const uint8_t* in_downweight; /* 1 -> information * 1e-2 (i == N-1, :3371) */
+  /* optional EdgeICP factors (pbICPFlag, :3260-3321): vertex 0 = previous keyframe, vertex 1 = keyframe,
+   * measurement T_c1_c2 = GICP result (row-major R then t, 12 doubles); information 1e2 * I, Huber
+   * sqrt(0.4); Jacobians by g2o's central differences (delta 1e-9, base_binary_edge.hpp:124-190). */
+  int n_icp;
+  const int *icp_kf1, *icp_kf2;
+  const double* icp_Rt; /* [n_icp][12] */
 } GfsBaProblem;
 
 typedef struct GfsBaResult {

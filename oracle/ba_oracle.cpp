@@ -271,7 +271,7 @@ struct Problem {
   int nOpt, nKf, nPt, nObs, nIn, dimP;
   std::vector<double> infoIn;  // [nIn][81]
   std::vector<double> infoG, infoA;  // [nIn][9]
-  double deltaMono, deltaStereo, deltaIn;
+  double deltaMono, deltaStereo, deltaIn, deltaIcp;
 };
 
 // ImuCamPose::Update (G2oTypes.cc:191-217)
@@ -401,6 +401,107 @@ static void inertial_jacobian(const Problem& pr, const State& s, int e, double* 
   put(3, 21, Rbw1, 1.0);
 }
 
+// ---- g2o::SE3Quat restated (Thirdparty/g2o/g2o/types/se3quat.h:40-215, se3_ops.hpp) for EdgeICP
+struct Quat { double w, x, y, z; };
+struct SE3Q { Quat r; double t[3]; };
+static Quat quat_from_R(const double* m) {  // Eigen::Quaterniond(Matrix3d)
+  Quat q;
+  double t = m[0] + m[4] + m[8];
+  if (t > 0) {
+    t = std::sqrt(t + 1.0);
+    q.w = 0.5 * t;
+    t = 0.5 / t;
+    q.x = (m[7] - m[5]) * t; q.y = (m[2] - m[6]) * t; q.z = (m[3] - m[1]) * t;
+  } else {
+    int i = 0;
+    if (m[4] > m[0]) i = 1;
+    if (m[8] > m[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(m[4 * i] - m[4 * j] - m[4 * k] + 1.0);
+    double v[3];
+    v[i] = 0.5 * t;
+    t = 0.5 / t;
+    q.w = (m[3 * k + j] - m[3 * j + k]) * t;
+    v[j] = (m[3 * j + i] + m[3 * i + j]) * t;
+    v[k] = (m[3 * k + i] + m[3 * i + k]) * t;
+    q.x = v[0]; q.y = v[1]; q.z = v[2];
+  }
+  return q;
+}
+static void quat_normalize_rot(Quat& q) {  // SE3Quat::normalizeRotation
+  if (q.w < 0) { q.w = -q.w; q.x = -q.x; q.y = -q.y; q.z = -q.z; }
+  const double n = std::sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+  q.w /= n; q.x /= n; q.y /= n; q.z /= n;
+}
+static Quat quat_mul(const Quat& a, const Quat& b) {
+  return Quat{a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+              a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z, a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x};
+}
+static void quat_rot(const Quat& q, const double* v, double* o) {  // Eigen _transformVector
+  const double ux = 2 * (q.y * v[2] - q.z * v[1]), uy = 2 * (q.z * v[0] - q.x * v[2]), uz = 2 * (q.x * v[1] - q.y * v[0]);
+  o[0] = v[0] + q.w * ux + (q.y * uz - q.z * uy);
+  o[1] = v[1] + q.w * uy + (q.z * ux - q.x * uz);
+  o[2] = v[2] + q.w * uz + (q.x * uy - q.y * ux);
+}
+static void quat_to_R(const Quat& q, double* R) {
+  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w, txx = tx * q.x, txy = ty * q.x, txz = tz * q.x, tyy = ty * q.y,
+               tyz = tz * q.y, tzz = tz * q.z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+static SE3Q se3q_make(const double* R, const double* t) {
+  SE3Q s; s.r = quat_from_R(R); quat_normalize_rot(s.r);
+  s.t[0] = t[0]; s.t[1] = t[1]; s.t[2] = t[2];
+  return s;
+}
+static SE3Q se3q_mul(const SE3Q& a, const SE3Q& b) {
+  SE3Q r = a;
+  double rt[3];
+  quat_rot(a.r, b.t, rt);
+  for (int i = 0; i < 3; i++) r.t[i] += rt[i];
+  r.r = quat_mul(a.r, b.r);
+  quat_normalize_rot(r.r);
+  return r;
+}
+static SE3Q se3q_inv(const SE3Q& a) {
+  SE3Q r;
+  r.r = Quat{a.r.w, -a.r.x, -a.r.y, -a.r.z};
+  const double nt[3] = {-a.t[0], -a.t[1], -a.t[2]};
+  quat_rot(r.r, nt, r.t);
+  return r;
+}
+static void se3q_log(const SE3Q& a, double* res) {
+  double R[9];
+  quat_to_R(a.r, R);
+  const double d = 0.5 * (R[0] + R[4] + R[8] - 1);
+  const double dR[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
+  double omega[3], Om[9], Om2[9], Vi[9];
+  if (d > 0.99999) {
+    for (int i = 0; i < 3; i++) omega[i] = 0.5 * dR[i];
+    skew(omega, Om);
+    mm3(Om, Om, Om2);
+    for (int i = 0; i < 9; i++) Vi[i] = (i % 4 == 0 ? 1.0 : 0.0) - 0.5 * Om[i] + (1. / 12.) * Om2[i];
+  } else {
+    const double theta = std::acos(d);
+    const double k = theta / (2 * std::sqrt(1 - d * d));
+    for (int i = 0; i < 3; i++) omega[i] = k * dR[i];
+    skew(omega, Om);
+    mm3(Om, Om, Om2);
+    const double c = (1 - theta / (2 * std::tan(theta / 2))) / (theta * theta);
+    for (int i = 0; i < 9; i++) Vi[i] = (i % 4 == 0 ? 1.0 : 0.0) - 0.5 * Om[i] + c * Om2[i];
+  }
+  double ups[3];
+  mv3(Vi, a.t, ups);
+  for (int i = 0; i < 3; i++) { res[i] = omega[i]; res[3 + i] = ups[i]; }
+}
+// EdgeICP::computeError (include/G2oTypes.h:524-540): log(T_c1c2^-1 * T_c1w * T_c2w^-1)
+static void icp_error_kf(const double* Rt, const KF& k1, const KF& k2, double* err6) {
+  const SE3Q Tm = se3q_make(Rt, Rt + 9), T1 = se3q_make(k1.Rcw, k1.tcw), T2 = se3q_make(k2.Rcw, k2.tcw);
+  se3q_log(se3q_mul(se3q_mul(se3q_inv(Tm), T1), se3q_inv(T2)), err6);
+}
+
 // pose-side layout: keyframe k (< nOpt) owns dofs [15k, 15k+15): pose 6, vel 3, bg 3, ba 3
 struct System {
   int dimP, nPt;
@@ -431,6 +532,14 @@ static double robust_chi2(const Problem& pr, const State& s, std::vector<double>
     for (int a = 0; a < 3; a++)
       for (int b = 0; b < 3; b++) { cg += rg[a] * G[3 * a + b] * rg[b]; ca += ra[a] * A[3 * a + b] * ra[b]; }
     chi += cg + ca;
+  }
+  for (int e = 0; e < P.n_icp; e++) {  // EdgeICP: information 1e2 * I, Huber sqrt(0.4) (Optimizer.cc:3258, 3306-3314)
+    double r[6];
+    icp_error_kf(P.icp_Rt + 12 * (size_t)e, s.kf[P.icp_kf1[e]], s.kf[P.icp_kf2[e]], r);
+    double c2 = 0;
+    for (int a = 0; a < 6; a++) c2 += r[a] * 1e2 * r[a];
+    huber(c2, pr.deltaIcp, rho);
+    chi += rho[0];
   }
   for (int e = 0; e < pr.nObs; e++) {
     double r[3];
@@ -512,6 +621,45 @@ static void build_system(const Problem& pr, const State& s, System& S) {
             S.Hpp[(size_t)(o2 + a) * dimP + o1 + b] += -Om[3 * b + a];
           }
         }
+      }
+    }
+  }
+  // EdgeICP: numeric Jacobians (BaseBinaryEdge::linearizeOplus, base_binary_edge.hpp:124-190) + quadratic form
+  for (int e = 0; e < P.n_icp; e++) {
+    const int k1 = P.icp_kf1[e], k2 = P.icp_kf2[e];
+    const double* Rt = P.icp_Rt + 12 * (size_t)e;
+    double r[6], J[6 * 12] = {0};
+    icp_error_kf(Rt, s.kf[k1], s.kf[k2], r);
+    const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+    for (int v = 0; v < 2; v++) {
+      const int k = v == 0 ? k1 : k2;
+      if (k >= pr.nOpt) continue;  // fixed vertex
+      for (int d = 0; d < 6; d++) {
+        double add[6] = {0, 0, 0, 0, 0, 0}, ep[6], em[6];
+        KF kp = s.kf[k], km = s.kf[k];
+        add[d] = delta; kf_update(P, kp, add);
+        add[d] = -delta; kf_update(P, km, add);
+        icp_error_kf(Rt, v == 0 ? kp : s.kf[k1], v == 0 ? s.kf[k2] : kp, ep);
+        icp_error_kf(Rt, v == 0 ? km : s.kf[k1], v == 0 ? s.kf[k2] : km, em);
+        for (int a = 0; a < 6; a++) J[a * 12 + 6 * v + d] = scalar * (ep[a] - em[a]);
+      }
+    }
+    double c2 = 0;
+    for (int a = 0; a < 6; a++) c2 += r[a] * 1e2 * r[a];
+    huber(c2, pr.deltaIcp, rho);
+    const double w = rho[1] * 1e2;
+    int col[12];
+    for (int c = 0; c < 6; c++) { col[c] = k1 < pr.nOpt ? 15 * k1 + c : -1; col[6 + c] = k2 < pr.nOpt ? 15 * k2 + c : -1; }
+    for (int c1 = 0; c1 < 12; c1++) {
+      if (col[c1] < 0) continue;
+      double t = 0;
+      for (int a = 0; a < 6; a++) t += J[a * 12 + c1] * (-w * r[a]);
+      S.bp[col[c1]] += t;
+      for (int c2i = 0; c2i < 12; c2i++) {
+        if (col[c2i] < 0) continue;
+        double h = 0;
+        for (int a = 0; a < 6; a++) h += J[a * 12 + c1] * w * J[a * 12 + c2i];
+        S.Hpp[(size_t)col[c1] * dimP + col[c2i]] += h;
       }
     }
   }
@@ -676,6 +824,7 @@ static void setup(const GfsBaProblem* P, Problem& pr, State& s) {
   pr.deltaMono = (double)(float)std::sqrt(5.991);    // const float thHuberMono = sqrt(5.991), Optimizer.cc:3427
   pr.deltaStereo = (double)(float)std::sqrt(7.815);  // :3429
   pr.deltaIn = std::sqrt(16.0);                      // :3372
+  pr.deltaIcp = (double)(float)std::sqrt(0.4);       // const float thHuberICP = sqrt(0.4), :3258
   pr.infoIn.resize((size_t)pr.nIn * 81); pr.infoG.resize((size_t)pr.nIn * 9); pr.infoA.resize((size_t)pr.nIn * 9);
   for (int e = 0; e < pr.nIn; e++) {
     const float* C = P->in_pre + (size_t)e * GFS_BA_PRE_STRIDE + 60;
@@ -846,6 +995,13 @@ double gfo_ba_chi2_at(const GfsBaProblem* P, const double* x, int robust) {
   gfo::ba::apply_update(pr, s, xv);
   if (!robust) { pr.deltaMono = pr.deltaStereo = pr.deltaIn = 1e300; }
   return gfo::ba::robust_chi2(pr, s, nullptr);
+}
+// SE3Quat(R, t).log() and EdgeICP error for two camera poses (validation hooks)
+void gfo_se3quat_log(const double* R, const double* t, double* out6) { gfo::ba::se3q_log(gfo::ba::se3q_make(R, t), out6); }
+void gfo_icp_error(const double* Rt12, const double* Rc1w, const double* tc1w, const double* Rc2w, const double* tc2w, double* out6) {
+  gfo::ba::KF a, b;
+  memcpy(a.Rcw, Rc1w, 72); memcpy(a.tcw, tc1w, 24); memcpy(b.Rcw, Rc2w, 72); memcpy(b.tcw, tc2w, 24);
+  gfo::ba::icp_error_kf(Rt12, a, b, out6);
 }
 void gfo_so3(const double* w, double* R_exp, double* log_of_exp, double* Jr, double* Jrinv) {
   gfo::ba::exp_so3(w, R_exp);

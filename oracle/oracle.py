@@ -273,7 +273,7 @@ class BaProblem(C.Structure):  # mirrors GfsBaProblem (include/gfs_b200.h)
                 ("kf_Rwb", dp), ("kf_twb", dp), ("kf_Rcw", dp), ("kf_tcw", dp), ("kf_vel", dp), ("kf_bg", dp),
                 ("kf_ba", dp), ("kf_has_imu", bp_), ("pt_xyz", dp), ("pt_close", bp_), ("obs_kf", ip), ("obs_pt", ip),
                 ("obs_uvr", dp), ("obs_inv_sigma2", fp), ("in_kf1", ip), ("in_kf2", ip), ("in_pre", fp),
-                ("in_downweight", bp_)]
+                ("in_downweight", bp_), ("n_icp", C.c_int), ("icp_kf1", ip), ("icp_kf2", ip), ("icp_Rt", dp)]
 
 
 class BaResult(C.Structure):  # mirrors GfsBaResult
@@ -288,6 +288,7 @@ _BA_ARRAYS = [("kf_Rwb", np.float64), ("kf_twb", np.float64), ("kf_Rcw", np.floa
               ("pt_xyz", np.float64), ("pt_close", np.uint8), ("obs_kf", np.int32), ("obs_pt", np.int32),
               ("obs_uvr", np.float64), ("obs_inv_sigma2", np.float32), ("in_kf1", np.int32), ("in_kf2", np.int32),
               ("in_pre", np.float32), ("in_downweight", np.uint8)]
+_BA_OPTIONAL = [("icp_kf1", np.int32), ("icp_kf2", np.int32), ("icp_Rt", np.float64)]
 
 
 def ba_pack(prob, struct_cls=BaProblem):
@@ -302,6 +303,11 @@ def ba_pack(prob, struct_cls=BaProblem):
     for k in ("fx", "fy", "cx", "cy"):
         setattr(P, k, float(prob[k]))
     P.bf = float(prob["bf"])
+    P.n_icp = int(prob.get("n_icp", 0))
+    for k, dt in _BA_OPTIONAL:
+        a = np.ascontiguousarray(prob.get(k, np.zeros(0)), dt)
+        keep.append(a)
+        setattr(P, k, a.ctypes.data_as(dict(type(P)._fields_)[k]))
     for k, dt in _BA_ARRAYS:
         a = np.ascontiguousarray(prob[k], dt)
         keep.append(a)

@@ -98,3 +98,18 @@ def test_many_fixed_keyframes():
     from geoflowslam_b200 import GfsError
     with pytest.raises(GfsError):
         opt.LocalInertialBA(p)                              # 24 optimizable keyframes: beyond the 21 supported
+
+
+def test_icp_edges_numeric_jacobian():
+    """EdgeICP factors (pbICPFlag, Optimizer.cc:3260-3321): g2o's central-difference Jacobians
+    (delta 1e-9) amplify rounding noise to ~1e-7, still far inside the 1e-4 pose tolerance."""
+    from geoflowslam_b200 import Optimizer
+    from oracle import oracle as O
+    p = synth.ba_problem(seed=3041, n_kf=10, n_points=400, b_large=False, n_icp=6)
+    opt = Optimizer(max_kf=21, max_points=400, max_obs=4096, max_inertial=20, max_batch=1)
+    g = opt.LocalInertialBA(p)
+    o = O.ba_solve(p)
+    _check(g, o, p, tol=1e-5)
+    q = dict(p); q["n_icp"] = 0
+    g0 = opt.LocalInertialBA(q)
+    assert np.abs(g0["kf_twb"] - g["kf_twb"]).max() > 1e-6      # the ICP factors do change the solution

@@ -152,3 +152,42 @@ def test_small_mode_eight_iterations_and_failure_guard():
     q = dict(p); q["n_obs"] = 0; q["n_inertial"] = 0
     r0 = O.ba_solve(q)
     assert r0["err"] == 0 and np.array_equal(r0["kf_twb"], p["kf_twb"])
+
+
+def test_se3quat_log_and_icp_edge():
+    """g2o::SE3Quat::log restated (se3quat.h:177-212) against scipy logm; EdgeICP error vanishes at the
+    measured relative pose and its numeric-Jacobian normal equations are the gradient of the cost."""
+    import ctypes as C
+    from scipy.linalg import logm
+    from scipy.spatial.transform import Rotation
+    L = O.lib()
+    L.gfo_se3quat_log.argtypes = [C.c_void_p] * 3
+    L.gfo_icp_error.argtypes = [C.c_void_p] * 6
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        R = Rotation.from_rotvec(rng.normal(0, 0.8, 3)).as_matrix(); t = rng.normal(0, 1, 3)
+        out = np.zeros(6)
+        L.gfo_se3quat_log(O._p(np.ascontiguousarray(R)), O._p(t), O._p(out))
+        T = np.eye(4); T[:3, :3] = R; T[:3, 3] = t
+        X = np.real(logm(T))
+        assert np.allclose(out[:3], [X[2, 1], X[0, 2], X[1, 0]], atol=1e-9)
+        assert np.allclose(out[3:], X[:3, 3], atol=1e-9)
+    p = synth.ba_problem(seed=3040, n_kf=6, n_points=150, outlier_frac=0.0, rot_noise_deg=0.05, trans_noise=0.002,
+                         point_noise=0.002, n_icp=4)
+    assert p["n_icp"] == 4
+    # normal equations with ICP edges = gradient of the robust cost (finite differences through chi2_at)
+    Hpp, bp, Hll, bl, Hpl = O.ba_system(p)
+    n, m = len(bp), p["n_points"]
+    b = np.concatenate([bp, bl.ravel()])
+    q = dict(p); q["n_icp"] = 0
+    b0 = np.concatenate([O.ba_system(q)[1], O.ba_system(q)[3].ravel()])
+    assert np.abs(b - b0)[:n].max() > 1e-3            # the ICP edges do contribute
+    for trial in range(3):
+        x = rng.normal(0, 1, n + 3 * m); x[n:] = 0
+        x[9::15][:p["n_opt_kf"]] *= 1e-2; x[10::15][:p["n_opt_kf"]] *= 1e-2
+        x /= np.linalg.norm(x)
+        h = 1e-5
+        g_fd = (O.ba_chi2_at(p, h * x) - O.ba_chi2_at(p, -h * x)) / (2 * h)
+        assert np.isclose(g_fd, -2 * b @ x, rtol=5e-3, atol=1e-3 * np.abs(b).max()), trial
+    r = O.ba_solve(p)
+    assert not r["failed"] and r["err_end"] < r["err"]
