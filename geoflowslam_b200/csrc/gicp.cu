@@ -48,6 +48,8 @@ struct GicpDev {
   int* nCells;               // [clouds] occupied grid cells
   int* cellBox;              // [clouds][6] min/max cell coordinate of the grid
   double* pts;               // [clouds][nmax][4]
+  uint4* tab;                // [clouds][hsize] kNN grid slot {key lo, key hi, start, count}: one 16-byte probe
+  double* rec;               // [clouds][nmax][4] downsampled points in cell order {x, y, z, index bits}
   double* cov;               // [clouds][nmax][6]
   // per pair
   int* corr;                 // [pairs][nmax] target index of source point (-1: none)
@@ -182,30 +184,47 @@ __global__ void __launch_bounds__(1024) k_group_rank(GicpDev D, int mode, int* _
   if (tid == 0) nGroups[c] = s_ca;
 }
 
-// One warp per cloud walks the points in input order and appends each to its group's member list;
-// lanes of one step that hit the same group are ordered by lane (= input order) via match_any.
-__global__ void __launch_bounds__(128) k_group_fill(GicpDev D, int mode, int clouds) {
-  const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (c >= clouds) return;
+// Append every point to its group's member list.  The order inside a group is whatever the atomics give:
+// the voxel mean sorts its (short) list back into input order, the k-NN grid does not depend on it.
+__global__ void __launch_bounds__(256) k_group_fill(GicpDev D, int mode) {
+  const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = mode == 0 ? D.nIn[c] : D.nDown[c];
-  const int* slotOf = D.slotOf + (size_t)c * D.nmax;
-  int* members = D.members + (size_t)c * D.nmax;
+  if (i >= n) return;
+  const int slot = D.slotOf[(size_t)c * D.nmax + i];
+  if (slot < 0) return;
   const size_t hb = (size_t)c * D.hsize;
-  for (int base = 0; base < n; base += 32) {
-    const int i = base + lane;
-    const int slot = (i < n) ? slotOf[i] : -1;
-    const unsigned grp = __match_any_sync(0xffffffffu, slot);
-    if (slot >= 0) {
-      const int leader = __ffs(grp) - 1;
-      const int r = __popc(grp & ((1u << lane) - 1u));
-      int cur = 0;
-      if (lane == leader) cur = D.cursor[hb + slot];
-      cur = __shfl_sync(grp, cur, leader);
-      members[D.start[hb + slot] + cur + r] = i;
-      if (lane == leader) D.cursor[hb + slot] = cur + __popc(grp);
+  const int pos = atomicAdd(&D.cursor[hb + slot], 1);
+  D.members[(size_t)c * D.nmax + D.start[hb + slot] + pos] = i;
+}
+
+// ascending in-place sort of one member list by its owning thread: insertion sort for the usual handful
+// of points per voxel, heap sort beyond that
+__device__ void sort_members(int* m, int n) {
+  if (n <= 24) {
+    for (int i = 1; i < n; i++) {
+      const int v = m[i];
+      int j = i - 1;
+      while (j >= 0 && m[j] > v) { m[j + 1] = m[j]; j--; }
+      m[j + 1] = v;
     }
-    __syncwarp();
+    return;
+  }
+  auto sift = [&](int root, int end) {
+    const int v = m[root];
+    while (true) {
+      int ch = 2 * root + 1;
+      if (ch >= end) break;
+      if (ch + 1 < end && m[ch + 1] > m[ch]) ch++;
+      if (m[ch] <= v) break;
+      m[root] = m[ch];
+      root = ch;
+    }
+    m[root] = v;
+  };
+  for (int i = n / 2 - 1; i >= 0; i--) sift(i, n);
+  for (int e = n - 1; e > 0; e--) {
+    const int t = m[0]; m[0] = m[e]; m[e] = t;
+    sift(0, e);
   }
 }
 
@@ -219,8 +238,9 @@ __global__ void __launch_bounds__(256) k_voxel_mean(GicpDev D, const float* __re
   const size_t hb = (size_t)c * D.hsize;
   if (D.minIdx[hb + slot] != i) return;
   const float* base = ((c & 1) ? src : tgt) + (size_t)(c >> 1) * stride * 4;
-  const int* mem = D.members + (size_t)c * D.nmax + D.start[hb + slot];
+  int* mem = D.members + (size_t)c * D.nmax + D.start[hb + slot];
   const int cnt = D.count[hb + slot];
+  sort_members(mem, cnt);
   double sx = 0, sy = 0, sz = 0, w = 0;
   for (int j = 0; j < cnt; j++) {
     const float4 v = *reinterpret_cast<const float4*>(base + (size_t)mem[j] * 4);
@@ -230,33 +250,60 @@ __global__ void __launch_bounds__(256) k_voxel_mean(GicpDev D, const float* __re
   o[0] = sx / w; o[1] = sy / w; o[2] = sz / w; o[3] = 1.0;
 }
 
-// ---- grid lookup
+// ---- k-NN grid: packed slot table + points stored in cell order
+__global__ void __launch_bounds__(256) k_cell_pack(GicpDev D, int clouds) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (long long)clouds * D.hsize) {
+    const unsigned long long k = D.keys[i];
+    D.tab[i] = make_uint4((unsigned)k, (unsigned)(k >> 32), (unsigned)D.start[i], (unsigned)D.count[i]);
+  }
+  if (i < (long long)clouds * D.nmax) {
+    const int c = (int)(i / D.nmax), m = (int)(i % D.nmax);
+    if (m < D.nDown[c]) {
+      const int pi = D.members[i];
+      const double2* p = reinterpret_cast<const double2*>(D.pts + ((size_t)c * D.nmax + pi) * 4);
+      double2* o = reinterpret_cast<double2*>(D.rec + (size_t)i * 4);
+      const double2 xy = p[0];
+      o[0] = xy;
+      o[1] = make_double2(p[1].x, __longlong_as_double((long long)pi));
+    }
+  }
+}
+
 struct Grid {
-  const unsigned long long* keys;
-  const int *count, *start, *members;
+  const uint4* tab;
+  const double2* rec;
   const double* pts;
   int hm;
 };
 __device__ __forceinline__ Grid make_grid(const GicpDev& D, int c) {
   Grid g;
-  g.keys = D.keys + (size_t)c * D.hsize;
-  g.count = D.count + (size_t)c * D.hsize;
-  g.start = D.start + (size_t)c * D.hsize;
-  g.members = D.members + (size_t)c * D.nmax;
+  g.tab = D.tab + (size_t)c * D.hsize;
+  g.rec = reinterpret_cast<const double2*>(D.rec + (size_t)c * D.nmax * 4);
   g.pts = D.pts + (size_t)c * D.nmax * 4;
   g.hm = D.hsize - 1;
   return g;
 }
-__device__ __forceinline__ int grid_find(const Grid& g, int cx, int cy, int cz) {
-  if ((unsigned)cx > 0x1fffffu || (unsigned)cy > 0x1fffffu || (unsigned)cz > 0x1fffffu) return -1;
+// occupied cell -> (first record, count); false for an empty cell
+__device__ __forceinline__ bool grid_find(const Grid& g, int cx, int cy, int cz, int& start, int& count) {
+  if ((unsigned)cx > 0x1fffffu || (unsigned)cy > 0x1fffffu || (unsigned)cz > 0x1fffffu) return false;
   const unsigned long long key = (unsigned long long)cx | ((unsigned long long)cy << 21) | ((unsigned long long)cz << 42);
   int h = (int)(mix64(key) & g.hm);
   while (true) {
-    const unsigned long long k = g.keys[h];
-    if (k == key) return h;
-    if (k == KEY_EMPTY) return -1;
+    const uint4 e = __ldg(&g.tab[h]);
+    const unsigned long long k = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
+    if (k == key) { start = (int)e.z; count = (int)e.w; return true; }
+    if (k == KEY_EMPTY) return false;
     h = (h + 1) & g.hm;
   }
+}
+// record -> squared distance to the query and the point index
+__device__ __forceinline__ double rec_sqdist(const Grid& g, int r, double qx, double qy, double qz, int& index) {
+  const double2 a = __ldg(&g.rec[2 * (size_t)r]), b = __ldg(&g.rec[2 * (size_t)r + 1]);
+  index = (int)__double_as_longlong(b.y);
+  // Eigen Vector4d::squaredNorm with SSE2 packets: (dx^2 + dz^2) + dy^2
+  const double dx = a.x - qx, dy = a.y - qy, dz = b.x - qz;
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz)), __dmul_rn(dy, dy));
 }
 __device__ __forceinline__ double sqdist3(const double* p, double qx, double qy, double qz) {
   // Eigen Vector4d::squaredNorm with SSE2 packets: (dx^2 + dz^2) + dy^2
@@ -293,56 +340,181 @@ struct KnnAcc {
 };
 
 template <int K>
-__device__ __forceinline__ void scan_cell(const Grid& g, int slot, double qx, double qy, double qz, KnnAcc<K>& acc) {
-  const int s = g.start[slot], n = g.count[slot];
+__device__ __forceinline__ void scan_cell(const Grid& g, int s, int n, double qx, double qy, double qz, KnnAcc<K>& acc) {
   for (int j = 0; j < n; j++) {
-    const int pi = g.members[s + j];
-    acc.push(pi, sqdist3(g.pts + (size_t)pi * 4, qx, qy, qz));
+    int pi;
+    const double d = rec_sqdist(g, s + j, qx, qy, qz, pi);
+    acc.push(pi, d);
   }
+}
+
+// ---- shell traversal with cell pruning
+// Query geometry: home cell (cx,cy,cz) and the offsets (fx,fy,fz) of the query inside it.
+struct ShellQuery {
+  int cx, cy, cz;
+  double fx, fy, fz, cell, margin;
+};
+__device__ __forceinline__ ShellQuery make_shell_query(double cell, double qx, double qy, double qz) {
+  ShellQuery s;
+  const double inv = 1.0 / cell;
+  const int off = 1 << 20;
+  s.cx = fast_floor_d(qx * inv) + off; s.cy = fast_floor_d(qy * inv) + off; s.cz = fast_floor_d(qz * inv) + off;
+  s.fx = qx - (double)(s.cx - off) * cell; s.fy = qy - (double)(s.cy - off) * cell; s.fz = qz - (double)(s.cz - off) * cell;
+  s.cell = cell;
+  // distance from the query to the nearest face of its own cell
+  const double m = fmin(fmin(s.fx, cell - s.fx), fmin(fmin(s.fy, cell - s.fy), fmin(s.fz, cell - s.fz)));
+  s.margin = fmax(m, 0.0) * 0.999999;  // guard the bound against rounding in fx..fz
+  return s;
+}
+// squared lower bound of the distance from the query to any point of a cell `d` cells away along one axis
+// (shrunk a little so that rounding in the cell assignment can never prune a cell that matters)
+__device__ __forceinline__ double axis_gap2(int d, double f, double cell) {
+  if (d == 0) return 0.0;
+  const double g = d > 0 ? (double)d * cell - f : f - (double)(d + 1) * cell;
+  const double gg = fmax(g * 0.999999 - 1e-12, 0.0);
+  return gg * gg;
+}
+// Visit the occupied cells of shell r (Chebyshev ring) whose lower bound does not exceed limit().
+template <class Limit, class Visit>
+__device__ __forceinline__ void visit_shell(const Grid& g, const int* box, const ShellQuery& q, int r, Limit limit, Visit visit) {
+  const int x0 = max(q.cx - r, box[0]), x1 = min(q.cx + r, box[3]);
+  const int y0 = max(q.cy - r, box[1]), y1 = min(q.cy + r, box[4]);
+  const int z0 = max(q.cz - r, box[2]), z1 = min(q.cz + r, box[5]);
+  for (int z = z0; z <= z1; z++) {
+    const double gz2 = axis_gap2(z - q.cz, q.fz, q.cell);
+    if (gz2 > limit()) continue;
+    for (int y = y0; y <= y1; y++) {
+      const double gyz2 = gz2 + axis_gap2(y - q.cy, q.fy, q.cell);
+      if (gyz2 > limit()) continue;
+      const bool face = (z == q.cz - r) || (z == q.cz + r) || (y == q.cy - r) || (y == q.cy + r);
+      if (face) {
+        for (int x = x0; x <= x1; x++) {
+          if (gyz2 + axis_gap2(x - q.cx, q.fx, q.cell) > limit()) continue;
+          int cs, cn;
+          if (grid_find(g, x, y, z, cs, cn)) visit(cs, cn);
+        }
+      } else {
+        if (q.cx - r >= x0 && !(gyz2 + axis_gap2(-r, q.fx, q.cell) > limit())) {
+          int cs, cn;
+          if (grid_find(g, q.cx - r, y, z, cs, cn)) visit(cs, cn);
+        }
+        if (r > 0 && q.cx + r <= x1 && !(gyz2 + axis_gap2(r, q.fx, q.cell) > limit())) {
+          int cs, cn;
+          if (grid_find(g, q.cx + r, y, z, cs, cn)) visit(cs, cn);
+        }
+      }
+    }
+  }
+}
+__device__ __forceinline__ bool box_covered(const int* box, const ShellQuery& q, int r) {
+  return q.cx - r <= box[0] && q.cx + r >= box[3] && q.cy - r <= box[1] && q.cy + r >= box[4] && q.cz - r <= box[2] &&
+         q.cz + r >= box[5];
 }
 
 // Exact k-NN: shells of grid cells around the query until the k-th distance is provably final,
 // brute force over the cloud beyond MAX_SHELL.  If max_r2 >= 0 the search may stop as soon as no
 // unvisited point can be closer than sqrt(max_r2) (bounded 1-NN for correspondences).
-static const int MAX_SHELL = 4;
+static const int MAX_SHELL = 8;
 template <int K>
 __device__ void grid_knn(const Grid& g, const int* box, int nPts, double cell, double qx, double qy, double qz,
-                         double max_r2, KnnAcc<K>& acc) {
-  acc.init();
-  const double inv = 1.0 / cell;
-  const int off = 1 << 20;
-  const int cx = fast_floor_d(qx * inv) + off, cy = fast_floor_d(qy * inv) + off, cz = fast_floor_d(qz * inv) + off;
-  // distance from the query to the nearest face of its own cell
-  const double fx = qx - (double)(cx - off) * cell, fy = qy - (double)(cy - off) * cell, fz = qz - (double)(cz - off) * cell;
-  double margin = fmin(fmin(fx, cell - fx), fmin(fmin(fy, cell - fy), fmin(fz, cell - fz)));
-  margin = fmax(margin, 0.0) * 0.999999;  // guard the bound against rounding in fx..fz
+                         double max_r2, KnnAcc<K>& acc, bool seeded = false) {
+  if (!seeded) acc.init();
+  const ShellQuery q = make_shell_query(cell, qx, qy, qz);
+  const double cap = max_r2 >= 0.0 ? max_r2 : DBL_MAX;
   for (int r = 0; r <= MAX_SHELL; r++) {
-    const int x0 = max(cx - r, box[0]), x1 = min(cx + r, box[3]);
-    const int y0 = max(cy - r, box[1]), y1 = min(cy + r, box[4]);
-    const int z0 = max(cz - r, box[2]), z1 = min(cz + r, box[5]);
-    for (int z = z0; z <= z1; z++)
-      for (int y = y0; y <= y1; y++) {
-        const bool face = (z == cz - r) || (z == cz + r) || (y == cy - r) || (y == cy + r);
-        if (face) {
-          for (int x = x0; x <= x1; x++) {
-            const int s = grid_find(g, x, y, z);
-            if (s >= 0) scan_cell<K>(g, s, qx, qy, qz, acc);
-          }
-        } else {
-          if (cx - r >= x0) { const int s = grid_find(g, cx - r, y, z); if (s >= 0) scan_cell<K>(g, s, qx, qy, qz, acc); }
-          if (r > 0 && cx + r <= x1) { const int s = grid_find(g, cx + r, y, z); if (s >= 0) scan_cell<K>(g, s, qx, qy, qz, acc); }
-        }
-      }
-    const double bound = (double)r * cell + margin;  // every unvisited point is farther than this
+    visit_shell(g, box, q, r,
+                [&]() { return acc.found == K ? fmin(acc.d[K - 1], cap) : cap; },
+                [&](int cs, int cn) { scan_cell<K>(g, cs, cn, qx, qy, qz, acc); });
+    const double bound = (double)r * cell + q.margin;  // every unvisited point is farther than this
     const double b2 = bound * bound;
     if (acc.found == K && acc.d[K - 1] <= b2) return;
     if (max_r2 >= 0.0 && b2 >= max_r2) return;
-    // whole bounding box visited?
-    if (cx - r <= box[0] && cx + r >= box[3] && cy - r <= box[1] && cy + r >= box[4] && cz - r <= box[2] && cz + r >= box[5]) return;
+    if (box_covered(box, q, r)) return;
   }
   // far / sparse query: exact brute force over the cloud
   acc.init();
   for (int i = 0; i < nPts; i++) acc.push(i, sqdist3(g.pts + (size_t)i * 4, qx, qy, qz));
+}
+
+// Exact 10-NN in two passes, shaped for SIMT.  Per shell the occupied cells that survive pruning are
+// first collected into a per-thread list in shared memory; the candidates of those cells are then
+// walked by ONE flat loop (a lane never waits in a per-cell inner loop of a neighbour lane).
+// Pass A keeps only the K smallest distances, rounded UP to float, in a branch-free min/max chain and
+// yields a radius rho >= the true k-th distance; pass B walks the listed cells again and appends the few
+// candidates with d <= rho to a short per-thread list; the exact (distance, index) selection then runs
+// once over that list.  Falls back to grid_knn when a list overflows (ties, dense cells, clouds with
+// fewer than K points) or the shells run out.
+static const int KNN_K = 10;
+static const int KNN_LIST = 16;    // candidates kept for the exact selection
+static const int KNN_CELLS = 48;   // occupied cells remembered per query, packed (start << 8 | count)
+static const int KNN_THREADS = 128;
+static const size_t KNN_SMEM = (size_t)KNN_THREADS * (KNN_LIST * 12 + KNN_CELLS * 4);
+
+// one flat loop over the records of cells[from..to)
+template <class Body>
+__device__ __forceinline__ void walk_cells(const unsigned* cells, int from, int to, Body body) {
+  int ci = from - 1, r = 0, end = 0;
+  for (;;) {
+    if (r >= end) {
+      if (++ci >= to) break;
+      const unsigned c = cells[ci * KNN_THREADS];
+      r = (int)(c >> 8); end = r + (int)(c & 0xffu);
+    }
+    body(r);
+    r++;
+  }
+}
+
+__device__ void knn10_two_pass(const Grid& g, const int* box, int nPts, double cell, double qx, double qy, double qz,
+                               double* s_d, int* s_id, unsigned* s_cells, KnnAcc<KNN_K>& acc) {
+  const ShellQuery q = make_shell_query(cell, qx, qy, qz);
+  float top[KNN_K];
+#pragma unroll
+  for (int i = 0; i < KNN_K; i++) top[i] = FLT_MAX;
+  int seen = 0, nc = 0;
+  bool ok = false, overflow = false;
+  for (int r = 0; r <= MAX_SHELL && !overflow; r++) {
+    const int from = nc;
+    const double lim = (double)top[KNN_K - 1];
+    visit_shell(g, box, q, r, [&]() { return lim; },
+                [&](int cs, int cn) {
+                  if (nc < KNN_CELLS && cn < 256 && cs < (1 << 24)) s_cells[nc++ * KNN_THREADS] = ((unsigned)cs << 8) | (unsigned)cn;
+                  else overflow = true;
+                });
+    walk_cells(s_cells, from, nc, [&](int rec) {
+      int pi;
+      float v = __double2float_ru(rec_sqdist(g, rec, qx, qy, qz, pi));
+#pragma unroll
+      for (int i = 0; i < KNN_K; i++) {
+        const float lo = fminf(top[i], v);
+        v = fmaxf(top[i], v);
+        top[i] = lo;
+      }
+      seen++;
+    });
+    const double bound = (double)r * cell + q.margin;
+    if ((seen >= KNN_K && (double)top[KNN_K - 1] <= bound * bound) || box_covered(box, q, r)) { ok = true; break; }
+  }
+  ok = ok && !overflow && seen >= KNN_K && top[KNN_K - 1] < FLT_MAX;
+  int cnt = 0;
+  if (ok) {
+    const double rho = (double)top[KNN_K - 1];
+    walk_cells(s_cells, 0, nc, [&](int rec) {
+      int pi;
+      const double dd = rec_sqdist(g, rec, qx, qy, qz, pi);
+      if (dd <= rho) {
+        if (cnt < KNN_LIST) { s_d[cnt * KNN_THREADS] = dd; s_id[cnt * KNN_THREADS] = pi; }
+        cnt++;
+      }
+    });
+    ok = cnt <= KNN_LIST;
+  }
+  if (!ok) {
+    grid_knn<KNN_K>(g, box, nPts, cell, qx, qy, qz, -1.0, acc);
+    return;
+  }
+  acc.init();
+  for (int j = 0; j < cnt; j++) acc.push(s_id[j * KNN_THREADS], s_d[j * KNN_THREADS]);
 }
 
 // ---- Eigen SelfAdjointEigenSolver<Matrix3d>::computeDirect restated (see oracle/gicp_oracle.cpp)
@@ -437,14 +609,18 @@ __device__ void eig3_direct(const double A[3][3], double V[3][3]) {
 }
 
 // estimate_local_features<CovarianceSetter> (normal_estimation.hpp:66-92), K = 10
-__global__ void __launch_bounds__(128) k_knn_cov(GicpDev D) {
+__global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_cov(GicpDev D) {
+  extern __shared__ __align__(16) unsigned char s_knn[];
+  double* s_d = reinterpret_cast<double*>(s_knn);
+  unsigned* s_cells = reinterpret_cast<unsigned*>(s_d + KNN_LIST * KNN_THREADS);
+  int* s_id = reinterpret_cast<int*>(s_cells + KNN_CELLS * KNN_THREADS);
   const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = D.nDown[c];
   if (i >= n) return;
   const Grid g = make_grid(D, c);
   const double* q = g.pts + (size_t)i * 4;
-  KnnAcc<10> acc;
-  grid_knn<10>(g, D.cellBox + c * 6, n, D.cell, q[0], q[1], q[2], -1.0, acc);
+  KnnAcc<KNN_K> acc;
+  knn10_two_pass(g, D.cellBox + c * 6, n, D.cell, q[0], q[1], q[2], s_d + threadIdx.x, s_id + threadIdx.x, s_cells + threadIdx.x, acc);
   double* out = D.cov + ((size_t)c * D.nmax + i) * 6;
   const int nf = acc.found;
   if (nf < 5) {
@@ -503,7 +679,7 @@ __device__ __forceinline__ void xform(const double* T, const double* p, double o
 
 static const int LIN_THREADS = 128;
 // GICPFactor::linearize for every source point of every active pair + partial sums
-__global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D) {
+__global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D, int iter) {
   const int p = blockIdx.y;
   if (!D.istate[p * LM_ISTATE + I_ACTIVE]) return;
   const int ct = 2 * p, cs = 2 * p + 1;
@@ -519,8 +695,13 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D) {
     xform(T, ps, q);
     const Grid g = make_grid(D, ct);
     KnnAcc<1> nn;
+    nn.init();
     const double max_d2 = D.max_dist * D.max_dist;
-    grid_knn<1>(g, D.cellBox + ct * 6, D.nDown[ct], D.cell, q[0], q[1], q[2], max_d2 * 1.0000001, nn);
+    // the previous iteration's correspondence is a real target point: starting from it only tightens
+    // the pruning radius, the result is still the exact nearest neighbour
+    const int prev = iter > 0 ? D.corr[(size_t)p * D.nmax + i] : -1;
+    if (prev >= 0) nn.push(prev, sqdist3(g.pts + (size_t)prev * 4, q[0], q[1], q[2]));
+    grid_knn<1>(g, D.cellBox + ct * 6, D.nDown[ct], D.cell, q[0], q[1], q[2], max_d2 * 1.0000001, nn, true);
     int tgt = -1;
     if (nn.found == 1 && !(nn.d[0] > max_d2)) tgt = nn.id[0];  // DistanceRejector: sq_dist > max_dist_sq
     D.corr[(size_t)p * D.nmax + i] = tgt;
@@ -803,7 +984,7 @@ using namespace gfs;
 struct GfsGicp {
   GicpDev dev;
   int maxPairs = 0;
-  DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_box, b_pts, b_cov,
+  DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_box, b_pts, b_cov, b_tab, b_rec,
       b_corr, b_maha, b_partial, b_partialE, b_state, b_istate, b_counters;
   DevBuf b_tgt, b_src, b_n, b_T0, b_res;
   PinnedBuf h_counters;
@@ -835,6 +1016,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   GFS_REQUIRE(s.num_neighbors == 10, GFS_ERR_INVALID, "num_neighbors must be 10 (the value align() hard-codes)");
   int rc = gfs_device_check();
   if (rc) return rc;
+  GFS_CUDA(cudaFuncSetAttribute(k_knn_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KNN_SMEM));
   GfsGicp* h = new GfsGicp();
   GicpDev& D = h->dev;
   memset(&D, 0, sizeof(D));
@@ -873,6 +1055,8 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   RES(b_box, C * 6 * 4, cellBox, int*)
   RES(b_pts, C * N * 32, pts, double*)
   RES(b_cov, C * N * 48, cov, double*)
+  RES(b_tab, C * H * 16, tab, uint4*)
+  RES(b_rec, C * N * 32, rec, double*)
   RES(b_corr, P * N * 4, corr, int*)
   RES(b_maha, P * N * 72, maha, double*)
   RES(b_partial, P * D.nblk * RED_N * 8, partial, double*)
@@ -889,7 +1073,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
 int gfs_gicp_destroy(GfsGicp* h) {
   if (!h) return GFS_OK;
   DevBuf* d[] = {&h->b_keys, &h->b_minIdx, &h->b_count, &h->b_start, &h->b_cursor, &h->b_rank, &h->b_slotOf, &h->b_members,
-                 &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_box, &h->b_pts, &h->b_cov, &h->b_corr, &h->b_maha, &h->b_partial,
+                 &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_box, &h->b_pts, &h->b_cov, &h->b_tab, &h->b_rec, &h->b_corr, &h->b_maha, &h->b_partial,
                  &h->b_partialE, &h->b_state, &h->b_istate, &h->b_counters, &h->b_tgt, &h->b_src, &h->b_n, &h->b_T0, &h->b_res};
   for (DevBuf* b : d) b->release();
   h->h_counters.release();
@@ -906,7 +1090,7 @@ static int group_build(GfsGicp* h, cudaStream_t st, int mode, int clouds, const 
   k_group_clear<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(D, clouds);
   k_group_insert<<<dim3(div_up(D.nmax, 256), clouds), 256, 0, st>>>(D, mode, tgt, src, stride);
   k_group_rank<<<clouds, 1024, 0, st>>>(D, mode, nGroupsOut);
-  k_group_fill<<<div_up(clouds, 4), 128, 0, st>>>(D, mode, clouds);
+  k_group_fill<<<dim3(div_up(D.nmax, 256), clouds), 256, 0, st>>>(D, mode);
   h->launches += 4;
   return GFS_OK;
 }
@@ -926,14 +1110,18 @@ int gfs_gicp_align_batch_device(GfsGicp* h, void* stream, const float* d_target,
   k_voxel_mean<<<dim3(div_up(D.nmax, 256), clouds), 256, 0, st>>>(D, d_target, d_source, stride);
   // grid over the downsampled points (reuses the hash-table storage); group count is not needed
   group_build(h, st, 1, clouds, nullptr, nullptr, 0, D.nCells);
-  k_knn_cov<<<dim3(div_up(D.nmax, 128), clouds), 128, 0, st>>>(D);
+  {
+    const long long work = (long long)clouds * std::max(D.hsize, D.nmax);
+    k_cell_pack<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(D, clouds);
+  }
+  k_knn_cov<<<dim3(div_up(D.nmax, KNN_THREADS), clouds), KNN_THREADS, KNN_SMEM, st>>>(D);
   k_lm_init<<<div_up(pairs, 128), 128, 0, st>>>(D, pairs, d_T0);
-  h->launches += 4;
+  h->launches += 5;
   GFS_CUDA(cudaGetLastError());
   int* hc = (int*)h->h_counters.p;
   for (int it = 0; it < D.max_iter; it++) {
     GFS_CUDA(cudaMemsetAsync(D.counters, 0, 8, st));
-    k_linearize<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D);
+    k_linearize<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D, it);
     k_lm_begin<<<pairs, 32, 0, st>>>(D, it);
     h->launches += 2;
     for (int j = 0; j < 10; j++) {
