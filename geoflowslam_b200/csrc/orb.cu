@@ -104,6 +104,95 @@ __global__ void __launch_bounds__(256) k_pyr_level(OrbDev P, int l, const uint8_
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_pyr_level3: the same arithmetic for scale factors below 2 (every destination pixel covers 2 or 3
+// source pixels; the tables are padded to exactly 3 taps with zero weights, which adds an exact 0).
+// CTA = 64 x 32 destination tile.  Source window -> shared memory as floats (word loads, each source
+// pixel converted once) -> horizontal pass into shared memory -> vertical pass, 4 pixels per thread,
+// packed 32-bit stores.
+// ------------------------------------------------------------------------------------------------
+struct Area3 {
+  int s0;
+  float a0, a1, a2;
+};
+__device__ __forceinline__ unsigned sat_u8_rn(float v) {  // saturate_cast<uchar>(cvRound(v))
+  unsigned r;
+  asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__global__ void __launch_bounds__(256) k_pyr_level3(OrbDev P, int l, const uint8_t* __restrict__ src_base,
+                                                    long long src_stride, int src_pitch, int word_ok,
+                                                    uint8_t* __restrict__ pyr, const Area3* __restrict__ tabs, int srcRows,
+                                                    int srcPitchF) {
+  extern __shared__ float s_buf[];
+  float* s_src = s_buf;                        // [srcRows][srcPitchF]
+  float* s_h = s_buf + srcRows * srcPitchF;    // [srcRows][PYR_TW]
+  const LevelDev& L = P.lv[l];
+  const int tid = threadIdx.x, frame = blockIdx.z;
+  const int dx0 = blockIdx.x * PYR_TW, dy0 = blockIdx.y * PYR_TH;
+  const int tw = min(PYR_TW, L.w - dx0), th = min(PYR_TH, L.h - dy0);
+  const Area3* tx = tabs + L.tabX + dx0;
+  const Area3* ty = tabs + L.tabY + dy0;
+  const int xs = tx[0].s0 & ~3;
+  const int words = ((tx[tw - 1].s0 + 2 - xs) >> 2) + 1;
+  const int r0 = ty[0].s0, nr = ty[th - 1].s0 + 3 - r0;
+  const uint8_t* src = src_base + (long long)frame * src_stride + (long long)r0 * src_pitch + xs;
+  {
+    const int wd = tid & 31;
+    if (wd < words) {
+      const bool whole = word_ok && (xs + 4 * wd + 4 <= src_pitch);
+      for (int r = tid >> 5; r < nr; r += 8) {
+        const uint8_t* S = src + (long long)r * src_pitch + 4 * wd;
+        float4 f;
+        if (whole) {
+          const unsigned v = __ldg(reinterpret_cast<const unsigned*>(S));
+          f = make_float4((float)(v & 0xffu), (float)((v >> 8) & 0xffu), (float)((v >> 16) & 0xffu), (float)(v >> 24));
+        } else {
+          const int lim = src_pitch - 1 - (xs + 4 * wd);  // last readable byte of the row
+          f = make_float4((float)__ldg(S + min(0, lim)), (float)__ldg(S + min(1, lim)), (float)__ldg(S + min(2, lim)),
+                          (float)__ldg(S + min(3, lim)));
+        }
+        *reinterpret_cast<float4*>(s_src + r * srcPitchF + 4 * wd) = f;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int c = tid & (PYR_TW - 1);
+    if (c < tw) {
+      const Area3 e = tx[c];
+      const float* p = s_src + (e.s0 - xs);
+      for (int r = tid >> 6; r < nr; r += 256 / PYR_TW) {
+        const float* q = p + r * srcPitchF;
+        float buf = __fmul_rn(q[0], e.a0);
+        buf = __fadd_rn(buf, __fmul_rn(q[1], e.a1));
+        buf = __fadd_rn(buf, __fmul_rn(q[2], e.a2));
+        s_h[r * PYR_TW + c] = buf;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int cg = (tid & 15) * 4;
+    if (cg < tw) {
+      uint8_t* out = pyr + (long long)frame * P.pyrStride + L.off + dx0 + cg;
+      for (int ry = tid >> 4; ry < th; ry += 16) {
+        const Area3 e = ty[ry];
+        const float* q = s_h + (e.s0 - r0) * PYR_TW + cg;
+        const float4 h0 = *reinterpret_cast<const float4*>(q), h1 = *reinterpret_cast<const float4*>(q + PYR_TW),
+                     h2 = *reinterpret_cast<const float4*>(q + 2 * PYR_TW);
+        float sx = __fmul_rn(e.a0, h0.x), sy = __fmul_rn(e.a0, h0.y), sz = __fmul_rn(e.a0, h0.z), sw = __fmul_rn(e.a0, h0.w);
+        sx = __fadd_rn(sx, __fmul_rn(e.a1, h1.x)); sy = __fadd_rn(sy, __fmul_rn(e.a1, h1.y));
+        sz = __fadd_rn(sz, __fmul_rn(e.a1, h1.z)); sw = __fadd_rn(sw, __fmul_rn(e.a1, h1.w));
+        sx = __fadd_rn(sx, __fmul_rn(e.a2, h2.x)); sy = __fadd_rn(sy, __fmul_rn(e.a2, h2.y));
+        sz = __fadd_rn(sz, __fmul_rn(e.a2, h2.z)); sw = __fadd_rn(sw, __fmul_rn(e.a2, h2.w));
+        const unsigned v = sat_u8_rn(sx) | (sat_u8_rn(sy) << 8) | (sat_u8_rn(sz) << 16) | (sat_u8_rn(sw) << 24);
+        *reinterpret_cast<unsigned*>(out + (long long)(dy0 + ry) * L.pitch) = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_fast_cells: one CTA per (cell, frame).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool has_arc9(unsigned m16) {
@@ -911,7 +1000,9 @@ struct GfsOrb {
   DevBuf d_pyr, d_blur, d_cellKeys, d_cellCount, d_keysA, d_keysB, d_sel, d_selCount, d_tabs, d_status;
   DevBuf d_in, d_okp, d_odesc, d_on, d_omono, d_tkp, d_tdesc, d_pattern;
   PinnedBuf h_in, h_okp, h_odesc, h_on;
-  size_t fastSmem = 0, octSmem = 0, pyrSmem = 0;
+  size_t fastSmem = 0, octSmem = 0, pyrSmem = 0, pyr3Smem = 0;
+  int pyr3Rows = 0, pyr3PitchF = 0;  // k_pyr_level3 shared-memory geometry; pyr3Rows == 0: generic kernel
+  DevBuf d_tabs3;
   // optional per-stage CUDA-event timing (bench roofline): pyramid, fast, octree, blur, orient/desc, pack
   bool profiling = false;
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -1013,6 +1104,43 @@ static int orb_set_geometry(GfsOrb* h, int w, int ht) {
     }
   }
   h->pyrSmem = (size_t)maxSrcRows * PYR_TW * sizeof(float);
+  // 3-tap tables (same indexing as `tabs`) when no entry needs more than 3 source pixels
+  std::vector<Area3> tabs3;
+  bool three = !tabs.empty();
+  for (const AreaEntry& e : tabs) three = three && e.n >= 1 && e.n <= 3;
+  int pyr3Rows = 0, pyr3PitchF = 0;
+  if (three) {
+    tabs3.resize(tabs.size());
+    auto pad = [&](int first, int count, int ssize) {
+      for (int i = first; i < first + count && three; i++) {
+        const AreaEntry& e = tabs[i];
+        float a[3] = {0.f, 0.f, 0.f};
+        int s0 = e.s0;
+        if (ssize < 3) { three = false; break; }
+        const int shift = std::max(0, s0 + 3 - ssize);  // zero taps go in front when the window would leave the image
+        s0 -= shift;
+        for (int k = 0; k < e.n; k++) a[k + shift] = e.a[k];
+        tabs3[i] = Area3{s0, a[0], a[1], a[2]};
+      }
+    };
+    for (int l = 1; l < h->nlevels; l++) {
+      pad(D.lv[l].tabX, D.lv[l].w, D.lv[l - 1].w);
+      pad(D.lv[l].tabY, D.lv[l].h, D.lv[l - 1].h);
+    }
+    for (int l = 1; l < h->nlevels && three; l++) {
+      const LevelDev& L = D.lv[l];
+      for (int dy0 = 0; dy0 < L.h; dy0 += PYR_TH)
+        pyr3Rows = std::max(pyr3Rows, tabs3[L.tabY + std::min(dy0 + PYR_TH, L.h) - 1].s0 + 3 - tabs3[L.tabY + dy0].s0);
+      for (int dx0 = 0; dx0 < L.w; dx0 += PYR_TW) {
+        const int xs = tabs3[L.tabX + dx0].s0 & ~3;
+        const int words = ((tabs3[L.tabX + std::min(dx0 + PYR_TW, L.w) - 1].s0 + 2 - xs) >> 2) + 1;
+        if (words > 32) three = false;
+        pyr3PitchF = std::max(pyr3PitchF, 4 * words);
+      }
+    }
+  }
+  if (!three) pyr3Rows = pyr3PitchF = 0;
+  const size_t pyr3Smem = (size_t)pyr3Rows * (pyr3PitchF + PYR_TW) * sizeof(float);
   for (const AreaEntry& e : tabs)
     if (e.n > 4 || e.n < 1) {
       set_error("scale factor outside the supported (1, 3) range");
@@ -1073,6 +1201,10 @@ static int orb_set_geometry(GfsOrb* h, int w, int ht) {
   if ((rc = h->d_status.reserve(16))) return rc;
   if ((rc = h->d_tabs.reserve(std::max<size_t>(tabs.size(), 1) * sizeof(AreaEntry)))) return rc;
   if (!tabs.empty()) GFS_CUDA(cudaMemcpy(h->d_tabs.p, tabs.data(), tabs.size() * sizeof(AreaEntry), cudaMemcpyHostToDevice));
+  if (pyr3Rows) {
+    if ((rc = h->d_tabs3.reserve(tabs3.size() * sizeof(Area3)))) return rc;
+    GFS_CUDA(cudaMemcpy(h->d_tabs3.p, tabs3.data(), tabs3.size() * sizeof(Area3), cudaMemcpyHostToDevice));
+  }
   GFS_CUDA(cudaMemset(h->d_status.p, 0, 16));
   if ((rc = h->d_pattern.reserve(1024))) return rc;
   GFS_CUDA(cudaMemcpy(h->d_pattern.p, GFS_ORB_PATTERN, 1024, cudaMemcpyHostToDevice));
@@ -1084,7 +1216,11 @@ static int orb_set_geometry(GfsOrb* h, int w, int ht) {
     return GFS_ERR_CAPACITY;
   }
   // the attribute is per function (shared by every handle): only ever raise it
-  static size_t octMax = 48 * 1024, fastMax = 48 * 1024, pyrMax = 48 * 1024;
+  static size_t octMax = 48 * 1024, fastMax = 48 * 1024, pyrMax = 48 * 1024, pyr3Max = 48 * 1024;
+  if (pyr3Smem > pyr3Max) {
+    GFS_CUDA(cudaFuncSetAttribute(k_pyr_level3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pyr3Smem));
+    pyr3Max = pyr3Smem;
+  }
   if (h->pyrSmem > pyrMax) {
     GFS_CUDA(cudaFuncSetAttribute(k_pyr_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pyrSmem));
     pyrMax = h->pyrSmem;
@@ -1097,6 +1233,9 @@ static int orb_set_geometry(GfsOrb* h, int w, int ht) {
     GFS_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem));
     fastMax = h->fastSmem;
   }
+  h->pyr3Rows = pyr3Rows;
+  h->pyr3PitchF = pyr3PitchF;
+  h->pyr3Smem = pyr3Smem;
   h->dev = D;
   h->geomW = w;
   h->geomH = ht;
@@ -1149,7 +1288,7 @@ int gfs_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fa
 int gfs_orb_destroy(GfsOrb* h) {
   if (!h) return GFS_OK;
   DevBuf* d[] = {&h->d_pyr, &h->d_blur, &h->d_cellKeys, &h->d_cellCount, &h->d_keysA, &h->d_keysB, &h->d_sel,
-                 &h->d_selCount, &h->d_tabs, &h->d_status, &h->d_in, &h->d_okp, &h->d_odesc, &h->d_on, &h->d_omono,
+                 &h->d_selCount, &h->d_tabs, &h->d_tabs3, &h->d_status, &h->d_in, &h->d_okp, &h->d_odesc, &h->d_on, &h->d_omono,
                  &h->d_tkp, &h->d_tdesc, &h->d_pattern};
   for (DevBuf* b : d) b->release();
   h->h_in.release(); h->h_okp.release(); h->h_odesc.release(); h->h_on.release();
@@ -1211,7 +1350,13 @@ static int orb_run_chunk(GfsOrb* h, cudaStream_t st, const uint8_t* d_imgs, int 
     const uint8_t* src = (l == 1) ? d_imgs : pyr + D.lv[l - 1].off;
     const long long ss = (l == 1) ? (long long)img_stride : D.pyrStride;
     const int sp = (l == 1) ? pitch : D.lv[l - 1].pitch;
-    k_pyr_level<<<grd, blk, h->pyrSmem, st>>>(D, l, src, ss, sp, pyr, (const AreaEntry*)h->d_tabs.p);
+    if (h->pyr3Rows) {
+      const int word_ok = (((uintptr_t)src | (uintptr_t)ss | (uintptr_t)sp) & 3) == 0;
+      k_pyr_level3<<<grd, blk, h->pyr3Smem, st>>>(D, l, src, ss, sp, word_ok, pyr, (const Area3*)h->d_tabs3.p, h->pyr3Rows,
+                                                  h->pyr3PitchF);
+    } else {
+      k_pyr_level<<<grd, blk, h->pyrSmem, st>>>(D, l, src, ss, sp, pyr, (const AreaEntry*)h->d_tabs.p);
+    }
   }
   mark(1);
   k_fast_cells<<<dim3(D.totalCells, batch), FAST_THREADS, h->fastSmem, st>>>(
