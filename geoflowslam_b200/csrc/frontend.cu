@@ -140,14 +140,15 @@ int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batc
   uint8_t* d_desc = (uint8_t*)f->d_desc.p;
   uint8_t* d_in = (uint8_t*)f->d_in.p;
   const bool pinned = is_pinned_host(imgs) && is_pinned_host(out_kp) && is_pinned_host(out_desc);
-  f->chunk = std::max(64, div_up(batch, 4));  // 4 chunks: enough overlap, kernels stay large
+  f->chunk = std::max(64, div_up(batch, 4));  // large chunks keep the kernels efficient ...
+  const int firstChunk = std::max(32, batch / 16);  // ... but only the first H2D is exposed: keep that one short
   if (pinned && batch > f->chunk) {
     // ---- pipelined: chunked H2D on a copy stream, kernels on the caller's stream, D2H on a third
     if (!f->copyStream) {
       GFS_CUDA(cudaStreamCreateWithFlags(&f->copyStream, cudaStreamNonBlocking));
       GFS_CUDA(cudaStreamCreateWithFlags(&f->outStream, cudaStreamNonBlocking));
     }
-    const int nChunks = div_up(batch, f->chunk);
+    const int nChunks = 1 + div_up(batch - firstChunk, f->chunk);
     while ((int)f->evIn.size() < nChunks) {
       cudaEvent_t a, b2;
       GFS_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -160,7 +161,8 @@ int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batc
     GFS_CUDA(cudaStreamWaitEvent(f->copyStream, f->evDone[0], 0));
     GFS_CUDA(cudaStreamWaitEvent(f->outStream, f->evDone[0], 0));
     for (int c = 0; c < nChunks; c++) {
-      const size_t b0 = (size_t)c * f->chunk, nb = std::min<size_t>(f->chunk, B - b0);
+      const size_t b0 = c == 0 ? 0 : (size_t)firstChunk + (size_t)(c - 1) * f->chunk;
+      const size_t nb = c == 0 ? (size_t)firstChunk : std::min<size_t>(f->chunk, B - b0);
       if (img_stride == (size_t)pitch * h_img) {
         GFS_CUDA(cudaMemcpy2DAsync(d_in + b0 * dstride, dpitch, imgs + b0 * img_stride, pitch, w, (size_t)h_img * nb,
                                    cudaMemcpyHostToDevice, f->copyStream));

@@ -327,6 +327,9 @@ static int launch_gms(cudaStream_t st, const GfsKeyPoint* kp1, const int* n1, co
   return GFS_OK;
 }
 
+// match_umma.cu
+int launch_bf_hamming_umma(cudaStream_t st, const uint8_t* d_dq, const int* d_nq, const uint8_t* d_dt, const int* d_nt,
+                           int pairs, int stride, int* d_out_idx, int* d_out_dist);
 }  // namespace gfs
 
 using namespace gfs;
@@ -337,6 +340,13 @@ int gfs_match_bf_hamming_batch_device(void* stream, const uint8_t* d_dq, const i
                                       const int* d_nt, int pairs, int stride, int* d_out_idx, int* d_out_dist) {
   GFS_REQUIRE(d_dq && d_nq && d_dt && d_nt && d_out_idx && d_out_dist, GFS_ERR_INVALID, "null pointer");
   GFS_REQUIRE(pairs > 0 && stride > 0, GFS_ERR_INVALID, "bad pairs/stride");
+  // Default: tensor-core kernel (tcgen05.mma.kind::i8 on +-1 expanded descriptors, match_umma.cu).
+  // GFS_BF_POPC=1 / GFS_BF_MMA=1 select the two CUDA-core / legacy-MMA kernels below (kept for comparison;
+  // all three are bit-identical).
+  static int variant = -1;
+  if (variant < 0) variant = getenv("GFS_BF_MMA") ? 2 : (getenv("GFS_BF_POPC") ? 1 : 0);
+  if (variant == 0 && stride <= 65536)
+    return launch_bf_hamming_umma((cudaStream_t)stream, d_dq, d_nq, d_dt, d_nt, pairs, stride, d_out_idx, d_out_dist);
   const size_t smem = (size_t)((stride + 31) & ~31) * 32;
   GFS_REQUIRE(smem <= 200 * 1024, GFS_ERR_CAPACITY, "train set too large for shared memory (max 6400 rows)");
   static size_t configured = 0;
@@ -347,9 +357,7 @@ int gfs_match_bf_hamming_batch_device(void* stream, const uint8_t* d_dq, const i
   // GFS_BF_MMA=1 selects the binary-MMA kernel.  Measured on B200 (1023 pairs x 1000 x 1000): POPC kernel
   // 1.90 ms, b1-MMA kernel 2.73 ms -- sm_100a has no native b1 MMA, ptxas emulates it with IMMA.16832.U8
   // sequences, so the POPC-pipe kernel stays the default.
-  static int use_mma = -1;
-  if (use_mma < 0) use_mma = getenv("GFS_BF_MMA") ? 1 : 0;
-  if (use_mma) {
+  if (variant == 2) {
     static size_t configured2 = 0;
     if (smem > 48 * 1024 && smem > configured2) {
       GFS_CUDA(cudaFuncSetAttribute(k_bf_hamming_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
