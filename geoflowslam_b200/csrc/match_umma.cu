@@ -88,32 +88,41 @@ __device__ __forceinline__ uint32_t expand_nibble(uint32_t nib) {
   const uint32_t t = (nib * 0x00204081u) & 0x01010101u;
   return t * 0xFEu + 0x01010101u;
 }
-// Expand `rows` packed descriptors (32 B each, row r at g + r*32; rows >= limit re-read row limit-1)
-// into one operand tile.  A warp step covers 8 rows x 8 K-chunks of 16 B: every quarter-warp writes
-// one contiguous 128-B core matrix (conflict-free 128-bit stores).
-__device__ __forceinline__ void expand_tile(uint8_t* tile, const uint8_t* __restrict__ g, int row0, int limit, int worker,
-                                            int nWorkers) {
-  const int lane = worker & 31, w = worker >> 5, nW = nWorkers >> 5;
-  const int r8 = lane & 7, cp = lane >> 3;  // row in the 8-row group, pair of K-chunks
-  // steps: 16 row groups x 2 halves of the 8 chunk pairs
-  for (int step = w; step < 32; step += nW) {
-    const int grp = step >> 1, half = step & 1;
-    const int row = min(row0 + grp * 8 + r8, limit - 1);
-    const int pair = half * 4 + cp;  // K-chunks 2*pair, 2*pair+1 <-> descriptor bytes 4*pair .. 4*pair+3
-    const uint32_t bits = __ldg(reinterpret_cast<const uint32_t*>(g + (size_t)row * 32) + pair);
-    uint8_t* dst = tile + grp * UM_SBO + (2 * pair) * 128 + r8 * 16;
+// Expansion of `rows` packed descriptors (32 B each, row r at g + r*32; rows >= limit re-read row
+// limit-1) into one operand tile, in two halves so that the global loads of the next tile can be in
+// flight while the current one is written.  A warp step covers 8 rows x 8 K-chunks of 16 B: every
+// quarter-warp writes one contiguous 128-B core matrix (conflict-free 128-bit stores).  The bit ->
+// int8 expansion is arithmetic (a 256-entry shared-memory table was tried: its bank conflicts made the
+// shared-memory pipe the bottleneck).
+template <int NW>  // warps sharing the tile; 32 / NW steps per warp
+struct TileWords {
+  uint32_t w[32 / NW];
+  __device__ __forceinline__ void load(const uint8_t* __restrict__ g, int row0, int limit, int worker) {
+    const int lane = worker & 31, wp = worker >> 5;
+    const int r8 = lane & 7, cp = lane >> 3;
 #pragma unroll
-    for (int e = 0; e < 2; e++) {
-      const uint32_t h = (bits >> (16 * e)) & 0xffffu;
-      uint4 v;
-      v.x = expand_nibble(h & 15u);
-      v.y = expand_nibble((h >> 4) & 15u);
-      v.z = expand_nibble((h >> 8) & 15u);
-      v.w = expand_nibble(h >> 12);
-      *reinterpret_cast<uint4*>(dst + e * 128) = v;
+    for (int i = 0; i < 32 / NW; i++) {
+      const int step = wp + i * NW, grp = step >> 1, half = step & 1;
+      const int row = min(row0 + grp * 8 + r8, limit - 1);
+      w[i] = __ldg(reinterpret_cast<const uint32_t*>(g + (size_t)row * 32) + half * 4 + cp);
     }
   }
-}
+  __device__ __forceinline__ void store(uint8_t* tile, int worker) const {
+    const int lane = worker & 31, wp = worker >> 5;
+    const int r8 = lane & 7, cp = lane >> 3;
+#pragma unroll
+    for (int i = 0; i < 32 / NW; i++) {
+      const int step = wp + i * NW, grp = step >> 1, half = step & 1;
+      const int pair = half * 4 + cp;  // K-chunks 2*pair, 2*pair+1 <-> descriptor bytes 4*pair .. 4*pair+3
+      uint8_t* dst = tile + grp * UM_SBO + (2 * pair) * 128 + r8 * 16;
+      const uint32_t bits = w[i];
+      *reinterpret_cast<uint4*>(dst) = make_uint4(expand_nibble(bits & 15u), expand_nibble((bits >> 4) & 15u),
+                                                  expand_nibble((bits >> 8) & 15u), expand_nibble((bits >> 12) & 15u));
+      *reinterpret_cast<uint4*>(dst + 128) = make_uint4(expand_nibble((bits >> 16) & 15u), expand_nibble((bits >> 20) & 15u),
+                                                        expand_nibble((bits >> 24) & 15u), expand_nibble(bits >> 28));
+    }
+  }
+};
 
 __global__ void __launch_bounds__(UM_THREADS) k_bf_hamming_umma(const uint8_t* __restrict__ dq, const int* __restrict__ nq,
                                                                 const uint8_t* __restrict__ dt, const int* __restrict__ nt,
@@ -158,7 +167,11 @@ __global__ void __launch_bounds__(UM_THREADS) k_bf_hamming_umma(const uint8_t* _
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // query tile: expanded once by warps 0-7
-  if (warp < 8) expand_tile(sA, gq, q0, stride, tid, 256);
+  TileWords<8> aw;
+  if (warp < 8) {
+    aw.load(gq, q0, stride, tid);
+    aw.store(sA, tid);
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -167,12 +180,19 @@ __global__ void __launch_bounds__(UM_THREADS) k_bf_hamming_umma(const uint8_t* _
 
   if (warp >= 4 && warp < 8) {
     // ---- producers
+    // packed words of the next two tiles stay in flight while the current one is expanded
+    TileWords<4> t0, t1, t2;
+    t0.load(gt, 0, stride, tid - 128);
+    if (nTiles > 1) t1.load(gt, UM_N, stride, tid - 128);
     for (int j = 0; j < nTiles; j++) {
       const int s = j & 1;
+      if (j + 2 < nTiles) t2.load(gt, (j + 2) * UM_N, stride, tid - 128);
       mbar_wait(BAR(1, s), ((j >> 1) & 1) ^ 1);
-      expand_tile(sB + s * UM_TILE_BYTES, gt, j * UM_N, stride, tid - 128, 128);
+      t0.store(sB + s * UM_TILE_BYTES, tid - 128);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(BAR(0, s));
+      t0 = t1;
+      t1 = t2;
     }
   } else if (warp == 8) {
     // ---- MMA issuer
