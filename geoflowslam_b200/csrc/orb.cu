@@ -288,9 +288,16 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbDev P, const uin
     const uint32_t* s32 = (const uint32_t*)(src + (long long)iniY * pitch + (iniX - shift));
     const int p32 = pitch >> 2, rp32 = RP >> 2;
     uint32_t* d32 = (uint32_t*)sm;
-    for (int idx = tid; idx < nW * rh; idx += FAST_THREADS) {
-      const int y = idx / nW, x = idx - y * nW;
-      d32[y * rp32 + x] = __ldg(s32 + (long long)y * p32 + x);
+    if (nW <= 16) {
+      // 16 lanes per row, 8 rows per step: no index division
+      const int x = tid & 15;
+      if (x < nW)
+        for (int y = tid >> 4; y < rh; y += FAST_THREADS / 16) d32[y * rp32 + x] = __ldg(s32 + (long long)y * p32 + x);
+    } else {
+      for (int idx = tid; idx < nW * rh; idx += FAST_THREADS) {
+        const int y = idx / nW, x = idx - y * nW;
+        d32[y * rp32 + x] = __ldg(s32 + (long long)y * p32 + x);
+      }
     }
   } else {
     for (int idx = tid; idx < rw * rh; idx += FAST_THREADS) {
@@ -784,7 +791,7 @@ static const int OD_WARPS = 8;
 static const int PATCH_R = 21;                 // 18 (largest rounded rotated pattern radius) + 3 (blur taps)
 static const int PATCH_W = 2 * PATCH_R + 1;    // 43
 static const int RAW_PITCH = 52;               // 13 words per row: odd, so column walks hit distinct banks
-static const int HB_W = 37, HB_PITCH = 38;     // horizontally blurred rows, radius 18, u16
+static const int HB_W = 37, HB_PITCH = 40;     // horizontally blurred rows, radius 18, u16 (10 quads per row)
 
 // The warp stages the keypoint's 43x43 neighbourhood of the level image in shared memory (one
 // coalesced sweep), takes the IC_Angle moments from it, runs the horizontal pass of the 7x7 sigma-2
@@ -841,9 +848,10 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(OrbDev P, const u
       const uint32_t* s32 = (const uint32_t*)(src + (long long)y0 * pitch + (x0 - shift));
       const int p32 = pitch >> 2;
       uint32_t* d32 = (uint32_t*)raw;
-      for (int idx = lane; idx < PATCH_W * nW; idx += 32) {
-        const int r = idx / nW, c = idx - r * nW;
-        d32[r * (RAW_PITCH / 4) + c] = __ldg(s32 + (long long)r * p32 + c);
+      // 16 lanes per row (nW <= 12 of them active), two rows per step: no index division
+      const int c = lane & 15;
+      if (c < nW) {
+        for (int r = lane >> 4; r < PATCH_W; r += 2) d32[r * (RAW_PITCH / 4) + c] = __ldg(s32 + (long long)r * p32 + c);
       }
     }
   }
@@ -876,18 +884,24 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(OrbDev P, const u
   m01 = __reduce_add_sync(0xffffffffu, m01);
   const float angle = fast_atan2_deg(P, (float)m01, (float)m10);
 
-  // ---- horizontal blur pass: hb[r][c] = sum_k K[k] * raw[r][c + k], c in [0, 37); 86 half-rows over 32 lanes
+  // ---- horizontal blur pass: hb[r][c] = sum_k K[k] * raw[r][c + k], c in [0, 40) (37 used).  An item is
+  // four adjacent outputs: 4 aligned words of the raw row are realigned to the patch origin, every output
+  // is two 4-tap byte dot products (dp4a) with the kernel (18 34 48 56 | 48 34 18 0).
   uint16_t* hb = s_hb[warp];
-  for (int item = lane; item < 2 * PATCH_W; item += 32) {
-    const int r = item >> 1, half = item & 1;
-    const int c0 = half ? 19 : 0, n = half ? 18 : 19;
-    const uint8_t* q = rp + r * RAW_PITCH + c0;
-    int a = q[0], b = q[1], c = q[2], d = q[3], e = q[4], f = q[5];
-    uint16_t* o = hb + r * HB_PITCH + c0;
-    for (int k = 0; k < n; k++) {
-      const int g = q[k + 6];
-      o[k] = (uint16_t)(18 * (a + g) + 34 * (b + f) + 48 * (c + e) + 56 * d);
-      a = b; b = c; c = d; d = e; e = f; f = g;
+  {
+    const unsigned sh8 = 8u * (unsigned)shift;
+    const uint32_t* raw32 = (const uint32_t*)raw;
+    for (int item = lane; item < PATCH_W * (HB_PITCH / 4); item += 32) {
+      const int r = item / (HB_PITCH / 4), qd = item - r * (HB_PITCH / 4);
+      const uint32_t* w = raw32 + r * (RAW_PITCH / 4) + qd;
+      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+      const uint32_t s0 = __funnelshift_r(w0, w1, sh8), s1 = __funnelshift_r(w1, w2, sh8), s2 = __funnelshift_r(w2, w3, sh8);
+      const uint32_t a0 = s0, a1 = __byte_perm(s0, s1, 0x4321), a2 = __byte_perm(s0, s1, 0x5432), a3 = __byte_perm(s0, s1, 0x6543);
+      const uint32_t a4 = s1, a5 = __byte_perm(s1, s2, 0x4321), a6 = __byte_perm(s1, s2, 0x5432), a7 = __byte_perm(s1, s2, 0x6543);
+      const uint32_t kA = 18u | (34u << 8) | (48u << 16) | (56u << 24), kB = 48u | (34u << 8) | (18u << 16);
+      const unsigned o0 = __dp4a(a4, kB, __dp4a(a0, kA, 0u)), o1 = __dp4a(a5, kB, __dp4a(a1, kA, 0u));
+      const unsigned o2 = __dp4a(a6, kB, __dp4a(a2, kA, 0u)), o3 = __dp4a(a7, kB, __dp4a(a3, kA, 0u));
+      *reinterpret_cast<uint2*>(hb + r * HB_PITCH + 4 * qd) = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
     }
   }
   __syncwarp();
