@@ -6,8 +6,15 @@
 #include <algorithm>
 #include <vector>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
+namespace gfs {
+// orb.cu: one chunk of frames on scratch slots slot0 .. slot0+nb-1 of the extractor
+int orb_extract_slots(GfsOrb* h, cudaStream_t st, int slot0, const uint8_t* d_imgs, int nb, int w, int h_img, int pitch,
+                      size_t img_stride, GfsKeyPoint* d_kp, uint8_t* d_desc, int* d_n, int* d_mono);
+}
 using namespace gfs;
 
 struct GfsFrontend {
@@ -16,7 +23,8 @@ struct GfsFrontend {
   DevBuf d_in, d_kp, d_desc, d_n, d_idx, d_dist, d_inl, d_cnt;
   PinnedBuf h_in;
   // host-buffer path: H2D of chunk k+1 and D2H of chunk k-1 overlap the kernels of chunk k
-  cudaStream_t copyStream = nullptr, outStream = nullptr;
+  cudaStream_t copyStream = nullptr, outStream = nullptr, auxStream = nullptr;
+  cudaEvent_t evStart = nullptr;
   std::vector<cudaEvent_t> evIn, evDone;
   int chunk = 128;
   bool profiling = false;
@@ -52,6 +60,8 @@ int gfs_frontend_destroy(GfsFrontend* f) {
   for (cudaEvent_t e : f->evDone) cudaEventDestroy(e);
   if (f->copyStream) cudaStreamDestroy(f->copyStream);
   if (f->outStream) cudaStreamDestroy(f->outStream);
+  if (f->auxStream) cudaStreamDestroy(f->auxStream);
+  if (f->evStart) cudaEventDestroy(f->evStart);
   delete f;
   return GFS_OK;
 }
@@ -140,13 +150,19 @@ int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batc
   uint8_t* d_desc = (uint8_t*)f->d_desc.p;
   uint8_t* d_in = (uint8_t*)f->d_in.p;
   const bool pinned = is_pinned_host(imgs) && is_pinned_host(out_kp) && is_pinned_host(out_desc);
-  f->chunk = std::max(64, div_up(batch, 4));  // large chunks keep the kernels efficient ...
-  const int firstChunk = std::max(32, batch / 16);  // ... but only the first H2D is exposed: keep that one short
+  // H2D is faster than the kernels, so after the first chunk the copy stream stays ahead: only the first
+  // copy is exposed.  Chunks of batch/8 keep it short while the kernels still see >= 64 frames.
+  const char* ce = getenv("GFS_FRONTEND_CHUNKS");
+  const int nDiv = ce ? std::max(1, atoi(ce)) : 8;
+  f->chunk = std::max(64, div_up(batch, nDiv));
+  const int firstChunk = std::max(32, f->chunk / 2);
   if (pinned && batch > f->chunk) {
     // ---- pipelined: chunked H2D on a copy stream, kernels on the caller's stream, D2H on a third
     if (!f->copyStream) {
       GFS_CUDA(cudaStreamCreateWithFlags(&f->copyStream, cudaStreamNonBlocking));
       GFS_CUDA(cudaStreamCreateWithFlags(&f->outStream, cudaStreamNonBlocking));
+      GFS_CUDA(cudaStreamCreateWithFlags(&f->auxStream, cudaStreamNonBlocking));
+      GFS_CUDA(cudaEventCreateWithFlags(&f->evStart, cudaEventDisableTiming));
     }
     const int nChunks = 1 + div_up(batch - firstChunk, f->chunk);
     while ((int)f->evIn.size() < nChunks) {
@@ -156,13 +172,17 @@ int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batc
       f->evIn.push_back(a);
       f->evDone.push_back(b2);
     }
-    // the copy stream must not run ahead of work already queued on the caller's stream
-    GFS_CUDA(cudaEventRecord(f->evDone[0], st));
-    GFS_CUDA(cudaStreamWaitEvent(f->copyStream, f->evDone[0], 0));
-    GFS_CUDA(cudaStreamWaitEvent(f->outStream, f->evDone[0], 0));
+    // the side streams must not run ahead of work already queued on the caller's stream
+    GFS_CUDA(cudaEventRecord(f->evStart, st));
+    GFS_CUDA(cudaStreamWaitEvent(f->copyStream, f->evStart, 0));
+    GFS_CUDA(cudaStreamWaitEvent(f->outStream, f->evStart, 0));
+    GFS_CUDA(cudaStreamWaitEvent(f->auxStream, f->evStart, 0));
+    // chunks alternate between the caller's stream and a second compute stream: the latency-bound
+    // quadtree kernel of one chunk overlaps the throughput-bound kernels of the next
     for (int c = 0; c < nChunks; c++) {
       const size_t b0 = c == 0 ? 0 : (size_t)firstChunk + (size_t)(c - 1) * f->chunk;
       const size_t nb = c == 0 ? (size_t)firstChunk : std::min<size_t>(f->chunk, B - b0);
+      cudaStream_t cs = (c & 1) ? f->auxStream : st;
       if (img_stride == (size_t)pitch * h_img) {
         GFS_CUDA(cudaMemcpy2DAsync(d_in + b0 * dstride, dpitch, imgs + b0 * img_stride, pitch, w, (size_t)h_img * nb,
                                    cudaMemcpyHostToDevice, f->copyStream));
@@ -172,15 +192,16 @@ int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batc
                                      cudaMemcpyHostToDevice, f->copyStream));
       }
       GFS_CUDA(cudaEventRecord(f->evIn[c], f->copyStream));
-      GFS_CUDA(cudaStreamWaitEvent(st, f->evIn[c], 0));
-      rc = gfs_orb_extract_batch_device(f->orb, stream, d_in + b0 * dstride, (int)nb, w, h_img, (int)dpitch, dstride, 0, 0,
-                                        d_kp + b0 * s, d_desc + b0 * s * 32, d_n + b0, d_mono + b0);
+      GFS_CUDA(cudaStreamWaitEvent(cs, f->evIn[c], 0));
+      rc = orb_extract_slots(f->orb, cs, (int)b0, d_in + b0 * dstride, (int)nb, w, h_img, (int)dpitch, dstride, d_kp + b0 * s,
+                             d_desc + b0 * s * 32, d_n + b0, d_mono + b0);
       if (rc) return rc;
-      GFS_CUDA(cudaEventRecord(f->evDone[c], st));
+      GFS_CUDA(cudaEventRecord(f->evDone[c], cs));
       GFS_CUDA(cudaStreamWaitEvent(f->outStream, f->evDone[c], 0));
       GFS_CUDA(cudaMemcpyAsync(out_kp + b0 * s, d_kp + b0 * s, nb * s * sizeof(GfsKeyPoint), cudaMemcpyDeviceToHost, f->outStream));
       GFS_CUDA(cudaMemcpyAsync(out_desc + b0 * s * 32, d_desc + b0 * s * 32, nb * s * 32, cudaMemcpyDeviceToHost, f->outStream));
     }
+    for (int c = 1; c < nChunks; c += 2) GFS_CUDA(cudaStreamWaitEvent(st, f->evDone[c], 0));  // the matcher runs on `st`
     if (f->profiling) { cudaEventRecord(f->ev[0], st); cudaEventRecord(f->ev[1], st); }
     rc = gfs_match_bf_hamming_batch_device(stream, d_desc, d_n, d_desc + (size_t)s * 32, d_n + 1, batch - 1, s,
                                            (int*)f->d_idx.p, (int*)f->d_dist.p);

@@ -1021,6 +1021,8 @@ struct GfsOrb {
   bool profiling = false;
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // last batch (debug hooks)
+  cudaStream_t auxStream = nullptr;  // second stream of gfs_orb_extract_batch_device
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
   const uint8_t* lastImgs = nullptr;
   long long lastStride = 0;
   int lastPitch = 0, lastBatch = 0;
@@ -1308,6 +1310,9 @@ int gfs_orb_destroy(GfsOrb* h) {
   h->h_in.release(); h->h_okp.release(); h->h_odesc.release(); h->h_on.release();
   for (int i = 0; i < 7; i++)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->evFork) cudaEventDestroy(h->evFork);
+  if (h->evJoin) cudaEventDestroy(h->evJoin);
+  if (h->auxStream) cudaStreamDestroy(h->auxStream);
   delete h;
   return GFS_OK;
 }
@@ -1351,11 +1356,19 @@ int gfs_orb_launches_per_call(const GfsOrb* h, int lap0, int lap1) {
   return (h->nlevels - 1) + 1 + 1 + 1 + ((lap0 != 0 || lap1 != 0) ? 1 : 0);
 }
 
-static int orb_run_chunk(GfsOrb* h, cudaStream_t st, const uint8_t* d_imgs, int batch, int w, int ht, int pitch,
+// Frames of the chunk use scratch slots slot0 .. slot0+batch-1 of the handle, so chunks with disjoint
+// slot ranges may run concurrently on different streams.
+static int orb_run_chunk(GfsOrb* h, cudaStream_t st, int slot0, const uint8_t* d_imgs, int batch, int w, int ht, int pitch,
                          size_t img_stride, int lap0, int lap1, GfsKeyPoint* d_kp, uint8_t* d_desc, int* d_n,
                          int* d_mono) {
   const OrbDev& D = h->dev;
-  uint8_t* pyr = (uint8_t*)h->d_pyr.p;
+  uint8_t* pyr = (uint8_t*)h->d_pyr.p + (size_t)slot0 * D.pyrStride;
+  uint32_t* cellKeys = (uint32_t*)h->d_cellKeys.p + (size_t)slot0 * D.totalCells * D.cellCap;
+  int* cellCount = (int*)h->d_cellCount.p + (size_t)slot0 * D.totalCells;
+  uint32_t* keysA = (uint32_t*)h->d_keysA.p + (size_t)slot0 * D.keysPerFrame;
+  uint32_t* keysB = (uint32_t*)h->d_keysB.p + (size_t)slot0 * D.keysPerFrame;
+  uint32_t* selKeys = (uint32_t*)h->d_sel.p + (size_t)slot0 * D.selPerFrame;
+  int* selCount = (int*)h->d_selCount.p + (size_t)slot0 * D.nlevels;
   auto mark = [&](int i) { if (h->profiling) cudaEventRecord(h->ev[i], st); };
   mark(0);
   for (int l = 1; l < h->nlevels; l++) {
@@ -1374,11 +1387,10 @@ static int orb_run_chunk(GfsOrb* h, cudaStream_t st, const uint8_t* d_imgs, int 
   }
   mark(1);
   k_fast_cells<<<dim3(D.totalCells, batch), FAST_THREADS, h->fastSmem, st>>>(
-      D, d_imgs, (long long)img_stride, pitch, pyr, (uint32_t*)h->d_cellKeys.p, (int*)h->d_cellCount.p);
+      D, d_imgs, (long long)img_stride, pitch, pyr, cellKeys, cellCount);
   mark(2);
   k_octree<<<div_up(batch * h->nlevels, OCT_WARPS), OCT_WARPS * 32, h->octSmem, st>>>(
-      D, batch, (const uint32_t*)h->d_cellKeys.p, (const int*)h->d_cellCount.p, (uint32_t*)h->d_keysA.p,
-      (uint32_t*)h->d_keysB.p, (uint32_t*)h->d_sel.p, (int*)h->d_selCount.p, (int*)h->d_status.p);
+      D, batch, cellKeys, cellCount, keysA, keysB, selKeys, selCount, (int*)h->d_status.p);
   mark(3);
   mark(4);  // (the 7x7 blur is fused into k_orient_desc; k_blur7 only serves gfs_orb_get_level)
   const bool lapping = (lap0 != 0 || lap1 != 0);
@@ -1388,23 +1400,40 @@ static int orb_run_chunk(GfsOrb* h, cudaStream_t st, const uint8_t* d_imgs, int 
     int rc;
     if ((rc = h->d_tkp.reserve((size_t)h->maxBatch * D.kpStride * sizeof(GfsKeyPoint)))) return rc;
     if ((rc = h->d_tdesc.reserve((size_t)h->maxBatch * D.kpStride * 32))) return rc;
-    kpDst = (GfsKeyPoint*)h->d_tkp.p;
-    descDst = (uint8_t*)h->d_tdesc.p;
+    kpDst = (GfsKeyPoint*)h->d_tkp.p + (size_t)slot0 * D.kpStride;
+    descDst = (uint8_t*)h->d_tdesc.p + (size_t)slot0 * D.kpStride * 32;
   }
   k_orient_desc<<<dim3(div_up(D.selPerFrame, OD_WARPS), batch), OD_WARPS * 32, 0, st>>>(
-      D, d_imgs, (long long)img_stride, pitch, pyr, (const uint4*)h->d_pattern.p, (const uint32_t*)h->d_sel.p,
-      (const int*)h->d_selCount.p, kpDst, descDst, d_n, d_mono);
+      D, d_imgs, (long long)img_stride, pitch, pyr, (const uint4*)h->d_pattern.p, selKeys, selCount, kpDst, descDst, d_n,
+      d_mono);
   mark(5);
   if (lapping)
     k_pack_lapping<<<batch, 1024, 0, st>>>(D.kpStride, lap0, lap1, kpDst, descDst, d_kp, d_desc, d_n, d_mono);
   mark(6);
   GFS_CUDA(cudaGetLastError());
-  h->lastImgs = d_imgs;
-  h->lastStride = (long long)img_stride;
-  h->lastPitch = pitch;
-  h->lastBatch = batch;
+  if (slot0 == 0) {
+    h->lastImgs = d_imgs;
+    h->lastStride = (long long)img_stride;
+    h->lastPitch = pitch;
+  }
+  h->lastBatch = slot0 + batch;
   return GFS_OK;
 }
+
+// internal entry used by the front-end pipeline (frontend.cu): one chunk on the caller's stream, scratch
+// slots slot0 .. slot0+nb-1
+extern "C++" {
+namespace gfs {
+int orb_extract_slots(GfsOrb* h, cudaStream_t st, int slot0, const uint8_t* d_imgs, int nb, int w, int h_img, int pitch,
+                      size_t img_stride, GfsKeyPoint* d_kp, uint8_t* d_desc, int* d_n, int* d_mono) {
+  GFS_REQUIRE(h && slot0 >= 0 && nb > 0 && slot0 + nb <= h->maxBatch, GFS_ERR_CAPACITY, "slot range exceeds max_batch");
+  GFS_REQUIRE(w <= h->maxW && h_img <= h->maxH, GFS_ERR_CAPACITY, "image larger than the handle's max_w/max_h");
+  int rc = orb_set_geometry(h, w, h_img);
+  if (rc) return rc;
+  return orb_run_chunk(h, st, slot0, d_imgs, nb, w, h_img, pitch, img_stride, 0, 0, d_kp, d_desc, d_n, d_mono);
+}
+}  // namespace gfs
+}  // extern "C++"
 
 int gfs_orb_extract_batch_device(GfsOrb* h, void* stream, const uint8_t* d_imgs, int batch, int w, int h_img,
                                  int pitch, size_t img_stride, int lap0, int lap1, GfsKeyPoint* d_out_kp,
@@ -1418,9 +1447,31 @@ int gfs_orb_extract_batch_device(GfsOrb* h, void* stream, const uint8_t* d_imgs,
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int ks = h->dev.kpStride;
+  if (!h->profiling && batch >= 128 && batch <= h->maxBatch) {
+    // Two halves on two streams: the latency-bound quadtree kernel of one half (one warp per frame and
+    // level) overlaps the throughput-bound kernels of the other.
+    if (!h->auxStream) {
+      GFS_CUDA(cudaStreamCreateWithFlags(&h->auxStream, cudaStreamNonBlocking));
+      GFS_CUDA(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+      GFS_CUDA(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
+    }
+    const int n0 = batch / 2, n1 = batch - n0;
+    GFS_CUDA(cudaEventRecord(h->evFork, st));
+    GFS_CUDA(cudaStreamWaitEvent(h->auxStream, h->evFork, 0));
+    rc = orb_run_chunk(h, st, 0, d_imgs, n0, w, h_img, pitch, img_stride, lap0, lap1, d_out_kp, d_out_desc, d_out_n,
+                       d_out_mono);
+    if (rc) return rc;
+    rc = orb_run_chunk(h, h->auxStream, n0, d_imgs + (size_t)n0 * img_stride, n1, w, h_img, pitch, img_stride, lap0, lap1,
+                       d_out_kp + (size_t)n0 * ks, d_out_desc + (size_t)n0 * ks * 32, d_out_n + n0, d_out_mono + n0);
+    if (rc) return rc;
+    GFS_CUDA(cudaEventRecord(h->evJoin, h->auxStream));
+    GFS_CUDA(cudaStreamWaitEvent(st, h->evJoin, 0));
+    h->lastImgs = d_imgs;
+    return GFS_OK;
+  }
   for (int b0 = 0; b0 < batch; b0 += h->maxBatch) {
     const int nb = std::min(h->maxBatch, batch - b0);
-    rc = orb_run_chunk(h, st, d_imgs + (size_t)b0 * img_stride, nb, w, h_img, pitch, img_stride, lap0, lap1,
+    rc = orb_run_chunk(h, st, 0, d_imgs + (size_t)b0 * img_stride, nb, w, h_img, pitch, img_stride, lap0, lap1,
                        d_out_kp + (size_t)b0 * ks, d_out_desc + (size_t)b0 * ks * 32, d_out_n + b0, d_out_mono + b0);
     if (rc) return rc;
   }
