@@ -293,11 +293,16 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
     top = max(prof, key=prof.get)
-    cand_per_frame = 3400.0  # measured mean FAST candidates/frame on this workload (profiles/r01_stage_stats.md)
+    cand_per_frame = 3400.0  # measured mean FAST candidates/frame on this workload
     alg = algorithmic_bytes(top, B if top not in ("bf_hamming", "gms") else B - 1, mean_kp, cand_per_frame)
     achieved = alg / (prof[top] / 1e3) / 1e9
+    # DRAM traffic per frame of the dominant kernels from the committed `ncu --set full` captures
+    # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r01_summary.md), scaled to this launch
+    ncu_traffic_per_frame = {"fast_cells": (113.197056e6 + 5.351680e6) / 128}
+    traffic = ncu_traffic_per_frame[top] * B if top in ncu_traffic_per_frame else None
     roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "ms_per_launch_group": prof[top], "peak_source": peak_src,
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": "ncu capture profiles/r01_final_k_fast_cells_ncu_details.txt" if traffic else None,
+            "algorithmic_bytes": alg, "ms_per_launch_group": prof[top], "peak_source": peak_src,
             "stage_ms": prof}
 
     cpu = None
