@@ -6,3 +6,4 @@ from .orb import ORBextractor  # noqa: F401
 from .frontend import TrackingFrontend  # noqa: F401
 from .gicp import RegistrationGICP  # noqa: F401
 from .optimizer import Optimizer  # noqa: F401
+from .pose import PoseOptimizer  # noqa: F401

@@ -350,3 +350,56 @@ def ba_problem(seed=3000, n_kf=20, n_points=3000, obs_per_point=5, kf_dt=0.5, im
         in_kf1=in_kf1, in_kf2=in_kf2, in_pre=pre, in_downweight=down,
         truth=dict(Rwb=np.array([Rwb_t[c] for c in order]), twb=np.array([twb_t[c] for c in order]), pts=pts,
                    vel=np.array([vel_t[c] for c in order]), bg=bg_true, ba=ba_true))
+
+
+# ------------------------------------------------------------------------------------------------
+# PoseOptimization problem: one frame, ~400 map-point observations (mostly
+# RGB-D "stereo" observations, some monocular), a few gross outliers, pose prior off by ~1 deg / 3 cm.
+# ------------------------------------------------------------------------------------------------
+def _quat_from_R(R):
+    """rotation matrix -> unit quaternion (w, x, y, z), w >= 0"""
+    t = np.trace(R)
+    if t > 0:
+        s = np.sqrt(t + 1.0) * 2
+        q = np.array([0.25 * s, (R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s])
+    else:
+        i = int(np.argmax(np.diag(R)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0) * 2
+        v = np.zeros(3)
+        v[i] = 0.25 * s
+        v[j] = (R[j, i] + R[i, j]) / s
+        v[k] = (R[k, i] + R[i, k]) / s
+        q = np.array([(R[k, j] - R[j, k]) / s, v[0], v[1], v[2]])
+    q = q / np.linalg.norm(q)
+    return q if q[0] >= 0 else -q
+
+
+def pose_problem(seed=5000, n_obs=400, outlier_frac=0.1, mono_frac=0.2, rot_deg=1.0, trans=0.03, w=640, h=480):
+    """-> dict(n_obs, q_wxyz f32, t f32, fx.., bf, Xw f64 (n,3), uvr f32 (n,3), inv_sigma2 f32 (n), truth...)"""
+    rng = np.random.default_rng(seed)
+    cam = G1_CAM
+    R_true = _rot(np.deg2rad(rng.uniform(-20, 20, 3)))
+    t_true = rng.uniform(-1, 1, 3)
+    u = rng.uniform(20, w - 20, n_obs)
+    v = rng.uniform(20, h - 20, n_obs)
+    z = rng.uniform(0.6, 8.0, n_obs)
+    Xc = np.stack([(u - cam["cx"]) / cam["fx"] * z, (v - cam["cy"]) / cam["fy"] * z, z], 1)
+    Xw = (Xc - t_true) @ R_true  # Xc = R Xw + t
+    octave = rng.integers(0, 8, n_obs)
+    sigma = 1.2 ** octave
+    uu = u + rng.normal(0, 1, n_obs) * sigma * 0.7
+    vv = v + rng.normal(0, 1, n_obs) * sigma * 0.7
+    ur = uu - cam["bf"] / z + rng.normal(0, 0.3, n_obs)
+    bad = rng.random(n_obs) < outlier_frac
+    uu[bad] += rng.uniform(8, 60, bad.sum()) * rng.choice([-1, 1], bad.sum())
+    vv[bad] += rng.uniform(8, 60, bad.sum()) * rng.choice([-1, 1], bad.sum())
+    mono = rng.random(n_obs) < mono_frac
+    ur[mono] = -1.0
+    R0 = _rot(np.deg2rad(rng.uniform(-rot_deg, rot_deg, 3))) @ R_true
+    t0 = t_true + rng.uniform(-trans, trans, 3)
+    return dict(n_obs=n_obs, q_wxyz=_quat_from_R(R0).astype(np.float32), t=t0.astype(np.float32),
+                fx=np.float32(cam["fx"]), fy=np.float32(cam["fy"]), cx=np.float32(cam["cx"]), cy=np.float32(cam["cy"]),
+                bf=np.float32(cam["bf"]), Xw=np.ascontiguousarray(Xw, np.float64),
+                uvr=np.ascontiguousarray(np.stack([uu, vv, ur], 1), np.float32),
+                inv_sigma2=(1.0 / sigma ** 2).astype(np.float32), truth_R=R_true, truth_t=t_true, truth_bad=bad)

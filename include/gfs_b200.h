@@ -308,6 +308,43 @@ int gfs_ba_last_launches(const GfsBa* h);
 typedef int (*GfsAllReduceFn)(double* device_buf, int count, void* user);
 int gfs_ba_set_partition(GfsBa* h, int rank, int world, GfsAllReduceFn allreduce, void* user);
 
+/* ------------------------------------------------------------------------------------------------
+ * Motion-only bundle adjustment of the tracking thread.
+ * Replaces the g2o block of Optimizer::PoseOptimization (reference include/Optimizer.h:62-65,
+ * src/Optimizer.cc:763-1099): one VertexSE3Expmap, EdgeSE3ProjectXYZOnlyPose (monocular, pinhole)
+ * and g2o::EdgeStereoSE3ProjectXYZOnlyPose (stereo / RGB-D) edges with Huber kernels, 4 rounds of
+ * 10 Levenberg iterations (dense 6x6 LDLT) each restarted from the frame's pose, chi2 classification
+ * after every round (5.991 / 7.815), outliers moved to level 1, kernels removed after the third round.
+ * The fork does not write the optimised pose back (the SetPose calls are commented out, :1086-1097):
+ * the results the caller consumes are mvbOutlier, the average reprojection error and the inlier count.
+ * Observations are the frame's features with a MapPoint, in feature order.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct GfsPoseProblem {
+  int n_obs;               /* nInitialCorrespondences */
+  float q_wxyz[4], t[3];   /* pFrame->GetPose(): unit quaternion (w, x, y, z) and translation of Tcw */
+  float fx, fy, cx, cy, bf;/* Frame::fx, fy, cx, cy, mbf = pinhole parameters */
+  const double* Xw;        /* [n_obs][3] pMP->GetWorldPos().cast<double>() */
+  const float* uvr;        /* [n_obs][3] kpUn.pt.x, kpUn.pt.y, mvuRight (< 0: monocular observation) */
+  const float* inv_sigma2; /* [n_obs] mvInvLevelSigma2[kpUn.octave] */
+} GfsPoseProblem;
+typedef struct GfsPoseResult {
+  int n_inliers;           /* return value: nInitialCorrespondences - nBad (0 when n_obs < 3) */
+  int n_bad, n_good;       /* nBad of the last round; nGood accumulates over the rounds as the reference's does */
+  float avg_reproj_error;  /* SetFrame2FrameReprojError / SetFrame2MapReprojError value of the last round */
+  int rounds_done;
+  int lm_iterations[4];    /* Levenberg iterations g2o ran in each round */
+  double q_wxyz[4], t[3];  /* vSE3_recov->estimate() */
+  uint8_t* outlier;        /* [n_obs] mvbOutlier */
+  float* chi2;             /* [n_obs] chi2 of the last round (may be NULL) */
+} GfsPoseResult;
+typedef struct GfsPose GfsPose;
+int gfs_pose_create(int max_obs, int max_batch, GfsPose** out);
+int gfs_pose_destroy(GfsPose* h);
+/* Host pointers inside the structs; one CUDA block per frame, the whole optimisation in one launch. */
+int gfs_pose_optimize_batch(GfsPose* h, void* stream, const GfsPoseProblem* problems, int batch, GfsPoseResult* results);
+int gfs_pose_optimize(GfsPose* h, void* stream, const GfsPoseProblem* problem, GfsPoseResult* result);
+int gfs_pose_last_launches(const GfsPose* h);
+
 #ifdef __cplusplus
 }
 #endif

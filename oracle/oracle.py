@@ -432,3 +432,76 @@ def depth_to_cloud(depth, stride, fx, fy, cx, cy):
     out = np.zeros((cap, 4), np.float32)
     n = lib().gfo_depth_to_cloud(_p(depth), w, h, int(stride), fx, fy, cx, cy, _p(out), cap)
     return out[:n].copy()
+
+
+# ------------------------------------------------------------------------------ PoseOptimization
+class PoseProblem(C.Structure):  # mirrors GfsPoseProblem (include/gfs_b200.h)
+    _fields_ = [("n_obs", C.c_int), ("q_wxyz", C.c_float * 4), ("t", C.c_float * 3), ("fx", C.c_float), ("fy", C.c_float),
+                ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float), ("Xw", dp), ("uvr", fp), ("inv_sigma2", fp)]
+
+
+class PoseResult(C.Structure):  # mirrors GfsPoseResult
+    _fields_ = [("n_inliers", C.c_int), ("n_bad", C.c_int), ("n_good", C.c_int), ("avg_reproj_error", C.c_float),
+                ("rounds_done", C.c_int), ("lm_iterations", C.c_int * 4), ("q_wxyz", C.c_double * 4), ("t", C.c_double * 3),
+                ("outlier", bp_), ("chi2", fp)]
+
+
+def pose_pack(prob):
+    P = PoseProblem()
+    n = int(prob["n_obs"])
+    P.n_obs = n
+    P.q_wxyz = (C.c_float * 4)(*np.asarray(prob["q_wxyz"], np.float32))
+    P.t = (C.c_float * 3)(*np.asarray(prob["t"], np.float32))
+    for k in ("fx", "fy", "cx", "cy", "bf"):
+        setattr(P, k, float(np.float32(prob[k])))
+    keep = [np.ascontiguousarray(prob["Xw"], np.float64).reshape(-1, 3), np.ascontiguousarray(prob["uvr"], np.float32).reshape(-1, 3),
+            np.ascontiguousarray(prob["inv_sigma2"], np.float32).reshape(-1)]
+    P.Xw, P.uvr, P.inv_sigma2 = keep[0].ctypes.data_as(dp), keep[1].ctypes.data_as(fp), keep[2].ctypes.data_as(fp)
+    return P, keep
+
+
+def _bind_pose(L):
+    L.gfo_pose_optimize.argtypes = [C.POINTER(PoseProblem), C.POINTER(PoseResult)]
+    L.gfo_pose_edge.restype = C.c_int
+    L.gfo_pose_edge.argtypes = [C.POINTER(PoseProblem), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.gfo_pose_oplus.argtypes = [C.c_void_p] * 5
+    L.gfo_eigen_ldlt_solve.restype = C.c_int
+    L.gfo_eigen_ldlt_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+
+
+_LATE_BINDERS.append(("gfo_pose_optimize", _bind_pose))
+
+
+def pose_optimize(prob):
+    """Optimizer::PoseOptimization -> dict(n_inliers, outlier, chi2, avg_reproj_error, q_wxyz, t, ...)"""
+    P, keep = pose_pack(prob)
+    n = int(prob["n_obs"])
+    R = PoseResult()
+    outl, chi2 = np.zeros(max(n, 1), np.uint8), np.zeros(max(n, 1), np.float32)
+    R.outlier, R.chi2 = outl.ctypes.data_as(bp_), chi2.ctypes.data_as(fp)
+    lib().gfo_pose_optimize(C.byref(P), C.byref(R))
+    return dict(n_inliers=R.n_inliers, n_bad=R.n_bad, n_good=R.n_good, avg_reproj_error=float(R.avg_reproj_error),
+                rounds_done=R.rounds_done, lm_iterations=list(R.lm_iterations), q_wxyz=np.array(R.q_wxyz), t=np.array(R.t),
+                outlier=outl[:n].astype(bool), chi2=chi2[:n].copy())
+
+
+def pose_edge(prob, q_wxyz, t, e):
+    P, keep = pose_pack(prob)
+    q = np.ascontiguousarray(q_wxyz, np.float64); tt = np.ascontiguousarray(t, np.float64)
+    err = np.zeros(3); J = np.zeros(18)
+    d = lib().gfo_pose_edge(C.byref(P), _p(q), _p(tt), int(e), _p(err), _p(J))
+    return err[:d].copy(), J[:6 * d].reshape(d, 6).copy()
+
+
+def pose_oplus(q_wxyz, t, u6):
+    q = np.ascontiguousarray(q_wxyz, np.float64); tt = np.ascontiguousarray(t, np.float64); u = np.ascontiguousarray(u6, np.float64)
+    qo = np.zeros(4); to = np.zeros(3)
+    lib().gfo_pose_oplus(_p(q), _p(tt), _p(u), _p(qo), _p(to))
+    return qo, to
+
+
+def eigen_ldlt_solve(H, b):
+    H = np.ascontiguousarray(H, np.float64); b = np.ascontiguousarray(b, np.float64)
+    x = np.zeros(len(b))
+    ok = lib().gfo_eigen_ldlt_solve(_p(H), _p(b), len(b), _p(x))
+    return bool(ok), x
