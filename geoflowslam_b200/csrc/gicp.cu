@@ -54,7 +54,7 @@ struct GicpDev {
   // per pair
   int* corr;                 // [pairs][nmax] target index of source point (-1: none)
   double* maha;              // [pairs][nmax][6]
-  double* partial;           // [pairs][nblk][RED_N]
+  double* partial;           // [pairs][nblk][warps per block][RED_N]
   double* partialE;          // [pairs][nblk]
   double* state;             // [pairs][LM_STATE]
   int* istate;               // [pairs][LM_ISTATE]
@@ -416,7 +416,7 @@ __device__ __forceinline__ bool box_covered(const int* box, const ShellQuery& q,
 // unvisited point can be closer than sqrt(max_r2) (bounded 1-NN for correspondences).
 static const int MAX_SHELL = 8;
 template <int K>
-__device__ void grid_knn(const Grid& g, const int* box, int nPts, double cell, double qx, double qy, double qz,
+__device__ bool grid_knn(const Grid& g, const int* box, int nPts, double cell, double qx, double qy, double qz,
                          double max_r2, KnnAcc<K>& acc, bool seeded = false) {
   if (!seeded) acc.init();
   const ShellQuery q = make_shell_query(cell, qx, qy, qz);
@@ -427,14 +427,45 @@ __device__ void grid_knn(const Grid& g, const int* box, int nPts, double cell, d
                 [&](int cs, int cn) { scan_cell<K>(g, cs, cn, qx, qy, qz, acc); });
     const double bound = (double)r * cell + q.margin;  // every unvisited point is farther than this
     const double b2 = bound * bound;
-    if (acc.found == K && acc.d[K - 1] <= b2) return;
-    if (max_r2 >= 0.0 && b2 >= max_r2) return;
-    if (box_covered(box, q, r)) return;
+    if (acc.found == K && acc.d[K - 1] <= b2) return true;
+    if (max_r2 >= 0.0 && b2 >= max_r2) return true;
+    if (box_covered(box, q, r)) return true;
   }
-  // far / sparse query: exact brute force over the cloud
-  acc.init();
-  for (int i = 0; i < nPts; i++) acc.push(i, sqdist3(g.pts + (size_t)i * 4, qx, qy, qz));
+  return false;  // far / sparse query: the caller finishes it by brute force over the cloud
 }
+
+// Exact k-NN of ONE query by the whole warp: every lane scans a 1/32 slice of the cloud (coalesced), the 32
+// sorted lists are merged by K rounds of warp-wide (distance, index) minima.  The result is returned in
+// `acc` of lane `dst`.  Used for the few sparse / far queries the shell search cannot finish: done by a single
+// lane it is 42k dependent iterations, the longest tail of the kernel.
+template <int K>
+__device__ void warp_brute_knn(const double* pts, int nPts, double qx, double qy, double qz, int dst, KnnAcc<K>& acc) {
+  const int lane = threadIdx.x & 31;
+  KnnAcc<K> loc;
+  loc.init();
+  for (int i = lane; i < nPts; i += 32) loc.push(i, sqdist3(pts + (size_t)i * 4, qx, qy, qz));
+  int found = 0;
+#pragma unroll
+  for (int r = 0; r < K; r++) {
+    double bd = loc.d[0];
+    int bi = loc.id[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    if (loc.id[0] == bi && bi != 0x7fffffff) {  // this lane held the minimum: pop it
+#pragma unroll
+      for (int k = 0; k + 1 < K; k++) { loc.d[k] = loc.d[k + 1]; loc.id[k] = loc.id[k + 1]; }
+      loc.d[K - 1] = DBL_MAX; loc.id[K - 1] = 0x7fffffff;
+    }
+    if (bi != 0x7fffffff) found = r + 1;
+    if (lane == dst) { acc.d[r] = bd; acc.id[r] = bi; }
+  }
+  if (lane == dst) acc.found = found;
+}
+
 
 // Exact 10-NN in two passes, shaped for SIMT.  Per shell the occupied cells that survive pruning are
 // first collected into a per-thread list in shared memory; the candidates of those cells are then
@@ -465,7 +496,7 @@ __device__ __forceinline__ void walk_cells(const unsigned* cells, int from, int 
   }
 }
 
-__device__ void knn10_two_pass(const Grid& g, const int* box, int nPts, double cell, double qx, double qy, double qz,
+__device__ bool knn10_two_pass(const Grid& g, const int* box, int nPts, double cell, double qx, double qy, double qz,
                                double* s_d, int* s_id, unsigned* s_cells, KnnAcc<KNN_K>& acc) {
   const ShellQuery q = make_shell_query(cell, qx, qy, qz);
   float top[KNN_K];
@@ -509,12 +540,10 @@ __device__ void knn10_two_pass(const Grid& g, const int* box, int nPts, double c
     });
     ok = cnt <= KNN_LIST;
   }
-  if (!ok) {
-    grid_knn<KNN_K>(g, box, nPts, cell, qx, qy, qz, -1.0, acc);
-    return;
-  }
+  if (!ok) return grid_knn<KNN_K>(g, box, nPts, cell, qx, qy, qz, -1.0, acc);
   acc.init();
   for (int j = 0; j < cnt; j++) acc.push(s_id[j * KNN_THREADS], s_d[j * KNN_THREADS]);
+  return true;
 }
 
 // ---- Eigen SelfAdjointEigenSolver<Matrix3d>::computeDirect restated (see oracle/gicp_oracle.cpp)
@@ -616,11 +645,25 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_cov(GicpDev D) {
   int* s_id = reinterpret_cast<int*>(s_cells + KNN_CELLS * KNN_THREADS);
   const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = D.nDown[c];
-  if (i >= n) return;
+  if (blockIdx.x * blockDim.x >= n) return;
   const Grid g = make_grid(D, c);
-  const double* q = g.pts + (size_t)i * 4;
+  const bool active = i < n;
+  const double* q = g.pts + (size_t)(active ? i : 0) * 4;
+  const double qx = q[0], qy = q[1], qz = q[2];
   KnnAcc<KNN_K> acc;
-  knn10_two_pass(g, D.cellBox + c * 6, n, D.cell, q[0], q[1], q[2], s_d + threadIdx.x, s_id + threadIdx.x, s_cells + threadIdx.x, acc);
+  bool finished = true;
+  if (active)
+    finished = knn10_two_pass(g, D.cellBox + c * 6, n, D.cell, qx, qy, qz, s_d + threadIdx.x, s_id + threadIdx.x,
+                              s_cells + threadIdx.x, acc);
+  // queries the shell search could not finish: the warp brute-forces them together, one at a time
+  unsigned need = __ballot_sync(0xffffffffu, active && !finished);
+  while (need) {
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    warp_brute_knn<KNN_K>(g.pts, n, __shfl_sync(0xffffffffu, qx, src), __shfl_sync(0xffffffffu, qy, src),
+                          __shfl_sync(0xffffffffu, qz, src), src, acc);
+  }
+  if (!active) return;
   double* out = D.cov + ((size_t)c * D.nmax + i) * 6;
   const int nf = acc.found;
   if (nf < 5) {
@@ -701,7 +744,11 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D, int iter) 
     // the pruning radius, the result is still the exact nearest neighbour
     const int prev = iter > 0 ? D.corr[(size_t)p * D.nmax + i] : -1;
     if (prev >= 0) nn.push(prev, sqdist3(g.pts + (size_t)prev * 4, q[0], q[1], q[2]));
-    grid_knn<1>(g, D.cellBox + ct * 6, D.nDown[ct], D.cell, q[0], q[1], q[2], max_d2 * 1.0000001, nn, true);
+    if (!grid_knn<1>(g, D.cellBox + ct * 6, D.nDown[ct], D.cell, q[0], q[1], q[2], max_d2 * 1.0000001, nn, true)) {
+      // unreachable while max_dist <= (MAX_SHELL + 1) cells; kept so the search stays exact for any setting
+      nn.init();
+      for (int t = 0; t < D.nDown[ct]; t++) nn.push(t, sqdist3(g.pts + (size_t)t * 4, q[0], q[1], q[2]));
+    }
     int tgt = -1;
     if (nn.found == 1 && !(nn.d[0] > max_d2)) tgt = nn.id[0];  // DistanceRejector: sq_dist > max_dist_sq
     D.corr[(size_t)p * D.nmax + i] = tgt;
@@ -758,7 +805,19 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D, int iter) 
       acc[28] = 1.0;
     }
   }
-  block_reduce_store<RED_N, LIN_THREADS>(acc, D.partial + ((size_t)p * D.nblk + blockIdx.x) * RED_N);
+  // per-warp partial sums (no block barrier: a warp whose lanes all found their neighbour quickly retires
+  // without waiting for a slow sibling); k_lm_begin adds them in a fixed order
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* out = D.partial + (((size_t)p * D.nblk + blockIdx.x) * (LIN_THREADS / 32) + warp) * RED_N;
+#pragma unroll
+    for (int k = 0; k < RED_N; k++) {
+      double x = acc[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (lane == 0) out[k] = x;
+    }
+  }
 }
 
 // GICPFactor::error with the stored correspondences / Mahalanobis matrices
@@ -878,21 +937,33 @@ __device__ void lm_trial(double* st) {
 }
 
 // one warp per pair: sum the partials in block order (lane v owns value v), start the first trial
-__global__ void __launch_bounds__(32) k_lm_begin(GicpDev D, int iter) {
-  const int p = blockIdx.x, lane = threadIdx.x;
+__global__ void __launch_bounds__(LIN_THREADS) k_lm_begin(GicpDev D, int iter) {
+  __shared__ double s_tot[RED_N];
+  const int p = blockIdx.x, tid = threadIdx.x;
   int* is = D.istate + p * LM_ISTATE;
   if (!is[I_ACTIVE]) return;
   double* st = D.state + (size_t)p * LM_STATE;
-  const int nb = (D.nDown[2 * p + 1] + LIN_THREADS - 1) / LIN_THREADS;
-  double s = 0;
-  if (lane < RED_N)
-    for (int b = 0; b < nb; b++) s += D.partial[((size_t)p * D.nblk + b) * RED_N + lane];
-  if (lane < 21) st[S_H + lane] = s;
-  else if (lane < 27) st[S_B + lane - 21] = s;
-  else if (lane == 27) st[S_E] = s;
-  else if (lane == 28) is[I_INL] = (int)(s + 0.5);
-  __syncwarp();
-  if (lane == 0) {
+  // fixed-order sum of the per-warp partials: thread t takes partials t, t+128, ...; then lanes, then warps
+  const int nw = ((D.nDown[2 * p + 1] + LIN_THREADS - 1) / LIN_THREADS) * (LIN_THREADS / 32);
+  double acc[RED_N];
+#pragma unroll
+  for (int k = 0; k < RED_N; k++) acc[k] = 0.0;
+  const double* part = D.partial + (size_t)p * D.nblk * (LIN_THREADS / 32) * RED_N;
+  for (int b = tid; b < nw; b += LIN_THREADS) {
+#pragma unroll
+    for (int k = 0; k < RED_N; k++) acc[k] += part[(size_t)b * RED_N + k];
+  }
+  block_reduce_store<RED_N, LIN_THREADS>(acc, s_tot);
+  __syncthreads();
+  if (tid < RED_N) {
+    const double s = s_tot[tid];
+    if (tid < 21) st[S_H + tid] = s;
+    else if (tid < 27) st[S_B + tid - 21] = s;
+    else if (tid == 27) st[S_E] = s;
+    else if (tid == 28) is[I_INL] = (int)(s + 0.5);
+  }
+  __syncthreads();
+  if (tid == 0) {
     is[I_ITER] = iter;
     is[I_TRIAL] = 0;
     is[I_SUCCESS] = 0;
@@ -1059,7 +1130,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   RES(b_rec, C * N * 32, rec, double*)
   RES(b_corr, P * N * 4, corr, int*)
   RES(b_maha, P * N * 72, maha, double*)
-  RES(b_partial, P * D.nblk * RED_N * 8, partial, double*)
+  RES(b_partial, P * D.nblk * (LIN_THREADS / 32) * RED_N * 8, partial, double*)
   RES(b_partialE, P * D.nblk * 8, partialE, double*)
   RES(b_state, P * LM_STATE * 8, state, double*)
   RES(b_istate, P * LM_ISTATE * 4, istate, int*)
@@ -1122,7 +1193,7 @@ int gfs_gicp_align_batch_device(GfsGicp* h, void* stream, const float* d_target,
   for (int it = 0; it < D.max_iter; it++) {
     GFS_CUDA(cudaMemsetAsync(D.counters, 0, 8, st));
     k_linearize<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D, it);
-    k_lm_begin<<<pairs, 32, 0, st>>>(D, it);
+    k_lm_begin<<<pairs, LIN_THREADS, 0, st>>>(D, it);
     h->launches += 2;
     for (int j = 0; j < 10; j++) {
       k_error<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D);
