@@ -137,7 +137,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = max(2 * cores, 32)
+    n = max(16 * cores, 64)  # ~1 s of wall per step on the host cores: a bounded sample of the 1024-frame batch
     frames = make_frames(n, 1000, min(cores, 16))
     for _ in range(args.warmup):
         cpu_frames_per_sec(frames[:max(cores, 8)], cores)
@@ -307,7 +307,9 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu:
-        ns = max(2 * cores, 32)
+        # bounded sample: a short probe sizes it to about 8 s of wall on all host cores (capped by the batch)
+        fps0, _ = cpu_frames_per_sec(frames[:min(B, max(2 * cores, 32))], cores)
+        ns = int(min(B, max(2 * cores, 32, fps0 * 8.0)))
         fps, dt = cpu_frames_per_sec(frames[:ns], cores)
         cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": "first %d frames + %d pairs of the same batch, %.1f s wall, %d worker threads" % (ns, ns - 1, dt, cores)}

@@ -71,6 +71,7 @@ SIGNATURES = {
     "gfs_gicp_align_batch_device": ([vp, vp, vp, vp, vp, vp, ci, ci, vp, vp], ci),
     "gfs_gicp_get_cloud": ([vp, vp, ci, vp, vp, ci, vp], ci),
     "gfs_gicp_last_launches": ([vp], ci),
+    "gfs_gicp_get_knn_stats": ([vp, vp, ci, vp, vp], ci),
     "gfs_ba_create": ([ci, ci, ci, ci, ci, C.POINTER(vp)], ci),
     "gfs_ba_destroy": ([vp], ci),
     "gfs_ba_solve_batch": ([vp, vp, vp, vp, ci], ci),

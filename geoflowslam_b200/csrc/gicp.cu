@@ -14,12 +14,13 @@
 //   k_voxel_mean       per-voxel mean in input order          (voxelgrid_sampling :23-78)
 //   k_knn_cov          exact 10-NN by expanding grid shells (KdTree::knn_search semantics: exact
 //                      k nearest) + covariance regularisation (normal_estimation.hpp:66-92)
-//   k_linearize        exact 1-NN within max_correspondence_distance, GICPFactor::linearize
-//                      (gicp_factor.hpp:34-73), block-reduced partial sums of H, b, e
+//   k_nn_corr          exact 1-NN within max_correspondence_distance (seeded with the previous correspondence)
+//   k_linearize        GICPFactor::linearize (gicp_factor.hpp:34-73), per-warp partial sums of H, b, e
 //   k_lm_begin / k_error / k_lm_decide              LevenbergMarquardtOptimizer (optimizer.hpp:83-148)
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -46,6 +47,7 @@ struct GicpDev {
   int* nIn;                  // [clouds] input point count
   int* nDown;                // [clouds] downsampled point count
   int* nCells;               // [clouds] occupied grid cells
+  int* nFall;                // [clouds] queries the cell-centric 10-NN kernel left to the per-query kernel
   int* cellBox;              // [clouds][6] min/max cell coordinate of the grid
   double* pts;               // [clouds][nmax][4]
   uint4* tab;                // [clouds][hsize] kNN grid slot {key lo, key hi, start, count}: one 16-byte probe
@@ -256,7 +258,10 @@ __global__ void __launch_bounds__(256) k_cell_pack(GicpDev D, int clouds) {
   if (i < (long long)clouds * D.hsize) {
     const unsigned long long k = D.keys[i];
     D.tab[i] = make_uint4((unsigned)k, (unsigned)(k >> 32), (unsigned)D.start[i], (unsigned)D.count[i]);
+    // occupied cells in first-occurrence order -> slot (the fill cursors are dead by now: reuse their storage)
+    if (k != KEY_EMPTY) D.cursor[(i / D.hsize) * D.hsize + D.rank[i]] = (int)(i % D.hsize);
   }
+  if (i < clouds) D.nFall[i] = 0;
   if (i < (long long)clouds * D.nmax) {
     const int c = (int)(i / D.nmax), m = (int)(i % D.nmax);
     if (m < D.nDown[c]) {
@@ -637,34 +642,8 @@ __device__ void eig3_direct(const double A[3][3], double V[3][3]) {
     for (int r = 0; r < 3; r++) V[r][k] = v[k][r];
 }
 
-// estimate_local_features<CovarianceSetter> (normal_estimation.hpp:66-92), K = 10
-__global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_cov(GicpDev D) {
-  extern __shared__ __align__(16) unsigned char s_knn[];
-  double* s_d = reinterpret_cast<double*>(s_knn);
-  unsigned* s_cells = reinterpret_cast<unsigned*>(s_d + KNN_LIST * KNN_THREADS);
-  int* s_id = reinterpret_cast<int*>(s_cells + KNN_CELLS * KNN_THREADS);
-  const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = D.nDown[c];
-  if (blockIdx.x * blockDim.x >= n) return;
-  const Grid g = make_grid(D, c);
-  const bool active = i < n;
-  const double* q = g.pts + (size_t)(active ? i : 0) * 4;
-  const double qx = q[0], qy = q[1], qz = q[2];
-  KnnAcc<KNN_K> acc;
-  bool finished = true;
-  if (active)
-    finished = knn10_two_pass(g, D.cellBox + c * 6, n, D.cell, qx, qy, qz, s_d + threadIdx.x, s_id + threadIdx.x,
-                              s_cells + threadIdx.x, acc);
-  // queries the shell search could not finish: the warp brute-forces them together, one at a time
-  unsigned need = __ballot_sync(0xffffffffu, active && !finished);
-  while (need) {
-    const int src = __ffs(need) - 1;
-    need &= need - 1;
-    warp_brute_knn<KNN_K>(g.pts, n, __shfl_sync(0xffffffffu, qx, src), __shfl_sync(0xffffffffu, qy, src),
-                          __shfl_sync(0xffffffffu, qz, src), src, acc);
-  }
-  if (!active) return;
-  double* out = D.cov + ((size_t)c * D.nmax + i) * 6;
+// CovarianceSetter (normal_estimation.hpp:66-92): regularised covariance of the k neighbours, in (distance, index) order
+__device__ void cov_from_knn(const Grid& g, const KnnAcc<KNN_K>& acc, double* out) {
   const int nf = acc.found;
   if (nf < 5) {
     out[0] = 1; out[1] = 0; out[2] = 0; out[3] = 1; out[4] = 0; out[5] = 1;
@@ -694,6 +673,183 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_cov(GicpDev D) {
   out[0] = R[0][0]; out[1] = R[0][1]; out[2] = R[0][2]; out[3] = R[1][1]; out[4] = R[1][2]; out[5] = R[2][2];
 }
 
+// estimate_local_features<CovarianceSetter>, one thread per query (shell search around the query).
+// use_list = 0: every point of the cloud; use_list = 1: only the queries k_knn_cov_cells handed over
+// (slotOf[] holds their point indices, nFall[] their number).
+__global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_cov(GicpDev D, int use_list) {
+  extern __shared__ __align__(16) unsigned char s_knn[];
+  double* s_d = reinterpret_cast<double*>(s_knn);
+  unsigned* s_cells = reinterpret_cast<unsigned*>(s_d + KNN_LIST * KNN_THREADS);
+  int* s_id = reinterpret_cast<int*>(s_cells + KNN_CELLS * KNN_THREADS);
+  const int c = blockIdx.y;
+  const int nPts = D.nDown[c];
+  const int n = use_list ? D.nFall[c] : nPts;
+  const int* list = D.slotOf + (size_t)c * D.nmax;
+  const Grid g = make_grid(D, c);
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const int t = base + threadIdx.x;
+    const bool active = t < n;
+    const int i = active ? (use_list ? list[t] : t) : 0;
+    const double* q = g.pts + (size_t)i * 4;
+    const double qx = q[0], qy = q[1], qz = q[2];
+    KnnAcc<KNN_K> acc;
+    bool finished = true;
+    if (active)
+      finished = knn10_two_pass(g, D.cellBox + c * 6, nPts, D.cell, qx, qy, qz, s_d + threadIdx.x, s_id + threadIdx.x,
+                                s_cells + threadIdx.x, acc);
+    // queries the shell search could not finish: the warp brute-forces them together, one at a time
+    unsigned need = __ballot_sync(0xffffffffu, active && !finished);
+    while (need) {
+      const int src = __ffs(need) - 1;
+      need &= need - 1;
+      warp_brute_knn<KNN_K>(g.pts, nPts, __shfl_sync(0xffffffffu, qx, src), __shfl_sync(0xffffffffu, qy, src),
+                            __shfl_sync(0xffffffffu, qz, src), src, acc);
+    }
+    if (active) cov_from_knn(g, acc, D.cov + ((size_t)c * D.nmax + i) * 6);
+  }
+}
+
+// ---- cell-centric exact 10-NN + covariance.
+// Eight lanes own one occupied grid cell.  They look its 26 neighbour cells up together (one hash probe
+// chain per lane and round instead of ~27 dependent chains per query), copy the records of the 3x3x3
+// block into shared memory once, and every lane then scans that list for one query of the cell: pass A
+// keeps the K smallest distances rounded UP to float in a branch-free min/max chain (radius rho >= the
+// true k-th distance), pass B remembers the positions of the candidates with d <= rho (one byte each, 16
+// packed in four registers), the exact (distance, index) selection runs once over those.  The block is
+// complete for a query when its k-th distance does not exceed cell + (distance to the nearest face of its
+// own cell); the other queries (sparse surroundings, overfull blocks, ties) go to k_knn_cov(use_list = 1).
+static const int KC_THREADS = 128;
+static const int KC_LANES = 8;
+static const int KC_CAP = 192;                        // candidates of one 3x3x3 block (positions fit a byte)
+static const int KC_STRIDE = KC_CAP * 28 + 8;         // per-group bytes; = 8 mod 128: groups start on different banks
+static const size_t KC_SMEM = (size_t)(KC_THREADS / KC_LANES) * KC_STRIDE;
+
+__global__ void __launch_bounds__(KC_THREADS) k_knn_cov_cells(GicpDev D) {
+  extern __shared__ __align__(16) unsigned char s_kc[];
+  const int c = blockIdx.y;
+  const int nCells = D.nCells[c];
+  const int grp = threadIdx.x / KC_LANES, gl = threadIdx.x % KC_LANES;
+  double* X = reinterpret_cast<double*>(s_kc + (size_t)grp * KC_STRIDE);
+  double* Y = X + KC_CAP;
+  double* Z = Y + KC_CAP;
+  int* I = reinterpret_cast<int*>(Z + KC_CAP);
+  const Grid g = make_grid(D, c);
+  const int* cellSlot = D.cursor + (size_t)c * D.hsize;
+  int* fall = D.slotOf + (size_t)c * D.nmax;
+  for (int cell0 = blockIdx.x * (KC_THREADS / KC_LANES); cell0 < nCells; cell0 += gridDim.x * (KC_THREADS / KC_LANES)) {
+    const int ci = cell0 + grp;
+    const bool have = ci < nCells;
+    int qs = 0, qn = 0;
+    int st[4] = {0, 0, 0, 0}, cn[4] = {0, 0, 0, 0};
+    if (have) {
+      const uint4 e = __ldg(&g.tab[cellSlot[ci]]);
+      const unsigned long long key = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
+      const int cx = (int)(key & 0x1fffff), cy = (int)((key >> 21) & 0x1fffff), cz = (int)((key >> 42) & 0x1fffff);
+      qs = (int)e.z; qn = (int)e.w;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int nb = gl + KC_LANES * k;
+        if (nb == 13) { st[k] = qs; cn[k] = qn; }
+        else if (nb < 27) {
+          int s0, n0;
+          if (grid_find(g, cx + nb % 3 - 1, cy + (nb / 3) % 3 - 1, cz + nb / 9 - 1, s0, n0)) { st[k] = s0; cn[k] = n0; }
+        }
+      }
+    }
+    // offsets of this lane's cells in the group's candidate list (exclusive scan over the 8 lanes, 4 rounds)
+    int off[4], total = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      int inc = cn[k];
+#pragma unroll
+      for (int o = 1; o < KC_LANES; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o, KC_LANES);
+        if (gl >= o) inc += t;
+      }
+      off[k] = total + inc - cn[k];
+      total += __shfl_sync(0xffffffffu, inc, KC_LANES - 1, KC_LANES);
+    }
+    const bool fits = total <= KC_CAP;
+    __syncwarp();  // the previous cell's scans are done before its list is overwritten
+    if (have && fits) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        for (int j = 0; j < cn[k]; j += 2) {
+          const size_t r0 = 2 * (size_t)(st[k] + j);
+          const bool two = j + 1 < cn[k];
+          const double2 a0 = __ldg(&g.rec[r0]), b0 = __ldg(&g.rec[r0 + 1]);
+          double2 a1 = a0, b1 = b0;
+          if (two) { a1 = __ldg(&g.rec[r0 + 2]); b1 = __ldg(&g.rec[r0 + 3]); }
+          const int o = off[k] + j;
+          X[o] = a0.x; Y[o] = a0.y; Z[o] = b0.x; I[o] = (int)__double_as_longlong(b0.y);
+          if (two) { X[o + 1] = a1.x; Y[o + 1] = a1.y; Z[o + 1] = b1.x; I[o + 1] = (int)__double_as_longlong(b1.y); }
+        }
+      }
+    }
+    __syncwarp();
+    const int home = __shfl_sync(0xffffffffu, off[1], 13 - KC_LANES, KC_LANES);  // nb 13 = lane 5, round 1
+    for (int q0 = 0; q0 < qn; q0 += KC_LANES) {
+      const int qi = q0 + gl;
+      if (qi >= qn) continue;
+      int pidx;
+      double qx, qy, qz;
+      if (fits) { qx = X[home + qi]; qy = Y[home + qi]; qz = Z[home + qi]; pidx = I[home + qi]; }
+      else {
+        const double2 a = __ldg(&g.rec[2 * (size_t)(qs + qi)]), b = __ldg(&g.rec[2 * (size_t)(qs + qi) + 1]);
+        qx = a.x; qy = a.y; qz = b.x; pidx = (int)__double_as_longlong(b.y);
+      }
+      bool ok = fits && total >= KNN_K;
+      unsigned w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+      int cnt = 0;
+      if (ok) {
+        float top[KNN_K];
+#pragma unroll
+        for (int i = 0; i < KNN_K; i++) top[i] = FLT_MAX;
+#pragma unroll 2
+        for (int j = 0; j < total; j++) {
+          const double dx = X[j] - qx, dy = Y[j] - qy, dz = Z[j] - qz;
+          float v = __double2float_ru(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz)), __dmul_rn(dy, dy)));
+#pragma unroll
+          for (int i = 0; i < KNN_K; i++) {
+            const float lo = fminf(top[i], v);
+            v = fmaxf(top[i], v);
+            top[i] = lo;
+          }
+        }
+        const ShellQuery sq = make_shell_query(D.cell, qx, qy, qz);
+        const double bound = D.cell + sq.margin;
+        const double rho = (double)top[KNN_K - 1];
+        ok = rho <= bound * bound;
+        if (ok) {
+          for (int j = 0; j < total; j++) {
+            const double dx = X[j] - qx, dy = Y[j] - qy, dz = Z[j] - qz;
+            const double dd = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz)), __dmul_rn(dy, dy));
+            if (dd <= rho) {
+              w3 = __funnelshift_l(w2, w3, 8); w2 = __funnelshift_l(w1, w2, 8); w1 = __funnelshift_l(w0, w1, 8);
+              w0 = (w0 << 8) | (unsigned)j;
+              cnt++;
+            }
+          }
+          ok = cnt <= 16;
+        }
+      }
+      if (!ok) {
+        fall[atomicAdd(&D.nFall[c], 1)] = pidx;
+        continue;
+      }
+      KnnAcc<KNN_K> acc;
+      acc.init();
+      for (int t = 0; t < cnt; t++) {
+        const int j = (int)(w0 & 0xffu);
+        w0 = __funnelshift_r(w0, w1, 8); w1 = __funnelshift_r(w1, w2, 8); w2 = __funnelshift_r(w2, w3, 8); w3 >>= 8;
+        const double dx = X[j] - qx, dy = Y[j] - qy, dz = Z[j] - qz;
+        acc.push(I[j], __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz)), __dmul_rn(dy, dy)));
+      }
+      cov_from_knn(g, acc, D.cov + ((size_t)c * D.nmax + pidx) * 6);
+    }
+  }
+}
+
 // ---- block reduction of NV doubles per thread into out[NV] (fixed order: lanes, then warps)
 template <int NV, int THREADS>
 __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* out) {
@@ -721,6 +877,72 @@ __device__ __forceinline__ void xform(const double* T, const double* p, double o
 }
 
 static const int LIN_THREADS = 128;
+
+// 1-NN of every transformed source point in the target cloud within max_correspondence_distance
+// (KdTree::nearest_neighbor_search + DistanceRejector, gicp_factor.hpp:40-48).  A kernel of its own: the
+// search is a chain of dependent loads (hash probe -> cell records) and wants many resident warps, the
+// linearisation is register-heavy arithmetic.  Candidates of a cell are fetched four at a time so four
+// record loads are in flight per lane.
+struct Nn1 {
+  double d;
+  int id;
+  __device__ __forceinline__ void push(int index, double dist) {
+    if (dist < d || (dist == d && index < id)) { d = dist; id = index; }
+  }
+};
+__device__ __forceinline__ void scan_cell_nn1(const Grid& g, int s, int n, double qx, double qy, double qz, Nn1& nn) {
+  for (int j = 0; j < n; j += 4) {
+    double2 a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const size_t r = 2 * (size_t)(s + min(j + u, n - 1));
+      a[u] = __ldg(&g.rec[r]); b[u] = __ldg(&g.rec[r + 1]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const double dx = a[u].x - qx, dy = a[u].y - qy, dz = b[u].x - qz;
+      nn.push((int)__double_as_longlong(b[u].y), __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz)), __dmul_rn(dy, dy)));
+    }
+  }
+}
+static const int NN_THREADS = 128;
+__global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr(GicpDev D, int iter) {
+  const int p = blockIdx.y;
+  if (!D.istate[p * LM_ISTATE + I_ACTIVE]) return;
+  const int ct = 2 * p, cs = 2 * p + 1;
+  const int i = blockIdx.x * NN_THREADS + threadIdx.x;
+  if (i >= D.nDown[cs]) return;
+  const double* T = D.state + (size_t)p * LM_STATE + S_T;
+  const double* ps = D.pts + ((size_t)cs * D.nmax + i) * 4;
+  double q[3];
+  xform(T, ps, q);
+  const Grid g = make_grid(D, ct);
+  const double max_d2 = D.max_dist * D.max_dist;
+  const double cap = max_d2 * 1.0000001;
+  Nn1 nn;
+  nn.d = DBL_MAX; nn.id = 0x7fffffff;
+  // the previous iteration's correspondence is a real target point: starting from it only tightens
+  // the pruning radius, the result is still the exact nearest neighbour
+  const int prev = iter > 0 ? D.corr[(size_t)p * D.nmax + i] : -1;
+  if (prev >= 0) nn.push(prev, sqdist3(g.pts + (size_t)prev * 4, q[0], q[1], q[2]));
+  const ShellQuery sq = make_shell_query(D.cell, q[0], q[1], q[2]);
+  const int* box = D.cellBox + ct * 6;
+  bool done = false;
+  for (int r = 0; r <= MAX_SHELL && !done; r++) {
+    visit_shell(g, box, sq, r, [&]() { return fmin(nn.d, cap); },
+                [&](int cs_, int cn_) { scan_cell_nn1(g, cs_, cn_, q[0], q[1], q[2], nn); });
+    const double bound = (double)r * D.cell + sq.margin;  // every unvisited point is farther than this
+    const double b2 = bound * bound;
+    done = nn.d <= b2 || b2 >= cap || box_covered(box, sq, r);
+  }
+  if (!done) {
+    // unreachable while max_dist <= (MAX_SHELL + 1) cells; kept so the search stays exact for any setting
+    nn.d = DBL_MAX; nn.id = 0x7fffffff;
+    for (int t = 0; t < D.nDown[ct]; t++) nn.push(t, sqdist3(g.pts + (size_t)t * 4, q[0], q[1], q[2]));
+  }
+  D.corr[(size_t)p * D.nmax + i] = (nn.id != 0x7fffffff && !(nn.d > max_d2)) ? nn.id : -1;  // DistanceRejector: sq_dist > max_dist_sq
+}
+
 // GICPFactor::linearize for every source point of every active pair + partial sums
 __global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D, int iter) {
   const int p = blockIdx.y;
@@ -737,21 +959,7 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D, int iter) 
     double q[3];
     xform(T, ps, q);
     const Grid g = make_grid(D, ct);
-    KnnAcc<1> nn;
-    nn.init();
-    const double max_d2 = D.max_dist * D.max_dist;
-    // the previous iteration's correspondence is a real target point: starting from it only tightens
-    // the pruning radius, the result is still the exact nearest neighbour
-    const int prev = iter > 0 ? D.corr[(size_t)p * D.nmax + i] : -1;
-    if (prev >= 0) nn.push(prev, sqdist3(g.pts + (size_t)prev * 4, q[0], q[1], q[2]));
-    if (!grid_knn<1>(g, D.cellBox + ct * 6, D.nDown[ct], D.cell, q[0], q[1], q[2], max_d2 * 1.0000001, nn, true)) {
-      // unreachable while max_dist <= (MAX_SHELL + 1) cells; kept so the search stays exact for any setting
-      nn.init();
-      for (int t = 0; t < D.nDown[ct]; t++) nn.push(t, sqdist3(g.pts + (size_t)t * 4, q[0], q[1], q[2]));
-    }
-    int tgt = -1;
-    if (nn.found == 1 && !(nn.d[0] > max_d2)) tgt = nn.id[0];  // DistanceRejector: sq_dist > max_dist_sq
-    D.corr[(size_t)p * D.nmax + i] = tgt;
+    const int tgt = D.corr[(size_t)p * D.nmax + i];
     if (tgt >= 0) {
       const double* cS = D.cov + ((size_t)cs * D.nmax + i) * 6;
       const double* cT = D.cov + ((size_t)ct * D.nmax + tgt) * 6;
@@ -1055,11 +1263,12 @@ using namespace gfs;
 struct GfsGicp {
   GicpDev dev;
   int maxPairs = 0;
-  DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_box, b_pts, b_cov, b_tab, b_rec,
+  DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_nFall, b_box, b_pts, b_cov, b_tab, b_rec,
       b_corr, b_maha, b_partial, b_partialE, b_state, b_istate, b_counters;
   DevBuf b_tgt, b_src, b_n, b_T0, b_res;
   PinnedBuf h_counters;
   int launches = 0;
+  bool cellKnn = false;  // GFS_GICP_KNN_CELLS=1: cell-centric 10-NN kernel first (same results)
 };
 
 extern "C" {
@@ -1088,6 +1297,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   int rc = gfs_device_check();
   if (rc) return rc;
   GFS_CUDA(cudaFuncSetAttribute(k_knn_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KNN_SMEM));
+  GFS_CUDA(cudaFuncSetAttribute(k_knn_cov_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KC_SMEM));
   GfsGicp* h = new GfsGicp();
   GicpDev& D = h->dev;
   memset(&D, 0, sizeof(D));
@@ -1097,14 +1307,21 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   D.hsize = hs;
   D.nblk = div_up(max_points, LIN_THREADS);
   D.voxel = s.downsampling_resolution;
-  // grid cell: half the correspondence radius, but never finer than 2.5 voxels (10-NN radius)
-  D.cell = std::max(0.5 * s.max_correspondence_distance, 2.5 * s.downsampling_resolution);
+  // grid cell = the correspondence radius (the bounded 1-NN search then ends after shells 0-1), never finer than
+  // 4 voxels (a 3x3x3 block must hold the 10 nearest neighbours of almost every point).  Measured on the
+  // configs[2] clouds: 0.05 m -> 1816 pairs/s, 0.065 -> 2447, 0.08 -> 2445, 0.1 -> 2505 (profiles/r01_summary.md)
+  D.cell = std::max(s.max_correspondence_distance, 4.0 * s.downsampling_resolution);
+  if (const char* ce = getenv("GFS_GICP_CELL")) {  // tuning knob (metres); any value gives the same results
+    const double v = atof(ce);
+    if (v > 0) D.cell = v;
+  }
   D.max_dist = s.max_correspondence_distance;
   D.rot_eps = s.rotation_eps;
   D.trans_eps = s.translation_eps;
   D.k = s.num_neighbors;
   D.max_iter = s.max_iterations;
   h->maxPairs = max_pairs;
+  h->cellKnn = getenv("GFS_GICP_KNN_CELLS") != nullptr;
   const size_t C = 2 * (size_t)max_pairs, P = max_pairs, N = max_points, H = hs;
 #define RES(buf, bytes, field, type)            \
   if ((rc = h->buf.reserve(bytes))) {           \
@@ -1123,6 +1340,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   RES(b_nIn, C * 4, nIn, int*)
   RES(b_nDown, C * 4, nDown, int*)
   RES(b_nCells, C * 4, nCells, int*)
+  RES(b_nFall, C * 4, nFall, int*)
   RES(b_box, C * 6 * 4, cellBox, int*)
   RES(b_pts, C * N * 32, pts, double*)
   RES(b_cov, C * N * 48, cov, double*)
@@ -1144,7 +1362,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
 int gfs_gicp_destroy(GfsGicp* h) {
   if (!h) return GFS_OK;
   DevBuf* d[] = {&h->b_keys, &h->b_minIdx, &h->b_count, &h->b_start, &h->b_cursor, &h->b_rank, &h->b_slotOf, &h->b_members,
-                 &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_box, &h->b_pts, &h->b_cov, &h->b_tab, &h->b_rec, &h->b_corr, &h->b_maha, &h->b_partial,
+                 &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_nFall, &h->b_box, &h->b_pts, &h->b_cov, &h->b_tab, &h->b_rec, &h->b_corr, &h->b_maha, &h->b_partial,
                  &h->b_partialE, &h->b_state, &h->b_istate, &h->b_counters, &h->b_tgt, &h->b_src, &h->b_n, &h->b_T0, &h->b_res};
   for (DevBuf* b : d) b->release();
   h->h_counters.release();
@@ -1185,16 +1403,25 @@ int gfs_gicp_align_batch_device(GfsGicp* h, void* stream, const float* d_target,
     const long long work = (long long)clouds * std::max(D.hsize, D.nmax);
     k_cell_pack<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(D, clouds);
   }
-  k_knn_cov<<<dim3(div_up(D.nmax, KNN_THREADS), clouds), KNN_THREADS, KNN_SMEM, st>>>(D);
+  if (!h->cellKnn) {
+    k_knn_cov<<<dim3(div_up(D.nmax, KNN_THREADS), clouds), KNN_THREADS, KNN_SMEM, st>>>(D, 0);
+  } else {
+    // ~3 resident CTAs per SM in flight over the whole batch; every CTA strides over its cloud's cells
+    const int gx = std::min(std::max(div_up(148 * 6, clouds), 24), div_up(D.nmax, KC_THREADS / KC_LANES));
+    k_knn_cov_cells<<<dim3(gx, clouds), KC_THREADS, KC_SMEM, st>>>(D);
+    k_knn_cov<<<dim3(8, clouds), KNN_THREADS, KNN_SMEM, st>>>(D, 1);
+    h->launches += 1;
+  }
   k_lm_init<<<div_up(pairs, 128), 128, 0, st>>>(D, pairs, d_T0);
   h->launches += 5;
   GFS_CUDA(cudaGetLastError());
   int* hc = (int*)h->h_counters.p;
   for (int it = 0; it < D.max_iter; it++) {
     GFS_CUDA(cudaMemsetAsync(D.counters, 0, 8, st));
+    k_nn_corr<<<dim3(div_up(D.nmax, NN_THREADS), pairs), NN_THREADS, 0, st>>>(D, it);
     k_linearize<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D, it);
     k_lm_begin<<<pairs, LIN_THREADS, 0, st>>>(D, it);
-    h->launches += 2;
+    h->launches += 3;
     for (int j = 0; j < 10; j++) {
       k_error<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D);
       GFS_CUDA(cudaMemsetAsync(D.counters, 0, 4, st));
@@ -1263,6 +1490,14 @@ int gfs_gicp_align(GfsGicp* h, void* stream, const float* target, int nt, const 
   if (rc) return rc;
   GFS_CUDA(cudaMemcpyAsync(out, h->b_res.p, sizeof(GfsGicpResult), cudaMemcpyDeviceToHost, st));
   GFS_CUDA(cudaStreamSynchronize(st));
+  return GFS_OK;
+}
+
+int gfs_gicp_get_knn_stats(GfsGicp* h, void* stream, int cloud, int* n_cells, int* n_per_query) {
+  GFS_REQUIRE(h && n_cells && n_per_query && cloud >= 0 && cloud < 2 * h->maxPairs, GFS_ERR_INVALID, "bad handle/cloud");
+  GFS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  GFS_CUDA(cudaMemcpy(n_cells, h->dev.nCells + cloud, 4, cudaMemcpyDeviceToHost));
+  GFS_CUDA(cudaMemcpy(n_per_query, h->dev.nFall + cloud, 4, cudaMemcpyDeviceToHost));
   return GFS_OK;
 }
 

@@ -87,6 +87,12 @@ class RegistrationGICP:
     def last_launches(self):
         return self._L.gfs_gicp_last_launches(self._h)
 
+    def knn_stats(self, index, stream=None):
+        """(occupied grid cells, queries finished by the per-query kernel) of cloud `index` of the last batch."""
+        a, b = C.c_int(), C.c_int()
+        check(self._L.gfs_gicp_get_knn_stats(self._h, stream, index, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def cloud(self, index, stream=None):
         """(downsampled xyz (M,3), covariances (M,6)) of cloud `index` of the last batch."""
         xyz = np.zeros((self.max_points, 3), np.float64); cov = np.zeros((self.max_points, 6), np.float64)

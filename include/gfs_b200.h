@@ -230,6 +230,8 @@ int gfs_gicp_align_batch_device(GfsGicp* h, void* stream, const float* d_target,
 /* parity hook: downsampled points + covariances of cloud (2*pair = target, 2*pair+1 = source) */
 int gfs_gicp_get_cloud(GfsGicp* h, void* stream, int cloud, double* out_xyz, double* out_cov6, int cap, int* n);
 int gfs_gicp_last_launches(const GfsGicp* h);
+/* diagnostics: grid cells of `cloud` and the queries its cell-centric 10-NN pass handed to the per-query kernel */
+int gfs_gicp_get_knn_stats(GfsGicp* h, void* stream, int cloud, int* n_cells, int* n_per_query);
 
 /* ------------------------------------------------------------------------------------------
  * Local inertial bundle adjustment -- replaces the numerical core of
