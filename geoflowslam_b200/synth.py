@@ -403,3 +403,102 @@ def pose_problem(seed=5000, n_obs=400, outlier_frac=0.1, mono_frac=0.2, rot_deg=
                 bf=np.float32(cam["bf"]), Xw=np.ascontiguousarray(Xw, np.float64),
                 uvr=np.ascontiguousarray(np.stack([uu, vv, ur], 1), np.float32),
                 inv_sigma2=(1.0 / sigma ** 2).astype(np.float32), truth_R=R_true, truth_t=t_true, truth_bad=bad)
+
+
+# ------------------------------------------------------------------------------------------------
+# PoseInertialOptimizationLastKeyFrame / LastFrame problem: the frame's body
+# state and ~n_obs map-point observations, the previous keyframe (fixed) or previous frame (free, with
+# the ConstraintPoseImu prior), and the IMU preintegration between them.
+# ------------------------------------------------------------------------------------------------
+def pose_inertial_problem(seed=6000, mode=0, n_obs=400, outlier_frac=0.1, mono_frac=0.2, rot_deg=0.5, trans=0.02,
+                          n_rounds=4, rec_init=0, imu_rate=200, prior_H=None, w=640, h=480):
+    """-> dict in the GfsPoseInertialProblem layout (include/gfs_b200.h) plus `truth`.
+    mode 0 = LastKeyFrame (0.4 s of IMU since the keyframe), mode 1 = LastFrame (one 30 Hz frame interval)."""
+    rng = np.random.default_rng(seed)
+    g = np.array([0, 0, -9.81])
+    cam = G1_CAM
+    Rbc = np.array([[0, 0, 1.0], [-1, 0, 0], [0, -1, 0]])
+    tbc = np.array([0.05, 0.02, 0.01])
+    Rcb = Rbc.T; tcb = -Rcb @ tbc
+    dt = 1.0 / imu_rate
+    ph = rng.uniform(0, 6.28, 4)
+
+    def pose(t):
+        yaw = 0.15 * t + 0.05 * np.sin(1.3 * t + ph[0])
+        pitch = 0.03 * np.sin(0.9 * t + ph[1]); roll = 0.02 * np.cos(1.1 * t + ph[2])
+        R = _rot(np.array([0, 0, yaw])) @ _rot(np.array([0, pitch, 0])) @ _rot(np.array([roll, 0, 0]))
+        p = np.array([0.6 * t + 0.1 * np.sin(0.8 * t + ph[3]), 0.2 * np.sin(0.5 * t), 0.05 * np.sin(0.7 * t)])
+        return R, p
+
+    hh = 1e-4
+
+    def vel(t):
+        return (pose(t + hh)[1] - pose(t - hh)[1]) / (2 * hh)
+
+    t_kf = 1.0
+    n_kf = 80                      # IMU samples since the last keyframe (0.4 s)
+    n_fr = max(1, imu_rate // 30)  # IMU samples since the previous frame
+    t1 = t_kf + n_kf * dt
+    t0 = t_kf if mode == 0 else t1 - n_fr * dt
+    ts = t_kf + np.arange(n_kf) * dt + dt / 2
+    acc = np.zeros((n_kf, 3)); gyr = np.zeros((n_kf, 3))
+    bg_true = np.array([0.002, -0.001, 0.0015]); ba_true = np.array([0.02, -0.03, 0.01])
+    for i, t in enumerate(ts):
+        R0, p0 = pose(t); Rp, pp = pose(t + hh); Rm, pm = pose(t - hh)
+        a_w = (pp - 2 * p0 + pm) / (hh * hh)
+        dRm = R0.T @ (Rp - Rm) / (2 * hh)
+        gyr[i] = [dRm[2, 1], dRm[0, 2], dRm[1, 0]]
+        acc[i] = R0.T @ (a_w - g)
+    gyr += bg_true + rng.normal(0, IMU_NOISE["ng"] * np.sqrt(imu_rate), gyr.shape)
+    acc += ba_true + rng.normal(0, IMU_NOISE["na"] * np.sqrt(imu_rate), acc.shape)
+    bias_est = np.concatenate([ba_true, bg_true]) + rng.normal(0, [2e-3] * 3 + [2e-4] * 3)
+    pre_kf = preintegrate(acc, gyr, dt, bias_est)
+    pre = pre_kf if mode == 0 else preintegrate(acc[-n_fr:], gyr[-n_fr:], dt, bias_est)
+    Ckf = pre_kf[60:285].reshape(15, 15)
+
+    def f64(x):
+        return np.asarray(x, np.float32).astype(np.float64)
+
+    R1, p1 = pose(t1); R0_, p0_ = pose(t0)
+    # current frame: perturbed float32 state, Tcw composed in float32 as the Frame stores it
+    Ri = R1 @ _rot(np.deg2rad(rng.uniform(-rot_deg, rot_deg, 3)))
+    pi_ = p1 + rng.uniform(-trans, trans, 3)
+    R32 = _polar32(Ri.astype(np.float32)); p32 = pi_.astype(np.float32)
+    Rcw32 = (Rcb.astype(np.float32) @ R32.T).astype(np.float32)
+    tcw32 = (Rcb.astype(np.float32) @ (-(R32.T @ p32)) + tcb.astype(np.float32)).astype(np.float32)
+    pert = 0.0 if mode == 0 else 1.0
+    Rp32 = _polar32((R0_ @ _rot(np.deg2rad(pert * rng.uniform(-0.1, 0.1, 3)))).astype(np.float32))
+    pp32 = (p0_ + pert * rng.uniform(-0.005, 0.005, 3)).astype(np.float32)
+    # observations of the current frame
+    u = rng.uniform(20, w - 20, n_obs); v = rng.uniform(20, h - 20, n_obs); z = rng.uniform(0.6, 12.0, n_obs)
+    Xc = np.stack([(u - cam["cx"]) / cam["fx"] * z, (v - cam["cy"]) / cam["fy"] * z, z], 1)
+    Xw = (Xc @ Rbc.T + tbc) @ R1.T + p1
+    octave = rng.integers(0, 8, n_obs)
+    sigma = 1.2 ** octave
+    uu = u + rng.normal(0, 1, n_obs) * sigma * 0.7
+    vv = v + rng.normal(0, 1, n_obs) * sigma * 0.7
+    ur = uu - cam["bf"] / z + rng.normal(0, 0.3, n_obs)
+    bad = rng.random(n_obs) < outlier_frac
+    uu[bad] += rng.uniform(8, 60, bad.sum()) * rng.choice([-1, 1], bad.sum())
+    vv[bad] += rng.uniform(8, 60, bad.sum()) * rng.choice([-1, 1], bad.sum())
+    mono = rng.random(n_obs) < mono_frac
+    ur[mono] = -1.0
+    if prior_H is None:
+        A = rng.normal(0, 1, (15, 15)) * np.sqrt([3e3] * 6 + [3e2] * 3 + [1e5] * 3 + [3e3] * 3)
+        prior_H = A.T @ A / 15 + np.diag([1e4] * 6 + [1e3] * 3 + [1e6] * 3 + [1e4] * 3)
+    prior_H = np.asarray(prior_H, np.float64).reshape(15, 15)
+    return dict(
+        mode=int(mode), n_obs=int(n_obs), n_rounds=int(n_rounds), rec_init=int(rec_init),
+        fx=np.float32(cam["fx"]), fy=np.float32(cam["fy"]), cx=np.float32(cam["cx"]), cy=np.float32(cam["cy"]),
+        bf=np.float32(cam["bf"]), Rcb=f64(Rcb).ravel(), tcb=f64(tcb), tbc=f64(tbc),
+        Rwb=f64(R32).ravel(), twb=f64(p32), Rcw=f64(Rcw32).ravel(), tcw=f64(tcw32),
+        vel=f64(vel(t1) + rng.uniform(-0.05, 0.05, 3)), bg=f64(bias_est[3:]), ba=f64(bias_est[:3]),
+        p_Rwb=f64(Rp32).ravel(), p_twb=f64(pp32), p_vel=f64(vel(t0) + pert * rng.uniform(-0.01, 0.01, 3)),
+        p_bg=f64(bias_est[3:]), p_ba=f64(bias_est[:3]),
+        pre=np.ascontiguousarray(pre, np.float32),
+        rw_Cg=np.ascontiguousarray(Ckf[9:12, 9:12], np.float32).ravel(), rw_Ca=np.ascontiguousarray(Ckf[12:15, 12:15], np.float32).ravel(),
+        c_Rwb=f64(Rp32).ravel(), c_twb=f64(pp32), c_vwb=f64(vel(t0)), c_bg=f64(bias_est[3:]), c_ba=f64(bias_est[:3]),
+        c_H=np.ascontiguousarray(prior_H, np.float64).ravel(),
+        Xw=np.ascontiguousarray(np.asarray(Xw, np.float32), np.float64), uvr=np.ascontiguousarray(np.stack([uu, vv, ur], 1), np.float32),
+        inv_sigma2=(1.0 / sigma ** 2).astype(np.float32), close=(z < 10.0).astype(np.uint8),
+        truth=dict(Rwb=R1, twb=p1, vel=vel(t1), bg=bg_true, ba=ba_true, bad=bad))

@@ -347,6 +347,63 @@ int gfs_pose_optimize_batch(GfsPose* h, void* stream, const GfsPoseProblem* prob
 int gfs_pose_optimize(GfsPose* h, void* stream, const GfsPoseProblem* problem, GfsPoseResult* result);
 int gfs_pose_last_launches(const GfsPose* h);
 
+/* ------------------------------------------------------------------------------------------------
+ * Inertial pose-only optimisers of the tracking thread.
+ * Replace the g2o blocks of Optimizer::PoseInertialOptimizationLastKeyFrame (reference
+ * include/Optimizer.h:80-83, src/Optimizer.cc:5899-6284) and Optimizer::PoseInertialOptimizationLastFrame
+ * (include/Optimizer.h:92-95, src/Optimizer.cc:6762-7172; Tracking.cc:3777,3792 call them from
+ * TrackLocalMap): VertexPose / VertexVelocity / VertexGyroBias / VertexAccBias of the frame (and, LastFrame,
+ * of the previous frame), EdgeMonoOnlyPose / EdgeStereoOnlyPose with Huber (G2oTypes.cc:362-383,418-443),
+ * EdgeInertial with Huber 6.0 (G2oTypes.cc:473-719), EdgeGyroRW / EdgeAccRW, EdgePriorPoseImu with Huber 5
+ * (G2oTypes.cc:927-995), Gauss-Newton with the dense Eigen LDLT over all 15 / 30 unknowns
+ * (optimization_algorithm_gauss_newton.cpp:49-93, linear_solver_dense.h:66-114), nIterations rounds of 10
+ * iterations with chi2 classification, and the Hessian hand-over: GetHessian2 blocks (LastKeyFrame) or the
+ * 30x30 Hessian marginalised over the previous frame (Optimizer::Marginalize, :4408-4487), clamped like
+ * the ConstraintPoseImu constructor (G2oTypes.h:857-868).
+ * ------------------------------------------------------------------------------------------------ */
+#define GFS_PIN_LAST_KEYFRAME 0
+#define GFS_PIN_LAST_FRAME 1
+typedef struct GfsPoseInertialProblem {
+  int mode;     /* GFS_PIN_LAST_KEYFRAME: previous state fixed; GFS_PIN_LAST_FRAME: previous frame free + prior */
+  int n_obs;    /* features of the frame with a MapPoint, in feature order */
+  int n_rounds; /* nIterations (<= 4) */
+  int rec_init; /* bRecInit */
+  float fx, fy, cx, cy, bf;       /* Pinhole parameters, Frame::mbf */
+  double Rcb[9], tcb[3], tbc[3];  /* mImuCalib.mTcb / mTbc (G2oTypes.cc:96-101); row-major */
+  /* the frame: ImuCamPose(Frame*) + VertexVelocity / GyroBias / AccBias (floats widened, G2oTypes.cc:76-101) */
+  double Rwb[9], twb[3], Rcw[9], tcw[3], vel[3], bg[3], ba[3];
+  /* mpLastKeyFrame (mode 0) or mpPrevFrame (mode 1) */
+  double p_Rwb[9], p_twb[3], p_vel[3], p_bg[3], p_ba[3];
+  const float* pre;         /* [GFS_BA_PRE_STRIDE] mpImuPreintegrated (mode 0) / mpImuPreintegratedFrame (mode 1) */
+  float rw_Cg[9], rw_Ca[9]; /* pFrame->mpImuPreintegrated->C.block<3,3>(9,9) and (12,12): random-walk covariances */
+  /* pFp->mpcpi (mode 1 only): ConstraintPoseImu members; H row-major 15x15 */
+  double c_Rwb[9], c_twb[3], c_vwb[3], c_bg[3], c_ba[3], c_H[225];
+  const double* Xw;         /* [n_obs][3] pMP->GetWorldPos().cast<double>() */
+  const float* uvr;         /* [n_obs][3] kpUn.pt.x, kpUn.pt.y, mvuRight (< 0: EdgeMonoOnlyPose) */
+  const float* inv_sigma2;  /* [n_obs] mvInvLevelSigma2[octave] / unc2 */
+  const uint8_t* close;     /* [n_obs] mTrackDepth < 10 (monocular edges only) */
+} GfsPoseInertialProblem;
+typedef struct GfsPoseInertialResult {
+  int n_inliers;            /* return value: nInitialCorrespondences - nBad */
+  int n_bad, n_inliers_last;/* nBad as returned; nInliers of the last round */
+  float avg_reproj_error;   /* SetFrame2FrameReprojError / SetFrame2MapReprojError value of the last round */
+  int rounds_done;
+  int gn_iterations[4];     /* iterations g2o ran in each round */
+  double Rwb[9], twb[3], vel[3], bg[3], ba[3]; /* VP / VV / VG / VA estimates (the caller narrows to float) */
+  double H[225];            /* pFrame->mpcpi->H: the prior handed to the next frame, after the eigenvalue clamp */
+  uint8_t* outlier;         /* [n_obs] mvbOutlier */
+  float* chi2;              /* [n_obs] chi2 of the last round (may be NULL) */
+} GfsPoseInertialResult;
+typedef struct GfsPoseInertial GfsPoseInertial;
+int gfs_pose_inertial_create(int max_obs, int max_batch, GfsPoseInertial** out);
+int gfs_pose_inertial_destroy(GfsPoseInertial* h);
+/* Host pointers inside the structs; one CUDA block per frame, the whole optimisation in one launch. */
+int gfs_pose_inertial_optimize_batch(GfsPoseInertial* h, void* stream, const GfsPoseInertialProblem* problems, int batch,
+                                     GfsPoseInertialResult* results);
+int gfs_pose_inertial_optimize(GfsPoseInertial* h, void* stream, const GfsPoseInertialProblem* problem,
+                               GfsPoseInertialResult* result);
+int gfs_pose_inertial_last_launches(const GfsPoseInertial* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -312,11 +312,12 @@ static inline void huber(double e, double delta, double* rho) {  // robust_kerne
 }
 
 // EdgeInertial::computeError (G2oTypes.cc:495-522)
+static void inertial_error_core(const Pre& pre, const KF& k1, const KF& k2, double* err9);
 static void inertial_error(const Problem& pr, const State& s, int e, double* err9) {
   const GfsBaProblem& P = *pr.P;
-  const KF& k1 = s.kf[P.in_kf1[e]];
-  const KF& k2 = s.kf[P.in_kf2[e]];
-  const Pre pre(P.in_pre + (size_t)e * GFS_BA_PRE_STRIDE);
+  inertial_error_core(Pre(P.in_pre + (size_t)e * GFS_BA_PRE_STRIDE), s.kf[P.in_kf1[e]], s.kf[P.in_kf2[e]], err9);
+}
+static void inertial_error_core(const Pre& pre, const KF& k1, const KF& k2, double* err9) {
   double dR[9], dV[3], dP[3];
   delta_for_bias(pre, k1.bg, k1.ba, dR, dV, dP, nullptr);
   const double dt = (double)pre.dT;
@@ -338,11 +339,12 @@ static void inertial_error(const Problem& pr, const State& s, int e, double* err
   for (int i = 0; i < 3; i++) { err9[3 + i] = rv[i] - dV[i]; err9[6 + i] = rp[i] - dP[i]; }
 }
 // EdgeInertial::linearizeOplus (:524-719): J is 9 x 24, columns [pose1(6) vel1(3) bg1(3) ba1(3) pose2(6) vel2(3)]
+static void inertial_jacobian_core(const Pre& pre, const KF& k1, const KF& k2, double* J /*9x24*/);
 static void inertial_jacobian(const Problem& pr, const State& s, int e, double* J /*9x24*/) {
   const GfsBaProblem& P = *pr.P;
-  const KF& k1 = s.kf[P.in_kf1[e]];
-  const KF& k2 = s.kf[P.in_kf2[e]];
-  const Pre pre(P.in_pre + (size_t)e * GFS_BA_PRE_STRIDE);
+  inertial_jacobian_core(Pre(P.in_pre + (size_t)e * GFS_BA_PRE_STRIDE), s.kf[P.in_kf1[e]], s.kf[P.in_kf2[e]], J);
+}
+static void inertial_jacobian_core(const Pre& pre, const KF& k1, const KF& k2, double* J /*9x24*/) {
   double dR[9], dV[3], dP[3], dbg[3];
   delta_for_bias(pre, k1.bg, k1.ba, dR, dV, dP, dbg);
   const double dt = (double)pre.dT;
@@ -939,6 +941,454 @@ static void solve(const GfsBaProblem* P, GfsBaResult* R) {
   memcpy(R->pt_xyz, s.pt.data(), sizeof(double) * s.pt.size());
 }
 
+
+// =================================================================================================
+// Inertial pose-only optimisers of the tracking thread:
+// Optimizer::PoseInertialOptimizationLastKeyFrame (reference src/Optimizer.cc:5899-6284) and
+// Optimizer::PoseInertialOptimizationLastFrame (:6762-7172) on the flattened GfsPoseInertialProblem.
+//   vertices  VertexPose (ImuCamPose::Update, G2oTypes.cc:193-217), VertexVelocity / GyroBias / AccBias
+//   edges     EdgeMonoOnlyPose / EdgeStereoOnlyPose (G2oTypes.h:354-456, G2oTypes.cc:362-383,418-443),
+//             EdgeInertial (cores above), EdgeGyroRW / EdgeAccRW (G2oTypes.h:782-852),
+//             EdgePriorPoseImu (G2oTypes.cc:927-995)
+//   solver    OptimizationAlgorithmGaussNewton (optimization_algorithm_gauss_newton.cpp:49-93): errors,
+//             linearise, dense Eigen LDLT over all unknowns in vertex-id order (linear_solver_dense.h:66-114),
+//             update; a failed factorisation re-applies the previous x and ends the round
+//   hand-over GetHessian / GetHessian2 blocks, Optimizer::Marginalize (:4408-4487; the JacobiSVD
+//             pseudo-inverse of a symmetric matrix is restated through its eigen-decomposition),
+//             ConstraintPoseImu's eigenvalue clamp (G2oTypes.h:857-868)
+// The reference has no tests for this path: parity unpinned; tests/test_oracle_pose_inertial.py checks the
+// Jacobians by finite differences, the marginalisation against numpy and the result against ground truth.
+// =================================================================================================
+extern "C" int gfo_eigen_ldlt_solve(const double* H, const double* b, int n, double* x);  // pose_oracle.cpp
+
+namespace pin {
+
+struct Cam { double fx, fy, cx, cy, bf; const double *Rcb, *tcb, *tbc; };
+
+static void cam_update(const Cam& C, KF& k, const double* pu) {  // ImuCamPose::Update
+  double t[3], E[9];
+  mv3(k.Rwb, pu + 3, t);
+  for (int i = 0; i < 3; i++) k.twb[i] += t[i];
+  exp_so3(pu, E);
+  mm3(k.Rwb, E, k.Rwb);
+  double Rbw[9], tbw[3];
+  mt3(k.Rwb, Rbw);
+  mv3(Rbw, k.twb, tbw);
+  for (int i = 0; i < 3; i++) tbw[i] = -tbw[i];
+  mm3(C.Rcb, Rbw, k.Rcw);
+  mv3(C.Rcb, tbw, k.tcw);
+  for (int i = 0; i < 3; i++) k.tcw[i] += C.tcb[i];
+}
+// obs - Project[Stereo](Xw); returns the dimension
+static int vis_err(const Cam& C, const KF& k, const double* Xw, const float* o, double* err, double* Xc_out) {
+  double Xc[3];
+  mv3(k.Rcw, Xw, Xc);
+  for (int i = 0; i < 3; i++) Xc[i] += k.tcw[i];
+  if (Xc_out) memcpy(Xc_out, Xc, sizeof(Xc));
+  const double u = C.fx * Xc[0] / Xc[2] + C.cx, v = C.fy * Xc[1] / Xc[2] + C.cy;
+  err[0] = (double)o[0] - u;
+  err[1] = (double)o[1] - v;
+  err[2] = 0;
+  if (o[2] < 0) return 2;
+  const double invZ = 1 / Xc[2];
+  err[2] = (double)o[2] - (u - C.bf * invZ);
+  return 3;
+}
+// Edge{Mono,Stereo}OnlyPose::linearizeOplus: J = proj_jac * Rcb * SE3deriv(Xb), d x 6 (unused rows zero)
+static void vis_jac(const Cam& C, const KF& k, const double* Xw, bool mono, double* J /*3x6*/) {
+  double Xc[3], Xb[3];
+  mv3(k.Rcw, Xw, Xc);
+  for (int i = 0; i < 3; i++) Xc[i] += k.tcw[i];
+  mtv3(C.Rcb, Xc, Xb);  // Rbc = Rcb^T
+  for (int i = 0; i < 3; i++) Xb[i] += C.tbc[i];
+  double pj[9] = {C.fx / Xc[2], 0.0, -C.fx * Xc[0] / (Xc[2] * Xc[2]), 0.0, C.fy / Xc[2], -C.fy * Xc[1] / (Xc[2] * Xc[2]), 0, 0, 0};
+  if (!mono) {
+    const double inv_z2 = 1.0 / (Xc[2] * Xc[2]);
+    pj[6] = pj[0]; pj[7] = pj[1]; pj[8] = pj[2] + C.bf * inv_z2;
+  }
+  double A[9];
+  mm3(pj, C.Rcb, A);
+  const double x = Xb[0], y = Xb[1], z = Xb[2];
+  const double D[18] = {0, z, -y, 1, 0, 0, -z, 0, x, 0, 1, 0, y, -x, 0, 0, 0, 1};
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 6; c++) J[6 * r + c] = A[3 * r] * D[c] + A[3 * r + 1] * D[6 + c] + A[3 * r + 2] * D[12 + c];
+  if (mono) for (int c = 0; c < 6; c++) J[12 + c] = 0;
+}
+// EdgePriorPoseImu::computeError / linearizeOplus for the state k (pose, v, bg, ba)
+static void prior_err(const GfsPoseInertialProblem& P, const KF& k, double* e15) {
+  double Rt[9], M[9], d[3];
+  mt3(P.c_Rwb, Rt);
+  mm3(Rt, k.Rwb, M);
+  log_so3(M, e15);
+  for (int i = 0; i < 3; i++) d[i] = k.twb[i] - P.c_twb[i];
+  mv3(Rt, d, e15 + 3);
+  for (int i = 0; i < 3; i++) { e15[6 + i] = k.vel[i] - P.c_vwb[i]; e15[9 + i] = k.bg[i] - P.c_bg[i]; e15[12 + i] = k.ba[i] - P.c_ba[i]; }
+}
+static void prior_jac(const GfsPoseInertialProblem& P, const KF& k, double* J /*15x15*/) {
+  double Rt[9], M[9], er[3], iJ[9];
+  mt3(P.c_Rwb, Rt);
+  mm3(Rt, k.Rwb, M);
+  log_so3(M, er);
+  inv_right_jac(er, iJ);
+  memset(J, 0, sizeof(double) * 225);
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) { J[15 * r + c] = iJ[3 * r + c]; J[15 * (3 + r) + 3 + c] = M[3 * r + c]; }
+  for (int i = 6; i < 15; i++) J[15 * i + i] = 1.0;
+}
+// Optimizer::Marginalize(H, 0, 14) on a 30x30 matrix -> the lower-right 15x15 block of the result
+static void marginalize_first15(const double* H30, double* out15) {
+  std::vector<double> Hb(225), e, V;
+  for (int r = 0; r < 15; r++)
+    for (int c = 0; c < 15; c++) Hb[15 * r + c] = H30[30 * r + c];
+  // JacobiSVD of the (symmetric) block: singular values |lambda|, U = V sign(lambda)  ->  V diag(1/lambda) V^T
+  jacobi_eig(Hb, 15, e, V);
+  std::vector<double> inv(225, 0.0);
+  for (int k = 0; k < 15; k++) {
+    if (!(std::fabs(e[k]) > 1e-6)) continue;
+    const double w = 1.0 / e[k];
+    for (int r = 0; r < 15; r++)
+      for (int c = 0; c < 15; c++) inv[15 * r + c] += V[15 * r + k] * w * V[15 * c + k];
+  }
+  // c* = Hcc - Hcb * invHb * Hbc   (Hcb = H[15:30, 0:15], Hbc = H[0:15, 15:30])
+  std::vector<double> T(225);
+  for (int r = 0; r < 15; r++)
+    for (int c = 0; c < 15; c++) {
+      double a = 0;
+      for (int k = 0; k < 15; k++) a += H30[30 * (15 + r) + k] * inv[15 * k + c];
+      T[15 * r + c] = a;
+    }
+  for (int r = 0; r < 15; r++)
+    for (int c = 0; c < 15; c++) {
+      double a = 0;
+      for (int k = 0; k < 15; k++) a += T[15 * r + k] * H30[30 * k + 15 + c];
+      out15[15 * r + c] = H30[30 * (15 + r) + 15 + c] - a;
+    }
+}
+// ConstraintPoseImu constructor: H = (H + H) / 2 (sic), eigenvalues < 1e-12 zeroed
+static void constraint_clamp(double* H15) {
+  std::vector<double> A(H15, H15 + 225), e, V;
+  for (auto& v : A) v = (v + v) / 2;
+  // SelfAdjointEigenSolver reads the lower triangle only
+  for (int r = 0; r < 15; r++)
+    for (int c = r + 1; c < 15; c++) A[15 * r + c] = A[15 * c + r];
+  jacobi_eig(A, 15, e, V);
+  for (int i = 0; i < 15; i++)
+    if (e[i] < 1e-12) e[i] = 0;
+  for (int r = 0; r < 15; r++)
+    for (int c = 0; c < 15; c++) {
+      double a = 0;
+      for (int k = 0; k < 15; k++) a += V[15 * r + k] * e[k] * V[15 * c + k];
+      H15[15 * r + c] = a;
+    }
+}
+
+struct Ctx {
+  const GfsPoseInertialProblem* P;
+  Cam C;
+  int n, dim;
+  bool free_prev;
+  KF cur, prev;
+  double infoI[81], infoG[9], infoA[9];
+  double deltaI, deltaMono, deltaStereo;
+  std::vector<double> err;     // [n][3] stored _error of the visual edges
+  std::vector<int> level;
+  std::vector<char> robust;
+  double errI[9], errG[3], errA[3], errP[15];
+};
+static void compute_active_errors(Ctx& X) {
+  const GfsPoseInertialProblem& P = *X.P;
+  for (int e = 0; e < X.n; e++)
+    if (X.level[e] == 0) vis_err(X.C, X.cur, P.Xw + 3 * (size_t)e, P.uvr + 3 * (size_t)e, &X.err[3 * (size_t)e], nullptr);
+  inertial_error_core(Pre(P.pre), X.prev, X.cur, X.errI);
+  for (int i = 0; i < 3; i++) { X.errG[i] = X.cur.bg[i] - X.prev.bg[i]; X.errA[i] = X.cur.ba[i] - X.prev.ba[i]; }
+  if (X.free_prev) prior_err(P, X.prev, X.errP);
+}
+static double quad(const double* e, const double* Om, int n) {  // e^T Om e as g2o's chi2(): _error.dot(information()*_error)
+  double s = 0;
+  for (int r = 0; r < n; r++) {
+    double a = 0;
+    for (int c = 0; c < n; c++) a += Om[n * r + c] * e[c];
+    s += e[r] * a;
+  }
+  return s;
+}
+// unknown order = vertex ids: VP 0-5, VV 6-8, VG 9-11, VA 12-14, then (LastFrame) VPk 15-20, VVk 21-23, VGk 24-26, VAk 27-29
+static void add_block(std::vector<double>& H, std::vector<double>& b, int dim, const double* J, int rows, int jcols, const int* map,
+                      const double* Om, double w, const double* e) {
+  // H += J^T (w Om) J,  b -= w J^T Om e   over the mapped (non-fixed) columns
+  std::vector<double> WJ((size_t)rows * jcols), We(rows);
+  for (int r = 0; r < rows; r++) {
+    for (int c = 0; c < jcols; c++) {
+      double a = 0;
+      for (int k = 0; k < rows; k++) a += (w * Om[rows * r + k]) * J[jcols * k + c];
+      WJ[(size_t)r * jcols + c] = a;
+    }
+    double a = 0;
+    for (int k = 0; k < rows; k++) a += Om[rows * r + k] * e[k];
+    We[r] = w * a;
+  }
+  for (int a = 0; a < jcols; a++) {
+    if (map[a] < 0) continue;
+    double g = 0;
+    for (int r = 0; r < rows; r++) g += J[jcols * r + a] * We[r];
+    b[map[a]] -= g;
+    for (int c = 0; c < jcols; c++) {
+      if (map[c] < 0) continue;
+      double h = 0;
+      for (int r = 0; r < rows; r++) h += J[jcols * r + a] * WJ[(size_t)r * jcols + c];
+      H[(size_t)map[a] * dim + map[c]] += h;
+    }
+  }
+}
+static void build_system(Ctx& X, std::vector<double>& H, std::vector<double>& b) {
+  const GfsPoseInertialProblem& P = *X.P;
+  const int dim = X.dim;
+  H.assign((size_t)dim * dim, 0.0);
+  b.assign(dim, 0.0);
+  for (int e = 0; e < X.n; e++) {
+    if (X.level[e] != 0) continue;
+    const bool mono = P.uvr[3 * (size_t)e + 2] < 0;
+    const int d = mono ? 2 : 3;
+    double J[18];
+    vis_jac(X.C, X.cur, P.Xw + 3 * (size_t)e, mono, J);
+    const double om = (double)P.inv_sigma2[e];
+    const double* er = &X.err[3 * (size_t)e];
+    double w = 1.0;
+    if (X.robust[e]) {
+      double c2 = 0;
+      for (int i = 0; i < d; i++) c2 += er[i] * (om * er[i]);
+      double rho[3];
+      huber(c2, mono ? X.deltaMono : X.deltaStereo, rho);
+      w = rho[1];
+    }
+    for (int a = 0; a < 6; a++) {
+      double g = 0;
+      for (int i = 0; i < d; i++) g += J[6 * i + a] * (om * er[i]);
+      b[a] -= w * g;
+      for (int c = 0; c < 6; c++) {
+        double h = 0;
+        for (int i = 0; i < d; i++) h += J[6 * i + a] * ((w * om) * J[6 * i + c]);
+        H[(size_t)a * dim + c] += h;
+      }
+    }
+  }
+  {  // EdgeInertial: J columns [p1 v1 bg1 ba1 p2 v2]
+    double J[9 * 24];
+    inertial_jacobian_core(Pre(P.pre), X.prev, X.cur, J);
+    int map[24];
+    for (int c = 0; c < 15; c++) map[c] = X.free_prev ? 15 + c : -1;
+    for (int c = 0; c < 9; c++) map[15 + c] = c;
+    double rho[3];
+    huber(quad(X.errI, X.infoI, 9), X.deltaI, rho);
+    add_block(H, b, dim, J, 9, 24, map, X.infoI, rho[1], X.errI);
+  }
+  {  // EdgeGyroRW / EdgeAccRW: J = [-I, I] over (prev bias, cur bias), no kernel
+    double J[18] = {-1, 0, 0, 1, 0, 0, 0, -1, 0, 0, 1, 0, 0, 0, -1, 0, 0, 1};
+    int mg[6], ma[6];
+    for (int c = 0; c < 3; c++) { mg[c] = X.free_prev ? 24 + c : -1; mg[3 + c] = 9 + c; ma[c] = X.free_prev ? 27 + c : -1; ma[3 + c] = 12 + c; }
+    add_block(H, b, dim, J, 3, 6, mg, X.infoG, 1.0, X.errG);
+    add_block(H, b, dim, J, 3, 6, ma, X.infoA, 1.0, X.errA);
+  }
+  if (X.free_prev) {  // EdgePriorPoseImu, Huber 5
+    double J[225];
+    prior_jac(P, X.prev, J);
+    int map[15];
+    for (int c = 0; c < 15; c++) map[c] = 15 + c;
+    double rho[3];
+    huber(quad(X.errP, P.c_H, 15), 5.0, rho);
+    add_block(H, b, dim, J, 15, 15, map, P.c_H, rho[1], X.errP);
+  }
+}
+static void apply_update(Ctx& X, const double* x) {
+  cam_update(X.C, X.cur, x);
+  for (int i = 0; i < 3; i++) { X.cur.vel[i] += x[6 + i]; X.cur.bg[i] += x[9 + i]; X.cur.ba[i] += x[12 + i]; }
+  if (X.free_prev) {
+    cam_update(X.C, X.prev, x + 15);
+    for (int i = 0; i < 3; i++) { X.prev.vel[i] += x[21 + i]; X.prev.bg[i] += x[24 + i]; X.prev.ba[i] += x[27 + i]; }
+  }
+}
+
+static void optimize(const GfsPoseInertialProblem* Pp, GfsPoseInertialResult* R) {
+  const GfsPoseInertialProblem& P = *Pp;
+  Ctx X;
+  X.P = Pp;
+  X.C = Cam{(double)P.fx, (double)P.fy, (double)P.cx, (double)P.cy, (double)P.bf, P.Rcb, P.tcb, P.tbc};
+  X.n = P.n_obs;
+  X.free_prev = P.mode == GFS_PIN_LAST_FRAME;
+  X.dim = X.free_prev ? 30 : 15;
+  memcpy(X.cur.Rwb, P.Rwb, 72); memcpy(X.cur.twb, P.twb, 24); memcpy(X.cur.Rcw, P.Rcw, 72); memcpy(X.cur.tcw, P.tcw, 24);
+  memcpy(X.cur.vel, P.vel, 24); memcpy(X.cur.bg, P.bg, 24); memcpy(X.cur.ba, P.ba, 24);
+  memset(&X.prev, 0, sizeof(KF));
+  memcpy(X.prev.Rwb, P.p_Rwb, 72); memcpy(X.prev.twb, P.p_twb, 24);
+  memcpy(X.prev.vel, P.p_vel, 24); memcpy(X.prev.bg, P.p_bg, 24); memcpy(X.prev.ba, P.p_ba, 24);
+  inertial_information(Pre(P.pre).C, X.infoI);
+  {
+    double Cg[9], Ca[9];
+    for (int i = 0; i < 9; i++) { Cg[i] = (double)P.rw_Cg[i]; Ca[i] = (double)P.rw_Ca[i]; }
+    inv3(Cg, X.infoG);
+    inv3(Ca, X.infoA);
+  }
+  X.deltaI = 6.0;
+  X.deltaMono = (double)(float)std::sqrt(5.991);
+  X.deltaStereo = (double)(float)std::sqrt(7.815);
+  const int N = X.n;
+  X.err.assign((size_t)3 * N + 3, 0.0);
+  X.level.assign(N, 0);
+  X.robust.assign(N, 1);
+  for (int e = 0; e < N; e++) { R->outlier[e] = 0; if (R->chi2) R->chi2[e] = 0.f; }
+  memset(R->gn_iterations, 0, sizeof(R->gn_iterations));
+  R->rounds_done = 0;
+  const bool lastKF = !X.free_prev;
+  const float chi2MonoKF[4] = {12, 7.5, 5.991, 5.991}, chi2MonoF[4] = {5.991, 5.991, 5.991, 5.991};
+  const float chi2Stereo[4] = {15.6f, 9.8f, 7.815f, 7.815f};
+  const float* chi2Mono = lastKF ? chi2MonoKF : chi2MonoF;
+  int nBad = 0, nInliers = 0;
+  float avg = 0.f;
+  std::vector<double> H, b, x(X.dim, 0.0);
+  const int rounds = std::min(std::max(P.n_rounds, 0), 4);
+  for (int it = 0; it < rounds; it++) {
+    // optimizer.initializeOptimization(0); optimizer.optimize(10)
+    for (int iter = 0; iter < 10; iter++) {
+      compute_active_errors(X);
+      build_system(X, H, b);
+      const bool ok = gfo_eigen_ldlt_solve(H.data(), b.data(), X.dim, x.data()) != 0;  // a failure leaves x as it was
+      apply_update(X, x.data());
+      R->gn_iterations[it]++;
+      if (!ok) break;
+    }
+    nBad = 0;
+    int nInMono = 0, nInStereo = 0;
+    const float chi2close = 1.5 * chi2Mono[it];
+    avg = 0.0f;
+    if (lastKF) {
+      const float chi2IMU = (float)quad(X.errI, X.infoI, 9);
+      if (chi2IMU > 15.0) {
+        X.deltaI = 2.0;
+        for (int i = 0; i < 81; i++) X.infoI[i] *= 1e-2;
+      }
+    }
+    for (int pass = 0; pass < 2; pass++)
+      for (int e = 0; e < N; e++) {
+        const float* o = P.uvr + 3 * (size_t)e;
+        const bool mono = o[2] < 0;
+        if (mono != (pass == 0)) continue;
+        double* er = &X.err[3 * (size_t)e];
+        if (R->outlier[e]) vis_err(X.C, X.cur, P.Xw + 3 * (size_t)e, o, er, nullptr);
+        const int d = mono ? 2 : 3;
+        const double om = (double)P.inv_sigma2[e];
+        double c2 = 0;
+        for (int i = 0; i < d; i++) c2 += er[i] * (om * er[i]);
+        const float chi2 = (float)c2;
+        if (R->chi2) R->chi2[e] = chi2;
+        bool bad;
+        if (mono) {
+          const bool bClose = P.close[e] != 0;
+          const double* Xw = P.Xw + 3 * (size_t)e;
+          const bool depthPos = (X.cur.Rcw[6] * Xw[0] + X.cur.Rcw[7] * Xw[1] + X.cur.Rcw[8] * Xw[2] + X.cur.tcw[2]) > 0.0;
+          bad = (chi2 > chi2Mono[it] && !bClose) || (bClose && chi2 > chi2close) || !depthPos;
+        } else {
+          bad = chi2 > chi2Stereo[it];
+        }
+        if (bad) { R->outlier[e] = 1; X.level[e] = 1; nBad++; }
+        else { avg += chi2; R->outlier[e] = 0; X.level[e] = 0; (mono ? nInMono : nInStereo)++; }
+        if (it == 2) X.robust[e] = 0;
+      }
+    nInliers = nInMono + nInStereo;
+    avg /= nInliers;
+    R->rounds_done = it + 1;
+    if (N + (X.free_prev ? 4 : 3) < 10) break;  // optimizer.edges().size() < 10
+  }
+  // If not too much tracks, recover not too bad points
+  if (nInliers < 30 && !P.rec_init) {
+    nBad = 0;
+    for (int pass = 0; pass < 2; pass++)
+      for (int e = 0; e < N; e++) {
+        const float* o = P.uvr + 3 * (size_t)e;
+        const bool mono = o[2] < 0;
+        if (mono != (pass == 0)) continue;
+        double* er = &X.err[3 * (size_t)e];
+        vis_err(X.C, X.cur, P.Xw + 3 * (size_t)e, o, er, nullptr);
+        const int d = mono ? 2 : 3;
+        const double om = (double)P.inv_sigma2[e];
+        double c2 = 0;
+        for (int i = 0; i < d; i++) c2 += er[i] * (om * er[i]);
+        if (c2 < (mono ? 18.0 : 24.0)) R->outlier[e] = 0;
+        else nBad++;
+      }
+  }
+  memcpy(R->Rwb, X.cur.Rwb, 72); memcpy(R->twb, X.cur.twb, 24); memcpy(R->vel, X.cur.vel, 24);
+  memcpy(R->bg, X.cur.bg, 24); memcpy(R->ba, X.cur.ba, 24);
+  // ---- Hessian hand-over (fresh linearisation at the final estimates, raw information, inlier edges only)
+  double Hv[36] = {0};
+  for (int e = 0; e < N; e++) {
+    if (R->outlier[e]) continue;
+    const bool mono = P.uvr[3 * (size_t)e + 2] < 0;
+    const int d = mono ? 2 : 3;
+    double J[18];
+    vis_jac(X.C, X.cur, P.Xw + 3 * (size_t)e, mono, J);
+    const double om = (double)P.inv_sigma2[e];
+    for (int a = 0; a < 6; a++)
+      for (int c = 0; c < 6; c++) {
+        double h = 0;
+        for (int i = 0; i < d; i++) h += J[6 * i + a] * (om * J[6 * i + c]);
+        Hv[6 * a + c] += h;
+      }
+  }
+  double JI[9 * 24];
+  inertial_jacobian_core(Pre(P.pre), X.prev, X.cur, JI);
+  std::vector<double> HI(24 * 24, 0.0), dummyb(24, 0.0);
+  {
+    int map[24];
+    for (int c = 0; c < 24; c++) map[c] = c;
+    double zero[9] = {0};
+    add_block(HI, dummyb, 24, JI, 9, 24, map, X.infoI, 1.0, zero);  // J^T information() J
+  }
+  double Hout[225];
+  if (lastKF) {
+    memset(Hout, 0, sizeof(Hout));
+    for (int r = 0; r < 9; r++)
+      for (int c = 0; c < 9; c++) Hout[15 * r + c] += HI[24 * (15 + r) + 15 + c];  // GetHessian2: [p2 v2]
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) { Hout[15 * (9 + r) + 9 + c] += X.infoG[3 * r + c]; Hout[15 * (12 + r) + 12 + c] += X.infoA[3 * r + c]; }
+    for (int r = 0; r < 6; r++)
+      for (int c = 0; c < 6; c++) Hout[15 * r + c] += Hv[6 * r + c];
+  } else {
+    std::vector<double> H30(900, 0.0);
+    for (int r = 0; r < 24; r++)
+      for (int c = 0; c < 24; c++) H30[30 * r + c] += HI[24 * r + c];
+    const int gi[2] = {9, 24}, ai[2] = {12, 27};
+    const double sg[2] = {-1.0, 1.0};
+    for (int A = 0; A < 2; A++)
+      for (int B = 0; B < 2; B++)
+        for (int r = 0; r < 3; r++)
+          for (int c = 0; c < 3; c++) {
+            H30[30 * (gi[A] + r) + gi[B] + c] += sg[A] * sg[B] * X.infoG[3 * r + c];
+            H30[30 * (ai[A] + r) + ai[B] + c] += sg[A] * sg[B] * X.infoA[3 * r + c];
+          }
+    {
+      double J[225];
+      prior_jac(P, X.prev, J);
+      std::vector<double> HP(225, 0.0), db(15, 0.0);
+      int map[15];
+      for (int c = 0; c < 15; c++) map[c] = c;
+      double zero[15] = {0};
+      add_block(HP, db, 15, J, 15, 15, map, P.c_H, 1.0, zero);
+      for (int r = 0; r < 15; r++)
+        for (int c = 0; c < 15; c++) H30[30 * r + c] += HP[15 * r + c];
+    }
+    for (int r = 0; r < 6; r++)
+      for (int c = 0; c < 6; c++) H30[30 * (15 + r) + 15 + c] += Hv[6 * r + c];
+    marginalize_first15(H30.data(), Hout);
+  }
+  constraint_clamp(Hout);
+  memcpy(R->H, Hout, sizeof(Hout));
+  R->n_bad = nBad;
+  R->n_inliers_last = nInliers;
+  R->avg_reproj_error = avg;
+  R->n_inliers = N - nBad;
+}
+
+}  // namespace pin
 }  // namespace ba
 }  // namespace gfo
 
@@ -1009,4 +1459,40 @@ void gfo_so3(const double* w, double* R_exp, double* log_of_exp, double* Jr, dou
   gfo::ba::right_jac(w, Jr);
   gfo::ba::inv_right_jac(w, Jrinv);
 }
+
+void gfo_pose_inertial_optimize(const GfsPoseInertialProblem* P, GfsPoseInertialResult* R) { gfo::ba::pin::optimize(P, R); }
+// test hooks: visual edge (error, 3x6 Jacobian) at a body pose; prior edge; marginalisation; clamp
+int gfo_pin_vis_edge(const GfsPoseInertialProblem* P, const double* Rwb, const double* twb, int e, double* err3, double* J18) {
+  using namespace gfo::ba;
+  pin::Cam C{(double)P->fx, (double)P->fy, (double)P->cx, (double)P->cy, (double)P->bf, P->Rcb, P->tcb, P->tbc};
+  KF k;
+  memset(&k, 0, sizeof(k));
+  memcpy(k.Rwb, Rwb, 72); memcpy(k.twb, twb, 24);
+  const double zero[6] = {0, 0, 0, 0, 0, 0};
+  pin::cam_update(C, k, zero);  // Rcw / tcw from Rwb / twb
+  const bool mono = P->uvr[3 * (size_t)e + 2] < 0;
+  const int d = pin::vis_err(C, k, P->Xw + 3 * (size_t)e, P->uvr + 3 * (size_t)e, err3, nullptr);
+  pin::vis_jac(C, k, P->Xw + 3 * (size_t)e, mono, J18);
+  return d;
+}
+void gfo_pin_pose_update(const GfsPoseInertialProblem* P, const double* Rwb, const double* twb, const double* u6, double* Rwb_out, double* twb_out) {
+  using namespace gfo::ba;
+  pin::Cam C{(double)P->fx, (double)P->fy, (double)P->cx, (double)P->cy, (double)P->bf, P->Rcb, P->tcb, P->tbc};
+  KF k;
+  memset(&k, 0, sizeof(k));
+  memcpy(k.Rwb, Rwb, 72); memcpy(k.twb, twb, 24);
+  pin::cam_update(C, k, u6);
+  memcpy(Rwb_out, k.Rwb, 72); memcpy(twb_out, k.twb, 24);
+}
+void gfo_pin_prior_edge(const GfsPoseInertialProblem* P, const double* Rwb, const double* twb, const double* v, const double* bg,
+                        const double* ba, double* err15, double* J225) {
+  using namespace gfo::ba;
+  KF k;
+  memset(&k, 0, sizeof(k));
+  memcpy(k.Rwb, Rwb, 72); memcpy(k.twb, twb, 24); memcpy(k.vel, v, 24); memcpy(k.bg, bg, 24); memcpy(k.ba, ba, 24);
+  pin::prior_err(*P, k, err15);
+  pin::prior_jac(*P, k, J225);
+}
+void gfo_pin_marginalize(const double* H30, double* out15) { gfo::ba::pin::marginalize_first15(H30, out15); }
+void gfo_pin_clamp(double* H15) { gfo::ba::pin::constraint_clamp(H15); }
 }

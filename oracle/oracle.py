@@ -505,3 +505,68 @@ def eigen_ldlt_solve(H, b):
     x = np.zeros(len(b))
     ok = lib().gfo_eigen_ldlt_solve(_p(H), _p(b), len(b), _p(x))
     return bool(ok), x
+
+
+# ---- PoseInertialOptimizationLastKeyFrame / LastFrame (ba_oracle.cpp, namespace pin)
+def _bind_pin(L):
+    from geoflowslam_b200.pose_inertial import PoseInertialProblem, PoseInertialResult
+    PP = C.POINTER(PoseInertialProblem)
+    L.gfo_pose_inertial_optimize.argtypes = [PP, C.POINTER(PoseInertialResult)]
+    L.gfo_pin_vis_edge.restype = C.c_int
+    L.gfo_pin_vis_edge.argtypes = [PP, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.gfo_pin_pose_update.argtypes = [PP] + [C.c_void_p] * 5
+    L.gfo_pin_prior_edge.argtypes = [PP] + [C.c_void_p] * 7
+    L.gfo_pin_marginalize.argtypes = [C.c_void_p, C.c_void_p]
+    L.gfo_pin_clamp.argtypes = [C.c_void_p]
+
+
+_LATE_BINDERS.append(("gfo_pose_inertial_optimize", _bind_pin))
+
+
+def pose_inertial_optimize(prob):
+    """Optimizer::PoseInertialOptimizationLast{KeyFrame,Frame} -> dict (same keys as the product's result)"""
+    from geoflowslam_b200 import pose_inertial as pi
+    P, keep = pi.pack_problem(prob)
+    n = int(prob["n_obs"])
+    R, out = pi.alloc_result(n)
+    lib().gfo_pose_inertial_optimize(C.byref(P), C.byref(R))
+    return pi.unpack_result(R, out, n)
+
+
+def pin_vis_edge(prob, Rwb, twb, e):
+    from geoflowslam_b200 import pose_inertial as pi
+    P, keep = pi.pack_problem(prob)
+    R = np.ascontiguousarray(Rwb, np.float64); t = np.ascontiguousarray(twb, np.float64)
+    err = np.zeros(3); J = np.zeros(18)
+    d = lib().gfo_pin_vis_edge(C.byref(P), _p(R), _p(t), int(e), _p(err), _p(J))
+    return err[:d].copy(), J[:6 * d].reshape(d, 6).copy()
+
+
+def pin_pose_update(prob, Rwb, twb, u6):
+    from geoflowslam_b200 import pose_inertial as pi
+    P, keep = pi.pack_problem(prob)
+    R = np.ascontiguousarray(Rwb, np.float64); t = np.ascontiguousarray(twb, np.float64); u = np.ascontiguousarray(u6, np.float64)
+    Ro = np.zeros(9); to = np.zeros(3)
+    lib().gfo_pin_pose_update(C.byref(P), _p(R), _p(t), _p(u), _p(Ro), _p(to))
+    return Ro.reshape(3, 3), to
+
+
+def pin_prior_edge(prob, Rwb, twb, v, bg, ba):
+    from geoflowslam_b200 import pose_inertial as pi
+    P, keep = pi.pack_problem(prob)
+    a = [np.ascontiguousarray(x, np.float64) for x in (Rwb, twb, v, bg, ba)]
+    err = np.zeros(15); J = np.zeros(225)
+    lib().gfo_pin_prior_edge(C.byref(P), *[_p(x) for x in a], _p(err), _p(J))
+    return err, J.reshape(15, 15)
+
+
+def pin_marginalize(H30):
+    H = np.ascontiguousarray(H30, np.float64); out = np.zeros((15, 15))
+    lib().gfo_pin_marginalize(_p(H), _p(out))
+    return out
+
+
+def pin_clamp(H15):
+    H = np.array(H15, np.float64, order="C", copy=True)
+    lib().gfo_pin_clamp(_p(H))
+    return H
