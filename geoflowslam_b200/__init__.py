@@ -7,3 +7,4 @@ from .frontend import TrackingFrontend  # noqa: F401
 from .gicp import RegistrationGICP  # noqa: F401
 from .optimizer import Optimizer  # noqa: F401
 from .pose import PoseOptimizer  # noqa: F401
+from .pose_inertial import PoseInertialOptimizer  # noqa: F401

@@ -86,6 +86,11 @@ SIGNATURES = {
     "gfs_pose_optimize_batch": ([vp, vp, vp, ci, vp], ci),
     "gfs_pose_optimize": ([vp, vp, vp, vp], ci),
     "gfs_pose_last_launches": ([vp], ci),
+    "gfs_pose_inertial_create": ([ci, ci, C.POINTER(vp)], ci),
+    "gfs_pose_inertial_destroy": ([vp], ci),
+    "gfs_pose_inertial_optimize_batch": ([vp, vp, vp, ci, vp], ci),
+    "gfs_pose_inertial_optimize": ([vp, vp, vp, vp], ci),
+    "gfs_pose_inertial_last_launches": ([vp], ci),
     "gfs_match_bf_hamming_batch_device": ([vp, vp, vp, vp, vp, ci, ci, vp, vp], ci),
     "gfs_match_bf_hamming": ([vp, vp, ci, vp, ci, vp, vp], ci),
     "gfs_gms_filter_batch_device": ([vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp], ci),
