@@ -499,6 +499,56 @@ def run_pose(args):
     print(json.dumps(line))
 
 
+def run_pose_inertial(args):
+    """SURVEY.md 8f rank 1: Optimizer::PoseInertialOptimizationLastFrame / LastKeyFrame, one problem per frame, batched."""
+    import torch
+    from geoflowslam_b200 import PoseInertialOptimizer, synth
+    from geoflowslam_b200 import pose_inertial as pin
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    B = args.batch
+    uniq = min(B, 64)
+    # TrackLocalMap alternates: LastFrame while the map is unchanged, LastKeyFrame after a map update (Tracking.cc:3770-3795)
+    probs = [synth.pose_inertial_problem(seed=6000 + i, mode=(0 if i % 4 == 0 else 1), n_obs=400) for i in range(uniq)]
+    batch = [probs[i % uniq] for i in range(B)]
+    opt = PoseInertialOptimizer(max_obs=512, max_batch=B)
+    Ps = (pin.PoseInertialProblem * B)()
+    Rs = (pin.PoseInertialResult * B)()
+    keep = [pin.pack_problem(pr, Ps[i])[1] for i, pr in enumerate(batch)]
+    outs = [pin.alloc_result(400, Rs[i])[1] for i in range(B)]
+    stream = torch.cuda.current_stream().cuda_stream
+    call = lambda: pin.check(opt._L.gfs_pose_inertial_optimize_batch(opt._h, stream, Ps, B, Rs))
+    for _ in range(max(args.warmup, 3)):
+        call()
+    ms, clocks = _clock_block(lambda: [call() for _ in range(args.steps)], local)
+    ms /= args.steps
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    for p in probs[:32]:
+        O.pose_inertial_optimize(p)
+    cpu_s = (time.perf_counter() - t0) / 32
+    iters = float(np.mean([sum(Rs[i].gn_iterations) for i in range(B)]))
+    h2d = B * (5400 + 400 * (24 + 12 + 4 + 1))
+    d2h = B * (2000 + 400 * 5)
+    alg = B * iters * 400 * (24 + 12 + 4 + 24)  # per GN iteration one pass over (Xw, uvr, info, stored error)
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    line = {"metric": "frames/sec PoseInertialOptimizationLast{Frame,KeyFrame} 400 map-point observations per frame (SURVEY 8f rank 1)",
+            "value": B / (ms / 1e3), "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "PoseInertialOptimization: 4 rounds x 10 Gauss-Newton iterations, 15 (LastKeyFrame) / 30 (LastFrame) unknowns, 400 observations (80 % stereo), 10 % gross outliers",
+                       "batch": B, "distinct_problems": uniq, "mean_gn_iterations": iters,
+                       "note": "latency-bound dense solves, not an HBM kernel; value is measured through the host-pointer C-ABI call (the only entry point): it equals e2e"},
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_pose_inertial", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms / 1e3) / 1e9 / peak, "traffic": None},
+            "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": 1, "kind": "port",
+                             "sample": "32 frames, 1 thread (the tracking thread runs it serially)"},
+            "e2e": {"value": B / (ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": args.steps * opt.last_launches()}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -507,7 +557,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="orb", choices=["orb", "gicp", "ba", "pose"],
+    ap.add_argument("--workload", default="orb", choices=["orb", "gicp", "ba", "pose", "pose_inertial"],
                     help="orb = BASELINE configs[1] (the driver's default); gicp / ba = configs[2] / configs[3]")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -518,6 +568,8 @@ def main():
         run_ba(args)
     elif args.workload == "pose":
         run_pose(args)
+    elif args.workload == "pose_inertial":
+        run_pose_inertial(args)
     else:
         run_ours(args)
 

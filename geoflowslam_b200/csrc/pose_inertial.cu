@@ -17,8 +17,9 @@
 // One CTA per frame runs everything in ONE launch.  Threads stride over the frame's observations (error,
 // Jacobian, the 21 + 6 visual entries of H and b in registers, fixed-order block sums); thread 0 linearises the
 // inertial edge and thread 32 the prior / random-walk edges meanwhile; the 15 / 30-dim system is assembled entry-
-// parallel in shared memory; warp 0 factorises it (one lane per row) and runs the cyclic Jacobi eigen-solver of
-// the hand-over.  No fp atomics: results do not depend on scheduling.
+// parallel in shared memory, already in Eigen's pivot order (which follows from the diagonal alone), and
+// factorised by the whole CTA (rank-1 trailing updates); the eigen-decompositions of the hand-over run on the whole
+// CTA too (seven disjoint Jacobi rotations per step).  No fp atomics: results do not depend on scheduling.
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -39,7 +40,7 @@ struct PinHdr {
   double fx, fy, cx, cy, bf;
   double Rcb[9], tcb[3], tbc[3];
   double cur[KF_STRIDE], prev[KF_STRIDE];
-  double infoI[81], infoG[9], infoA[9];
+  double infoG[9], infoA[9];
   double c_Rwb[9], c_twb[3], c_vwb[3], c_bg[3], c_ba[3], c_H[225];
   float pre[GFS_BA_PRE_STRIDE];
 };
@@ -124,125 +125,197 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* s_part, doubl
   __syncthreads();
 }
 
-// Eigen::LDLT<MatrixXd>::compute + solve by one warp: lane r owns row r of the n x n matrix M (n <= 32, row-major,
-// leading dimension ld, destroyed).  Same pivoting as Eigen's unblocked algorithm (largest |diagonal|, first on
-// ties).  Returns isPositive(); x is written only then (LinearSolverDense leaves it untouched otherwise).
-__device__ bool warp_ldlt_solve(double* M, int ld, int n, const double* b, double* x, double* tmp, int* tr) {
-  const int lane = threadIdx.x & 31;
+// Eigen::LDLT<MatrixXd> pivots on the largest |diagonal| of the not-yet-eliminated part; its unblocked algorithm is
+// left-looking, so those diagonal entries are still the ORIGINAL ones: the pivot order is the diagonal sorted by
+// decreasing magnitude, known before the factorisation starts.  perm[k] = original index that ends up at position k.
+// Exactly equal diagonal entries (the three axes of a bias random walk) are ordered by index here; Eigen orders
+// them by its swap history -- either order eliminates the same unknowns, the results differ by rounding only.
+__device__ __forceinline__ void ldlt_pivot_order(const double* diag, int n, int* perm) {
+  const int i = threadIdx.x;
+  if (i < n) {
+    const double di = fabs(diag[i]);
+    int rank = 0;
+    for (int j = 0; j < n; j++) {
+      const double dj = fabs(diag[j]);
+      rank += (dj > di || (dj == di && j < i)) ? 1 : 0;
+    }
+    perm[rank] = i;
+  }
+}
+// LDL^T of the symmetrically permuted matrix (P H P^T, already in M: n <= 32, row-major, leading dimension ld, lower
+// triangle used, destroyed) by the whole CTA, then the two triangular solves by warp 0.  Right-looking: step k applies
+// the rank-1 update of column k to the trailing lower triangle, one entry per thread and pass
+// (the factors are those of Eigen's left-looking kernel up to rounding).  Returns isPositive() (Eigen's sign bookkeeping); x (in
+// the ORIGINAL ordering) is written only then (LinearSolverDense leaves it untouched otherwise).  bp = P b.
+__device__ bool block_ldlt_solve_permuted(double* M, int ld, int n, const double* bp, const int* perm, double* x, double* col) {
+  const int tid = threadIdx.x, lane = tid & 31;
   int sign = 2;  // 0 PosSemi, 1 NegSemi, 2 Zero, 3 Indefinite
 #define M_(r, c) M[(r) * ld + (c)]
   for (int k = 0; k < n; k++) {
-    double v = (lane >= k && lane < n) ? fabs(M_(lane, lane)) : -1.0;
-    int big = lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, big, o);
-      if (ov > v || (ov == v && oi < big)) { v = ov; big = oi; }
-    }
-    if (lane == 0) tr[k] = big;
-    if (k != big) {
-      if (lane < k) { const double t = M_(k, lane); M_(k, lane) = M_(big, lane); M_(big, lane) = t; }
-      if (lane > big && lane < n) { const double t = M_(lane, k); M_(lane, k) = M_(lane, big); M_(lane, big) = t; }
-      if (lane == 0) { const double t = M_(k, k); M_(k, k) = M_(big, big); M_(big, big) = t; }
-      if (lane > k && lane < big) { const double t = M_(lane, k); M_(lane, k) = M_(big, lane); M_(big, lane) = t; }
-    }
-    __syncwarp();
-    if (lane < k) tmp[lane] = M_(lane, lane) * M_(k, lane);
-    __syncwarp();
-    if (k > 0 && lane >= k && lane < n) {
-      double a = 0;
-      for (int c = 0; c < k; c++) a += M_(lane, c) * tmp[c];
-      M_(lane, k) -= a;
-    }
-    __syncwarp();
     const double akk = M_(k, k);
     const bool valid = fabs(akk) > 0;
-    if (k == 0 && !valid) {
-      sign = 2;
-      if (lane < n) tr[lane] = lane;
-      break;
-    }
-    __syncwarp();
-    if (valid && lane > k && lane < n) M_(lane, k) /= akk;
+    if (k == 0 && !valid) break;  // ZeroSign: the matrix is treated as zero (uniform)
     if (sign == 0) { if (akk < 0) sign = 3; }
     else if (sign == 1) { if (akk > 0) sign = 3; }
     else if (sign == 2) { if (akk > 0) sign = 0; else if (akk < 0) sign = 1; }
-    __syncwarp();
+    const int m = n - k - 1;
+    if (m == 0) break;
+    // l_j = M(j,k) / d_k once per row (double-buffered across steps), then the trailing update with the unscaled
+    // column: M(i,j) -= M(i,k) * l_j; warp w takes rows w, w+4, ...
+    double* cl = col + (k & 1) * 32;
+    if (tid < m) cl[tid] = valid ? M_(k + 1 + tid, k) / akk : M_(k + 1 + tid, k);
+    __syncthreads();
+    for (int i = tid >> 5; i < m; i += PIN_THREADS / 32) {
+      const int j = tid & 31;
+      if (j <= i) M_(k + 1 + i, k + 1 + j) -= M_(k + 1 + i, k) * cl[j];
+    }
+    __syncthreads();
   }
-  __syncwarp();
-  if (!(sign == 0 || sign == 2)) return false;
-  if (lane < n) tmp[lane] = b[lane];
-  __syncwarp();
-  if (lane == 0)
-    for (int k = 0; k < n; k++) { const double t = tmp[k]; tmp[k] = tmp[tr[k]]; tmp[tr[k]] = t; }
-  __syncwarp();
-  double y = lane < n ? tmp[lane] : 0.0;
-  for (int c = 0; c < n; c++) {  // L y = P b (unit lower)
-    const double yc = __shfl_sync(0xffffffffu, y, c);
-    if (lane > c && lane < n) y -= M_(lane, c) * yc;
+  // L(i,k) = M(i,k) / d_k, all columns at once
+  for (int e = tid; e < n * 32; e += PIN_THREADS) {
+    const int i = e >> 5, k = e & 31;
+    if (k < i) {
+      const double d = M_(k, k);
+      if (fabs(d) > 0) M_(i, k) /= d;
+    }
   }
-  const double tol = 1.0 / DBL_MAX;
-  if (lane < n) y = (fabs(M_(lane, lane)) > tol) ? y / M_(lane, lane) : 0.0;
-  for (int c = n - 1; c >= 1; c--) {  // L^T z = y
-    const double yc = __shfl_sync(0xffffffffu, y, c);
-    if (lane < c) y -= M_(c, lane) * yc;
+  __syncthreads();
+  const bool positive = sign == 0 || sign == 2;
+  if (positive && tid < 32) {
+    double y = lane < n ? bp[lane] : 0.0;
+    for (int c = 0; c < n; c++) {  // L y = P b (unit lower)
+      const double yc = __shfl_sync(0xffffffffu, y, c);
+      if (lane > c && lane < n) y -= M_(lane, c) * yc;
+    }
+    const double tol = 1.0 / DBL_MAX;
+    if (lane < n) y = (fabs(M_(lane, lane)) > tol) ? y / M_(lane, lane) : 0.0;
+    for (int c = n - 1; c >= 1; c--) {  // L^T z = y
+      const double yc = __shfl_sync(0xffffffffu, y, c);
+      if (lane < c) y -= M_(c, lane) * yc;
+    }
+    if (lane < n) x[perm[lane]] = y;
   }
-  if (lane < n) tmp[lane] = y;
-  __syncwarp();
-  if (lane == 0)
-    for (int k = n - 1; k >= 0; k--) { const double t = tmp[k]; tmp[k] = tmp[tr[k]]; tmp[tr[k]] = t; }
-  __syncwarp();
-  if (lane < n) x[lane] = tmp[lane];
-  __syncwarp();
 #undef M_
-  return true;
+  return positive;
 }
 
-// Cyclic Jacobi eigen-decomposition A = V diag(e) V^T of a symmetric n x n matrix (n <= 32) by one warp; A is
-// destroyed (its diagonal holds the eigenvalues).  The same rotation sequence as oracle/ba_oracle.cpp jacobi_eig.
-__device__ void warp_jacobi_eig(double* A, double* V, int n) {
-  const int k = threadIdx.x & 31;
-  for (int i = k; i < n * n; i += 32) V[i] = (i / n == i % n) ? 1.0 : 0.0;
-  __syncwarp();
+// Jacobi eigen-decomposition A = V diag(e) V^T of a symmetric N x N matrix (N odd, <= 15) by the whole CTA (128
+// threads): every round applies (N-1)/2 disjoint rotations at once (round-robin pairing, one 16-thread group per
+// pair, thread k of a group owning row / column k), N rounds per sweep.  A is destroyed (its diagonal holds the eigenvalues).  The
+// oracle runs the cyclic-by-row order; both converge to the same decomposition, and only V f(e) V^T is used.
+template <int N>
+__device__ void block_jacobi_eig(double* A, double* V, double* red) {
+  const int n = N;
+  const int tid = threadIdx.x, g = tid >> 4, k = tid & 15;
+  for (int i = tid; i < n * n; i += PIN_THREADS) V[i] = (i / n == i % n) ? 1.0 : 0.0;
+  __syncthreads();
   for (int sweep = 0; sweep < 100; sweep++) {
+    if (tid < n) {
+      double off = 0, diag = 0;
+      for (int j = 0; j < n; j++) { const double a = A[tid * n + j]; if (j == tid) diag += a * a; else off += a * a; }
+      red[tid] = off; red[16 + tid] = diag;
+    }
+    __syncthreads();
     double off = 0, diag = 0;
-    if (k < n)
-      for (int j = 0; j < n; j++) { const double a = A[k * n + j]; if (j == k) diag += a * a; else off += a * a; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); diag += __shfl_xor_sync(0xffffffffu, diag, o); }
-    if (off <= 1e-32 * diag) break;
-    for (int p = 0; p < n; p++)
-      for (int q = p + 1; q < n; q++) {
+    for (int j = 0; j < n; j++) { off += red[j]; diag += red[16 + j]; }
+    if (off <= 1e-32 * diag) break;  // uniform
+    for (int r = 0; r < n; r++) {
+      // circle method over 16 players (15 = bye): pair g+1 of round r
+      int p = (r + g + 1) % n, q = (r + n - (g + 1)) % n;
+      if (p > q) { const int t = p; p = q; q = t; }
+      double c = 1.0, s = 0.0;
+      const bool on = g < (N - 1) / 2 && k < n;
+      if (on) {
         const double apq = A[p * n + q];
-        if (apq == 0.0) continue;  // uniform: every lane reads the same element
-        const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-        __syncwarp();
-        if (k < n) {
-          const double akp = A[k * n + p], akq = A[k * n + q];
-          A[k * n + p] = c * akp - s * akq;
-          A[k * n + q] = s * akp + c * akq;
-          const double vkp = V[k * n + p], vkq = V[k * n + q];
-          V[k * n + p] = c * vkp - s * vkq;
-          V[k * n + q] = s * vkp + c * vkq;
+        if (apq != 0.0) {
+          const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+          const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          c = 1.0 / sqrt(t * t + 1.0);
+          s = t * c;
         }
-        __syncwarp();
-        if (k < n) {
-          const double apk = A[p * n + k], aqk = A[q * n + k];
-          A[p * n + k] = c * apk - s * aqk;
-          A[q * n + k] = s * apk + c * aqk;
-        }
-        __syncwarp();
       }
+      __syncwarp();  // the pair's (p,p), (q,q), (p,q) are read by its whole group before anyone overwrites them
+      if (on) {
+        const double akp = A[k * n + p], akq = A[k * n + q];
+        A[k * n + p] = c * akp - s * akq;
+        A[k * n + q] = s * akp + c * akq;
+        const double vkp = V[k * n + p], vkq = V[k * n + q];
+        V[k * n + p] = c * vkp - s * vkq;
+        V[k * n + q] = s * vkp + c * vkq;
+      }
+      __syncthreads();
+      if (on) {
+        const double apk = A[p * n + k], aqk = A[q * n + k];
+        A[p * n + k] = c * apk - s * aqk;
+        A[q * n + k] = s * apk + c * aqk;
+      }
+      __syncthreads();
+    }
   }
-  __syncwarp();
+  __syncthreads();
+}
+
+// EdgeInertial constructor (G2oTypes.cc:487-494): Info = C[0:9,0:9]^-1, symmetrised, eigenvalues < 1e-12 zeroed.
+// The inverse is the Gauss-Jordan elimination with partial pivoting the host / oracle restatement runs (the same
+// operations entry by entry), spread over the CTA; scratch: aug[9 x 18], E[81], V[81].
+__device__ void block_inertial_information(const float* C15, double* info81, double* aug, double* E, double* V, double* red) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 162; i += PIN_THREADS) {
+    const int r = i / 18, k = i % 18;
+    aug[i] = k < 9 ? (double)C15[15 * r + k] : (k - 9 == r ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  for (int c = 0; c < 9; c++) {
+    int piv = c;
+    for (int r = c + 1; r < 9; r++)
+      if (fabs(aug[r * 18 + c]) > fabs(aug[piv * 18 + c])) piv = r;
+    const bool singular = aug[piv * 18 + c] == 0.0;
+    __syncthreads();
+    if (singular) break;  // uniform
+    if (piv != c) {
+      if (tid < 18) { const double t = aug[c * 18 + tid]; aug[c * 18 + tid] = aug[piv * 18 + tid]; aug[piv * 18 + tid] = t; }
+      __syncthreads();
+    }
+    const double d = 1.0 / aug[c * 18 + c];
+    __syncthreads();
+    if (tid < 18) aug[c * 18 + tid] *= d;
+    __syncthreads();
+    double f[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int i = tid + u * PIN_THREADS;
+      f[u] = i < 162 ? aug[(i / 18) * 18 + c] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int i = tid + u * PIN_THREADS;
+      if (i < 162 && i / 18 != c && f[u] != 0.0) aug[i] -= f[u] * aug[c * 18 + i % 18];
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < 81; i += PIN_THREADS) {
+    const int r = i / 9, c = i % 9;
+    E[i] = (aug[r * 18 + 9 + c] + aug[c * 18 + 9 + r]) / 2;
+  }
+  __syncthreads();
+  block_jacobi_eig<9>(E, V, red);
+  for (int i = tid; i < 81; i += PIN_THREADS) {
+    const int r = i / 9, c = i % 9;
+    double a = 0;
+    for (int k = 0; k < 9; k++) {
+      double ev = E[10 * k];
+      if (ev < 1e-12) ev = 0;
+      a += V[9 * r + k] * ev * V[9 * c + k];
+    }
+    info81[i] = a;
+  }
+  __syncthreads();
 }
 
 struct PinShared {
   double cur[KF_STRIDE], prev[KF_STRIDE];
-  double H[MAXD * MAXD], b[MAXD], x[MAXD], tmp[32];
+  double H[MAXD * (MAXD + 1)], b[MAXD], x[MAXD], tmp[32], hd[32], col[64];  // H rows padded to an odd length (bank spread)
   double J[225], WJ[225], We[16];   // inertial edge: 9 x 24; prior edge: 15 x 15 (second slot)
   double Jp[225], WJp[225], Wep[16];
   double infoI[81];
@@ -250,7 +323,7 @@ struct PinShared {
   double wI, wP, deltaI;
   double sums[28], part[(PIN_THREADS / 32) * 28];
   double V[225], E[225];
-  int tr[32];
+  int perm[32];
   int ok, counts[3];
 };
 
@@ -285,7 +358,7 @@ __device__ double quad_form(const double* e, const double* Om, int n) {
   return s;
 }
 
-__global__ void __launch_bounds__(PIN_THREADS) k_pose_inertial(const PinHdr* __restrict__ hdr, const double* __restrict__ gXw,
+__global__ void __launch_bounds__(PIN_THREADS, 4) k_pose_inertial(const PinHdr* __restrict__ hdr, const double* __restrict__ gXw,
                                                                const float* __restrict__ guvr, const float* __restrict__ gis2,
                                                                const uint8_t* __restrict__ gclose, double* __restrict__ gerr,
                                                                uint8_t* __restrict__ glevel, uint8_t* __restrict__ goutlier,
@@ -310,11 +383,11 @@ __global__ void __launch_bounds__(PIN_THREADS) k_pose_inertial(const PinHdr* __r
   C.Rcb = h.Rcb; C.tcb = h.tcb; C.tbc = h.tbc;
   const double deltaMono = (double)(float)sqrt(5.991), deltaStereo = (double)(float)sqrt(7.815);
   for (int i = tid; i < KF_STRIDE; i += PIN_THREADS) { S.cur[i] = h.cur[i]; S.prev[i] = h.prev[i]; }
-  for (int i = tid; i < 81; i += PIN_THREADS) S.infoI[i] = h.infoI[i];
   for (int i = tid; i < MAXD; i += PIN_THREADS) S.x[i] = 0.0;
   for (int e = tid; e < n; e += PIN_THREADS) { level[e] = 0; outlier[e] = 0; chi2[e] = 0.f; }
   if (tid == 0) { S.deltaI = 6.0; S.ok = 1; }
   __syncthreads();
+  block_inertial_information(h.pre + 60, S.infoI, S.H, S.E, S.V, S.tmp);
   const bool lastKF = !freePrev;
   const float chi2MonoKF[4] = {12, 7.5, 5.991, 5.991}, chi2MonoF[4] = {5.991, 5.991, 5.991, 5.991};
   const float chi2Stereo[4] = {15.6f, 9.8f, 7.815f, 7.815f};
@@ -377,8 +450,6 @@ __global__ void __launch_bounds__(PIN_THREADS) k_pose_inertial(const PinHdr* __r
       }
       block_sum<27>(acc, S.part, S.sums);  // barriers inside: the serial edges are published too
       // ---- assembly, entry-parallel
-      for (int i = tid; i < dim * dim; i += PIN_THREADS) S.H[i] = 0.0;
-      for (int i = tid; i < dim; i += PIN_THREADS) S.b[i] = 0.0;
       for (int i = tid; i < 9 * 24; i += PIN_THREADS) {  // WJ = (w Omega) J
         const int r = i / 24, c = i % 24;
         double a = 0;
@@ -405,9 +476,8 @@ __global__ void __launch_bounds__(PIN_THREADS) k_pose_inertial(const PinHdr* __r
         }
       }
       __syncthreads();
-      // every H entry is owned by one thread; the edges are added in a fixed order: visual, inertial, RW, prior
-      for (int i = tid; i < dim * dim; i += PIN_THREADS) {
-        const int a = i / dim, c = i % dim;
+      // entry (a, c) of H: the edges are added in a fixed order: visual, inertial, random walks, prior
+      auto h_entry = [&](int a, int c) {
         double v = 0.0;
         if (a < 6 && c < 6) {
           const int lo = min(a, c), hi = max(a, c);
@@ -416,31 +486,31 @@ __global__ void __launch_bounds__(PIN_THREADS) k_pose_inertial(const PinHdr* __r
         // inertial: unknown a -> Jacobian column (cur pose/vel 0..8 -> 15..23, prev 15..29 -> 0..14)
         const int ja = a < 9 ? 15 + a : (a >= 15 ? a - 15 : -1), jc = c < 9 ? 15 + c : (c >= 15 ? c - 15 : -1);
         if (ja >= 0 && jc >= 0) {
-          double s = 0;
-          for (int r = 0; r < 9; r++) s += S.J[24 * r + ja] * S.WJ[24 * r + jc];
-          v += s;
+          double t = 0;
+#pragma unroll
+          for (int r = 0; r < 9; r++) t += S.J[24 * r + ja] * S.WJ[24 * r + jc];
+          v += t;
         }
         // random walks: J = [-I, I] over (prev bias, cur bias)
-        {
-          const int ga = (a >= 9 && a < 12) ? a - 9 : ((a >= 24 && a < 27) ? a - 24 : -1), gc = (c >= 9 && c < 12) ? c - 9 : ((c >= 24 && c < 27) ? c - 24 : -1);
-          if (ga >= 0 && gc >= 0) v += (((a >= 24) != (c >= 24)) ? -1.0 : 1.0) * h.infoG[3 * ga + gc];
-          const int aa = (a >= 12 && a < 15) ? a - 12 : ((a >= 27 && a < 30) ? a - 27 : -1), ac = (c >= 12 && c < 15) ? c - 12 : ((c >= 27 && c < 30) ? c - 27 : -1);
-          if (aa >= 0 && ac >= 0) v += (((a >= 27) != (c >= 27)) ? -1.0 : 1.0) * h.infoA[3 * aa + ac];
-        }
+        const int ga = (a >= 9 && a < 12) ? a - 9 : ((a >= 24 && a < 27) ? a - 24 : -1), gc = (c >= 9 && c < 12) ? c - 9 : ((c >= 24 && c < 27) ? c - 24 : -1);
+        if (ga >= 0 && gc >= 0) v += (((a >= 24) != (c >= 24)) ? -1.0 : 1.0) * h.infoG[3 * ga + gc];
+        const int aa = (a >= 12 && a < 15) ? a - 12 : ((a >= 27 && a < 30) ? a - 27 : -1), ac = (c >= 12 && c < 15) ? c - 12 : ((c >= 27 && c < 30) ? c - 27 : -1);
+        if (aa >= 0 && ac >= 0) v += (((a >= 27) != (c >= 27)) ? -1.0 : 1.0) * h.infoA[3 * aa + ac];
         if (freePrev && a >= 15 && c >= 15) {
-          double s = 0;
-          for (int r = 0; r < 15; r++) s += S.Jp[15 * r + (a - 15)] * S.WJp[15 * r + (c - 15)];
-          v += s;
+          double t = 0;
+#pragma unroll
+          for (int r = 0; r < 15; r++) t += S.Jp[15 * r + (a - 15)] * S.WJp[15 * r + (c - 15)];
+          v += t;
         }
-        S.H[i] = v;
-      }
-      for (int a = tid; a < dim; a += PIN_THREADS) {
+        return v;
+      };
+      auto b_entry = [&](int a) {
         double v = a < 6 ? S.sums[21 + a] : 0.0;
         const int ja = a < 9 ? 15 + a : (a >= 15 ? a - 15 : -1);
         if (ja >= 0) {
-          double s = 0;
-          for (int r = 0; r < 9; r++) s += S.J[24 * r + ja] * S.We[r];
-          v -= s;
+          double t = 0;
+          for (int r = 0; r < 9; r++) t += S.J[24 * r + ja] * S.We[r];
+          v -= t;
         }
         if ((a >= 9 && a < 12) || (a >= 24 && a < 27)) {
           const int r = a >= 24 ? a - 24 : a - 9;
@@ -453,24 +523,36 @@ __global__ void __launch_bounds__(PIN_THREADS) k_pose_inertial(const PinHdr* __r
           v -= (a >= 27 ? -1.0 : 1.0) * g;
         }
         if (freePrev && a >= 15) {
-          double s = 0;
-          for (int r = 0; r < 15; r++) s += S.Jp[15 * r + (a - 15)] * S.Wep[r];
-          v -= s;
+          double t = 0;
+          for (int r = 0; r < 15; r++) t += S.Jp[15 * r + (a - 15)] * S.Wep[r];
+          v -= t;
         }
-        S.b[a] = v;
+        return v;
+      };
+      // the diagonal first: it fixes Eigen's pivot order, H is then assembled already permuted
+      if (tid < dim) S.hd[tid] = h_entry(tid, tid);
+      __syncthreads();
+      ldlt_pivot_order(S.hd, dim, S.perm);
+      __syncthreads();
+      const int ld = dim + 1;
+      for (int i = tid; i < dim * dim; i += PIN_THREADS) {
+        const int r = i / dim, c = i % dim;
+        if (c <= r) S.H[r * ld + c] = h_entry(S.perm[r], S.perm[c]);
       }
+      if (tid < dim) S.b[tid] = b_entry(S.perm[tid]);
       __syncthreads();
       // ---- solve + update
-      if (tid < 32) {
-        const bool ok = warp_ldlt_solve(S.H, dim, dim, S.b, S.x, S.tmp, S.tr);
-        if (tid == 0) {
-          S.ok = ok ? 1 : 0;
-          state_oplus(C, S.cur, S.x);
-          for (int i = 0; i < 3; i++) { S.cur[K_VEL + i] += S.x[6 + i]; S.cur[K_BG + i] += S.x[9 + i]; S.cur[K_BA + i] += S.x[12 + i]; }
-        } else if (tid == 1 && freePrev) {
-          state_oplus(C, S.prev, S.x + 15);
-          for (int i = 0; i < 3; i++) { S.prev[K_VEL + i] += S.x[21 + i]; S.prev[K_BG + i] += S.x[24 + i]; S.prev[K_BA + i] += S.x[27 + i]; }
-        }
+      {
+        const bool ok = block_ldlt_solve_permuted(S.H, ld, dim, S.b, S.perm, S.x, S.col);
+        if (tid == 0) S.ok = ok ? 1 : 0;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        state_oplus(C, S.cur, S.x);
+        for (int i = 0; i < 3; i++) { S.cur[K_VEL + i] += S.x[6 + i]; S.cur[K_BG + i] += S.x[9 + i]; S.cur[K_BA + i] += S.x[12 + i]; }
+      } else if (tid == 32 && freePrev) {
+        state_oplus(C, S.prev, S.x + 15);
+        for (int i = 0; i < 3; i++) { S.prev[K_VEL + i] += S.x[21 + i]; S.prev[K_BG + i] += S.x[24 + i]; S.prev[K_BA + i] += S.x[27 + i]; }
       }
       __syncthreads();
       gnIters[it]++;
@@ -514,27 +596,25 @@ __global__ void __launch_bounds__(PIN_THREADS) k_pose_inertial(const PinHdr* __r
       if (isBad) { outlier[e] = 1; level[e] = 1; bad++; }
       else { outlier[e] = 0; level[e] = 0; good++; }
     }
+    // counts (integers: order-free) and the chi2 sum of the inliers.  The reference adds the chi2 in float, monocular
+    // edges first, then stereo, in frame order; here both groups are summed in double in the block's fixed tree order
+    // and narrowed once (the two agree to float rounding, ~1e-7 relative)
+    double cs[2] = {0.0, 0.0};
+    for (int e = tid; e < n; e += PIN_THREADS)
+      if (!outlier[e]) cs[uvr[3 * (size_t)e + 2] < 0 ? 0 : 1] += (double)chi2[e];
     if (tid == 0) { S.counts[0] = 0; S.counts[1] = 0; }
-    __syncthreads();
+    block_sum<2>(cs, S.part, S.sums);
     atomicAdd(&S.counts[0], bad);
     atomicAdd(&S.counts[1], good);
     __syncthreads();
     nBad = S.counts[0];
     nInliers = S.counts[1];
-    if (tid == 0) {
-      // avgReprojectionError: float sum, monocular edges first, then stereo, each in frame order
-      float avg = 0.0f;
-      for (int pass = 0; pass < 2; pass++)
-        for (int e = 0; e < n; e++) {
-          const bool mono = uvr[3 * (size_t)e + 2] < 0;
-          if (mono != (pass == 0) || outlier[e]) continue;
-          avg += chi2[e];
-        }
+    {
+      float avg = (float)S.sums[0] + (float)S.sums[1];
       avg /= nInliers;
-      S.counts[2] = __float_as_int(avg);
+      avgOut = avg;
     }
     __syncthreads();
-    avgOut = __int_as_float(S.counts[2]);
     roundsDone = it + 1;
     if (n + (freePrev ? 4 : 3) < 10) break;  // optimizer.edges().size() < 10
   }
@@ -643,8 +723,7 @@ __global__ void __launch_bounds__(PIN_THREADS) k_pose_inertial(const PinHdr* __r
     // Optimizer::Marginalize(H, 0, 14): pseudo-inverse of the previous frame's block through its eigen-decomposition
     for (int i = tid; i < 225; i += PIN_THREADS) S.E[i] = S.H[30 * (i / 15) + (i % 15)];
     __syncthreads();
-    if (tid < 32) warp_jacobi_eig(S.E, S.V, 15);
-    __syncthreads();
+    block_jacobi_eig<15>(S.E, S.V, S.tmp);
     for (int i = tid; i < 225; i += PIN_THREADS) {  // inv = V diag(1/lambda, |lambda| > 1e-6) V^T
       const int r = i / 15, c = i % 15;
       double a = 0;
@@ -677,8 +756,7 @@ __global__ void __launch_bounds__(PIN_THREADS) k_pose_inertial(const PinHdr* __r
     S.E[i] = (v + v) / 2;
   }
   __syncthreads();
-  if (tid < 32) warp_jacobi_eig(S.E, S.V, 15);
-  __syncthreads();
+  block_jacobi_eig<15>(S.E, S.V, S.tmp);
   for (int i = tid; i < 225; i += PIN_THREADS) {
     const int r = i / 15, c = i % 15;
     double a = 0;
@@ -783,7 +861,6 @@ int gfs_pose_inertial_optimize_batch(GfsPoseInertial* h, void* stream, const Gfs
     memcpy(H.prev + K_RWB, P.p_Rwb, 72); memcpy(H.prev + K_TWB, P.p_twb, 24); memcpy(H.prev + K_VEL, P.p_vel, 24);
     memcpy(H.prev + K_BG, P.p_bg, 24); memcpy(H.prev + K_BA, P.p_ba, 24);
     memcpy(H.pre, P.pre, sizeof(H.pre));
-    inertial_information(P.pre + 60, H.infoI);  // EdgeInertial ctor (G2oTypes.cc:487-494)
     double Cg[9], Ca[9];
     for (int i = 0; i < 9; i++) { Cg[i] = (double)P.rw_Cg[i]; Ca[i] = (double)P.rw_Ca[i]; }
     inv3_host(Cg, H.infoG);

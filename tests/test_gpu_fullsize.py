@@ -91,3 +91,25 @@ def test_configs3_batch_of_64_problems():
     g = res[1]
     assert g["lm_trials"] == o["lm_trials"] and g["iterations_done"] == o["iterations_done"]
     assert np.allclose(g["kf_twb"], o["kf_twb"], atol=1e-6) and np.allclose(g["pt_xyz"], o["pt_xyz"], atol=1e-6)
+
+
+def test_pose_inertial_batch_of_512_frames():
+    """Size-independent properties at a tracking-rate batch: every frame of the batch is solved exactly like the same
+    frame alone (the batch shares no state), results are permutation-equivariant, and the prior that comes out is
+    symmetric positive semi-definite."""
+    from geoflowslam_b200 import PoseInertialOptimizer, synth
+    uniq = [synth.pose_inertial_problem(6300 + i, mode=i % 2, n_obs=200 + 37 * (i % 7)) for i in range(16)]
+    order = np.random.default_rng(0).permutation(512)
+    batch = [uniq[j % 16] for j in order]
+    opt = PoseInertialOptimizer(max_obs=512, max_batch=512)
+    res = opt.optimize_batch(batch)
+    one = PoseInertialOptimizer(max_obs=512, max_batch=1)
+    ref = [one.optimize_batch([p])[0] for p in uniq]
+    for j, r in zip(order, res):
+        o = ref[j % 16]
+        assert np.array_equal(r["twb"], o["twb"]) and np.array_equal(r["Rwb"], o["Rwb"]) and np.array_equal(r["outlier"], o["outlier"])
+        assert np.array_equal(r["H"], o["H"]) and r["n_inliers"] == o["n_inliers"]
+    for o in ref:
+        H = o["H"]
+        assert np.allclose(H, H.T, rtol=0, atol=1e-9 * np.abs(H).max())
+        assert np.linalg.eigvalsh((H + H.T) / 2).min() > -1e-9 * np.abs(H).max()
