@@ -570,3 +570,84 @@ def pin_clamp(H15):
     H = np.array(H15, np.float64, order="C", copy=True)
     lib().gfo_pin_clamp(_p(H))
     return H
+
+
+# ---- optical-flow front end (klt_oracle.cpp): buildOpticalFlowPyramid, calcOpticalFlowPyrLK, fbKltTracking
+def _bind_klt(L):
+    vp_, ci_, cf_ = C.c_void_p, C.c_int, C.c_float
+    L.gfo_pyr_down.argtypes = [vp_, ci_, ci_, vp_]
+    L.gfo_scharr.argtypes = [vp_, ci_, ci_, vp_]
+    L.gfo_klt_pyramid_pixels.restype = ci_
+    L.gfo_klt_pyramid_pixels.argtypes = [ci_, ci_, ci_]
+    L.gfo_klt_build_pyramid.argtypes = [vp_, ci_, ci_, ci_, vp_, vp_]
+    L.gfo_klt_calc.argtypes = [vp_, vp_, vp_, vp_, ci_, ci_, ci_, vp_, vp_, ci_, ci_, ci_, ci_, cf_, ci_, vp_, vp_]
+    L.gfo_fb_klt.argtypes = [vp_, vp_, vp_, vp_, ci_, ci_, ci_, vp_, vp_, ci_, ci_, ci_, cf_, cf_, vp_]
+
+
+_LATE_BINDERS.append(("gfo_fb_klt", _bind_klt))
+
+
+def pyr_down(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros(((h + 1) // 2, (w + 1) // 2), np.uint8)
+    lib().gfo_pyr_down(_p(img), w, h, _p(out))
+    return out
+
+
+def scharr_deriv(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros((h, w, 2), np.int16)
+    lib().gfo_scharr(_p(img), w, h, _p(out))
+    return out
+
+
+def klt_level_shapes(w, h, levels):
+    out = []
+    for _ in range(levels + 1):
+        out.append((h, w))
+        w, h = (w + 1) // 2, (h + 1) // 2
+    return out
+
+
+def klt_build_pyramid(img, levels=3):
+    """cv::buildOpticalFlowPyramid(img, pyr, winSize, levels) -> (packed images u8, packed derivatives int16)"""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    n = lib().gfo_klt_pyramid_pixels(w, h, levels)
+    pi = np.zeros(n, np.uint8); pd = np.zeros(2 * n, np.int16)
+    lib().gfo_klt_build_pyramid(_p(img), w, h, levels, _p(pi), _p(pd))
+    return pi, pd
+
+
+def klt_unpack(pyr, w, h, levels):
+    pi, pd = pyr
+    out, off = [], 0
+    for (lh, lw) in klt_level_shapes(w, h, levels):
+        out.append((pi[off:off + lh * lw].reshape(lh, lw), pd[2 * off:2 * (off + lh * lw)].reshape(lh, lw, 2)))
+        off += lh * lw
+    return out
+
+
+def klt_calc(prev_pyr, cur_pyr, w, h, levels, pts, init=None, win=35, max_level=3, max_count=30, eps=0.01):
+    """cv::calcOpticalFlowPyrLK(prevPyr, curPyr, ..., OPTFLOW_LK_GET_MIN_EIGENVALS [| USE_INITIAL_FLOW])
+    -> (next points (n,2) f32, status (n,) u8, min eigenvalues (n,) f32)"""
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    n = len(pts)
+    nxt = np.ascontiguousarray(pts if init is None else init, np.float32).reshape(-1, 2).copy()
+    st = np.zeros(max(n, 1), np.uint8); er = np.zeros(max(n, 1), np.float32)
+    lib().gfo_klt_calc(_p(prev_pyr[0]), _p(prev_pyr[1]), _p(cur_pyr[0]), _p(cur_pyr[1]), w, h, levels, _p(pts), _p(nxt), n, win,
+                       max_level, max_count, eps, 0 if init is None else 1, _p(st), _p(er))
+    return nxt, st[:n], er[:n]
+
+
+def fb_klt_tracking(prev_pyr, cur_pyr, w, h, levels, kps, priors, win=35, nbpyrlvl=3, ferr=15.0, max_fbklt_dist=0.5):
+    """ORBmatcher::fbKltTracking -> (priors after tracking (n,2) f32, vkpstatus (n,) bool)"""
+    kps = np.ascontiguousarray(kps, np.float32).reshape(-1, 2)
+    pr = np.ascontiguousarray(priors, np.float32).reshape(-1, 2).copy()
+    n = len(kps)
+    st = np.zeros(max(n, 1), np.uint8)
+    lib().gfo_fb_klt(_p(prev_pyr[0]), _p(prev_pyr[1]), _p(cur_pyr[0]), _p(cur_pyr[1]), w, h, levels, _p(kps), _p(pr), n, win, nbpyrlvl,
+                     ferr, max_fbklt_dist, _p(st))
+    return pr, st[:n].astype(bool)
