@@ -8,3 +8,4 @@ from .gicp import RegistrationGICP  # noqa: F401
 from .optimizer import Optimizer  # noqa: F401
 from .pose import PoseOptimizer  # noqa: F401
 from .pose_inertial import PoseInertialOptimizer  # noqa: F401
+from .klt import KltTracker  # noqa: F401

@@ -91,6 +91,15 @@ SIGNATURES = {
     "gfs_pose_inertial_optimize_batch": ([vp, vp, vp, ci, vp], ci),
     "gfs_pose_inertial_optimize": ([vp, vp, vp, vp], ci),
     "gfs_pose_inertial_last_launches": ([vp], ci),
+    "gfs_klt_create": ([ci, ci, ci, ci, ci, C.POINTER(vp)], ci),
+    "gfs_klt_destroy": ([vp], ci),
+    "gfs_klt_pyramid_bytes": ([vp, ci, ci], C.c_size_t),
+    "gfs_klt_pyramid_layout": ([vp, ci, ci, vp, vp, vp, vp], ci),
+    "gfs_klt_build_pyramid_batch_device": ([vp, vp, vp, ci, ci, ci, ci, C.c_size_t, vp], ci),
+    "gfs_klt_fb_track_batch_device": ([vp, vp, vp, vp, ci, ci, ci, vp, vp, vp, ci, ci, ci, C.c_float, C.c_float, vp], ci),
+    "gfs_klt_calc_batch_device": ([vp, vp, vp, vp, ci, ci, ci, vp, vp, vp, ci, ci, ci, ci, C.c_float, ci, vp, vp], ci),
+    "gfs_klt_fb_track": ([vp, vp, vp, vp, ci, ci, ci, vp, vp, ci, ci, ci, C.c_float, C.c_float, vp], ci),
+    "gfs_klt_last_launches": ([vp], ci),
     "gfs_match_bf_hamming_batch_device": ([vp, vp, vp, vp, vp, ci, ci, vp, vp], ci),
     "gfs_match_bf_hamming": ([vp, vp, ci, vp, ci, vp, vp], ci),
     "gfs_gms_filter_batch_device": ([vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp], ci),

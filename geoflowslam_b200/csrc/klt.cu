@@ -1,0 +1,451 @@
+// Optical-flow front end on sm_100a, batched over frames / frame pairs.
+//
+// Replaces
+//   cv::buildOpticalFlowPyramid(image, mImGray, winSize, 3)                 reference src/Frame.cc:370-373
+//   ORBmatcher::fbKltTracking / Tracking::fbKltTracking                     src/ORBmatcher.cc:2186-2293, src/Tracking.cc:3262-3360
+//     (two cv::calcOpticalFlowPyrLK calls with OPTFLOW_USE_INITIAL_FLOW | OPTFLOW_LK_GET_MIN_EIGENVALS, 30 iterations,
+//      eps 0.01: forward over nbpyrlvl levels, status / min-eigenvalue / inBorder filter, backward at level 0,
+//      forward-backward distance check)
+// OpenCV's arithmetic restated (modules/imgproc/src/pyramids.cpp pyrDown 8U; modules/video/src/lkpyramid.cpp
+// calcScharrDeriv, LKTrackerInvoker): everything up to the 2x2 solve is integer / fixed point and is reproduced
+// exactly; the sums of integer products OpenCV accumulates in float SIMD lanes are accumulated exactly in int64
+// (order-free, so the result does not depend on the lane layout) and narrowed once.
+//
+//   k_klt_pyr_down   CTA per 32x8 destination tile: the 68x20 source window staged in shared memory, separable
+//                    [1 4 6 4 1], (sum + 128) >> 8
+//   k_klt_scharr     thread per pixel: int16 (dI/dx, dI/dy), reflect-101 inside the image
+//   k_klt_track      one warp per point, all pyramid levels and both passes in ONE launch: the 35x35 template patch
+//                    (int16 intensities with 5 fractional bits + int16 derivatives) lives in shared memory, the
+//                    36x36 window of the other image is staged per iteration, the five sums are warp-reduced int64
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gfs {
+namespace klt {
+
+static const int MAX_LEVELS = 8;
+static const int TRACK_WARPS = 4;
+
+struct PyrGeom {
+  int levels;                 // number of levels above level 0
+  int w[MAX_LEVELS + 1], h[MAX_LEVELS + 1];
+  int off[MAX_LEVELS + 1];    // pixel offset of the level inside the packed image / derivative arrays
+  int npix;                   // total pixels over all levels
+  size_t imgBytes;            // npix rounded up to 16: the derivatives start there
+  size_t frameBytes;          // imgBytes + 4 * npix
+};
+
+static PyrGeom make_geom(int w, int h, int levels) {
+  PyrGeom g;
+  memset(&g, 0, sizeof(g));
+  g.levels = levels;
+  int off = 0;
+  for (int l = 0; l <= levels; l++) {
+    g.w[l] = w; g.h[l] = h; g.off[l] = off;
+    off += w * h;
+    w = (w + 1) / 2; h = (h + 1) / 2;
+  }
+  g.npix = off;
+  g.imgBytes = align_up((size_t)off, 16);
+  g.frameBytes = g.imgBytes + (size_t)4 * off;
+  return g;
+}
+
+__device__ __forceinline__ int reflect101(int p, int len) {  // cv::borderInterpolate(BORDER_REFLECT_101)
+  if (len == 1) return 0;
+  while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+  return p;
+}
+
+// ---- cv::pyrDown, 8U: dst (dw x dh) from src (sw x sh), one frame per blockIdx.z
+static const int PD_TX = 32, PD_TY = 8;
+__global__ void __launch_bounds__(PD_TX * PD_TY) k_klt_pyr_down(uint8_t* __restrict__ pyr, size_t frameBytes, int srcOff, int sw, int sh,
+                                                                int dstOff, int dw, int dh) {
+  __shared__ uint8_t s_src[2 * PD_TY + 3][2 * PD_TX + 4];
+  __shared__ int s_row[2 * PD_TY + 3][PD_TX];
+  const uint8_t* src = pyr + (size_t)blockIdx.z * frameBytes + srcOff;
+  uint8_t* dst = pyr + (size_t)blockIdx.z * frameBytes + dstOff;
+  const int x0 = blockIdx.x * PD_TX, y0 = blockIdx.y * PD_TY;
+  const int tid = threadIdx.y * PD_TX + threadIdx.x;
+  for (int i = tid; i < (2 * PD_TY + 3) * (2 * PD_TX + 4); i += PD_TX * PD_TY) {
+    const int r = i / (2 * PD_TX + 4), c = i % (2 * PD_TX + 4);
+    s_src[r][c] = src[(size_t)reflect101(2 * y0 - 2 + r, sh) * sw + reflect101(2 * x0 - 2 + c, sw)];
+  }
+  __syncthreads();
+  for (int i = tid; i < (2 * PD_TY + 3) * PD_TX; i += PD_TX * PD_TY) {
+    const int r = i / PD_TX, x = i % PD_TX;
+    const uint8_t* s = &s_src[r][2 * x];
+    s_row[r][x] = s[0] + s[4] + 4 * (s[1] + s[3]) + 6 * s[2];
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  if (x < dw && y < dh) {
+    const int r = 2 * threadIdx.y, c = threadIdx.x;
+    const int v = s_row[r][c] + s_row[r + 4][c] + 4 * (s_row[r + 1][c] + s_row[r + 3][c]) + 6 * s_row[r + 2][c];
+    dst[(size_t)y * dw + x] = (uint8_t)((v + 128) >> 8);
+  }
+}
+
+// ---- calcScharrDeriv for every level of every frame: thread per pixel of the packed pyramid
+__global__ void __launch_bounds__(256) k_klt_scharr(uint8_t* __restrict__ pyr, PyrGeom G) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G.npix) return;
+  int l = 0;
+  while (l < G.levels && i >= G.off[l + 1]) l++;
+  const int w = G.w[l], h = G.h[l], p = i - G.off[l];
+  const int y = p / w, x = p - y * w;
+  const uint8_t* img = pyr + (size_t)blockIdx.y * G.frameBytes + G.off[l];
+  short2* der = reinterpret_cast<short2*>(pyr + (size_t)blockIdx.y * G.frameBytes + G.imgBytes) + i;
+  const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+  const uint8_t* r0 = img + (size_t)reflect101(y - 1, h) * w;
+  const uint8_t* r1 = img + (size_t)y * w;
+  const uint8_t* r2 = img + (size_t)reflect101(y + 1, h) * w;
+  const int t0m = (r0[xm] + r2[xm]) * 3 + r1[xm] * 10, t0p = (r0[xp] + r2[xp]) * 3 + r1[xp] * 10;
+  const int t1m = r2[xm] - r0[xm], t1c = r2[x] - r0[x], t1p = r2[xp] - r0[xp];
+  *der = make_short2((short)(t0p - t0m), (short)((t1p + t1m) * 3 + t1c * 10));
+}
+
+// ---- LKTrackerInvoker for one point by one warp
+struct LevelView { const uint8_t* img; const short2* der; int w, h; };
+__device__ __forceinline__ LevelView level_view(const uint8_t* frame, const PyrGeom& G, int l) {
+  LevelView v;
+  v.img = frame + G.off[l];
+  v.der = reinterpret_cast<const short2*>(frame + G.imgBytes) + G.off[l];
+  v.w = G.w[l]; v.h = G.h[l];
+  return v;
+}
+__device__ __forceinline__ int descale(int v, int n) { return (v + (1 << (n - 1))) >> n; }
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// stage the (win+1) x (win+1) window of `img` whose top-left pixel is (x0, y0) (reflect-101 outside the image)
+__device__ __forceinline__ void stage_window(const LevelView& L, int x0, int y0, int win, uint8_t* s_win) {
+  const int lane = threadIdx.x & 31, ww = win + 1;
+  const bool inside = x0 >= 0 && y0 >= 0 && x0 + ww <= L.w && y0 + ww <= L.h;
+  int x = lane, y = 0;
+  while (x >= ww) { x -= ww; y++; }
+  for (int i = lane; i < ww * ww; i += 32) {
+    const int X = inside ? x0 + x : reflect101(x0 + x, L.w), Y = inside ? y0 + y : reflect101(y0 + y, L.h);
+    s_win[i] = L.img[(size_t)Y * L.w + X];
+    x += 32;
+    while (x >= ww) { x -= ww; y++; }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ short2 der_at(const LevelView& L, int x, int y) {
+  if (x < 0 || y < 0 || x >= L.w || y >= L.h) return make_short2(0, 0);  // derivBorder = BORDER_CONSTANT
+  return L.der[(size_t)y * L.w + x];
+}
+// One pyramid level.  (nx, ny) in/out as OpenCV's nextPts[ptidx]; status / err updated as the invoker does.
+__device__ void lk_level(const LevelView& I, const LevelView& J, int level, int maxLevel, int win, int maxCount, float eps2,
+                         bool useInitial, float px, float py, float& nx, float& ny, int& status, float& err, short* s_I, short2* s_dI,
+                         uint8_t* s_win) {
+  const int lane = threadIdx.x & 31, ww = win + 1;
+  const float halfWin = (win - 1) * 0.5f;
+  const float sc = (float)(1. / (1 << level));
+  float prevx = px * sc, prevy = py * sc;
+  float nextx, nexty;
+  if (level == maxLevel) {
+    if (useInitial) { nextx = nx * sc; nexty = ny * sc; }
+    else { nextx = prevx; nexty = prevy; }
+  } else {
+    nextx = nx * 2.f; nexty = ny * 2.f;
+  }
+  nx = nextx; ny = nexty;
+  prevx -= halfWin; prevy -= halfWin;
+  const int ipx = (int)floorf(prevx), ipy = (int)floorf(prevy);
+  if (ipx < -win || ipx >= I.w || ipy < -win || ipy >= I.h) {
+    if (level == 0) { status = 0; err = 0; }
+    return;
+  }
+  float a = prevx - ipx, b = prevy - ipy;
+  const int W_BITS = 14;
+  const float FLT_SCALE = 1.f / (1 << 20);
+  int iw00 = __float2int_rn((1.f - a) * (1.f - b) * (1 << W_BITS));
+  int iw01 = __float2int_rn(a * (1.f - b) * (1 << W_BITS));
+  int iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS));
+  int iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+  __syncwarp();
+  stage_window(I, ipx, ipy, win, s_win);
+  long long sA11 = 0, sA12 = 0, sA22 = 0;
+  {
+    int x = lane, y = 0;
+    while (x >= win) { x -= win; y++; }
+    for (int i = lane; i < win * win; i += 32) {
+      const uint8_t* s = s_win + y * ww + x;
+      const int ival = descale(s[0] * iw00 + s[1] * iw01 + s[ww] * iw10 + s[ww + 1] * iw11, W_BITS - 5);
+      const int X = ipx + x, Y = ipy + y;
+      const short2 d00 = der_at(I, X, Y), d01 = der_at(I, X + 1, Y), d10 = der_at(I, X, Y + 1), d11 = der_at(I, X + 1, Y + 1);
+      const int ixval = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, W_BITS);
+      const int iyval = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, W_BITS);
+      s_I[i] = (short)ival;
+      s_dI[i] = make_short2((short)ixval, (short)iyval);
+      sA11 += (long long)ixval * ixval; sA12 += (long long)ixval * iyval; sA22 += (long long)iyval * iyval;
+      x += 32;
+      while (x >= win) { x -= win; y++; }
+    }
+  }
+  sA11 = warp_sum_ll(sA11); sA12 = warp_sum_ll(sA12); sA22 = warp_sum_ll(sA22);
+  const float A11 = (float)sA11 * FLT_SCALE, A12 = (float)sA12 * FLT_SCALE, A22 = (float)sA22 * FLT_SCALE;
+  float D = A11 * A22 - A12 * A12;
+  const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+  err = minEig;  // OPTFLOW_LK_GET_MIN_EIGENVALS
+  if (minEig < 1e-4f || D < FLT_EPSILON) {
+    if (level == 0) status = 0;
+    return;
+  }
+  D = 1.f / D;
+  nextx -= halfWin; nexty -= halfWin;
+  float pdx = 0, pdy = 0;
+  for (int j = 0; j < maxCount; j++) {
+    const int inx = (int)floorf(nextx), iny = (int)floorf(nexty);
+    if (inx < -win || inx >= J.w || iny < -win || iny >= J.h) {
+      if (level == 0) status = 0;
+      break;
+    }
+    a = nextx - inx; b = nexty - iny;
+    iw00 = __float2int_rn((1.f - a) * (1.f - b) * (1 << W_BITS));
+    iw01 = __float2int_rn(a * (1.f - b) * (1 << W_BITS));
+    iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS));
+    iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+    __syncwarp();
+    stage_window(J, inx, iny, win, s_win);
+    long long sb1 = 0, sb2 = 0;
+    {
+      int x = lane, y = 0;
+      while (x >= win) { x -= win; y++; }
+      for (int i = lane; i < win * win; i += 32) {
+        const uint8_t* s = s_win + y * ww + x;
+        const int diff = descale(s[0] * iw00 + s[1] * iw01 + s[ww] * iw10 + s[ww + 1] * iw11, W_BITS - 5) - s_I[i];
+        const short2 d = s_dI[i];
+        sb1 += (long long)(diff * d.x);  // |diff| < 2^13, |d| < 2^15: the product fits an int
+        sb2 += (long long)(diff * d.y);
+        x += 32;
+        while (x >= win) { x -= win; y++; }
+      }
+    }
+    sb1 = warp_sum_ll(sb1); sb2 = warp_sum_ll(sb2);
+    const float b1 = (float)sb1 * FLT_SCALE, b2 = (float)sb2 * FLT_SCALE;
+    const float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
+    nextx += dx; nexty += dy;
+    nx = nextx + halfWin; ny = nexty + halfWin;
+    if ((double)dx * dx + (double)dy * dy <= (double)eps2) break;
+    if (j > 0 && (double)fabsf(dx + pdx) < 0.01 && (double)fabsf(dy + pdy) < 0.01) {
+      nx -= dx * 0.5f; ny -= dy * 0.5f;
+      break;
+    }
+    pdx = dx; pdy = dy;
+  }
+}
+
+struct TrackArgs {
+  const uint8_t *prevPyr, *curPyr;   // [batch][frameBytes]
+  const float* kps;                  // [batch][stride][2]
+  float* next;                       // [batch][stride][2] in/out
+  const int* n;                      // [batch]
+  uint8_t* status;                   // [batch][stride]
+  float* err;                        // [batch][stride] (may be null)
+  int stride, win, maxLevel, maxCount, useInitial, fb;
+  float eps2, ferr, fbDist;
+};
+
+// mode fb = 0: cv::calcOpticalFlowPyrLK(prev, cur) with OPTFLOW_LK_GET_MIN_EIGENVALS; fb = 1: ORBmatcher::fbKltTracking
+__global__ void __launch_bounds__(TRACK_WARPS * 32) k_klt_track(TrackArgs A, PyrGeom G) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int f = blockIdx.y, p = blockIdx.x * TRACK_WARPS + warp;
+  if (p >= A.n[f]) return;
+  const int win = A.win, ww = win + 1;
+  const size_t perWarp = ((size_t)win * win * 6 + (size_t)ww * ww + 15) / 16 * 16;
+  unsigned char* base = s_raw + perWarp * warp;
+  short2* s_dI = reinterpret_cast<short2*>(base);
+  short* s_I = reinterpret_cast<short*>(base + (size_t)win * win * 4);
+  uint8_t* s_win = base + (size_t)win * win * 6;
+  const uint8_t* P = A.prevPyr + (size_t)f * G.frameBytes;
+  const uint8_t* C = A.curPyr + (size_t)f * G.frameBytes;
+  const size_t o = (size_t)f * A.stride + p;
+  const float kx = A.kps[2 * o], ky = A.kps[2 * o + 1];
+  float nx = A.next[2 * o], ny = A.next[2 * o + 1];
+  int status = 1;
+  float err = 0;
+  const int maxLevel = min(A.maxLevel, G.levels);
+  for (int l = maxLevel; l >= 0; l--)
+    lk_level(level_view(P, G, l), level_view(C, G, l), l, maxLevel, win, A.maxCount, A.eps2, A.useInitial != 0, kx, ky, nx, ny, status, err,
+             s_I, s_dI, s_win);
+  const int lane = threadIdx.x & 31;
+  if (!A.fb) {
+    if (lane == 0) { A.next[2 * o] = nx; A.next[2 * o + 1] = ny; A.status[o] = (uint8_t)status; if (A.err) A.err[o] = err; }
+    return;
+  }
+  // fbKltTracking: forward filter, backward pass at level 0 from the tracked position with the keypoint as initial flow
+  bool ok = status != 0 && !(err > A.ferr) && 1.f <= nx && nx < (float)G.w[0] - 1.f && 1.f <= ny && ny < (float)G.h[0] - 1.f;
+  if (ok) {
+    float bx = kx, by = ky, err2 = 0;
+    int st2 = 1;
+    lk_level(level_view(C, G, 0), level_view(P, G, 0), 0, 0, win, A.maxCount, A.eps2, true, nx, ny, bx, by, st2, err2, s_I, s_dI, s_win);
+    const double ddx = (double)kx - (double)bx, ddy = (double)ky - (double)by;
+    ok = st2 != 0 && !(sqrt(ddx * ddx + ddy * ddy) > (double)A.fbDist);
+  }
+  if (lane == 0) { A.next[2 * o] = nx; A.next[2 * o + 1] = ny; A.status[o] = ok ? 1 : 0; if (A.err) A.err[o] = err; }
+}
+
+}  // namespace klt
+}  // namespace gfs
+
+using namespace gfs;
+using namespace gfs::klt;
+
+struct GfsKlt {
+  int maxW = 0, maxH = 0, levels = 0, maxPoints = 0, maxBatch = 0;
+  DevBuf d_img, d_pyrA, d_pyrB, d_kps, d_next, d_n, d_status, d_err;
+  int launches = 0;
+};
+
+extern "C" {
+
+int gfs_klt_create(int max_w, int max_h, int levels, int max_points, int max_batch, GfsKlt** out) {
+  GFS_REQUIRE(out, GFS_ERR_INVALID, "out is null");
+  *out = nullptr;
+  GFS_REQUIRE(max_w > 0 && max_h > 0 && levels >= 0 && levels <= MAX_LEVELS && max_points > 0 && max_batch > 0, GFS_ERR_INVALID,
+              "bad capacity");
+  int rc = gfs_device_check();
+  if (rc) return rc;
+  GfsKlt* h = new GfsKlt();
+  h->maxW = max_w; h->maxH = max_h; h->levels = levels; h->maxPoints = max_points; h->maxBatch = max_batch;
+  *out = h;
+  return GFS_OK;
+}
+
+int gfs_klt_destroy(GfsKlt* h) {
+  if (!h) return GFS_OK;
+  DevBuf* d[] = {&h->d_img, &h->d_pyrA, &h->d_pyrB, &h->d_kps, &h->d_next, &h->d_n, &h->d_status, &h->d_err};
+  for (DevBuf* b : d) b->release();
+  delete h;
+  return GFS_OK;
+}
+
+int gfs_klt_last_launches(const GfsKlt* h) { return h ? h->launches : GFS_ERR_INVALID; }
+
+size_t gfs_klt_pyramid_bytes(const GfsKlt* h, int w, int h_img) {
+  if (!h || w <= 0 || h_img <= 0) return 0;
+  return make_geom(w, h_img, h->levels).frameBytes;
+}
+int gfs_klt_pyramid_layout(const GfsKlt* h, int w, int h_img, int* level_w, int* level_h, int* level_off, size_t* deriv_offset) {
+  GFS_REQUIRE(h && level_w && level_h && level_off && deriv_offset, GFS_ERR_INVALID, "null argument");
+  const PyrGeom g = make_geom(w, h_img, h->levels);
+  for (int l = 0; l <= g.levels; l++) { level_w[l] = g.w[l]; level_h[l] = g.h[l]; level_off[l] = g.off[l]; }
+  *deriv_offset = g.imgBytes;
+  return GFS_OK;
+}
+
+int gfs_klt_build_pyramid_batch_device(GfsKlt* h, void* stream, const uint8_t* d_imgs, int batch, int w, int h_img, int pitch,
+                                       size_t img_stride, uint8_t* d_pyr) {
+  GFS_REQUIRE(h && d_imgs && d_pyr, GFS_ERR_INVALID, "null argument");
+  GFS_REQUIRE(batch > 0 && batch <= h->maxBatch, GFS_ERR_CAPACITY, "batch exceeds the handle's max_batch");
+  GFS_REQUIRE(w > 0 && h_img > 0 && w <= h->maxW && h_img <= h->maxH && pitch >= w, GFS_ERR_CAPACITY, "image larger than the handle's size");
+  cudaStream_t st = (cudaStream_t)stream;
+  const PyrGeom g = make_geom(w, h_img, h->levels);
+  // level 0 = the image itself (buildOpticalFlowPyramid copies it into the padded pyramid)
+  for (int b = 0; b < batch; b++)
+    GFS_CUDA(cudaMemcpy2DAsync(d_pyr + (size_t)b * g.frameBytes, (size_t)w, d_imgs + (size_t)b * img_stride, (size_t)pitch, (size_t)w,
+                               (size_t)h_img, cudaMemcpyDeviceToDevice, st));
+  h->launches = 0;
+  for (int l = 0; l < g.levels; l++) {
+    k_klt_pyr_down<<<dim3(div_up(g.w[l + 1], PD_TX), div_up(g.h[l + 1], PD_TY), batch), dim3(PD_TX, PD_TY), 0, st>>>(
+        d_pyr, g.frameBytes, g.off[l], g.w[l], g.h[l], g.off[l + 1], g.w[l + 1], g.h[l + 1]);
+    h->launches++;
+  }
+  k_klt_scharr<<<dim3(div_up(g.npix, 256), batch), 256, 0, st>>>(d_pyr, g);
+  h->launches++;
+  GFS_CUDA(cudaGetLastError());
+  return GFS_OK;
+}
+
+static int launch_track(GfsKlt* h, cudaStream_t st, const TrackArgs& A, const PyrGeom& g, int batch, int maxPts) {
+  const int win = A.win, ww = win + 1;
+  const size_t perWarp = align_up((size_t)win * win * 6 + (size_t)ww * ww, 16);
+  const size_t smem = perWarp * TRACK_WARPS;
+  if (smem > 48 * 1024) GFS_CUDA(cudaFuncSetAttribute(k_klt_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_klt_track<<<dim3(div_up(maxPts, TRACK_WARPS), batch), TRACK_WARPS * 32, smem, st>>>(A, g);
+  h->launches++;
+  GFS_CUDA(cudaGetLastError());
+  return GFS_OK;
+}
+
+int gfs_klt_calc_batch_device(GfsKlt* h, void* stream, const uint8_t* d_prev_pyr, const uint8_t* d_cur_pyr, int batch, int w, int h_img,
+                              const float* d_pts, float* d_next, const int* d_n, int stride, int win, int max_level, int max_count,
+                              float eps, int use_initial_flow, uint8_t* d_status, float* d_err) {
+  GFS_REQUIRE(h && d_prev_pyr && d_cur_pyr && d_pts && d_next && d_n && d_status, GFS_ERR_INVALID, "null argument");
+  GFS_REQUIRE(batch > 0 && batch <= h->maxBatch && stride > 0 && stride <= h->maxPoints, GFS_ERR_CAPACITY, "batch / stride exceed the handle");
+  GFS_REQUIRE(win >= 3 && win <= 63 && max_level >= 0, GFS_ERR_INVALID, "bad window / level");
+  const PyrGeom g = make_geom(w, h_img, h->levels);
+  TrackArgs A;
+  memset(&A, 0, sizeof(A));
+  A.prevPyr = d_prev_pyr; A.curPyr = d_cur_pyr; A.kps = d_pts; A.next = d_next; A.n = d_n; A.status = d_status; A.err = d_err;
+  A.stride = stride; A.win = win; A.maxLevel = max_level; A.maxCount = std::min(std::max(max_count, 0), 100);
+  const float e = std::min(std::max(eps, 0.f), 10.f);
+  A.eps2 = e * e; A.useInitial = use_initial_flow; A.fb = 0;
+  h->launches = 0;
+  return launch_track(h, (cudaStream_t)stream, A, g, batch, stride);
+}
+
+int gfs_klt_fb_track_batch_device(GfsKlt* h, void* stream, const uint8_t* d_prev_pyr, const uint8_t* d_cur_pyr, int batch, int w, int h_img,
+                                  const float* d_kps, float* d_priors, const int* d_n, int stride, int win, int nbpyrlvl, float ferr,
+                                  float fmax_fbklt_dist, uint8_t* d_status) {
+  GFS_REQUIRE(h && d_prev_pyr && d_cur_pyr && d_kps && d_priors && d_n && d_status, GFS_ERR_INVALID, "null argument");
+  GFS_REQUIRE(batch > 0 && batch <= h->maxBatch && stride > 0 && stride <= h->maxPoints, GFS_ERR_CAPACITY, "batch / stride exceed the handle");
+  GFS_REQUIRE(win >= 3 && win <= 63 && nbpyrlvl >= 0, GFS_ERR_INVALID, "bad window / level");
+  const PyrGeom g = make_geom(w, h_img, h->levels);
+  TrackArgs A;
+  memset(&A, 0, sizeof(A));
+  A.prevPyr = d_prev_pyr; A.curPyr = d_cur_pyr; A.kps = d_kps; A.next = d_priors; A.n = d_n; A.status = d_status; A.err = nullptr;
+  A.stride = stride; A.win = win; A.maxLevel = nbpyrlvl; A.maxCount = 30; A.eps2 = 0.01f * 0.01f; A.useInitial = 1; A.fb = 1;
+  A.ferr = ferr; A.fbDist = fmax_fbklt_dist;
+  h->launches = 0;
+  return launch_track(h, (cudaStream_t)stream, A, g, batch, stride);
+}
+
+// Host-pointer convenience: one frame pair, images in, tracks out (both pyramids are built on the way).
+int gfs_klt_fb_track(GfsKlt* h, void* stream, const uint8_t* prev_img, const uint8_t* cur_img, int w, int h_img, int pitch, const float* kps,
+                     float* priors, int n, int win, int nbpyrlvl, float ferr, float fmax_fbklt_dist, uint8_t* status) {
+  GFS_REQUIRE(h && prev_img && cur_img, GFS_ERR_INVALID, "null image");
+  GFS_REQUIRE(n >= 0 && n <= h->maxPoints, GFS_ERR_CAPACITY, "n exceeds the handle's max_points");
+  GFS_REQUIRE(w > 0 && h_img > 0 && w <= h->maxW && h_img <= h->maxH && pitch >= w, GFS_ERR_CAPACITY, "image larger than the handle's size");
+  if (n == 0) return GFS_OK;  // fbKltTracking returns before touching its outputs (ORBmatcher.cc:2197-2199)
+  GFS_REQUIRE(kps && priors && status, GFS_ERR_INVALID, "null point arrays");
+  cudaStream_t st = (cudaStream_t)stream;
+  const PyrGeom g = make_geom(w, h_img, h->levels);
+  int rc;
+  if ((rc = h->d_img.reserve((size_t)2 * pitch * h_img)) || (rc = h->d_pyrA.reserve(g.frameBytes)) || (rc = h->d_pyrB.reserve(g.frameBytes)) ||
+      (rc = h->d_kps.reserve((size_t)n * 8)) || (rc = h->d_next.reserve((size_t)n * 8)) || (rc = h->d_n.reserve(4)) ||
+      (rc = h->d_status.reserve((size_t)n)))
+    return rc;
+  uint8_t* dimg = (uint8_t*)h->d_img.p;
+  GFS_CUDA(cudaMemcpyAsync(dimg, prev_img, (size_t)pitch * h_img, cudaMemcpyHostToDevice, st));
+  GFS_CUDA(cudaMemcpyAsync(dimg + (size_t)pitch * h_img, cur_img, (size_t)pitch * h_img, cudaMemcpyHostToDevice, st));
+  GFS_CUDA(cudaMemcpyAsync(h->d_kps.p, kps, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  GFS_CUDA(cudaMemcpyAsync(h->d_next.p, priors, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  GFS_CUDA(cudaMemcpyAsync(h->d_n.p, &n, 4, cudaMemcpyHostToDevice, st));
+  const int saveBatch = h->maxBatch;
+  if ((rc = gfs_klt_build_pyramid_batch_device(h, stream, dimg, 1, w, h_img, pitch, 0, (uint8_t*)h->d_pyrA.p))) return rc;
+  int l1 = h->launches;
+  if ((rc = gfs_klt_build_pyramid_batch_device(h, stream, dimg + (size_t)pitch * h_img, 1, w, h_img, pitch, 0, (uint8_t*)h->d_pyrB.p))) return rc;
+  l1 += h->launches;
+  (void)saveBatch;
+  rc = gfs_klt_fb_track_batch_device(h, stream, (const uint8_t*)h->d_pyrA.p, (const uint8_t*)h->d_pyrB.p, 1, w, h_img, (const float*)h->d_kps.p,
+                                     (float*)h->d_next.p, (const int*)h->d_n.p, n, win, nbpyrlvl, ferr, fmax_fbklt_dist, (uint8_t*)h->d_status.p);
+  if (rc) return rc;
+  h->launches += l1;
+  GFS_CUDA(cudaMemcpyAsync(priors, h->d_next.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  GFS_CUDA(cudaMemcpyAsync(status, h->d_status.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+  GFS_CUDA(cudaStreamSynchronize(st));
+  return GFS_OK;
+}
+
+}  // extern "C"

@@ -404,6 +404,43 @@ int gfs_pose_inertial_optimize(GfsPoseInertial* h, void* stream, const GfsPoseIn
                                GfsPoseInertialResult* result);
 int gfs_pose_inertial_last_launches(const GfsPoseInertial* h);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optical-flow front end -- replaces cv::buildOpticalFlowPyramid(image, mImGray, winSize, 3)
+ * (reference src/Frame.cc:370-373) and ORBmatcher::fbKltTracking / Tracking::fbKltTracking
+ * (include/ORBmatcher.h:56-60, src/ORBmatcher.cc:2186-2293; src/Tracking.cc:3262-3360): forward
+ * cv::calcOpticalFlowPyrLK over nbpyrlvl levels (OPTFLOW_USE_INITIAL_FLOW | OPTFLOW_LK_GET_MIN_EIGENVALS, 30
+ * iterations, eps 0.01), status / min-eigenvalue / inBorder filter, backward pass at level 0, forward-backward
+ * distance check.  The F-matrix RANSAC that follows in SearchByProjectionWithOF (cv::findFundamentalMat,
+ * ORBmatcher.cc:2399,2463) is NOT part of this entry point.
+ * A frame's pyramid is one caller-owned device block of gfs_klt_pyramid_bytes() bytes: the images of levels
+ * 0..levels tightly packed (level l is ((w+1)/2, (h+1)/2) of level l-1), then, 16-byte aligned, the int16
+ * (dI/dx, dI/dy) Scharr derivatives in the same order -- what mImGray holds, without the winSize border (reads
+ * outside the image follow the border rules of the padded OpenCV pyramid: reflect-101 image, zero derivative).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct GfsKlt GfsKlt;
+int gfs_klt_create(int max_w, int max_h, int levels, int max_points, int max_batch, GfsKlt** out);
+int gfs_klt_destroy(GfsKlt* h);
+size_t gfs_klt_pyramid_bytes(const GfsKlt* h, int w, int h_img);
+/* level sizes, pixel offsets of the levels and the byte offset of the derivative block; arrays of levels + 1 */
+int gfs_klt_pyramid_layout(const GfsKlt* h, int w, int h_img, int* level_w, int* level_h, int* level_off, size_t* deriv_offset);
+/* cv::buildOpticalFlowPyramid for `batch` gray frames (device pointers); d_pyr is [batch][gfs_klt_pyramid_bytes] */
+int gfs_klt_build_pyramid_batch_device(GfsKlt* h, void* stream, const uint8_t* d_imgs, int batch, int w, int h_img, int pitch,
+                                       size_t img_stride, uint8_t* d_pyr);
+/* ORBmatcher::fbKltTracking for `batch` frame pairs: kps [batch][stride][2] (vkps), priors in/out (vpriorkps),
+ * n [batch] points per pair, status [batch][stride] (vkpstatus) */
+int gfs_klt_fb_track_batch_device(GfsKlt* h, void* stream, const uint8_t* d_prev_pyr, const uint8_t* d_cur_pyr, int batch, int w, int h_img,
+                                  const float* d_kps, float* d_priors, const int* d_n, int stride, int win, int nbpyrlvl, float ferr,
+                                  float fmax_fbklt_dist, uint8_t* d_status);
+/* cv::calcOpticalFlowPyrLK on prebuilt pyramids with OPTFLOW_LK_GET_MIN_EIGENVALS (d_err = minimum eigenvalues, may
+ * be NULL) and optionally OPTFLOW_USE_INITIAL_FLOW; parity hook against OpenCV itself */
+int gfs_klt_calc_batch_device(GfsKlt* h, void* stream, const uint8_t* d_prev_pyr, const uint8_t* d_cur_pyr, int batch, int w, int h_img,
+                              const float* d_pts, float* d_next, const int* d_n, int stride, int win, int max_level, int max_count,
+                              float eps, int use_initial_flow, uint8_t* d_status, float* d_err);
+/* one frame pair, HOST pointers: images in, tracks out (both pyramids are built on the way) */
+int gfs_klt_fb_track(GfsKlt* h, void* stream, const uint8_t* prev_img, const uint8_t* cur_img, int w, int h_img, int pitch, const float* kps,
+                     float* priors, int n, int win, int nbpyrlvl, float ferr, float fmax_fbklt_dist, uint8_t* status);
+int gfs_klt_last_launches(const GfsKlt* h);
+
 #ifdef __cplusplus
 }
 #endif
