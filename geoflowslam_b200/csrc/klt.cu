@@ -15,8 +15,10 @@
 //                    [1 4 6 4 1], (sum + 128) >> 8
 //   k_klt_scharr     thread per pixel: int16 (dI/dx, dI/dy), reflect-101 inside the image
 //   k_klt_track      one warp per point, all pyramid levels and both passes in ONE launch: the 35x35 template patch
-//                    (int16 intensities with 5 fractional bits + int16 derivatives) lives in shared memory, the
-//                    36x36 window of the other image is staged per iteration, the five sums are warp-reduced int64
+//                    (int16 intensities with 5 fractional bits + int16 derivatives, interpolated in place from the
+//                    staged 36x36 derivative window) lives in shared memory, the 36x36 window of the other image is
+//                    staged per iteration (aligned 32-bit words inside the image, reflect-101 bytes at the border),
+//                    the five sums are warp-reduced int64
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -124,29 +126,49 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// stage the (win+1) x (win+1) window of `img` whose top-left pixel is (x0, y0) (reflect-101 outside the image)
-__device__ __forceinline__ void stage_window(const LevelView& L, int x0, int y0, int win, uint8_t* s_win) {
-  const int lane = threadIdx.x & 31, ww = win + 1;
+// Stage the (win+1) x (win+1) window of `img` whose top-left pixel is (x0, y0) into shared memory, row pitch `pitch`
+// bytes.  A window inside the image is copied as aligned 32-bit words (the row keeps its misalignment: pixel (x, y)
+// sits at s_win[y * pitch + ((a0 + y * w) & 3) + x], a0 = the returned low address bits of the first pixel); a
+// window that leaves the image is copied byte by byte with the reflect-101 rule and a0 = NO_SHIFT.
+static const unsigned NO_SHIFT = 0xffffffffu;
+__device__ __forceinline__ int win_pitch(int win) { return (win + 1 + 6) / 4 * 4; }
+__device__ __forceinline__ unsigned stage_window(const LevelView& L, int x0, int y0, int win, uint8_t* s_win) {
+  const int lane = threadIdx.x & 31, ww = win + 1, pitch = win_pitch(win);
   const bool inside = x0 >= 0 && y0 >= 0 && x0 + ww <= L.w && y0 + ww <= L.h;
-  int x = lane, y = 0;
-  while (x >= ww) { x -= ww; y++; }
-  for (int i = lane; i < ww * ww; i += 32) {
-    const int X = inside ? x0 + x : reflect101(x0 + x, L.w), Y = inside ? y0 + y : reflect101(y0 + y, L.h);
-    s_win[i] = L.img[(size_t)Y * L.w + X];
-    x += 32;
-    while (x >= ww) { x -= ww; y++; }
+  unsigned a0 = NO_SHIFT;
+  if (inside) {
+    const uint8_t* p0 = L.img + (size_t)y0 * L.w + x0;
+    a0 = (unsigned)(reinterpret_cast<size_t>(p0) & 3);
+    const int wpr = pitch / 4;
+    int r = 0, k = lane;
+    while (k >= wpr) { k -= wpr; r++; }
+    for (int i = lane; i < ww * wpr; i += 32) {
+      const uint8_t* row = p0 + (size_t)r * L.w;
+      const unsigned* src = reinterpret_cast<const unsigned*>(row - (reinterpret_cast<size_t>(row) & 3));
+      reinterpret_cast<unsigned*>(s_win)[r * wpr + k] = __ldg(src + k);
+      k += 32;
+      while (k >= wpr) { k -= wpr; r++; }
+    }
+  } else {
+    // rows outer, lanes over the columns: the reflected column of a lane is the same for every row
+    const int c0 = reflect101(x0 + lane, L.w), c1 = lane + 32 < ww ? reflect101(x0 + lane + 32, L.w) : 0;
+    for (int y = 0; y < ww; y++) {
+      const uint8_t* row = L.img + (size_t)reflect101(y0 + y, L.h) * L.w;
+      s_win[y * pitch + lane] = row[c0];
+      if (lane + 32 < ww) s_win[y * pitch + lane + 32] = row[c1];
+    }
   }
   __syncwarp();
+  return a0;
 }
-__device__ __forceinline__ short2 der_at(const LevelView& L, int x, int y) {
-  if (x < 0 || y < 0 || x >= L.w || y >= L.h) return make_short2(0, 0);  // derivBorder = BORDER_CONSTANT
-  return L.der[(size_t)y * L.w + x];
+__device__ __forceinline__ const uint8_t* win_px(const uint8_t* s_win, int pitch, unsigned a0, int w, int x, int y) {
+  return s_win + y * pitch + x + (a0 == NO_SHIFT ? 0 : (int)((a0 + (unsigned)(y * w)) & 3u));
 }
 // One pyramid level.  (nx, ny) in/out as OpenCV's nextPts[ptidx]; status / err updated as the invoker does.
 __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int maxLevel, int win, int maxCount, float eps2,
                          bool useInitial, float px, float py, float& nx, float& ny, int& status, float& err, short* s_I, short2* s_dI,
                          uint8_t* s_win) {
-  const int lane = threadIdx.x & 31, ww = win + 1;
+  const int lane = threadIdx.x & 31;
   const float halfWin = (win - 1) * 0.5f;
   const float sc = (float)(1. / (1 << level));
   float prevx = px * sc, prevy = py * sc;
@@ -172,21 +194,46 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
   int iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS));
   int iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
   __syncwarp();
-  stage_window(I, ipx, ipy, win, s_win);
+  const int pitch = win_pitch(win);
+  const unsigned aI = stage_window(I, ipx, ipy, win, s_win);
   long long sA11 = 0, sA12 = 0, sA22 = 0;
   {
+    // the (win+1)^2 derivative window (zero outside the image: derivBorder = BORDER_CONSTANT) goes to shared memory
+    // row by row, then is interpolated IN PLACE: output (x, y) needs inputs (x..x+1, y..y+1), which no later output of
+    // the raster order reads once this batch of 32 has loaded them
+    const int dw = win + 1;
+    for (int y = 0; y < dw; y++) {
+      const int Y = ipy + y;
+      const bool rowIn = Y >= 0 && Y < I.h;
+      const short2* row = I.der + (size_t)(rowIn ? Y : 0) * I.w;
+      for (int x = lane; x < dw; x += 32) {
+        const int X = ipx + x;
+        s_dI[y * dw + x] = (rowIn && X >= 0 && X < I.w) ? row[X] : make_short2(0, 0);
+      }
+    }
+    __syncwarp();
     int x = lane, y = 0;
     while (x >= win) { x -= win; y++; }
-    for (int i = lane; i < win * win; i += 32) {
-      const uint8_t* s = s_win + y * ww + x;
-      const int ival = descale(s[0] * iw00 + s[1] * iw01 + s[ww] * iw10 + s[ww + 1] * iw11, W_BITS - 5);
-      const int X = ipx + x, Y = ipy + y;
-      const short2 d00 = der_at(I, X, Y), d01 = der_at(I, X + 1, Y), d10 = der_at(I, X, Y + 1), d11 = der_at(I, X + 1, Y + 1);
-      const int ixval = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, W_BITS);
-      const int iyval = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, W_BITS);
-      s_I[i] = (short)ival;
-      s_dI[i] = make_short2((short)ixval, (short)iyval);
-      sA11 += (long long)ixval * ixval; sA12 += (long long)ixval * iyval; sA22 += (long long)iyval * iyval;
+    const int n = win * win;
+    for (int i0 = 0; i0 < n; i0 += 32) {  // uniform trip count: every lane takes part in the barriers
+      const int i = i0 + lane;
+      const bool valid = i < n;
+      int ival = 0, ixval = 0, iyval = 0;
+      if (valid) {
+        const short2 d00 = s_dI[y * dw + x], d01 = s_dI[y * dw + x + 1], d10 = s_dI[(y + 1) * dw + x], d11 = s_dI[(y + 1) * dw + x + 1];
+        const uint8_t* s0 = win_px(s_win, pitch, aI, I.w, x, y);
+        const uint8_t* s1 = win_px(s_win, pitch, aI, I.w, x, y + 1);
+        ival = descale(s0[0] * iw00 + s0[1] * iw01 + s1[0] * iw10 + s1[1] * iw11, W_BITS - 5);
+        ixval = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, W_BITS);
+        iyval = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, W_BITS);
+        sA11 += (long long)ixval * ixval; sA12 += (long long)ixval * iyval; sA22 += (long long)iyval * iyval;
+      }
+      __syncwarp();
+      if (valid) {
+        s_I[i] = (short)ival;
+        s_dI[y * dw + x] = make_short2((short)ixval, (short)iyval);
+      }
+      __syncwarp();
       x += 32;
       while (x >= win) { x -= win; y++; }
     }
@@ -215,16 +262,17 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
     iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS));
     iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
     __syncwarp();
-    stage_window(J, inx, iny, win, s_win);
+    const unsigned aJ = stage_window(J, inx, iny, win, s_win);
     long long sb1 = 0, sb2 = 0;
     {
       int x = lane, y = 0;
       while (x >= win) { x -= win; y++; }
       for (int i = lane; i < win * win; i += 32) {
-        const uint8_t* s = s_win + y * ww + x;
-        const int diff = descale(s[0] * iw00 + s[1] * iw01 + s[ww] * iw10 + s[ww + 1] * iw11, W_BITS - 5) - s_I[i];
-        const short2 d = s_dI[i];
-        sb1 += (long long)(diff * d.x);  // |diff| < 2^13, |d| < 2^15: the product fits an int
+        const uint8_t* s0 = win_px(s_win, pitch, aJ, J.w, x, y);
+        const uint8_t* s1 = win_px(s_win, pitch, aJ, J.w, x, y + 1);
+        const int diff = descale(s0[0] * iw00 + s0[1] * iw01 + s1[0] * iw10 + s1[1] * iw11, W_BITS - 5) - s_I[i];
+        const short2 d = s_dI[y * (win + 1) + x];
+        sb1 += (long long)(diff * d.x);  // |diff| < 2^14, |d| < 2^13: the product fits an int
         sb2 += (long long)(diff * d.y);
         x += 32;
         while (x >= win) { x -= win; y++; }
@@ -262,11 +310,11 @@ __global__ void __launch_bounds__(TRACK_WARPS * 32) k_klt_track(TrackArgs A, Pyr
   const int f = blockIdx.y, p = blockIdx.x * TRACK_WARPS + warp;
   if (p >= A.n[f]) return;
   const int win = A.win, ww = win + 1;
-  const size_t perWarp = ((size_t)win * win * 6 + (size_t)ww * ww + 15) / 16 * 16;
+  const size_t perWarp = ((size_t)ww * ww * 4 + (size_t)win * win * 2 + (size_t)ww * win_pitch(win) + 15) / 16 * 16;
   unsigned char* base = s_raw + perWarp * warp;
   short2* s_dI = reinterpret_cast<short2*>(base);
-  short* s_I = reinterpret_cast<short*>(base + (size_t)win * win * 4);
-  uint8_t* s_win = base + (size_t)win * win * 6;
+  uint8_t* s_win = base + (size_t)ww * ww * 4;                         // word-aligned: staged with 32-bit stores
+  short* s_I = reinterpret_cast<short*>(s_win + (size_t)ww * win_pitch(win));
   const uint8_t* P = A.prevPyr + (size_t)f * G.frameBytes;
   const uint8_t* C = A.curPyr + (size_t)f * G.frameBytes;
   const size_t o = (size_t)f * A.stride + p;
@@ -369,7 +417,7 @@ int gfs_klt_build_pyramid_batch_device(GfsKlt* h, void* stream, const uint8_t* d
 
 static int launch_track(GfsKlt* h, cudaStream_t st, const TrackArgs& A, const PyrGeom& g, int batch, int maxPts) {
   const int win = A.win, ww = win + 1;
-  const size_t perWarp = align_up((size_t)win * win * 6 + (size_t)ww * ww, 16);
+  const size_t perWarp = align_up((size_t)ww * ww * 4 + (size_t)win * win * 2 + (size_t)ww * ((ww + 6) / 4 * 4), 16);
   const size_t smem = perWarp * TRACK_WARPS;
   if (smem > 48 * 1024) GFS_CUDA(cudaFuncSetAttribute(k_klt_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_klt_track<<<dim3(div_up(maxPts, TRACK_WARPS), batch), TRACK_WARPS * 32, smem, st>>>(A, g);
