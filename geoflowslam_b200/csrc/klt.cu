@@ -11,6 +11,7 @@
 // exactly; the sums of integer products OpenCV accumulates in float SIMD lanes are accumulated exactly in int64
 // (order-free, so the result does not depend on the lane layout) and narrowed once.
 //
+//   k_clahe_lut/apply  cv::CLAHE (Frame.cc:366-368): per-tile histogram + clip + LUT, then the bilinear LUT blend
 //   k_klt_pyr_down   CTA per 32x8 destination tile: the 68x20 source window staged in shared memory, separable
 //                    [1 4 6 4 1], (sum + 128) >> 8
 //   k_klt_scharr     thread per pixel: int16 (dI/dx, dI/dy), reflect-101 inside the image
@@ -61,6 +62,74 @@ __device__ __forceinline__ int reflect101(int p, int len) {  // cv::borderInterp
   if (len == 1) return 0;
   while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
   return p;
+}
+
+// ---- cv::CLAHE::apply, CV_8UC1 (modules/imgproc/src/clahe.cpp), as Frame::Frame applies it (reference
+// src/Frame.cc:366-368: createCLAHE(3.0, Size(8, 8)), in place).
+struct ClaheGeom { int w, h, tilesX, tilesY, tw, th, clipLimit; float lutScale; };
+// CTA per (tile, frame): histogram in shared memory, clip + redistribute exactly as CLAHE_CalcLut_Body, prefix sum -> LUT
+__global__ void __launch_bounds__(256) k_clahe_lut(const uint8_t* __restrict__ src, int pitch, size_t imgStride, ClaheGeom G,
+                                                   uint8_t* __restrict__ lut) {
+  __shared__ int s_hist[256];
+  __shared__ int s_scan[256];
+  __shared__ int s_clipped;
+  const int tid = threadIdx.x, k = blockIdx.x, ty = k / G.tilesX, tx = k % G.tilesX;
+  const uint8_t* img = src + (size_t)blockIdx.y * imgStride;
+  s_hist[tid] = 0;
+  if (tid == 0) s_clipped = 0;
+  __syncthreads();
+  const bool interior = (tx + 1) * G.tw <= G.w && (ty + 1) * G.th <= G.h;
+  for (int i = tid; i < G.tw * G.th; i += 256) {
+    const int y = i / G.tw, x = i - y * G.tw;
+    const int X = tx * G.tw + x, Y = ty * G.th + y;
+    const uint8_t v = interior ? img[(size_t)Y * pitch + X] : img[(size_t)reflect101(Y, G.h) * pitch + reflect101(X, G.w)];
+    atomicAdd(&s_hist[v], 1);
+  }
+  __syncthreads();
+  int hv = s_hist[tid];
+  if (G.clipLimit > 0) {
+    if (hv > G.clipLimit) { atomicAdd(&s_clipped, hv - G.clipLimit); hv = G.clipLimit; }
+    __syncthreads();
+    const int clipped = s_clipped;
+    const int redistBatch = clipped / 256;
+    const int residual = clipped - redistBatch * 256;
+    hv += redistBatch;
+    if (residual != 0) {
+      const int step = max(256 / residual, 1);
+      // for (i = 0; i < 256 && residual > 0; i += step, residual--) hist[i]++
+      if (tid % step == 0 && tid / step < residual) hv++;
+    }
+  }
+  // inclusive prefix sum over the 256 bins (Hillis-Steele in shared memory: integers, order-free)
+  s_scan[tid] = hv;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    const int t = tid >= o ? s_scan[tid - o] : 0;
+    __syncthreads();
+    s_scan[tid] += t;
+    __syncthreads();
+  }
+  const int v = __float2int_rn((float)s_scan[tid] * G.lutScale);  // saturate_cast<uchar>(sum * lutScale)
+  lut[((size_t)blockIdx.y * G.tilesX * G.tilesY + k) * 256 + tid] = (uint8_t)min(max(v, 0), 255);
+}
+// thread per pixel: bilinear blend of the four surrounding tile LUTs (CLAHE_Interpolation_Body)
+__global__ void __launch_bounds__(256) k_clahe_apply(const uint8_t* __restrict__ src, int pitch, size_t imgStride, ClaheGeom G,
+                                                     const uint8_t* __restrict__ lut, uint8_t* __restrict__ dst, int dstPitch,
+                                                     size_t dstStride) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= G.w || y >= G.h) return;
+  const float inv_tw = 1.0f / G.tw, inv_th = 1.0f / G.th;
+  const float tyf = y * inv_th - 0.5f, txf = x * inv_tw - 0.5f;
+  int ty1 = (int)floorf(tyf), tx1 = (int)floorf(txf);
+  int ty2 = ty1 + 1, tx2 = tx1 + 1;
+  const float ya = tyf - ty1, ya1 = 1.0f - ya, xa = txf - tx1, xa1 = 1.0f - xa;
+  ty1 = max(ty1, 0); ty2 = min(ty2, G.tilesY - 1); tx1 = max(tx1, 0); tx2 = min(tx2, G.tilesX - 1);
+  const int v = src[(size_t)blockIdx.z * imgStride + (size_t)y * pitch + x];
+  const uint8_t* L = lut + (size_t)blockIdx.z * G.tilesX * G.tilesY * 256;
+  const float l11 = L[(ty1 * G.tilesX + tx1) * 256 + v], l12 = L[(ty1 * G.tilesX + tx2) * 256 + v];
+  const float l21 = L[(ty2 * G.tilesX + tx1) * 256 + v], l22 = L[(ty2 * G.tilesX + tx2) * 256 + v];
+  const float res = (l11 * xa1 + l12 * xa) * ya1 + (l21 * xa1 + l22 * xa) * ya;
+  dst[(size_t)blockIdx.z * dstStride + (size_t)y * dstPitch + x] = (uint8_t)min(max(__float2int_rn(res), 0), 255);
 }
 
 // ---- cv::pyrDown, 8U: dst (dw x dh) from src (sw x sh), one frame per blockIdx.z
@@ -492,6 +561,53 @@ int gfs_klt_fb_track(GfsKlt* h, void* stream, const uint8_t* prev_img, const uin
   h->launches += l1;
   GFS_CUDA(cudaMemcpyAsync(priors, h->d_next.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   GFS_CUDA(cudaMemcpyAsync(status, h->d_status.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+  GFS_CUDA(cudaStreamSynchronize(st));
+  return GFS_OK;
+}
+
+// cv::createCLAHE(clip_limit, Size(tiles_x, tiles_y))->apply for a batch of 8-bit gray frames (device pointers);
+// d_dst may alias d_src (Frame::Frame applies it in place).
+int gfs_clahe_apply_batch_device(void* stream, const uint8_t* d_src, int batch, int w, int h_img, int pitch, size_t img_stride,
+                                 double clip_limit, int tiles_x, int tiles_y, uint8_t* d_dst, int dst_pitch, size_t dst_stride) {
+  GFS_REQUIRE(d_src && d_dst, GFS_ERR_INVALID, "null pointer");
+  GFS_REQUIRE(batch > 0 && w > 0 && h_img > 0 && pitch >= w && dst_pitch >= w && tiles_x > 0 && tiles_y > 0, GFS_ERR_INVALID, "bad geometry");
+  int rc = gfs_device_check();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  ClaheGeom G;
+  G.w = w; G.h = h_img; G.tilesX = tiles_x; G.tilesY = tiles_y;
+  int ew = w, eh = h_img;  // copyMakeBorder(BORDER_REFLECT_101) on the right / bottom when the size is not divisible
+  if (!(w % tiles_x == 0 && h_img % tiles_y == 0)) { ew = w + (tiles_x - (w % tiles_x)); eh = h_img + (tiles_y - (h_img % tiles_y)); }
+  G.tw = ew / tiles_x; G.th = eh / tiles_y;
+  const int total = G.tw * G.th;
+  G.lutScale = static_cast<float>(255) / total;
+  G.clipLimit = 0;
+  if (clip_limit > 0.0) G.clipLimit = std::max(static_cast<int>(clip_limit * total / 256), 1);
+  uint8_t* lut = nullptr;
+  GFS_CUDA(cudaMallocAsync((void**)&lut, (size_t)batch * tiles_x * tiles_y * 256, st));
+  k_clahe_lut<<<dim3(tiles_x * tiles_y, batch), 256, 0, st>>>(d_src, pitch, img_stride, G, lut);
+  k_clahe_apply<<<dim3(div_up(w, 32), div_up(h_img, 8), batch), 256, 0, st>>>(d_src, pitch, img_stride, G, lut, d_dst, dst_pitch, dst_stride);
+  const cudaError_t e = cudaGetLastError();
+  GFS_CUDA(cudaFreeAsync(lut, st));
+  GFS_CUDA(e);
+  return GFS_OK;
+}
+// one frame, HOST pointers
+int gfs_clahe_apply(void* stream, const uint8_t* src, int w, int h_img, int pitch, double clip_limit, int tiles_x, int tiles_y, uint8_t* dst) {
+  GFS_REQUIRE(src && dst && w > 0 && h_img > 0 && pitch >= w, GFS_ERR_INVALID, "bad argument");
+  int rc = gfs_device_check();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* d = nullptr;
+  GFS_CUDA(cudaMallocAsync((void**)&d, (size_t)pitch * h_img, st));
+  GFS_CUDA(cudaMemcpyAsync(d, src, (size_t)pitch * h_img, cudaMemcpyHostToDevice, st));
+  rc = gfs_clahe_apply_batch_device(stream, d, 1, w, h_img, pitch, 0, clip_limit, tiles_x, tiles_y, d, pitch, 0);
+  if (rc == GFS_OK) {
+    const cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)w, d, (size_t)pitch, (size_t)w, (size_t)h_img, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) { gfs::set_error("cudaMemcpy2DAsync -> %s", cudaGetErrorString(e)); rc = GFS_ERR_CUDA; }
+  }
+  cudaFreeAsync(d, st);
+  if (rc) return rc;
   GFS_CUDA(cudaStreamSynchronize(st));
   return GFS_OK;
 }

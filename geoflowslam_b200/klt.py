@@ -76,3 +76,21 @@ class KltTracker:
 
     def last_launches(self):
         return int(self._L.gfs_klt_last_launches(self._h))
+
+
+def clahe_apply(img, clip_limit=3.0, tiles=(8, 8), stream=None):
+    """cv::createCLAHE(clip_limit, tiles)->apply(img) on one host image (reference src/Frame.cc:366-368)"""
+    L = _lib.lib()
+    _lib.require_device()
+    img = np.ascontiguousarray(img, np.uint8)
+    assert img.ndim == 2
+    h, w = img.shape
+    out = np.zeros_like(img)
+    check(L.gfs_clahe_apply(stream, ptr(img), w, h, w, float(clip_limit), int(tiles[0]), int(tiles[1]), ptr(out)))
+    return out
+
+
+def clahe_apply_device(d_src, batch, w, h, pitch, img_stride, d_dst, clip_limit=3.0, tiles=(8, 8), stream=None):
+    """batched, device buffers; d_dst may be d_src (in place, as Frame::Frame does)"""
+    check(_lib.lib().gfs_clahe_apply_batch_device(stream, ptr(d_src), int(batch), int(w), int(h), int(pitch), int(img_stride),
+                                                  float(clip_limit), int(tiles[0]), int(tiles[1]), ptr(d_dst), int(pitch), int(img_stride)))

@@ -440,6 +440,11 @@ int gfs_klt_calc_batch_device(GfsKlt* h, void* stream, const uint8_t* d_prev_pyr
 int gfs_klt_fb_track(GfsKlt* h, void* stream, const uint8_t* prev_img, const uint8_t* cur_img, int w, int h_img, int pitch, const float* kps,
                      float* priors, int n, int win, int nbpyrlvl, float ferr, float fmax_fbklt_dist, uint8_t* status);
 int gfs_klt_last_launches(const GfsKlt* h);
+/* cv::createCLAHE(clip_limit, Size(tiles_x, tiles_y))->apply on 8-bit gray frames -- replaces the optional in-place
+ * CLAHE pass of Frame::Frame (reference src/Frame.cc:366-368, 498-500: clip 3.0, 8x8 tiles).  d_dst may alias d_src. */
+int gfs_clahe_apply_batch_device(void* stream, const uint8_t* d_src, int batch, int w, int h_img, int pitch, size_t img_stride,
+                                 double clip_limit, int tiles_x, int tiles_y, uint8_t* d_dst, int dst_pitch, size_t dst_stride);
+int gfs_clahe_apply(void* stream, const uint8_t* src, int w, int h_img, int pitch, double clip_limit, int tiles_x, int tiles_y, uint8_t* dst);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,66 @@ static inline int reflect101(int p, int len) {  // cv::borderInterpolate(BORDER_
 static inline int cv_round(float v) { return (int)lrintf(v); }   // cvRound: round half to even (SSE cvtss2si)
 static inline int cv_floor(float v) { return (int)std::floor(v); }
 
+// cv::CLAHE::apply for CV_8UC1 (modules/imgproc/src/clahe.cpp: CLAHE_CalcLut_Body, CLAHE_Interpolation_Body), as
+// Frame::Frame applies it in place with createCLAHE(3.0, Size(8, 8)) (reference src/Frame.cc:366-368, 498-500)
+static void clahe(const uint8_t* src, int w, int h, double clipLimit_, int tilesX, int tilesY, uint8_t* dst) {
+  const int histSize = 256;
+  int ew = w, eh = h;  // extended size: copyMakeBorder(BORDER_REFLECT_101) on the right / bottom when not divisible
+  if (!(w % tilesX == 0 && h % tilesY == 0)) { ew = w + (tilesX - (w % tilesX)); eh = h + (tilesY - (h % tilesY)); }
+  const int tw = ew / tilesX, th = eh / tilesY;
+  const int tileSizeTotal = tw * th;
+  const float lutScale = static_cast<float>(histSize - 1) / tileSizeTotal;
+  int clipLimit = 0;
+  if (clipLimit_ > 0.0) {
+    clipLimit = static_cast<int>(clipLimit_ * tileSizeTotal / histSize);
+    clipLimit = std::max(clipLimit, 1);
+  }
+  std::vector<uint8_t> lut((size_t)tilesX * tilesY * histSize);
+  for (int k = 0; k < tilesX * tilesY; k++) {
+    const int ty = k / tilesX, tx = k % tilesX;
+    int hist[256] = {0};
+    for (int y = 0; y < th; y++)
+      for (int x = 0; x < tw; x++) hist[src[(size_t)reflect101(ty * th + y, h) * w + reflect101(tx * tw + x, w)]]++;
+    if (clipLimit > 0) {
+      int clipped = 0;
+      for (int i = 0; i < histSize; i++)
+        if (hist[i] > clipLimit) { clipped += hist[i] - clipLimit; hist[i] = clipLimit; }
+      const int redistBatch = clipped / histSize;
+      int residual = clipped - redistBatch * histSize;
+      for (int i = 0; i < histSize; i++) hist[i] += redistBatch;
+      if (residual != 0) {
+        const int residualStep = std::max(histSize / residual, 1);
+        for (int i = 0; i < histSize && residual > 0; i += residualStep, residual--) hist[i]++;
+      }
+    }
+    int sum = 0;
+    for (int i = 0; i < histSize; i++) {
+      sum += hist[i];
+      const int v = cv_round(sum * lutScale);
+      lut[(size_t)k * histSize + i] = (uint8_t)std::min(std::max(v, 0), 255);
+    }
+  }
+  const float inv_tw = 1.0f / tw, inv_th = 1.0f / th;
+  for (int y = 0; y < h; y++) {
+    const float tyf = y * inv_th - 0.5f;
+    int ty1 = cv_floor(tyf), ty2 = ty1 + 1;
+    const float ya = tyf - ty1, ya1 = 1.0f - ya;
+    ty1 = std::max(ty1, 0); ty2 = std::min(ty2, tilesY - 1);
+    const uint8_t* p1 = lut.data() + (size_t)ty1 * tilesX * histSize;
+    const uint8_t* p2 = lut.data() + (size_t)ty2 * tilesX * histSize;
+    for (int x = 0; x < w; x++) {
+      const float txf = x * inv_tw - 0.5f;
+      int tx1 = cv_floor(txf), tx2 = tx1 + 1;
+      const float xa = txf - tx1, xa1 = 1.0f - xa;
+      tx1 = std::max(tx1, 0); tx2 = std::min(tx2, tilesX - 1);
+      const int v = src[(size_t)y * w + x];
+      const int i1 = tx1 * histSize + v, i2 = tx2 * histSize + v;
+      const float res = (p1[i1] * xa1 + p1[i2] * xa) * ya1 + (p2[i1] * xa1 + p2[i2] * xa) * ya;
+      dst[(size_t)y * w + x] = (uint8_t)std::min(std::max(cv_round(res), 0), 255);
+    }
+  }
+}
+
 static void pyr_down(const uint8_t* src, int w, int h, uint8_t* dst) {
   const int dw = (w + 1) / 2, dh = (h + 1) / 2;
   std::vector<int> row((size_t)5 * dw);
@@ -188,6 +248,7 @@ using namespace gfo::klt;
 extern "C" {
 
 void gfo_pyr_down(const uint8_t* src, int w, int h, uint8_t* dst) { pyr_down(src, w, h, dst); }
+void gfo_clahe(const uint8_t* src, int w, int h, double clip_limit, int tiles_x, int tiles_y, uint8_t* dst) { clahe(src, w, h, clip_limit, tiles_x, tiles_y, dst); }
 void gfo_scharr(const uint8_t* src, int w, int h, int16_t* dst) { scharr(src, w, h, dst); }
 
 // level sizes and offsets (in pixels) of the packed pyramid: images [sum w*h] u8, derivatives [2 * sum w*h] int16

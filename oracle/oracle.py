@@ -577,6 +577,7 @@ def _bind_klt(L):
     vp_, ci_, cf_ = C.c_void_p, C.c_int, C.c_float
     L.gfo_pyr_down.argtypes = [vp_, ci_, ci_, vp_]
     L.gfo_scharr.argtypes = [vp_, ci_, ci_, vp_]
+    L.gfo_clahe.argtypes = [vp_, ci_, ci_, C.c_double, ci_, ci_, vp_]
     L.gfo_klt_pyramid_pixels.restype = ci_
     L.gfo_klt_pyramid_pixels.argtypes = [ci_, ci_, ci_]
     L.gfo_klt_build_pyramid.argtypes = [vp_, ci_, ci_, ci_, vp_, vp_]
@@ -592,6 +593,15 @@ def pyr_down(img):
     h, w = img.shape
     out = np.zeros(((h + 1) // 2, (w + 1) // 2), np.uint8)
     lib().gfo_pyr_down(_p(img), w, h, _p(out))
+    return out
+
+
+def clahe(img, clip_limit=3.0, tiles=(8, 8)):
+    """cv::createCLAHE(clip_limit, tiles)->apply(img) for an 8-bit gray image (reference src/Frame.cc:366-368)"""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros_like(img)
+    lib().gfo_clahe(_p(img), w, h, float(clip_limit), int(tiles[0]), int(tiles[1]), _p(out))
     return out
 
 

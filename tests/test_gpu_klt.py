@@ -127,3 +127,22 @@ def test_capacity_errors_are_loud():
     small = np.zeros((240, 320), np.uint8)
     with pytest.raises(GfsError):
         trk.fbKltTracking(small, small, np.zeros((11, 2), np.float32), np.zeros((11, 2), np.float32))
+
+
+def test_clahe_bit_exact_vs_oracle_and_cv2():
+    import cv2
+    import torch
+    from geoflowslam_b200.klt import clahe_apply, clahe_apply_device
+    from oracle import oracle as O
+    for shape, clip, tiles in (((480, 640), 3.0, (8, 8)), ((333, 445), 3.0, (8, 8)), ((100, 120), 40.0, (4, 6)), ((480, 640), 0.0, (8, 8))):
+        rng = np.random.default_rng(shape[1])
+        for img in (rng.integers(0, 256, shape, dtype=np.uint8), (rng.integers(0, 40, shape) + 100).astype(np.uint8), np.full(shape, 7, np.uint8)):
+            g = clahe_apply(img, clip, tiles)
+            assert np.array_equal(g, O.clahe(img, clip, tiles))
+            assert np.array_equal(g, cv2.createCLAHE(clip, tiles).apply(img))
+    fr = _frames(4, seed0=1040)
+    d = torch.from_numpy(fr).cuda()
+    clahe_apply_device(d, 4, 640, 480, 640, 640 * 480, d)  # in place, as Frame::Frame does
+    torch.cuda.synchronize()
+    for i in range(4):
+        assert np.array_equal(d[i].cpu().numpy(), cv2.createCLAHE(3.0, (8, 8)).apply(fr[i]))

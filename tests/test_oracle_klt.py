@@ -93,3 +93,15 @@ def test_fb_klt_tracking_matches_cv2_composition(pair):
     # empty input: untouched outputs
     pr_e, st_e = O.fb_klt_tracking(pa, pb, 640, 480, 3, np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32))
     assert len(pr_e) == 0 and len(st_e) == 0
+
+
+@pytest.mark.parametrize("shape,clip,tiles", [((480, 640), 3.0, (8, 8)), ((333, 445), 3.0, (8, 8)), ((100, 120), 40.0, (4, 6)), ((64, 64), 3.0, (8, 8)),
+                                              ((480, 640), 0.0, (8, 8))])
+def test_clahe_bit_exact_vs_cv2(shape, clip, tiles):
+    rng = np.random.default_rng(shape[1])
+    imgs = [rng.integers(0, 256, shape, dtype=np.uint8), (rng.integers(0, 40, shape) + 100).astype(np.uint8), np.full(shape, 7, np.uint8)]
+    if shape == (480, 640):
+        imgs.append(synth.orb_frames(1, 640, 480, group=8, seed0=1000)[0])
+    c = cv2.createCLAHE(clip, tiles)
+    for img in imgs:
+        assert np.array_equal(O.clahe(img, clip, tiles), c.apply(img))
