@@ -102,6 +102,8 @@ SIGNATURES = {
     "gfs_klt_last_launches": ([vp], ci),
     "gfs_clahe_apply_batch_device": ([vp, vp, ci, ci, ci, ci, C.c_size_t, C.c_double, ci, ci, vp, ci, C.c_size_t], ci),
     "gfs_clahe_apply": ([vp, vp, ci, ci, ci, C.c_double, ci, ci, vp], ci),
+    "gfs_imu_preintegrate_batch": ([vp, vp, vp, vp, ci, C.c_float, C.c_float, C.c_float, C.c_float, vp], ci),
+    "gfs_imu_preintegrate_batch_device": ([vp, vp, vp, vp, ci, C.c_float, C.c_float, C.c_float, C.c_float, vp], ci),
     "gfs_match_bf_hamming_batch_device": ([vp, vp, vp, vp, vp, ci, ci, vp, vp], ci),
     "gfs_match_bf_hamming": ([vp, vp, ci, vp, ci, vp, vp], ci),
     "gfs_gms_filter_batch_device": ([vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp], ci),

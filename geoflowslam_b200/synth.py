@@ -502,3 +502,16 @@ def pose_inertial_problem(seed=6000, mode=0, n_obs=400, outlier_frac=0.1, mono_f
         Xw=np.ascontiguousarray(np.asarray(Xw, np.float32), np.float64), uvr=np.ascontiguousarray(np.stack([uu, vv, ur], 1), np.float32),
         inv_sigma2=(1.0 / sigma ** 2).astype(np.float32), close=(z < 10.0).astype(np.uint8),
         truth=dict(Rwb=R1, twb=p1, vel=vel(t1), bg=bg_true, ba=ba_true, bad=bad))
+
+
+def imu_calib_noise(noise=IMU_NOISE):
+    """(ng, na, ngw, naw) as IMU::Calib receives them: densities scaled by sqrt(frequency) (Settings / Tracking)"""
+    sf = np.sqrt(np.float32(noise["freq"]))
+    return np.float32(noise["ng"]) * sf, np.float32(noise["na"]) * sf, np.float32(noise["ngw"]) / sf, np.float32(noise["naw"]) / sf
+
+
+def imu_samples(rng, n, dt=1 / 200, w_scale=0.3):
+    """n random (acc, gyro) samples -> (acc (n,3), gyr (n,3), rows (n,7) float32: ax ay az wx wy wz dt)"""
+    acc = rng.normal(0, 1, (n, 3)) + [0, 0, 9.81]
+    gyr = rng.normal(0, w_scale, (n, 3))
+    return acc, gyr, np.concatenate([acc, gyr, np.full((n, 1), dt)], 1).astype(np.float32)

@@ -446,6 +446,25 @@ int gfs_clahe_apply_batch_device(void* stream, const uint8_t* d_src, int batch, 
                                  double clip_limit, int tiles_x, int tiles_y, uint8_t* d_dst, int dst_pitch, size_t dst_stride);
 int gfs_clahe_apply(void* stream, const uint8_t* src, int w, int h_img, int pitch, double clip_limit, int tiles_x, int tiles_y, uint8_t* dst);
 
+/* ------------------------------------------------------------------------------------------------
+ * IMU preintegration -- replaces IMU::Preintegrated::Initialize + IntegrateNewMeasurement over
+ * an interval's measurements (reference include/ImuTypes.h:172-274, src/ImuTypes.cc:163-246; IntegratedRotation
+ * :87-112; Calib::Set :399-412) for a batch of independent intervals: what Tracking::PreintegrateIMU,
+ * Preintegrated::Reintegrate (:176-182) and MergePrevious (:248-269) compute one interval at a time.
+ *   meas    [offsets[n]][7]  acceleration xyz, angular velocity xyz, dt -- the (acc, angVel, tstep) triples the
+ *                            caller forms from consecutive IMU samples (Tracking.cc mid-point rule)
+ *   offsets [n + 1]          interval i owns rows offsets[i] .. offsets[i+1]-1 (an empty interval gives the
+ *                            Initialize() state)
+ *   bias    [n][6]           bax bay baz bwx bwy bwz (IMU::Bias)
+ *   ng, na, ngw, naw         the IMU::Calib noise densities (already scaled by sqrt(frequency) as Settings does)
+ *   out     [n][GFS_BA_PRE_STRIDE]  dR9 dV3 dP3 JRg9 JVg9 JVa9 JPg9 JPa9 C225 dT1 b6: the record GfsBaProblem.in_pre
+ *                            and GfsPoseInertialProblem.pre take
+ * ------------------------------------------------------------------------------------------------ */
+int gfs_imu_preintegrate_batch(void* stream, const float* meas, const int* offsets, const float* bias, int n, float ng, float na, float ngw,
+                               float naw, float* out);
+int gfs_imu_preintegrate_batch_device(void* stream, const float* d_meas, const int* d_offsets, const float* d_bias, int n, float ng,
+                                      float na, float ngw, float naw, float* d_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -661,3 +661,20 @@ def fb_klt_tracking(prev_pyr, cur_pyr, w, h, levels, kps, priors, win=35, nbpyrl
     lib().gfo_fb_klt(_p(prev_pyr[0]), _p(prev_pyr[1]), _p(cur_pyr[0]), _p(cur_pyr[1]), w, h, levels, _p(kps), _p(pr), n, win, nbpyrlvl,
                      ferr, max_fbklt_dist, _p(st))
     return pr, st[:n].astype(bool)
+
+
+# ---- IMU preintegration (imu_oracle.cpp)
+def _bind_imu(L):
+    L.gfo_imu_preintegrate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+
+
+_LATE_BINDERS.append(("gfo_imu_preintegrate", _bind_imu))
+
+
+def imu_preintegrate(meas, bias, ng, na, ngw, naw):
+    """IMU::Preintegrated(bias, calib) + IntegrateNewMeasurement over meas rows (ax ay az wx wy wz dt) -> record (292,) f32"""
+    m = np.ascontiguousarray(meas, np.float32).reshape(-1, 7)
+    b = np.ascontiguousarray(bias, np.float32).reshape(6)
+    out = np.zeros(292, np.float32)
+    lib().gfo_imu_preintegrate(_p(m), len(m), _p(b), float(ng), float(na), float(ngw), float(naw), _p(out))
+    return out
