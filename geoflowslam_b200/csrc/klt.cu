@@ -220,10 +220,10 @@ __device__ __forceinline__ unsigned stage_window(const LevelView& L, int x0, int
     }
   } else {
     // rows outer, lanes over the columns: the reflected column of a lane is the same for every row
-    const int c0 = reflect101(x0 + lane, L.w), c1 = lane + 32 < ww ? reflect101(x0 + lane + 32, L.w) : 0;
+    const int c0 = lane < ww ? reflect101(x0 + lane, L.w) : 0, c1 = lane + 32 < ww ? reflect101(x0 + lane + 32, L.w) : 0;
     for (int y = 0; y < ww; y++) {
       const uint8_t* row = L.img + (size_t)reflect101(y0 + y, L.h) * L.w;
-      s_win[y * pitch + lane] = row[c0];
+      if (lane < ww) s_win[y * pitch + lane] = row[c0];
       if (lane + 32 < ww) s_win[y * pitch + lane + 32] = row[c1];
     }
   }

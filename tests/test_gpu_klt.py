@@ -146,3 +146,26 @@ def test_clahe_bit_exact_vs_oracle_and_cv2():
     torch.cuda.synchronize()
     for i in range(4):
         assert np.array_equal(d[i].cpu().numpy(), cv2.createCLAHE(3.0, (8, 8)).apply(fr[i]))
+
+
+@pytest.mark.parametrize("win,levels", [(21, 2), (15, 3), (41, 1), (7, 0)])
+def test_other_window_sizes_match_oracle_bitwise(win, levels):
+    """windows narrower and wider than a warp, fewer / more levels than the reference's 35 / 3"""
+    import torch
+    from geoflowslam_b200 import KltTracker
+    from oracle import oracle as O
+    fr = _frames(2, seed0=1048)
+    pts = _points(fr[0], 300)
+    pts = np.concatenate([pts, np.array([[0.0, 0.0], [639.0, 479.0], [2.5, 470.2], [630.0, 3.0]], np.float32)])
+    n = len(pts)
+    trk = KltTracker(levels=3, max_points=512, max_batch=2)
+    pyr = _pyramids(trk, fr)
+    d_pts = torch.from_numpy(pts).cuda(); d_next = d_pts.clone()
+    d_n = torch.tensor([n], dtype=torch.int32, device="cuda")
+    d_st = torch.zeros(n, dtype=torch.uint8, device="cuda"); d_er = torch.zeros(n, dtype=torch.float32, device="cuda")
+    trk.calc_device(pyr[0], pyr[1], 1, 640, 480, d_pts, d_next, d_n, n, d_st, d_er, win=win, max_level=levels)
+    torch.cuda.synchronize()
+    pa, pb = O.klt_build_pyramid(fr[0], 3), O.klt_build_pyramid(fr[1], 3)
+    o_next, o_st, o_er = O.klt_calc(pa, pb, 640, 480, 3, pts, init=pts, win=win, max_level=levels)
+    assert np.array_equal(d_st.cpu().numpy(), o_st)
+    assert np.array_equal(d_next.cpu().numpy(), o_next) and np.array_equal(d_er.cpu().numpy(), o_er)
