@@ -587,7 +587,6 @@ def run_klt(args):
         d_pr.copy_(d_kps)
         if timed: ev[0].record()
         trk.build_pyramids_device(d_imgs, B, W, H, W, W * H, d_pyr, stream=stream)
-        if timed: ev[1].record()
         torch.index_select(d_pyr, 0, d_next_idx, out=d_cur)   # pairing only: the "current" frame of pair i
         if timed: ev[1].record()
         trk.fb_track_device(d_pyr, d_cur, B, W, H, d_kps, d_pr, d_n, 1024, d_st, nwinsize=35, nbpyrlvl=3, ferr=15.0, fmax_fbklt_dist=0.5,

@@ -549,12 +549,10 @@ int gfs_klt_fb_track(GfsKlt* h, void* stream, const uint8_t* prev_img, const uin
   GFS_CUDA(cudaMemcpyAsync(h->d_kps.p, kps, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   GFS_CUDA(cudaMemcpyAsync(h->d_next.p, priors, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   GFS_CUDA(cudaMemcpyAsync(h->d_n.p, &n, 4, cudaMemcpyHostToDevice, st));
-  const int saveBatch = h->maxBatch;
   if ((rc = gfs_klt_build_pyramid_batch_device(h, stream, dimg, 1, w, h_img, pitch, 0, (uint8_t*)h->d_pyrA.p))) return rc;
   int l1 = h->launches;
   if ((rc = gfs_klt_build_pyramid_batch_device(h, stream, dimg + (size_t)pitch * h_img, 1, w, h_img, pitch, 0, (uint8_t*)h->d_pyrB.p))) return rc;
   l1 += h->launches;
-  (void)saveBatch;
   rc = gfs_klt_fb_track_batch_device(h, stream, (const uint8_t*)h->d_pyrA.p, (const uint8_t*)h->d_pyrB.p, 1, w, h_img, (const float*)h->d_kps.p,
                                      (float*)h->d_next.p, (const int*)h->d_n.p, n, win, nbpyrlvl, ferr, fmax_fbklt_dist, (uint8_t*)h->d_status.p);
   if (rc) return rc;
