@@ -649,7 +649,7 @@ def run_klt(args):
                              "sample": "%d pairs in %.1f s: cv2 %s buildOpticalFlowPyramid + calcOpticalFlowPyrLK forward/backward, the OpenCV calls the reference makes (OpenCV's own thread pool)" % (cnt, cnt * cpu_s, cv2.__version__)},
             "e2e": {"value": 1.0 / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": 2 * W * H + int(npts) * 16, "d2h_bytes_per_step": int(npts) * 9,
                     "note": "one pair per host-pointer call (gfs_klt_fb_track), both pyramids rebuilt per call"},
-            "gpu_launches": args.steps * (4 + 1 + 1)}
+            "gpu_launches": args.steps * (5 + 1 + 1)}
     print(json.dumps(line))
 
 

@@ -14,7 +14,7 @@
 //   k_clahe_lut/apply  cv::CLAHE (Frame.cc:366-368): per-tile histogram + clip + LUT, then the bilinear LUT blend
 //   k_klt_pyr_down   CTA per 32x8 destination tile: the 68x20 source window staged in shared memory, separable
 //                    [1 4 6 4 1], (sum + 128) >> 8
-//   k_klt_scharr     thread per pixel: int16 (dI/dx, dI/dy), reflect-101 inside the image
+//   k_klt_scharr     CTA per 128x32 tile: int16 (dI/dx, dI/dy), reflect-101 inside the image, 16-byte stores
 //   k_klt_track      one warp per point, all pyramid levels and both passes in ONE launch: the 35x35 template patch
 //                    (int16 intensities with 5 fractional bits + int16 derivatives, interpolated in place from the
 //                    staged 36x36 derivative window) lives in shared memory, the 36x36 window of the other image is
@@ -38,6 +38,7 @@ struct PyrGeom {
   int w[MAX_LEVELS + 1], h[MAX_LEVELS + 1];
   int off[MAX_LEVELS + 1];    // pixel offset of the level inside the packed image / derivative arrays
   int npix;                   // total pixels over all levels
+  int tilesX[MAX_LEVELS + 1], tileBase[MAX_LEVELS + 2];  // 128x32 tiles of k_klt_scharr: per-level grid width and first block
   size_t imgBytes;            // npix rounded up to 16: the derivatives start there
   size_t frameBytes;          // imgBytes + 4 * npix
 };
@@ -53,8 +54,15 @@ static PyrGeom make_geom(int w, int h, int levels) {
     w = (w + 1) / 2; h = (h + 1) / 2;
   }
   g.npix = off;
+  int tb = 0;
+  for (int l = 0; l <= levels; l++) {
+    g.tilesX[l] = (g.w[l] + 127) / 128;
+    g.tileBase[l] = tb;
+    tb += g.tilesX[l] * ((g.h[l] + 31) / 32);
+  }
+  g.tileBase[levels + 1] = tb;
   g.imgBytes = align_up((size_t)off, 16);
-  g.frameBytes = g.imgBytes + (size_t)4 * off;
+  g.frameBytes = align_up(g.imgBytes + (size_t)4 * off, 16);
   return g;
 }
 
@@ -132,6 +140,27 @@ __global__ void __launch_bounds__(256) k_clahe_apply(const uint8_t* __restrict__
   dst[(size_t)blockIdx.z * dstStride + (size_t)y * dstPitch + x] = (uint8_t)min(max(__float2int_rn(res), 0), 255);
 }
 
+// ---- level 0 of the pyramid = the image itself (buildOpticalFlowPyramid copies it into its padded block): one launch
+// for the whole batch, 16 bytes per thread when pitch, width and the pointers allow it
+__global__ void __launch_bounds__(256) k_klt_copy_level0(const uint8_t* __restrict__ imgs, int pitch, size_t imgStride, int w, int h,
+                                                         uint8_t* __restrict__ pyr, size_t frameBytes, int vec) {
+  const uint8_t* src = imgs + (size_t)blockIdx.y * imgStride;
+  uint8_t* dst = pyr + (size_t)blockIdx.y * frameBytes;
+  if (vec) {
+    const int wq = w >> 4, n = wq * h;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const int y = i / wq, x = i - y * wq;
+      reinterpret_cast<uint4*>(dst + (size_t)y * w)[x] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)y * pitch) + x);
+    }
+  } else {
+    const int n = w * h;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const int y = i / w, x = i - y * w;
+      dst[i] = src[(size_t)y * pitch + x];
+    }
+  }
+}
+
 // ---- cv::pyrDown, 8U: dst (dw x dh) from src (sw x sh), one frame per blockIdx.z
 static const int PD_TX = 32, PD_TY = 8;
 __global__ void __launch_bounds__(PD_TX * PD_TY) k_klt_pyr_down(uint8_t* __restrict__ pyr, size_t frameBytes, int srcOff, int sw, int sh,
@@ -161,23 +190,67 @@ __global__ void __launch_bounds__(PD_TX * PD_TY) k_klt_pyr_down(uint8_t* __restr
   }
 }
 
-// ---- calcScharrDeriv for every level of every frame: thread per pixel of the packed pyramid
+// ---- calcScharrDeriv for every level of every frame.  CTA per 128x32 tile of one level: the 130x34 source window goes to
+// shared memory (aligned 32-bit loads inside the image, reflect-101 bytes on the rim), every thread produces four
+// pixels and writes them as one 16-byte store when the level's geometry allows it.  HBM-bound: 1 byte read + 4 bytes
+// written per pixel.
+static const int SC_TX = 128, SC_TY = 32;
 __global__ void __launch_bounds__(256) k_klt_scharr(uint8_t* __restrict__ pyr, PyrGeom G) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= G.npix) return;
-  int l = 0;
-  while (l < G.levels && i >= G.off[l + 1]) l++;
-  const int w = G.w[l], h = G.h[l], p = i - G.off[l];
-  const int y = p / w, x = p - y * w;
+  __shared__ __align__(16) uint8_t s_t[SC_TY + 2][SC_TX + 8];  // column c of the tile at [.][c + 4]: words stay aligned
+  int b = blockIdx.x, l = 0;
+  while (l < G.levels && b >= G.tileBase[l + 1]) l++;
+  b -= G.tileBase[l];
+  const int w = G.w[l], h = G.h[l];
+  const int x0 = (b % G.tilesX[l]) * SC_TX, y0 = (b / G.tilesX[l]) * SC_TY;
   const uint8_t* img = pyr + (size_t)blockIdx.y * G.frameBytes + G.off[l];
-  short2* der = reinterpret_cast<short2*>(pyr + (size_t)blockIdx.y * G.frameBytes + G.imgBytes) + i;
-  const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
-  const uint8_t* r0 = img + (size_t)reflect101(y - 1, h) * w;
-  const uint8_t* r1 = img + (size_t)y * w;
-  const uint8_t* r2 = img + (size_t)reflect101(y + 1, h) * w;
-  const int t0m = (r0[xm] + r2[xm]) * 3 + r1[xm] * 10, t0p = (r0[xp] + r2[xp]) * 3 + r1[xp] * 10;
-  const int t1m = r2[xm] - r0[xm], t1c = r2[x] - r0[x], t1p = r2[xp] - r0[xp];
-  *der = make_short2((short)(t0p - t0m), (short)((t1p + t1m) * 3 + t1c * 10));
+  short2* der = reinterpret_cast<short2*>(pyr + (size_t)blockIdx.y * G.frameBytes + G.imgBytes) + G.off[l];
+  const int tid = threadIdx.x;
+  const bool wordRows = (w % 4 == 0) && (G.off[l] % 4 == 0) && x0 + SC_TX <= w;
+  if (wordRows) {
+    for (int i = tid; i < (SC_TY + 2) * (SC_TX / 4); i += 256) {
+      const int r = i / (SC_TX / 4), k = i - r * (SC_TX / 4);
+      const int Y = reflect101(y0 - 1 + r, h);
+      reinterpret_cast<unsigned*>(&s_t[r][4])[k] = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)Y * w + x0) + k);
+    }
+    if (tid < 2 * (SC_TY + 2)) {  // the two rim columns (68 threads)
+      const int r = tid >> 1, right = tid & 1;
+      const int Y = reflect101(y0 - 1 + r, h);
+      s_t[r][right ? 4 + SC_TX : 3] = img[(size_t)Y * w + reflect101(right ? x0 + SC_TX : x0 - 1, w)];
+    }
+  } else {
+    for (int i = tid; i < (SC_TY + 2) * (SC_TX + 2); i += 256) {
+      const int r = i / (SC_TX + 2), c = i - r * (SC_TX + 2);
+      s_t[r][3 + c] = img[(size_t)reflect101(y0 - 1 + r, h) * w + reflect101(x0 - 1 + c, w)];
+    }
+  }
+  __syncthreads();
+  const int cx = (tid & 31) * 4, x = x0 + cx;
+  if (x >= w) return;
+  const bool vecStore = wordRows && x + 4 <= w;
+  for (int r = tid >> 5; r < SC_TY; r += 8) {
+    const int y = y0 + r;
+    if (y >= h) break;
+    // t0 = (s(y-1) + s(y+1)) * 3 + s(y) * 10 ; t1 = s(y+1) - s(y-1) for the six columns x-1 .. x+4
+    int t0[6], t1[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const int a = s_t[r][3 + cx + k], m = s_t[r + 1][3 + cx + k], c = s_t[r + 2][3 + cx + k];
+      t0[k] = (a + c) * 3 + m * 10;
+      t1[k] = c - a;
+    }
+    short2 o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) o[k] = make_short2((short)(t0[k + 2] - t0[k]), (short)((t1[k + 2] + t1[k]) * 3 + t1[k + 1] * 10));
+    short2* dst = der + (size_t)y * w + x;
+    if (vecStore) {
+      auto pk = [](short2 v) { return (unsigned)(unsigned short)v.x | ((unsigned)(unsigned short)v.y << 16); };
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pk(o[0]), pk(o[1]), pk(o[2]), pk(o[3]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (x + k < w) dst[k] = o[k];
+    }
+  }
 }
 
 // ---- LKTrackerInvoker for one point by one warp
@@ -469,16 +542,20 @@ int gfs_klt_build_pyramid_batch_device(GfsKlt* h, void* stream, const uint8_t* d
   cudaStream_t st = (cudaStream_t)stream;
   const PyrGeom g = make_geom(w, h_img, h->levels);
   // level 0 = the image itself (buildOpticalFlowPyramid copies it into the padded pyramid)
-  for (int b = 0; b < batch; b++)
-    GFS_CUDA(cudaMemcpy2DAsync(d_pyr + (size_t)b * g.frameBytes, (size_t)w, d_imgs + (size_t)b * img_stride, (size_t)pitch, (size_t)w,
-                               (size_t)h_img, cudaMemcpyDeviceToDevice, st));
-  h->launches = 0;
+  {
+    const bool vec = (w % 16 == 0) && (pitch % 16 == 0) && (img_stride % 16 == 0) && (g.frameBytes % 16 == 0) &&
+                     (reinterpret_cast<size_t>(d_imgs) % 16 == 0) && (reinterpret_cast<size_t>(d_pyr) % 16 == 0);
+    const int work = vec ? (w / 16) * h_img : w * h_img;
+    k_klt_copy_level0<<<dim3(std::min(div_up(work, 256), 148 * 4), batch), 256, 0, st>>>(d_imgs, pitch, img_stride, w, h_img, d_pyr,
+                                                                                     g.frameBytes, vec ? 1 : 0);
+  }
+  h->launches = 1;
   for (int l = 0; l < g.levels; l++) {
     k_klt_pyr_down<<<dim3(div_up(g.w[l + 1], PD_TX), div_up(g.h[l + 1], PD_TY), batch), dim3(PD_TX, PD_TY), 0, st>>>(
         d_pyr, g.frameBytes, g.off[l], g.w[l], g.h[l], g.off[l + 1], g.w[l + 1], g.h[l + 1]);
     h->launches++;
   }
-  k_klt_scharr<<<dim3(div_up(g.npix, 256), batch), 256, 0, st>>>(d_pyr, g);
+  k_klt_scharr<<<dim3(g.tileBase[g.levels + 1], batch), 256, 0, st>>>(d_pyr, g);
   h->launches++;
   GFS_CUDA(cudaGetLastError());
   return GFS_OK;
