@@ -380,8 +380,10 @@ __device__ __forceinline__ double axis_gap2(int d, double f, double cell) {
   return gg * gg;
 }
 // Visit the occupied cells of shell r (Chebyshev ring) whose lower bound does not exceed limit().
+// cls > 0 (only meaningful for r == 1): visit only the cells with exactly `cls` non-zero offsets -- 1 = the six face
+// neighbours, 2 = the twelve edge neighbours, 3 = the eight corners -- so the caller can tighten limit() in between.
 template <class Limit, class Visit>
-__device__ __forceinline__ void visit_shell(const Grid& g, const int* box, const ShellQuery& q, int r, Limit limit, Visit visit) {
+__device__ __forceinline__ void visit_shell(const Grid& g, const int* box, const ShellQuery& q, int r, Limit limit, Visit visit, int cls = 0) {
   const int x0 = max(q.cx - r, box[0]), x1 = min(q.cx + r, box[3]);
   const int y0 = max(q.cy - r, box[1]), y1 = min(q.cy + r, box[4]);
   const int z0 = max(q.cz - r, box[2]), z1 = min(q.cz + r, box[5]);
@@ -392,13 +394,16 @@ __device__ __forceinline__ void visit_shell(const Grid& g, const int* box, const
       const double gyz2 = gz2 + axis_gap2(y - q.cy, q.fy, q.cell);
       if (gyz2 > limit()) continue;
       const bool face = (z == q.cz - r) || (z == q.cz + r) || (y == q.cy - r) || (y == q.cy + r);
+      const int nzy = (z != q.cz) + (y != q.cy);
       if (face) {
         for (int x = x0; x <= x1; x++) {
+          if (cls && nzy + (x != q.cx) != cls) continue;
           if (gyz2 + axis_gap2(x - q.cx, q.fx, q.cell) > limit()) continue;
           int cs, cn;
           if (grid_find(g, x, y, z, cs, cn)) visit(cs, cn);
         }
       } else {
+        if (cls && nzy + 1 != cls) continue;
         if (q.cx - r >= x0 && !(gyz2 + axis_gap2(-r, q.fx, q.cell) > limit())) {
           int cs, cn;
           if (grid_find(g, q.cx - r, y, z, cs, cn)) visit(cs, cn);
@@ -531,23 +536,28 @@ __device__ bool knn10_two_pass(const Grid& g, const int* box, int nPts, double c
   int seen = 0, nc = 0;
   bool ok = false, overflow = false;
   for (int r = 0; r <= MAX_SHELL && !overflow; r++) {
-    const int from = nc;
-    const double lim = (double)top[KNN_K - 1];
-    visit_shell(g, box, q, r, [&]() { return lim; },
-                [&](int cs, int cn) {
-                  if (nc < KNN_CELLS && cn < 256 && cs < (1 << 24)) s_cells[nc++ * KNN_THREADS] = ((unsigned)cs << 8) | (unsigned)cn;
-                  else overflow = true;
-                });
-    walk_cells(g, qx, qy, qz, s_cells, from, nc, [&](double dd, int) {
-      float v = __double2float_ru(dd);
+    // shell 1 goes in three rounds -- face, edge, corner neighbours -- so that the k-th distance found so far prunes the
+    // farther cells (with ~8 points per cell the home cell alone rarely holds k: nothing would be pruned otherwise)
+    const int rounds = r == 1 ? 3 : 1;
+    for (int cls = 1; cls <= rounds; cls++) {
+      const int from = nc;
+      const double lim = (double)top[KNN_K - 1];
+      visit_shell(g, box, q, r, [&]() { return lim; },
+                  [&](int cs, int cn) {
+                    if (nc < KNN_CELLS && cn < 256 && cs < (1 << 24)) s_cells[nc++ * KNN_THREADS] = ((unsigned)cs << 8) | (unsigned)cn;
+                    else overflow = true;
+                  }, r == 1 ? cls : 0);
+      walk_cells(g, qx, qy, qz, s_cells, from, nc, [&](double dd, int) {
+        float v = __double2float_ru(dd);
 #pragma unroll
-      for (int i = 0; i < KNN_K; i++) {
-        const float lo = fminf(top[i], v);
-        v = fmaxf(top[i], v);
-        top[i] = lo;
-      }
-      seen++;
-    });
+        for (int i = 0; i < KNN_K; i++) {
+          const float lo = fminf(top[i], v);
+          v = fmaxf(top[i], v);
+          top[i] = lo;
+        }
+        seen++;
+      });
+    }
     const double bound = (double)r * cell + q.margin;
     if ((seen >= KNN_K && (double)top[KNN_K - 1] <= bound * bound) || box_covered(box, q, r)) { ok = true; break; }
   }
