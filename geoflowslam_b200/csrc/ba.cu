@@ -38,6 +38,7 @@ struct BaCalib {
   double fx, fy, cx, cy, bf, lambda_init;
   double deltaMono, deltaStereo;  // (float)sqrt(5.991), (float)sqrt(7.815) widened (Optimizer.cc:3427-3429)
   int nOpt, nKf, nPt, nObs, nIn, nIcp, iterations, bLarge, dimP;
+  int se3;  // 1: g2o::VertexSE3Expmap keyframes (Optimizer::LocalBundleAdjustment), 0: VertexPose (LocalInertialBA)
 };
 
 struct BaDev {
@@ -190,13 +191,50 @@ __device__ __forceinline__ int vis_error(const BaCalib& C, const double* kf, con
   err[0] = obs[0] - u;
   err[1] = obs[1] - v;
   if (obs[2] < 0) return 2;
+  if (C.se3) {  // g2o::EdgeStereoSE3ProjectXYZ::cam_project narrows 1/z to float (types_six_dof_expmap.cpp:213-221)
+    const float invz = (float)(1.0 / Xc[2]);
+    const double us = Xc[0] * (double)invz * C.fx + C.cx;
+    err[0] = obs[0] - us;
+    err[1] = obs[1] - (Xc[1] * (double)invz * C.fy + C.cy);
+    err[2] = obs[2] - (us - C.bf * (double)invz);
+    return 3;
+  }
   const double invZ = 1 / Xc[2];
   err[2] = obs[2] - (u - C.bf * invZ);
   return 3;
 }
 
-// ImuCamPose::Update (G2oTypes.cc:191-217) on a keyframe state record (pose part)
+// SE3Quat::exp (Thirdparty/g2o/g2o/types/se3quat.h:223-257)
+__device__ SE3Q se3q_exp(const double* u) {
+  const double theta = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+  double O[9], O2[9], R[9], V[9];
+  skew3(u, O);
+  mm3(O, O, O2);
+  if (theta < 0.00001) {
+    for (int i = 0; i < 9; i++) { R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + O[i] + O2[i]; V[i] = R[i]; }
+  } else {
+    const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta), c = (theta - sin(theta)) / pow(theta, 3.0);
+    for (int i = 0; i < 9; i++) {
+      const double I = (i % 4 == 0) ? 1.0 : 0.0;
+      R[i] = I + a * O[i] + b * O2[i];
+      V[i] = I + b * O[i] + c * O2[i];
+    }
+  }
+  SE3Q s;
+  s.r = quat_from_R(R);
+  quat_normalize_rot(s.r);
+  mv3(V, u + 3, s.t);
+  return s;
+}
+// ImuCamPose::Update (G2oTypes.cc:191-217) on a keyframe state record (pose part); in SE3 mode
+// g2o::VertexSE3Expmap::oplusImpl (types_six_dof_expmap.h:55-70): Tcw <- exp(u) * Tcw
 __device__ void kf_oplus(const BaCalib& C, double* st, const double* u) {
+  if (C.se3) {
+    const SE3Q T = se3q_mul(se3q_exp(u), se3q_make(st + K_RCW, st + K_TCW));
+    quat_to_R(T.r, st + K_RCW);
+    st[K_TCW] = T.t[0]; st[K_TCW + 1] = T.t[1]; st[K_TCW + 2] = T.t[2];
+    return;
+  }
   double t[3], E[9];
   mv3(st + K_RWB, u + 3, t);
   st[K_TWB] += t[0]; st[K_TWB + 1] += t[1]; st[K_TWB + 2] += t[2];
@@ -353,14 +391,20 @@ __global__ void __launch_bounds__(128) k_lin_points(BaDev D) {
         }
       }
       if (k < C.nOpt) {
+        // VertexPose: proj_jac * Rcb * SE3deriv(Xb); VertexSE3Expmap (EdgeSE3ProjectXYZ, g2o::EdgeStereoSE3ProjectXYZ):
+        // -proj_jac * SE3deriv(Xc)
         double Xb[3];
-        mv3(C.Rbc, Xc, Xb);
-        Xb[0] += C.tbc[0]; Xb[1] += C.tbc[1]; Xb[2] += C.tbc[2];
+        if (C.se3) {
+          Xb[0] = Xc[0]; Xb[1] = Xc[1]; Xb[2] = Xc[2];
+        } else {
+          mv3(C.Rbc, Xc, Xb);
+          Xb[0] += C.tbc[0]; Xb[1] += C.tbc[1]; Xb[2] += C.tbc[2];
+        }
         const double Dm[18] = {0.0, Xb[2], -Xb[1], 1.0, 0.0, 0.0, -Xb[2], 0.0, Xb[0], 0.0, 1.0, 0.0, Xb[1], -Xb[0], 0.0, 0.0, 0.0, 1.0};
         double PR[9], Jp[18];
         for (int a = 0; a < 3; a++)
           for (int c = 0; c < 3; c++)
-            PR[3 * a + c] = (a < d) ? pj[3 * a] * C.Rcb[c] + pj[3 * a + 1] * C.Rcb[3 + c] + pj[3 * a + 2] * C.Rcb[6 + c] : 0.0;
+            PR[3 * a + c] = (a < d) ? (C.se3 ? -pj[3 * a + c] : pj[3 * a] * C.Rcb[c] + pj[3 * a + 1] * C.Rcb[3 + c] + pj[3 * a + 2] * C.Rcb[6 + c]) : 0.0;
         for (int a = 0; a < 3; a++)
           for (int c = 0; c < 6; c++) Jp[6 * a + c] = PR[3 * a] * Dm[c] + PR[3 * a + 1] * Dm[6 + c] + PR[3 * a + 2] * Dm[12 + c];
         double* Eo = D.E + ((size_t)b * D.maxObs + e) * 18;
@@ -1041,6 +1085,26 @@ __global__ void k_lm_control(BaDev D, int batch, int mode, int it) {
   else atomicAdd(&D.counters[1], 1);
 }
 
+// computeLambdaInit (optimization_algorithm_levenberg.cpp:166-178) for the problems without a user lambda
+// (lambda_init <= 0): tau * max |H_jj| over the pose blocks and the landmark blocks, tau = 1e-5.  CTA per problem.
+__global__ void __launch_bounds__(256) k_lambda_auto(BaDev D) {
+  __shared__ double s_max[256];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const BaCalib& C = D.calib[b];
+  if (C.lambda_init > 0 || !problem_on(D, b, J_ACTIVE)) return;
+  double m = 0;
+  const double* H = D.Hpp + (size_t)b * D.maxDim * D.maxDim;
+  for (int j = tid; j < C.dimP; j += 256) m = fmax(m, fabs(H[(size_t)j * C.dimP + j]));
+  for (int j = tid; j < C.nPt * 3; j += 256) m = fmax(m, fabs(D.Hll[((size_t)b * D.maxPt + j / 3) * 9 + 4 * (j % 3)]));
+  s_max[tid] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) s_max[tid] = fmax(s_max[tid], s_max[tid + o]);
+    __syncthreads();
+  }
+  if (tid == 0) D.dstate[b * D_NSTATE + D_LAMBDA] = 1e-5 * s_max[0];
+}
+
 __global__ void k_ba_init(BaDev D, int batch) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
@@ -1063,7 +1127,7 @@ __global__ void __launch_bounds__(128) k_ba_finish(BaDev D, BaOutDev O) {
   if (e == 0) {
     const float err = (float)D.dstate[b * D_NSTATE + D_ERR0], err_end = (float)D.dstate[b * D_NSTATE + D_LAST];
     O.errs[2 * b] = err; O.errs[2 * b + 1] = err_end;
-    O.info[4 * b] = ((2 * err < err_end || isnan(err) || isnan(err_end)) && !C.bLarge) ? 1 : 0;
+    O.info[4 * b] = (!C.se3 && (2 * err < err_end || isnan(err) || isnan(err_end)) && !C.bLarge) ? 1 : 0;
     O.info[4 * b + 1] = D.istate[b * J_NSTATE + J_DONE];
     O.info[4 * b + 2] = D.istate[b * J_NSTATE + J_TRIALS];
     O.lambda[b] = D.dstate[b * D_NSTATE + D_LAMBDA];
@@ -1075,10 +1139,12 @@ __global__ void __launch_bounds__(128) k_ba_finish(BaDev D, BaOutDev O) {
   const double* kf = D.kf + ((size_t)b * D.maxKf + k) * KF_STRIDE;
   const double* X = D.pt + ((size_t)b * D.maxPt + j) * 3;
   const double z = kf[K_RCW + 6] * X[0] + kf[K_RCW + 7] * X[1] + kf[K_RCW + 8] * X[2] + kf[K_TCW + 2];
-  const bool dpos = mono ? (z > 0.0) : true;
+  const bool dpos = (mono || C.se3) ? (z > 0.0) : true;
   const float chi2Mono2 = 5.991f, chi2Stereo2 = 7.815f;  // Optimizer.cc:3428, 3430
   bool out;
-  if (mono) {
+  if (C.se3) {  // LocalBundleAdjustment (Optimizer.cc:1972, 1996)
+    out = c2 > (mono ? 5.991 : 7.815) || !dpos;
+  } else if (mono) {
     const bool close = D.ptClose[(size_t)b * D.maxPt + j] != 0;
     out = (c2 > chi2Mono2 && !close) || (c2 > 1.5f * chi2Mono2 && close) || !dpos;
   } else {
@@ -1239,6 +1305,8 @@ int gfs_ba_upload(GfsBa* h, void* stream, const GfsBaProblem* problems, int batc
       memcpy(&h->h_icpRt[(b * D.maxIn + e) * 12], P.icp_Rt + 12 * (size_t)e, 96);
     }
     C.iterations = P.iterations; C.bLarge = P.b_large; C.dimP = 15 * P.n_opt_kf;
+    C.se3 = P.vertex_se3 ? 1 : 0;
+    GFS_REQUIRE(!C.se3 || (P.n_inertial == 0 && P.n_icp == 0), GFS_ERR_INVALID, "vertex_se3 problems take no inertial / ICP edges");
     for (int k = 0; k < nKf; k++) {
       double* s = &h->h_kf[(b * D.maxKf + k) * KF_STRIDE];
       memcpy(s + K_RWB, P.kf_Rwb + 9 * (size_t)k, 72); memcpy(s + K_TWB, P.kf_twb + 3 * (size_t)k, 24);
@@ -1355,7 +1423,8 @@ int gfs_ba_solve_uploaded(GfsBa* h, void* stream) {
   k_lm_control<<<div_up(B, 128), 128, 0, st>>>(D, B, 0, 0);
   h->launches += 2;
   int maxIt = 0;
-  for (const BaCalib& c : h->calib) maxIt = std::max(maxIt, c.iterations);
+  bool autoLambda = false;
+  for (const BaCalib& c : h->calib) { maxIt = std::max(maxIt, c.iterations); autoLambda = autoLambda || !(c.lambda_init > 0); }
   for (int it = 0; it < maxIt; it++) {
     GFS_CUDA(cudaMemsetAsync(D.counters, 0, 8, st));
     errors(J_ACTIVE);  // computeActiveErrors at the current estimate
@@ -1366,6 +1435,7 @@ int gfs_ba_solve_uploaded(GfsBa* h, void* stream) {
     k_lin_points<<<gPt, 128, 0, st>>>(D);
     k_lin_kf<<<gKfW, 128, 0, st>>>(D);
     k_lin_inertial<<<B, INERTIAL_THREADS, 0, st>>>(D);
+    if (it == 0 && autoLambda) { k_lambda_auto<<<B, 256, 0, st>>>(D); h->launches += 1; }
     k_backup<<<gCopy, 256, 0, st>>>(D, J_ACTIVE);
     h->launches += 5;
     for (int trial = 0; trial < 10; trial++) {

@@ -20,7 +20,8 @@ class BaProblem(C.Structure):  # GfsBaProblem
                 ("kf_Rwb", dp), ("kf_twb", dp), ("kf_Rcw", dp), ("kf_tcw", dp), ("kf_vel", dp), ("kf_bg", dp),
                 ("kf_ba", dp), ("kf_has_imu", bp_), ("pt_xyz", dp), ("pt_close", bp_), ("obs_kf", ip), ("obs_pt", ip),
                 ("obs_uvr", dp), ("obs_inv_sigma2", fp), ("in_kf1", ip), ("in_kf2", ip), ("in_pre", fp),
-                ("in_downweight", bp_), ("n_icp", C.c_int), ("icp_kf1", ip), ("icp_kf2", ip), ("icp_Rt", dp)]
+                ("in_downweight", bp_), ("n_icp", C.c_int), ("icp_kf1", ip), ("icp_kf2", ip), ("icp_Rt", dp),
+                ("vertex_se3", C.c_int)]
 
 
 class BaResult(C.Structure):  # GfsBaResult
@@ -51,6 +52,7 @@ def pack_problem(prob, P=None):
     P.bf = float(prob["bf"])
     fields = dict(BaProblem._fields_)
     P.n_icp = int(prob.get("n_icp", 0))
+    P.vertex_se3 = int(prob.get("vertex_se3", 0))
     for k, dt in _BA_OPTIONAL:
         a = np.ascontiguousarray(prob.get(k, np.zeros(0)), dt)
         keep.append(a)
@@ -86,7 +88,8 @@ def unpack_result(R, out, prob):
 
 
 class Optimizer:
-    """Optimizer.LocalInertialBA(problem) -> result dict; batch variant for independent problems."""
+    """Optimizer.LocalInertialBA(problem) / Optimizer.LocalBundleAdjustment(problem) -> result dict; batch variant for
+    independent problems (inertial and non-inertial problems may share a batch)."""
 
     def __init__(self, max_kf=21, max_points=3000, max_obs=16384, max_inertial=20, max_batch=1):
         self._L = _lib.lib()
@@ -110,6 +113,13 @@ class Optimizer:
             pass
 
     def LocalInertialBA(self, problem, stream=None):
+        return self.LocalInertialBA_batch([problem], stream)[0]
+
+    def LocalBundleAdjustment(self, problem, stream=None):
+        """Optimizer::LocalBundleAdjustment (reference src/Optimizer.cc:1588-2040): the same flattened problem with
+        vertex_se3 = 1 (g2o::VertexSE3Expmap keyframes in kf_Rcw / kf_tcw, no inertial edges, 10 iterations)."""
+        if not int(problem.get("vertex_se3", 0)):
+            raise ValueError("LocalBundleAdjustment expects a vertex_se3 problem (synth.lba_problem layout)")
         return self.LocalInertialBA_batch([problem], stream)[0]
 
     def LocalInertialBA_batch(self, problems, stream=None):

@@ -515,3 +515,24 @@ def imu_samples(rng, n, dt=1 / 200, w_scale=0.3):
     acc = rng.normal(0, 1, (n, 3)) + [0, 0, 9.81]
     gyr = rng.normal(0, w_scale, (n, 3))
     return acc, gyr, np.concatenate([acc, gyr, np.full((n, 1), dt)], 1).astype(np.float32)
+
+
+def lba_problem(seed=7000, n_kf=12, n_fixed=3, n_points=1500, **kw):
+    """Synthetic Optimizer::LocalBundleAdjustment problem (reference src/Optimizer.cc:1588-2040): the non-inertial local
+    BA of the RGB-D configuration.  Same flattened layout as ba_problem with vertex_se3 = 1: g2o::VertexSE3Expmap
+    keyframes (kf_Rcw / kf_tcw), no inertial edges, 10 Levenberg iterations from g2o's default lambda, several fixed
+    covisible keyframes (lFixedCameras)."""
+    p = ba_problem(seed=seed, n_kf=n_kf + n_fixed - 1, n_points=n_points, b_large=False, **kw)
+    nk = n_kf + n_fixed
+    assert len(p["kf_Rcw"]) == nk
+    # fixed keyframes were optimised before: they hold their ground-truth pose (float32, as the KeyFrame stores it)
+    Rcb32, tcb32 = p["Rcb"].reshape(3, 3).astype(np.float32), p["tcb"].astype(np.float32)
+    for i in range(n_kf, nk):
+        R32 = _polar32(p["truth"]["Rwb"][i].astype(np.float32)); t32 = p["truth"]["twb"][i].astype(np.float32)
+        p["kf_Rwb"][i] = R32.astype(np.float64).ravel(); p["kf_twb"][i] = t32.astype(np.float64)
+        p["kf_Rcw"][i] = (Rcb32 @ R32.T).astype(np.float32).astype(np.float64).ravel()
+        p["kf_tcw"][i] = (Rcb32 @ (-(R32.T @ t32)) + tcb32).astype(np.float32).astype(np.float64)
+    p.update(vertex_se3=1, n_opt_kf=n_kf, n_fixed_kf=n_fixed, n_inertial=0, iterations=10, lambda_init=0.0, b_large=0,
+             in_kf1=np.zeros(0, np.int32), in_kf2=np.zeros(0, np.int32), in_pre=np.zeros((0, PRE_STRIDE), np.float32),
+             in_downweight=np.zeros(0, np.uint8), kf_has_imu=np.zeros(nk, np.uint8), n_icp=0)
+    return p

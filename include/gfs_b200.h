@@ -276,6 +276,11 @@ typedef struct GfsBaProblem {
   int n_icp;
   const int *icp_kf1, *icp_kf2;
   const double* icp_Rt; /* [n_icp][12] */
+  /* 0: VertexPose keyframes (LocalInertialBA).  1: g2o::VertexSE3Expmap keyframes = Optimizer::LocalBundleAdjustment
+   * (src/Optimizer.cc:1588-2040): EdgeSE3ProjectXYZ / g2o::EdgeStereoSE3ProjectXYZ, poses kf_Rcw /
+   * kf_tcw updated as exp(u) * Tcw, no inertial / ICP edges (n_inertial = n_icp = 0), iterations = 10, lambda_init <= 0
+   * (g2o's default tau * max diagonal), every observation with chi2 > 5.991 / 7.815 or non-positive depth flagged. */
+  int vertex_se3;
 } GfsBaProblem;
 
 typedef struct GfsBaResult {

@@ -274,8 +274,10 @@ struct Problem {
   double deltaMono, deltaStereo, deltaIn, deltaIcp;
 };
 
+static void se3_exp_update(KF& k, const double* u);  // VertexSE3Expmap::oplusImpl, defined after the SE3Quat helpers
 // ImuCamPose::Update (G2oTypes.cc:191-217)
 static void kf_update(const GfsBaProblem& P, KF& k, const double* pu) {
+  if (P.vertex_se3) { se3_exp_update(k, pu); return; }
   double t[3], E[9];
   mv3(k.Rwb, pu + 3, t);
   for (int i = 0; i < 3; i++) k.twb[i] += t[i];
@@ -301,6 +303,14 @@ static int vis_error(const GfsBaProblem& P, const KF& k, const double* Xw, const
   err[0] = obs[0] - u;
   err[1] = obs[1] - v;
   if (obs[2] < 0) return 2;
+  if (P.vertex_se3) {  // g2o::EdgeStereoSE3ProjectXYZ::cam_project: `const float invz = 1.0f/trans_xyz[2];` (types_six_dof_expmap.cpp:213-221)
+    const float invz = (float)(1.0 / Xc[2]);
+    const double us = Xc[0] * (double)invz * P.fx + P.cx;
+    err[0] = obs[0] - us;
+    err[1] = obs[1] - (Xc[1] * (double)invz * P.fy + P.cy);
+    err[2] = obs[2] - (us - P.bf * (double)invz);
+    return 3;
+  }
   const double invZ = 1 / Xc[2];
   err[2] = obs[2] - (u - P.bf * invZ);
   return 3;
@@ -473,6 +483,36 @@ static SE3Q se3q_inv(const SE3Q& a) {
   const double nt[3] = {-a.t[0], -a.t[1], -a.t[2]};
   quat_rot(r.r, nt, r.t);
   return r;
+}
+// SE3Quat::exp (Thirdparty/g2o/g2o/types/se3quat.h:223-257)
+static SE3Q se3q_exp(const double* u) {
+  const double w[3] = {u[0], u[1], u[2]}, ups[3] = {u[3], u[4], u[5]};
+  const double theta = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  double O[9], O2[9], R[9], V[9];
+  skew(w, O);
+  mm3(O, O, O2);
+  if (theta < 0.00001) {
+    for (int i = 0; i < 9; i++) { R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + O[i] + O2[i]; V[i] = R[i]; }
+  } else {
+    const double a = std::sin(theta) / theta, b = (1 - std::cos(theta)) / (theta * theta), c = (theta - std::sin(theta)) / std::pow(theta, 3);
+    for (int i = 0; i < 9; i++) {
+      const double I = (i % 4 == 0) ? 1.0 : 0.0;
+      R[i] = I + a * O[i] + b * O2[i];
+      V[i] = I + b * O[i] + c * O2[i];
+    }
+  }
+  SE3Q s;
+  s.r = quat_from_R(R);
+  quat_normalize_rot(s.r);
+  mv3(V, ups, s.t);
+  return s;
+}
+// g2o::VertexSE3Expmap::oplusImpl (types_six_dof_expmap.h:55-70): estimate = SE3Quat::exp(update) * estimate; the
+// keyframe record keeps Tcw as (Rcw, tcw)
+static void se3_exp_update(KF& k, const double* u) {
+  const SE3Q T = se3q_mul(se3q_exp(u), se3q_make(k.Rcw, k.tcw));
+  quat_to_R(T.r, k.Rcw);
+  memcpy(k.tcw, T.t, sizeof(T.t));
 }
 static void se3q_log(const SE3Q& a, double* res) {
   double R[9];
@@ -683,13 +723,20 @@ static void build_system(const Problem& pr, const State& s, System& S) {
     double Jl[9] = {0};  // d x 3 = -proj_jac * Rcw
     for (int a = 0; a < d; a++)
       for (int c = 0; c < 3; c++) Jl[3 * a + c] = -(pj[3 * a] * kf.Rcw[c] + pj[3 * a + 1] * kf.Rcw[3 + c] + pj[3 * a + 2] * kf.Rcw[6 + c]);
+    // VertexPose: d x 6 = proj_jac * Rcb * SE3deriv(Xb).  VertexSE3Expmap (EdgeSE3ProjectXYZ, OptimizableTypes.cpp;
+    // g2o::EdgeStereoSE3ProjectXYZ, types_six_dof_expmap.cpp:228-274): d x 6 = -proj_jac * SE3deriv(Xc)
     double Xb[3];
-    mv3(P.Rbc, Xc, Xb);
-    for (int i = 0; i < 3; i++) Xb[i] += P.tbc[i];
+    if (P.vertex_se3) {
+      memcpy(Xb, Xc, sizeof(Xb));
+    } else {
+      mv3(P.Rbc, Xc, Xb);
+      for (int i = 0; i < 3; i++) Xb[i] += P.tbc[i];
+    }
     const double D[18] = {0.0, Xb[2], -Xb[1], 1.0, 0.0, 0.0, -Xb[2], 0.0, Xb[0], 0.0, 1.0, 0.0, Xb[1], -Xb[0], 0.0, 0.0, 0.0, 1.0};
-    double PR[9] = {0}, Jp[18] = {0};  // d x 6 = proj_jac * Rcb * SE3deriv
+    double PR[9] = {0}, Jp[18] = {0};
     for (int a = 0; a < d; a++)
-      for (int c = 0; c < 3; c++) PR[3 * a + c] = pj[3 * a] * P.Rcb[c] + pj[3 * a + 1] * P.Rcb[3 + c] + pj[3 * a + 2] * P.Rcb[6 + c];
+      for (int c = 0; c < 3; c++)
+        PR[3 * a + c] = P.vertex_se3 ? -pj[3 * a + c] : pj[3 * a] * P.Rcb[c] + pj[3 * a + 1] * P.Rcb[3 + c] + pj[3 * a + 2] * P.Rcb[6 + c];
     for (int a = 0; a < d; a++)
       for (int c = 0; c < 6; c++) Jp[6 * a + c] = PR[3 * a] * D[c] + PR[3 * a + 1] * D[6 + c] + PR[3 * a + 2] * D[12 + c];
     // point block
@@ -868,7 +915,17 @@ static void solve(const GfsBaProblem* P, GfsBaResult* R) {
     const double iniChi = currentChi;
     double tempChi = currentChi;
     build_system(pr, s, S);
-    if (it == 0) { lambda = P->lambda_init; ni = 2; nBad = 0; }
+    if (it == 0) {
+      lambda = P->lambda_init;
+      if (!(lambda > 0)) {  // computeLambdaInit: tau * max |H_jj| over every vertex (optimization_algorithm_levenberg.cpp:166-178)
+        double md = 0;
+        for (int j = 0; j < pr.dimP; j++) md = std::max(std::fabs(S.Hpp[(size_t)j * pr.dimP + j]), md);
+        for (int j = 0; j < pr.nPt; j++)
+          for (int a = 0; a < 3; a++) md = std::max(std::fabs(S.Hll[9 * (size_t)j + 4 * a]), md);
+        lambda = 1e-5 * md;
+      }
+      ni = 2; nBad = 0;
+    }
     double rho = 0;
     int qmax = 0;
     do {
@@ -912,7 +969,7 @@ static void solve(const GfsBaProblem* P, GfsBaResult* R) {
   R->iterations_done = done;
   R->lm_trials = trials;
   R->lambda_final = lambda;
-  R->failed = ((2 * R->err < R->err_end || std::isnan(R->err) || std::isnan(R->err_end)) && !P->b_large) ? 1 : 0;
+  R->failed = (!P->vertex_se3 && (2 * R->err < R->err_end || std::isnan(R->err) || std::isnan(R->err_end)) && !P->b_large) ? 1 : 0;
   const float chi2Mono2 = 5.991f, chi2Stereo2 = 7.815f;
   for (int e = 0; e < pr.nObs; e++) {
     const int k = P->obs_kf[e], j = P->obs_pt[e];
@@ -921,10 +978,12 @@ static void solve(const GfsBaProblem* P, GfsBaResult* R) {
     R->obs_chi2[e] = c2;
     const KF& kf = s.kf[k];
     const double z = kf.Rcw[6] * s.pt[3 * (size_t)j] + kf.Rcw[7] * s.pt[3 * (size_t)j + 1] + kf.Rcw[8] * s.pt[3 * (size_t)j + 2] + kf.tcw[2];
-    const bool dpos = mono ? (z > 0.0) : true;
+    const bool dpos = (mono || P->vertex_se3) ? (z > 0.0) : true;
     R->obs_depth_positive[e] = dpos;
     bool out;
-    if (mono) {
+    if (P->vertex_se3) {  // LocalBundleAdjustment (Optimizer.cc:1972, 1996)
+      out = c2 > (mono ? 5.991 : 7.815) || !dpos;
+    } else if (mono) {
       const bool close = P->pt_close[j] != 0;
       out = (c2 > chi2Mono2 && !close) || (c2 > 1.5f * chi2Mono2 && close) || !dpos;
     } else {

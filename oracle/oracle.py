@@ -273,7 +273,8 @@ class BaProblem(C.Structure):  # mirrors GfsBaProblem (include/gfs_b200.h)
                 ("kf_Rwb", dp), ("kf_twb", dp), ("kf_Rcw", dp), ("kf_tcw", dp), ("kf_vel", dp), ("kf_bg", dp),
                 ("kf_ba", dp), ("kf_has_imu", bp_), ("pt_xyz", dp), ("pt_close", bp_), ("obs_kf", ip), ("obs_pt", ip),
                 ("obs_uvr", dp), ("obs_inv_sigma2", fp), ("in_kf1", ip), ("in_kf2", ip), ("in_pre", fp),
-                ("in_downweight", bp_), ("n_icp", C.c_int), ("icp_kf1", ip), ("icp_kf2", ip), ("icp_Rt", dp)]
+                ("in_downweight", bp_), ("n_icp", C.c_int), ("icp_kf1", ip), ("icp_kf2", ip), ("icp_Rt", dp),
+                ("vertex_se3", C.c_int)]
 
 
 class BaResult(C.Structure):  # mirrors GfsBaResult
@@ -304,6 +305,7 @@ def ba_pack(prob, struct_cls=BaProblem):
         setattr(P, k, float(prob[k]))
     P.bf = float(prob["bf"])
     P.n_icp = int(prob.get("n_icp", 0))
+    P.vertex_se3 = int(prob.get("vertex_se3", 0))
     for k, dt in _BA_OPTIONAL:
         a = np.ascontiguousarray(prob.get(k, np.zeros(0)), dt)
         keep.append(a)

@@ -113,3 +113,34 @@ def test_icp_edges_numeric_jacobian():
     q = dict(p); q["n_icp"] = 0
     g0 = opt.LocalInertialBA(q)
     assert np.abs(g0["kf_twb"] - g["kf_twb"]).max() > 1e-6      # the ICP factors do change the solution
+
+
+def test_local_bundle_adjustment_matches_oracle():
+    """Optimizer::LocalBundleAdjustment (SURVEY.md 8f rank 3): g2o::VertexSE3Expmap keyframes, no inertial edges"""
+    from geoflowslam_b200 import Optimizer
+    from oracle import oracle as O
+    opt = Optimizer(max_kf=21, max_points=1500, max_obs=8192, max_inertial=20, max_batch=1)
+    for seed, kw in ((7000, {}), (7001, dict(n_kf=4, n_fixed=2, n_points=120)), (7002, dict(n_kf=18, n_fixed=1, n_points=800, outlier_frac=0.05))):
+        p = synth.lba_problem(seed, **kw)
+        g = opt.LocalBundleAdjustment(p)
+        o = O.ba_solve(p)
+        _check(g, o, p)
+        assert g["failed"] is False and o["iterations_done"] >= 5
+        # stereo edges report their depth sign in this mode; the velocity / bias records pass through untouched
+        assert np.array_equal(g["kf_vel"], p["kf_vel"]) and np.array_equal(g["kf_bg"], p["kf_bg"])
+        nk = p["n_opt_kf"]
+        assert np.array_equal(g["kf_Rcw"][nk:], p["kf_Rcw"][nk:])  # fixed keyframes
+        tr = p["truth"]
+        Rcb, tcb = p["Rcb"].reshape(3, 3), p["tcb"]
+        tcw_t = np.array([Rcb @ (-(tr["Rwb"][k].T @ tr["twb"][k])) + tcb for k in range(nk)])
+        assert np.abs(g["kf_tcw"][:nk] - tcw_t).mean() < 0.5 * np.abs(p["kf_tcw"][:nk] - tcw_t).mean()
+
+
+def test_mixed_batch_inertial_and_se3():
+    from geoflowslam_b200 import Optimizer
+    from oracle import oracle as O
+    probs = [synth.ba_problem(seed=3010, n_kf=8, n_points=300, b_large=False), synth.lba_problem(7003, n_kf=6, n_fixed=2, n_points=300),
+             synth.lba_problem(7004, n_kf=10, n_fixed=3, n_points=400), synth.ba_problem(seed=3011, n_kf=12, n_points=400)]
+    opt = Optimizer(max_kf=21, max_points=400, max_obs=4096, max_inertial=20, max_batch=4)
+    for g, p in zip(opt.LocalInertialBA_batch(probs), probs):
+        _check(g, O.ba_solve(p), p)
