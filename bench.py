@@ -300,7 +300,14 @@ def run_ours(args):
     # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r01_summary.md), scaled to this launch
     ncu_traffic_per_frame = {"fast_cells": (113.197056e6 + 5.351680e6) / 128}
     traffic = ncu_traffic_per_frame[top] * B if top in ncu_traffic_per_frame else None
-    roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+    # every stage against the same roof (algorithmic bytes / CUDA-event time), for the stage table in DESIGN.md
+    stage_roof = {}
+    for st_name, st_ms in prof.items():
+        if st_ms <= 0.01:
+            continue
+        a = algorithmic_bytes(st_name, B if st_name not in ("bf_hamming", "gms") else B - 1, mean_kp, cand_per_frame)
+        stage_roof[st_name] = {"ms": st_ms, "algorithmic_bytes": a, "achieved": a / (st_ms / 1e3) / 1e9, "frac": a / (st_ms / 1e3) / 1e9 / peak}
+    roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "stages": stage_roof,
             "frac": achieved / peak, "traffic": traffic, "traffic_source": "ncu capture profiles/r01_final_k_fast_cells_ncu_details.txt" if traffic else None,
             "algorithmic_bytes": alg, "ms_per_launch_group": prof[top], "peak_source": peak_src,
             "stage_ms": prof}
