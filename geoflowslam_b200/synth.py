@@ -536,3 +536,65 @@ def lba_problem(seed=7000, n_kf=12, n_fixed=3, n_points=1500, **kw):
              in_kf1=np.zeros(0, np.int32), in_kf2=np.zeros(0, np.int32), in_pre=np.zeros((0, PRE_STRIDE), np.float32),
              in_downweight=np.zeros(0, np.uint8), kf_has_imu=np.zeros(nk, np.uint8), n_icp=0)
     return p
+
+
+# ------------------------------------------------------------------------------------------------
+# A closed-loop test sequence (BASELINE configs[4] in miniature): a textured wall seen by a moving RGB-D-inertial rig.
+# Exact geometry, so landmarks, depth and IMU samples are mutually consistent.
+# ------------------------------------------------------------------------------------------------
+def vio_sequence(seed=8000, n_frames=20, w=640, h=480, fps=30, imu_rate=200, wall_x=3.0, ppm=260.0):
+    """-> dict(frames (n,h,w) u8, depth (n,h,w) f32, stamps, Rwb/twb/vel truth per frame, imu rows per frame interval
+    [(m,7) ax ay az wx wy wz dt], calibration).  Body frame: x forward, y left, z up; camera z forward."""
+    rng = np.random.default_rng(seed)
+    cam = G1_CAM
+    Rbc = np.array([[0, 0, 1.0], [-1, 0, 0], [0, -1, 0]])
+    tbc = np.array([0.05, 0.02, 0.01])
+    tex = scene(seed, 1400, 1800, nrect=900)
+    y0, z0 = -tex.shape[1] / (2 * ppm), -tex.shape[0] / (2 * ppm)
+    g = np.array([0, 0, -9.81])
+    ph = rng.uniform(0, 6.28, 4)
+
+    def pose(t):
+        yaw = 0.10 * np.sin(1.1 * t + ph[0]); pitch = 0.04 * np.sin(0.9 * t + ph[1]); roll = 0.03 * np.cos(1.3 * t + ph[2])
+        R = _rot(np.array([0, 0, yaw])) @ _rot(np.array([0, pitch, 0])) @ _rot(np.array([roll, 0, 0]))
+        p = np.array([0.15 * np.sin(0.8 * t + ph[3]), 0.35 * np.sin(0.7 * t), 0.10 * np.sin(0.9 * t)])
+        return R, p
+
+    hh = 1e-4
+    vs, us = np.mgrid[0:h, 0:w].astype(np.float64)
+    dc = np.stack([(us - cam["cx"]) / cam["fx"], (vs - cam["cy"]) / cam["fy"], np.ones_like(us)], -1)
+    frames = np.zeros((n_frames, h, w), np.uint8); depth = np.zeros((n_frames, h, w), np.float32)
+    Rs, ps, vels, stamps = [], [], [], []
+    for k in range(n_frames):
+        t = k / fps
+        R, p = pose(t)
+        Rwc = R @ Rbc; twc = R @ tbc + p
+        dw = dc @ Rwc.T
+        s = (wall_x - twc[0]) / dw[..., 0]
+        P = twc + s[..., None] * dw
+        tu = (P[..., 1] - y0) * ppm; tv = (P[..., 2] - z0) * ppm
+        u0 = np.clip(np.floor(tu).astype(np.int32), 0, tex.shape[1] - 2); v0 = np.clip(np.floor(tv).astype(np.int32), 0, tex.shape[0] - 2)
+        fu = (tu - u0).astype(np.float32); fv = (tv - v0).astype(np.float32)
+        img = (tex[v0, u0] * (1 - fu) + tex[v0, u0 + 1] * fu) * (1 - fv) + (tex[v0 + 1, u0] * (1 - fu) + tex[v0 + 1, u0 + 1] * fu) * fv
+        img = img + rng.normal(0, 1.0, img.shape).astype(np.float32)
+        frames[k] = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+        depth[k] = s.astype(np.float32)
+        Rs.append(R); ps.append(p); vels.append((pose(t + hh)[1] - pose(t - hh)[1]) / (2 * hh)); stamps.append(t)
+    # IMU: mid-point samples between consecutive frames (the last interval of each frame is shortened to end on the frame)
+    bg_true = np.array([0.002, -0.001, 0.0015]); ba_true = np.array([0.02, -0.03, 0.01])
+    imu = []
+    for k in range(1, n_frames):
+        ta, tb = stamps[k - 1], stamps[k]
+        edges = list(np.arange(ta, tb - 1e-9, 1.0 / imu_rate)) + [tb]
+        rows = []
+        for a, b in zip(edges[:-1], edges[1:]):
+            tm = 0.5 * (a + b)
+            R0, p0 = pose(tm); Rp, pp = pose(tm + hh); Rm, pm = pose(tm - hh)
+            a_w = (pp - 2 * p0 + pm) / (hh * hh)
+            dRm = R0.T @ (Rp - Rm) / (2 * hh)
+            gyr = np.array([dRm[2, 1], dRm[0, 2], dRm[1, 0]]) + bg_true + rng.normal(0, 2e-4, 3)
+            acc = R0.T @ (a_w - g) + ba_true + rng.normal(0, 2e-3, 3)
+            rows.append(np.concatenate([acc, gyr, [b - a]]))
+        imu.append(np.array(rows, np.float32))
+    return dict(frames=frames, depth=depth, stamps=np.array(stamps), Rwb=np.array(Rs), twb=np.array(ps), vel=np.array(vels), imu=imu,
+                bg=bg_true, ba=ba_true, Rbc=Rbc, tbc=tbc, cam=cam, gravity=g)
