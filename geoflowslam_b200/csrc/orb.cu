@@ -17,6 +17,7 @@
 // with explicit _rn intrinsics so nvcc cannot contract them into FMAs.
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -418,6 +419,227 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbDev P, const uin
     for (int j = 0; j < nKept; j++) rank += (int)(keptList[j] & 0xffffu) < idx;
     const int y = idx / dw, x = idx - y * dw;
     const unsigned kx = (unsigned)(x + 3 + cj * L.wCell), ky = (unsigned)(y + 3 + ci * L.hCell);
+    out[rank] = kx | (ky << 12) | ((e >> 16) << 24);
+  }
+  if (tid == 0) *outCount = nKept;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fast_cells2: same contract as k_fast_cells (one CTA per (cell, frame), same outputs), fewer
+// instructions per pixel.
+//   phase 1: one thread per aligned 4-pixel word of the tested region.  The word and its four ring
+//            neighbours (3 rows up / down, 3 columns left / right) are split into even / odd bytes
+//            as 16-bit lanes, so `v > c + th` and `v < c - th` are one 32-bit add each for two
+//            pixels (bit 15 of `c + th + 0x8000 - v` / `v + 0x8000 - c + th`; no lane ever
+//            borrows).  Survivors of the antipodal-pair reject are appended as (y << 8 | x) keys.
+//   phase 2: per survivor the 16 ring differences are packed as (d + 256, -d + 256) in the two
+//            halves of a register (one IMAD: v * 0xFFFF + const) and the nine-arc min / max network
+//            runs on both polarities at once with VIMNMX(3).S16x2.  corner <=> best > th, which is
+//            the arc test itself (min over an arc of +-d > th).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned fast_best16_packed(const unsigned (&q)[16]) {
+  unsigned a2[16], a4[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) a2[k] = __vmins2(q[k], q[(k + 1) & 15]);
+#pragma unroll
+  for (int k = 0; k < 16; k++) a4[k] = __vmins2(a2[k], a2[(k + 2) & 15]);
+  unsigned best = 0u;
+#pragma unroll
+  for (int k = 0; k < 16; k += 2) {
+    const unsigned e0 = __vimin3_s16x2(a4[k], a4[(k + 4) & 15], q[(k + 8) & 15]);
+    const unsigned e1 = __vimin3_s16x2(a4[k + 1], a4[(k + 5) & 15], q[(k + 9) & 15]);
+    best = __vimax3_s16x2(best, e0, e1);
+  }
+  return best;
+}
+
+__global__ void __launch_bounds__(FAST_THREADS) k_fast_cells2(OrbDev P, const uint8_t* __restrict__ img0,
+                                                               long long img_stride, int pitch0,
+                                                               const uint8_t* __restrict__ pyr,
+                                                               uint32_t* __restrict__ cellKeys,
+                                                               int* __restrict__ cellCount) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  __shared__ int s_nCand, s_nCorner, s_nKept;
+  __shared__ unsigned s_vm[FAST_THREADS];
+  const int tid = threadIdx.x;
+  const int cell = blockIdx.x, frame = blockIdx.y;
+  int l = 0;
+  while (l + 1 < P.nlevels && cell >= P.lv[l + 1].cellBase) l++;
+  const LevelDev& L = P.lv[l];
+  const int c = cell - L.cellBase;
+  const int ci = c / L.nCols, cj = c - ci * L.nCols;
+  const int iniY = MIN_BORDER + ci * L.hCell, iniX = MIN_BORDER + cj * L.wCell;
+  int maxY = iniY + L.hCell + 6, maxX = iniX + L.wCell + 6;
+  const bool skip = (iniY >= L.maxBorderY - 3) || (iniX >= L.maxBorderX - 6);
+  maxY = min(maxY, L.maxBorderY);
+  maxX = min(maxX, L.maxBorderX);
+  const int rw = maxX - iniX, rh = maxY - iniY;
+  int* outCount = cellCount + (long long)frame * P.totalCells + cell;
+  if (skip || rw < 7 || rh < 7) {
+    if (tid == 0) *outCount = 0;
+    return;
+  }
+  const uint8_t* src;
+  int pitch;
+  if (l == 0) {
+    src = img0 + (long long)frame * img_stride;
+    pitch = pitch0;
+  } else {
+    src = pyr + (long long)frame * P.pyrStride + L.off;
+    pitch = L.pitch;
+  }
+  const int RP = P.roiPitch, SP = P.scPitch;
+  uint8_t* sc = sm + P.offSc;                       // [(dh+2)][SP], zero border
+  uint16_t* corners = (uint16_t*)(sm + P.offCorner);
+  uint16_t* cand = (uint16_t*)(sm + P.offCand);
+  uint32_t* keptList = (uint32_t*)(sm + P.offKept);
+  const int dw = rw - 6, dh = rh - 6;
+  // the ROI is staged so that its words are the source's words: pixel (y, x) at sm[y * RP + shift + x]
+  const int shift = (int)(((size_t)src + (size_t)iniX) & 3);
+  const uint8_t* roi = sm + shift;
+  const int rp32 = RP >> 2;
+  if ((pitch & 3) == 0) {
+    const int nW = (shift + rw + 3) >> 2;
+    const uint32_t* s32 = (const uint32_t*)(src + (long long)iniY * pitch + (iniX - shift));
+    const int p32 = pitch >> 2;
+    uint32_t* d32 = (uint32_t*)sm;
+    if (nW <= 16) {
+      const int x = tid & 15;
+      if (x < nW)
+        for (int y = tid >> 4; y < rh; y += FAST_THREADS / 16) d32[y * rp32 + x] = __ldg(s32 + (long long)y * p32 + x);
+    } else {
+      for (int idx = tid; idx < nW * rh; idx += FAST_THREADS) {
+        const int y = idx / nW, x = idx - y * nW;
+        d32[y * rp32 + x] = __ldg(s32 + (long long)y * p32 + x);
+      }
+    }
+  } else {
+    for (int idx = tid; idx < rw * rh; idx += FAST_THREADS) {
+      const int y = idx / rw, x = idx - y * rw;
+      sm[shift + y * RP + x] = __ldg(src + (long long)(iniY + y) * pitch + iniX + x);
+    }
+  }
+  {
+    uint32_t* z = (uint32_t*)sc;
+    for (int idx = tid; idx < ((dh + 2) * SP) >> 2; idx += FAST_THREADS) z[idx] = 0u;
+  }
+  const int wLo = (shift + 3) >> 2, wHi = (shift + rw - 4) >> 2, nWt = wHi - wLo + 1;
+  const unsigned inv = 65536u / (unsigned)nWt + 1u;  // i / nWt == (i * inv) >> 16 for i < 4096
+  if (tid < nWt) {
+    // which bytes of word wLo + tid are tested pixels (column in [0, dw)), as bits 14 / 15 / 30 / 31
+    const int xb = 4 * (wLo + tid) - shift - 3;
+    unsigned vm = 0u;
+    if (xb >= 0 && xb < dw) vm |= 0x00004000u;
+    if (xb + 1 >= 0 && xb + 1 < dw) vm |= 0x00008000u;
+    if (xb + 2 >= 0 && xb + 2 < dw) vm |= 0x40000000u;
+    if (xb + 3 >= 0 && xb + 3 < dw) vm |= 0x80000000u;
+    s_vm[tid] = vm;
+  }
+  if (tid == 0) { s_nCorner = 0; s_nCand = 0; s_nKept = 0; }
+  __syncthreads();
+
+  const int thMin = P.minTh, thIni = P.iniTh;
+  const int items = nWt * dh;  // (row, word) grid of the words that hold tested pixels (x in [3, rw - 3))
+  const uint32_t* sm32 = (const uint32_t*)sm;
+  int nKept = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    const int th = pass == 0 ? thIni : thMin;
+    // phase 1: antipodal-pair reject, four pixels per thread.  Every 9-arc of the 16-ring holds one
+    // pixel of each antipodal pair, so both (0,8) and (4,12) must have a bright (dark) member.
+    {
+      const unsigned K = (unsigned)(th + 0x8000) * 0x00010001u;
+      const uint32_t* r0 = sm32 + 3 * rp32 + wLo;
+      const int key0 = 4 * wLo - shift - 3;
+      for (int it = tid; it < items; it += FAST_THREADS) {
+        const int y = (int)(((unsigned)it * inv) >> 16), w = it - y * nWt;
+        const uint32_t* r = r0 + y * rp32 + w;
+        const unsigned key = (unsigned)((y << 8) + 4 * w + key0);  // (row << 8 | column) of byte 0
+        const unsigned C = r[0], Wm = r[-1], Wp = r[1], U = r[-3 * rp32], D = r[3 * rp32];
+        const unsigned Lw = __byte_perm(Wm, C, 0x4321), Rw = __byte_perm(C, Wp, 0x6543);
+        unsigned ok[2];
+#pragma unroll
+        for (int par = 0; par < 2; par++) {
+          const unsigned sel = par ? 0x4341u : 0x4240u;
+          const unsigned cc = __byte_perm(C, 0u, sel);
+          const unsigned HB = cc + K, LB = K - cc;
+          const unsigned u = __byte_perm(U, 0u, sel), d = __byte_perm(D, 0u, sel);
+          const unsigned lf = __byte_perm(Lw, 0u, sel), rt = __byte_perm(Rw, 0u, sel);
+          const unsigned notBright = ((HB - u) & (HB - d)) | ((HB - lf) & (HB - rt));
+          const unsigned notDark = ((LB + u) & (LB + d)) | ((LB + lf) & (LB + rt));
+          ok[par] = ~(notBright & notDark);
+        }
+        // bits 14 / 15 / 30 / 31 = pixels 0 / 1 / 2 / 3 of the word
+        const unsigned t = (((ok[0] & 0x80008000u) >> 1) | (ok[1] & 0x80008000u)) & s_vm[w];
+        if (t) {
+          int pos = atomicAdd(&s_nCand, __popc(t));
+          if (t & 0x00004000u) cand[pos++] = (uint16_t)key;
+          if (t & 0x00008000u) cand[pos++] = (uint16_t)(key + 1u);
+          if (t & 0x40000000u) cand[pos++] = (uint16_t)(key + 2u);
+          if (t & 0x80000000u) cand[pos] = (uint16_t)(key + 3u);
+        }
+      }
+    }
+    __syncthreads();
+    // phase 2 (survivors only, densely packed): score over the nine-arcs, corner list
+    {
+      const int nCand = s_nCand;
+      for (int i = tid; i < nCand; i += FAST_THREADS) {
+        const unsigned key = cand[i];
+        const int y = (int)(key >> 8), x = (int)(key & 255u);
+        const uint8_t* p = roi + (y + 3) * RP + (x + 3);
+        const unsigned cval = p[0];
+        const unsigned CC = (cval + 256u) + ((256u - cval) << 16);
+        unsigned q[16];
+        q[0] = p[3 * RP];       q[1] = p[3 * RP + 1];   q[2] = p[2 * RP + 2];   q[3] = p[RP + 3];
+        q[4] = p[3];            q[5] = p[-RP + 3];      q[6] = p[-2 * RP + 2];  q[7] = p[-3 * RP + 1];
+        q[8] = p[-3 * RP];      q[9] = p[-3 * RP - 1];  q[10] = p[-2 * RP - 2]; q[11] = p[-RP - 3];
+        q[12] = p[-3];          q[13] = p[RP - 3];      q[14] = p[2 * RP - 2];  q[15] = p[3 * RP - 1];
+#pragma unroll
+        for (int k = 0; k < 16; k++) q[k] = q[k] * 0xFFFFu + CC;  // (c - v + 256) | (v - c + 256) << 16
+        const unsigned b2 = fast_best16_packed(q);
+        const int best = (int)max(b2 & 0xFFFFu, b2 >> 16) - 256;
+        if (best > th) {
+          sc[(y + 1) * SP + (x + 1)] = (uint8_t)(best - 1);  // th >= 0, best <= 255
+          corners[atomicAdd(&s_nCorner, 1)] = (uint16_t)key;
+        }
+      }
+    }
+    __syncthreads();
+    // 3x3 NMS with strict '>' over the corners of this pass; pixels outside the cell's tested region
+    // (and non-corners) score 0
+    {
+      const int nCorner = s_nCorner;
+      for (int i = tid; i < nCorner; i += FAST_THREADS) {
+        const unsigned key = corners[i];
+        const int y = (int)(key >> 8), x = (int)(key & 255u);
+        const uint8_t* q = sc + (y + 1) * SP + (x + 1);
+        const int sv = q[0];
+        if (sv == 0) continue;
+        int m = max(max(q[-SP - 1], q[-SP]), max(q[-SP + 1], q[-1]));
+        m = max(m, max(max(q[1], q[SP - 1]), max(q[SP], q[SP + 1])));
+        if (sv > m) keptList[atomicAdd(&s_nKept, 1)] = key | ((uint32_t)sv << 16);
+      }
+    }
+    __syncthreads();
+    nKept = s_nKept;
+    if (nKept > 0 || thIni == thMin) break;
+    // nothing at iniTh: clear and redo the cell at minTh
+    __syncthreads();
+    {
+      uint32_t* z = (uint32_t*)sc;
+      for (int idx = tid; idx < ((dh + 2) * SP) >> 2; idx += FAST_THREADS) z[idx] = 0u;
+    }
+    if (tid == 0) { s_nCorner = 0; s_nCand = 0; s_nKept = 0; }
+    __syncthreads();
+  }
+  // output in cv::FAST order (row-major): rank = number of survivors with a smaller key
+  uint32_t* out = cellKeys + ((long long)frame * P.totalCells + cell) * P.cellCap;
+  for (int i = tid; i < nKept; i += FAST_THREADS) {
+    const uint32_t e = keptList[i];
+    const unsigned key = e & 0xffffu;
+    int rank = 0;
+    for (int j = 0; j < nKept; j++) rank += (keptList[j] & 0xffffu) < key;
+    const unsigned kx = (key & 255u) + 3u + (unsigned)(cj * L.wCell), ky = (key >> 8) + 3u + (unsigned)(ci * L.hCell);
     out[rank] = kx | (ky << 12) | ((e >> 16) << 24);
   }
   if (tid == 0) *outCount = nKept;
@@ -1015,6 +1237,7 @@ struct GfsOrb {
   DevBuf d_in, d_okp, d_odesc, d_on, d_omono, d_tkp, d_tdesc, d_pattern;
   PinnedBuf h_in, h_okp, h_odesc, h_on;
   size_t fastSmem = 0, octSmem = 0, pyrSmem = 0, pyr3Smem = 0;
+  bool fastV1 = getenv("GFS_FAST_V1") != nullptr;  // first-generation FAST kernel (A/B runs); same results
   int pyr3Rows = 0, pyr3PitchF = 0;  // k_pyr_level3 shared-memory geometry; pyr3Rows == 0: generic kernel
   DevBuf d_tabs3;
   // optional per-stage CUDA-event timing (bench roofline): pyramid, fast, octree, blur, orient/desc, pack
@@ -1247,6 +1470,7 @@ static int orb_set_geometry(GfsOrb* h, int w, int ht) {
   }
   if (h->fastSmem > fastMax) {
     GFS_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem));
+    GFS_CUDA(cudaFuncSetAttribute(k_fast_cells2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fastSmem));
     fastMax = h->fastSmem;
   }
   h->pyr3Rows = pyr3Rows;
@@ -1386,8 +1610,12 @@ static int orb_run_chunk(GfsOrb* h, cudaStream_t st, int slot0, const uint8_t* d
     }
   }
   mark(1);
-  k_fast_cells<<<dim3(D.totalCells, batch), FAST_THREADS, h->fastSmem, st>>>(
-      D, d_imgs, (long long)img_stride, pitch, pyr, cellKeys, cellCount);
+  if (h->fastV1)
+    k_fast_cells<<<dim3(D.totalCells, batch), FAST_THREADS, h->fastSmem, st>>>(
+        D, d_imgs, (long long)img_stride, pitch, pyr, cellKeys, cellCount);
+  else
+    k_fast_cells2<<<dim3(D.totalCells, batch), FAST_THREADS, h->fastSmem, st>>>(
+        D, d_imgs, (long long)img_stride, pitch, pyr, cellKeys, cellCount);
   mark(2);
   k_octree<<<div_up(batch * h->nlevels, OCT_WARPS), OCT_WARPS * 32, h->octSmem, st>>>(
       D, batch, cellKeys, cellCount, keysA, keysB, selKeys, selCount, (int*)h->d_status.p);
