@@ -25,7 +25,7 @@ struct GfsFrontend {
   // host-buffer path: H2D of chunk k+1 and D2H of chunk k-1 overlap the kernels of chunk k
   cudaStream_t copyStream = nullptr, outStream = nullptr, auxStream = nullptr;
   cudaEvent_t evStart = nullptr;
-  std::vector<cudaEvent_t> evIn, evDone;
+  std::vector<cudaEvent_t> evIn, evDone, evExt;
   int chunk = 128;
   bool profiling = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, after orb, after bf, after gms
@@ -58,6 +58,7 @@ int gfs_frontend_destroy(GfsFrontend* f) {
     if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : f->evIn) cudaEventDestroy(e);
   for (cudaEvent_t e : f->evDone) cudaEventDestroy(e);
+  for (cudaEvent_t e : f->evExt) cudaEventDestroy(e);
   if (f->copyStream) cudaStreamDestroy(f->copyStream);
   if (f->outStream) cudaStreamDestroy(f->outStream);
   if (f->auxStream) cudaStreamDestroy(f->auxStream);
@@ -149,7 +150,9 @@ int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batc
   GfsKeyPoint* d_kp = (GfsKeyPoint*)f->d_kp.p;
   uint8_t* d_desc = (uint8_t*)f->d_desc.p;
   uint8_t* d_in = (uint8_t*)f->d_in.p;
-  const bool pinned = is_pinned_host(imgs) && is_pinned_host(out_kp) && is_pinned_host(out_desc);
+  const bool pinned = is_pinned_host(imgs) && is_pinned_host(out_kp) && is_pinned_host(out_desc) &&
+                      (batch == 1 || (is_pinned_host(out_train_idx) && is_pinned_host(out_dist) && is_pinned_host(out_inlier)));
+  bool matchedInChunks = false;
   // H2D is faster than the kernels, so after the first chunk the copy stream stays ahead: only the first
   // copy is exposed.  Chunks of batch/8 keep it short while the kernels still see >= 64 frames.
   const char* ce = getenv("GFS_FRONTEND_CHUNKS");
@@ -166,11 +169,13 @@ int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batc
     }
     const int nChunks = 1 + div_up(batch - firstChunk, f->chunk);
     while ((int)f->evIn.size() < nChunks) {
-      cudaEvent_t a, b2;
+      cudaEvent_t a, b2, c2;
       GFS_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
       GFS_CUDA(cudaEventCreateWithFlags(&b2, cudaEventDisableTiming));
+      GFS_CUDA(cudaEventCreateWithFlags(&c2, cudaEventDisableTiming));
       f->evIn.push_back(a);
       f->evDone.push_back(b2);
+      f->evExt.push_back(c2);
     }
     // the side streams must not run ahead of work already queued on the caller's stream
     GFS_CUDA(cudaEventRecord(f->evStart, st));
@@ -178,7 +183,9 @@ int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batc
     GFS_CUDA(cudaStreamWaitEvent(f->outStream, f->evStart, 0));
     GFS_CUDA(cudaStreamWaitEvent(f->auxStream, f->evStart, 0));
     // chunks alternate between the caller's stream and a second compute stream: the latency-bound
-    // quadtree kernel of one chunk overlaps the throughput-bound kernels of the next
+    // quadtree kernel of one chunk overlaps the throughput-bound kernels of the next.  A chunk's frame
+    // pairs (and the pair that straddles the previous chunk) are matched and copied out right behind
+    // its extraction, so the tail after the last chunk is one chunk's matcher, not the batch's.
     for (int c = 0; c < nChunks; c++) {
       const size_t b0 = c == 0 ? 0 : (size_t)firstChunk + (size_t)(c - 1) * f->chunk;
       const size_t nb = c == 0 ? (size_t)firstChunk : std::min<size_t>(f->chunk, B - b0);
@@ -196,21 +203,33 @@ int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batc
       rc = orb_extract_slots(f->orb, cs, (int)b0, d_in + b0 * dstride, (int)nb, w, h_img, (int)dpitch, dstride, d_kp + b0 * s,
                              d_desc + b0 * s * 32, d_n + b0, d_mono + b0);
       if (rc) return rc;
+      GFS_CUDA(cudaEventRecord(f->evExt[c], cs));
+      // the pairs both of whose frames are extracted now: [p0, p1); frame b0 - 1 belongs to the previous chunk
+      const size_t p0 = c == 0 ? 0 : b0 - 1, p1 = b0 + nb - 1;
+      if (p1 > p0) {
+        if (c > 0) GFS_CUDA(cudaStreamWaitEvent(cs, f->evExt[c - 1], 0));
+        rc = gfs_match_bf_hamming_batch_device(cs, d_desc + p0 * s * 32, d_n + p0, d_desc + (p0 + 1) * s * 32, d_n + p0 + 1,
+                                               (int)(p1 - p0), s, (int*)f->d_idx.p + p0 * s, (int*)f->d_dist.p + p0 * s);
+        if (rc) return rc;
+        rc = gfs_gms_filter_batch_device(cs, d_kp + p0 * s, d_n + p0, d_kp + (p0 + 1) * s, d_n + p0 + 1,
+                                         (int*)f->d_idx.p + p0 * s, (int)(p1 - p0), s, w, h_img, w, h_img,
+                                         (uint8_t*)f->d_inl.p + p0 * s, (int*)f->d_cnt.p + p0);
+        if (rc) return rc;
+      }
       GFS_CUDA(cudaEventRecord(f->evDone[c], cs));
       GFS_CUDA(cudaStreamWaitEvent(f->outStream, f->evDone[c], 0));
       GFS_CUDA(cudaMemcpyAsync(out_kp + b0 * s, d_kp + b0 * s, nb * s * sizeof(GfsKeyPoint), cudaMemcpyDeviceToHost, f->outStream));
       GFS_CUDA(cudaMemcpyAsync(out_desc + b0 * s * 32, d_desc + b0 * s * 32, nb * s * 32, cudaMemcpyDeviceToHost, f->outStream));
+      if (p1 > p0) {
+        const size_t np = p1 - p0;
+        GFS_CUDA(cudaMemcpyAsync(out_train_idx + p0 * s, (int*)f->d_idx.p + p0 * s, np * s * sizeof(int), cudaMemcpyDeviceToHost, f->outStream));
+        GFS_CUDA(cudaMemcpyAsync(out_dist + p0 * s, (int*)f->d_dist.p + p0 * s, np * s * sizeof(int), cudaMemcpyDeviceToHost, f->outStream));
+        GFS_CUDA(cudaMemcpyAsync(out_inlier + p0 * s, (uint8_t*)f->d_inl.p + p0 * s, np * s, cudaMemcpyDeviceToHost, f->outStream));
+      }
     }
-    for (int c = 1; c < nChunks; c += 2) GFS_CUDA(cudaStreamWaitEvent(st, f->evDone[c], 0));  // the matcher runs on `st`
-    if (f->profiling) { cudaEventRecord(f->ev[0], st); cudaEventRecord(f->ev[1], st); }
-    rc = gfs_match_bf_hamming_batch_device(stream, d_desc, d_n, d_desc + (size_t)s * 32, d_n + 1, batch - 1, s,
-                                           (int*)f->d_idx.p, (int*)f->d_dist.p);
-    if (rc) return rc;
-    if (f->profiling) cudaEventRecord(f->ev[2], st);
-    rc = gfs_gms_filter_batch_device(stream, d_kp, d_n, d_kp + s, d_n + 1, (int*)f->d_idx.p, batch - 1, s, w, h_img, w, h_img,
-                                     (uint8_t*)f->d_inl.p, (int*)f->d_cnt.p);
-    if (rc) return rc;
-    if (f->profiling) cudaEventRecord(f->ev[3], st);
+    for (int c = 1; c < nChunks; c += 2) GFS_CUDA(cudaStreamWaitEvent(st, f->evDone[c], 0));
+    if (f->profiling) for (int i = 0; i < 4; i++) cudaEventRecord(f->ev[i], st);  // stages interleave: no per-stage split here
+    matchedInChunks = true;
   } else {
     const uint8_t* src = imgs;
     size_t spitch = pitch;
@@ -238,9 +257,11 @@ int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batc
   GFS_CUDA(cudaMemcpyAsync(out_n, d_n, B * sizeof(int), cudaMemcpyDeviceToHost, st));
   GFS_CUDA(cudaMemcpyAsync(out_mono, d_mono, B * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (batch > 1) {
-    GFS_CUDA(cudaMemcpyAsync(out_train_idx, f->d_idx.p, (B - 1) * s * sizeof(int), cudaMemcpyDeviceToHost, st));
-    GFS_CUDA(cudaMemcpyAsync(out_dist, f->d_dist.p, (B - 1) * s * sizeof(int), cudaMemcpyDeviceToHost, st));
-    GFS_CUDA(cudaMemcpyAsync(out_inlier, f->d_inl.p, (B - 1) * s, cudaMemcpyDeviceToHost, st));
+    if (!matchedInChunks) {
+      GFS_CUDA(cudaMemcpyAsync(out_train_idx, f->d_idx.p, (B - 1) * s * sizeof(int), cudaMemcpyDeviceToHost, st));
+      GFS_CUDA(cudaMemcpyAsync(out_dist, f->d_dist.p, (B - 1) * s * sizeof(int), cudaMemcpyDeviceToHost, st));
+      GFS_CUDA(cudaMemcpyAsync(out_inlier, f->d_inl.p, (B - 1) * s, cudaMemcpyDeviceToHost, st));
+    }
     GFS_CUDA(cudaMemcpyAsync(out_inlier_count, f->d_cnt.p, (B - 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
   }
   if (f->outStream) GFS_CUDA(cudaStreamSynchronize(f->outStream));

@@ -453,7 +453,26 @@ __device__ __forceinline__ unsigned fast_best16_packed(const unsigned (&q)[16]) 
   return best;
 }
 
-__global__ void __launch_bounds__(FAST_THREADS) k_fast_cells2(OrbDev P, const uint8_t* __restrict__ img0,
+// One precomputed record per cell (all levels of a frame): level and ROI of ComputeKeyPointsOctTree's
+// cell loop (:794-808), so the CTA does not search the level table or divide.
+struct FastCell {
+  int l, iniX, iniY, rwrh;  // rw | rh << 16; 0: nothing to test in this cell
+};
+
+__device__ __forceinline__ void fast_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(FAST_THREADS) k_fast_cells2(OrbDev P, const FastCell* __restrict__ cellTab,
+                                                               const uint8_t* __restrict__ img0,
                                                                long long img_stride, int pitch0,
                                                                const uint8_t* __restrict__ pyr,
                                                                uint32_t* __restrict__ cellKeys,
@@ -461,21 +480,14 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells2(OrbDev P, const ui
   extern __shared__ __align__(16) uint8_t sm[];
   __shared__ int s_nCand, s_nCorner, s_nKept;
   __shared__ unsigned s_vm[FAST_THREADS];
+  __shared__ __align__(8) unsigned long long s_bar;
   const int tid = threadIdx.x;
   const int cell = blockIdx.x, frame = blockIdx.y;
-  int l = 0;
-  while (l + 1 < P.nlevels && cell >= P.lv[l + 1].cellBase) l++;
-  const LevelDev& L = P.lv[l];
-  const int c = cell - L.cellBase;
-  const int ci = c / L.nCols, cj = c - ci * L.nCols;
-  const int iniY = MIN_BORDER + ci * L.hCell, iniX = MIN_BORDER + cj * L.wCell;
-  int maxY = iniY + L.hCell + 6, maxX = iniX + L.wCell + 6;
-  const bool skip = (iniY >= L.maxBorderY - 3) || (iniX >= L.maxBorderX - 6);
-  maxY = min(maxY, L.maxBorderY);
-  maxX = min(maxX, L.maxBorderX);
-  const int rw = maxX - iniX, rh = maxY - iniY;
+  const int4 ct = __ldg(reinterpret_cast<const int4*>(cellTab) + cell);
+  const int l = ct.x, iniX = ct.y, iniY = ct.z;
+  const int rw = ct.w & 0xffff, rh = ct.w >> 16;
   int* outCount = cellCount + (long long)frame * P.totalCells + cell;
-  if (skip || rw < 7 || rh < 7) {
+  if (ct.w == 0) {
     if (tid == 0) *outCount = 0;
     return;
   }
@@ -485,8 +497,8 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells2(OrbDev P, const ui
     src = img0 + (long long)frame * img_stride;
     pitch = pitch0;
   } else {
-    src = pyr + (long long)frame * P.pyrStride + L.off;
-    pitch = L.pitch;
+    src = pyr + (long long)frame * P.pyrStride + P.lv[l].off;
+    pitch = P.lv[l].pitch;
   }
   const int RP = P.roiPitch, SP = P.scPitch;
   uint8_t* sc = sm + P.offSc;                       // [(dh+2)][SP], zero border
@@ -494,37 +506,56 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells2(OrbDev P, const ui
   uint16_t* cand = (uint16_t*)(sm + P.offCand);
   uint32_t* keptList = (uint32_t*)(sm + P.offKept);
   const int dw = rw - 6, dh = rh - 6;
-  // the ROI is staged so that its words are the source's words: pixel (y, x) at sm[y * RP + shift + x]
-  const int shift = (int)(((size_t)src + (size_t)iniX) & 3);
-  const uint8_t* roi = sm + shift;
   const int rp32 = RP >> 2;
-  if ((pitch & 3) == 0) {
+  // The ROI is staged so that its 16-byte (4-byte) groups are the source's: pixel (y, x) at
+  // sm[y * RP + shift + x].  Rows whose 16-byte groups are addressable go through the bulk-copy
+  // engine (one cp.async.bulk per row, completion on an mbarrier) while the CTA clears the score
+  // map; otherwise word / byte loads.
+  const bool bulk = ((pitch & 15) == 0) && ((((size_t)src) & 15) == 0);
+  int shift;
+  if (bulk) {
+    shift = iniX & 15;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    const uint32_t rowBytes = (uint32_t)((shift + rw + 15) & ~15);  // <= RP, stays inside the source row (pitch % 16 == 0)
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(rowBytes * (uint32_t)rh) : "memory");
+    }
+    __syncthreads();
+    const uint8_t* g0 = src + (long long)iniY * pitch + (iniX - shift);
+    const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(sm);
+    for (int y = tid; y < rh; y += FAST_THREADS) {
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d0 + (uint32_t)(y * RP)),
+          "l"(g0 + (long long)y * pitch), "r"(rowBytes), "r"(bar)
+          : "memory");
+    }
+  } else if ((pitch & 3) == 0) {
+    shift = (int)(((size_t)src + (size_t)iniX) & 3);
     const int nW = (shift + rw + 3) >> 2;
     const uint32_t* s32 = (const uint32_t*)(src + (long long)iniY * pitch + (iniX - shift));
     const int p32 = pitch >> 2;
     uint32_t* d32 = (uint32_t*)sm;
-    if (nW <= 16) {
-      const int x = tid & 15;
-      if (x < nW)
-        for (int y = tid >> 4; y < rh; y += FAST_THREADS / 16) d32[y * rp32 + x] = __ldg(s32 + (long long)y * p32 + x);
-    } else {
-      for (int idx = tid; idx < nW * rh; idx += FAST_THREADS) {
-        const int y = idx / nW, x = idx - y * nW;
-        d32[y * rp32 + x] = __ldg(s32 + (long long)y * p32 + x);
-      }
+    for (int idx = tid; idx < nW * rh; idx += FAST_THREADS) {
+      const int y = idx / nW, x = idx - y * nW;
+      d32[y * rp32 + x] = __ldg(s32 + (long long)y * p32 + x);
     }
   } else {
+    shift = (int)(((size_t)src + (size_t)iniX) & 3);
     for (int idx = tid; idx < rw * rh; idx += FAST_THREADS) {
       const int y = idx / rw, x = idx - y * rw;
       sm[shift + y * RP + x] = __ldg(src + (long long)(iniY + y) * pitch + iniX + x);
     }
   }
+  const uint8_t* roi = sm + shift;
   {
-    uint32_t* z = (uint32_t*)sc;
-    for (int idx = tid; idx < ((dh + 2) * SP) >> 2; idx += FAST_THREADS) z[idx] = 0u;
+    uint4* z = (uint4*)sc;  // offSc and the region's size are multiples of 16
+    for (int idx = tid; idx < ((dh + 2) * SP + 15) >> 4; idx += FAST_THREADS) z[idx] = make_uint4(0u, 0u, 0u, 0u);
   }
   const int wLo = (shift + 3) >> 2, wHi = (shift + rw - 4) >> 2, nWt = wHi - wLo + 1;
-  const unsigned inv = 65536u / (unsigned)nWt + 1u;  // i / nWt == (i * inv) >> 16 for i < 4096
+  // i / nWt == (i * inv) >> 16 for i < 4096 (nWt <= 32: the float quotient cannot round across an integer)
+  const unsigned inv = (unsigned)(65536.0f / (float)nWt) + 1u;
   if (tid < nWt) {
     // which bytes of word wLo + tid are tested pixels (column in [0, dw)), as bits 14 / 15 / 30 / 31
     const int xb = 4 * (wLo + tid) - shift - 3;
@@ -536,6 +567,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells2(OrbDev P, const ui
     s_vm[tid] = vm;
   }
   if (tid == 0) { s_nCorner = 0; s_nCand = 0; s_nKept = 0; }
+  if (bulk) fast_mbar_wait((uint32_t)__cvta_generic_to_shared(&s_bar), 0u);
   __syncthreads();
 
   const int thMin = P.minTh, thIni = P.iniTh;
@@ -639,7 +671,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells2(OrbDev P, const ui
     const unsigned key = e & 0xffffu;
     int rank = 0;
     for (int j = 0; j < nKept; j++) rank += (keptList[j] & 0xffffu) < key;
-    const unsigned kx = (key & 255u) + 3u + (unsigned)(cj * L.wCell), ky = (key >> 8) + 3u + (unsigned)(ci * L.hCell);
+    const unsigned kx = (key & 255u) + (unsigned)(3 + iniX - MIN_BORDER), ky = (key >> 8) + (unsigned)(3 + iniY - MIN_BORDER);
     out[rank] = kx | (ky << 12) | ((e >> 16) << 24);
   }
   if (tid == 0) *outCount = nKept;
@@ -1239,7 +1271,7 @@ struct GfsOrb {
   size_t fastSmem = 0, octSmem = 0, pyrSmem = 0, pyr3Smem = 0;
   bool fastV1 = getenv("GFS_FAST_V1") != nullptr;  // first-generation FAST kernel (A/B runs); same results
   int pyr3Rows = 0, pyr3PitchF = 0;  // k_pyr_level3 shared-memory geometry; pyr3Rows == 0: generic kernel
-  DevBuf d_tabs3;
+  DevBuf d_tabs3, d_cellTab;
   // optional per-stage CUDA-event timing (bench roofline): pyramid, fast, octree, blur, orient/desc, pack
   bool profiling = false;
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -1396,7 +1428,11 @@ static int orb_set_geometry(GfsOrb* h, int w, int ht) {
   D.keysPerFrame = keyOff;
   D.selPerFrame = selOff;
   D.nodeCap = nodeCap;
-  D.roiPitch = (int)align_up(maxWC + 6 + 3, 4) + 4;  // + word-alignment shift of the first column
+  // ROI row pitch: room for the 16-byte alignment shift of the first column and the rounded-up row
+  // of the bulk copy; a pitch of 4 (mod 8) words keeps eight consecutive rows on distinct banks
+  D.roiPitch = (int)align_up(maxWC + 6 + 15, 16);
+  if (((D.roiPitch >> 2) & 7) != 4) D.roiPitch += 16;
+  if (((D.roiPitch >> 2) & 7) != 4) D.roiPitch += 16;
   D.roiRows = maxHC + 6;
   D.scPitch = (int)align_up(maxWC + 2, 4);
   D.offSc = (int)align_up((size_t)D.roiRows * D.roiPitch + 4, 16);
@@ -1438,6 +1474,25 @@ static int orb_set_geometry(GfsOrb* h, int w, int ht) {
   if ((rc = h->d_sel.reserve(B * (size_t)D.selPerFrame * 4))) return rc;
   if ((rc = h->d_selCount.reserve(B * MAX_LEVELS * 4))) return rc;
   if ((rc = h->d_status.reserve(16))) return rc;
+  {
+    std::vector<FastCell> cells((size_t)D.totalCells);
+    for (int l = 0; l < h->nlevels; l++) {
+      const LevelDev& L = D.lv[l];
+      for (int ci = 0; ci < L.nRows; ci++)
+        for (int cj = 0; cj < L.nCols; cj++) {
+          FastCell& c = cells[(size_t)L.cellBase + (size_t)ci * L.nCols + cj];
+          c.l = l;
+          c.iniY = MIN_BORDER + ci * L.hCell;
+          c.iniX = MIN_BORDER + cj * L.wCell;
+          const int maxY = std::min(c.iniY + L.hCell + 6, L.maxBorderY), maxX = std::min(c.iniX + L.wCell + 6, L.maxBorderX);
+          const bool skip = (c.iniY >= L.maxBorderY - 3) || (c.iniX >= L.maxBorderX - 6);
+          const int rw = maxX - c.iniX, rh = maxY - c.iniY;
+          c.rwrh = (skip || rw < 7 || rh < 7) ? 0 : (rw | (rh << 16));
+        }
+    }
+    if ((rc = h->d_cellTab.reserve(cells.size() * sizeof(FastCell)))) return rc;
+    GFS_CUDA(cudaMemcpy(h->d_cellTab.p, cells.data(), cells.size() * sizeof(FastCell), cudaMemcpyHostToDevice));
+  }
   if ((rc = h->d_tabs.reserve(std::max<size_t>(tabs.size(), 1) * sizeof(AreaEntry)))) return rc;
   if (!tabs.empty()) GFS_CUDA(cudaMemcpy(h->d_tabs.p, tabs.data(), tabs.size() * sizeof(AreaEntry), cudaMemcpyHostToDevice));
   if (pyr3Rows) {
@@ -1528,7 +1583,7 @@ int gfs_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th_fa
 int gfs_orb_destroy(GfsOrb* h) {
   if (!h) return GFS_OK;
   DevBuf* d[] = {&h->d_pyr, &h->d_blur, &h->d_cellKeys, &h->d_cellCount, &h->d_keysA, &h->d_keysB, &h->d_sel,
-                 &h->d_selCount, &h->d_tabs, &h->d_tabs3, &h->d_status, &h->d_in, &h->d_okp, &h->d_odesc, &h->d_on, &h->d_omono,
+                 &h->d_selCount, &h->d_tabs, &h->d_tabs3, &h->d_cellTab, &h->d_status, &h->d_in, &h->d_okp, &h->d_odesc, &h->d_on, &h->d_omono,
                  &h->d_tkp, &h->d_tdesc, &h->d_pattern};
   for (DevBuf* b : d) b->release();
   h->h_in.release(); h->h_okp.release(); h->h_odesc.release(); h->h_on.release();
@@ -1615,7 +1670,7 @@ static int orb_run_chunk(GfsOrb* h, cudaStream_t st, int slot0, const uint8_t* d
         D, d_imgs, (long long)img_stride, pitch, pyr, cellKeys, cellCount);
   else
     k_fast_cells2<<<dim3(D.totalCells, batch), FAST_THREADS, h->fastSmem, st>>>(
-        D, d_imgs, (long long)img_stride, pitch, pyr, cellKeys, cellCount);
+        D, (const FastCell*)h->d_cellTab.p, d_imgs, (long long)img_stride, pitch, pyr, cellKeys, cellCount);
   mark(2);
   k_octree<<<div_up(batch * h->nlevels, OCT_WARPS), OCT_WARPS * 32, h->octSmem, st>>>(
       D, batch, cellKeys, cellCount, keysA, keysB, selKeys, selCount, (int*)h->d_status.p);

@@ -46,7 +46,7 @@ def test_batch_matches_oracle(ex, frames4):
         _assert_same(kps[i, :n[i]], desc[i, :n[i]], ko, do)
 
 
-@pytest.mark.parametrize("kind", ["noise", "flat", "gradient", "checker", "wide"])
+@pytest.mark.parametrize("kind", ["noise", "flat", "gradient", "checker", "wide", "pitch4", "pitch2"])
 def test_edge_images(kind):
     from geoflowslam_b200 import ORBextractor
     rng = np.random.default_rng(7)
@@ -59,6 +59,10 @@ def test_edge_images(kind):
     elif kind == "checker":
         yy, xx = np.mgrid[0:480, 0:640]
         img = (((yy // 8 + xx // 8) % 2) * 200 + 20).astype(np.uint8)  # score plateaus / ties
+    elif kind == "pitch4":
+        img = rng.integers(0, 256, (301, 644), dtype=np.uint8)        # level-0 rows 4- but not 16-byte aligned (word staging)
+    elif kind == "pitch2":
+        img = rng.integers(0, 256, (300, 642), dtype=np.uint8)        # level-0 rows unaligned (byte staging)
     else:
         img = rng.integers(0, 256, (280, 752), dtype=np.uint8)        # several initial quadtree nodes
     h, w = img.shape
