@@ -298,7 +298,10 @@ def run_ours(args):
     achieved = alg / (prof[top] / 1e3) / 1e9
     # DRAM traffic per frame of the dominant kernels from the committed `ncu --set full` captures
     # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r01_summary.md), scaled to this launch
-    ncu_traffic_per_frame = {"fast_cells": (113.197056e6 + 5.351680e6) / 128}
+    ncu_traffic_per_frame = {"fast_cells": (113.192192e6 + 5.287680e6) / 128,     # profiles/r01_s3_k_fast_cells2_ncu_details.txt
+                             "orient_desc": (122.655488e6 + 9.598208e6) / 128}   # profiles/r01_s3_k_orient_desc_ncu_details.txt
+    ncu_traffic_src = {"fast_cells": "ncu capture profiles/r01_s3_k_fast_cells2_ncu_details.txt",
+                       "orient_desc": "ncu capture profiles/r01_s3_k_orient_desc_ncu_details.txt"}
     traffic = ncu_traffic_per_frame[top] * B if top in ncu_traffic_per_frame else None
     # every stage against the same roof (algorithmic bytes / CUDA-event time), for the stage table in DESIGN.md
     stage_roof = {}
@@ -308,7 +311,7 @@ def run_ours(args):
         a = algorithmic_bytes(st_name, B if st_name not in ("bf_hamming", "gms") else B - 1, mean_kp, cand_per_frame)
         stage_roof[st_name] = {"ms": st_ms, "algorithmic_bytes": a, "achieved": a / (st_ms / 1e3) / 1e9, "frac": a / (st_ms / 1e3) / 1e9 / peak}
     roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "stages": stage_roof,
-            "frac": achieved / peak, "traffic": traffic, "traffic_source": "ncu capture profiles/r01_final_k_fast_cells_ncu_details.txt" if traffic else None,
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": ncu_traffic_src.get(top) if traffic else None,
             "algorithmic_bytes": alg, "ms_per_launch_group": prof[top], "peak_source": peak_src,
             "stage_ms": prof}
 

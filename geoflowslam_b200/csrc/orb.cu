@@ -141,18 +141,32 @@ __global__ void __launch_bounds__(256) k_pyr_level3(OrbDev P, int l, const uint8
     const int wd = tid & 31;
     if (wd < words) {
       const bool whole = word_ok && (xs + 4 * wd + 4 <= src_pitch);
-      for (int r = tid >> 5; r < nr; r += 8) {
-        const uint8_t* S = src + (long long)r * src_pitch + 4 * wd;
-        float4 f;
-        if (whole) {
-          const unsigned v = __ldg(reinterpret_cast<const unsigned*>(S));
-          f = make_float4((float)(v & 0xffu), (float)((v >> 8) & 0xffu), (float)((v >> 16) & 0xffu), (float)(v >> 24));
-        } else {
-          const int lim = src_pitch - 1 - (xs + 4 * wd);  // last readable byte of the row
-          f = make_float4((float)__ldg(S + min(0, lim)), (float)__ldg(S + min(1, lim)), (float)__ldg(S + min(2, lim)),
+      const uint8_t* S0 = src + 4 * wd;
+      float* D0 = s_src + 4 * wd;
+      if (whole) {
+        // four rows per trip: all four loads are issued before the first conversion waits on one
+        for (int r = tid >> 5; r < nr; r += 32) {
+          unsigned v[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int rr = min(r + 8 * k, nr - 1);  // clamped rows reload the last row (stored again below, same value)
+            v[k] = __ldg(reinterpret_cast<const unsigned*>(S0 + (long long)rr * src_pitch));
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int rr = min(r + 8 * k, nr - 1);
+            *reinterpret_cast<float4*>(D0 + rr * srcPitchF) =
+                make_float4((float)(v[k] & 0xffu), (float)((v[k] >> 8) & 0xffu), (float)((v[k] >> 16) & 0xffu), (float)(v[k] >> 24));
+          }
+        }
+      } else {
+        const int lim = src_pitch - 1 - (xs + 4 * wd);  // last readable byte of the row
+        for (int r = tid >> 5; r < nr; r += 8) {
+          const uint8_t* S = S0 + (long long)r * src_pitch;
+          *reinterpret_cast<float4*>(D0 + r * srcPitchF) =
+              make_float4((float)__ldg(S + min(0, lim)), (float)__ldg(S + min(1, lim)), (float)__ldg(S + min(2, lim)),
                           (float)__ldg(S + min(3, lim)));
         }
-        *reinterpret_cast<float4*>(s_src + r * srcPitchF + 4 * wd) = f;
       }
     }
   }
@@ -162,6 +176,7 @@ __global__ void __launch_bounds__(256) k_pyr_level3(OrbDev P, int l, const uint8
     if (c < tw) {
       const Area3 e = tx[c];
       const float* p = s_src + (e.s0 - xs);
+#pragma unroll 2
       for (int r = tid >> 6; r < nr; r += 256 / PYR_TW) {
         const float* q = p + r * srcPitchF;
         float buf = __fmul_rn(q[0], e.a0);
