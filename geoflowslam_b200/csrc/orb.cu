@@ -1125,11 +1125,13 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(OrbDev P, const u
     }
   }
   if (!fast) {
+    // border keypoints: the lane's (up to) two reflected columns once, then row by row
     shift = 0;
-    for (int idx = lane; idx < PATCH_W * PATCH_W; idx += 32) {
-      const int r = idx / PATCH_W, c = idx - r * PATCH_W;
-      const int gy = reflect101(y0 + r, L.h), gx = reflect101(x0 + c, L.w);
-      raw[r * RAW_PITCH + c] = __ldg(src + (long long)gy * pitch + gx);
+    const int gx0 = reflect101(x0 + lane, L.w), gx1 = reflect101(x0 + min(lane + 32, PATCH_W - 1), L.w);
+    for (int r = 0; r < PATCH_W; r++) {
+      const uint8_t* row = src + (long long)reflect101(y0 + r, L.h) * pitch;
+      raw[r * RAW_PITCH + lane] = __ldg(row + gx0);
+      if (lane < PATCH_W - 32) raw[r * RAW_PITCH + lane + 32] = __ldg(row + gx1);
     }
   }
   __syncwarp();
