@@ -763,37 +763,78 @@ __device__ void oct_divide(OctState* S, OctNode* nodes, int* vszF, int* vszS, ui
   const uint32_t* src = (nd.buf ? keys1 : keys0) + nd.begin;
   uint32_t* dst = (nd.buf ? keys0 : keys1) + nd.begin;
   int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-  for (int i = lane; i < nd.count; i += 32) {
-    const uint32_t k = src[i];
-    const int x = k & 0xFFF, y = (k >> 12) & 0xFFF;
-    const int q = (x < midX) ? ((y < midY) ? 0 : 2) : ((y < midY) ? 1 : 3);
-    c0 += (q == 0); c1 += (q == 1); c2 += (q == 2); c3 += (q == 3);
-  }
-  c0 = __reduce_add_sync(0xffffffffu, c0);
-  c1 = __reduce_add_sync(0xffffffffu, c1);
-  c2 = __reduce_add_sync(0xffffffffu, c2);
-  c3 = __reduce_add_sync(0xffffffffu, c3);
-  int b0 = 0, b1 = c0, b2 = c0 + c1, b3 = c0 + c1 + c2;
   const unsigned lt = (1u << lane) - 1u;
-  for (int s = 0; s < nd.count; s += 32) {
-    const int i = s + lane;
-    const bool valid = i < nd.count;
-    uint32_t k = 0;
-    int q = -1;
-    if (valid) {
-      k = src[i];
-      const int x = k & 0xFFF, y = (k >> 12) & 0xFFF;
-      q = (x < midX) ? ((y < midY) ? 0 : 2) : ((y < midY) ? 1 : 3);
+  if (nd.count <= 128) {
+    // the node's keys fit four registers per lane: one trip to memory instead of a count and a scatter pass
+    uint32_t kk[4];
+    int qq[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = lane + 32 * u;
+      qq[u] = -1;
+      kk[u] = 0;
+      if (i < nd.count) kk[u] = src[i];
     }
-    const unsigned m0 = __ballot_sync(0xffffffffu, q == 0);
-    const unsigned m1 = __ballot_sync(0xffffffffu, q == 1);
-    const unsigned m2 = __ballot_sync(0xffffffffu, q == 2);
-    const unsigned m3 = __ballot_sync(0xffffffffu, q == 3);
-    if (q == 0) dst[b0 + __popc(m0 & lt)] = k;
-    else if (q == 1) dst[b1 + __popc(m1 & lt)] = k;
-    else if (q == 2) dst[b2 + __popc(m2 & lt)] = k;
-    else if (q == 3) dst[b3 + __popc(m3 & lt)] = k;
-    b0 += __popc(m0); b1 += __popc(m1); b2 += __popc(m2); b3 += __popc(m3);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (lane + 32 * u < nd.count) {
+        const int x = kk[u] & 0xFFF, y = (kk[u] >> 12) & 0xFFF;
+        qq[u] = (x < midX) ? ((y < midY) ? 0 : 2) : ((y < midY) ? 1 : 3);
+      }
+      c0 += (qq[u] == 0); c1 += (qq[u] == 1); c2 += (qq[u] == 2); c3 += (qq[u] == 3);
+    }
+    c0 = __reduce_add_sync(0xffffffffu, c0);
+    c1 = __reduce_add_sync(0xffffffffu, c1);
+    c2 = __reduce_add_sync(0xffffffffu, c2);
+    c3 = __reduce_add_sync(0xffffffffu, c3);
+    int b0 = 0, b1 = c0, b2 = c0 + c1, b3 = c0 + c1 + c2;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (32 * u < nd.count) {  // warp-uniform
+        const int q = qq[u];
+        const unsigned m0 = __ballot_sync(0xffffffffu, q == 0);
+        const unsigned m1 = __ballot_sync(0xffffffffu, q == 1);
+        const unsigned m2 = __ballot_sync(0xffffffffu, q == 2);
+        const unsigned m3 = __ballot_sync(0xffffffffu, q == 3);
+        if (q == 0) dst[b0 + __popc(m0 & lt)] = kk[u];
+        else if (q == 1) dst[b1 + __popc(m1 & lt)] = kk[u];
+        else if (q == 2) dst[b2 + __popc(m2 & lt)] = kk[u];
+        else if (q == 3) dst[b3 + __popc(m3 & lt)] = kk[u];
+        b0 += __popc(m0); b1 += __popc(m1); b2 += __popc(m2); b3 += __popc(m3);
+      }
+    }
+  } else {
+    for (int i = lane; i < nd.count; i += 32) {
+      const uint32_t k = src[i];
+      const int x = k & 0xFFF, y = (k >> 12) & 0xFFF;
+      const int q = (x < midX) ? ((y < midY) ? 0 : 2) : ((y < midY) ? 1 : 3);
+      c0 += (q == 0); c1 += (q == 1); c2 += (q == 2); c3 += (q == 3);
+    }
+    c0 = __reduce_add_sync(0xffffffffu, c0);
+    c1 = __reduce_add_sync(0xffffffffu, c1);
+    c2 = __reduce_add_sync(0xffffffffu, c2);
+    c3 = __reduce_add_sync(0xffffffffu, c3);
+    int b0 = 0, b1 = c0, b2 = c0 + c1, b3 = c0 + c1 + c2;
+    for (int s = 0; s < nd.count; s += 32) {
+      const int i = s + lane;
+      const bool valid = i < nd.count;
+      uint32_t k = 0;
+      int q = -1;
+      if (valid) {
+        k = src[i];
+        const int x = k & 0xFFF, y = (k >> 12) & 0xFFF;
+        q = (x < midX) ? ((y < midY) ? 0 : 2) : ((y < midY) ? 1 : 3);
+      }
+      const unsigned m0 = __ballot_sync(0xffffffffu, q == 0);
+      const unsigned m1 = __ballot_sync(0xffffffffu, q == 1);
+      const unsigned m2 = __ballot_sync(0xffffffffu, q == 2);
+      const unsigned m3 = __ballot_sync(0xffffffffu, q == 3);
+      if (q == 0) dst[b0 + __popc(m0 & lt)] = k;
+      else if (q == 1) dst[b1 + __popc(m1 & lt)] = k;
+      else if (q == 2) dst[b2 + __popc(m2 & lt)] = k;
+      else if (q == 3) dst[b3 + __popc(m3 & lt)] = k;
+      b0 += __popc(m0); b1 += __popc(m1); b2 += __popc(m2); b3 += __popc(m3);
+    }
   }
   __syncwarp();
   if (lane == 0) {
@@ -864,14 +905,11 @@ __global__ void __launch_bounds__(OCT_WARPS * 32) k_octree(OrbDev P, int batch, 
       const int t = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += t;
     }
+    // every lane copies its own cell: 32 independent copy chains instead of one cell at a time
     const int excl = ncand + inc - n;
-    const int m = min(32, nCells - cb);
-    for (int j = 0; j < m; j++) {
-      const int nj = __shfl_sync(0xffffffffu, n, j);
-      const int oj = __shfl_sync(0xffffffffu, excl, j);
-      const uint32_t* s = ck + (long long)(cb + j) * P.cellCap;
-      for (int k = lane; k < nj; k += 32) keys1[oj + k] = s[k];
-    }
+    const uint32_t* s = ck + (long long)c * P.cellCap;
+#pragma unroll 4
+    for (int k = 0; k < n; k++) keys1[excl + k] = s[k];
     ncand += __shfl_sync(0xffffffffu, inc, 31);
   }
   __syncwarp();
@@ -957,24 +995,54 @@ __global__ void __launch_bounds__(OCT_WARPS * 32) k_octree(OrbDev P, int batch, 
     }
   }
 
-  // ---- best response per node, in list order (:749-767); first maximum wins
+  // ---- best response per node, in list order (:749-767); first maximum wins.  Lane 0 flattens the list,
+  // then every lane takes whole nodes (a node holds a handful of keys by now); only nodes too large for
+  // one lane are reduced by the whole warp.
   uint32_t* out = sel + (long long)frame * P.selPerFrame + L.selOff;
-  int nout = 0;
-  for (int cur = S->head; cur != NIL; cur = nodes[cur].next) {
-    const OctNode nd = nodes[cur];
-    const uint32_t* src = (nd.buf ? keys1 : keys0) + nd.begin;
-    // order by (score desc, index asc): pack score in the high bits, inverted index below
-    unsigned long long bestv = 0ull;
-    for (int i = lane; i < nd.count; i += 32) {
-      const uint32_t k = src[i];
-      const unsigned long long v = ((unsigned long long)(k >> 24) << 32) | (unsigned)(0x7fffffff - i);
-      bestv = max(bestv, v);
+  __syncwarp();
+  if (lane == 0) {
+    int n = 0;
+    for (int cur = S->head; cur != NIL; cur = nodes[cur].next) vszS[n++] = cur;
+    S->nvsz = n;
+  }
+  __syncwarp();
+  const int nout = S->nvsz;
+  for (int jb = 0; jb < nout; jb += 32) {
+    const int j = jb + lane;
+    bool big = false;
+    if (j < nout) {
+      const OctNode nd = nodes[vszS[j]];
+      if (nd.count <= 48) {
+        const uint32_t* src = (nd.buf ? keys1 : keys0) + nd.begin;
+        uint32_t bk = src[0];
+#pragma unroll 4
+        for (int i = 1; i < nd.count; i++) {
+          const uint32_t k = src[i];
+          if ((k >> 24) > (bk >> 24)) bk = k;
+        }
+        if (j < L.selCap) out[j] = bk;
+      } else {
+        big = true;
+      }
     }
+    unsigned bm = __ballot_sync(0xffffffffu, big);
+    while (bm) {
+      const int jj = jb + __ffs(bm) - 1;
+      bm &= bm - 1;
+      const OctNode nd = nodes[vszS[jj]];
+      const uint32_t* src = (nd.buf ? keys1 : keys0) + nd.begin;
+      // order by (score desc, index asc): pack score in the high bits, inverted index below
+      unsigned long long bestv = 0ull;
+      for (int i = lane; i < nd.count; i += 32) {
+        const uint32_t k = src[i];
+        const unsigned long long v = ((unsigned long long)(k >> 24) << 32) | (unsigned)(0x7fffffff - i);
+        bestv = max(bestv, v);
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) bestv = max(bestv, __shfl_xor_sync(0xffffffffu, bestv, o));
-    const int bi = 0x7fffffff - (int)(bestv & 0xffffffffu);
-    if (lane == 0 && nout < L.selCap) out[nout] = src[bi];
-    nout++;
+      for (int o = 16; o > 0; o >>= 1) bestv = max(bestv, __shfl_xor_sync(0xffffffffu, bestv, o));
+      const int bi = 0x7fffffff - (int)(bestv & 0xffffffffu);
+      if (lane == 0 && jj < L.selCap) out[jj] = src[bi];
+    }
   }
   if (lane == 0) {
     selCount[frame * P.nlevels + l] = min(nout, L.selCap);
