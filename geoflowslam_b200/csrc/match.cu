@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(BFM_WARPS * 32) k_bf_hamming_mma(const uint8_t
 
 // ------------------------------------------------------------------------------------------------
 // k_gms: one CTA per frame pair.  The reference's dense 400x400 motion-statistics table (640 KB,
-// cleared four times per call) is replaced by the sorted list of the <= nm occupied (left cell,
-// right cell) keys; every table read becomes a binary-search count, which is exact.
+// cleared four times per call) is replaced by a shared-memory hash table of the <= nm occupied (left cell,
+// right cell) keys; every table read becomes a lookup, which is exact.
 // ------------------------------------------------------------------------------------------------
 static const int GMS_G = 20, GMS_NG = 400, GMS_THREADS = 256;
 
@@ -164,25 +164,34 @@ __device__ __forceinline__ int gms_nb9(int idx, int k) {
   if (x < 0 || x >= GMS_G || y < 0 || y >= GMS_G) return -1;
   return x + y * GMS_G;
 }
-__device__ __forceinline__ int lower_bound_u32(const uint32_t* a, int n, uint32_t key) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (a[mid] < key) lo = mid + 1;
-    else hi = mid;
+// Occupied (left cell, right cell) keys live in an open-addressing hash table in shared memory
+// (key -> number of matches): building it is one atomicCAS + two atomicAdd per match, every read of the
+// reference's motion-statistics table is a one- or two-probe lookup.  (First version: bitonic sort of the
+// keys + binary searches -- 55 barrier-separated stages per grid type, 45 % of the kernel's instructions.)
+static const uint32_t GMS_EMPTY = 0xffffffffu;
+__device__ __forceinline__ unsigned gms_hash(uint32_t key, int tbits) { return (key * 2654435761u) >> (32 - tbits); }
+__device__ __forceinline__ int gms_count(const uint32_t* hkey, const uint32_t* hcnt, int tbits, uint32_t key) {
+  const unsigned tmask = (1u << tbits) - 1u;
+  unsigned h = gms_hash(key, tbits);
+  while (true) {
+    const uint32_t k = hkey[h];
+    if (k == key) return (int)hcnt[h];
+    if (k == GMS_EMPTY) return 0;
+    h = (h + 1) & tmask;
   }
-  return lo;
 }
 
 __global__ void __launch_bounds__(GMS_THREADS) k_gms(const GfsKeyPoint* __restrict__ kp1, const int* __restrict__ n1,
                                                      const GfsKeyPoint* __restrict__ kp2, const int* __restrict__ n2,
                                                      const int* __restrict__ mq, const int* __restrict__ mt,
-                                                     const int* __restrict__ nmArr, int stride, int mstride, int pow2,
+                                                     const int* __restrict__ nmArr, int stride, int mstride, int tbits,
                                                      int w1, int h1, int w2, int h2, uint8_t* __restrict__ out_inlier,
                                                      int* __restrict__ out_count) {
   extern __shared__ uint32_t gsm[];
-  uint32_t* keys = gsm;                          // [pow2]
-  short* ml = (short*)(keys + pow2);             // [mstride] left cell of match i (this grid type)
+  const int tsize = 1 << tbits;
+  uint32_t* hkey = gsm;                          // [tsize] l * 400 + r, GMS_EMPTY when free
+  uint32_t* hcnt = hkey + tsize;                 // [tsize] matches with that key
+  short* ml = (short*)(hcnt + tsize);            // [mstride] left cell of match i (this grid type)
   short* mr = ml + mstride;                      // [mstride] right cell (grid type 1)
   int* nLeft = (int*)(ml + 2 * mstride);        // [400] (2*mstride shorts keep 4-byte alignment)
   int* cellPair = nLeft + GMS_NG;                // [400]
@@ -197,76 +206,66 @@ __global__ void __launch_bounds__(GMS_THREADS) k_gms(const GfsKeyPoint* __restri
   uint8_t* mask = out_inlier + (size_t)pair * mstride;
   for (int i = tid; i < nm; i += GMS_THREADS) mask[i] = 0;
   if (tid == 0) s_cnt = 0;
+  const unsigned tmask = (unsigned)tsize - 1u;
 
   for (int type = 1; type <= 4; type++) {
     __syncthreads();
-    for (int i = tid; i < pow2; i += GMS_THREADS) {
-      uint32_t key = 0xffffffffu;
-      if (i < nm) {
-        const int q = MQ ? MQ[i] : i, t = MT[i];
-        int l = -1, r = -1;
-        if (q >= 0 && q < N1 && t >= 0 && t < N2) {
-          // NormalizePoints :104-115 and GetGridIndexLeft/Right :125-160
-          const float lx = __fmul_rn(__fdiv_rn(K1[q].x, (float)w1), (float)GMS_G);
-          const float ly = __fmul_rn(__fdiv_rn(K1[q].y, (float)h1), (float)GMS_G);
-          const int x = (type == 2 || type == 4) ? (int)floor((double)lx + 0.5) : (int)floorf(lx);
-          const int y = (type == 3 || type == 4) ? (int)floor((double)ly + 0.5) : (int)floorf(ly);
-          l = (x >= GMS_G || y >= GMS_G) ? -1 : x + y * GMS_G;
-          if (type == 1) {
-            const float rx = __fmul_rn(__fdiv_rn(K2[t].x, (float)w2), (float)GMS_G);
-            const float ry = __fmul_rn(__fdiv_rn(K2[t].y, (float)h2), (float)GMS_G);
-            r = (int)floorf(rx) + (int)floorf(ry) * GMS_G;
-            // keep -1 / -2 exact (the reference compares raw indices against mCellPairs, :406)
-            r = (r < -2) ? -3 : min(r, 32000);
-            mr[i] = (short)r;
-          } else {
-            r = mr[i];
-          }
-        } else if (type == 1) {
-          mr[i] = -1;
+    for (int i = tid; i < tsize; i += GMS_THREADS) { hkey[i] = GMS_EMPTY; hcnt[i] = 0u; }
+    for (int c = tid; c < GMS_NG; c += GMS_THREADS) { nLeft[c] = 0; cellPair[c] = 0; }
+    __syncthreads();
+    for (int i = tid; i < nm; i += GMS_THREADS) {
+      const int q = MQ ? MQ[i] : i, t = MT[i];
+      int l = -1, r = -1;
+      if (q >= 0 && q < N1 && t >= 0 && t < N2) {
+        // NormalizePoints :104-115 and GetGridIndexLeft/Right :125-160
+        const float lx = __fmul_rn(__fdiv_rn(K1[q].x, (float)w1), (float)GMS_G);
+        const float ly = __fmul_rn(__fdiv_rn(K1[q].y, (float)h1), (float)GMS_G);
+        const int x = (type == 2 || type == 4) ? (int)floor((double)lx + 0.5) : (int)floorf(lx);
+        const int y = (type == 3 || type == 4) ? (int)floor((double)ly + 0.5) : (int)floorf(ly);
+        l = (x >= GMS_G || y >= GMS_G) ? -1 : x + y * GMS_G;
+        if (type == 1) {
+          const float rx = __fmul_rn(__fdiv_rn(K2[t].x, (float)w2), (float)GMS_G);
+          const float ry = __fmul_rn(__fdiv_rn(K2[t].y, (float)h2), (float)GMS_G);
+          r = (int)floorf(rx) + (int)floorf(ry) * GMS_G;
+          // keep -1 / -2 exact (the reference compares raw indices against mCellPairs, :406)
+          r = (r < -2) ? -3 : min(r, 32000);
+          mr[i] = (short)r;
+        } else {
+          r = mr[i];
         }
-        ml[i] = (short)max(-1, min(l, 32000));
-        if (l >= 0 && r >= 0 && l < GMS_NG && r < GMS_NG) key = (uint32_t)(l * GMS_NG + r);
+      } else if (type == 1) {
+        mr[i] = -1;
       }
-      keys[i] = key;
+      ml[i] = (short)max(-1, min(l, 32000));
+      if (l >= 0 && r >= 0 && l < GMS_NG && r < GMS_NG) {
+        const uint32_t key = (uint32_t)(l * GMS_NG + r);
+        unsigned h = gms_hash(key, tbits);
+        while (true) {  // the table is at most 2/3 full: a free or matching slot always turns up
+          const uint32_t prev = atomicCAS(&hkey[h], GMS_EMPTY, key);
+          if (prev == GMS_EMPTY || prev == key) break;
+          h = (h + 1) & tmask;
+        }
+        atomicAdd(&hcnt[h], 1u);
+        atomicAdd(&nLeft[l], 1);
+      }
     }
     __syncthreads();
-    // bitonic sort of keys[0..pow2)
-    for (int k = 2; k <= pow2; k <<= 1)
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < pow2; i += GMS_THREADS) {
-          const int ixj = i ^ j;
-          if (ixj > i) {
-            const uint32_t a = keys[i], b = keys[ixj];
-            const bool up = (i & k) == 0;
-            if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
-          }
-        }
-        __syncthreads();
+    // per left cell: first-maximum right cell (VerifyCellPairs :338-356) = max of (count, -right cell)
+    for (int sidx = tid; sidx < tsize; sidx += GMS_THREADS) {
+      const uint32_t k = hkey[sidx];
+      if (k != GMS_EMPTY) {
+        const int l = (int)(k / GMS_NG), r = (int)(k - (uint32_t)l * GMS_NG);
+        atomicMax((unsigned*)&cellPair[l], (hcnt[sidx] << 16) | (uint32_t)(0xFFFF - r));
       }
-    // per left cell: population, first-maximum right cell (VerifyCellPairs :338-356)
-    for (int c = tid; c < GMS_NG; c += GMS_THREADS) {
-      const int lo = lower_bound_u32(keys, pow2, (uint32_t)(c * GMS_NG));
-      const int hi = lower_bound_u32(keys, pow2, (uint32_t)((c + 1) * GMS_NG));
-      nLeft[c] = hi - lo;
-      int bestR = -1, bestN = 0, i = lo;
-      while (i < hi) {
-        const uint32_t k = keys[i];
-        int j = i + 1;
-        while (j < hi && keys[j] == k) j++;
-        if (j - i > bestN) { bestN = j - i; bestR = (int)(k - (uint32_t)(c * GMS_NG)); }
-        i = j;
-      }
-      cellPair[c] = bestR;  // -1 when the row is empty
     }
     __syncthreads();
-    // neighbourhood support test (:358-381); decisions are staged so every cell reads the
-    // unmodified nLeft / keys
+    // neighbourhood support test (:358-381); decisions are staged so every cell reads the unmodified tables
     int dec[(GMS_NG + GMS_THREADS - 1) / GMS_THREADS];
     {
       int u = 0;
       for (int c = tid; c < GMS_NG; c += GMS_THREADS, u++) {
-        const int rt = cellPair[c];
+        const unsigned packed = (unsigned)cellPair[c];
+        const int rt = packed ? 0xFFFF - (int)(packed & 0xFFFFu) : -1;  // -1 when the row is empty
         dec[u] = rt;
         if (rt < 0) continue;
         int score = 0, numpair = 0;
@@ -274,10 +273,7 @@ __global__ void __launch_bounds__(GMS_THREADS) k_gms(const GfsKeyPoint* __restri
         for (int k = 0; k < 9; k++) {
           const int ll = gms_nb9(c, k), rr = gms_nb9(rt, k);
           if (ll == -1 || rr == -1) continue;
-          const uint32_t key = (uint32_t)(ll * GMS_NG + rr);
-          const int lo = lower_bound_u32(keys, pow2, key);
-          const int hi = lower_bound_u32(keys, pow2, key + 1);
-          score += hi - lo;
+          score += gms_count(hkey, hcnt, tbits, (uint32_t)(ll * GMS_NG + rr));
           thresh += nLeft[ll];
           numpair++;
         }
@@ -314,15 +310,18 @@ static int next_pow2(int n) {
 static int launch_gms(cudaStream_t st, const GfsKeyPoint* kp1, const int* n1, const GfsKeyPoint* kp2, const int* n2,
                       const int* mq, const int* mt, const int* nm, int pairs, int stride, int mstride, int w1, int h1,
                       int w2, int h2, uint8_t* inl, int* cnt) {
-  const int p2 = next_pow2(mstride);
-  const size_t smem = (size_t)p2 * 4 + (size_t)mstride * 4 + 2 * GMS_NG * 4;
-  GFS_REQUIRE(smem <= 200 * 1024, GFS_ERR_CAPACITY, "too many matches per pair for the GMS kernel (max ~24k)");
+  // hash table: a power of two >= 1.5 x the matches of a pair (load factor <= 2/3)
+  const int tsize = next_pow2(mstride + mstride / 2 + 1);
+  int tbits = 0;
+  while ((1 << tbits) < tsize) tbits++;
+  const size_t smem = (size_t)tsize * 8 + (size_t)mstride * 4 + 2 * GMS_NG * 4;
+  GFS_REQUIRE(smem <= 200 * 1024 && mstride < 65536, GFS_ERR_CAPACITY, "too many matches per pair for the GMS kernel (max ~16k)");
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     GFS_CUDA(cudaFuncSetAttribute(k_gms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  k_gms<<<pairs, GMS_THREADS, smem, st>>>(kp1, n1, kp2, n2, mq, mt, nm, stride, mstride, p2, w1, h1, w2, h2, inl, cnt);
+  k_gms<<<pairs, GMS_THREADS, smem, st>>>(kp1, n1, kp2, n2, mq, mt, nm, stride, mstride, tbits, w1, h1, w2, h2, inl, cnt);
   GFS_CUDA(cudaGetLastError());
   return GFS_OK;
 }
