@@ -1223,24 +1223,30 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(OrbDev P, const u
   m01 = __reduce_add_sync(0xffffffffu, m01);
   const float angle = fast_atan2_deg(P, (float)m01, (float)m10);
 
-  // ---- horizontal blur pass: hb[r][c] = sum_k K[k] * raw[r][c + k], c in [0, 40) (37 used).  An item is
-  // four adjacent outputs: 4 aligned words of the raw row are realigned to the patch origin, every output
-  // is two 4-tap byte dot products (dp4a) with the kernel (18 34 48 56 | 48 34 18 0).
+  // ---- horizontal blur pass: hb[r][c] = sum_k K[k] * raw[r][c + k], c in [0, 40) (37 used).  The aligned
+  // words of the raw row are realigned to the patch origin (funnel shifts), every output is two 4-tap
+  // byte dot products (dp4a) with the kernel (18 34 48 56 | 48 34 18 0).
   uint16_t* hb = s_hb[warp];
   {
     const unsigned sh8 = 8u * (unsigned)shift;
     const uint32_t* raw32 = (const uint32_t*)raw;
-    for (int item = lane; item < PATCH_W * (HB_PITCH / 4); item += 32) {
-      const int r = item / (HB_PITCH / 4), qd = item - r * (HB_PITCH / 4);
-      const uint32_t* w = raw32 + r * (RAW_PITCH / 4) + qd;
-      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
-      const uint32_t s0 = __funnelshift_r(w0, w1, sh8), s1 = __funnelshift_r(w1, w2, sh8), s2 = __funnelshift_r(w2, w3, sh8);
-      const uint32_t a0 = s0, a1 = __byte_perm(s0, s1, 0x4321), a2 = __byte_perm(s0, s1, 0x5432), a3 = __byte_perm(s0, s1, 0x6543);
-      const uint32_t a4 = s1, a5 = __byte_perm(s1, s2, 0x4321), a6 = __byte_perm(s1, s2, 0x5432), a7 = __byte_perm(s1, s2, 0x6543);
-      const uint32_t kA = 18u | (34u << 8) | (48u << 16) | (56u << 24), kB = 48u | (34u << 8) | (18u << 16);
-      const unsigned o0 = __dp4a(a4, kB, __dp4a(a0, kA, 0u)), o1 = __dp4a(a5, kB, __dp4a(a1, kA, 0u));
-      const unsigned o2 = __dp4a(a6, kB, __dp4a(a2, kA, 0u)), o3 = __dp4a(a7, kB, __dp4a(a3, kA, 0u));
-      *reinterpret_cast<uint2*>(hb + r * HB_PITCH + 4 * qd) = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
+    const uint32_t kA = 18u | (34u << 8) | (48u << 16) | (56u << 24), kB = 48u | (34u << 8) | (18u << 16);
+    // an item is eight adjacent outputs (five aligned words in, one 16-byte store out)
+    for (int item = lane; item < PATCH_W * (HB_PITCH / 8); item += 32) {
+      const int r = item / (HB_PITCH / 8), q8 = item - r * (HB_PITCH / 8);
+      const uint32_t* w = raw32 + r * (RAW_PITCH / 4) + 2 * q8;
+      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+      const uint32_t s0 = __funnelshift_r(w0, w1, sh8), s1 = __funnelshift_r(w1, w2, sh8), s2 = __funnelshift_r(w2, w3, sh8),
+                     s3 = __funnelshift_r(w3, w4, sh8);
+      uint32_t a[12];
+      a[0] = s0; a[1] = __byte_perm(s0, s1, 0x4321); a[2] = __byte_perm(s0, s1, 0x5432); a[3] = __byte_perm(s0, s1, 0x6543);
+      a[4] = s1; a[5] = __byte_perm(s1, s2, 0x4321); a[6] = __byte_perm(s1, s2, 0x5432); a[7] = __byte_perm(s1, s2, 0x6543);
+      a[8] = s2; a[9] = __byte_perm(s2, s3, 0x4321); a[10] = __byte_perm(s2, s3, 0x5432); a[11] = __byte_perm(s2, s3, 0x6543);
+      unsigned o[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) o[k] = __dp4a(a[k + 4], kB, __dp4a(a[k], kA, 0u));
+      *reinterpret_cast<uint4*>(hb + r * HB_PITCH + 8 * q8) =
+          make_uint4(o[0] | (o[1] << 16), o[2] | (o[3] << 16), o[4] | (o[5] << 16), o[6] | (o[7] << 16));
     }
   }
   __syncwarp();
