@@ -67,7 +67,7 @@ struct AreaEntry {
 // row, buf = S0*a0 (+ S1*a1 (+ S2*a2)) in float and then sum = b0*buf0 (+ b1*buf1 ...) -- the same
 // order is kept here, every product and sum rounded separately.
 // ------------------------------------------------------------------------------------------------
-static const int PYR_TW = 64, PYR_TH = 32;
+static const int PYR_TW = 64, PYR_TH = 48;
 __global__ void __launch_bounds__(256) k_pyr_level(OrbDev P, int l, const uint8_t* __restrict__ src_base,
                                                    long long src_stride, int src_pitch, uint8_t* __restrict__ pyr,
                                                    const AreaEntry* __restrict__ tabs) {
@@ -569,9 +569,10 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells2(OrbDev P, const Fa
     for (int idx = tid; idx < ((dh + 2) * SP + 15) >> 4; idx += FAST_THREADS) z[idx] = make_uint4(0u, 0u, 0u, 0u);
   }
   const int wLo = (shift + 3) >> 2, wHi = (shift + rw - 4) >> 2, nWt = wHi - wLo + 1;
-  // i / nWt == (i * inv) >> 16 for i < 4096 (nWt <= 32: the float quotient cannot round across an integer)
-  const unsigned inv = (unsigned)(65536.0f / (float)nWt) + 1u;
-  if (tid < nWt) {
+  // i / nPair == (i * inv) >> 16 for i < 4096 (nPair <= 32: the float quotient cannot round across an integer)
+  const int nPair = (nWt + 1) >> 1;  // a thread of phase 1 takes two adjacent words
+  const unsigned inv = (unsigned)(65536.0f / (float)nPair) + 1u;
+  if (tid <= nWt) {  // entry nWt (all zero) pads an odd row
     // which bytes of word wLo + tid are tested pixels (column in [0, dw)), as bits 14 / 15 / 30 / 31
     const int xb = 4 * (wLo + tid) - shift - 3;
     unsigned vm = 0u;
@@ -586,43 +587,51 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells2(OrbDev P, const Fa
   __syncthreads();
 
   const int thMin = P.minTh, thIni = P.iniTh;
-  const int items = nWt * dh;  // (row, word) grid of the words that hold tested pixels (x in [3, rw - 3))
+  const int items = nPair * dh;  // (row, word pair) grid of the words that hold tested pixels (x in [3, rw - 3))
   const uint32_t* sm32 = (const uint32_t*)sm;
   int nKept = 0;
   for (int pass = 0; pass < 2; pass++) {
     const int th = pass == 0 ? thIni : thMin;
-    // phase 1: antipodal-pair reject, four pixels per thread.  Every 9-arc of the 16-ring holds one
-    // pixel of each antipodal pair, so both (0,8) and (4,12) must have a bright (dark) member.
+    // phase 1: antipodal-pair reject, eight pixels (two adjacent words) per thread.  Every 9-arc of the
+    // 16-ring holds one pixel of each antipodal pair, so both (0,8) and (4,12) must have a bright (dark)
+    // member.  E(w) / O(w) = even / odd bytes of a word as 16-bit lanes; the neighbours 3 columns to the
+    // left / right of the even pixels are odd bytes and vice versa, half of them straddle two words.
     {
       const unsigned K = (unsigned)(th + 0x8000) * 0x00010001u;
       const uint32_t* r0 = sm32 + 3 * rp32 + wLo;
       const int key0 = 4 * wLo - shift - 3;
+      auto reject = [K](unsigned c, unsigned u, unsigned d, unsigned lf, unsigned rt) -> unsigned {
+        const unsigned HB = c + K, LB = K - c;
+        const unsigned notBright = ((HB - u) & (HB - d)) | ((HB - lf) & (HB - rt));
+        const unsigned notDark = ((LB + u) & (LB + d)) | ((LB + lf) & (LB + rt));
+        return ~(notBright & notDark) & 0x80008000u;
+      };
       for (int it = tid; it < items; it += FAST_THREADS) {
-        const int y = (int)(((unsigned)it * inv) >> 16), w = it - y * nWt;
+        const int y = (int)(((unsigned)it * inv) >> 16), w = 2 * (it - y * nPair);
         const uint32_t* r = r0 + y * rp32 + w;
         const unsigned key = (unsigned)((y << 8) + 4 * w + key0);  // (row << 8 | column) of byte 0
-        const unsigned C = r[0], Wm = r[-1], Wp = r[1], U = r[-3 * rp32], D = r[3 * rp32];
-        const unsigned Lw = __byte_perm(Wm, C, 0x4321), Rw = __byte_perm(C, Wp, 0x6543);
-        unsigned ok[2];
-#pragma unroll
-        for (int par = 0; par < 2; par++) {
-          const unsigned sel = par ? 0x4341u : 0x4240u;
-          const unsigned cc = __byte_perm(C, 0u, sel);
-          const unsigned HB = cc + K, LB = K - cc;
-          const unsigned u = __byte_perm(U, 0u, sel), d = __byte_perm(D, 0u, sel);
-          const unsigned lf = __byte_perm(Lw, 0u, sel), rt = __byte_perm(Rw, 0u, sel);
-          const unsigned notBright = ((HB - u) & (HB - d)) | ((HB - lf) & (HB - rt));
-          const unsigned notDark = ((LB + u) & (LB + d)) | ((LB + lf) & (LB + rt));
-          ok[par] = ~(notBright & notDark);
-        }
-        // bits 14 / 15 / 30 / 31 = pixels 0 / 1 / 2 / 3 of the word
-        const unsigned t = (((ok[0] & 0x80008000u) >> 1) | (ok[1] & 0x80008000u)) & s_vm[w];
-        if (t) {
-          int pos = atomicAdd(&s_nCand, __popc(t));
-          if (t & 0x00004000u) cand[pos++] = (uint16_t)key;
-          if (t & 0x00008000u) cand[pos++] = (uint16_t)(key + 1u);
-          if (t & 0x40000000u) cand[pos++] = (uint16_t)(key + 2u);
-          if (t & 0x80000000u) cand[pos] = (uint16_t)(key + 3u);
+        const unsigned Wm = r[-1], C0 = r[0], C1 = r[1], Wp = r[2];
+        const unsigned U0 = r[-3 * rp32], U1 = r[-3 * rp32 + 1], D0 = r[3 * rp32], D1 = r[3 * rp32 + 1];
+        const unsigned eM = __byte_perm(Wm, 0u, 0x4240), oM = __byte_perm(Wm, 0u, 0x4341);
+        const unsigned e0 = __byte_perm(C0, 0u, 0x4240), o0 = __byte_perm(C0, 0u, 0x4341);
+        const unsigned e1 = __byte_perm(C1, 0u, 0x4240), o1 = __byte_perm(C1, 0u, 0x4341);
+        const unsigned eP = __byte_perm(Wp, 0u, 0x4240), oP = __byte_perm(Wp, 0u, 0x4341);
+        const unsigned t0e = reject(e0, __byte_perm(U0, 0u, 0x4240), __byte_perm(D0, 0u, 0x4240), oM, __byte_perm(o0, o1, 0x5432));
+        const unsigned t0o = reject(o0, __byte_perm(U0, 0u, 0x4341), __byte_perm(D0, 0u, 0x4341), __byte_perm(eM, e0, 0x5432), e1);
+        const unsigned t1e = reject(e1, __byte_perm(U1, 0u, 0x4240), __byte_perm(D1, 0u, 0x4240), o0, __byte_perm(o1, oP, 0x5432));
+        const unsigned t1o = reject(o1, __byte_perm(U1, 0u, 0x4341), __byte_perm(D1, 0u, 0x4341), __byte_perm(e0, e1, 0x5432), eP);
+        // bits 14 / 15 / 30 / 31 = pixels 0 / 1 / 2 / 3 of a word
+        const unsigned ta = ((t0e >> 1) | t0o) & s_vm[w], tb = ((t1e >> 1) | t1o) & s_vm[w + 1];
+        if (ta | tb) {
+          int pos = atomicAdd(&s_nCand, __popc(ta) + __popc(tb));
+          if (ta & 0x00004000u) cand[pos++] = (uint16_t)key;
+          if (ta & 0x00008000u) cand[pos++] = (uint16_t)(key + 1u);
+          if (ta & 0x40000000u) cand[pos++] = (uint16_t)(key + 2u);
+          if (ta & 0x80000000u) cand[pos++] = (uint16_t)(key + 3u);
+          if (tb & 0x00004000u) cand[pos++] = (uint16_t)(key + 4u);
+          if (tb & 0x00008000u) cand[pos++] = (uint16_t)(key + 5u);
+          if (tb & 0x40000000u) cand[pos++] = (uint16_t)(key + 6u);
+          if (tb & 0x80000000u) cand[pos] = (uint16_t)(key + 7u);
         }
       }
     }

@@ -1,11 +1,7 @@
 set -x
-python -m pytest tests/test_gpu_orb.py tests/test_gpu_fullsize.py tests/test_golden.py -m gpu -x -q > gpurun_out/s11_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/s11_tests.log
-tail -3 gpurun_out/s11_tests.log
-python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/s11_bench.json 2> gpurun_out/s11_bench.err
-python - <<'PY'
-import json,glob
-for f in sorted(glob.glob("gpurun_out/s11_bench*.json")):
-    try:
-        d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, round(d["value"]), round(d["e2e"]["value"]), round(d["e2e"]["ms_per_step"],3), {k:round(v["ms"],3) for k,v in d["roofline"]["stages"].items()})
-    except Exception as e: print(f, e)
-PY
+python -m pytest tests/test_gpu_orb.py tests/test_gpu_match.py tests/test_gpu_fullsize.py tests/test_golden.py -m gpu -x -q > gpurun_out/s13_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/s13_tests.log
+tail -3 gpurun_out/s13_tests.log
+python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/s13_bench.json 2> gpurun_out/s13_bench.err
+cp geoflowslam_b200/libgfs_b200.so /tmp/lib_keep.so
+for v in th40 th56; do cp geoflowslam_b200/_variant_$v.so geoflowslam_b200/libgfs_b200.so; python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/s13_bench_$v.json 2>/dev/null; done
+cp /tmp/lib_keep.so geoflowslam_b200/libgfs_b200.so
