@@ -299,7 +299,7 @@ def run_ours(args):
     # DRAM traffic per frame of the dominant kernels from the committed `ncu --set full` captures
     # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r01_summary.md), scaled to this launch
     ncu_traffic_per_frame = {"fast_cells": (113.192192e6 + 5.287680e6) / 128,     # profiles/r01_s3_k_fast_cells2_ncu_details.txt
-                             "orient_desc": (122.655488e6 + 9.598208e6) / 128}   # profiles/r01_s3_k_orient_desc_ncu_details.txt
+                             "orient_desc": (122.779648e6 + 8.324864e6) / 128}   # profiles/r01_s3_k_orient_desc_ncu_details.txt
     ncu_traffic_src = {"fast_cells": "ncu capture profiles/r01_s3_k_fast_cells2_ncu_details.txt",
                        "orient_desc": "ncu capture profiles/r01_s3_k_orient_desc_ncu_details.txt"}
     traffic = ncu_traffic_per_frame[top] * B if top in ncu_traffic_per_frame else None

@@ -156,9 +156,9 @@ int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batc
                       (batch == 1 || (is_pinned_host(out_train_idx) && is_pinned_host(out_dist) && is_pinned_host(out_inlier)));
   bool matchedInChunks = false;
   // H2D is faster than the kernels, so after the first chunk the copy stream stays ahead: only the first
-  // copy is exposed.  Chunks of batch/8 keep it short while the kernels still see >= 64 frames.
+  // copy is exposed.  Chunks of batch/12 keep it short while the kernels still see >= 64 frames.
   const char* ce = getenv("GFS_FRONTEND_CHUNKS");
-  const int nDiv = ce ? std::max(1, atoi(ce)) : 8;
+  const int nDiv = ce ? std::max(1, atoi(ce)) : 12;
   f->chunk = std::max(64, div_up(batch, nDiv));
   const char* fe = getenv("GFS_FRONTEND_FIRST");
   const int firstChunk = fe ? std::min(f->chunk, std::max(1, atoi(fe))) : std::max(32, f->chunk / 2);
@@ -186,11 +186,12 @@ int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batc
     GFS_CUDA(cudaStreamWaitEvent(f->copyStream, f->evStart, 0));
     GFS_CUDA(cudaStreamWaitEvent(f->outStream, f->evStart, 0));
     for (int i = 0; i < 7; i++) GFS_CUDA(cudaStreamWaitEvent(f->aux[i], f->evStart, 0));
-    // Chunks rotate over nStreams compute streams.  Measured (B200, 1024 VGA frames, 8 chunks): 2 streams 100.0k
-    // frames/s end to end, 3: 104.9k, 4: 108.8k -- the latency-bound quadtree kernel of a chunk (~0.5 ms whatever
-    // the chunk size) needs the throughput kernels of several other chunks to hide behind.
+    // Chunks rotate over nStreams compute streams: the latency-bound quadtree kernel of a chunk (~0.4 ms whatever
+    // the chunk size) needs the throughput kernels of several other chunks to hide behind.  Measured (B200, 1024
+    // VGA frames, frames/s end to end; profiles/r01_summary.md): 8 chunks on 2 / 3 / 4 streams 100.0k / 104.9k /
+    // 108.8k; with the final kernels 4 streams x 8 chunks 123.5k, 6 x 10 125.3k, 8 x 12 127.0k (default).
     const char* se = getenv("GFS_FRONTEND_STREAMS");
-    const int nStreams = se ? std::min(8, std::max(1, atoi(se))) : 4;
+    const int nStreams = se ? std::min(8, std::max(1, atoi(se))) : 8;
     cudaStream_t streams[8] = {st, f->aux[0], f->aux[1], f->aux[2], f->aux[3], f->aux[4], f->aux[5], f->aux[6]};
     // A chunk's frame
     // pairs (and the pair that straddles the previous chunk) are matched and copied out right behind

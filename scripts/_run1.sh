@@ -1,7 +1,9 @@
 set -x
-python -m pytest tests/test_gpu_orb.py tests/test_gpu_match.py tests/test_gpu_fullsize.py tests/test_golden.py -m gpu -x -q > gpurun_out/s13_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/s13_tests.log
-tail -3 gpurun_out/s13_tests.log
-python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/s13_bench.json 2> gpurun_out/s13_bench.err
-cp geoflowslam_b200/libgfs_b200.so /tmp/lib_keep.so
-for v in th40 th56; do cp geoflowslam_b200/_variant_$v.so geoflowslam_b200/libgfs_b200.so; python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/s13_bench_$v.json 2>/dev/null; done
-cp /tmp/lib_keep.so geoflowslam_b200/libgfs_b200.so
+python -m pytest tests -m gpu -x -q > gpurun_out/s14_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/s14_tests.log
+tail -3 gpurun_out/s14_tests.log
+python bench.py --steps 10 --warmup 3 > gpurun_out/s14_bench.json 2> gpurun_out/s14_bench.err
+for cfg in "4 6" "4 10" "6 8" "6 10" "8 12"; do set -- $cfg; GFS_FRONTEND_STREAMS=$1 GFS_FRONTEND_CHUNKS=$2 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/s14_bench_s$1_c$2.json 2>/dev/null; done
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/s14_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/s14_ncu_list.log 2>&1
+timeout 200 ncu --set full --clock-control none --import-source on -k k_orient_desc -c 1 -f -o gpurun_out/s14_od python bench.py --steps 1 --warmup 1 --no-cpu --batch 256 > gpurun_out/s14_ncu.log 2>&1
+timeout 200 python bench.py --workload track --steps 3 --warmup 1 > gpurun_out/s14_track.json 2> gpurun_out/s14_track.err
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/s14_smoke.log 2>&1
