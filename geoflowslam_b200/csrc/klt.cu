@@ -406,7 +406,25 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
     __syncwarp();
     const unsigned aJ = stage_window(J, inx, iny, win, s_win);
     long long sb1 = 0, sb2 = 0;
-    {
+    if (((win * win + 31) >> 5) <= 64 && (aJ == NO_SHIFT || (J.w & 3) == 0)) {
+      // Common case (level widths that are multiples of 4, or a reflected window): every staged row has the same
+      // misalignment, so a pixel's address is one multiply-add; and a lane's <= 64 products (|diff| <= 8160 =
+      // 255 * 32, |d| <= 4080 = 16 * 255: each < 2^25) sum exactly in 32 bits.
+      const uint8_t* wbase = s_win + (aJ == NO_SHIFT ? 0 : (int)aJ);
+      int a1 = 0, a2 = 0;
+      int x = lane, y = 0;
+      while (x >= win) { x -= win; y++; }
+      for (int i = lane; i < win * win; i += 32) {
+        const uint8_t* s0 = wbase + y * pitch + x;
+        const int diff = descale(s0[0] * iw00 + s0[1] * iw01 + s0[pitch] * iw10 + s0[pitch + 1] * iw11, W_BITS - 5) - s_I[i];
+        const short2 d = s_dI[y * (win + 1) + x];
+        a1 += diff * d.x;
+        a2 += diff * d.y;
+        x += 32;
+        while (x >= win) { x -= win; y++; }
+      }
+      sb1 = a1; sb2 = a2;
+    } else {
       int x = lane, y = 0;
       while (x >= win) { x -= win; y++; }
       for (int i = lane; i < win * win; i += 32) {
