@@ -93,7 +93,10 @@ int gfs_frontend_get_profile(GfsFrontend* f, float* ms8) {
 
 int gfs_frontend_launches_per_call(const GfsFrontend* f, int batch) {
   if (!f) return GFS_ERR_INVALID;
-  return gfs_orb_launches_per_call(f->orb, 0, 0) + (batch > 1 ? 2 : 0);
+  // gfs_frontend_run_device: the extractor splits batches of >= 128 frames into two halves on two streams
+  // (gfs_orb_extract_batch_device), each half launching the whole kernel sequence; then matcher + GMS
+  const int halves = (!f->profiling && batch >= 128 && batch <= f->maxBatch) ? 2 : 1;
+  return halves * gfs_orb_launches_per_call(f->orb, 0, 0) + (batch > 1 ? 2 : 0);
 }
 
 int gfs_frontend_run_device(GfsFrontend* f, void* stream, const uint8_t* d_imgs, int batch, int w, int h_img,
