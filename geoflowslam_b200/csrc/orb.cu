@@ -4,7 +4,8 @@
 // OpenCV primitives underneath it.  One launch sequence processes a whole batch of frames:
 //
 //   k_pyr_level   x (nlevels-1)  INTER_AREA pyramid (ComputePyramid :1227-1251, cv::resize)
-//   k_fast_cells                 per 35-px cell FAST-9/16 + 3x3 NMS + ini->min threshold retry
+//   k_fast_cells2                per 35-px cell FAST-9/16 + 3x3 NMS + ini->min threshold retry
+//                                (k_fast_cells: first generation, GFS_FAST_V1=1)
 //                                (ComputeKeyPointsOctTree cell loop :794-851, cv::FAST)
 //   k_octree                     quadtree keypoint distribution (DistributeOctTree :567-768), one
 //                                warp per (frame, level), exact std::list / std::sort semantics
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbDev P, const uin
 // ------------------------------------------------------------------------------------------------
 // k_fast_cells2: same contract as k_fast_cells (one CTA per (cell, frame), same outputs), fewer
 // instructions per pixel.
-//   phase 1: one thread per aligned 4-pixel word of the tested region.  The word and its four ring
+//   phase 1: one thread per two aligned 4-pixel words of the tested region.  The words and their ring
 //            neighbours (3 rows up / down, 3 columns left / right) are split into even / odd bytes
 //            as 16-bit lanes, so `v > c + th` and `v < c - th` are one 32-bit add each for two
 //            pixels (bit 15 of `c + th + 0x8000 - v` / `v + 0x8000 - c + th`; no lane ever
