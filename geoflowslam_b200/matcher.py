@@ -57,6 +57,90 @@ class ORBmatcher:
         return m, mask, n
 
 
+def _default_fundamental(p1, p2, thr):
+    """cv::findFundamentalMat(p1, p2, FM_RANSAC, thr, 0.99, status) -- the OpenCV call the reference makes on the host
+    (src/ORBmatcher.cc:2399,2463); its RANSAC draws from OpenCV's own RNG, so it stays OpenCV's."""
+    import cv2
+    _, st = cv2.findFundamentalMat(np.ascontiguousarray(p1, np.float32), np.ascontiguousarray(p2, np.float32), cv2.FM_RANSAC,
+                                   float(thr), 0.99)
+    return None if st is None else st.ravel().astype(bool)
+
+
+def search_by_projection_with_of(tracker, cur_keys, last_keys, last_mp_state, last_mp_world, Rcw, tcw, K, bounds, prev_img, cur_img,
+                                 mask, winsize=35, F_THRESHOLD=1.0, DIST_THRESHOLD=10, fundamental=None):
+    """ORBmatcher::SearchByProjectionWithOF (src/ORBmatcher.cc:2303-2497), the caller of fbKltTracking in the dual-stream
+    front end (Tracking.cc:3499,3623,3646), on plain arrays instead of Frame / MapPoint objects.
+
+    tracker: `KltTracker.fbKltTracking`-compatible callable (prev_img, cur_img, kps, priors, win, nbpyrlvl, ferr, max_dist)
+    -> (priors, status) -- the CUDA path.  last_mp_state[i]: 0 = no map point, 1 = usable map point, 2 = bad map point or
+    outlier (skipped).  K = (fx, fy, cx, cy); bounds = (mnMinX, mnMaxX, mnMinY, mnMaxY); mask (h, w) u8 is updated in place.
+    Returns (nbgood, tracked_ids (m,) int32 into the last frame, tracked_pts (m, 2) float32) in the order the reference hands
+    them to Frame::AddPts: points with a map point that projects into the image are tracked from their projection over 3
+    pyramid levels, everything else (and the failures of the first pass) from the old position over all levels; both
+    passes are filtered by OpenCV's fundamental-matrix RANSAC and by the occupancy mask (DIST_THRESHOLD-px discs).
+    Sophus applies Tcw through its unit quaternion; here R x + t in float32, so a prior can differ from the reference's in
+    the last ulp."""
+    import cv2
+    f32 = np.float32
+    fundamental = fundamental or _default_fundamental
+    H, W = mask.shape
+    ck = np.asarray(cur_keys, f32).reshape(-1, 2)
+    ok = (ck[:, 0] > 0) & (ck[:, 0] < W) & (ck[:, 1] > 0) & (ck[:, 1] < H)
+    mask[ck[ok, 1].astype(np.int64), ck[ok, 0].astype(np.int64)] = 255                        # :2327-2334 (truncating index)
+    lk = np.asarray(last_keys, f32).reshape(-1, 2)
+    state = np.asarray(last_mp_state).reshape(-1)
+    R = np.asarray(Rcw, f32).reshape(3, 3); t = np.asarray(tcw, f32).reshape(3)
+    X = np.asarray(last_mp_world, f32).reshape(-1, 3)
+    fx, fy, cx, cy = (f32(v) for v in K)
+    # float32 throughout, products and sums rounded one by one in Eigen's order (:2352-2360)
+    pc = [(R[r, 0] * X[:, 0] + R[r, 1] * X[:, 1]) + R[r, 2] * X[:, 2] + t[r] for r in range(3)]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        invz = (1.0 / pc[2].astype(np.float64)).astype(f32)
+        u = fx * pc[0] * invz + cx
+        v = fy * pc[1] * invz + cy
+    inside = ~((invz < 0) | (u < f32(bounds[0])) | (u > f32(bounds[1])) | (v < f32(bounds[2])) | (v > f32(bounds[3])))
+    is3d = (state == 1) & inside
+    is2d = (state == 0) | ((state == 1) & ~inside)
+    ids3 = np.flatnonzero(is3d)
+    ids2 = list(np.flatnonzero(is2d))
+    out_ids, out_pts = [], []
+
+    def accept(ids, pts, status):
+        rejected = []
+        for i, good in enumerate(status):
+            if not good:
+                rejected.append(int(ids[i]))
+                continue
+            x, y = float(pts[i, 0]), float(pts[i, 1])
+            if mask[int(y), int(x)] == 255:                                                   # isPointNearby: truncation
+                continue
+            out_ids.append(int(ids[i])); out_pts.append((x, y))
+            cv2.circle(mask, (int(round(x)), int(round(y))), int(DIST_THRESHOLD), 255, cv2.FILLED)  # Point2f -> Point rounds
+        return rejected
+
+    def fcheck(kps, pts, status, thr):
+        idx = np.flatnonzero(status)
+        if len(idx) > 8:
+            st = fundamental(kps[idx], pts[idx], thr)
+            if st is not None:
+                status[idx[:len(st)][~np.asarray(st, bool)]] = False
+
+    if len(ids3):                                                                             # :2380-2437
+        kps = lk[ids3]
+        pts, status = tracker(prev_img, cur_img, kps, np.stack([u[ids3], v[ids3]], 1).astype(f32), winsize, 3, 15.0, 0.5)
+        status = np.asarray(status, bool).copy()
+        fcheck(kps, pts, status, F_THRESHOLD)
+        ids2 += accept(ids3, pts, status)                                                     # failures join the second pass
+    if len(ids2):                                                                             # :2440-2492
+        ids2 = np.asarray(ids2, np.int64)
+        kps = lk[ids2]
+        pts, status = tracker(prev_img, cur_img, kps, kps.copy(), winsize, 6, 15.0, 0.5)
+        status = np.asarray(status, bool).copy()
+        fcheck(kps, pts, status, F_THRESHOLD * 0.5)
+        accept(ids2, pts, status)
+    return len(out_ids), np.asarray(out_ids, np.int32), np.asarray(out_pts, f32).reshape(-1, 2)
+
+
 def _as_kp(k):
     if isinstance(k, np.ndarray) and k.dtype == KP_DTYPE:
         return np.ascontiguousarray(k)

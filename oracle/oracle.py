@@ -680,3 +680,99 @@ def imu_preintegrate(meas, bias, ng, na, ngw, naw):
     out = np.zeros(292, np.float32)
     lib().gfo_imu_preintegrate(_p(m), len(m), _p(b), float(ng), float(na), float(ngw), float(naw), _p(out))
     return out
+
+
+# ---- ORBmatcher::SearchByProjectionWithOF (reference src/ORBmatcher.cc:2303-2497): host logic around
+# fbKltTracking, restated statement by statement (test infrastructure: the product version is
+# geoflowslam_b200.matcher.ORBmatcher.SearchByProjectionWithOF)
+def search_by_projection_with_of(cur_keys, last_keys, last_mp_state, last_mp_world, Rcw, tcw, K, bounds, prev_img, cur_img, mask,
+                                 winsize=35, F_THRESHOLD=1.0, DIST_THRESHOLD=10, tracker=None, fundamental=None):
+    """last_mp_state[i]: 0 = no map point (nullptr), 1 = usable map point, 2 = bad map point or outlier (skipped, :2349).
+    K = (fx, fy, cx, cy), bounds = (mnMinX, mnMaxX, mnMinY, mnMaxY).  tracker(prev_img, cur_img, kps, priors, win, nbpyrlvl,
+    ferr, max_dist) -> (priors, status) is fbKltTracking; fundamental(p1, p2, thr) -> uchar status or None is
+    cv::findFundamentalMat(p1, p2, FM_RANSAC, thr, 0.99, status).  Returns (nbgood, tracked, mask) with tracked = the
+    (index into the last frame, new position) pairs in the order Frame::AddPts receives them."""
+    import cv2
+    f32 = np.float32
+    H, W = mask.shape
+    fx, fy, cx, cy = (f32(v) for v in K)
+    mnMinX, mnMaxX, mnMinY, mnMaxY = (f32(v) for v in bounds)
+    if fundamental is None:
+        def fundamental(p1, p2, thr):
+            _, st = cv2.findFundamentalMat(np.asarray(p1, f32), np.asarray(p2, f32), cv2.FM_RANSAC, float(thr), 0.99)
+            return None if st is None else st.ravel()
+    for kp in np.asarray(cur_keys, f32).reshape(-1, 2):                                       # :2327-2334
+        if kp[0] > 0 and kp[0] < W and kp[1] > 0 and kp[1] < H:
+            mask[int(kp[1]), int(kp[0])] = 255
+    last_keys = np.asarray(last_keys, f32).reshape(-1, 2)
+    R = np.asarray(Rcw, f32).reshape(3, 3); t = np.asarray(tcw, f32).reshape(3)
+    v3dkps, v3dpriors, v3dkpids, v2dkps, v2dpriors, v2dkpids = [], [], [], [], [], []
+    for cnt in range(len(last_keys)):                                                         # :2336-2374
+        u, v = last_keys[cnt]
+        if last_mp_state[cnt] == 0:
+            v2dkps.append((u, v)); v2dpriors.append((u, v)); v2dkpids.append(cnt)
+            continue
+        if last_mp_state[cnt] == 2:
+            continue
+        x = np.asarray(last_mp_world[cnt], f32)
+        xc = f32(f32(f32(R[0, 0] * x[0]) + f32(R[0, 1] * x[1])) + f32(R[0, 2] * x[2])) + t[0]
+        yc = f32(f32(f32(R[1, 0] * x[0]) + f32(R[1, 1] * x[1])) + f32(R[1, 2] * x[2])) + t[1]
+        zc = f32(f32(f32(R[2, 0] * x[0]) + f32(R[2, 1] * x[1])) + f32(R[2, 2] * x[2])) + t[2]
+        with np.errstate(divide="ignore"):
+            invzc = f32(np.float64(1.0) / np.float64(zc))
+        pu = f32(f32(f32(fx * xc) * invzc) + cx)
+        pv = f32(f32(f32(fy * yc) * invzc) + cy)
+        if invzc < 0 or pu < mnMinX or pu > mnMaxX or pv < mnMinY or pv > mnMaxY:
+            v2dkps.append((u, v)); v2dpriors.append((u, v)); v2dkpids.append(cnt)
+            continue
+        v3dkps.append((u, v)); v3dpriors.append((pu, pv)); v3dkpids.append(cnt)
+    nbgood, tracked = 0, []
+
+    def near(pt):                                                                             # isPointNearby :2299-2301
+        return mask[int(pt[1]), int(pt[0])] == 255
+
+    def update(pt):                                                                           # updateMask :2295-2297
+        cv2.circle(mask, (int(round(float(pt[0]))), int(round(float(pt[1])))), int(DIST_THRESHOLD), 255, cv2.FILLED)
+
+    def fcheck(kps, priors, status, thr):                                                     # :2389-2407, :2453-2470
+        index = [i for i in range(len(status)) if status[i]]
+        if len(index) > 8:
+            st = fundamental([kps[i] for i in index], [priors[i] for i in index], thr)
+            if st is not None:
+                for i in range(len(st)):
+                    if not st[i]:
+                        status[index[i]] = False
+
+    if v3dpriors:                                                                             # :2380-2437
+        pr, status = tracker(prev_img, cur_img, np.array(v3dkps, f32), np.array(v3dpriors, f32), winsize, 3, 15.0, 0.5)
+        status = [bool(s) for s in status]
+        fcheck(v3dkps, pr, status, F_THRESHOLD)
+        for i in range(len(v3dkps)):
+            if status[i]:
+                if near(pr[i]):
+                    continue
+                tracked.append((v3dkpids[i], (float(pr[i][0]), float(pr[i][1]))))
+                nbgood += 1
+                update(pr[i])
+            else:
+                u, v = last_keys[v3dkpids[i]]
+                v2dkps.append((u, v)); v2dpriors.append((u, v)); v2dkpids.append(v3dkpids[i])
+    if v2dkps:                                                                                # :2440-2492
+        pr, status = tracker(prev_img, cur_img, np.array(v2dkps, f32), np.array(v2dpriors, f32), winsize, 6, 15.0, 0.5)
+        status = [bool(s) for s in status]
+        fcheck(v2dkps, pr, status, F_THRESHOLD * 0.5)
+        for i in range(len(v2dkps)):
+            if status[i]:
+                if near(pr[i]):
+                    continue
+                tracked.append((v2dkpids[i], (float(pr[i][0]), float(pr[i][1]))))
+                update(pr[i])
+                nbgood += 1
+    return nbgood, tracked, mask
+
+
+def fb_klt_tracking_images(prev_img, cur_img, kps, priors, win=35, nbpyrlvl=3, ferr=15.0, max_fbklt_dist=0.5, levels=3):
+    """fbKltTracking on two gray images: the pyramids Frame::Frame builds (maxLevel 3, src/Frame.cc:370-373) + fb_klt_tracking."""
+    h, w = prev_img.shape
+    return fb_klt_tracking(klt_build_pyramid(prev_img, levels), klt_build_pyramid(cur_img, levels), w, h, levels, kps, priors, win,
+                           nbpyrlvl, ferr, max_fbklt_dist)
