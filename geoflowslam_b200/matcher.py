@@ -141,6 +141,35 @@ def search_by_projection_with_of(tracker, cur_keys, last_keys, last_mp_state, la
     return len(out_ids), np.asarray(out_ids, np.int32), np.asarray(out_pts, f32).reshape(-1, 2)
 
 
+def filter_outliers(keys, has_mp, mp_world, Rcw, tcw, K, F_THRESHOLD, fundamental=None):
+    """ORBmatcher::FilterOutliers (src/ORBmatcher.cc:208-246) on plain arrays: keypoints with a map point in front of the
+    camera are paired with the map point's projection and filtered by OpenCV's fundamental-matrix RANSAC.  Returns
+    (inliers, mvbOutlier (n,) bool).  The reference writes the status of the j-th FILTERED pair to mvbOutlier[j] (:237-240),
+    not to the keypoint the pair came from; that is kept."""
+    f32 = np.float32
+    fundamental = fundamental or _default_fundamental
+    keys = np.asarray(keys, f32).reshape(-1, 2)
+    has = np.asarray(has_mp, bool).reshape(-1)
+    R = np.asarray(Rcw, f32).reshape(3, 3); t = np.asarray(tcw, f32).reshape(3)
+    X = np.asarray(mp_world, f32).reshape(-1, 3)
+    fx, fy, cx, cy = (f32(v) for v in K)
+    pc = [(R[r, 0] * X[:, 0] + R[r, 1] * X[:, 1]) + R[r, 2] * X[:, 2] + t[r] for r in range(3)]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        invz = (1.0 / pc[2].astype(np.float64)).astype(f32)
+        u = fx * pc[0] / pc[2] + cx                                                            # Pinhole::project, float32
+        v = fy * pc[1] / pc[2] + cy
+    sel = np.flatnonzero(has & ~(invz < 0))
+    outlier = np.zeros(len(keys), bool)
+    inliers = 0
+    if len(sel) > 8:
+        st = fundamental(np.stack([u[sel], v[sel]], 1).astype(f32), keys[sel], F_THRESHOLD)
+        if st is not None:
+            st = np.asarray(st, bool)
+            outlier[:len(st)] = ~st
+            inliers = int(st.sum())
+    return inliers, outlier
+
+
 def _as_kp(k):
     if isinstance(k, np.ndarray) and k.dtype == KP_DTYPE:
         return np.ascontiguousarray(k)

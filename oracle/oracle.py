@@ -776,3 +776,45 @@ def fb_klt_tracking_images(prev_img, cur_img, kps, priors, win=35, nbpyrlvl=3, f
     h, w = prev_img.shape
     return fb_klt_tracking(klt_build_pyramid(prev_img, levels), klt_build_pyramid(cur_img, levels), w, h, levels, kps, priors, win,
                            nbpyrlvl, ferr, max_fbklt_dist)
+
+
+def filter_outliers(keys, has_mp, mp_world, Rcw, tcw, K, F_THRESHOLD, fundamental=None):
+    """ORBmatcher::FilterOutliers (reference src/ORBmatcher.cc:208-246), statement by statement.  Returns (inliers,
+    mvbOutlier).  As in the reference, the status of the j-th point handed to findFundamentalMat is written to
+    mvbOutlier[j] -- the position in the filtered list, not the keypoint's own index (:237-240)."""
+    import cv2
+    f32 = np.float32
+    fx, fy, cx, cy = (f32(v) for v in K)
+    R = np.asarray(Rcw, f32).reshape(3, 3); t = np.asarray(tcw, f32).reshape(3)
+    keys = np.asarray(keys, f32).reshape(-1, 2)
+    outlier = np.zeros(len(keys), bool)
+    un_cur, un_forw = [], []
+    for i in range(len(keys)):
+        if not has_mp[i]:
+            continue
+        outlier[i] = False
+        x = np.asarray(mp_world[i], f32)
+        xc = f32(f32(f32(R[0, 0] * x[0]) + f32(R[0, 1] * x[1])) + f32(R[0, 2] * x[2])) + t[0]
+        yc = f32(f32(f32(R[1, 0] * x[0]) + f32(R[1, 1] * x[1])) + f32(R[1, 2] * x[2])) + t[1]
+        zc = f32(f32(f32(R[2, 0] * x[0]) + f32(R[2, 1] * x[1])) + f32(R[2, 2] * x[2])) + t[2]
+        with np.errstate(divide="ignore"):
+            invzc = f32(np.float64(1.0) / np.float64(zc))
+        if invzc < 0:
+            continue
+        # Pinhole::project(const Eigen::Vector3f&) (CameraModels/Pinhole.cpp:43-49): fx * x / z + cx, left to right in float32
+        un_forw.append((keys[i][0], keys[i][1]))
+        un_cur.append((f32(f32(f32(fx * xc) / zc) + cx), f32(f32(f32(fy * yc) / zc) + cy)))
+    inliers = 0
+    if len(un_cur) > 8:
+        if fundamental is None:
+            _, st = cv2.findFundamentalMat(np.array(un_cur, f32), np.array(un_forw, f32), cv2.FM_RANSAC, float(F_THRESHOLD), 0.99)
+            st = None if st is None else st.ravel()
+        else:
+            st = fundamental(np.array(un_cur, f32), np.array(un_forw, f32), F_THRESHOLD)
+        if st is not None:
+            for j in range(len(st)):
+                if not st[j]:
+                    outlier[j] = True
+                else:
+                    inliers += 1
+    return inliers, outlier

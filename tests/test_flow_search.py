@@ -63,3 +63,18 @@ def test_everything_rejected_and_empty_inputs():
     n, ids, pts = search_by_projection_with_of(O.fb_klt_tracking_images, cur, last, np.zeros(len(last), np.int32), X, R, t, K,
                                                BOUNDS, fr[0], fr[1], full)
     assert n == 0
+
+
+def test_filter_outliers_equals_oracle_restatement():
+    from geoflowslam_b200.matcher import filter_outliers
+    from oracle import oracle as O
+    fr, cur, last, state, X, R, t = _scenario(3)
+    has = state == 1
+    n_o, out_o = O.filter_outliers(last, has, X, R, t, K, 1.0)
+    n_p, out_p = filter_outliers(last, has, X, R, t, K, 1.0)
+    assert n_p == n_o and np.array_equal(out_p, out_o)
+    assert 0 < n_p < int(has.sum()) and out_p.any()          # the displaced map points are rejected
+    # at most 8 pairs: no F check, nothing flagged (:233)
+    few = np.zeros(len(last), bool); few[:8] = True
+    n8, out8 = filter_outliers(last, few, X, R, t, K, 1.0)
+    assert n8 == 0 and not out8.any()
