@@ -55,3 +55,22 @@ def test_tum_flavour_and_sparse_imu(tmp_path):
     # frames with fewer than three IMU samples are not tracked (rgbd_inertial.cc:171)
     g = D.frame_measurements(np.array([0.0, 0.1, 0.2]), np.array([0.01, 0.02, 0.03, 0.15, 0.16]))
     assert [x[0] for x in g] == [1]
+
+
+def test_config0_plumbing_chain_from_disk(tmp_path):
+    """configs[0] / [4] plumbing end to end on the CPU: sequence -> disk -> loaders / frame loop -> closed-loop chain on the
+    oracle -> SaveTrajectoryTUM file + ATE (scripts/config0_plumbing.py)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "config0_plumbing", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "config0_plumbing.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    r = mod.run(8, str(tmp_path / "seq"))
+    assert r["ate"] < 2e-3 and r["est"]["n_tracked"][-1] > 0.9 * r["est"]["n_tracked"][0]
+    # the inertial samples came back from imu.txt grouped exactly as they were generated
+    assert [len(b) for b in r["seq"]["imu"]] == [len(b) for b in r["truth"]["imu"]]
+    assert np.allclose(np.concatenate(r["seq"]["imu"])[:, :6], np.concatenate(r["truth"]["imu"])[:, :6], rtol=1e-6, atol=1e-7)
+    assert np.allclose(np.concatenate(r["seq"]["imu"])[:, 6], np.concatenate(r["truth"]["imu"])[:, 6], atol=2e-7)
+    lines = open(r["trajectory"]).read().strip().split("\n")
+    assert len(lines) == 8 and all(len(ln.split()) == 8 for ln in lines)
+    assert abs(float(lines[1].split()[0]) - 1e3 / 30) < 1e-3                 # stamps in ms, 4 decimals (System.cc:1136)
