@@ -99,3 +99,28 @@ class RegistrationGICP:
         n = C.c_int()
         check(self._L.gfs_gicp_get_cloud(self._h, stream, index, ptr(xyz), ptr(cov), self.max_points, C.byref(n)))
         return xyz[:n.value].copy(), cov[:n.value].copy()
+
+
+def predict_state_icp(register, Tcw_last, Tcw_cur, last_points, cur_points, min_points=10, min_inliers=200):
+    """Tracking::PredictStateICP (reference src/Tracking.cc:3364-3413), the tracking thread's caller of
+    RegistrationGICP::RegisterPointClouds, on plain arrays.  `register(target, source, init_T_target_source)` is
+    RegisterPointClouds (the CUDA path: `RegistrationGICP(...).RegisterPointClouds`) and returns its result dict.
+
+    The last frame's cloud is the target, the current frame's the source, the initial guess is Tc1c2 = Tcw_last * Tcw_cur^-1
+    (composed in float32, widened to double).  The result is accepted iff `converged && num_inliers > 200`; then the
+    current pose becomes T_target_source^-1 * Tcw_last (in float32).  Returns dict(ok, Tcw (4,4) float32 -- unchanged
+    if not ok --, delta (4,4) float64 = T_target_source, pos_error = |translation of delta^-1 * Tc1c2|, result)."""
+    f32 = np.float32
+    last_points = np.asarray(last_points, f32).reshape(-1, 4); cur_points = np.asarray(cur_points, f32).reshape(-1, 4)
+    Tl = np.asarray(Tcw_last, f32).reshape(4, 4); Tc = np.asarray(Tcw_cur, f32).reshape(4, 4)
+    if len(cur_points) < min_points or len(last_points) < min_points:                        # :3366-3370
+        return dict(ok=False, Tcw=Tc.copy(), delta=np.eye(4), pos_error=None, result=None)
+    Tc1c2 = (Tl @ np.linalg.inv(Tc)).astype(f32)                                              # :3374-3375
+    res = register(last_points, cur_points, Tc1c2.astype(np.float64))                         # :3377-3381
+    delta = np.asarray(res["T"], np.float64).reshape(4, 4)
+    err = np.linalg.inv(delta) @ Tc1c2.astype(np.float64)                                     # :3387-3391
+    pos_error = float(np.linalg.norm(err[:3, 3]))
+    if res["converged"] and res["num_inliers"] > min_inliers:                                 # :3392
+        Tcw = (np.linalg.inv(delta.astype(f32)) @ Tl).astype(f32)                             # :3393-3395
+        return dict(ok=True, Tcw=Tcw, delta=delta, pos_error=pos_error, result=res)
+    return dict(ok=False, Tcw=Tc.copy(), delta=delta, pos_error=pos_error, result=res)

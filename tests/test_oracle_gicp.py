@@ -117,3 +117,32 @@ def test_align_degenerate_inputs():
     assert r["num_inliers"] == 0 and not np.isnan(r["T"]).any()
     r = O.gicp_align(tgt, tgt)                      # identical clouds: identity, converged at once
     assert r["converged"] and np.allclose(r["T"], np.eye(4), atol=1e-9)
+
+
+def test_predict_state_icp_gating_and_pose_update():
+    """Tracking::PredictStateICP (Tracking.cc:3364-3413) around RegisterPointClouds: target = last cloud, source = current
+    cloud, init = Tcw_last * Tcw_cur^-1, accepted iff converged && num_inliers > 200, new pose = T^-1 * Tcw_last."""
+    from geoflowslam_b200 import synth
+    from geoflowslam_b200.gicp import predict_state_icp
+    from oracle import oracle as O
+    tgt, src, T_true = synth.gicp_pair(2100, n_target=6000)
+    calls = []
+
+    def register(t, s, T0):
+        calls.append((len(t), len(s), np.array(T0)))
+        return O.gicp_align(t, s, T0, threads=2)
+
+    Tl = np.eye(4, dtype=np.float32); Tl[:3, 3] = [0.1, -0.2, 0.05]
+    Tc_guess = Tl.copy()                                             # constant-pose prior: init = identity
+    r = predict_state_icp(register, Tl, Tc_guess, tgt, src)
+    assert calls[0][0] == len(tgt) and calls[0][1] == len(src) and np.allclose(calls[0][2], np.eye(4), atol=1e-6)
+    assert r["ok"] and r["result"]["converged"] and r["result"]["num_inliers"] > 200
+    # T_target_source maps current-camera points into the last camera: Tcw_cur = T^-1 * Tcw_last
+    assert np.allclose(r["Tcw"], np.linalg.inv(r["delta"]) @ Tl.astype(np.float64), atol=1e-5)
+    assert np.allclose(r["delta"], T_true, atol=5e-3) and r["Tcw"].dtype == np.float32
+    assert abs(r["pos_error"] - np.linalg.norm(np.linalg.inv(r["delta"])[:3, 3])) < 1e-6
+    # gates: too few points -> no registration at all; too few inliers -> pose untouched
+    n0 = len(calls)
+    assert not predict_state_icp(register, Tl, Tc_guess, tgt[:9], src)["ok"] and len(calls) == n0
+    few = predict_state_icp(register, Tl, Tc_guess, tgt[:150], src[:150])
+    assert not few["ok"] and np.array_equal(few["Tcw"], Tc_guess)
