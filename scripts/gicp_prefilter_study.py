@@ -37,13 +37,27 @@ def main():
     d2_64 = (d[ok] ** 2)
     f1 = cell_local_f32_d2(T[idx[ok, 0]], S[ok]); f2 = cell_local_f32_d2(T[idx[ok, 1]], S[ok])
     err = np.abs(f1.astype(np.float64) - d2_64[:, 0])
-    tol = 6e-8 * np.sqrt(np.maximum(f1, 0)) + 1e-14            # one-sided bound used by the prefilter
+    A = 1.2 * 2 * np.sqrt(3.0) * 2.0 ** -24 * (2 * CELL + MAXD)  # guaranteed bound: A sqrt(v) + 5e-7 v + 1e-14
+    bound = lambda v: A * np.sqrt(np.maximum(v, 0)) + 5e-7 * v + 1e-14
+    tol = bound(f1.astype(np.float64))
     print("1-NN: float32 cell-local d^2 error: max %.2e, max error / bound %.3f (must be < 1)" % (err.max(), (err / tol).max()))
-    ambiguous = (f2.astype(np.float64) - tol) <= (f1.astype(np.float64) + tol)
+    ambiguous = (f2.astype(np.float64) - bound(f2.astype(np.float64))) <= (f1.astype(np.float64) + tol)
     print("1-NN: queries whose runner-up falls inside the bound (need the exact fp64 comparison): %d of %d = %.4f %%; "
           "warps of 32 consecutive queries with at least one: %.2f %%" %
           (ambiguous.sum(), ok.sum(), 100.0 * ambiguous.mean(),
            100.0 * np.mean([ambiguous[i:i + 32].any() for i in range(0, len(ambiguous), 32)])))
+    # emulation of the decision the kernel makes (`k_nn_corr_f32` on the git branch r2-gicp-f32-prefilter: compiled and emulated here, not yet run on a GPU): best / runner-up by
+    # float32 value among the 8 exact nearest (a superset of everything that matters), clear winner <=> runner-up's lower
+    # bound above the best's upper bound; every clear winner must be the exact nearest neighbour
+    d8, i8 = tree.query(S[ok], k=8)
+    v8 = np.stack([cell_local_f32_d2(T[i8[:, j]], S[ok]) for j in range(8)], 1).astype(np.float64)
+    order = np.argsort(v8, 1, kind="stable")
+    b1 = np.take_along_axis(v8, order[:, :1], 1)[:, 0]; b2 = np.take_along_axis(v8, order[:, 1:2], 1)[:, 0]
+    id1 = np.take_along_axis(i8, order[:, :1], 1)[:, 0]
+    clear = (b2 - bound(b2)) > (b1 + bound(b1))
+    wrong = clear & (id1 != i8[:, 0])
+    print("1-NN decision emulation: clear winners %.4f %%, of which not the exact nearest neighbour: %d (must be 0)" %
+          (100.0 * clear.mean(), int(wrong.sum())))
     # candidates a 27-cell scan looks at vs. what a search pruned by the final distance needs
     cells = np.floor(T / CELL).astype(np.int64)
     key = (cells[:, 0] + 512) | ((cells[:, 1] + 512) << 20) | ((cells[:, 2] + 512) << 40)
@@ -99,7 +113,7 @@ def main():
     dk, ik = tree.query(T[::8], k=K + 7)
     q = T[::8]
     up = np.stack([cell_local_f32_d2(T[ik[:, j]], q) for j in range(K + 7)], 1).astype(np.float64)
-    up = up + 6e-8 * np.sqrt(np.maximum(up, 0)) + 1e-14
+    up = up + bound(up)
     rho = np.sort(up, 1)[:, K - 1]                               # k-th smallest upper bound >= true k-th distance
     n_in = ((dk ** 2) <= rho[:, None]).sum(1)
     print("10-NN: exact candidates inside the float32-derived radius: mean %.3f, max %d (list capacity 16); queries with more "
