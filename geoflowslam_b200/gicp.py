@@ -124,3 +124,36 @@ def predict_state_icp(register, Tcw_last, Tcw_cur, last_points, cur_points, min_
         Tcw = (np.linalg.inv(delta.astype(f32)) @ Tl).astype(f32)                             # :3393-3395
         return dict(ok=True, Tcw=Tcw, delta=delta, pos_error=pos_error, result=res)
     return dict(ok=False, Tcw=Tc.copy(), delta=delta, pos_error=pos_error, result=res)
+
+
+def local_ba_icp_edges(register, kf_Tcw, kf_prev, kf_matches_inliers, kf_points, min_inliers=400, max_mean_error=0.01,
+                       max_delta_xy=0.1, max_matches=75):
+    """The EdgeICP block of Optimizer::LocalInertialBA (reference src/Optimizer.cc:3262-3318), the local-mapping thread's
+    caller of RegisterPointClouds, on plain arrays: for every optimizable keyframe i with a predecessor and at most 75
+    tracked inliers, register its cloud (source) against the predecessor's (target) starting from
+    Tcjci = Tcw[prev] * Tcw[i]^-1 and keep the result as an edge iff it converged, has more than 400 inliers, a mean
+    error below 0.01 and moved the initial guess by less than 0.1 m in x-y.
+
+    kf_Tcw (n,4,4); kf_prev[i] = index of the predecessor in the same arrays or -1; kf_points[i] = (m,4) float32 cloud.
+    Returns the arrays of the BA problem: dict(n_icp, icp_kf1 (predecessor), icp_kf2 (keyframe), icp_Rt (n_icp,12) =
+    [R row-major | t] of T_target_source), plus `results` (one RegisterPointClouds result per attempted keyframe)."""
+    T = np.asarray(kf_Tcw, np.float64).reshape(-1, 4, 4)
+    kf1, kf2, Rt, results = [], [], [], []
+    for i in range(len(T)):
+        if kf_matches_inliers[i] > max_matches:                                               # :3266
+            continue
+        j = int(kf_prev[i])
+        if j < 0:                                                                             # :3282
+            continue
+        Tcjci = T[j] @ np.linalg.inv(T[i])                                                    # :3267-3275 (Sim3 with s = 1)
+        res = register(np.asarray(kf_points[j], np.float32), np.asarray(kf_points[i], np.float32), Tcjci)   # :3291-3292
+        results.append((i, res))
+        rel = np.asarray(res["T"], np.float64).reshape(4, 4)
+        delta = rel @ np.linalg.inv(Tcjci)                                                    # :3294
+        delta_dist = float(np.float32(np.sqrt(delta[0, 3] * delta[0, 3] + delta[1, 3] * delta[1, 3])))    # :3295-3298
+        if (res["converged"] and res["num_inliers"] > min_inliers and res["error"] / res["num_inliers"] < max_mean_error
+                and delta_dist < max_delta_xy):                                               # :3299-3300
+            kf1.append(j); kf2.append(i)
+            Rt.append(np.concatenate([rel[:3, :3].ravel(), rel[:3, 3]]))
+    return dict(n_icp=len(kf1), icp_kf1=np.asarray(kf1, np.int32), icp_kf2=np.asarray(kf2, np.int32),
+                icp_Rt=np.asarray(Rt, np.float64).reshape(-1, 12), results=results)

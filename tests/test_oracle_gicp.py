@@ -146,3 +146,36 @@ def test_predict_state_icp_gating_and_pose_update():
     assert not predict_state_icp(register, Tl, Tc_guess, tgt[:9], src)["ok"] and len(calls) == n0
     few = predict_state_icp(register, Tl, Tc_guess, tgt[:150], src[:150])
     assert not few["ok"] and np.array_equal(few["Tcw"], Tc_guess)
+
+
+def test_local_ba_icp_edges_gating():
+    """The EdgeICP block of LocalInertialBA (Optimizer.cc:3262-3318): which keyframe pairs are registered and which
+    registrations become edges."""
+    from geoflowslam_b200 import synth
+    from geoflowslam_b200.gicp import local_ba_icp_edges
+    from oracle import oracle as O
+    tgt, src, T_true = synth.gicp_pair(2101, n_target=8000)
+    T_true = np.asarray(T_true, np.float64)
+    # three keyframes: 0 has no predecessor, 1 follows 0 (clouds tgt -> src), 2 follows 1 but tracks well (> 75 inliers)
+    T0 = np.eye(4); T1 = np.linalg.inv(T_true) @ T0; T2 = T1.copy()
+    calls = []
+
+    def register(t, s, init):
+        calls.append(np.array(init))
+        return O.gicp_align(t, s, init, threads=2)
+
+    e = local_ba_icp_edges(register, [T0, T1, T2], [-1, 0, 1], [20, 30, 120], [tgt, src, src])
+    assert len(calls) == 1 and np.allclose(calls[0], T0 @ np.linalg.inv(T1), atol=1e-12)   # only keyframe 1 is registered
+    assert e["n_icp"] == 1 and e["icp_kf1"].tolist() == [0] and e["icp_kf2"].tolist() == [1]
+    rel = np.eye(4); rel[:3, :3] = e["icp_Rt"][0, :9].reshape(3, 3); rel[:3, 3] = e["icp_Rt"][0, 9:]
+    assert np.allclose(rel, T_true, atol=5e-3) and np.allclose(rel, e["results"][0][1]["T"])
+    # a bad initial guess that the registration corrects by more than 0.1 m in x-y is not trusted
+    Tbad = T1.copy(); Tbad[0, 3] += 0.09; Tbad[1, 3] -= 0.09
+    e2 = local_ba_icp_edges(register, [T0, Tbad], [-1, 0], [20, 30], [tgt, src])
+    r2 = e2["results"][0][1]
+    d = np.asarray(r2["T"]) @ np.linalg.inv(T0 @ np.linalg.inv(Tbad))
+    expect = bool(r2["converged"] and r2["num_inliers"] > 400 and r2["error"] / r2["num_inliers"] < 0.01
+                  and np.hypot(d[0, 3], d[1, 3]) < 0.1)
+    assert e2["n_icp"] == int(expect)
+    # too few inliers: tiny clouds never make an edge
+    assert local_ba_icp_edges(register, [T0, T1], [-1, 0], [20, 30], [tgt[:300], src[:300]])["n_icp"] == 0
