@@ -69,6 +69,10 @@ SIGNATURES = {
     "gfs_gicp_align": ([vp, vp, vp, ci, vp, ci, vp, vp], ci),
     "gfs_gicp_align_batch": ([vp, vp, vp, vp, vp, vp, ci, ci, vp, vp], ci),
     "gfs_gicp_align_batch_device": ([vp, vp, vp, vp, vp, vp, ci, ci, vp, vp], ci),
+    "gfs_gicp_track_reset": ([vp], ci),
+    "gfs_gicp_track_calls": ([vp], ci),
+    "gfs_gicp_track_batch_device": ([vp, vp, vp, vp, ci, ci, vp, vp], ci),
+    "gfs_gicp_track_batch": ([vp, vp, vp, vp, ci, ci, vp, vp], ci),
     "gfs_gicp_get_cloud": ([vp, vp, ci, vp, vp, ci, vp], ci),
     "gfs_gicp_last_launches": ([vp], ci),
     "gfs_gicp_get_knn_stats": ([vp, vp, ci, vp, vp], ci),

@@ -35,6 +35,12 @@ struct GicpDev {
   int nblk;         // partial-sum blocks per pair
   double voxel, cell, max_dist, rot_eps, trans_eps;
   int k, max_iter;
+  // which clouds a launch works on: cloud(y) = cbase + y * cstep.  align: all 2 * pairs clouds (0, 1); track: only the
+  // new cloud of every sequence (slot, 2).  swap = 0: cloud 2p is the target of pair p and 2p + 1 its source; 1: the
+  // other way round (track mode alternates, so last call's source is this call's target without being rebuilt).
+  int cbase, cstep, swap;
+  int inputAll;     // 1: every cloud's raw points come from the `src` array (track mode); 0: even clouds from `tgt`
+  int cellOrder;    // 1: neighbour-search kernels take their queries in grid-cell order (rec[]), not in point order
   // per cloud (2 * pairs clouds; cloud 2p = target of pair p, 2p+1 = source)
   unsigned long long* keys;  // [clouds][hsize]
   int* minIdx;               // [clouds][hsize]
@@ -52,6 +58,8 @@ struct GicpDev {
   double* pts;               // [clouds][nmax][4]
   uint4* tab;                // [clouds][hsize] kNN grid slot {key lo, key hi, start, count}: one 16-byte probe
   double* rec;               // [clouds][nmax][4] downsampled points in cell order {x, y, z, index bits}
+  float4* recf;              // [clouds][nmax] the same records as float32 RELATIVE TO THEIR CELL's origin {x, y, z, index bits}
+  float nnBoundA;            // error bound of a float32 cell-local squared distance v: nnBoundA * sqrt(v) + 5e-7 * v + 1e-14
   double* cov;               // [clouds][nmax][6]
   // per pair
   int* corr;                 // [pairs][nmax] target index of source point (-1: none)
@@ -67,6 +75,13 @@ struct GicpDev {
 enum { S_T = 0, S_NEWT = 12, S_H = 24, S_B = 45, S_E = 51, S_LAMBDA = 52, S_DELTA = 53, LM_STATE = 60 };
 // per-pair LM state layout (ints)
 enum { I_ACTIVE = 0, I_NEED = 1, I_CONV = 2, I_ITER = 3, I_TRIAL = 4, I_INL = 5, I_INNER = 6, I_SUCCESS = 7, LM_ISTATE = 8 };
+
+__device__ __forceinline__ int cloud_of(const GicpDev& D, int y) { return D.cbase + y * D.cstep; }
+__device__ __forceinline__ int tgt_cloud(const GicpDev& D, int p) { return 2 * p + D.swap; }
+__device__ __forceinline__ int src_cloud(const GicpDev& D, int p) { return 2 * p + 1 - D.swap; }
+__device__ __forceinline__ const float* raw_points(const GicpDev& D, int c, const float* tgt, const float* src, int stride) {
+  return ((D.inputAll || (c & 1)) ? src : tgt) + (size_t)(c >> 1) * stride * 4;
+}
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
@@ -91,23 +106,24 @@ __global__ void k_group_clear(GicpDev D, int clouds) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n = (long long)clouds * D.hsize;
   if (i < n) {
-    D.keys[i] = KEY_EMPTY;
-    D.minIdx[i] = 0x7fffffff;
-    D.count[i] = 0;
-    D.cursor[i] = 0;
+    const size_t j = (size_t)cloud_of(D, (int)(i / D.hsize)) * D.hsize + (size_t)(i % D.hsize);
+    D.keys[j] = KEY_EMPTY;
+    D.minIdx[j] = 0x7fffffff;
+    D.count[j] = 0;
+    D.cursor[j] = 0;
   }
-  if (i < (long long)clouds * 6) D.cellBox[i] = ((i % 6) < 3) ? 0x7fffffff : -0x7fffffff;
+  if (i < (long long)clouds * 6) D.cellBox[cloud_of(D, (int)(i / 6)) * 6 + (i % 6)] = ((i % 6) < 3) ? 0x7fffffff : -0x7fffffff;
 }
 
 // mode 0: keys of the raw float4 input points, voxel leaf; mode 1: keys of the downsampled points, grid cell
 __global__ void __launch_bounds__(256) k_group_insert(GicpDev D, int mode, const float* __restrict__ tgt,
                                                       const float* __restrict__ src, int stride) {
-  const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = cloud_of(D, blockIdx.y), i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = mode == 0 ? D.nIn[c] : D.nDown[c];
   if (i >= n) return;
   double x, y, z, inv;
   if (mode == 0) {
-    const float* p = ((c & 1) ? src : tgt) + ((size_t)(c >> 1) * stride + i) * 4;
+    const float* p = raw_points(D, c, tgt, src, stride) + (size_t)i * 4;
     const float4 v = *reinterpret_cast<const float4*>(p);
     x = (double)v.x; y = (double)v.y; z = (double)v.z;
     inv = 1.0 / D.voxel;
@@ -145,7 +161,7 @@ __global__ void __launch_bounds__(256) k_group_insert(GicpDev D, int mode, const
 __global__ void __launch_bounds__(1024) k_group_rank(GicpDev D, int mode, int* __restrict__ nGroups) {
   __shared__ int s_a[32], s_b[32];
   __shared__ int s_ca, s_cb;
-  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = cloud_of(D, blockIdx.x), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = mode == 0 ? D.nIn[c] : D.nDown[c];
   const int* slotOf = D.slotOf + (size_t)c * D.nmax;
   const size_t hb = (size_t)c * D.hsize;
@@ -189,7 +205,7 @@ __global__ void __launch_bounds__(1024) k_group_rank(GicpDev D, int mode, int* _
 // Append every point to its group's member list.  The order inside a group is whatever the atomics give:
 // the voxel mean sorts its (short) list back into input order, the k-NN grid does not depend on it.
 __global__ void __launch_bounds__(256) k_group_fill(GicpDev D, int mode) {
-  const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = cloud_of(D, blockIdx.y), i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = mode == 0 ? D.nIn[c] : D.nDown[c];
   if (i >= n) return;
   const int slot = D.slotOf[(size_t)c * D.nmax + i];
@@ -233,13 +249,13 @@ __device__ void sort_members(int* m, int n) {
 // voxelgrid_sampling: mean of each voxel's points, summed in input order (downsampling.hpp:60-75)
 __global__ void __launch_bounds__(256) k_voxel_mean(GicpDev D, const float* __restrict__ tgt, const float* __restrict__ src,
                                                     int stride) {
-  const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = cloud_of(D, blockIdx.y), i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= D.nIn[c]) return;
   const int slot = D.slotOf[(size_t)c * D.nmax + i];
   if (slot < 0) return;
   const size_t hb = (size_t)c * D.hsize;
   if (D.minIdx[hb + slot] != i) return;
-  const float* base = ((c & 1) ? src : tgt) + (size_t)(c >> 1) * stride * 4;
+  const float* base = raw_points(D, c, tgt, src, stride);
   int* mem = D.members + (size_t)c * D.nmax + D.start[hb + slot];
   const int cnt = D.count[hb + slot];
   sort_members(mem, cnt);
@@ -254,16 +270,18 @@ __global__ void __launch_bounds__(256) k_voxel_mean(GicpDev D, const float* __re
 
 // ---- k-NN grid: packed slot table + points stored in cell order
 __global__ void __launch_bounds__(256) k_cell_pack(GicpDev D, int clouds) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < (long long)clouds * D.hsize) {
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 < (long long)clouds * D.hsize) {
+    const size_t cb = (size_t)cloud_of(D, (int)(i0 / D.hsize)) * D.hsize, i = cb + (size_t)(i0 % D.hsize);
     const unsigned long long k = D.keys[i];
     D.tab[i] = make_uint4((unsigned)k, (unsigned)(k >> 32), (unsigned)D.start[i], (unsigned)D.count[i]);
     // occupied cells in first-occurrence order -> slot (the fill cursors are dead by now: reuse their storage)
-    if (k != KEY_EMPTY) D.cursor[(i / D.hsize) * D.hsize + D.rank[i]] = (int)(i % D.hsize);
+    if (k != KEY_EMPTY) D.cursor[cb + D.rank[i]] = (int)(i0 % D.hsize);
   }
-  if (i < clouds) D.nFall[i] = 0;
-  if (i < (long long)clouds * D.nmax) {
-    const int c = (int)(i / D.nmax), m = (int)(i % D.nmax);
+  if (i0 < clouds) D.nFall[cloud_of(D, (int)i0)] = 0;
+  if (i0 < (long long)clouds * D.nmax) {
+    const int c = cloud_of(D, (int)(i0 / D.nmax)), m = (int)(i0 % D.nmax);
+    const size_t i = (size_t)c * D.nmax + m;
     if (m < D.nDown[c]) {
       const int pi = D.members[i];
       const double2* p = reinterpret_cast<const double2*>(D.pts + ((size_t)c * D.nmax + pi) * 4);
@@ -271,6 +289,12 @@ __global__ void __launch_bounds__(256) k_cell_pack(GicpDev D, int clouds) {
       const double2 xy = p[0];
       o[0] = xy;
       o[1] = make_double2(p[1].x, __longlong_as_double((long long)pi));
+      // float32 copy relative to the origin of the record's own cell (|.| < cell: 6e-9 m of rounding at cell = 0.1 m);
+      // the same floor as point_key, so the origin is the one a search computes from the cell it visits
+      const double inv = 1.0 / D.cell;
+      const double ox = (double)fast_floor_d(xy.x * inv) * D.cell, oy = (double)fast_floor_d(xy.y * inv) * D.cell,
+                   oz = (double)fast_floor_d(p[1].x * inv) * D.cell;
+      D.recf[i] = make_float4((float)(xy.x - ox), (float)(xy.y - oy), (float)(p[1].x - oz), __int_as_float(pi));
     }
   }
 }
@@ -278,6 +302,7 @@ __global__ void __launch_bounds__(256) k_cell_pack(GicpDev D, int clouds) {
 struct Grid {
   const uint4* tab;
   const double2* rec;
+  const float4* recf;
   const double* pts;
   int hm;
 };
@@ -285,6 +310,7 @@ __device__ __forceinline__ Grid make_grid(const GicpDev& D, int c) {
   Grid g;
   g.tab = D.tab + (size_t)c * D.hsize;
   g.rec = reinterpret_cast<const double2*>(D.rec + (size_t)c * D.nmax * 4);
+  g.recf = D.recf + (size_t)c * D.nmax;
   g.pts = D.pts + (size_t)c * D.nmax * 4;
   g.hm = D.hsize - 1;
   return g;
@@ -709,7 +735,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_cov(GicpDev D, int use_l
   double* s_d = reinterpret_cast<double*>(s_knn);
   unsigned* s_cells = reinterpret_cast<unsigned*>(s_d + KNN_LIST * KNN_THREADS);
   int* s_id = reinterpret_cast<int*>(s_cells + KNN_CELLS * KNN_THREADS);
-  const int c = blockIdx.y;
+  const int c = cloud_of(D, blockIdx.y);
   const int nPts = D.nDown[c];
   const int n = use_list ? D.nFall[c] : nPts;
   const int* list = D.slotOf + (size_t)c * D.nmax;
@@ -717,9 +743,20 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_cov(GicpDev D, int use_l
   for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
     const int t = base + threadIdx.x;
     const bool active = t < n;
-    const int i = active ? (use_list ? list[t] : t) : 0;
-    const double* q = g.pts + (size_t)i * 4;
-    const double qx = q[0], qy = q[1], qz = q[2];
+    int i = active ? (use_list ? list[t] : t) : 0;
+    double qx, qy, qz;
+    if (!use_list && D.cellOrder) {
+      // queries in grid-cell order: the lanes of a warp share their home cell (a 0.1 m cell holds about a warp's worth of
+      // points), so they probe the same hash slots and walk the same records -- the loads of a trip hit the same lines
+      // and the per-lane loops have (nearly) the same trip counts.  Every downsampled point has a record: its cell key
+      // is valid because its voxel key was.
+      const double2 a = __ldg(&g.rec[2 * (size_t)i]), b = __ldg(&g.rec[2 * (size_t)i + 1]);
+      qx = a.x; qy = a.y; qz = b.x;
+      i = (int)__double_as_longlong(b.y);
+    } else {
+      const double* q = g.pts + (size_t)i * 4;
+      qx = q[0]; qy = q[1]; qz = q[2];
+    }
     KnnAcc<KNN_K> acc;
     bool finished = true;
     if (active)
@@ -754,7 +791,7 @@ static const size_t KC_SMEM = (size_t)(KC_THREADS / KC_LANES) * KC_STRIDE;
 
 __global__ void __launch_bounds__(KC_THREADS) k_knn_cov_cells(GicpDev D) {
   extern __shared__ __align__(16) unsigned char s_kc[];
-  const int c = blockIdx.y;
+  const int c = cloud_of(D, blockIdx.y);
   const int nCells = D.nCells[c];
   const int grp = threadIdx.x / KC_LANES, gl = threadIdx.x % KC_LANES;
   double* X = reinterpret_cast<double*>(s_kc + (size_t)grp * KC_STRIDE);
@@ -937,7 +974,7 @@ static const int NN_THREADS = 128;
 __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr(GicpDev D, int iter) {
   const int p = blockIdx.y;
   if (!D.istate[p * LM_ISTATE + I_ACTIVE]) return;
-  const int ct = 2 * p, cs = 2 * p + 1;
+  const int ct = tgt_cloud(D, p), cs = src_cloud(D, p);
   const int i = blockIdx.x * NN_THREADS + threadIdx.x;
   if (i >= D.nDown[cs]) return;
   const double* T = D.state + (size_t)p * LM_STATE + S_T;
@@ -971,11 +1008,157 @@ __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr(GicpDev D, int iter) 
   D.corr[(size_t)p * D.nmax + i] = (nn.id != 0x7fffffff && !(nn.d > max_d2)) ? nn.id : -1;  // DistanceRejector: sq_dist > max_dist_sq
 }
 
+// ---- correspondence search, second generation (the default; GFS_GICP_NN=0 selects k_nn_corr above).
+// Same result as k_nn_corr -- the exact nearest target point under (distance, index), or none within
+// max_correspondence_distance -- reached with less work per query:
+//  * queries are taken in the SOURCE cloud's grid-cell order (rec[]): a rigid transform keeps neighbours together,
+//    so the lanes of a warp land in the same one to eight target cells and their probes / record loads hit the same
+//    lines (in point order a warp's queries were strung out along an image row, ~0.6 m, six cells apart);
+//  * the search region is the ball around the query whose radius is the best distance so far (the previous
+//    iteration's correspondence seeds it: ~1 cm once the clouds are roughly aligned).  The home cell is scanned
+//    first, then only the cells whose index range the ball reaches -- typically one to three more -- instead of
+//    testing all 26 neighbours of shell 1 one by one;
+//  * F32 = true: the scan runs on the float32 cell-local records (one 16-byte load and six float operations per
+//    record instead of two loads and eight double operations) and keeps best + runner-up.  With the guaranteed
+//    one-sided error bound nn_bound() the cells it visits are a superset of the exact search's; if the runner-up is
+//    provably farther than the best, the best IS the exact nearest neighbour and its exact fp64 distance feeds the
+//    rejection test; otherwise (about 1 query in 40 000) the lane repeats the search in fp64.
+// Exactness of the region: a target point closer than `lim` lies in a cell whose lower bound axis_gap2 (shrunk by
+// 1e-6 relative + 1e-12 against rounding in the cell assignment) does not exceed lim, and whose index is inside
+// [floor((f - R) / cell), floor((f + R) / cell)] per axis for R = sqrt(lim) inflated the same way.
+//
+// Error bound of the float32 distance (scripts/gicp_prefilter_study.py measures it): a record's coordinates are below
+// `cell`, a visited cell's origin is within max_dist + cell of the query per axis, each is rounded once (relative
+// 2^-24), and d(d^2) = 2 sum |d_c| e_c plus the roundings of the float products and sums (< 5 * 2^-24 d^2):
+//     bound(v) = A * sqrt(v) + 5e-7 * v + 1e-14,   A = 1.2 * 2 sqrt(3) 2^-24 (2 cell + max_dist)   (20 % of slack)
+__device__ __forceinline__ float nn_bound(float v, float A) { return A * sqrtf(v) + 5e-7f * v + 1e-14f; }
+
+struct Nn1f {
+  float v1, v2;
+  int id1;
+};
+__device__ __forceinline__ void scan_cell_nn1f(const Grid& g, int s, int n, float qx, float qy, float qz, Nn1f& nn) {
+  for (int j = 0; j < n; j += 4) {
+    float4 f[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) f[u] = __ldg(&g.recf[s + min(j + u, n - 1)]);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (j + u >= n) break;
+      const int idx = __float_as_int(f[u].w);
+      if (idx == nn.id1) continue;  // the seed (or the current best) met again: its fp32 twin must not become the runner-up
+      const float dx = f[u].x - qx, dy = f[u].y - qy, dz = f[u].z - qz;
+      const float v = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      if (v < nn.v1) { nn.v2 = nn.v1; nn.v1 = v; nn.id1 = idx; }
+      else if (v < nn.v2) nn.v2 = v;
+    }
+  }
+}
+
+// cells the ball of squared radius limit() around the query reaches, home cell first; limit() may shrink while visiting
+template <class Limit, class Visit>
+__device__ __forceinline__ void visit_ball(const Grid& g, const int* box, const ShellQuery& q, Limit limit, Visit visit) {
+  {
+    int cs, cn;
+    if (grid_find(g, q.cx, q.cy, q.cz, cs, cn)) visit(cs, cn, q.cx, q.cy, q.cz);
+  }
+  const double lim0 = limit();
+  if (lim0 <= q.margin * q.margin) return;  // the ball stays inside the home cell
+  const double R = sqrt(lim0) * 1.000001 + 1e-12, inv = 1.0 / q.cell;
+  const int x0 = max(q.cx + fast_floor_d((q.fx - R) * inv), box[0]), x1 = min(q.cx + fast_floor_d((q.fx + R) * inv), box[3]);
+  const int y0 = max(q.cy + fast_floor_d((q.fy - R) * inv), box[1]), y1 = min(q.cy + fast_floor_d((q.fy + R) * inv), box[4]);
+  const int z0 = max(q.cz + fast_floor_d((q.fz - R) * inv), box[2]), z1 = min(q.cz + fast_floor_d((q.fz + R) * inv), box[5]);
+  for (int z = z0; z <= z1; z++) {
+    const double gz2 = axis_gap2(z - q.cz, q.fz, q.cell);
+    if (gz2 > limit()) continue;
+    for (int y = y0; y <= y1; y++) {
+      const double gyz2 = gz2 + axis_gap2(y - q.cy, q.fy, q.cell);
+      if (gyz2 > limit()) continue;
+      for (int x = x0; x <= x1; x++) {
+        if (x == q.cx && y == q.cy && z == q.cz) continue;
+        if (gyz2 + axis_gap2(x - q.cx, q.fx, q.cell) > limit()) continue;
+        int cs, cn;
+        if (grid_find(g, x, y, z, cs, cn)) visit(cs, cn, x, y, z);
+      }
+    }
+  }
+}
+
+template <bool F32>
+__global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr2(GicpDev D, int iter) {
+  const int p = blockIdx.y;
+  if (!D.istate[p * LM_ISTATE + I_ACTIVE]) return;
+  const int ct = tgt_cloud(D, p), cs = src_cloud(D, p);
+  const int t = blockIdx.x * NN_THREADS + threadIdx.x;
+  if (t >= D.nDown[cs]) return;
+  const double* T = D.state + (size_t)p * LM_STATE + S_T;
+  int i = t;
+  double ps[3];
+  if (D.cellOrder) {
+    const double2* rs = reinterpret_cast<const double2*>(D.rec + ((size_t)cs * D.nmax + t) * 4);
+    const double2 a = __ldg(&rs[0]), b = __ldg(&rs[1]);
+    ps[0] = a.x; ps[1] = a.y; ps[2] = b.x;
+    i = (int)__double_as_longlong(b.y);
+  } else {
+    const double* pp = D.pts + ((size_t)cs * D.nmax + t) * 4;
+    ps[0] = pp[0]; ps[1] = pp[1]; ps[2] = pp[2];
+  }
+  double q[3];
+  xform(T, ps, q);
+  const Grid g = make_grid(D, ct);
+  const double max_d2 = D.max_dist * D.max_dist;
+  const double cap = max_d2 * 1.0000001;
+  const int prev = iter > 0 ? D.corr[(size_t)p * D.nmax + i] : -1;
+  const ShellQuery sq = make_shell_query(D.cell, q[0], q[1], q[2]);
+  const int* box = D.cellBox + ct * 6;
+  int id = 0x7fffffff;
+  double d = DBL_MAX;
+  bool exact = !F32;
+  if (F32) {
+    const double capf = cap * 1.000001 + 1e-12;  // pruning cap of the float32 pass: never tighter than the exact one
+    Nn1f nf;
+    nf.v1 = FLT_MAX; nf.v2 = FLT_MAX; nf.id1 = 0x7fffffff;
+    if (prev >= 0) {
+      // seed: an upper bound of the exact distance to the previous correspondence
+      nf.v1 = __double2float_ru(sqdist3(g.pts + (size_t)prev * 4, q[0], q[1], q[2]));
+      nf.id1 = prev;
+    }
+    auto ub = [&]() -> double { return nf.v1 < FLT_MAX ? (double)nf.v1 + (double)nn_bound(nf.v1, D.nnBoundA) : DBL_MAX; };
+    const int off = 1 << 20;
+    visit_ball(g, box, sq, [&]() { return fmin(ub(), capf); },
+               [&](int cs_, int cn_, int x, int y, int z) {
+                 const float qx = (float)(q[0] - (double)(x - off) * D.cell), qy = (float)(q[1] - (double)(y - off) * D.cell),
+                             qz = (float)(q[2] - (double)(z - off) * D.cell);
+                 scan_cell_nn1f(g, cs_, cn_, qx, qy, qz, nf);
+               });
+    // the best is the exact nearest neighbour iff no other candidate can be as close: the runner-up's lower bound is
+    // above the best's upper bound (a seed that was never beaten carries an exact upper bound already)
+    const bool clear_winner = nf.id1 != 0x7fffffff &&
+                              (nf.v2 == FLT_MAX || (double)nf.v2 - (double)nn_bound(nf.v2, D.nnBoundA) > (double)nf.v1 + (double)nn_bound(nf.v1, D.nnBoundA));
+    if (clear_winner) {
+      id = nf.id1;
+      d = sqdist3(g.pts + (size_t)id * 4, q[0], q[1], q[2]);
+    } else if (nf.id1 != 0x7fffffff) {
+      exact = true;  // ambiguous: redo this query in fp64
+    }
+  }
+  if (exact) {
+    Nn1 nn;
+    nn.d = DBL_MAX; nn.id = 0x7fffffff;
+    // the previous iteration's correspondence is a real target point: starting from it only tightens the radius
+    if (prev >= 0) nn.push(prev, sqdist3(g.pts + (size_t)prev * 4, q[0], q[1], q[2]));
+    visit_ball(g, box, sq, [&]() { return fmin(nn.d, cap); },
+               [&](int cs_, int cn_, int, int, int) { scan_cell_nn1(g, cs_, cn_, q[0], q[1], q[2], nn); });
+    id = nn.id; d = nn.d;
+  }
+  D.corr[(size_t)p * D.nmax + i] = (id != 0x7fffffff && !(d > max_d2)) ? id : -1;  // DistanceRejector: sq_dist > max_dist_sq
+}
+
 // GICPFactor::linearize for every source point of every active pair + partial sums
 __global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D, int iter) {
   const int p = blockIdx.y;
   if (!D.istate[p * LM_ISTATE + I_ACTIVE]) return;
-  const int ct = 2 * p, cs = 2 * p + 1;
+  const int ct = tgt_cloud(D, p), cs = src_cloud(D, p);
   const int ns = D.nDown[cs];
   const int i = blockIdx.x * LIN_THREADS + threadIdx.x;
   double acc[RED_N];
@@ -1060,7 +1243,7 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D, int iter) 
 __global__ void __launch_bounds__(LIN_THREADS) k_error(GicpDev D) {
   const int p = blockIdx.y;
   if (!D.istate[p * LM_ISTATE + I_NEED]) return;
-  const int ct = 2 * p, cs = 2 * p + 1;
+  const int ct = tgt_cloud(D, p), cs = src_cloud(D, p);
   const int ns = D.nDown[cs];
   const int i = blockIdx.x * LIN_THREADS + threadIdx.x;
   double acc[1] = {0.0};
@@ -1180,7 +1363,7 @@ __global__ void __launch_bounds__(LIN_THREADS) k_lm_begin(GicpDev D, int iter) {
   if (!is[I_ACTIVE]) return;
   double* st = D.state + (size_t)p * LM_STATE;
   // fixed-order sum of the per-warp partials: thread t takes partials t, t+128, ...; then lanes, then warps
-  const int nw = ((D.nDown[2 * p + 1] + LIN_THREADS - 1) / LIN_THREADS) * (LIN_THREADS / 32);
+  const int nw = ((D.nDown[src_cloud(D, p)] + LIN_THREADS - 1) / LIN_THREADS) * (LIN_THREADS / 32);
   double acc[RED_N];
 #pragma unroll
   for (int k = 0; k < RED_N; k++) acc[k] = 0.0;
@@ -1215,7 +1398,7 @@ __global__ void __launch_bounds__(32) k_lm_decide(GicpDev D, int iter) {
   int* is = D.istate + p * LM_ISTATE;
   if (!is[I_NEED]) return;
   double* st = D.state + (size_t)p * LM_STATE;
-  const int nb = (D.nDown[2 * p + 1] + LIN_THREADS - 1) / LIN_THREADS;
+  const int nb = (D.nDown[src_cloud(D, p)] + LIN_THREADS - 1) / LIN_THREADS;
   // fixed-order sum: lane-strided partial sums are NOT order-preserving, so lane 0 sums serially
   double new_e = 0;
   if (lane == 0) {
@@ -1271,17 +1454,24 @@ __global__ void k_gicp_result(GicpDev D, int pairs, GfsGicpResult* __restrict__ 
   r.iterations = is[I_ITER];
   r.num_inliers = is[I_INL];
   r.converged = is[I_CONV];
-  r.n_target = D.nDown[2 * p];
-  r.n_source = D.nDown[2 * p + 1];
+  r.n_target = D.nDown[tgt_cloud(D, p)];
+  r.n_source = D.nDown[src_cloud(D, p)];
   r.inner_evals = is[I_INNER];
   out[p] = r;
 }
 
-__global__ void k_set_counts(GicpDev D, int pairs, const int* __restrict__ nt, const int* __restrict__ ns) {
+// per-cloud input counts, clamped to [0, stride]: a count beyond the batch stride would make the grouping kernels read
+// the next pair's cloud.  nt == nullptr (track mode): only the new cloud of every sequence, cloud 2p + cbase.
+__global__ void k_set_counts(GicpDev D, int pairs, const int* __restrict__ nt, const int* __restrict__ ns, int stride) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= pairs) return;
-  D.nIn[2 * p] = min(nt[p], D.nmax);
-  D.nIn[2 * p + 1] = min(ns[p], D.nmax);
+  const int lim = min(stride, D.nmax);
+  if (nt) {
+    D.nIn[2 * p] = min(max(nt[p], 0), lim);
+    D.nIn[2 * p + 1] = min(max(ns[p], 0), lim);
+  } else {
+    D.nIn[2 * p + D.cbase] = min(max(ns[p], 0), lim);
+  }
 }
 
 }  // namespace gfs
@@ -1291,12 +1481,15 @@ using namespace gfs;
 struct GfsGicp {
   GicpDev dev;
   int maxPairs = 0;
-  DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_nFall, b_box, b_pts, b_cov, b_tab, b_rec,
+  DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_nFall, b_box, b_pts, b_cov, b_tab, b_rec, b_recf,
       b_corr, b_maha, b_partial, b_partialE, b_state, b_istate, b_counters;
   DevBuf b_tgt, b_src, b_n, b_T0, b_res;
   PinnedBuf h_counters;
   int launches = 0;
   bool cellKnn = false;  // GFS_GICP_KNN_CELLS=1: cell-centric 10-NN kernel first (same results)
+  int nnMode = 2;        // GFS_GICP_NN: 0 = k_nn_corr (shell walk), 1 = k_nn_corr2 in fp64, 2 = k_nn_corr2 with the float32 prefilter
+  int trackCalls = 0;    // gfs_gicp_track_*: calls since the last reset (the new cloud goes to slot trackCalls & 1)
+  int trackSeqs = 0;
 };
 
 extern "C" {
@@ -1344,6 +1537,11 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
     if (v > 0) D.cell = v;
   }
   D.max_dist = s.max_correspondence_distance;
+  D.nnBoundA = (float)(1.2 * 2.0 * 1.7320508 * 5.9604645e-8 * (2.0 * D.cell + s.max_correspondence_distance));
+  D.cbase = 0; D.cstep = 1; D.swap = 0; D.inputAll = 0;
+  D.cellOrder = 1;
+  if (const char* e = getenv("GFS_GICP_ORDER")) D.cellOrder = atoi(e) != 0;  // 0: queries in point order (first generation)
+  if (const char* e = getenv("GFS_GICP_NN")) h->nnMode = atoi(e);
   D.rot_eps = s.rotation_eps;
   D.trans_eps = s.translation_eps;
   D.k = s.num_neighbors;
@@ -1374,6 +1572,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   RES(b_cov, C * N * 48, cov, double*)
   RES(b_tab, C * H * 16, tab, uint4*)
   RES(b_rec, C * N * 32, rec, double*)
+  RES(b_recf, C * N * 16, recf, float4*)
   RES(b_corr, P * N * 4, corr, int*)
   RES(b_maha, P * N * 72, maha, double*)
   RES(b_partial, P * D.nblk * (LIN_THREADS / 32) * RED_N * 8, partial, double*)
@@ -1390,7 +1589,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
 int gfs_gicp_destroy(GfsGicp* h) {
   if (!h) return GFS_OK;
   DevBuf* d[] = {&h->b_keys, &h->b_minIdx, &h->b_count, &h->b_start, &h->b_cursor, &h->b_rank, &h->b_slotOf, &h->b_members,
-                 &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_nFall, &h->b_box, &h->b_pts, &h->b_cov, &h->b_tab, &h->b_rec, &h->b_corr, &h->b_maha, &h->b_partial,
+                 &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_nFall, &h->b_box, &h->b_pts, &h->b_cov, &h->b_tab, &h->b_rec, &h->b_recf, &h->b_corr, &h->b_maha, &h->b_partial,
                  &h->b_partialE, &h->b_state, &h->b_istate, &h->b_counters, &h->b_tgt, &h->b_src, &h->b_n, &h->b_T0, &h->b_res};
   for (DevBuf* b : d) b->release();
   h->h_counters.release();
@@ -1400,9 +1599,8 @@ int gfs_gicp_destroy(GfsGicp* h) {
 
 int gfs_gicp_last_launches(const GfsGicp* h) { return h ? h->launches : GFS_ERR_INVALID; }
 
-static int group_build(GfsGicp* h, cudaStream_t st, int mode, int clouds, const float* tgt, const float* src, int stride,
-                       int* nGroupsOut) {
-  const GicpDev& D = h->dev;
+static int group_build(GfsGicp* h, const GicpDev& D, cudaStream_t st, int mode, int clouds, const float* tgt, const float* src,
+                       int stride, int* nGroupsOut) {
   const long long slots = (long long)clouds * D.hsize;
   k_group_clear<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(D, clouds);
   k_group_insert<<<dim3(div_up(D.nmax, 256), clouds), 256, 0, st>>>(D, mode, tgt, src, stride);
@@ -1412,21 +1610,13 @@ static int group_build(GfsGicp* h, cudaStream_t st, int mode, int clouds, const 
   return GFS_OK;
 }
 
-int gfs_gicp_align_batch_device(GfsGicp* h, void* stream, const float* d_target, const int* d_nt, const float* d_source,
-                                const int* d_ns, int pairs, int stride, const double* d_T0, GfsGicpResult* d_out) {
-  GFS_REQUIRE(h, GFS_ERR_INVALID, "null handle");
-  GFS_REQUIRE(d_target && d_nt && d_source && d_ns && d_T0 && d_out, GFS_ERR_INVALID, "null pointer");
-  GFS_REQUIRE(pairs > 0 && pairs <= h->maxPairs, GFS_ERR_CAPACITY, "pairs exceeds the handle's max_pairs");
-  GFS_REQUIRE(stride > 0 && stride <= h->dev.nmax, GFS_ERR_CAPACITY, "stride exceeds the handle's max_points");
-  cudaStream_t st = (cudaStream_t)stream;
-  const GicpDev& D = h->dev;
-  const int clouds = 2 * pairs;
-  h->launches = 0;
-  k_set_counts<<<div_up(pairs, 128), 128, 0, st>>>(D, pairs, d_nt, d_ns);
-  group_build(h, st, 0, clouds, d_target, d_source, stride, D.nDown);
+// Voxel downsampling, k-NN grid and covariances of `clouds` clouds (those D.cbase / D.cstep select).
+static int preprocess_clouds(GfsGicp* h, const GicpDev& D, cudaStream_t st, int clouds, const float* d_target, const float* d_source,
+                             int stride) {
+  group_build(h, D, st, 0, clouds, d_target, d_source, stride, D.nDown);
   k_voxel_mean<<<dim3(div_up(D.nmax, 256), clouds), 256, 0, st>>>(D, d_target, d_source, stride);
   // grid over the downsampled points (reuses the hash-table storage); group count is not needed
-  group_build(h, st, 1, clouds, nullptr, nullptr, 0, D.nCells);
+  group_build(h, D, st, 1, clouds, nullptr, nullptr, 0, D.nCells);
   {
     const long long work = (long long)clouds * std::max(D.hsize, D.nmax);
     k_cell_pack<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(D, clouds);
@@ -1440,13 +1630,22 @@ int gfs_gicp_align_batch_device(GfsGicp* h, void* stream, const float* d_target,
     k_knn_cov<<<dim3(8, clouds), KNN_THREADS, KNN_SMEM, st>>>(D, 1);
     h->launches += 1;
   }
-  k_lm_init<<<div_up(pairs, 128), 128, 0, st>>>(D, pairs, d_T0);
-  h->launches += 5;
+  h->launches += 3;
   GFS_CUDA(cudaGetLastError());
+  return GFS_OK;
+}
+
+// LevenbergMarquardtOptimizer::optimize for every pair (registration/optimizer.hpp:83-148)
+static int optimize_pairs(GfsGicp* h, const GicpDev& D, cudaStream_t st, int pairs, const double* d_T0, GfsGicpResult* d_out) {
+  k_lm_init<<<div_up(pairs, 128), 128, 0, st>>>(D, pairs, d_T0);
+  h->launches += 1;
   int* hc = (int*)h->h_counters.p;
   for (int it = 0; it < D.max_iter; it++) {
     GFS_CUDA(cudaMemsetAsync(D.counters, 0, 8, st));
-    k_nn_corr<<<dim3(div_up(D.nmax, NN_THREADS), pairs), NN_THREADS, 0, st>>>(D, it);
+    const dim3 gn(div_up(D.nmax, NN_THREADS), pairs);
+    if (h->nnMode == 0) k_nn_corr<<<gn, NN_THREADS, 0, st>>>(D, it);
+    else if (h->nnMode == 1) k_nn_corr2<false><<<gn, NN_THREADS, 0, st>>>(D, it);
+    else k_nn_corr2<true><<<gn, NN_THREADS, 0, st>>>(D, it);
     k_linearize<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D, it);
     k_lm_begin<<<pairs, LIN_THREADS, 0, st>>>(D, it);
     h->launches += 3;
@@ -1467,12 +1666,98 @@ int gfs_gicp_align_batch_device(GfsGicp* h, void* stream, const float* d_target,
   return GFS_OK;
 }
 
+int gfs_gicp_align_batch_device(GfsGicp* h, void* stream, const float* d_target, const int* d_nt, const float* d_source,
+                                const int* d_ns, int pairs, int stride, const double* d_T0, GfsGicpResult* d_out) {
+  GFS_REQUIRE(h, GFS_ERR_INVALID, "null handle");
+  GFS_REQUIRE(d_target && d_nt && d_source && d_ns && d_T0 && d_out, GFS_ERR_INVALID, "null pointer");
+  GFS_REQUIRE(pairs > 0 && pairs <= h->maxPairs, GFS_ERR_CAPACITY, "pairs exceeds the handle's max_pairs");
+  GFS_REQUIRE(stride > 0 && stride <= h->dev.nmax, GFS_ERR_CAPACITY, "stride exceeds the handle's max_points");
+  cudaStream_t st = (cudaStream_t)stream;
+  GicpDev D = h->dev;
+  D.cbase = 0; D.cstep = 1; D.swap = 0; D.inputAll = 0;
+  h->trackCalls = 0;  // the clouds of a tracked sequence are overwritten
+  h->launches = 0;
+  k_set_counts<<<div_up(pairs, 128), 128, 0, st>>>(D, pairs, d_nt, d_ns, stride);
+  h->launches += 1;
+  int rc = preprocess_clouds(h, D, st, 2 * pairs, d_target, d_source, stride);
+  if (rc) return rc;
+  return optimize_pairs(h, D, st, pairs, d_T0, d_out);
+}
+
+// ---- tracking mode: one new cloud per sequence and call (Tracking::PredictStateICP, reference src/Tracking.cc:3364-3413,
+// registers the current frame's cloud -- the source -- against the last frame's -- the target).  small_gicp::align
+// preprocesses both clouds on every call (registration_helper.cpp:23-35, 56-68), so a frame's cloud is downsampled,
+// indexed and given covariances twice: once as the source, once more one frame later as the target.  Preprocessing is a
+// function of the cloud alone, so here each cloud is preprocessed ONCE and stays in HBM for the next call; the results
+// are those of gfs_gicp_align_batch on the pairs (cloud[k-1], cloud[k]) bit for bit (tests/test_gpu_gicp.py).
+int gfs_gicp_track_reset(GfsGicp* h) {
+  GFS_REQUIRE(h, GFS_ERR_INVALID, "null handle");
+  h->trackCalls = 0;
+  h->trackSeqs = 0;
+  return GFS_OK;
+}
+
+int gfs_gicp_track_calls(const GfsGicp* h) { return h ? h->trackCalls : GFS_ERR_INVALID; }
+
+int gfs_gicp_track_batch_device(GfsGicp* h, void* stream, const float* d_cloud, const int* d_n, int seqs, int stride,
+                                const double* d_T0, GfsGicpResult* d_out) {
+  GFS_REQUIRE(h, GFS_ERR_INVALID, "null handle");
+  GFS_REQUIRE(d_cloud && d_n, GFS_ERR_INVALID, "null pointer");
+  GFS_REQUIRE(seqs > 0 && seqs <= h->maxPairs, GFS_ERR_CAPACITY, "seqs exceeds the handle's max_pairs");
+  GFS_REQUIRE(stride > 0 && stride <= h->dev.nmax, GFS_ERR_CAPACITY, "stride exceeds the handle's max_points");
+  GFS_REQUIRE(h->trackCalls == 0 || seqs == h->trackSeqs, GFS_ERR_INVALID, "the number of sequences changed: call gfs_gicp_track_reset first");
+  GFS_REQUIRE(h->trackCalls == 0 || (d_T0 && d_out), GFS_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  GicpDev D = h->dev;
+  const int slot = h->trackCalls & 1;
+  D.cbase = slot; D.cstep = 2; D.swap = 1 - slot; D.inputAll = 1;
+  h->launches = 0;
+  k_set_counts<<<div_up(seqs, 128), 128, 0, st>>>(D, seqs, nullptr, d_n, stride);
+  h->launches += 1;
+  int rc = preprocess_clouds(h, D, st, seqs, nullptr, d_cloud, stride);
+  if (rc) return rc;
+  const bool first = h->trackCalls == 0;
+  h->trackCalls++;
+  h->trackSeqs = seqs;
+  if (first) return GFS_OK;  // nothing to register the first cloud against
+  return optimize_pairs(h, D, st, seqs, d_T0, d_out);
+}
+
+int gfs_gicp_track_batch(GfsGicp* h, void* stream, const float* cloud, const int* n, int seqs, int stride, const double* T0,
+                         GfsGicpResult* out) {
+  GFS_REQUIRE(h, GFS_ERR_INVALID, "null handle");
+  GFS_REQUIRE(cloud && n, GFS_ERR_INVALID, "null pointer");
+  GFS_REQUIRE(seqs > 0 && seqs <= h->maxPairs, GFS_ERR_CAPACITY, "seqs exceeds the handle's max_pairs");
+  GFS_REQUIRE(stride > 0 && stride <= h->dev.nmax, GFS_ERR_CAPACITY, "stride exceeds the handle's max_points");
+  const bool first = h->trackCalls == 0;
+  GFS_REQUIRE(first || (T0 && out), GFS_ERR_INVALID, "null pointer");
+  for (int i = 0; i < seqs; i++) GFS_REQUIRE(n[i] >= 0 && n[i] <= stride, GFS_ERR_INVALID, "point count outside [0, stride]");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t P = seqs, cb = P * stride * 16;
+  int rc;
+  if ((rc = h->b_src.reserve(cb))) return rc;
+  if ((rc = h->b_n.reserve(P * 8))) return rc;
+  if ((rc = h->b_T0.reserve(P * 128))) return rc;
+  if ((rc = h->b_res.reserve(P * sizeof(GfsGicpResult)))) return rc;
+  GFS_CUDA(cudaMemcpyAsync(h->b_src.p, cloud, cb, cudaMemcpyHostToDevice, st));
+  GFS_CUDA(cudaMemcpyAsync(h->b_n.p, n, P * 4, cudaMemcpyHostToDevice, st));
+  if (!first) GFS_CUDA(cudaMemcpyAsync(h->b_T0.p, T0, P * 128, cudaMemcpyHostToDevice, st));
+  rc = gfs_gicp_track_batch_device(h, stream, (const float*)h->b_src.p, (const int*)h->b_n.p, seqs, stride,
+                                   (const double*)h->b_T0.p, (GfsGicpResult*)h->b_res.p);
+  if (rc) return rc;
+  if (!first) GFS_CUDA(cudaMemcpyAsync(out, h->b_res.p, P * sizeof(GfsGicpResult), cudaMemcpyDeviceToHost, st));
+  GFS_CUDA(cudaStreamSynchronize(st));
+  return GFS_OK;
+}
+
 int gfs_gicp_align_batch(GfsGicp* h, void* stream, const float* target, const int* nt, const float* source, const int* ns,
                          int pairs, int stride, const double* T0, GfsGicpResult* out) {
   GFS_REQUIRE(h, GFS_ERR_INVALID, "null handle");
   GFS_REQUIRE(target && nt && source && ns && T0 && out, GFS_ERR_INVALID, "null pointer");
   GFS_REQUIRE(pairs > 0 && pairs <= h->maxPairs, GFS_ERR_CAPACITY, "pairs exceeds the handle's max_pairs");
   GFS_REQUIRE(stride > 0 && stride <= h->dev.nmax, GFS_ERR_CAPACITY, "stride exceeds the handle's max_points");
+  for (int i = 0; i < pairs; i++)
+    GFS_REQUIRE(nt[i] >= 0 && nt[i] <= stride && ns[i] >= 0 && ns[i] <= stride, GFS_ERR_INVALID, "point count outside [0, stride]");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t P = pairs, cb = P * stride * 16;
   int rc;

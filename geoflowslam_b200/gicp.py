@@ -84,6 +84,28 @@ class RegistrationGICP:
         check(self._L.gfs_gicp_align_batch_device(self._h, stream, ptr(d_targets), ptr(d_nt), ptr(d_sources), ptr(d_ns),
                                                   int(pairs), int(stride), ptr(d_T0), ptr(d_out)))
 
+    # -- tracking mode (Tracking::PredictStateICP's call pattern): every cloud is preprocessed once and kept on the device
+    def track_reset(self):
+        check(self._L.gfs_gicp_track_reset(self._h))
+
+    def track_batch_device(self, d_cloud, d_n, seqs, stride, d_T0, d_out, stream=None):
+        """New cloud of each of `seqs` sequences (device arrays); registers it against the previous call's.  The first
+        call after a reset only stores the clouds."""
+        check(self._L.gfs_gicp_track_batch_device(self._h, stream, ptr(d_cloud), ptr(d_n), int(seqs), int(stride), ptr(d_T0),
+                                                  ptr(d_out)))
+
+    def track_batch(self, clouds, n, T0=None, stream=None):
+        """clouds: (S, stride, 4) float32 host array, n: (S,) int32, T0: (S,4,4) init_T_target_source (previous <- new).
+        Returns the (S,) result array, or None for the first call after a reset."""
+        clouds = np.ascontiguousarray(clouds, np.float32)
+        S, stride = clouds.shape[0], clouds.shape[1]
+        n = np.ascontiguousarray(n, np.int32)
+        T0 = np.ascontiguousarray(np.tile(np.eye(4), (S, 1, 1)) if T0 is None else T0, np.float64).reshape(S, 16)
+        r = np.zeros(S, RESULT_DTYPE)
+        first = self._L.gfs_gicp_track_calls(self._h) == 0
+        check(self._L.gfs_gicp_track_batch(self._h, stream, ptr(clouds), ptr(n), S, stride, ptr(T0), ptr(r)))
+        return None if first else r
+
     def last_launches(self):
         return self._L.gfs_gicp_last_launches(self._h)
 

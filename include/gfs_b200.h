@@ -227,6 +227,19 @@ int gfs_gicp_align_batch(GfsGicp* h, void* stream, const float* target, const in
                          int pairs, int stride, const double* T0, GfsGicpResult* out);
 int gfs_gicp_align_batch_device(GfsGicp* h, void* stream, const float* d_target, const int* d_nt, const float* d_source,
                                 const int* d_ns, int pairs, int stride, const double* d_T0, GfsGicpResult* d_out);
+/* Tracking mode -- the call pattern of Tracking::PredictStateICP (src/Tracking.cc:3364-3413): every frame the current
+ * cloud (source) is registered against the last frame's cloud (target).  d_cloud is [seqs][stride][4] floats with d_n[s]
+ * valid points: the NEW cloud of each of `seqs` independent sequences.  Each cloud is preprocessed (voxel grid, k-NN
+ * grid, covariances) once and kept in HBM, instead of twice as small_gicp::align does (registration_helper.cpp:56-68);
+ * results equal gfs_gicp_align_batch on (previous cloud, new cloud) bit for bit.  The first call after create / reset /
+ * gfs_gicp_align* only stores the clouds (d_T0 / d_out may be NULL, nothing is written).  Same stream semantics as
+ * gfs_gicp_align_batch_device.  gfs_gicp_track_batch is the host-pointer variant (copies in, results out, synchronises). */
+int gfs_gicp_track_reset(GfsGicp* h);
+int gfs_gicp_track_calls(const GfsGicp* h);   /* clouds stored per sequence since the last reset (0: the next call only stores) */
+int gfs_gicp_track_batch_device(GfsGicp* h, void* stream, const float* d_cloud, const int* d_n, int seqs, int stride,
+                                const double* d_T0, GfsGicpResult* d_out);
+int gfs_gicp_track_batch(GfsGicp* h, void* stream, const float* cloud, const int* n, int seqs, int stride, const double* T0,
+                         GfsGicpResult* out);
 /* parity hook: downsampled points + covariances of cloud (2*pair = target, 2*pair+1 = source) */
 int gfs_gicp_get_cloud(GfsGicp* h, void* stream, int cloud, double* out_xyz, double* out_cov6, int cap, int* n);
 int gfs_gicp_last_launches(const GfsGicp* h);

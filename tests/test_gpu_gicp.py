@@ -85,3 +85,76 @@ def test_degenerate_inputs():
     from geoflowslam_b200 import GfsError
     with pytest.raises(GfsError):
         reg.RegisterPointClouds(np.zeros((10000, 4), np.float32), src)      # beyond max_points
+
+
+def _pack(clouds):
+    stride = max(len(c) for c in clouds)
+    a = np.zeros((len(clouds), stride, 4), np.float32); n = np.zeros(len(clouds), np.int32)
+    for i, c in enumerate(clouds):
+        a[i, :len(c)] = c; n[i] = len(c)
+    return a, n
+
+
+def test_search_variants_are_bit_identical(monkeypatch):
+    """The query order (point / grid-cell order) and the correspondence kernels (shell walk, ball walk in fp64, ball walk with
+    the float32 prefilter) are different routes to the same exact neighbours: every result field is equal bit for bit."""
+    from geoflowslam_b200 import RegistrationGICP
+    pairs = [synth.gicp_pair(2030 + i, n_target=[20000, 6000][i]) for i in range(2)]
+    tg, nt = _pack([p[0] for p in pairs]); sr, ns = _pack([p[1] for p in pairs])
+    stride = max(tg.shape[1], sr.shape[1])
+    tg = np.pad(tg, ((0, 0), (0, stride - tg.shape[1]), (0, 0))); sr = np.pad(sr, ((0, 0), (0, stride - sr.shape[1]), (0, 0)))
+    T0 = np.tile(np.eye(4), (2, 1, 1))
+    out = {}
+    for order, nn in ((0, 0), (1, 0), (1, 1), (1, 2), (0, 2)):
+        monkeypatch.setenv("GFS_GICP_ORDER", str(order)); monkeypatch.setenv("GFS_GICP_NN", str(nn))
+        reg = RegistrationGICP(max_points=stride, max_pairs=2)
+        out[(order, nn)] = reg.align_batch(tg, nt, sr, ns, T0).tobytes()
+        covs = [reg.cloud(c)[1].tobytes() for c in range(4)]
+        out[(order, nn, "cov")] = covs
+        reg.close()
+    base = out[(0, 0)]
+    for k, v in out.items():
+        if len(k) == 2:
+            assert v == base, "variant order=%d nn=%d differs from the first-generation search" % k
+        else:
+            assert v == out[(0, 0, "cov")], "covariances of variant order=%d nn=%d differ" % k[:2]
+
+
+def test_track_mode_equals_pairwise_align():
+    """gfs_gicp_track_batch: each cloud preprocessed once, registered against the previous call's -> the same bytes as
+    gfs_gicp_align_batch on the pairs (cloud[k-1], cloud[k])."""
+    from geoflowslam_b200 import RegistrationGICP
+    # two sequences of four clouds each: views of one scene from a slowly moving camera
+    seqs = []
+    for s in range(2):
+        t0, s0, _ = synth.gicp_pair(2040 + s, n_target=[15000, 7000][s])
+        t1, s1, _ = synth.gicp_pair(2050 + s, n_target=[15000, 7000][s])
+        seqs.append([t0, s0, t0[::2].copy(), s0])   # cloud 2 is a subsample of cloud 0, cloud 3 repeats cloud 1
+    K = 4
+    packed = [_pack([seqs[s][k] for s in range(2)]) for k in range(K)]
+    stride = max(a.shape[1] for a, _ in packed)
+    packed = [(np.pad(a, ((0, 0), (0, stride - a.shape[1]), (0, 0))), n) for a, n in packed]
+    T0 = np.tile(np.eye(4), (2, 1, 1)); T0[1, :3, 3] += 0.01
+    trk = RegistrationGICP(max_points=stride, max_pairs=2)
+    ref = RegistrationGICP(max_points=stride, max_pairs=2)
+    assert trk.track_batch(*packed[0]) is None
+    for k in range(1, K):
+        r = trk.track_batch(packed[k][0], packed[k][1], T0)
+        e = ref.align_batch(packed[k - 1][0], packed[k - 1][1], packed[k][0], packed[k][1], T0)
+        assert r is not None and r.tobytes() == e.tobytes(), "track call %d differs from the pairwise align" % k
+    # a reset starts a new chain; align_batch on the same handle also invalidates the stored clouds
+    trk.track_reset()
+    assert trk.track_batch(*packed[2]) is None
+    r = trk.track_batch(packed[3][0], packed[3][1], T0)
+    assert r.tobytes() == ref.align_batch(packed[2][0], packed[2][1], packed[3][0], packed[3][1], T0).tobytes()
+
+
+def test_counts_beyond_stride_are_rejected():
+    from geoflowslam_b200 import RegistrationGICP
+    from geoflowslam_b200._lib import GfsError
+    reg = RegistrationGICP(max_points=4096, max_pairs=1)
+    a = np.zeros((1, 1024, 4), np.float32)
+    with pytest.raises(GfsError):
+        reg.align_batch(a, np.array([2000], np.int32), a, np.array([10], np.int32), np.eye(4)[None])
+    with pytest.raises(GfsError):
+        reg.align_batch(a, np.array([10], np.int32), a, np.array([-1], np.int32), np.eye(4)[None])
