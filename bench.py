@@ -382,7 +382,18 @@ def run_gicp(args):
     d_nt, d_ns, d_T0 = torch.from_numpy(nt).to(dev), torch.from_numpy(ns).to(dev), torch.from_numpy(T0).to(dev)
     d_out = torch.zeros(P * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
-    step = lambda: reg.align_batch_device(d_tg, d_nt, d_sr, d_ns, P, stride, d_T0, d_out, stream=stream)
+    if args.gicp_track:
+        # tracking mode: every step brings ONE new cloud per sequence (alternately the pair's source and target cloud) and
+        # registers it against the previous step's, which is already preprocessed and resident
+        calls = [0]
+        reg.track_batch_device(d_tg, d_nt, P, stride, None, None, stream=stream)
+
+        def step():
+            calls[0] += 1
+            new, n = (d_sr, d_ns) if calls[0] & 1 else (d_tg, d_nt)
+            reg.track_batch_device(new, n, P, stride, d_T0, d_out, stream=stream)
+    else:
+        step = lambda: reg.align_batch_device(d_tg, d_nt, d_sr, d_ns, P, stride, d_T0, d_out, stream=stream)
     for _ in range(max(args.warmup, 1)):
         step()
     ms, clocks = _clock_block(lambda: [step() for _ in range(args.steps)], local)
@@ -392,18 +403,23 @@ def run_gicp(args):
     I, J = float(res["iterations"].mean() + 1), float(res["inner_evals"].mean())
     alg = P * (16 * (nt.mean() + ns.mean()) + 400 * (M_t + M_s) + M_s * (160 * I + 112 * J))  # SURVEY 8d A_gicp
     t0 = time.perf_counter(); res_h = reg.align_batch(tg, nt, sr, ns, T0); e2e_s = time.perf_counter() - t0
-    assert np.array_equal(res_h["iterations"], res["iterations"])
-    from oracle import oracle as O
+    if not args.gicp_track:
+        assert np.array_equal(res_h["iterations"], res["iterations"])
     nsamp = min(uniq, 8)
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(max(1, (os.cpu_count() or 4) // 4)) as ex:  # 4 OpenMP threads per pair, as the reference
-        list(ex.map(lambda i: O.gicp_align(pairs[i][0], pairs[i][1], threads=4), range(nsamp)))
-    cpu_s = time.perf_counter() - t0
+    cpu_s = float("nan")
+    if not args.no_cpu:
+        from oracle import oracle as O
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max(1, (os.cpu_count() or 4) // 4)) as ex:  # 4 OpenMP threads per pair, as the reference
+            list(ex.map(lambda i: O.gicp_align(pairs[i][0], pairs[i][1], threads=4), range(nsamp)))
+        cpu_s = time.perf_counter() - t0
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     line = {"metric": "cloud pairs/sec GICP 50k-pt RGB-D pairs (BASELINE configs[2])", "value": P / (ms / 1e3), "unit": "pairs/s",
             "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[2]: RegistrationGICP voxel 0.02, max dist 0.1, k=10, <=20 LM iterations",
+            "config": {"workload": "configs[2]: RegistrationGICP voxel 0.02, max dist 0.1, k=10, <=20 LM iterations" +
+                                   (" -- tracking mode: one new cloud per sequence and step, registered against the resident previous one" if args.gicp_track else ""),
+                       "variant": {k: os.environ.get(k) for k in ("GFS_GICP_ORDER", "GFS_GICP_NN", "GFS_GICP_CELL", "GFS_GICP_KNN_CELLS") if os.environ.get(k)},
                        "pairs": P, "distinct_pairs": uniq, "points_per_cloud": int(nt.mean()), "downsampled": [M_t, M_s],
                        "outer_iterations": I, "inner_evals": J},
             "clocks": clocks,
@@ -875,6 +891,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gicp-track", action="store_true", help="--workload gicp in tracking mode (gfs_gicp_track_batch_device)")
     ap.add_argument("--workload", default="orb", choices=["orb", "gicp", "ba", "lba", "pose", "pose_inertial", "klt", "track"],
                     help="orb = BASELINE configs[1] (the driver's default); gicp / ba = configs[2] / configs[3]")
     args = ap.parse_args()
