@@ -1396,11 +1396,9 @@ int gfs_ba_solve_uploaded(GfsBa* h, void* stream) {
   h->launches = 0;
   const bool part = D.world > 1;
   const size_t ldltSmem = (size_t)(2 * LDLT_MAXN * LDLT_PITCH + 32 + LDLT_MAXN) * sizeof(double);
-  static bool ldltConfigured = false;
-  if (!ldltConfigured) {
-    GFS_CUDA(cudaFuncSetAttribute(k_ldlt_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldltSmem));
-    ldltConfigured = true;
-  }
+  // the attribute belongs to the (device, function) pair: set it on every solve (a process may drive several GPUs, and host
+  // threads may share the handle's device) -- one cheap driver call against ~200 launches
+  GFS_CUDA(cudaFuncSetAttribute(k_ldlt_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldltSmem));
   k_ba_init<<<div_up(B, 128), 128, 0, st>>>(D, B);
   // reset the working state from the uploaded problem (re-solvable)
   GFS_CUDA(cudaMemcpyAsync(D.kf, h->h_kf.data(), h->h_kf.size() * 8, cudaMemcpyHostToDevice, st));

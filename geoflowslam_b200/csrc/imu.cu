@@ -181,19 +181,24 @@ int gfs_imu_preintegrate_batch(void* stream, const float* meas, const int* offse
   const size_t total = (size_t)offsets[n];
   float *dm = nullptr, *db = nullptr, *dout = nullptr;
   int* doff = nullptr;
-  GFS_CUDA(cudaMallocAsync((void**)&dm, std::max<size_t>(total, 1) * 28, st));
-  GFS_CUDA(cudaMallocAsync((void**)&doff, (size_t)(n + 1) * 4, st));
-  GFS_CUDA(cudaMallocAsync((void**)&db, (size_t)n * 24, st));
-  GFS_CUDA(cudaMallocAsync((void**)&dout, (size_t)n * GFS_BA_PRE_STRIDE * 4, st));
-  if (total) GFS_CUDA(cudaMemcpyAsync(dm, meas, total * 28, cudaMemcpyHostToDevice, st));
-  GFS_CUDA(cudaMemcpyAsync(doff, offsets, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
-  GFS_CUDA(cudaMemcpyAsync(db, bias, (size_t)n * 24, cudaMemcpyHostToDevice, st));
-  rc = gfs_imu_preintegrate_batch_device(stream, dm, doff, db, n, ng, na, ngw, naw, dout);
-  if (rc == GFS_OK) {
-    const cudaError_t e = cudaMemcpyAsync(out, dout, (size_t)n * GFS_BA_PRE_STRIDE * 4, cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) { gfs::set_error("cudaMemcpyAsync -> %s", cudaGetErrorString(e)); rc = GFS_ERR_CUDA; }
-  }
-  cudaFreeAsync(dm, st); cudaFreeAsync(doff, st); cudaFreeAsync(db, st); cudaFreeAsync(dout, st);
+  // every exit path frees whatever was allocated (stream-ordered)
+  auto step = [&](cudaError_t e, const char* what) {
+    if (rc == GFS_OK && e != cudaSuccess) { gfs::set_error("%s -> %s", what, cudaGetErrorString(e)); rc = GFS_ERR_CUDA; }
+    return rc == GFS_OK;
+  };
+  step(cudaMallocAsync((void**)&dm, std::max<size_t>(total, 1) * 28, st), "cudaMallocAsync(meas)") &&
+      step(cudaMallocAsync((void**)&doff, (size_t)(n + 1) * 4, st), "cudaMallocAsync(offsets)") &&
+      step(cudaMallocAsync((void**)&db, (size_t)n * 24, st), "cudaMallocAsync(bias)") &&
+      step(cudaMallocAsync((void**)&dout, (size_t)n * GFS_BA_PRE_STRIDE * 4, st), "cudaMallocAsync(out)") &&
+      (!total || step(cudaMemcpyAsync(dm, meas, total * 28, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(meas)")) &&
+      step(cudaMemcpyAsync(doff, offsets, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(offsets)") &&
+      step(cudaMemcpyAsync(db, bias, (size_t)n * 24, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(bias)");
+  if (rc == GFS_OK) rc = gfs_imu_preintegrate_batch_device(stream, dm, doff, db, n, ng, na, ngw, naw, dout);
+  if (rc == GFS_OK) step(cudaMemcpyAsync(out, dout, (size_t)n * GFS_BA_PRE_STRIDE * 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(out)");
+  if (dm) cudaFreeAsync(dm, st);
+  if (doff) cudaFreeAsync(doff, st);
+  if (db) cudaFreeAsync(db, st);
+  if (dout) cudaFreeAsync(dout, st);
   if (rc) return rc;
   GFS_CUDA(cudaStreamSynchronize(st));
   return GFS_OK;

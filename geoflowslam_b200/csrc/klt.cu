@@ -66,6 +66,19 @@ static PyrGeom make_geom(int w, int h, int levels) {
   return g;
 }
 
+// Highest level cv::buildOpticalFlowPyramid(img, pyr, Size(win, win), levels) actually builds: it stops as soon as the
+// next level would be <= the window in either dimension (its return value), and calcOpticalFlowPyrLK clamps maxLevel to
+// what the pyramids hold.  VGA with the 35-px window keeps all 3 levels; QVGA keeps 2.
+static int effective_levels(int w, int h, int levels, int win) {
+  int l = 0;
+  while (l < levels) {
+    const int nw = (w + 1) / 2, nh = (h + 1) / 2;
+    if (nw <= win || nh <= win) break;
+    w = nw; h = nh; l++;
+  }
+  return l;
+}
+
 __device__ __forceinline__ int reflect101(int p, int len) {  // cv::borderInterpolate(BORDER_REFLECT_101)
   if (len == 1) return 0;
   while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
@@ -600,7 +613,7 @@ int gfs_klt_calc_batch_device(GfsKlt* h, void* stream, const uint8_t* d_prev_pyr
   TrackArgs A;
   memset(&A, 0, sizeof(A));
   A.prevPyr = d_prev_pyr; A.curPyr = d_cur_pyr; A.kps = d_pts; A.next = d_next; A.n = d_n; A.status = d_status; A.err = d_err;
-  A.stride = stride; A.win = win; A.maxLevel = max_level; A.maxCount = std::min(std::max(max_count, 0), 100);
+  A.stride = stride; A.win = win; A.maxLevel = std::min(max_level, effective_levels(w, h_img, h->levels, win)); A.maxCount = std::min(std::max(max_count, 0), 100);
   const float e = std::min(std::max(eps, 0.f), 10.f);
   A.eps2 = e * e; A.useInitial = use_initial_flow; A.fb = 0;
   h->launches = 0;
@@ -617,7 +630,7 @@ int gfs_klt_fb_track_batch_device(GfsKlt* h, void* stream, const uint8_t* d_prev
   TrackArgs A;
   memset(&A, 0, sizeof(A));
   A.prevPyr = d_prev_pyr; A.curPyr = d_cur_pyr; A.kps = d_kps; A.next = d_priors; A.n = d_n; A.status = d_status; A.err = nullptr;
-  A.stride = stride; A.win = win; A.maxLevel = nbpyrlvl; A.maxCount = 30; A.eps2 = 0.01f * 0.01f; A.useInitial = 1; A.fb = 1;
+  A.stride = stride; A.win = win; A.maxLevel = std::min(nbpyrlvl, effective_levels(w, h_img, h->levels, win)); A.maxCount = 30; A.eps2 = 0.01f * 0.01f; A.useInitial = 1; A.fb = 1;
   A.ferr = ferr; A.fbDist = fmax_fbklt_dist;
   h->launches = 0;
   return launch_track(h, (cudaStream_t)stream, A, g, batch, stride);

@@ -258,10 +258,13 @@ __global__ void __launch_bounds__(UM_THREADS) k_bf_hamming_umma(const uint8_t* _
 
 int launch_bf_hamming_umma(cudaStream_t st, const uint8_t* d_dq, const int* d_nq, const uint8_t* d_dt, const int* d_nt,
                            int pairs, int stride, int* d_out_idx, int* d_out_dist) {
-  static bool configured = false;
-  if (!configured) {
+  // the dynamic shared memory limit is a per-device attribute: one flag per device ordinal, not per process
+  static bool configured[64] = {};
+  int devId = 0;
+  GFS_CUDA(cudaGetDevice(&devId));
+  if (devId < 0 || devId >= 64 || !configured[devId]) {
     GFS_CUDA(cudaFuncSetAttribute(k_bf_hamming_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM));
-    configured = true;
+    if (devId >= 0 && devId < 64) configured[devId] = true;
   }
   k_bf_hamming_umma<<<dim3(div_up(stride, UM_M), pairs), UM_THREADS, UM_SMEM, st>>>(d_dq, d_nq, d_dt, d_nt, stride, d_out_idx,
                                                                                    d_out_dist);

@@ -96,11 +96,22 @@ def read_frame(root, rgb_path, depth_path, depth_factor=1000.0):
 
 def frame_measurements(frame_stamps, imu_stamps, odom_stamps=None, min_imu=3):
     """The frame loop of rgbd_inertial.cc: -> list of (frame index, imu index range, odom index range) for the frames that
-    are handed to TrackRGBD; index ranges are half-open [a, b) into the loaded sample arrays."""
+    are handed to TrackRGBD; index ranges are half-open [a, b) into the loaded sample arrays.
+
+    Before the loop the reference skips the samples stamped at or before frame 0 and then steps back by one
+    (`first_imu--`, rgbd_inertial.cc:80-81; the same for the odometry, :82-85): the LAST sample at or before frame 0 is the
+    first sample of frame 1's group -- Tracking::PreintegrateIMU interpolates from it at the start of the interval.
+    (With no sample at or before frame 0 the reference's index would go to -1; clamped to 0 here.)  Frame 0 itself gets no
+    samples (`if (ni > 0)`, :151,162) and is therefore dropped by the `vImuMeas.size() < 3` test (:171)."""
     first_imu = 0
     while first_imu < len(imu_stamps) and imu_stamps[first_imu] <= frame_stamps[0]:         # :80
         first_imu += 1
+    first_imu = max(first_imu - 1, 0)                                                        # :81
     first_odom = 0
+    if odom_stamps is not None:
+        while first_odom < len(odom_stamps) and odom_stamps[first_odom] <= frame_stamps[0]:  # :83
+            first_odom += 1
+        first_odom = max(first_odom - 1, 0)                                                  # :84
     out = []
     for ni in range(len(frame_stamps)):
         a, oa = first_imu, first_odom

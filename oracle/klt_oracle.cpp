@@ -230,6 +230,17 @@ static void lk_level(const Level& I, const Level& J, int level, int maxLevel, in
 static void calc_lk(const Pyr& P, const Pyr& C, const float* pts, float* next, int n, int win, int maxLevel, int maxCount, float eps,
                     bool useInitial, uint8_t* status, float* err) {
   maxLevel = std::min(maxLevel, (int)std::min(P.lv.size(), C.lv.size()) - 1);
+  // cv::buildOpticalFlowPyramid stops once the next level would be <= the window in either dimension and returns the
+  // last level it built; calcOpticalFlowPyrLK clamps maxLevel to that (lkpyramid.cpp)
+  {
+    int w = P.lv[0].w, h = P.lv[0].h, eff = 0;
+    while (eff < maxLevel) {
+      const int nw = (w + 1) / 2, nh = (h + 1) / 2;
+      if (nw <= win || nh <= win) break;
+      w = nw; h = nh; eff++;
+    }
+    maxLevel = eff;
+  }
   maxCount = std::min(std::max(maxCount, 0), 100);
   eps = std::min(std::max(eps, 0.f), 10.f);
   const float eps2 = eps * eps;

@@ -55,6 +55,15 @@ def test_tum_flavour_and_sparse_imu(tmp_path):
     # frames with fewer than three IMU samples are not tracked (rgbd_inertial.cc:171)
     g = D.frame_measurements(np.array([0.0, 0.1, 0.2]), np.array([0.01, 0.02, 0.03, 0.15, 0.16]))
     assert [x[0] for x in g] == [1]
+    # rgbd_inertial.cc:80-85: the samples at or before frame 0 are skipped, then `first_imu--` / `first_odom--`: the LAST
+    # sample at or before frame 0 opens frame 1's group (PreintegrateIMU interpolates from it)
+    t_imu = np.array([-0.02, -0.01, 0.0, 0.03, 0.06, 0.09, 0.12, 0.15, 0.18])
+    t_od = np.array([-0.05, 0.0, 0.05, 0.1, 0.15, 0.2])
+    g = D.frame_measurements(np.array([0.0, 0.1, 0.2]), t_imu, t_od)
+    assert g == [(1, (2, 6), (1, 4)), (2, (6, 9), (4, 6))]
+    # two samples after frame 0 + the one at its stamp make three: the frame is tracked (it was dropped before the fix)
+    g = D.frame_measurements(np.array([0.0, 0.1]), np.array([0.0, 0.04, 0.08]))
+    assert g == [(1, (0, 3), (0, 0))]
 
 
 def test_config0_plumbing_chain_from_disk(tmp_path):

@@ -169,3 +169,23 @@ def test_other_window_sizes_match_oracle_bitwise(win, levels):
     o_next, o_st, o_er = O.klt_calc(pa, pb, 640, 480, 3, pts, init=pts, win=win, max_level=levels)
     assert np.array_equal(d_st.cpu().numpy(), o_st)
     assert np.array_equal(d_next.cpu().numpy(), o_next) and np.array_equal(d_er.cpu().numpy(), o_er)
+
+
+def test_qvga_tracks_from_the_level_opencv_stops_at():
+    """QVGA with the 35-px window: cv::buildOpticalFlowPyramid keeps levels 0-2 only; the CUDA tracker starts there too."""
+    import cv2
+    from geoflowslam_b200 import KltTracker
+    from oracle import oracle as O
+    fr = _frames()
+    a = cv2.resize(fr[0], (320, 240), interpolation=cv2.INTER_AREA); b = cv2.resize(fr[1], (320, 240), interpolation=cv2.INTER_AREA)
+    pts = cv2.goodFeaturesToTrack(a, 300, 0.01, 7).reshape(-1, 2).astype(np.float32)
+    trk = KltTracker(max_size=(320, 240), max_points=512, max_batch=1)
+    pr_g, st_g = trk.fbKltTracking(a, b, pts, pts)
+    pa, pb = O.klt_build_pyramid(a, 3), O.klt_build_pyramid(b, 3)
+    pr_o, st_o = O.fb_klt_tracking(pa, pb, 320, 240, 3, pts, pts)
+    assert np.array_equal(st_g, st_o) and np.array_equal(pr_g, pr_o)
+    crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
+    cn, cs, ce = cv2.calcOpticalFlowPyrLK(a, b, pts, pts.copy(), winSize=(35, 35), maxLevel=3, criteria=crit,
+                                          flags=cv2.OPTFLOW_USE_INITIAL_FLOW + cv2.OPTFLOW_LK_GET_MIN_EIGENVALS)
+    ok = st_g.astype(bool) & cs.ravel().astype(bool)
+    assert ok.sum() > 0.5 * len(pts) and np.quantile(np.linalg.norm(pr_g - cn, axis=1)[ok], 0.99) < 5e-3

@@ -105,3 +105,24 @@ def test_clahe_bit_exact_vs_cv2(shape, clip, tiles):
     c = cv2.createCLAHE(clip, tiles)
     for img in imgs:
         assert np.array_equal(O.clahe(img, clip, tiles), c.apply(img))
+
+
+def test_qvga_pyramid_stops_early_like_opencv():
+    """cv::buildOpticalFlowPyramid stops when the next level would be <= the window (QVGA, 35 px: level 2 is the last) and
+    calcOpticalFlowPyrLK clamps maxLevel to that; the oracle tracks from the same level."""
+    f = synth.orb_frames(2, 640, 480, group=8, seed0=1000)
+    a, b = cv2.resize(f[0], (320, 240), interpolation=cv2.INTER_AREA), cv2.resize(f[1], (320, 240), interpolation=cv2.INTER_AREA)
+    n, _ = cv2.buildOpticalFlowPyramid(a, (35, 35), 3)
+    assert n == 2
+    pts = cv2.goodFeaturesToTrack(a, 300, 0.01, 7).reshape(-1, 2).astype(np.float32)
+    init = pts + np.float32(0.6)
+    pa, pb = O.klt_build_pyramid(a, 3), O.klt_build_pyramid(b, 3)
+    cn, cs, _ = cv2.calcOpticalFlowPyrLK(a, b, pts, init.copy(), winSize=(35, 35), maxLevel=3, criteria=CRIT, flags=FLAGS)
+    on, os_, _ = O.klt_calc(pa, pb, 320, 240, 3, pts, init=init, win=35, max_level=3)
+    o2, s2, _ = O.klt_calc(pa, pb, 320, 240, 3, pts, init=init, win=35, max_level=2)
+    assert np.array_equal(on, o2) and np.array_equal(os_, s2)            # level 3 is not used
+    cs = cs.ravel().astype(bool)
+    assert (cs == os_.astype(bool)).mean() >= 0.99
+    both = cs & os_.astype(bool)
+    d = np.linalg.norm(on - cn, axis=1)[both]
+    assert np.quantile(d, 0.99) < 5e-3 and np.median(d) < 1e-4, (np.median(d), d.max())
