@@ -1487,7 +1487,7 @@ struct GfsGicp {
   PinnedBuf h_counters;
   int launches = 0;
   bool cellKnn = false;  // GFS_GICP_KNN_CELLS=1: cell-centric 10-NN kernel first (same results)
-  int nnMode = 2;        // GFS_GICP_NN: 0 = k_nn_corr (shell walk), 1 = k_nn_corr2 in fp64, 2 = k_nn_corr2 with the float32 prefilter
+  int nnMode = 1;        // GFS_GICP_NN: 0 = k_nn_corr (shell walk), 1 = k_nn_corr2 in fp64 (default: measured fastest), 2 = k_nn_corr2 with the float32 prefilter
   int trackCalls = 0;    // gfs_gicp_track_*: calls since the last reset (the new cloud goes to slot trackCalls & 1)
   int trackSeqs = 0;
 };
