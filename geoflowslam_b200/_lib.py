@@ -75,6 +75,8 @@ SIGNATURES = {
     "gfs_gicp_track_batch": ([vp, vp, vp, vp, ci, ci, vp, vp], ci),
     "gfs_gicp_get_cloud": ([vp, vp, ci, vp, vp, ci, vp], ci),
     "gfs_gicp_last_launches": ([vp], ci),
+    "gfs_gicp_set_profiling": ([vp, ci], ci),
+    "gfs_gicp_get_profile": ([vp, vp, vp], ci),
     "gfs_gicp_get_knn_stats": ([vp, vp, ci, vp, vp], ci),
     "gfs_ba_create": ([ci, ci, ci, ci, ci, C.POINTER(vp)], ci),
     "gfs_ba_destroy": ([vp], ci),

@@ -1490,7 +1490,45 @@ struct GfsGicp {
   int nnMode = 1;        // GFS_GICP_NN: 0 = k_nn_corr (shell walk), 1 = k_nn_corr2 in fp64 (default: measured fastest), 2 = k_nn_corr2 with the float32 prefilter
   int trackCalls = 0;    // gfs_gicp_track_*: calls since the last reset (the new cloud goes to slot trackCalls & 1)
   int trackSeqs = 0;
+  // optional per-stage CUDA-event timing of one call (gfs_gicp_set_profiling): an event after every stage, read back at
+  // the end of the call; stage = GFS_GICP_STAGE_* index
+  bool profiling = false;
+  std::vector<cudaEvent_t> evPool;
+  std::vector<int> evStage;
+  size_t evUsed = 0;
+  float stageMs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int stageLaunches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
+
+// stage indices of gfs_gicp_get_profile: grouping + voxel means + cell pack, 10-NN covariances, correspondence search,
+// linearisation, LM bookkeeping (partial-sum reduction, error evaluations, decisions incl. the host's control reads)
+enum { ST_GROUP = 0, ST_KNN = 1, ST_NN = 2, ST_LIN = 3, ST_LM = 4 };
+
+static void prof_begin(GfsGicp* h, cudaStream_t st) {
+  if (!h->profiling) return;
+  h->evUsed = 0;
+  h->evStage.clear();
+  for (int k = 0; k < 8; k++) { h->stageMs[k] = 0; h->stageLaunches[k] = 0; }
+  if (h->evPool.empty()) { h->evPool.resize(1); cudaEventCreate(&h->evPool[0]); }
+  cudaEventRecord(h->evPool[0], st);
+  h->evUsed = 1;
+}
+// everything enqueued since the previous mark belongs to `stage`
+static void prof_mark(GfsGicp* h, cudaStream_t st, int stage, int launches = 1) {
+  if (!h->profiling) return;
+  if (h->evUsed == h->evPool.size()) { h->evPool.push_back(nullptr); cudaEventCreate(&h->evPool.back()); }
+  cudaEventRecord(h->evPool[h->evUsed++], st);
+  h->evStage.push_back(stage);
+  h->stageLaunches[stage] += launches;
+}
+static void prof_end(GfsGicp* h, cudaStream_t st) {
+  if (!h->profiling || h->evUsed < 2) return;
+  cudaStreamSynchronize(st);
+  for (size_t i = 1; i < h->evUsed; i++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->evPool[i - 1], h->evPool[i]) == cudaSuccess) h->stageMs[h->evStage[i - 1]] += ms;
+  }
+}
 
 extern "C" {
 
@@ -1593,11 +1631,23 @@ int gfs_gicp_destroy(GfsGicp* h) {
                  &h->b_partialE, &h->b_state, &h->b_istate, &h->b_counters, &h->b_tgt, &h->b_src, &h->b_n, &h->b_T0, &h->b_res};
   for (DevBuf* b : d) b->release();
   h->h_counters.release();
+  for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
   delete h;
   return GFS_OK;
 }
 
 int gfs_gicp_last_launches(const GfsGicp* h) { return h ? h->launches : GFS_ERR_INVALID; }
+
+int gfs_gicp_set_profiling(GfsGicp* h, int on) {
+  GFS_REQUIRE(h, GFS_ERR_INVALID, "null handle");
+  h->profiling = on != 0;
+  return GFS_OK;
+}
+int gfs_gicp_get_profile(const GfsGicp* h, float* ms8, int* launches8) {
+  GFS_REQUIRE(h && ms8, GFS_ERR_INVALID, "null argument");
+  for (int k = 0; k < 8; k++) { ms8[k] = h->stageMs[k]; if (launches8) launches8[k] = h->stageLaunches[k]; }
+  return GFS_OK;
+}
 
 static int group_build(GfsGicp* h, const GicpDev& D, cudaStream_t st, int mode, int clouds, const float* tgt, const float* src,
                        int stride, int* nGroupsOut) {
@@ -1613,6 +1663,7 @@ static int group_build(GfsGicp* h, const GicpDev& D, cudaStream_t st, int mode, 
 // Voxel downsampling, k-NN grid and covariances of `clouds` clouds (those D.cbase / D.cstep select).
 static int preprocess_clouds(GfsGicp* h, const GicpDev& D, cudaStream_t st, int clouds, const float* d_target, const float* d_source,
                              int stride) {
+  prof_begin(h, st);
   group_build(h, D, st, 0, clouds, d_target, d_source, stride, D.nDown);
   k_voxel_mean<<<dim3(div_up(D.nmax, 256), clouds), 256, 0, st>>>(D, d_target, d_source, stride);
   // grid over the downsampled points (reuses the hash-table storage); group count is not needed
@@ -1621,6 +1672,7 @@ static int preprocess_clouds(GfsGicp* h, const GicpDev& D, cudaStream_t st, int 
     const long long work = (long long)clouds * std::max(D.hsize, D.nmax);
     k_cell_pack<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(D, clouds);
   }
+  prof_mark(h, st, ST_GROUP, 10);
   if (!h->cellKnn) {
     k_knn_cov<<<dim3(div_up(D.nmax, KNN_THREADS), clouds), KNN_THREADS, KNN_SMEM, st>>>(D, 0);
   } else {
@@ -1630,6 +1682,7 @@ static int preprocess_clouds(GfsGicp* h, const GicpDev& D, cudaStream_t st, int 
     k_knn_cov<<<dim3(8, clouds), KNN_THREADS, KNN_SMEM, st>>>(D, 1);
     h->launches += 1;
   }
+  prof_mark(h, st, ST_KNN, h->cellKnn ? 2 : 1);
   h->launches += 3;
   GFS_CUDA(cudaGetLastError());
   return GFS_OK;
@@ -1646,7 +1699,9 @@ static int optimize_pairs(GfsGicp* h, const GicpDev& D, cudaStream_t st, int pai
     if (h->nnMode == 0) k_nn_corr<<<gn, NN_THREADS, 0, st>>>(D, it);
     else if (h->nnMode == 1) k_nn_corr2<false><<<gn, NN_THREADS, 0, st>>>(D, it);
     else k_nn_corr2<true><<<gn, NN_THREADS, 0, st>>>(D, it);
+    prof_mark(h, st, ST_NN);
     k_linearize<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D, it);
+    prof_mark(h, st, ST_LIN);
     k_lm_begin<<<pairs, LIN_THREADS, 0, st>>>(D, it);
     h->launches += 3;
     for (int j = 0; j < 10; j++) {
@@ -1658,10 +1713,13 @@ static int optimize_pairs(GfsGicp* h, const GicpDev& D, cudaStream_t st, int pai
       GFS_CUDA(cudaStreamSynchronize(st));
       if (hc[0] == 0) break;  // no pair needs another lambda trial
     }
+    prof_mark(h, st, ST_LM, 3);
     if (hc[1] == 0) break;  // every pair converged / failed / hit max_iterations
   }
   k_gicp_result<<<div_up(pairs, 128), 128, 0, st>>>(D, pairs, d_out);
   h->launches += 1;
+  prof_mark(h, st, ST_LM);
+  prof_end(h, st);
   GFS_CUDA(cudaGetLastError());
   return GFS_OK;
 }
@@ -1719,7 +1777,7 @@ int gfs_gicp_track_batch_device(GfsGicp* h, void* stream, const float* d_cloud, 
   const bool first = h->trackCalls == 0;
   h->trackCalls++;
   h->trackSeqs = seqs;
-  if (first) return GFS_OK;  // nothing to register the first cloud against
+  if (first) { prof_end(h, st); return GFS_OK; }  // nothing to register the first cloud against
   return optimize_pairs(h, D, st, seqs, d_T0, d_out);
 }
 

@@ -109,6 +109,17 @@ class RegistrationGICP:
     def last_launches(self):
         return self._L.gfs_gicp_last_launches(self._h)
 
+    STAGES = ("group_voxel_pack", "knn_cov", "nn_corr", "linearize", "lm")
+
+    def set_profiling(self, on=True):
+        check(self._L.gfs_gicp_set_profiling(self._h, int(on)))
+
+    def profile(self):
+        """{stage: (ms, launches)} of the last align / track call (CUDA events on the caller's stream)."""
+        ms = np.zeros(8, np.float32); ln = np.zeros(8, np.int32)
+        check(self._L.gfs_gicp_get_profile(self._h, ptr(ms), ptr(ln)))
+        return {k: (float(ms[i]), int(ln[i])) for i, k in enumerate(self.STAGES)}
+
     def knn_stats(self, index, stream=None):
         """(occupied grid cells, queries finished by the per-query kernel) of cloud `index` of the last batch."""
         a, b = C.c_int(), C.c_int()

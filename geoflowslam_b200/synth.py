@@ -140,6 +140,42 @@ def gicp_pair(seed, n_target=50000, max_rot_deg=3.0, max_trans=0.05, noise_z=0.0
     return tgt, src, T
 
 
+def depth_frames(seed, n_frames=4, w=640, h=480, stride=2, n_points=50052, max_rot_deg=3.0, max_trans=0.05, noise_z=0.002,
+                 depth_factor=1000.0, cam=None):
+    """n_frames 16-bit depth images (h, w) of ONE scene (the room and boxes of gicp_pair) seen from n_frames nearby camera
+    poses -- what an RGB-D driver hands to System::TrackRGBD (depth in 1 / depth_factor metres, 0 = invalid).  Even frames
+    sit at the base pose, every odd frame at its own U(+-max_rot_deg, +-max_trans) perturbation of it, so CONSECUTIVE
+    frames (also last -> first of an even-length ring) differ by exactly the configs[2] perturbation (+-3 deg, +-5 cm);
+    each frame has its own depth noise.  Only the pixels Frame::ConvertDepthToPointCloud samples
+    (every `stride`-th row and column, reference src/Frame.cc:606-607) inside a centred window are rendered, sized so that a
+    frame yields about n_points cloud points (configs[2]: 50k); everything else is 0 like the invalid border of a real
+    sensor.  -> (depth uint16 (n_frames, h, w), poses [(R, t) camera-to-world])."""
+    cam = cam or G1_CAM
+    rng = np.random.default_rng(seed)
+    boxes = []
+    for _ in range(5):
+        c = np.array([rng.uniform(-2, 2), rng.uniform(0.3, 1.2), rng.uniform(1.5, 5.0)])
+        sz = rng.uniform(0.2, 0.6, 3)
+        boxes.append((c - sz, c + sz))
+    gw, gh = (w + stride - 1) // stride, (h + stride - 1) // stride
+    ww = min(gw, int(round(np.sqrt(n_points * 4 / 3))))
+    wh = min(gh, int(round(ww * 3 / 4)))
+    u0, v0 = (gw - ww) // 2, (gh - wh) // 2
+    us, vs = np.meshgrid((u0 + np.arange(ww)) * stride, (v0 + np.arange(wh)) * stride)
+    dirs = np.stack([(us.ravel() - cam["cx"]) / cam["fx"], (vs.ravel() - cam["cy"]) / cam["fy"], np.ones(ww * wh)], 1)
+    out = np.zeros((n_frames, h, w), np.uint16)
+    poses = []
+    for k in range(n_frames):
+        R = _rot(np.deg2rad(rng.uniform(-max_rot_deg, max_rot_deg, 3))) if k & 1 else np.eye(3)
+        t = rng.uniform(-max_trans, max_trans, 3) if k & 1 else np.zeros(3)
+        depth = _raycast(t, dirs @ R.T, boxes)
+        ok = np.isfinite(depth) & (depth > 0.3) & (depth < 10.0)
+        z = np.where(ok, depth + rng.normal(0, noise_z, len(depth)), 0.0)
+        out[k, vs.ravel(), us.ravel()] = np.clip(np.rint(z * depth_factor), 0, 65535).astype(np.uint16)
+        poses.append((R, t))
+    return out, poses
+
+
 # ------------------------------------------------------------------------------------------------
 # LocalInertialBA problem (BASELINE configs[3]): 20 KFs on an arc, 3000 points, ~15k stereo
 # observations, 200 Hz IMU preintegrated in float32 as IMU::Preintegrated does

@@ -243,6 +243,11 @@ int gfs_gicp_track_batch(GfsGicp* h, void* stream, const float* cloud, const int
 /* parity hook: downsampled points + covariances of cloud (2*pair = target, 2*pair+1 = source) */
 int gfs_gicp_get_cloud(GfsGicp* h, void* stream, int cloud, double* out_xyz, double* out_cov6, int cap, int* n);
 int gfs_gicp_last_launches(const GfsGicp* h);
+/* measurement aid (bench.py's roofline): with profiling on, every align / track call records a CUDA event after each
+ * stage on the caller's stream and synchronises once more at its end; ms8 / launches8[0..4] = grouping + voxel means + cell
+ * pack, 10-NN covariances (k_knn_cov), correspondence search (k_nn_corr*), linearisation, LM bookkeeping of the last call */
+int gfs_gicp_set_profiling(GfsGicp* h, int on);
+int gfs_gicp_get_profile(const GfsGicp* h, float* ms8, int* launches8);
 /* diagnostics: grid cells of `cloud` and the queries its cell-centric 10-NN pass handed to the per-query kernel */
 int gfs_gicp_get_knn_stats(GfsGicp* h, void* stream, int cloud, int* n_cells, int* n_per_query);
 
