@@ -634,3 +634,75 @@ def vio_sequence(seed=8000, n_frames=20, w=640, h=480, fps=30, imu_rate=200, wal
         imu.append(np.array(rows, np.float32))
     return dict(frames=frames, depth=depth, stamps=np.array(stamps), Rwb=np.array(Rs), twb=np.array(ps), vel=np.array(vels), imu=imu,
                 bg=bg_true, ba=ba_true, Rbc=Rbc, tbc=tbc, cam=cam, gravity=g)
+
+
+def room_sequence(seed=8200, n_frames=30, w=640, h=480, fps=30, imu_rate=200, ppm=260.0, depth_noise=0.0):
+    """Like vio_sequence, but the camera looks into a room CORNER -- front wall x = 3, side wall y = 1.3, floor z = -0.6, each
+    textured -- so that the depth clouds constrain all six degrees of freedom (a single wall lets GICP slide along it).
+    -> the vio_sequence dict plus odom rows per frame interval (vx vy vz in the body frame, 30 Hz)."""
+    rng = np.random.default_rng(seed)
+    cam = G1_CAM
+    Rbc = np.array([[0, 0, 1.0], [-1, 0, 0], [0, -1, 0]])
+    tbc = np.array([0.05, 0.02, 0.01])
+    tex = [scene(seed + i, 1400, 1800, nrect=900) for i in range(3)]
+    g = np.array([0, 0, -9.81])
+    ph = rng.uniform(0, 6.28, 4)
+    # plane = (axis, value, in-plane axes, texture origin in metres)
+    planes = [(0, 3.0, (1, 2), (-3.5, -2.7)), (1, 1.3, (0, 2), (-1.0, -2.7)), (2, -0.6, (0, 1), (-1.0, -3.5))]
+
+    def pose(t):
+        yaw = 0.08 * np.sin(1.1 * t + ph[0]); pitch = 0.04 * np.sin(0.9 * t + ph[1]); roll = 0.03 * np.cos(1.3 * t + ph[2])
+        R = _rot(np.array([0, 0, yaw])) @ _rot(np.array([0, pitch, 0])) @ _rot(np.array([roll, 0, 0]))
+        p = np.array([0.15 * np.sin(0.8 * t + ph[3]), 0.25 * np.sin(0.7 * t), 0.08 * np.sin(0.9 * t)])
+        return R, p
+
+    hh = 1e-4
+    vs, us = np.mgrid[0:h, 0:w].astype(np.float64)
+    dc = np.stack([(us - cam["cx"]) / cam["fx"], (vs - cam["cy"]) / cam["fy"], np.ones_like(us)], -1)
+    frames = np.zeros((n_frames, h, w), np.uint8); depth = np.zeros((n_frames, h, w), np.float32)
+    Rs, ps, vels, stamps = [], [], [], []
+    for k in range(n_frames):
+        t = k / fps
+        R, p = pose(t)
+        Rwc = R @ Rbc; twc = R @ tbc + p
+        dw = dc @ Rwc.T
+        best = np.full((h, w), np.inf); img = np.zeros((h, w), np.float32)
+        for (ax, val, (a, b), (oa, ob)), tx in zip(planes, tex):
+            with np.errstate(divide="ignore", invalid="ignore"):
+                sp = (val - twc[ax]) / dw[..., ax]
+            hit = (sp > 0.05) & (sp < best)
+            P = twc + sp[..., None] * dw
+            tu = np.nan_to_num((P[..., a] - oa) * ppm, nan=-1.0, posinf=-1.0, neginf=-1.0)
+            tv = np.nan_to_num((P[..., b] - ob) * ppm, nan=-1.0, posinf=-1.0, neginf=-1.0)
+            hit &= (tu >= 0) & (tu < tx.shape[1] - 1) & (tv >= 0) & (tv < tx.shape[0] - 1)
+            tu = np.clip(tu, -1.0, tx.shape[1]); tv = np.clip(tv, -1.0, tx.shape[0])
+            u0 = np.clip(np.floor(tu), 0, tx.shape[1] - 2).astype(np.int32); v0 = np.clip(np.floor(tv), 0, tx.shape[0] - 2).astype(np.int32)
+            fu = (tu - u0).astype(np.float32); fv = (tv - v0).astype(np.float32)
+            col = (tx[v0, u0] * (1 - fu) + tx[v0, u0 + 1] * fu) * (1 - fv) + (tx[v0 + 1, u0] * (1 - fu) + tx[v0 + 1, u0 + 1] * fu) * fv
+            img = np.where(hit, col, img); best = np.where(hit, sp, best)
+        img = img + rng.normal(0, 1.0, img.shape).astype(np.float32)
+        frames[k] = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+        d = np.where(np.isfinite(best), best, 0.0)
+        if depth_noise > 0:
+            d = np.where(d > 0, d + rng.normal(0, depth_noise, d.shape), 0.0)
+        depth[k] = d.astype(np.float32)
+        Rs.append(R); ps.append(p); vels.append((pose(t + hh)[1] - pose(t - hh)[1]) / (2 * hh)); stamps.append(t)
+    bg_true = np.array([0.002, -0.001, 0.0015]); ba_true = np.array([0.02, -0.03, 0.01])
+    imu, odom = [], []
+    for k in range(1, n_frames):
+        ta, tb = stamps[k - 1], stamps[k]
+        edges = list(np.arange(ta, tb - 1e-9, 1.0 / imu_rate)) + [tb]
+        rows = []
+        for a, b in zip(edges[:-1], edges[1:]):
+            tm = 0.5 * (a + b)
+            R0, p0 = pose(tm); Rp, pp = pose(tm + hh); Rm, pm = pose(tm - hh)
+            a_w = (pp - 2 * p0 + pm) / (hh * hh)
+            dRm = R0.T @ (Rp - Rm) / (2 * hh)
+            gyr = np.array([dRm[2, 1], dRm[0, 2], dRm[1, 0]]) + bg_true + rng.normal(0, 2e-4, 3)
+            acc = R0.T @ (a_w - g) + ba_true + rng.normal(0, 2e-3, 3)
+            rows.append(np.concatenate([acc, gyr, [b - a]]))
+        imu.append(np.array(rows, np.float32))
+        Rm_, _ = pose(0.5 * (ta + tb))
+        odom.append((Rm_.T @ ((ps[k] - ps[k - 1]) / (tb - ta))).astype(np.float32).reshape(1, 3))
+    return dict(frames=frames, depth=depth, stamps=np.array(stamps), Rwb=np.array(Rs), twb=np.array(ps), vel=np.array(vels), imu=imu,
+                odom=odom, bg=bg_true, ba=ba_true, Rbc=Rbc, tbc=tbc, cam=cam, gravity=g)
