@@ -87,6 +87,9 @@ SIGNATURES = {
     "gfs_ba_download": ([vp, vp, vp, ci], ci),
     "gfs_ba_last_launches": ([vp], ci),
     "gfs_ba_set_partition": ([vp, ci, ci, vp, vp], ci),
+    "gfs_nccl_unique_id": ([vp], ci),
+    "gfs_ba_set_partition_nccl": ([vp, ci, ci, vp], ci),
+    "gfs_ba_last_nccl_calls": ([vp], ci),
     "gfs_pose_create": ([ci, ci, C.POINTER(vp)], ci),
     "gfs_pose_destroy": ([vp], ci),
     "gfs_pose_optimize_batch": ([vp, vp, vp, ci, vp], ci),

@@ -23,6 +23,8 @@
 #include <cmath>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "common.cuh"
 #include "inertial.cuh"
 
@@ -1177,8 +1179,54 @@ struct GfsBa {
   int launches = 0;
   GfsAllReduceFn allreduce = nullptr;
   void* allreduceUser = nullptr;
+  void* ncclComm = nullptr;  // ncclComm_t of the partition (gfs_ba_set_partition_nccl): collectives go straight onto the solve stream
+  int ncclCalls = 0;         // grouped NCCL launches of the last solve
   DevBuf redBuf;
 };
+
+// ---- NCCL, bound at run time (dlopen): the library must load on machines without NCCL (single-GPU use, the CPU-only build
+// check), so nothing is linked.  Prototypes as in <nccl.h> (2.x ABI: ncclUniqueId is 128 bytes, passed by value).
+namespace ncclrt {
+struct UniqueId { char internal[128]; };
+typedef int (*GetUniqueIdFn)(UniqueId*);
+typedef int (*CommInitRankFn)(void**, int, UniqueId, int);
+typedef int (*CommDestroyFn)(void*);
+typedef int (*AllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*GroupFn)();
+typedef const char* (*ErrStrFn)(int);
+static const int kDouble = 8, kSum = 0;  // ncclFloat64, ncclSum
+struct Api {
+  void* lib = nullptr;
+  GetUniqueIdFn getUniqueId = nullptr;
+  CommInitRankFn commInitRank = nullptr;
+  CommDestroyFn commDestroy = nullptr;
+  AllReduceFn allReduce = nullptr;
+  GroupFn groupStart = nullptr, groupEnd = nullptr;
+  ErrStrFn errStr = nullptr;
+};
+static Api* api() {
+  static Api a;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    // the copy the process already has (torch's bundled NCCL), else the system one
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (lib) {
+      a.lib = lib;
+      a.getUniqueId = (GetUniqueIdFn)dlsym(lib, "ncclGetUniqueId");
+      a.commInitRank = (CommInitRankFn)dlsym(lib, "ncclCommInitRank");
+      a.commDestroy = (CommDestroyFn)dlsym(lib, "ncclCommDestroy");
+      a.allReduce = (AllReduceFn)dlsym(lib, "ncclAllReduce");
+      a.groupStart = (GroupFn)dlsym(lib, "ncclGroupStart");
+      a.groupEnd = (GroupFn)dlsym(lib, "ncclGroupEnd");
+      a.errStr = (ErrStrFn)dlsym(lib, "ncclGetErrorString");
+    }
+  }
+  return (a.lib && a.getUniqueId && a.commInitRank && a.commDestroy && a.allReduce && a.groupStart && a.groupEnd) ? &a : nullptr;
+}
+}  // namespace ncclrt
 
 template <class T>
 static int dev_alloc(GfsBa* h, T** p, size_t count) {
@@ -1251,6 +1299,9 @@ int gfs_ba_destroy(GfsBa* h) {
   for (DevBuf& b : h->bufs) b.release();
   h->redBuf.release();
   h->h_counters.release();
+  if (h->ncclComm) {
+    if (ncclrt::Api* n = ncclrt::api()) n->commDestroy(h->ncclComm);
+  }
   delete h;
   return GFS_OK;
 }
@@ -1261,12 +1312,52 @@ int gfs_ba_set_partition(GfsBa* h, int rank, int world, GfsAllReduceFn allreduce
   GFS_REQUIRE(h, GFS_ERR_INVALID, "null handle");
   GFS_REQUIRE(world >= 1 && rank >= 0 && rank < world, GFS_ERR_INVALID, "bad rank/world");
   GFS_REQUIRE(world == 1 || allreduce, GFS_ERR_INVALID, "partitioned mode needs an all-reduce callback");
+  if (h->ncclComm) {
+    if (ncclrt::Api* n = ncclrt::api()) n->commDestroy(h->ncclComm);
+    h->ncclComm = nullptr;
+  }
   h->dev.rank = rank;
   h->dev.world = world;
   h->allreduce = allreduce;
   h->allreduceUser = user;
   return GFS_OK;
 }
+
+int gfs_nccl_unique_id(void* out128) {
+  GFS_REQUIRE(out128, GFS_ERR_INVALID, "null pointer");
+  ncclrt::Api* n = ncclrt::api();
+  GFS_REQUIRE(n, GFS_ERR_INVALID, "libnccl.so.2 not found (dlopen)");
+  ncclrt::UniqueId id;
+  const int rc = n->getUniqueId(&id);
+  if (rc != 0) { gfs::set_error("ncclGetUniqueId -> %s", n->errStr ? n->errStr(rc) : "error"); return GFS_ERR_CUDA; }
+  memcpy(out128, &id, sizeof(id));
+  return GFS_OK;
+}
+
+int gfs_ba_set_partition_nccl(GfsBa* h, int rank, int world, const void* unique_id128) {
+  GFS_REQUIRE(h, GFS_ERR_INVALID, "null handle");
+  GFS_REQUIRE(world >= 1 && rank >= 0 && rank < world, GFS_ERR_INVALID, "bad rank/world");
+  ncclrt::Api* n = ncclrt::api();
+  if (h->ncclComm && n) { n->commDestroy(h->ncclComm); h->ncclComm = nullptr; }
+  h->dev.rank = rank;
+  h->dev.world = world;
+  h->allreduce = nullptr;
+  h->allreduceUser = nullptr;
+  if (world == 1) return GFS_OK;
+  GFS_REQUIRE(unique_id128, GFS_ERR_INVALID, "null unique id");
+  GFS_REQUIRE(n, GFS_ERR_INVALID, "libnccl.so.2 not found (dlopen)");
+  ncclrt::UniqueId id;
+  memcpy(&id, unique_id128, sizeof(id));
+  const int rc = n->commInitRank(&h->ncclComm, world, id, rank);
+  if (rc != 0) {
+    h->ncclComm = nullptr; h->dev.rank = 0; h->dev.world = 1;
+    gfs::set_error("ncclCommInitRank -> %s", n->errStr ? n->errStr(rc) : "error");
+    return GFS_ERR_CUDA;
+  }
+  return GFS_OK;
+}
+
+int gfs_ba_last_nccl_calls(const GfsBa* h) { return h ? h->ncclCalls : GFS_ERR_INVALID; }
 
 int gfs_ba_upload(GfsBa* h, void* stream, const GfsBaProblem* problems, int batch) {
   GFS_REQUIRE(h && problems, GFS_ERR_INVALID, "null pointer");
@@ -1374,11 +1465,29 @@ int gfs_ba_upload(GfsBa* h, void* stream, const GfsBaProblem* problems, int batc
   return GFS_OK;
 }
 
-static int ba_allreduce(GfsBa* h, cudaStream_t st, double* buf, int count) {
+// In-place SUM over the ranks of up to four fp64 device buffers.  With an NCCL communicator (gfs_ba_set_partition_nccl) they go
+// out as ONE grouped launch on the solve stream, with no host synchronisation; the callback mode (gfs_ba_set_partition) syncs
+// and calls out once per buffer.
+struct RedBuf { double* p; int n; };
+static int ba_allreduce(GfsBa* h, cudaStream_t st, std::initializer_list<RedBuf> bufs) {
   if (h->dev.world <= 1) return GFS_OK;
+  if (h->ncclComm) {
+    ncclrt::Api* n = ncclrt::api();
+    int rc = n->groupStart();
+    for (const RedBuf& b : bufs)
+      if (rc == 0 && b.n > 0) rc = n->allReduce(b.p, b.p, (size_t)b.n, ncclrt::kDouble, ncclrt::kSum, h->ncclComm, st);
+    const int rc2 = n->groupEnd();
+    if (rc == 0) rc = rc2;
+    if (rc != 0) { gfs::set_error("ncclAllReduce -> %s", n->errStr ? n->errStr(rc) : "error"); return GFS_ERR_CUDA; }
+    h->ncclCalls++;
+    return GFS_OK;
+  }
+  GFS_REQUIRE(h->allreduce, GFS_ERR_INVALID, "partitioned mode without a communicator or callback");
   GFS_CUDA(cudaStreamSynchronize(st));
-  const int rc = h->allreduce(buf, count, h->allreduceUser);
-  GFS_REQUIRE(rc == 0, GFS_ERR_CUDA, "all-reduce callback failed");
+  for (const RedBuf& b : bufs) {
+    const int rc = h->allreduce(b.p, b.n, h->allreduceUser);
+    GFS_REQUIRE(rc == 0, GFS_ERR_CUDA, "all-reduce callback failed");
+  }
   return GFS_OK;
 }
 
@@ -1408,16 +1517,16 @@ int gfs_ba_solve_uploaded(GfsBa* h, void* stream) {
     k_in_error<<<gIn, 32, 0, st>>>(D, flag);
     h->launches += 2;
   };
-  auto reduce_chi = [&]() -> int {  // partitioned mode: sum the chi2 partials over ranks
+  h->ncclCalls = 0;
+  auto reduce_chi = [&](bool withScale) -> int {  // partitioned mode: sum the chi2 partials (and the gain-ratio scale) over ranks
     if (!part) return GFS_OK;
-    int rc = ba_allreduce(h, st, D.partChi, B * D.nblk);
-    if (rc) return rc;
-    if ((rc = ba_allreduce(h, st, D.icpRho, B * D.maxIn))) return rc;
-    return ba_allreduce(h, st, D.inRho, B * D.maxIn);
+    if (withScale)
+      return ba_allreduce(h, st, {{D.partChi, B * D.nblk}, {D.icpRho, B * D.maxIn}, {D.inRho, B * D.maxIn}, {D.partScale, B * D.nblk}});
+    return ba_allreduce(h, st, {{D.partChi, B * D.nblk}, {D.icpRho, B * D.maxIn}, {D.inRho, B * D.maxIn}});
   };
   int rc;
   errors(J_ACTIVE);
-  if ((rc = reduce_chi())) return rc;
+  if ((rc = reduce_chi(false))) return rc;
   k_lm_control<<<div_up(B, 128), 128, 0, st>>>(D, B, 0, 0);
   h->launches += 2;
   int maxIt = 0;
@@ -1426,7 +1535,7 @@ int gfs_ba_solve_uploaded(GfsBa* h, void* stream) {
   for (int it = 0; it < maxIt; it++) {
     GFS_CUDA(cudaMemsetAsync(D.counters, 0, 8, st));
     errors(J_ACTIVE);  // computeActiveErrors at the current estimate
-    if ((rc = reduce_chi())) return rc;
+    if ((rc = reduce_chi(false))) return rc;
     k_lm_control<<<div_up(B, 128), 128, 0, st>>>(D, B, 1, it);
     GFS_CUDA(cudaMemsetAsync(D.Hpp, 0, (size_t)B * D.maxDim * D.maxDim * 8, st));
     GFS_CUDA(cudaMemsetAsync(D.bp, 0, (size_t)B * D.maxDim * 8, st));
@@ -1442,16 +1551,12 @@ int gfs_ba_solve_uploaded(GfsBa* h, void* stream) {
       k_schur_pairs<<<gPairs, 128, 0, st>>>(D);
       k_schur_rhs<<<gKfW, 128, 0, st>>>(D);
       if (part) {  // sum of the per-shard reduced systems = the single-shard system
-        if ((rc = ba_allreduce(h, st, D.Hs, B * D.maxDim * D.maxDim))) return rc;
-        if ((rc = ba_allreduce(h, st, D.bs, B * D.maxDim))) return rc;
+        if ((rc = ba_allreduce(h, st, {{D.Hs, B * D.maxDim * D.maxDim}, {D.bs, B * D.maxDim}}))) return rc;
       }
       k_ldlt_solve<<<B, LDLT_THREADS, ldltSmem, st>>>(D);
       k_backsub_update<<<gUpd, 128, 0, st>>>(D);
       errors(J_NEED);
-      if (part) {
-        if ((rc = reduce_chi())) return rc;
-        if ((rc = ba_allreduce(h, st, D.partScale, B * D.nblk))) return rc;
-      }
+      if ((rc = reduce_chi(true))) return rc;
       GFS_CUDA(cudaMemsetAsync(D.counters, 0, 4, st));
       k_lm_control<<<div_up(B, 128), 128, 0, st>>>(D, B, 2, it);
       k_restore<<<gCopy, 256, 0, st>>>(D);

@@ -152,6 +152,27 @@ class Optimizer:
     def last_launches(self):
         return self._L.gfs_ba_last_launches(self._h)
 
+    def set_partition_nccl(self, rank, world, group=None):
+        """Edge-partitioned mode with NCCL called directly from the solve (no Python in the loop): rank 0 creates the NCCL
+        unique id, torch.distributed broadcasts its 128 bytes (any backend), every rank joins the communicator."""
+        import numpy as np
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            uid = np.zeros(128, np.uint8)
+            if rank == 0:
+                check(self._L.gfs_nccl_unique_id(uid.ctypes.data_as(C.c_void_p)))
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            t = torch.from_numpy(uid).to(dev)
+            dist.broadcast(t, src=0, group=group)
+            uid = t.cpu().numpy()
+            check(self._L.gfs_ba_set_partition_nccl(self._h, int(rank), int(world), uid.ctypes.data_as(C.c_void_p)))
+        else:
+            check(self._L.gfs_ba_set_partition_nccl(self._h, 0, 1, None))
+
+    def last_nccl_calls(self):
+        return self._L.gfs_ba_last_nccl_calls(self._h)
+
     def set_partition(self, rank, world, group=None):
         """Edge-partitioned mode: this rank owns landmarks p % world == rank; the reduced pose system
         is all-reduced over `group` (torch.distributed, NCCL) once per LM trial."""

@@ -332,6 +332,14 @@ int gfs_ba_last_launches(const GfsBa* h);
  * thin wrapper over ncclAllReduce / torch.distributed.all_reduce) once per LM trial. */
 typedef int (*GfsAllReduceFn)(double* device_buf, int count, void* user);
 int gfs_ba_set_partition(GfsBa* h, int rank, int world, GfsAllReduceFn allreduce, void* user);
+/* The same partition with NCCL called directly: the per-trial sums -- [Hs | bs] before the reduced solve and
+ * [chi2 partials | robust weights | gain-ratio scale] after the update -- go out as ONE grouped ncclAllReduce launch each on the
+ * solve stream (NVLink / NVSwitch), with no host synchronisation and no callback.  libnccl.so.2 is bound with dlopen when this
+ * is first called.  Rank 0 obtains the 128-byte id from gfs_nccl_unique_id and distributes it (e.g. a torch.distributed
+ * broadcast); every rank then calls gfs_ba_set_partition_nccl with its CUDA device current.  world == 1 leaves partitioned mode. */
+int gfs_nccl_unique_id(void* out128);
+int gfs_ba_set_partition_nccl(GfsBa* h, int rank, int world, const void* unique_id128);
+int gfs_ba_last_nccl_calls(const GfsBa* h);
 
 /* ------------------------------------------------------------------------------------------------
  * Motion-only bundle adjustment of the tracking thread.
