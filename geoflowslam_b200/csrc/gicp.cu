@@ -59,6 +59,8 @@ struct GicpDev {
   uint4* tab;                // [clouds][hsize] kNN grid slot {key lo, key hi, start, count}: one 16-byte probe
   double* rec;               // [clouds][nmax][4] downsampled points in cell order {x, y, z, index bits}
   float4* recf;              // [clouds][nmax] the same records as float32 RELATIVE TO THEIR CELL's origin {x, y, z, index bits}
+  uint2* oct;                // [clouds][hsize] per occupied cell: its records are sorted by octant (bit 0 / 1 / 2 = upper half in
+                             // x / y / z); eight 8-bit counts.  0xffffffff, 0xffffffff: more than 255 records, not sorted
   float nnBoundA;            // error bound of a float32 cell-local squared distance v: nnBoundA * sqrt(v) + 5e-7 * v + 1e-14
   double* cov;               // [clouds][nmax][6]
   // per pair
@@ -268,6 +270,46 @@ __global__ void __launch_bounds__(256) k_voxel_mean(GicpDev D, const float* __re
   o[0] = sx / w; o[1] = sy / w; o[2] = sz / w; o[3] = 1.0;
 }
 
+// ---- octant order inside a grid cell.  One thread per hash slot: the cell's member list is counting-sorted by the octant of
+// the cell each point falls in (decided in fp64 from the cell's origin, the expression every search recomputes), written to
+// slotOf[] (free between the grouping and the searches) where k_cell_pack picks it up, and the eight counts are packed into
+// oct[].  A search that knows how far it has to look visits only the octants its ball reaches (k_nn_corr2), and the 10-NN
+// kernel skips whole octants that cannot hold a neighbour (k_knn_cov_warp): a 0.1 m cell holds ~25 points, an octant ~3-6.
+__global__ void __launch_bounds__(256) k_cell_sort(GicpDev D, int clouds) {
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= (long long)clouds * D.hsize) return;
+  const int c = cloud_of(D, (int)(i0 / D.hsize));
+  const size_t i = (size_t)c * D.hsize + (size_t)(i0 % D.hsize);
+  const unsigned long long key = D.keys[i];
+  if (key == KEY_EMPTY) { D.oct[i] = make_uint2(0u, 0u); return; }
+  const int cnt = D.count[i], st = D.start[i];
+  const int* mem = D.members + (size_t)c * D.nmax + st;
+  int* out = D.slotOf + (size_t)c * D.nmax + st;
+  if (cnt > 255) {
+    for (int j = 0; j < cnt; j++) out[j] = mem[j];
+    D.oct[i] = make_uint2(0xffffffffu, 0xffffffffu);
+    return;
+  }
+  const int off = 1 << 20;
+  const double ox = (double)((int)(key & 0x1fffff) - off) * D.cell, oy = (double)((int)((key >> 21) & 0x1fffff) - off) * D.cell,
+               oz = (double)((int)((key >> 42) & 0x1fffff) - off) * D.cell;
+  const double half = 0.5 * D.cell;
+  const double* pts = D.pts + (size_t)c * D.nmax * 4;
+  auto octant = [&](int pi) -> int {
+    const double* p = pts + (size_t)pi * 4;
+    return ((p[0] - ox >= half) ? 1 : 0) | ((p[1] - oy >= half) ? 2 : 0) | ((p[2] - oz >= half) ? 4 : 0);
+  };
+  unsigned long long n8 = 0;  // eight byte counters
+  for (int j = 0; j < cnt; j++) n8 += 1ull << (8 * octant(mem[j]));
+  unsigned long long cur = n8 * 0x0101010101010100ull;  // byte k = sum of the bytes below k (no carries: total <= 255)
+  for (int j = 0; j < cnt; j++) {
+    const int pi = mem[j], o = octant(pi);
+    out[(int)((cur >> (8 * o)) & 0xffull)] = pi;
+    cur += 1ull << (8 * o);
+  }
+  D.oct[i] = make_uint2((unsigned)n8, (unsigned)(n8 >> 32));
+}
+
 // ---- k-NN grid: packed slot table + points stored in cell order
 __global__ void __launch_bounds__(256) k_cell_pack(GicpDev D, int clouds) {
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -283,7 +325,7 @@ __global__ void __launch_bounds__(256) k_cell_pack(GicpDev D, int clouds) {
     const int c = cloud_of(D, (int)(i0 / D.nmax)), m = (int)(i0 % D.nmax);
     const size_t i = (size_t)c * D.nmax + m;
     if (m < D.nDown[c]) {
-      const int pi = D.members[i];
+      const int pi = D.slotOf[i];   // the cell's members in octant order (k_cell_sort)
       const double2* p = reinterpret_cast<const double2*>(D.pts + ((size_t)c * D.nmax + pi) * 4);
       double2* o = reinterpret_cast<double2*>(D.rec + (size_t)i * 4);
       const double2 xy = p[0];
@@ -303,6 +345,7 @@ struct Grid {
   const uint4* tab;
   const double2* rec;
   const float4* recf;
+  const uint2* oct;
   const double* pts;
   int hm;
 };
@@ -311,6 +354,7 @@ __device__ __forceinline__ Grid make_grid(const GicpDev& D, int c) {
   g.tab = D.tab + (size_t)c * D.hsize;
   g.rec = reinterpret_cast<const double2*>(D.rec + (size_t)c * D.nmax * 4);
   g.recf = D.recf + (size_t)c * D.nmax;
+  g.oct = D.oct + (size_t)c * D.hsize;
   g.pts = D.pts + (size_t)c * D.nmax * 4;
   g.hm = D.hsize - 1;
   return g;
@@ -324,6 +368,19 @@ __device__ __forceinline__ bool grid_find(const Grid& g, int cx, int cy, int cz,
     const uint4 e = __ldg(&g.tab[h]);
     const unsigned long long k = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
     if (k == key) { start = (int)e.z; count = (int)e.w; return true; }
+    if (k == KEY_EMPTY) return false;
+    h = (h + 1) & g.hm;
+  }
+}
+// the same, also returning the hash slot (index into oct[])
+__device__ __forceinline__ bool grid_find_slot(const Grid& g, int cx, int cy, int cz, int& start, int& count, int& slot) {
+  if ((unsigned)cx > 0x1fffffu || (unsigned)cy > 0x1fffffu || (unsigned)cz > 0x1fffffu) return false;
+  const unsigned long long key = (unsigned long long)cx | ((unsigned long long)cy << 21) | ((unsigned long long)cz << 42);
+  int h = (int)(mix64(key) & g.hm);
+  while (true) {
+    const uint4 e = __ldg(&g.tab[h]);
+    const unsigned long long k = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
+    if (k == key) { start = (int)e.z; count = (int)e.w; slot = h; return true; }
     if (k == KEY_EMPTY) return false;
     h = (h + 1) & g.hm;
   }
@@ -1059,8 +1116,8 @@ __device__ __forceinline__ void scan_cell_nn1f(const Grid& g, int s, int n, floa
 template <class Limit, class Visit>
 __device__ __forceinline__ void visit_ball(const Grid& g, const int* box, const ShellQuery& q, Limit limit, Visit visit) {
   {
-    int cs, cn;
-    if (grid_find(g, q.cx, q.cy, q.cz, cs, cn)) visit(cs, cn, q.cx, q.cy, q.cz);
+    int cs, cn, slot;
+    if (grid_find_slot(g, q.cx, q.cy, q.cz, cs, cn, slot)) visit(cs, cn, q.cx, q.cy, q.cz, slot);
   }
   const double lim0 = limit();
   if (lim0 <= q.margin * q.margin) return;  // the ball stays inside the home cell
@@ -1077,14 +1134,49 @@ __device__ __forceinline__ void visit_ball(const Grid& g, const int* box, const 
       for (int x = x0; x <= x1; x++) {
         if (x == q.cx && y == q.cy && z == q.cz) continue;
         if (gyz2 + axis_gap2(x - q.cx, q.fx, q.cell) > limit()) continue;
-        int cs, cn;
-        if (grid_find(g, x, y, z, cs, cn)) visit(cs, cn, x, y, z);
+        int cs, cn, slot;
+        if (grid_find_slot(g, x, y, z, cs, cn, slot)) visit(cs, cn, x, y, z, slot);
       }
     }
   }
 }
 
-template <bool F32>
+// The octants of cell (x, y, z) a ball of squared radius lim around the query can reach, as an 8-bit mask (bit o = octant o of
+// k_cell_sort).  Per axis the lower half [0, cell/2) and the upper half [cell/2, cell) of the cell are tested against
+// [l - R, l + R] (l = query coordinate relative to the cell's origin, R inflated by 1e-6 relative + 1e-9: the octant of a
+// point is decided in fp64 from the same origin, so 1e-9 m covers the rounding of that decision many times over).
+__device__ __forceinline__ unsigned octant_mask(const double q[3], int x, int y, int z, double cell, double lim) {
+  const int off = 1 << 20;
+  const double R = sqrt(lim) * 1.000001 + 1e-9, half = 0.5 * cell;
+  const double l[3] = {q[0] - (double)(x - off) * cell, q[1] - (double)(y - off) * cell, q[2] - (double)(z - off) * cell};
+  const unsigned lo[3] = {0x55u, 0x33u, 0x0fu}, hi[3] = {0xaau, 0xccu, 0xf0u};  // octants in the lower / upper half along x, y, z
+  unsigned m = 0xffu;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    unsigned ma = 0;
+    if (l[a] - R < half && l[a] + R >= 0.0) ma |= lo[a];
+    if (l[a] + R >= half && l[a] - R < cell) ma |= hi[a];
+    m &= ma;
+  }
+  return m;
+}
+// scan(first record, count) for every octant of the cell whose bit is set in `mask`
+template <class Scan>
+__device__ __forceinline__ void for_octants(const Grid& g, int slot, int cs, int cn, unsigned mask, Scan scan) {
+  const uint2 oc = __ldg(&g.oct[slot]);
+  if (oc.x == 0xffffffffu && oc.y == 0xffffffffu) { scan(cs, cn); return; }  // an unsorted (overfull) cell: all of it
+  unsigned long long n8 = (unsigned long long)oc.x | ((unsigned long long)oc.y << 32);
+  int r = cs;
+#pragma unroll
+  for (int o = 0; o < 8; o++) {
+    const int c = (int)(n8 & 0xffull);
+    n8 >>= 8;
+    if (c && ((mask >> o) & 1u)) scan(r, c);
+    r += c;
+  }
+}
+
+template <bool F32, bool OCT>
 __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr2(GicpDev D, int iter) {
   const int p = blockIdx.y;
   if (!D.istate[p * LM_ISTATE + I_ACTIVE]) return;
@@ -1126,10 +1218,14 @@ __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr2(GicpDev D, int iter)
     auto ub = [&]() -> double { return nf.v1 < FLT_MAX ? (double)nf.v1 + (double)nn_bound(nf.v1, D.nnBoundA) : DBL_MAX; };
     const int off = 1 << 20;
     visit_ball(g, box, sq, [&]() { return fmin(ub(), capf); },
-               [&](int cs_, int cn_, int x, int y, int z) {
+               [&](int cs_, int cn_, int x, int y, int z, int slot) {
                  const float qx = (float)(q[0] - (double)(x - off) * D.cell), qy = (float)(q[1] - (double)(y - off) * D.cell),
                              qz = (float)(q[2] - (double)(z - off) * D.cell);
-                 scan_cell_nn1f(g, cs_, cn_, qx, qy, qz, nf);
+                 if (OCT)
+                   for_octants(g, slot, cs_, cn_, octant_mask(q, x, y, z, D.cell, fmin(ub(), capf)),
+                               [&](int r0, int rn) { scan_cell_nn1f(g, r0, rn, qx, qy, qz, nf); });
+                 else
+                   scan_cell_nn1f(g, cs_, cn_, qx, qy, qz, nf);
                });
     // the best is the exact nearest neighbour iff no other candidate can be as close: the runner-up's lower bound is
     // above the best's upper bound (a seed that was never beaten carries an exact upper bound already)
@@ -1148,7 +1244,13 @@ __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr2(GicpDev D, int iter)
     // the previous iteration's correspondence is a real target point: starting from it only tightens the radius
     if (prev >= 0) nn.push(prev, sqdist3(g.pts + (size_t)prev * 4, q[0], q[1], q[2]));
     visit_ball(g, box, sq, [&]() { return fmin(nn.d, cap); },
-               [&](int cs_, int cn_, int, int, int) { scan_cell_nn1(g, cs_, cn_, q[0], q[1], q[2], nn); });
+               [&](int cs_, int cn_, int x, int y, int z, int slot) {
+                 if (OCT)
+                   for_octants(g, slot, cs_, cn_, octant_mask(q, x, y, z, D.cell, fmin(nn.d, cap)),
+                               [&](int r0, int rn) { scan_cell_nn1(g, r0, rn, q[0], q[1], q[2], nn); });
+                 else
+                   scan_cell_nn1(g, cs_, cn_, q[0], q[1], q[2], nn);
+               });
     id = nn.id; d = nn.d;
   }
   D.corr[(size_t)p * D.nmax + i] = (id != 0x7fffffff && !(d > max_d2)) ? id : -1;  // DistanceRejector: sq_dist > max_dist_sq
@@ -1481,13 +1583,14 @@ using namespace gfs;
 struct GfsGicp {
   GicpDev dev;
   int maxPairs = 0;
-  DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_nFall, b_box, b_pts, b_cov, b_tab, b_rec, b_recf,
+  DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_nFall, b_box, b_pts, b_cov, b_tab, b_rec, b_recf, b_oct,
       b_corr, b_maha, b_partial, b_partialE, b_state, b_istate, b_counters;
   DevBuf b_tgt, b_src, b_n, b_T0, b_res;
   PinnedBuf h_counters;
   int launches = 0;
   bool cellKnn = false;  // GFS_GICP_KNN_CELLS=1: cell-centric 10-NN kernel first (same results)
-  int nnMode = 1;        // GFS_GICP_NN: 0 = k_nn_corr (shell walk), 1 = k_nn_corr2 in fp64 (default: measured fastest), 2 = k_nn_corr2 with the float32 prefilter
+  int nnMode = 3;        // GFS_GICP_NN: 0 = k_nn_corr (shell walk), 1 = k_nn_corr2 (ball walk, fp64), 2 = + float32 prefilter, 3 = ball walk over octants (fp64), 4 = octants + float32 prefilter
+  int knnMode = 1;       // GFS_GICP_KNN: 0 = k_knn_cov (thread per query), 1 = k_knn_cov_warp (warp per cell, octant skipping) + k_knn_cov for what it hands over
   int trackCalls = 0;    // gfs_gicp_track_*: calls since the last reset (the new cloud goes to slot trackCalls & 1)
   int trackSeqs = 0;
   // optional per-stage CUDA-event timing of one call (gfs_gicp_set_profiling): an event after every stage, read back at
@@ -1580,6 +1683,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   D.cellOrder = 1;
   if (const char* e = getenv("GFS_GICP_ORDER")) D.cellOrder = atoi(e) != 0;  // 0: queries in point order (first generation)
   if (const char* e = getenv("GFS_GICP_NN")) h->nnMode = atoi(e);
+  if (const char* e = getenv("GFS_GICP_KNN")) h->knnMode = atoi(e);
   D.rot_eps = s.rotation_eps;
   D.trans_eps = s.translation_eps;
   D.k = s.num_neighbors;
@@ -1611,6 +1715,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   RES(b_tab, C * H * 16, tab, uint4*)
   RES(b_rec, C * N * 32, rec, double*)
   RES(b_recf, C * N * 16, recf, float4*)
+  RES(b_oct, C * H * 8, oct, uint2*)
   RES(b_corr, P * N * 4, corr, int*)
   RES(b_maha, P * N * 72, maha, double*)
   RES(b_partial, P * D.nblk * (LIN_THREADS / 32) * RED_N * 8, partial, double*)
@@ -1627,7 +1732,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
 int gfs_gicp_destroy(GfsGicp* h) {
   if (!h) return GFS_OK;
   DevBuf* d[] = {&h->b_keys, &h->b_minIdx, &h->b_count, &h->b_start, &h->b_cursor, &h->b_rank, &h->b_slotOf, &h->b_members,
-                 &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_nFall, &h->b_box, &h->b_pts, &h->b_cov, &h->b_tab, &h->b_rec, &h->b_recf, &h->b_corr, &h->b_maha, &h->b_partial,
+                 &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_nFall, &h->b_box, &h->b_pts, &h->b_cov, &h->b_tab, &h->b_rec, &h->b_recf, &h->b_oct, &h->b_corr, &h->b_maha, &h->b_partial,
                  &h->b_partialE, &h->b_state, &h->b_istate, &h->b_counters, &h->b_tgt, &h->b_src, &h->b_n, &h->b_T0, &h->b_res};
   for (DevBuf* b : d) b->release();
   h->h_counters.release();
@@ -1669,10 +1774,13 @@ static int preprocess_clouds(GfsGicp* h, const GicpDev& D, cudaStream_t st, int 
   // grid over the downsampled points (reuses the hash-table storage); group count is not needed
   group_build(h, D, st, 1, clouds, nullptr, nullptr, 0, D.nCells);
   {
+    const long long slots = (long long)clouds * D.hsize;
+    k_cell_sort<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(D, clouds);
     const long long work = (long long)clouds * std::max(D.hsize, D.nmax);
     k_cell_pack<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(D, clouds);
+    h->launches += 1;
   }
-  prof_mark(h, st, ST_GROUP, 10);
+  prof_mark(h, st, ST_GROUP, 11);
   if (!h->cellKnn) {
     k_knn_cov<<<dim3(div_up(D.nmax, KNN_THREADS), clouds), KNN_THREADS, KNN_SMEM, st>>>(D, 0);
   } else {
@@ -1697,8 +1805,10 @@ static int optimize_pairs(GfsGicp* h, const GicpDev& D, cudaStream_t st, int pai
     GFS_CUDA(cudaMemsetAsync(D.counters, 0, 8, st));
     const dim3 gn(div_up(D.nmax, NN_THREADS), pairs);
     if (h->nnMode == 0) k_nn_corr<<<gn, NN_THREADS, 0, st>>>(D, it);
-    else if (h->nnMode == 1) k_nn_corr2<false><<<gn, NN_THREADS, 0, st>>>(D, it);
-    else k_nn_corr2<true><<<gn, NN_THREADS, 0, st>>>(D, it);
+    else if (h->nnMode == 1) k_nn_corr2<false, false><<<gn, NN_THREADS, 0, st>>>(D, it);
+    else if (h->nnMode == 2) k_nn_corr2<true, false><<<gn, NN_THREADS, 0, st>>>(D, it);
+    else if (h->nnMode == 3) k_nn_corr2<false, true><<<gn, NN_THREADS, 0, st>>>(D, it);
+    else k_nn_corr2<true, true><<<gn, NN_THREADS, 0, st>>>(D, it);
     prof_mark(h, st, ST_NN);
     k_linearize<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D, it);
     prof_mark(h, st, ST_LIN);
