@@ -59,6 +59,8 @@ struct GicpDev {
   uint4* tab;                // [clouds][hsize] kNN grid slot {key lo, key hi, start, count}: one 16-byte probe
   double* rec;               // [clouds][nmax][4] downsampled points in cell order {x, y, z, index bits}
   float4* recf;              // [clouds][nmax] the same records as float32 RELATIVE TO THEIR CELL's origin {x, y, z, index bits}
+  int* knnList;              // [clouds][nmax][16] candidates k_knn_cov_warp hands to k_knn_select_cov
+  unsigned char* knnCnt;     // [clouds][nmax] their number (0: the query went to the hand-over list instead)
   uint2* oct;                // [clouds][hsize] per occupied cell: its records are sorted by octant (bit 0 / 1 / 2 = upper half in
                              // x / y / z); eight 8-bit counts.  0xffffffff, 0xffffffff: more than 255 records, not sorted
   float nnBoundA;            // error bound of a float32 cell-local squared distance v: nnBoundA * sqrt(v) + 5e-7 * v + 1e-14
@@ -972,6 +974,220 @@ __global__ void __launch_bounds__(KC_THREADS) k_knn_cov_cells(GicpDev D) {
   }
 }
 
+// ---- 10-NN + covariance, third generation: ONE WARP PER GRID CELL (the default; GFS_GICP_KNN=0 selects k_knn_cov alone).
+// The lanes of a warp take the points of one cell as their queries (a 0.1 m cell holds about a warp's worth), so the
+// candidate set -- the 3x3x3 block of cells around it -- is the same for all of them:
+//  * 27 lanes probe the 27 cells at once (one hash chain each instead of 27 dependent chains per query);
+//  * the block's records are staged ONCE per cell in shared memory as float32 relative to the home cell's origin (coalesced
+//    16-byte loads of recf[]), octant by octant (k_cell_sort), with a table of the occupied octants ("blocks", ~4 points);
+//  * every lane then runs the branch-free top-10 min / max chain over the staged candidates out of shared memory (broadcast
+//    reads, all lanes active, no global load in the loop).  A block is skipped for the whole warp when no lane can still use
+//    it -- its box is farther from every query than that query's current 10th distance -- which leaves roughly the blocks
+//    inside (cell + 2 x 10-NN radius)^3, about half of the 3x3x3 block;
+//  * pass B collects the <= 16 candidates within the float32 radius + error bound, the exact (distance, index) selection and
+//    the covariance run in fp64 on those, exactly as in k_knn_cov.
+// Error bound of a float32 squared distance v between two staged points (coordinates below 2 cells, each rounded twice):
+//     E(v) = 3e-6 cell sqrt(v) + 1e-6 v + 1e-12      (twice the worst case 2 sqrt(3) d (4.4e-8 m at cell = 0.1) + 2.4e-7 d^2)
+// A query is finished here iff the block provably holds its 10 nearest points (10th distance + E <= (cell + distance to the
+// nearest face of its own cell)^2) and pass B's list did not overflow; the others -- sparse surroundings, overfull blocks,
+// ties -- are appended to the cloud's hand-over list and done by k_knn_cov(use_list = 1).  Results are bit-identical.
+static const int KW_WARPS = 4;
+static const int KW_CAP = 384;     // staged candidates per cell block
+static const int KW_BLOCKS = 216;  // 27 cells x 8 octants
+static const int KW_LIST = 16;
+struct KwSmem {
+  float4 cand[KW_CAP];
+  unsigned blk[KW_BLOCKS];         // start (10 bits) | count (8) | half-cell index x, y, z (3 bits each, 0..5)
+  int list[KW_LIST * 32];
+};
+static const size_t KW_SMEM = sizeof(KwSmem) * KW_WARPS;
+// visiting order of the 27 cells: home, 6 face, 12 edge, 8 corner neighbours (index = (dx+1) + 3 (dy+1) + 9 (dz+1))
+__device__ const unsigned char KW_ORDER[27] = {13, 12, 14, 10, 16, 4, 22, 9, 11, 15, 17, 3, 5, 21, 23, 1, 7, 19, 25, 0, 2, 6, 8, 18, 20, 24, 26};
+
+__device__ __forceinline__ float kw_err(float v, float ea) { return ea * sqrtf(v) + 1e-6f * v + 1e-12f; }
+// squared distance from a query at (lx, ly, lz) (home-cell coordinates) to the half-cell box of a block, shrunk by 1 um
+__device__ __forceinline__ float kw_gap2(unsigned e, float lx, float ly, float lz, float half) {
+  const float bx = (float)((int)((e >> 18) & 7u) - 2) * half, by = (float)((int)((e >> 21) & 7u) - 2) * half,
+              bz = (float)((int)((e >> 24) & 7u) - 2) * half;
+  const float gx = fmaxf(fmaxf(bx - lx, lx - (bx + half)) - 1e-6f, 0.f), gy = fmaxf(fmaxf(by - ly, ly - (by + half)) - 1e-6f, 0.f),
+              gz = fmaxf(fmaxf(bz - lz, lz - (bz + half)) - 1e-6f, 0.f);
+  return gx * gx + gy * gy + gz * gz;
+}
+
+__global__ void __launch_bounds__(KW_WARPS * 32) k_knn_cov_warp(GicpDev D) {
+  extern __shared__ __align__(16) unsigned char s_kw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  KwSmem& S = reinterpret_cast<KwSmem*>(s_kw)[warp];
+  const int c = cloud_of(D, blockIdx.y);
+  const int nCells = D.nCells[c];
+  const Grid g = make_grid(D, c);
+  const int* cellSlot = D.cursor + (size_t)c * D.hsize;
+  int* fall = D.slotOf + (size_t)c * D.nmax;
+  const float cellf = (float)D.cell, half = 0.5f * cellf, ea = (float)(3e-6 * D.cell);
+  const unsigned full = 0xffffffffu;
+  for (int ci = blockIdx.x * KW_WARPS + warp; ci < nCells; ci += gridDim.x * KW_WARPS) {
+    const int hslot = cellSlot[ci];
+    const uint4 he = __ldg(&g.tab[hslot]);
+    const unsigned long long hkey = (unsigned long long)he.x | ((unsigned long long)he.y << 32);
+    const int hx = (int)(hkey & 0x1fffff), hy = (int)((hkey >> 21) & 0x1fffff), hz = (int)((hkey >> 42) & 0x1fffff);
+    const int qs = (int)he.z, qn = (int)he.w;
+    // ---- the 27 cells: lane k probes cell KW_ORDER[k]
+    int st = 0, cn = 0, dx = 0, dy = 0, dz = 0;
+    unsigned long long n8 = 0;
+    bool unsorted = false;
+    if (lane < 27) {
+      const int nb = KW_ORDER[lane];
+      dx = nb % 3 - 1; dy = (nb / 3) % 3 - 1; dz = nb / 9 - 1;
+      int slot = hslot;
+      bool have = true;
+      if (lane == 0) { st = qs; cn = qn; }
+      else have = grid_find_slot(g, hx + dx, hy + dy, hz + dz, st, cn, slot);
+      if (have) {
+        const uint2 oc = __ldg(&g.oct[slot]);
+        unsorted = oc.x == 0xffffffffu && oc.y == 0xffffffffu;
+        n8 = (unsigned long long)oc.x | ((unsigned long long)oc.y << 32);
+      } else { st = 0; cn = 0; }
+    }
+    int inc = cn;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(full, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const int base = inc - cn, total = __shfl_sync(full, inc, 31);
+    const bool bad = __any_sync(full, unsorted) || total > KW_CAP || total < KNN_K;
+    __syncwarp();  // the previous cell's queries are done with S
+    if (bad) {     // hand every query of this cell over
+      for (int qi = lane; qi < qn; qi += 32) {
+        const int pidx = __float_as_int(__ldg(&g.recf[qs + qi]).w);
+        fall[atomicAdd(&D.nFall[c], 1)] = pidx;
+        D.knnCnt[(size_t)c * D.nmax + pidx] = 0;
+      }
+      continue;
+    }
+    // ---- stage the candidates cell by cell and list the occupied octants
+    int nblk = 0;
+    for (int k = 0; k < 27; k++) {
+      const int kcn = __shfl_sync(full, cn, k);
+      if (kcn == 0) continue;
+      const int kst = __shfl_sync(full, st, k), kbase = __shfl_sync(full, base, k);
+      const int kdx = __shfl_sync(full, dx, k), kdy = __shfl_sync(full, dy, k), kdz = __shfl_sync(full, dz, k);
+      const unsigned long long kn8 = __shfl_sync(full, n8, k);
+      const float ox = (float)kdx * cellf, oy = (float)kdy * cellf, oz = (float)kdz * cellf;
+      for (int j = lane; j < kcn; j += 32) {
+        float4 r = __ldg(&g.recf[kst + j]);
+        r.x += ox; r.y += oy; r.z += oz;
+        S.cand[kbase + j] = r;
+      }
+      const int ocnt = lane < 8 ? (int)((kn8 >> (8 * lane)) & 0xffull) : 0;
+      int pre = ocnt;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        const int t = __shfl_up_sync(full, pre, o);
+        if (lane >= o) pre += t;
+      }
+      const unsigned m = __ballot_sync(full, ocnt > 0);
+      if (ocnt > 0) {
+        const int pos = nblk + __popc(m & ((1u << lane) - 1u));
+        const unsigned hxh = (unsigned)((kdx + 1) * 2 + (lane & 1)), hyh = (unsigned)((kdy + 1) * 2 + ((lane >> 1) & 1)),
+                       hzh = (unsigned)((kdz + 1) * 2 + ((lane >> 2) & 1));
+        S.blk[pos] = (unsigned)(kbase + pre - ocnt) | ((unsigned)ocnt << 10) | (hxh << 18) | (hyh << 21) | (hzh << 24);
+      }
+      nblk += __popc(m);
+    }
+    __syncwarp();
+    // ---- queries: the home cell's records (staged first, at offset 0), 32 per pass
+    for (int q0 = 0; q0 < qn; q0 += 32) {
+      const int qi = q0 + lane;
+      const bool act = qi < qn;
+      const float4 me = S.cand[act ? qi : 0];
+      const float lx = me.x, ly = me.y, lz = me.z;
+      const int pidx = __float_as_int(me.w);
+      float top[KNN_K];
+#pragma unroll
+      for (int i = 0; i < KNN_K; i++) top[i] = FLT_MAX;
+      // pass A: the 10 smallest float32 distances
+      for (int b = 0; b < nblk; b++) {
+        const unsigned e = S.blk[b];
+        if (!__any_sync(full, act && kw_gap2(e, lx, ly, lz, half) <= top[KNN_K - 1])) continue;
+        const int s0 = (int)(e & 0x3ffu), n0 = (int)((e >> 10) & 0xffu);
+        for (int j = 0; j < n0; j++) {
+          const float4 cd = S.cand[s0 + j];
+          const float ddx = cd.x - lx, ddy = cd.y - ly, ddz = cd.z - lz;
+          float v = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
+#pragma unroll
+          for (int i = 0; i < KNN_K; i++) {
+            const float lo = fminf(top[i], v);
+            v = fmaxf(top[i], v);
+            top[i] = lo;
+          }
+        }
+      }
+      // is the block complete for this query?  (exact coordinates, fp64)
+      const double* qp = g.pts + (size_t)(act ? pidx : 0) * 4;
+      const double qx = qp[0], qy = qp[1], qz = qp[2];
+      const float rho = top[KNN_K - 1];
+      bool ok = act && rho < FLT_MAX;
+      if (ok) {
+        const ShellQuery sq = make_shell_query(D.cell, qx, qy, qz);
+        const double bound = D.cell + sq.margin;
+        ok = (double)rho + (double)kw_err(rho, ea) <= bound * bound;
+      }
+      // pass B: everything within the radius + twice the error bound goes to the exact selection
+      const float T = ok ? (rho + 2.f * kw_err(rho, ea)) * 1.000001f : -1.f;
+      int cnt = 0;
+      for (int b = 0; b < nblk; b++) {
+        const unsigned e = S.blk[b];
+        if (!__any_sync(full, ok && kw_gap2(e, lx, ly, lz, half) <= T)) continue;
+        const int s0 = (int)(e & 0x3ffu), n0 = (int)((e >> 10) & 0xffu);
+        for (int j = 0; j < n0; j++) {
+          const float4 cd = S.cand[s0 + j];
+          const float ddx = cd.x - lx, ddy = cd.y - ly, ddz = cd.z - lz;
+          const float v = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
+          if (v <= T) {
+            if (cnt < KW_LIST) S.list[cnt * 32 + lane] = __float_as_int(cd.w);
+            cnt++;
+          }
+        }
+      }
+      ok = ok && cnt <= KW_LIST && cnt >= KNN_K;
+      if (act && !ok) fall[atomicAdd(&D.nFall[c], 1)] = pidx;
+      if (act) {
+        // hand the short list to k_knn_select_cov (the fp64 selection and the eigen decomposition want ~120 registers;
+        // keeping them out of this kernel lets four times as many warps hide the shared-memory latency of the scans)
+        D.knnCnt[(size_t)c * D.nmax + pidx] = ok ? (unsigned char)cnt : (unsigned char)0;
+        if (ok) {
+          int* lst = D.knnList + ((size_t)c * D.nmax + pidx) * KW_LIST;
+          for (int t = 0; t < cnt; t++) lst[t] = S.list[t * 32 + lane];
+        }
+      }
+    }
+  }
+}
+
+// exact (distance, index) selection over the <= 16 listed candidates of every query k_knn_cov_warp finished + covariance
+__global__ void __launch_bounds__(128) k_knn_select_cov(GicpDev D) {
+  const int c = cloud_of(D, blockIdx.y);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D.nDown[c]) return;
+  const int cnt = D.knnCnt[(size_t)c * D.nmax + i];
+  if (cnt == 0) return;  // handed over to k_knn_cov(use_list = 1)
+  const Grid g = make_grid(D, c);
+  const double* q = g.pts + (size_t)i * 4;
+  const double qx = q[0], qy = q[1], qz = q[2];
+  const int4* lst = reinterpret_cast<const int4*>(D.knnList + ((size_t)c * D.nmax + i) * KW_LIST);
+  KnnAcc<KNN_K> acc;
+  acc.init();
+  for (int t4 = 0; t4 < (cnt + 3) / 4; t4++) {
+    const int4 v = __ldg(&lst[t4]);
+    const int id[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (4 * t4 + u < cnt) acc.push(id[u], sqdist3(g.pts + (size_t)id[u] * 4, qx, qy, qz));
+  }
+  cov_from_knn(g, acc, D.cov + ((size_t)c * D.nmax + i) * 6);
+}
+
 // ---- block reduction of NV doubles per thread into out[NV] (fixed order: lanes, then warps)
 template <int NV, int THREADS>
 __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* out) {
@@ -1583,7 +1799,7 @@ using namespace gfs;
 struct GfsGicp {
   GicpDev dev;
   int maxPairs = 0;
-  DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_nFall, b_box, b_pts, b_cov, b_tab, b_rec, b_recf, b_oct,
+  DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_nFall, b_box, b_pts, b_cov, b_tab, b_rec, b_recf, b_oct, b_knnList, b_knnCnt,
       b_corr, b_maha, b_partial, b_partialE, b_state, b_istate, b_counters;
   DevBuf b_tgt, b_src, b_n, b_T0, b_res;
   PinnedBuf h_counters;
@@ -1660,6 +1876,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   if (rc) return rc;
   GFS_CUDA(cudaFuncSetAttribute(k_knn_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KNN_SMEM));
   GFS_CUDA(cudaFuncSetAttribute(k_knn_cov_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KC_SMEM));
+  GFS_CUDA(cudaFuncSetAttribute(k_knn_cov_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KW_SMEM));
   GfsGicp* h = new GfsGicp();
   GicpDev& D = h->dev;
   memset(&D, 0, sizeof(D));
@@ -1716,6 +1933,8 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   RES(b_rec, C * N * 32, rec, double*)
   RES(b_recf, C * N * 16, recf, float4*)
   RES(b_oct, C * H * 8, oct, uint2*)
+  RES(b_knnList, C * N * 64, knnList, int*)
+  RES(b_knnCnt, C * N, knnCnt, unsigned char*)
   RES(b_corr, P * N * 4, corr, int*)
   RES(b_maha, P * N * 72, maha, double*)
   RES(b_partial, P * D.nblk * (LIN_THREADS / 32) * RED_N * 8, partial, double*)
@@ -1732,7 +1951,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
 int gfs_gicp_destroy(GfsGicp* h) {
   if (!h) return GFS_OK;
   DevBuf* d[] = {&h->b_keys, &h->b_minIdx, &h->b_count, &h->b_start, &h->b_cursor, &h->b_rank, &h->b_slotOf, &h->b_members,
-                 &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_nFall, &h->b_box, &h->b_pts, &h->b_cov, &h->b_tab, &h->b_rec, &h->b_recf, &h->b_oct, &h->b_corr, &h->b_maha, &h->b_partial,
+                 &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_nFall, &h->b_box, &h->b_pts, &h->b_cov, &h->b_tab, &h->b_rec, &h->b_recf, &h->b_oct, &h->b_knnList, &h->b_knnCnt, &h->b_corr, &h->b_maha, &h->b_partial,
                  &h->b_partialE, &h->b_state, &h->b_istate, &h->b_counters, &h->b_tgt, &h->b_src, &h->b_n, &h->b_T0, &h->b_res};
   for (DevBuf* b : d) b->release();
   h->h_counters.release();
@@ -1781,7 +2000,13 @@ static int preprocess_clouds(GfsGicp* h, const GicpDev& D, cudaStream_t st, int 
     h->launches += 1;
   }
   prof_mark(h, st, ST_GROUP, 11);
-  if (!h->cellKnn) {
+  if (h->knnMode == 1 && !h->cellKnn) {
+    // warp per cell; what it cannot finish (sparse surroundings, overfull blocks, ties) goes to the per-query kernel
+    k_knn_cov_warp<<<dim3(2 * 148, clouds), KW_WARPS * 32, KW_SMEM, st>>>(D);
+    k_knn_select_cov<<<dim3(div_up(D.nmax, 128), clouds), 128, 0, st>>>(D);
+    k_knn_cov<<<dim3(8, clouds), KNN_THREADS, KNN_SMEM, st>>>(D, 1);
+    h->launches += 2;
+  } else if (!h->cellKnn) {
     k_knn_cov<<<dim3(div_up(D.nmax, KNN_THREADS), clouds), KNN_THREADS, KNN_SMEM, st>>>(D, 0);
   } else {
     // ~3 resident CTAs per SM in flight over the whole batch; every CTA strides over its cloud's cells
@@ -1790,7 +2015,7 @@ static int preprocess_clouds(GfsGicp* h, const GicpDev& D, cudaStream_t st, int 
     k_knn_cov<<<dim3(8, clouds), KNN_THREADS, KNN_SMEM, st>>>(D, 1);
     h->launches += 1;
   }
-  prof_mark(h, st, ST_KNN, h->cellKnn ? 2 : 1);
+  prof_mark(h, st, ST_KNN, h->knnMode == 1 && !h->cellKnn ? 3 : (h->cellKnn ? 2 : 1));
   h->launches += 3;
   GFS_CUDA(cudaGetLastError());
   return GFS_OK;

@@ -96,28 +96,49 @@ def _pack(clouds):
 
 
 def test_search_variants_are_bit_identical(monkeypatch):
-    """The query order (point / grid-cell order) and the correspondence kernels (shell walk, ball walk in fp64, ball walk with
-    the float32 prefilter) are different routes to the same exact neighbours: every result field is equal bit for bit."""
+    """The query order (point / grid-cell order), the correspondence kernels (shell walk, ball walk, ball walk over octants, each
+    in fp64 or with the float32 prefilter) and the 10-NN kernels (thread per query, warp per cell with octant skipping) are
+    different routes to the same exact neighbours: every result field and every covariance is equal bit for bit."""
     from geoflowslam_b200 import RegistrationGICP
-    pairs = [synth.gicp_pair(2030 + i, n_target=[20000, 6000][i]) for i in range(2)]
+    pairs = [synth.gicp_pair(2030 + i, n_target=[20000, 6000, 900][i]) for i in range(3)]
     tg, nt = _pack([p[0] for p in pairs]); sr, ns = _pack([p[1] for p in pairs])
     stride = max(tg.shape[1], sr.shape[1])
     tg = np.pad(tg, ((0, 0), (0, stride - tg.shape[1]), (0, 0))); sr = np.pad(sr, ((0, 0), (0, stride - sr.shape[1]), (0, 0)))
-    T0 = np.tile(np.eye(4), (2, 1, 1))
+    T0 = np.tile(np.eye(4), (3, 1, 1))
     out = {}
-    for order, nn in ((0, 0), (1, 0), (1, 1), (1, 2), (0, 2)):
-        monkeypatch.setenv("GFS_GICP_ORDER", str(order)); monkeypatch.setenv("GFS_GICP_NN", str(nn))
-        reg = RegistrationGICP(max_points=stride, max_pairs=2)
-        out[(order, nn)] = reg.align_batch(tg, nt, sr, ns, T0).tobytes()
-        covs = [reg.cloud(c)[1].tobytes() for c in range(4)]
-        out[(order, nn, "cov")] = covs
+    variants = ((0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 2, 0), (0, 2, 0), (1, 3, 1), (1, 4, 1), (0, 3, 1), (1, 1, 1))
+    for order, nn, knn in variants:
+        monkeypatch.setenv("GFS_GICP_ORDER", str(order)); monkeypatch.setenv("GFS_GICP_NN", str(nn)); monkeypatch.setenv("GFS_GICP_KNN", str(knn))
+        reg = RegistrationGICP(max_points=stride, max_pairs=3)
+        out[(order, nn, knn)] = reg.align_batch(tg, nt, sr, ns, T0).tobytes()
+        out[(order, nn, knn, "cov")] = [reg.cloud(c)[1].tobytes() for c in range(6)]
+        if knn == 1:   # the warp-per-cell kernel must do the bulk of the work itself, not hand everything over
+            cells, handed = reg.knn_stats(0)
+            assert handed < 0.25 * nt[0], (cells, handed)
         reg.close()
-    base = out[(0, 0)]
+    base = out[(0, 0, 0)]
     for k, v in out.items():
-        if len(k) == 2:
-            assert v == base, "variant order=%d nn=%d differs from the first-generation search" % k
+        if len(k) == 3:
+            assert v == base, "variant order=%d nn=%d knn=%d differs from the first-generation search" % k
         else:
-            assert v == out[(0, 0, "cov")], "covariances of variant order=%d nn=%d differ" % k[:2]
+            assert v == out[(0, 0, 0, "cov")], "covariances of variant order=%d nn=%d knn=%d differ" % k[:3]
+
+
+def test_dense_and_sparse_clouds_take_the_hand_over_paths(monkeypatch):
+    """Clouds the warp-per-cell 10-NN kernel cannot finish on its own -- a coarse voxel size puts more points into a 3x3x3 block
+    than it stages; a very sparse cloud has its neighbours outside the block -- still give the thread-per-query results."""
+    from geoflowslam_b200 import RegistrationGICP
+    t, s_, _ = synth.gicp_pair(2033, n_target=30000)
+    sparse_t, sparse_s = t[::40].copy(), s_[::40].copy()
+    for cloud_t, cloud_s, kw in ((t, s_, dict(downsampling_resolution=0.005)), (sparse_t, sparse_s, {})):
+        res = {}
+        for knn in (0, 1):
+            monkeypatch.setenv("GFS_GICP_KNN", str(knn))
+            reg = RegistrationGICP(max_points=32768, max_pairs=1, **kw)
+            r = reg.RegisterPointClouds(cloud_t, cloud_s)
+            res[knn] = (r["T"].tobytes(), r["iterations"], r["num_inliers"], reg.cloud(0)[1].tobytes(), reg.cloud(1)[1].tobytes())
+            reg.close()
+        assert res[0] == res[1]
 
 
 def test_track_mode_equals_pairwise_align():
