@@ -841,6 +841,70 @@ def run_track_reference(args):
     print(json.dumps(line))
 
 
+def latency_table(data, reps=30):
+    """Batch = 1 latency of every entry point through the host-pointer C ABI (what one System::TrackRGBD call pays per stage),
+    median of `reps` calls in ms, next to one call of the CPU oracle on the same input."""
+    import torch
+    from geoflowslam_b200 import (KltTracker, Optimizer, ORBextractor, ORBmatcher, PoseInertialOptimizer, RegistrationGICP, imu, synth)
+    from oracle import oracle as O
+    cal = synth.imu_calib_noise()
+    g0, g1 = data["gray"][0, 0], data["gray"][1, 0]
+    c0, c1 = _depth_cloud_np(data["depth"][0, 0]), _depth_cloud_np(data["depth"][1, 0])
+    orb = ORBextractor(max_size=(W, H), max_batch=1, **ORB_CFG)
+    _, k0, d0 = orb(g0); _, k1, d1 = orb(g1)
+    pts = np.stack([k0["x"], k0["y"]], 1)[:KLT_PTS].astype(np.float32)
+    m = ORBmatcher(); trk = KltTracker(max_size=(W, H), levels=3, max_points=KLT_PTS, max_batch=1)
+    pio = PoseInertialOptimizer(max_obs=512, max_batch=1); reg = RegistrationGICP(max_points=65536, max_pairs=1)
+    opt = Optimizer(max_kf=21, max_points=3000, max_obs=16384, max_inertial=20, max_batch=1)
+    rows = data["imu"][0, 0]; zb = np.zeros(6, np.float32)
+    oo = O.OrbOracle(ORB_CFG["nfeatures"], ORB_CFG["scaleFactor"], ORB_CFG["nlevels"], ORB_CFG["iniThFAST"], ORB_CFG["minThFAST"], threads=1)
+
+    def o_match():
+        idx, _ = O.bf_match(d0, d1)
+        mm = np.stack([np.arange(len(idx), dtype=np.int32), idx], 1)
+        O.gms_filter(np.stack([k0["x"], k0["y"]], 1), (W, H), np.stack([k1["x"], k1["y"]], 1), (W, H), mm)
+
+    def o_klt():
+        pa, pb = O.klt_build_pyramid(g0, 3), O.klt_build_pyramid(g1, 3)
+        O.fb_klt_tracking(pa, pb, W, H, 3, pts, pts)
+    calls = {
+        "ORBextractor::operator()": (lambda: orb(g1), lambda: oo.extract(g1)),
+        "SearchWithGMS": (lambda: m.SearchWithGMS(k0, d0, k1, d1, (W, H)), o_match),
+        "buildOpticalFlowPyramid x2 + fbKltTracking": (lambda: trk.fbKltTracking(g0, g1, pts, pts), o_klt),
+        "IMU preintegration": (lambda: imu.preintegrate_batch([rows], [zb], *cal), lambda: O.imu_preintegrate(rows, zb, *cal)),
+        "PoseInertialOptimizationLastFrame": (lambda: pio.optimize_batch([data["pin"][0]]), lambda: O.pose_inertial_optimize(data["pin"][0])),
+        "RegisterPointClouds": (lambda: reg.RegisterPointClouds(c0, c1), lambda: O.gicp_align(c0, c1, threads=4)),
+        "LocalInertialBA": (lambda: opt.LocalInertialBA(data["ba"][0]), lambda: O.ba_solve(data["ba"][0])),
+    }
+    out = {}
+    for name, (fg, fo) in calls.items():
+        for _ in range(3):
+            fg()
+        ts = []
+        for _ in range(reps if name != "LocalInertialBA" else max(5, reps // 3)):
+            torch.cuda.synchronize(); t0 = time.perf_counter(); fg(); ts.append(1e3 * (time.perf_counter() - t0))
+        fo(); t0 = time.perf_counter(); fo(); to = 1e3 * (time.perf_counter() - t0)
+        out[name] = {"gpu_ms": round(statistics.median(ts), 4), "cpu_oracle_ms": round(to, 4)}
+    return out
+
+
+def ate_vs_oracle(n_frames=12, kf_every=3, seed=4000):
+    """The closed-loop tracker (geoflowslam_b200/tracker.py: ORB -> SearchByProjection / GMS -> GICP gate -> pose optimisers ->
+    keyframes -> LocalInertialBA) on the CUDA library and on the CPU oracle over one synthetic sequence: ATE of both against the
+    ground truth, their difference, and the number of integer decisions that differ."""
+    from geoflowslam_b200 import imu, synth, tracker
+    from oracle.tracker_backend import OracleBackend
+    seq = synth.room_sequence(seed, n_frames=n_frames)
+    g = tracker.run_tracker(seq, tracker.CudaBackend(), kf_every=kf_every)
+    o = tracker.run_tracker(seq, OracleBackend(), kf_every=kf_every)
+    gt = seq["twb"][:n_frames]
+    a, b = imu.ate_rmse(g["twb"], gt), imu.ate_rmse(o["twb"], gt)
+    return {"frames": n_frames, "keyframes": g["n_keyframes"], "ate_cuda_m": a, "ate_oracle_m": b, "ate_difference_m": abs(a - b),
+            "max_position_difference_m": float(np.abs(g["twb"] - o["twb"]).max()),
+            "differing_decisions": sum(1 for x, y in zip(g["decisions"], o["decisions"]) if x != y) + abs(len(g["decisions"]) - len(o["decisions"])),
+            "decisions_compared": len(g["decisions"])}
+
+
 def run_track(args):
     """BASELINE.json's metric.  One step advances B independent RGB-D-inertial sequences per GPU by one frame: the stages of
     System::TrackRGBD -> Tracking::Track (reference src/System.cc:661, src/Tracking.cc:2042-2260) that this library replaces,
@@ -1124,6 +1188,16 @@ def run_track(args):
         cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": "%d sequences x %d frames on %d worker threads in %.1f s wall (measured, not extrapolated); core-seconds per frame by stage: %s"
                          % (n_seq, RING, cores, dt, json.dumps({k: round(v, 5) for k, v in core_s.items()}))}
+    sub = {}
+    if world == 1 and not args.no_cpu:
+        try:
+            sub["latency_ms_batch1"] = latency_table(data)
+        except Exception as e:  # a side table must not cost the headline line
+            sub["latency_ms_batch1"] = {"error": str(e)}
+        try:
+            sub["ate_vs_oracle"] = ate_vs_oracle()
+        except Exception as e:
+            sub["ate_vs_oracle"] = {"error": str(e)}
     line = {"metric": TRACK_METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": W_,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32/f64",
             "data": "synthetic",
@@ -1134,6 +1208,7 @@ def run_track(args):
                        "step_mode": "front end (ORB, match, optical flow, IMU) on the main stream; pose optimiser, depth->cloud+GICP and BA on a stream + host thread each (the reference's Tracking / LocalMapping threads)",
                        "l2": "inputs larger than L2 (%.0f MB of new frames per step, ring of %d)" % ((h_gray[0].nbytes + h_depth[0].nbytes) / 1e6, RING),
                        "parallelism": "sequences sharded across ranks, no data-path collective",
+                       "sub_lines": sub,
                        "note": "map-dependent inputs (pose-optimiser observations, BA window) are synthetic problems of the named shapes; tests/test_gpu_closed_loop.py chains the stages causally"},
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -1153,6 +1228,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--gicp-track", action="store_true", help="--workload gicp in tracking mode (gfs_gicp_track_batch_device)")
+    ap.add_argument("--partition", action="store_true",
+                    help="--workload ba under torchrun: ONE problem, landmarks partitioned over the ranks, NCCL all-reduce (configs[3])")
     ap.add_argument("--workload", default="track", choices=["track", "orb", "gicp", "ba", "lba", "pose", "pose_inertial", "klt"],
                     help="track = BASELINE.json's metric (the driver's default); orb / gicp / ba = configs[1] / [2] / [3]")
     args = ap.parse_args()
@@ -1163,6 +1240,10 @@ def main():
             run_reference(args)
     elif args.workload == "gicp":
         run_gicp(args)
+    elif args.workload == "ba" and args.partition:
+        import runpy
+        sys.argv = [os.path.join(ROOT, "scripts", "ba_partition_check.py"), "--mode", "nccl", "--json", "--reps", str(max(args.steps, 1))]
+        runpy.run_path(sys.argv[0], run_name="__main__")
     elif args.workload == "ba":
         run_ba(args)
     elif args.workload == "lba":

@@ -1329,7 +1329,7 @@ __device__ __forceinline__ void scan_cell_nn1f(const Grid& g, int s, int n, floa
 }
 
 // cells the ball of squared radius limit() around the query reaches, home cell first; limit() may shrink while visiting
-template <class Limit, class Visit>
+template <bool FAST, class Limit, class Visit>
 __device__ __forceinline__ void visit_ball(const Grid& g, const int* box, const ShellQuery& q, Limit limit, Visit visit) {
   {
     int cs, cn, slot;
@@ -1338,6 +1338,27 @@ __device__ __forceinline__ void visit_ball(const Grid& g, const int* box, const 
   const double lim0 = limit();
   if (lim0 <= q.margin * q.margin) return;  // the ball stays inside the home cell
   const double R = sqrt(lim0) * 1.000001 + 1e-12, inv = 1.0 / q.cell;
+  if (FAST && 2.0 * R < q.cell) {
+    // The usual case once the clouds are roughly aligned (R ~ 1 cm, cell = 10 cm): the ball is narrower than a cell, so along
+    // each axis it reaches at most ONE neighbour.  The seven candidate cells are the non-empty subsets of those axis steps:
+    // a fixed seven-trip loop with three precomputed gaps instead of a triple loop over index ranges (the lanes of a warp
+    // stay together; the triple loop ran at 12 active lanes).
+    const int sx = (q.fx - R < 0.0) ? -1 : ((q.fx + R >= q.cell) ? 1 : 0), sy = (q.fy - R < 0.0) ? -1 : ((q.fy + R >= q.cell) ? 1 : 0),
+              sz = (q.fz - R < 0.0) ? -1 : ((q.fz + R >= q.cell) ? 1 : 0);
+    const double gx2 = axis_gap2(sx, q.fx, q.cell), gy2 = axis_gap2(sy, q.fy, q.cell), gz2 = axis_gap2(sz, q.fz, q.cell);
+#pragma unroll
+    for (int m = 1; m < 8; m++) {
+      const bool ux = m & 1, uy = m & 2, uz = m & 4;
+      if ((ux && !sx) || (uy && !sy) || (uz && !sz)) continue;
+      const double g2 = (ux ? gx2 : 0.0) + (uy ? gy2 : 0.0) + (uz ? gz2 : 0.0);
+      if (g2 > limit()) continue;
+      const int x = q.cx + (ux ? sx : 0), y = q.cy + (uy ? sy : 0), z = q.cz + (uz ? sz : 0);
+      if (x < box[0] || x > box[3] || y < box[1] || y > box[4] || z < box[2] || z > box[5]) continue;
+      int cs, cn, slot;
+      if (grid_find_slot(g, x, y, z, cs, cn, slot)) visit(cs, cn, x, y, z, slot);
+    }
+    return;
+  }
   const int x0 = max(q.cx + fast_floor_d((q.fx - R) * inv), box[0]), x1 = min(q.cx + fast_floor_d((q.fx + R) * inv), box[3]);
   const int y0 = max(q.cy + fast_floor_d((q.fy - R) * inv), box[1]), y1 = min(q.cy + fast_floor_d((q.fy + R) * inv), box[4]);
   const int z0 = max(q.cz + fast_floor_d((q.fz - R) * inv), box[2]), z1 = min(q.cz + fast_floor_d((q.fz + R) * inv), box[5]);
@@ -1392,7 +1413,7 @@ __device__ __forceinline__ void for_octants(const Grid& g, int slot, int cs, int
   }
 }
 
-template <bool F32, bool OCT>
+template <bool F32, bool OCT, bool FAST>
 __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr2(GicpDev D, int iter) {
   const int p = blockIdx.y;
   if (!D.istate[p * LM_ISTATE + I_ACTIVE]) return;
@@ -1433,7 +1454,7 @@ __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr2(GicpDev D, int iter)
     }
     auto ub = [&]() -> double { return nf.v1 < FLT_MAX ? (double)nf.v1 + (double)nn_bound(nf.v1, D.nnBoundA) : DBL_MAX; };
     const int off = 1 << 20;
-    visit_ball(g, box, sq, [&]() { return fmin(ub(), capf); },
+    visit_ball<FAST>(g, box, sq, [&]() { return fmin(ub(), capf); },
                [&](int cs_, int cn_, int x, int y, int z, int slot) {
                  const float qx = (float)(q[0] - (double)(x - off) * D.cell), qy = (float)(q[1] - (double)(y - off) * D.cell),
                              qz = (float)(q[2] - (double)(z - off) * D.cell);
@@ -1459,7 +1480,7 @@ __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr2(GicpDev D, int iter)
     nn.d = DBL_MAX; nn.id = 0x7fffffff;
     // the previous iteration's correspondence is a real target point: starting from it only tightens the radius
     if (prev >= 0) nn.push(prev, sqdist3(g.pts + (size_t)prev * 4, q[0], q[1], q[2]));
-    visit_ball(g, box, sq, [&]() { return fmin(nn.d, cap); },
+    visit_ball<FAST>(g, box, sq, [&]() { return fmin(nn.d, cap); },
                [&](int cs_, int cn_, int x, int y, int z, int slot) {
                  if (OCT)
                    for_octants(g, slot, cs_, cn_, octant_mask(q, x, y, z, D.cell, fmin(nn.d, cap)),
@@ -1805,8 +1826,10 @@ struct GfsGicp {
   PinnedBuf h_counters;
   int launches = 0;
   bool cellKnn = false;  // GFS_GICP_KNN_CELLS=1: cell-centric 10-NN kernel first (same results)
-  int nnMode = 3;        // GFS_GICP_NN: 0 = k_nn_corr (shell walk), 1 = k_nn_corr2 (ball walk, fp64), 2 = + float32 prefilter, 3 = ball walk over octants (fp64), 4 = octants + float32 prefilter
-  int knnMode = 1;       // GFS_GICP_KNN: 0 = k_knn_cov (thread per query), 1 = k_knn_cov_warp (warp per cell, octant skipping) + k_knn_cov for what it hands over
+  int nnMode = 5;        // GFS_GICP_NN: 0 = k_nn_corr (shell walk), 1 = k_nn_corr2 (ball walk, fp64), 2 = + float32 prefilter, 3 = ball walk over octants
+                         // (fp64), 4 = octants + float32 prefilter, 5 = ball walk with the seven-cell fast path (fp64; default), 6 = 5 + float32 prefilter
+  int knnMode = 0;       // GFS_GICP_KNN: 0 = k_knn_cov (thread per query; default, measured fastest), 1 = k_knn_cov_warp (warp per cell, octant
+                         // skipping) + k_knn_cov for what it hands over
   int trackCalls = 0;    // gfs_gicp_track_*: calls since the last reset (the new cloud goes to slot trackCalls & 1)
   int trackSeqs = 0;
   // optional per-stage CUDA-event timing of one call (gfs_gicp_set_profiling): an event after every stage, read back at
@@ -2030,10 +2053,12 @@ static int optimize_pairs(GfsGicp* h, const GicpDev& D, cudaStream_t st, int pai
     GFS_CUDA(cudaMemsetAsync(D.counters, 0, 8, st));
     const dim3 gn(div_up(D.nmax, NN_THREADS), pairs);
     if (h->nnMode == 0) k_nn_corr<<<gn, NN_THREADS, 0, st>>>(D, it);
-    else if (h->nnMode == 1) k_nn_corr2<false, false><<<gn, NN_THREADS, 0, st>>>(D, it);
-    else if (h->nnMode == 2) k_nn_corr2<true, false><<<gn, NN_THREADS, 0, st>>>(D, it);
-    else if (h->nnMode == 3) k_nn_corr2<false, true><<<gn, NN_THREADS, 0, st>>>(D, it);
-    else k_nn_corr2<true, true><<<gn, NN_THREADS, 0, st>>>(D, it);
+    else if (h->nnMode == 1) k_nn_corr2<false, false, false><<<gn, NN_THREADS, 0, st>>>(D, it);
+    else if (h->nnMode == 2) k_nn_corr2<true, false, false><<<gn, NN_THREADS, 0, st>>>(D, it);
+    else if (h->nnMode == 3) k_nn_corr2<false, true, false><<<gn, NN_THREADS, 0, st>>>(D, it);
+    else if (h->nnMode == 4) k_nn_corr2<true, true, false><<<gn, NN_THREADS, 0, st>>>(D, it);
+    else if (h->nnMode == 5) k_nn_corr2<false, false, true><<<gn, NN_THREADS, 0, st>>>(D, it);
+    else k_nn_corr2<true, false, true><<<gn, NN_THREADS, 0, st>>>(D, it);
     prof_mark(h, st, ST_NN);
     k_linearize<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D, it);
     prof_mark(h, st, ST_LIN);
