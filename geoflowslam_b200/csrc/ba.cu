@@ -1460,7 +1460,7 @@ int gfs_ba_upload(GfsBa* h, void* stream, const GfsBaProblem* problems, int batc
   UP(inKf1, h_inKf1); UP(inKf2, h_inKf2); UP(inPre, h_inPre); UP(infoIn, h_infoIn); UP(infoG, h_infoG); UP(infoA, h_infoA);
   UP(ptStart, h_ptStart); UP(ptEdges, h_ptEdges); UP(kfStart, h_kfStart); UP(kfEdges, h_kfEdges); UP(ptKfEdge, h_ptKfEdge);
 #undef UP
-  GFS_CUDA(cudaStreamSynchronize(st));  // the staging vectors may be reused by the next upload
+  GFS_CUDA(gfs::stream_wait(st));  // the staging vectors may be reused by the next upload
   h->batch = batch;
   return GFS_OK;
 }
@@ -1483,7 +1483,7 @@ static int ba_allreduce(GfsBa* h, cudaStream_t st, std::initializer_list<RedBuf>
     return GFS_OK;
   }
   GFS_REQUIRE(h->allreduce, GFS_ERR_INVALID, "partitioned mode without a communicator or callback");
-  GFS_CUDA(cudaStreamSynchronize(st));
+  GFS_CUDA(gfs::stream_wait(st));
   for (const RedBuf& b : bufs) {
     const int rc = h->allreduce(b.p, b.n, h->allreduceUser);
     GFS_REQUIRE(rc == 0, GFS_ERR_CUDA, "all-reduce callback failed");
@@ -1562,7 +1562,7 @@ int gfs_ba_solve_uploaded(GfsBa* h, void* stream) {
       k_restore<<<gCopy, 256, 0, st>>>(D);
       h->launches += 8;
       GFS_CUDA(cudaMemcpyAsync(hc, D.counters, 8, cudaMemcpyDeviceToHost, st));
-      GFS_CUDA(cudaStreamSynchronize(st));
+      GFS_CUDA(gfs::stream_wait(st));
       if (hc[0] == 0) break;
     }
     if (hc[1] == 0) break;
@@ -1590,7 +1590,7 @@ int gfs_ba_download(GfsBa* h, void* stream, GfsBaResult* results, int batch) {
   GFS_CUDA(cudaMemcpyAsync(errs.data(), h->out.errs, errs.size() * 4, cudaMemcpyDeviceToHost, st));
   GFS_CUDA(cudaMemcpyAsync(info.data(), h->out.info, info.size() * 4, cudaMemcpyDeviceToHost, st));
   GFS_CUDA(cudaMemcpyAsync(lam.data(), h->out.lambda, lam.size() * 8, cudaMemcpyDeviceToHost, st));
-  GFS_CUDA(cudaStreamSynchronize(st));
+  GFS_CUDA(gfs::stream_wait(st));
   for (size_t b = 0; b < B; b++) {
     const BaCalib& C = h->calib[b];
     GfsBaResult& R = results[b];

@@ -1,5 +1,7 @@
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace gfs {
 
 static thread_local char g_err[512] = "";
@@ -9,6 +11,30 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+cudaError_t stream_wait(cudaStream_t st) {
+  static const int mode = [] {
+    const char* e = getenv("GFS_SYNC");
+    return (e && (e[0] == 'b' || e[0] == 'B')) ? 1 : 0;
+  }();
+  if (mode == 0) return cudaStreamSynchronize(st);
+  // one blocking-sync event per (thread, device): events belong to the device that was current when they were made
+  struct Ev { cudaEvent_t e = nullptr; int dev = -1; };
+  static thread_local Ev ev;
+  int dev = 0;
+  cudaError_t rc = cudaGetDevice(&dev);
+  if (rc != cudaSuccess) return rc;
+  if (!ev.e || ev.dev != dev) {
+    if (ev.e) cudaEventDestroy(ev.e);
+    ev.e = nullptr;
+    rc = cudaEventCreateWithFlags(&ev.e, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (rc != cudaSuccess) return rc;
+    ev.dev = dev;
+  }
+  rc = cudaEventRecord(ev.e, st);
+  if (rc != cudaSuccess) return rc;
+  return cudaEventSynchronize(ev.e);
 }
 
 bool is_pinned_host(const void* p) {

@@ -33,6 +33,11 @@ void set_error(const char* fmt, ...);
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
+// Host wait for everything enqueued on `st`.  GFS_SYNC=spin (default): cudaStreamSynchronize, the CUDA runtime's spin wait
+// (lowest latency; right when the process has cores to itself).  GFS_SYNC=block: a blocking-sync event -- the thread sleeps, which
+// keeps eight ranks x four host threads from spinning on every logical core of the box (bench.py sets it for multi-rank runs).
+cudaError_t stream_wait(cudaStream_t st);
+
 // true when p is device-accessible pinned host memory (so async copies need no staging)
 bool is_pinned_host(const void* p);
 

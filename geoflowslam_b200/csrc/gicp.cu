@@ -78,7 +78,12 @@ struct GicpDev {
 // per-pair LM state layout (doubles)
 enum { S_T = 0, S_NEWT = 12, S_H = 24, S_B = 45, S_E = 51, S_LAMBDA = 52, S_DELTA = 53, LM_STATE = 60 };
 // per-pair LM state layout (ints)
-enum { I_ACTIVE = 0, I_NEED = 1, I_CONV = 2, I_ITER = 3, I_TRIAL = 4, I_INL = 5, I_INNER = 6, I_SUCCESS = 7, LM_ISTATE = 8 };
+enum { I_ACTIVE = 0, I_NEED = 1, I_CONV = 2, I_ITER = 3, I_TRIAL = 4, I_INL = 5, I_INNER = 6, I_SUCCESS = 7, I_OUTER = 8, LM_ISTATE = 12 };
+// Every pair walks its own LM state machine (optimizer.hpp:97-141) through the launches the host enqueues in "rounds" of
+// [search, linearize, begin, error, decide]: a pair BETWEEN outer iterations (I_ACTIVE && !I_NEED) takes part in the first three
+// kernels of a round, a pair IN an iteration (I_NEED: a lambda trial is waiting for its error) in the last two -- a rejected
+// trial simply uses the next round's error / decide slots.  I_OUTER is the pair's own outer-iteration index.  The host no
+// longer steers each trial: it only reads the number of unfinished pairs every few rounds to know when to stop.
 
 __device__ __forceinline__ int cloud_of(const GicpDev& D, int y) { return D.cbase + y * D.cstep; }
 __device__ __forceinline__ int tgt_cloud(const GicpDev& D, int p) { return 2 * p + D.swap; }
@@ -1244,9 +1249,10 @@ __device__ __forceinline__ void scan_cell_nn1(const Grid& g, int s, int n, doubl
   }
 }
 static const int NN_THREADS = 128;
-__global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr(GicpDev D, int iter) {
+__global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr(GicpDev D) {
   const int p = blockIdx.y;
-  if (!D.istate[p * LM_ISTATE + I_ACTIVE]) return;
+  if (!D.istate[p * LM_ISTATE + I_ACTIVE] || D.istate[p * LM_ISTATE + I_NEED]) return;
+  const int iter = D.istate[p * LM_ISTATE + I_OUTER];
   const int ct = tgt_cloud(D, p), cs = src_cloud(D, p);
   const int i = blockIdx.x * NN_THREADS + threadIdx.x;
   if (i >= D.nDown[cs]) return;
@@ -1414,9 +1420,10 @@ __device__ __forceinline__ void for_octants(const Grid& g, int slot, int cs, int
 }
 
 template <bool F32, bool OCT, bool FAST>
-__global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr2(GicpDev D, int iter) {
+__global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr2(GicpDev D) {
   const int p = blockIdx.y;
-  if (!D.istate[p * LM_ISTATE + I_ACTIVE]) return;
+  if (!D.istate[p * LM_ISTATE + I_ACTIVE] || D.istate[p * LM_ISTATE + I_NEED]) return;
+  const int iter = D.istate[p * LM_ISTATE + I_OUTER];
   const int ct = tgt_cloud(D, p), cs = src_cloud(D, p);
   const int t = blockIdx.x * NN_THREADS + threadIdx.x;
   if (t >= D.nDown[cs]) return;
@@ -1494,9 +1501,9 @@ __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr2(GicpDev D, int iter)
 }
 
 // GICPFactor::linearize for every source point of every active pair + partial sums
-__global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D, int iter) {
+__global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D) {
   const int p = blockIdx.y;
-  if (!D.istate[p * LM_ISTATE + I_ACTIVE]) return;
+  if (!D.istate[p * LM_ISTATE + I_ACTIVE] || D.istate[p * LM_ISTATE + I_NEED]) return;
   const int ct = tgt_cloud(D, p), cs = src_cloud(D, p);
   const int ns = D.nDown[cs];
   const int i = blockIdx.x * LIN_THREADS + threadIdx.x;
@@ -1695,11 +1702,12 @@ __device__ void lm_trial(double* st) {
 }
 
 // one warp per pair: sum the partials in block order (lane v owns value v), start the first trial
-__global__ void __launch_bounds__(LIN_THREADS) k_lm_begin(GicpDev D, int iter) {
+__global__ void __launch_bounds__(LIN_THREADS) k_lm_begin(GicpDev D) {
   __shared__ double s_tot[RED_N];
   const int p = blockIdx.x, tid = threadIdx.x;
   int* is = D.istate + p * LM_ISTATE;
-  if (!is[I_ACTIVE]) return;
+  if (!is[I_ACTIVE] || is[I_NEED]) return;
+  const int iter = is[I_OUTER];
   double* st = D.state + (size_t)p * LM_STATE;
   // fixed-order sum of the per-warp partials: thread t takes partials t, t+128, ...; then lanes, then warps
   const int nw = ((D.nDown[src_cloud(D, p)] + LIN_THREADS - 1) / LIN_THREADS) * (LIN_THREADS / 32);
@@ -1727,15 +1735,15 @@ __global__ void __launch_bounds__(LIN_THREADS) k_lm_begin(GicpDev D, int iter) {
     is[I_SUCCESS] = 0;
     is[I_NEED] = 1;
     lm_trial(st);
-    atomicAdd(&D.counters[0], 1);
   }
 }
 
 // one warp per pair: new_e, accept / reject, next trial or end of the outer iteration (:114-143)
-__global__ void __launch_bounds__(32) k_lm_decide(GicpDev D, int iter) {
+__global__ void __launch_bounds__(32) k_lm_decide(GicpDev D) {
   const int p = blockIdx.x, lane = threadIdx.x;
   int* is = D.istate + p * LM_ISTATE;
   if (!is[I_NEED]) return;
+  const int iter = is[I_OUTER];
   double* st = D.state + (size_t)p * LM_STATE;
   const int nb = (D.nDown[src_cloud(D, p)] + LIN_THREADS - 1) / LIN_THREADS;
   // fixed-order sum: lane-strided partial sums are NOT order-preserving, so lane 0 sums serially
@@ -1756,12 +1764,13 @@ __global__ void __launch_bounds__(32) k_lm_decide(GicpDev D, int iter) {
       st[S_LAMBDA] *= 10.0;
       is[I_TRIAL]++;
       if (is[I_TRIAL] >= 10) is[I_NEED] = 0;
-      else { lm_trial(st); atomicAdd(&D.counters[0], 1); }
+      else lm_trial(st);  // the next round's error / decide slots evaluate it
     }
     if (!is[I_NEED]) {  // the outer iteration is over for this pair
       if (!is[I_SUCCESS] || is[I_CONV] || iter + 1 >= D.max_iter) is[I_ACTIVE] = 0;
-      else atomicAdd(&D.counters[1], 1);
+      else is[I_OUTER] = iter + 1;
     }
+    if (is[I_ACTIVE]) atomicAdd(&D.counters[1], 1);  // pairs with work left (the host reads it every few rounds)
   }
 }
 
@@ -2049,32 +2058,40 @@ static int optimize_pairs(GfsGicp* h, const GicpDev& D, cudaStream_t st, int pai
   k_lm_init<<<div_up(pairs, 128), 128, 0, st>>>(D, pairs, d_T0);
   h->launches += 1;
   int* hc = (int*)h->h_counters.p;
-  for (int it = 0; it < D.max_iter; it++) {
-    GFS_CUDA(cudaMemsetAsync(D.counters, 0, 8, st));
+  // Rounds of [search, linearize, begin, error, decide]; every pair advances through its own state machine (see I_OUTER).  A pair
+  // needs one round per lambda trial, i.e. at least one per outer iteration; the host only looks every few rounds (after the
+  // 3rd, then every 2nd: most pairs converge within 3-8 iterations) whether any pair is left.  GFS_GICP_CHECK_EVERY=1 gives the
+  // round-1 behaviour of one host synchronisation per round.
+  static const int checkEvery = [] { const char* e = getenv("GFS_GICP_CHECK_EVERY"); const int v = e ? atoi(e) : 2; return v > 0 ? v : 2; }();
+  const int maxRounds = D.max_iter * 10;  // every outer iteration may take up to 10 trials (optimizer.hpp:107)
+  int nextCheck = checkEvery == 1 ? 0 : 2;
+  for (int round = 0; round < maxRounds; round++) {
     const dim3 gn(div_up(D.nmax, NN_THREADS), pairs);
-    if (h->nnMode == 0) k_nn_corr<<<gn, NN_THREADS, 0, st>>>(D, it);
-    else if (h->nnMode == 1) k_nn_corr2<false, false, false><<<gn, NN_THREADS, 0, st>>>(D, it);
-    else if (h->nnMode == 2) k_nn_corr2<true, false, false><<<gn, NN_THREADS, 0, st>>>(D, it);
-    else if (h->nnMode == 3) k_nn_corr2<false, true, false><<<gn, NN_THREADS, 0, st>>>(D, it);
-    else if (h->nnMode == 4) k_nn_corr2<true, true, false><<<gn, NN_THREADS, 0, st>>>(D, it);
-    else if (h->nnMode == 5) k_nn_corr2<false, false, true><<<gn, NN_THREADS, 0, st>>>(D, it);
-    else k_nn_corr2<true, false, true><<<gn, NN_THREADS, 0, st>>>(D, it);
+    if (h->nnMode == 0) k_nn_corr<<<gn, NN_THREADS, 0, st>>>(D);
+    else if (h->nnMode == 1) k_nn_corr2<false, false, false><<<gn, NN_THREADS, 0, st>>>(D);
+    else if (h->nnMode == 2) k_nn_corr2<true, false, false><<<gn, NN_THREADS, 0, st>>>(D);
+    else if (h->nnMode == 3) k_nn_corr2<false, true, false><<<gn, NN_THREADS, 0, st>>>(D);
+    else if (h->nnMode == 4) k_nn_corr2<true, true, false><<<gn, NN_THREADS, 0, st>>>(D);
+    else if (h->nnMode == 5) k_nn_corr2<false, false, true><<<gn, NN_THREADS, 0, st>>>(D);
+    else k_nn_corr2<true, false, true><<<gn, NN_THREADS, 0, st>>>(D);
     prof_mark(h, st, ST_NN);
-    k_linearize<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D, it);
+    k_linearize<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D);
     prof_mark(h, st, ST_LIN);
-    k_lm_begin<<<pairs, LIN_THREADS, 0, st>>>(D, it);
-    h->launches += 3;
-    for (int j = 0; j < 10; j++) {
-      k_error<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D);
-      GFS_CUDA(cudaMemsetAsync(D.counters, 0, 4, st));
-      k_lm_decide<<<pairs, 32, 0, st>>>(D, it);
-      h->launches += 2;
+    k_lm_begin<<<pairs, LIN_THREADS, 0, st>>>(D);
+    k_error<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D);
+    const bool check = round >= nextCheck;
+    if (check) GFS_CUDA(cudaMemsetAsync(D.counters, 0, 8, st));
+    k_lm_decide<<<pairs, 32, 0, st>>>(D);
+    h->launches += 5;
+    if (check) {
       GFS_CUDA(cudaMemcpyAsync(hc, D.counters, 8, cudaMemcpyDeviceToHost, st));
-      GFS_CUDA(cudaStreamSynchronize(st));
-      if (hc[0] == 0) break;  // no pair needs another lambda trial
+      GFS_CUDA(gfs::stream_wait(st));
+      prof_mark(h, st, ST_LM, 3);
+      if (hc[1] == 0) break;  // every pair converged / failed / hit max_iterations
+      nextCheck = round + checkEvery;
+    } else {
+      prof_mark(h, st, ST_LM, 3);
     }
-    prof_mark(h, st, ST_LM, 3);
-    if (hc[1] == 0) break;  // every pair converged / failed / hit max_iterations
   }
   k_gicp_result<<<div_up(pairs, 128), 128, 0, st>>>(D, pairs, d_out);
   h->launches += 1;
@@ -2164,7 +2181,7 @@ int gfs_gicp_track_batch(GfsGicp* h, void* stream, const float* cloud, const int
                                    (const double*)h->b_T0.p, (GfsGicpResult*)h->b_res.p);
   if (rc) return rc;
   if (!first) GFS_CUDA(cudaMemcpyAsync(out, h->b_res.p, P * sizeof(GfsGicpResult), cudaMemcpyDeviceToHost, st));
-  GFS_CUDA(cudaStreamSynchronize(st));
+  GFS_CUDA(gfs::stream_wait(st));
   return GFS_OK;
 }
 
@@ -2194,7 +2211,7 @@ int gfs_gicp_align_batch(GfsGicp* h, void* stream, const float* target, const in
                                    (GfsGicpResult*)h->b_res.p);
   if (rc) return rc;
   GFS_CUDA(cudaMemcpyAsync(out, h->b_res.p, P * sizeof(GfsGicpResult), cudaMemcpyDeviceToHost, st));
-  GFS_CUDA(cudaStreamSynchronize(st));
+  GFS_CUDA(gfs::stream_wait(st));
   return GFS_OK;
 }
 
@@ -2220,7 +2237,7 @@ int gfs_gicp_align(GfsGicp* h, void* stream, const float* target, int nt, const 
                                    (const int*)h->b_n.p + 1, 1, stride, (const double*)h->b_T0.p, (GfsGicpResult*)h->b_res.p);
   if (rc) return rc;
   GFS_CUDA(cudaMemcpyAsync(out, h->b_res.p, sizeof(GfsGicpResult), cudaMemcpyDeviceToHost, st));
-  GFS_CUDA(cudaStreamSynchronize(st));
+  GFS_CUDA(gfs::stream_wait(st));
   return GFS_OK;
 }
 
@@ -2237,7 +2254,7 @@ int gfs_gicp_get_knn_stats(GfsGicp* h, void* stream, int cloud, int* n_cells, in
 int gfs_gicp_get_cloud(GfsGicp* h, void* stream, int cloud, double* out_xyz, double* out_cov6, int cap, int* n) {
   GFS_REQUIRE(h && n && cloud >= 0 && cloud < 2 * h->maxPairs, GFS_ERR_INVALID, "bad handle/cloud");
   cudaStream_t st = (cudaStream_t)stream;
-  GFS_CUDA(cudaStreamSynchronize(st));
+  GFS_CUDA(gfs::stream_wait(st));
   int m = 0;
   GFS_CUDA(cudaMemcpy(&m, h->dev.nDown + cloud, 4, cudaMemcpyDeviceToHost));
   *n = m;

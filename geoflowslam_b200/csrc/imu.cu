@@ -200,7 +200,7 @@ int gfs_imu_preintegrate_batch(void* stream, const float* meas, const int* offse
   if (db) cudaFreeAsync(db, st);
   if (dout) cudaFreeAsync(dout, st);
   if (rc) return rc;
-  GFS_CUDA(cudaStreamSynchronize(st));
+  GFS_CUDA(gfs::stream_wait(st));
   return GFS_OK;
 }
 

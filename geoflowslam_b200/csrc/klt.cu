@@ -667,7 +667,7 @@ int gfs_klt_fb_track(GfsKlt* h, void* stream, const uint8_t* prev_img, const uin
   h->launches += l1;
   GFS_CUDA(cudaMemcpyAsync(priors, h->d_next.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   GFS_CUDA(cudaMemcpyAsync(status, h->d_status.p, (size_t)n, cudaMemcpyDeviceToHost, st));
-  GFS_CUDA(cudaStreamSynchronize(st));
+  GFS_CUDA(gfs::stream_wait(st));
   return GFS_OK;
 }
 
@@ -714,7 +714,7 @@ int gfs_clahe_apply(void* stream, const uint8_t* src, int w, int h_img, int pitc
   }
   cudaFreeAsync(d, st);
   if (rc) return rc;
-  GFS_CUDA(cudaStreamSynchronize(st));
+  GFS_CUDA(gfs::stream_wait(st));
   return GFS_OK;
 }
 

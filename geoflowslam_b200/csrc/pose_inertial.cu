@@ -897,7 +897,7 @@ int gfs_pose_inertial_optimize_batch(GfsPoseInertial* h, void* stream, const Gfs
     GFS_CUDA(cudaMemcpyAsync(hOut, h->d_outlier.p, total, cudaMemcpyDeviceToHost, st));
     GFS_CUDA(cudaMemcpyAsync(hChi, h->d_chi2.p, total * 4, cudaMemcpyDeviceToHost, st));
   }
-  GFS_CUDA(cudaStreamSynchronize(st));
+  GFS_CUDA(gfs::stream_wait(st));
   off = 0;
   for (int p = 0; p < batch; p++) {
     GfsPoseInertialResult& R = results[p];
