@@ -1026,6 +1026,7 @@ def run_track(args):
         counts["pose"] = pio.last_launches()
 
     step_no = [0]
+    pose_on_main = os.environ.get("GFS_TRACK_POSE_ON_MAIN", "0") == "1"
 
     def step(host=False, sequential=False, marks=None):
         """Advance every sequence by one frame.  host: inputs come from pinned host buffers and every result goes back to the
@@ -1047,7 +1048,9 @@ def run_track(args):
         if not sequential:
             for cs in side:
                 cs.wait_stream(s_main)
-            futs = [pool.submit(_gicp, f, depth16), pool.submit(_ba, host), pool.submit(_pose)]
+            futs = [pool.submit(_gicp, f, depth16), pool.submit(_ba, host)]
+            if not pose_on_main:
+                futs.append(pool.submit(_pose))
         # tracking front end on the main stream
         orb.extract_batch_device(gray, B, W, H, W, W * H, r_kp[f], r_desc[f], r_n[f], d_mono, stream=stream)
         check(L.gfs_match_bf_hamming_batch_device(stream, ptr(r_desc[fp]), ptr(r_n[fp]), ptr(r_desc[f]), ptr(r_n[f]), B, S, ptr(d_tidx), ptr(d_dist)))
@@ -1061,6 +1064,8 @@ def run_track(args):
         mark("klt")
         check(L.gfs_imu_preintegrate_batch_device(stream, ptr(imu), ptr(d_off), ptr(d_bias), B, cal[0], cal[1], cal[2], cal[3], ptr(d_pre)))
         mark("imu")
+        if pose_on_main and not sequential:
+            _pose()       # one launch + one wait: the main thread has nothing else to enqueue until the side streams finish
         if sequential:
             side_backup = side[:]
             side[0] = side[1] = side[2] = s_main
