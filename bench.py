@@ -926,7 +926,12 @@ def run_track(args):
     B = args.batch if args.batch != 1024 else 128
     cores = os.cpu_count() or 1
     uniq = min(B, 16)
-    data = make_track_data(uniq, 1000 + rank * 100000, max(1, min(16, cores // max(world, 1))))
+    # Weak scaling = the same work on every GPU.  GICP's cost is data dependent (3 to 20 LM iterations per pair; measured 33.7 to
+    # 41.3 ms per step over four different seed sets, profiles/r02_summary.md), so every rank gets the SAME pool of distinct
+    # synthetic sequences (tiled to B in a rank-rotated order) -- with per-rank seeds the max-over-ranks time measured the
+    # unluckiest data set, not the system.  GFS_BENCH_SEED_RANK=r (diagnostic) selects another pool.
+    seed_rank = int(os.environ.get("GFS_BENCH_SEED_RANK", "0"))
+    data = make_track_data(uniq, 1000 + seed_rank * 100000, max(1, min(16, cores // max(world, 1))))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -936,7 +941,7 @@ def run_track(args):
     L = lib()
     cam = synth.G1_CAM
     cal = synth.imu_calib_noise()
-    idx = np.arange(B) % uniq
+    idx = (np.arange(B) + rank) % uniq
 
     # ---- host inputs (pinned) and their resident copies
     def pinned(a):
@@ -1212,7 +1217,7 @@ def run_track(args):
                        "stage_ms_one_stream": stage,
                        "step_mode": "front end (ORB, match, optical flow, IMU) on the main stream; pose optimiser, depth->cloud+GICP and BA on a stream + host thread each (the reference's Tracking / LocalMapping threads)",
                        "l2": "inputs larger than L2 (%.0f MB of new frames per step, ring of %d)" % ((h_gray[0].nbytes + h_depth[0].nbytes) / 1e6, RING),
-                       "parallelism": "sequences sharded across ranks, no data-path collective",
+                       "parallelism": "sequences sharded across ranks (every rank: the same pool of %d distinct sequences tiled to %d, rank-rotated), no data-path collective" % (uniq, B),
                        "sub_lines": sub,
                        "note": "map-dependent inputs (pose-optimiser observations, BA window) are synthetic problems of the named shapes; tests/test_gpu_closed_loop.py chains the stages causally"},
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
