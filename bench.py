@@ -987,9 +987,15 @@ def run_track(args):
     CAP = 65536
     d_depthf = torch.empty((B, H, W), dtype=torch.float32, device=dev)
     d_cloud = torch.empty((B, CAP, 4), dtype=torch.float32, device=dev); d_cn = torch.zeros(B, dtype=torch.int32, device=dev)
-    reg = RegistrationGICP(max_points=CAP, max_pairs=B)
+    # the sequences' GICP can be cut into GSPLIT groups, each with its own handle, stream and host thread: the late LM rounds of one
+    # group (few unconverged pairs left, small grids) then overlap the full rounds of another (GFS_TRACK_GICP_SPLIT, default 1)
+    GSPLIT = max(1, int(os.environ.get("GFS_TRACK_GICP_SPLIT", "1")))
+    assert B % GSPLIT == 0
+    BG = B // GSPLIT
+    regs = [RegistrationGICP(max_points=CAP, max_pairs=BG) for _ in range(GSPLIT)]
+    reg = regs[0]
     d_T0 = torch.from_numpy(np.tile(np.eye(4), (B, 1, 1))).to(dev)
-    d_res = torch.zeros(B * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_res = torch.zeros((B, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     # ---- LocalInertialBA for the sequences that insert a keyframe this step
     nba = max(1, B // KF_EVERY)
     ba_batch = [data["ba"][i % len(data["ba"])] for i in range(nba)]
@@ -1003,7 +1009,8 @@ def run_track(args):
     o_pr, o_st, o_pre, o_res = pin_out(d_pr), pin_out(d_st), pin_out(d_pre), pin_out(d_res)
 
     side = [torch.cuda.Stream(device=dev) for _ in range(3)]
-    pool = ThreadPoolExecutor(3)
+    gside = [side[0]] + [torch.cuda.Stream(device=dev) for _ in range(GSPLIT - 1)]
+    pool = ThreadPoolExecutor(3 + GSPLIT - 1)
     counts = dict(orb=0, match=0, klt=0, imu=0, pose=0, cloud=0, gicp=0, ba=0)
     ba_host = [None]
 
@@ -1014,8 +1021,27 @@ def run_track(args):
         cs = side[0].cuda_stream
         check(L.gfs_depth_to_cloud_batch_device(cs, ptr(d_depthf), B, W, H, W, W * H, 2, cam["fx"], cam["fy"], cam["cx"], cam["cy"],
                                                 ptr(d_cloud), CAP, ptr(d_cn)))
-        reg.track_batch_device(d_cloud, d_cn, B, CAP, d_T0, d_res, stream=cs)
-        counts["cloud"] = 1; counts["gicp"] = reg.last_launches()
+        if GSPLIT == 1 or side[0] is s_main:
+            for gi, r in enumerate(regs):
+                sl = slice(gi * BG, (gi + 1) * BG)
+                r.track_batch_device(d_cloud[sl], d_cn[sl], BG, CAP, d_T0[sl], d_res[sl], stream=cs)
+        else:
+            ev = torch.cuda.Event(); ev.record(side[0])
+            fs = []
+            for gi in range(1, GSPLIT):
+                gside[gi].wait_event(ev)
+                fs.append(pool.submit(_gicp_group, gi))
+            _gicp_group(0)
+            for ft in fs:
+                ft.result()
+            for gi in range(1, GSPLIT):
+                side[0].wait_stream(gside[gi])
+        counts["cloud"] = 1; counts["gicp"] = sum(r.last_launches() for r in regs)
+
+    def _gicp_group(gi):
+        torch.cuda.set_device(local)
+        sl = slice(gi * BG, (gi + 1) * BG)
+        regs[gi].track_batch_device(d_cloud[sl], d_cn[sl], BG, CAP, d_T0[sl], d_res[sl], stream=gside[gi].cuda_stream)
 
     def _ba(host):
         torch.cuda.set_device(local)
@@ -1131,7 +1157,7 @@ def run_track(args):
     h2d = int(h_gray[0].nbytes + h_depth[0].nbytes + h_imu[0].nbytes) + pin_bytes + ba_bytes
     d2h = int(sum(o.nbytes for o in (o_kp, o_desc, o_n, o_tidx, o_inl, o_inlc, o_pr, o_st, o_pre, o_res))) + B * (2000 + 400 * 5) + \
         nba * (21 * 15 * 8 + 3000 * 24 + 16384)
-    gicp_res = o_res.numpy().view(RESULT_DTYPE).copy()
+    gicp_res = o_res.numpy().reshape(-1).view(RESULT_DTYPE).copy()
 
     # ---- per-stage times: one stream, stages back to back (CUDA events), and GICP's kernels by stage
     stage = {}
@@ -1144,16 +1170,19 @@ def run_track(args):
         for (k0, e0), (k1, e1) in zip(marks[:-1], marks[1:]):
             stage.setdefault(k1, []).append(e0.elapsed_time(e1))
     stage = {k: sum(v) / len(v) for k, v in stage.items()}
-    reg.set_profiling(True)
+    for r in regs:
+        r.set_profiling(True)
     gprof = {}
     for _ in range(3):
         step(sequential=True)
         torch.cuda.synchronize()
-        for k, (ms, ln) in reg.profile().items():
-            a = gprof.setdefault(k, [0.0, 0]); a[0] += ms / 3; a[1] += ln / 3
-    reg.set_profiling(False)
+        for r in regs:
+            for k, (ms, ln) in r.profile().items():
+                a = gprof.setdefault(k, [0.0, 0]); a[0] += ms / 3; a[1] += ln / 3
+    for r in regs:
+        r.set_profiling(False)
     pool.shutdown()
-    res = d_res.cpu().numpy().view(RESULT_DTYPE)
+    res = d_res.cpu().numpy().reshape(-1).view(RESULT_DTYPE)
     n_in = float(d_cn.float().mean().item())
     M = float(res["n_source"].mean()); I = float(res["iterations"].mean() + 1); J = float(res["inner_evals"].mean())
     kp_mean = float(r_n[0].float().mean().item())
@@ -1172,7 +1201,7 @@ def run_track(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
     # algorithmic bytes per launch: 10-NN covariances = query 32 B + 10 neighbours x 32 B
     # + covariance 48 B per downsampled point; correspondence search = source point 32 B + target point 32 B + index 4 B
-    alg = {"knn_cov": B * M * (32 + 320 + 48), "nn_corr": B * M * (32 + 32 + 4), "linearize": B * M * (32 + 4 + 48 + 48 + 32 + 72)}
+    alg = {"knn_cov": BG * M * (32 + 320 + 48), "nn_corr": BG * M * (32 + 32 + 4), "linearize": BG * M * (32 + 4 + 48 + 48 + 32 + 72)}   # per launch (one group)
     kern = {k: v for k, v in gprof.items() if k in alg and v[1] > 0}
     top = max(kern, key=lambda k: kern[k][0])
     per_launch_ms = kern[top][0] / kern[top][1]
@@ -1181,7 +1210,7 @@ def run_track(args):
                          "nn_corr": (105.925376e6 + 4.146176e6) / (64 * 42100.0)}        # profiles/r02_s1_gicp_nn_corr_after_ncu_details.txt
     roof = {"bound": "hbm", "kernel": {"knn_cov": "k_knn_cov", "nn_corr": "k_nn_corr2", "linearize": "k_linearize"}[top],
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic_per_query[top] * B * M if top in traffic_per_query else None,
+            "traffic": traffic_per_query[top] * BG * M if top in traffic_per_query else None,
             "traffic_source": "ncu --set full capture under profiles/ (r02_s1_gicp_*_ncu_details.txt), scaled per query" if top in traffic_per_query else None,
             "algorithmic_bytes": alg[top], "ms_per_launch": per_launch_ms, "launches_per_step": kern[top][1], "peak_source": peak_src,
             "gicp_stage_ms_per_step": {k: v[0] for k, v in gprof.items()},
@@ -1215,6 +1244,7 @@ def run_track(args):
                        "distinct_sequences": uniq, "mean_keypoints": kp_mean, "cloud_points": n_in, "downsampled": M,
                        "gicp_outer_iterations": I, "gicp_inner_evals": J,
                        "stage_ms_one_stream": stage,
+                       "gicp_groups": GSPLIT,
                        "step_mode": "front end (ORB, match, optical flow, IMU) on the main stream; pose optimiser, depth->cloud+GICP and BA on a stream + host thread each (the reference's Tracking / LocalMapping threads)",
                        "l2": "inputs larger than L2 (%.0f MB of new frames per step, ring of %d)" % ((h_gray[0].nbytes + h_depth[0].nbytes) / 1e6, RING),
                        "parallelism": "sequences sharded across ranks (every rank: the same pool of %d distinct sequences tiled to %d, rank-rotated), no data-path collective" % (uniq, B),

@@ -1921,7 +1921,9 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   // grid cell = the correspondence radius (the bounded 1-NN search then ends after shells 0-1), never finer than
   // 4 voxels (a 3x3x3 block must hold the 10 nearest neighbours of almost every point).  Measured on the
   // configs[2] clouds: 0.05 m -> 1816 pairs/s, 0.065 -> 2447, 0.08 -> 2445, 0.1 -> 2505 (profiles/r01_summary.md)
-  D.cell = std::max(s.max_correspondence_distance, 4.0 * s.downsampling_resolution);
+  // ... and 10 % above that: with cell == radius the first, unseeded search (R = radius) reaches two cells down an axis whenever the
+  // query sits right at a face; 0.11 m measured 4401 pairs/s against 4214 at 0.10 and 3954 at 0.125 (profiles/r02_summary.md)
+  D.cell = 1.1 * std::max(s.max_correspondence_distance, 4.0 * s.downsampling_resolution);
   if (const char* ce = getenv("GFS_GICP_CELL")) {  // tuning knob (metres); any value gives the same results
     const double v = atof(ce);
     if (v > 0) D.cell = v;
