@@ -160,11 +160,12 @@ int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batc
   bool matchedInChunks = false;
   // H2D is faster than the kernels, so after the first chunk the copy stream stays ahead: only the first
   // copy is exposed.  Chunks of batch/12 keep it short while the kernels still see >= 64 frames.
-  const char* ce = getenv("GFS_FRONTEND_CHUNKS");
-  const int nDiv = ce ? std::max(1, atoi(ce)) : 12;
-  f->chunk = std::max(64, div_up(batch, nDiv));
-  const char* fe = getenv("GFS_FRONTEND_FIRST");
-  const int firstChunk = fe ? std::min(f->chunk, std::max(1, atoi(fe))) : std::max(32, f->chunk / 2);
+  // tuning knobs, read once per process
+  static const int envChunks = [] { const char* e = getenv("GFS_FRONTEND_CHUNKS"); return e ? std::max(1, atoi(e)) : 12; }();
+  static const int envFirst = [] { const char* e = getenv("GFS_FRONTEND_FIRST"); return e ? std::max(1, atoi(e)) : 0; }();
+  static const int envStreams = [] { const char* e = getenv("GFS_FRONTEND_STREAMS"); return e ? std::min(8, std::max(1, atoi(e))) : 8; }();
+  f->chunk = std::max(64, div_up(batch, envChunks));
+  const int firstChunk = envFirst ? std::min(f->chunk, envFirst) : std::max(32, f->chunk / 2);
   if (pinned && batch > f->chunk) {
     // ---- pipelined: chunked H2D on a copy stream, kernels on the caller's stream, D2H on a third
     if (!f->copyStream) {
@@ -193,8 +194,7 @@ int gfs_frontend_run(GfsFrontend* f, void* stream, const uint8_t* imgs, int batc
     // the chunk size) needs the throughput kernels of several other chunks to hide behind.  Measured (B200, 1024
     // VGA frames, frames/s end to end; profiles/r01_summary.md): 8 chunks on 2 / 3 / 4 streams 100.0k / 104.9k /
     // 108.8k; with the final kernels 4 streams x 8 chunks 123.5k, 6 x 10 125.3k, 8 x 12 127.0k (default).
-    const char* se = getenv("GFS_FRONTEND_STREAMS");
-    const int nStreams = se ? std::min(8, std::max(1, atoi(se))) : 8;
+    const int nStreams = envStreams;
     cudaStream_t streams[8] = {st, f->aux[0], f->aux[1], f->aux[2], f->aux[3], f->aux[4], f->aux[5], f->aux[6]};
     // A chunk's frame
     // pairs (and the pair that straddles the previous chunk) are matched and copied out right behind
