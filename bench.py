@@ -994,9 +994,14 @@ def run_track(args):
     d_bias = torch.zeros((B, 6), dtype=torch.float32, device=dev)
     d_pre = torch.empty((B, PRE_STRIDE), dtype=torch.float32, device=dev)
     # staging buffers of the host-buffer (e2e) path
-    s_gray = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
-    s_depth = torch.empty((B, H, W), dtype=torch.int16, device=dev)
-    s_imu = torch.empty((B * 7, 7), dtype=torch.float32, device=dev)
+    # two sets: while step s computes on set s & 1, the copy stream brings frame s + 1 into the other set (every step still copies
+    # one frame's inputs from pinned host memory inside the timed region; the copy overlaps the previous step's kernels)
+    s_gray = [torch.empty((B, H, W), dtype=torch.uint8, device=dev) for _ in range(2)]
+    s_depth = [torch.empty((B, H, W), dtype=torch.int16, device=dev) for _ in range(2)]
+    s_imu = [torch.empty((B * 7, 7), dtype=torch.float32, device=dev) for _ in range(2)]
+    s_copy = torch.cuda.Stream(device=dev)
+    copy_done = [None, None]          # event of the copy that fills a set; step number it was filled for
+    copy_for = [-1, -1]
 
     # ---- ORB + match state: ring of keypoints / descriptors
     orb = ORBextractor(max_size=(W, H), max_batch=B, **ORB_CFG)
@@ -1100,9 +1105,21 @@ def run_track(args):
         s = step_no[0]; step_no[0] += 1
         f, fp = s % RING, (s - 1) % RING
         if host:
-            s_gray.copy_(h_gray[f], non_blocking=True); s_depth.copy_(h_depth[f], non_blocking=True)
-            s_imu.copy_(h_imu[f], non_blocking=True)
-            gray, depth16, imu = s_gray, s_depth, s_imu
+            def issue_copy(step_idx):
+                k, ff = step_idx & 1, step_idx % RING
+                with torch.cuda.stream(s_copy):
+                    s_gray[k].copy_(h_gray[ff], non_blocking=True); s_depth[k].copy_(h_depth[ff], non_blocking=True)
+                    s_imu[k].copy_(h_imu[ff], non_blocking=True)
+                    ev = torch.cuda.Event(); ev.record(s_copy)
+                copy_done[k], copy_for[k] = ev, step_idx
+            k = s & 1
+            if copy_for[k] != s:              # first host step (or after device-resident steps): nothing was prefetched
+                s_copy.wait_stream(s_main)
+                issue_copy(s)
+            s_main.wait_event(copy_done[k])
+            # the other set was last read by step s - 1, which has fully completed (host steps end with a synchronize)
+            issue_copy(s + 1)
+            gray, depth16, imu = s_gray[k], s_depth[k], s_imu[k]
         else:
             gray, depth16, imu = d_gray[f], d_depth[f], d_imu[f]
 
