@@ -958,7 +958,9 @@ def run_track(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    B = args.batch if args.batch != 1024 else 128
+    # sequences per GPU and step: 256 measured best (3937 / 4070 / 4178 / 4107 frames/s device-resident and 3820 / 4066 / 3951 / 3960 end
+    # to end at 128 / 256 / 384 / 512; the LM rounds' small-grid tails and the latency-bound BA / pose launches amortise)
+    B = args.batch if args.batch != 1024 else 256
     cores = os.cpu_count() or 1
     uniq = min(B, 16)
     # Weak scaling = the same work on every GPU.  GICP's cost is data dependent (3 to 20 LM iterations per pair; measured 33.7 to

@@ -41,6 +41,7 @@ struct GicpDev {
   int cbase, cstep, swap;
   int inputAll;     // 1: every cloud's raw points come from the `src` array (track mode); 0: even clouds from `tgt`
   int cellOrder;    // 1: neighbour-search kernels take their queries in grid-cell order (rec[]), not in point order
+  int octSorted;    // 1: k_cell_sort ran (an octant kernel is selected): k_cell_pack takes the cell's members from slotOf[]
   // per cloud (2 * pairs clouds; cloud 2p = target of pair p, 2p+1 = source)
   unsigned long long* keys;  // [clouds][hsize]
   int* minIdx;               // [clouds][hsize]
@@ -73,6 +74,7 @@ struct GicpDev {
   double* state;             // [pairs][LM_STATE]
   int* istate;               // [pairs][LM_ISTATE]
   int* counters;             // [4]: needTrial, active
+  int* tickets;              // [pairs][2] blocks of the pair that finished k_linearize / k_error (the last one does the pair's LM step)
 };
 
 // per-pair LM state layout (doubles)
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(256) k_cell_pack(GicpDev D, int clouds) {
     const int c = cloud_of(D, (int)(i0 / D.nmax)), m = (int)(i0 % D.nmax);
     const size_t i = (size_t)c * D.nmax + m;
     if (m < D.nDown[c]) {
-      const int pi = D.slotOf[i];   // the cell's members in octant order (k_cell_sort)
+      const int pi = D.octSorted ? D.slotOf[i] : D.members[i];   // octant order (k_cell_sort) only when an octant kernel needs it
       const double2* p = reinterpret_cast<const double2*>(D.pts + ((size_t)c * D.nmax + pi) * 4);
       double2* o = reinterpret_cast<double2*>(D.rec + (size_t)i * 4);
       const double2 xy = p[0];
@@ -1500,12 +1502,33 @@ __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr2(GicpDev D) {
   D.corr[(size_t)p * D.nmax + i] = (id != 0x7fffffff && !(d > max_d2)) ? id : -1;  // DistanceRejector: sq_dist > max_dist_sq
 }
 
-// GICPFactor::linearize for every source point of every active pair + partial sums
+__device__ void lm_begin_block(const GicpDev& D, int p);   // defined below (need lm_trial)
+__device__ void lm_decide_thread(const GicpDev& D, int p);
+// true in every thread of exactly one block of pair p: the one that finished last among the `nblocks` participating ones
+// (classic threadfence reduction: results written before the fence are visible to the block that draws the last ticket)
+__device__ __forceinline__ bool last_block_of_pair(const GicpDev& D, int p, int which, int nblocks) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(&D.tickets[2 * p + which], 1);
+    s_last = (t == nblocks - 1);
+    if (s_last) D.tickets[2 * p + which] = 0;  // ready for the next round
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
+// GICPFactor::linearize for every source point of every active pair + partial sums; the pair's last block then sums the
+// partials in their fixed order and starts the first lambda trial (what k_lm_begin did in a launch of its own)
 __global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D) {
   const int p = blockIdx.y;
   if (!D.istate[p * LM_ISTATE + I_ACTIVE] || D.istate[p * LM_ISTATE + I_NEED]) return;
   const int ct = tgt_cloud(D, p), cs = src_cloud(D, p);
   const int ns = D.nDown[cs];
+  const int nbp = max((ns + LIN_THREADS - 1) / LIN_THREADS, 1);  // participating blocks (block 0 always: an empty cloud still steps)
+  if ((int)blockIdx.x >= nbp) return;
   const int i = blockIdx.x * LIN_THREADS + threadIdx.x;
   double acc[RED_N];
 #pragma unroll
@@ -1583,14 +1606,18 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D) {
       if (lane == 0) out[k] = x;
     }
   }
+  if (last_block_of_pair(D, p, 0, nbp)) lm_begin_block(D, p);
 }
 
-// GICPFactor::error with the stored correspondences / Mahalanobis matrices
+// GICPFactor::error with the stored correspondences / Mahalanobis matrices; the pair's last block then decides the trial
+// (what k_lm_decide did in a launch of its own)
 __global__ void __launch_bounds__(LIN_THREADS) k_error(GicpDev D) {
   const int p = blockIdx.y;
   if (!D.istate[p * LM_ISTATE + I_NEED]) return;
   const int ct = tgt_cloud(D, p), cs = src_cloud(D, p);
   const int ns = D.nDown[cs];
+  const int nbp = max((ns + LIN_THREADS - 1) / LIN_THREADS, 1);
+  if ((int)blockIdx.x >= nbp) return;
   const int i = blockIdx.x * LIN_THREADS + threadIdx.x;
   double acc[1] = {0.0};
   if (i < ns) {
@@ -1609,6 +1636,7 @@ __global__ void __launch_bounds__(LIN_THREADS) k_error(GicpDev D) {
     }
   }
   block_reduce_store<1, LIN_THREADS>(acc, D.partialE + (size_t)p * D.nblk + blockIdx.x);
+  if (last_block_of_pair(D, p, 1, nbp) && threadIdx.x == 0) lm_decide_thread(D, p);
 }
 
 // ---- 6x6 LDL^T solve, se3_exp, compose (one thread)
@@ -1701,23 +1729,22 @@ __device__ void lm_trial(double* st) {
   for (int a = 0; a < 6; a++) st[S_DELTA + a] = delta[a];
 }
 
-// one warp per pair: sum the partials in block order (lane v owns value v), start the first trial
-__global__ void __launch_bounds__(LIN_THREADS) k_lm_begin(GicpDev D) {
+// all LIN_THREADS threads of one block: sum the pair's per-warp partials in block order, start the first trial (:97-112)
+__device__ void lm_begin_block(const GicpDev& D, int p) {
   __shared__ double s_tot[RED_N];
-  const int p = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   int* is = D.istate + p * LM_ISTATE;
-  if (!is[I_ACTIVE] || is[I_NEED]) return;
   const int iter = is[I_OUTER];
   double* st = D.state + (size_t)p * LM_STATE;
   // fixed-order sum of the per-warp partials: thread t takes partials t, t+128, ...; then lanes, then warps
-  const int nw = ((D.nDown[src_cloud(D, p)] + LIN_THREADS - 1) / LIN_THREADS) * (LIN_THREADS / 32);
+  const int nw = max((D.nDown[src_cloud(D, p)] + LIN_THREADS - 1) / LIN_THREADS, 1) * (LIN_THREADS / 32);
   double acc[RED_N];
 #pragma unroll
   for (int k = 0; k < RED_N; k++) acc[k] = 0.0;
   const double* part = D.partial + (size_t)p * D.nblk * (LIN_THREADS / 32) * RED_N;
   for (int b = tid; b < nw; b += LIN_THREADS) {
 #pragma unroll
-    for (int k = 0; k < RED_N; k++) acc[k] += part[(size_t)b * RED_N + k];
+    for (int k = 0; k < RED_N; k++) acc[k] += __ldcg(&part[(size_t)b * RED_N + k]);  // written by other blocks: read through L2
   }
   block_reduce_store<RED_N, LIN_THREADS>(acc, s_tot);
   __syncthreads();
@@ -1733,45 +1760,42 @@ __global__ void __launch_bounds__(LIN_THREADS) k_lm_begin(GicpDev D) {
     is[I_ITER] = iter;
     is[I_TRIAL] = 0;
     is[I_SUCCESS] = 0;
-    is[I_NEED] = 1;
     lm_trial(st);
+    __threadfence();
+    is[I_NEED] = 1;
   }
 }
 
-// one warp per pair: new_e, accept / reject, next trial or end of the outer iteration (:114-143)
-__global__ void __launch_bounds__(32) k_lm_decide(GicpDev D) {
-  const int p = blockIdx.x, lane = threadIdx.x;
+// one thread: new_e, accept / reject, next trial or end of the outer iteration (:114-143)
+__device__ void lm_decide_thread(const GicpDev& D, int p) {
   int* is = D.istate + p * LM_ISTATE;
-  if (!is[I_NEED]) return;
   const int iter = is[I_OUTER];
   double* st = D.state + (size_t)p * LM_STATE;
-  const int nb = (D.nDown[src_cloud(D, p)] + LIN_THREADS - 1) / LIN_THREADS;
-  // fixed-order sum: lane-strided partial sums are NOT order-preserving, so lane 0 sums serially
+  const int nb = max((D.nDown[src_cloud(D, p)] + LIN_THREADS - 1) / LIN_THREADS, 1);
+  // fixed-order sum: lane-strided partial sums are NOT order-preserving, so one thread sums serially
   double new_e = 0;
-  if (lane == 0) {
-    for (int b = 0; b < nb; b++) new_e += D.partialE[(size_t)p * D.nblk + b];
-    is[I_INNER]++;
-    if (new_e <= st[S_E]) {
-      const double* d = st + S_DELTA;
-      const double dr = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-      const double dt = sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
-      is[I_CONV] = (dr <= D.rot_eps && dt <= D.trans_eps) ? 1 : 0;
-      for (int k = 0; k < 12; k++) st[S_T + k] = st[S_NEWT + k];
-      st[S_LAMBDA] /= 10.0;
-      is[I_SUCCESS] = 1;
-      is[I_NEED] = 0;
-    } else {
-      st[S_LAMBDA] *= 10.0;
-      is[I_TRIAL]++;
-      if (is[I_TRIAL] >= 10) is[I_NEED] = 0;
-      else lm_trial(st);  // the next round's error / decide slots evaluate it
-    }
-    if (!is[I_NEED]) {  // the outer iteration is over for this pair
-      if (!is[I_SUCCESS] || is[I_CONV] || iter + 1 >= D.max_iter) is[I_ACTIVE] = 0;
-      else is[I_OUTER] = iter + 1;
-    }
-    if (is[I_ACTIVE]) atomicAdd(&D.counters[1], 1);  // pairs with work left (the host reads it every few rounds)
+  for (int b = 0; b < nb; b++) new_e += __ldcg(&D.partialE[(size_t)p * D.nblk + b]);
+  is[I_INNER]++;
+  if (new_e <= st[S_E]) {
+    const double* d = st + S_DELTA;
+    const double dr = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    const double dt = sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
+    is[I_CONV] = (dr <= D.rot_eps && dt <= D.trans_eps) ? 1 : 0;
+    for (int k = 0; k < 12; k++) st[S_T + k] = st[S_NEWT + k];
+    st[S_LAMBDA] /= 10.0;
+    is[I_SUCCESS] = 1;
+    is[I_NEED] = 0;
+  } else {
+    st[S_LAMBDA] *= 10.0;
+    is[I_TRIAL]++;
+    if (is[I_TRIAL] >= 10) is[I_NEED] = 0;
+    else lm_trial(st);  // the next round's error slot evaluates it
   }
+  if (!is[I_NEED]) {  // the outer iteration is over for this pair
+    if (!is[I_SUCCESS] || is[I_CONV] || iter + 1 >= D.max_iter) is[I_ACTIVE] = 0;
+    else is[I_OUTER] = iter + 1;
+  }
+  if (is[I_ACTIVE]) atomicAdd(&D.counters[1], 1);  // pairs with work left (the host reads it every few rounds)
 }
 
 __global__ void k_lm_init(GicpDev D, int pairs, const double* __restrict__ T0) {
@@ -1784,6 +1808,7 @@ __global__ void k_lm_init(GicpDev D, int pairs, const double* __restrict__ T0) {
   int* is = D.istate + p * LM_ISTATE;
   for (int k = 0; k < LM_ISTATE; k++) is[k] = 0;
   is[I_ACTIVE] = D.max_iter > 0 ? 1 : 0;
+  D.tickets[2 * p] = 0; D.tickets[2 * p + 1] = 0;
 }
 
 __global__ void k_gicp_result(GicpDev D, int pairs, GfsGicpResult* __restrict__ out) {
@@ -1830,7 +1855,7 @@ struct GfsGicp {
   GicpDev dev;
   int maxPairs = 0;
   DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_nFall, b_box, b_pts, b_cov, b_tab, b_rec, b_recf, b_oct, b_knnList, b_knnCnt,
-      b_corr, b_maha, b_partial, b_partialE, b_state, b_istate, b_counters;
+      b_corr, b_maha, b_partial, b_partialE, b_state, b_istate, b_counters, b_tickets;
   DevBuf b_tgt, b_src, b_n, b_T0, b_res;
   PinnedBuf h_counters;
   int launches = 0;
@@ -1935,6 +1960,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   if (const char* e = getenv("GFS_GICP_ORDER")) D.cellOrder = atoi(e) != 0;  // 0: queries in point order (first generation)
   if (const char* e = getenv("GFS_GICP_NN")) h->nnMode = atoi(e);
   if (const char* e = getenv("GFS_GICP_KNN")) h->knnMode = atoi(e);
+  D.octSorted = (h->knnMode == 1 || h->nnMode == 3 || h->nnMode == 4) ? 1 : 0;
   D.rot_eps = s.rotation_eps;
   D.trans_eps = s.translation_eps;
   D.k = s.num_neighbors;
@@ -1976,6 +2002,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   RES(b_state, P * LM_STATE * 8, state, double*)
   RES(b_istate, P * LM_ISTATE * 4, istate, int*)
   RES(b_counters, 16, counters, int*)
+  RES(b_tickets, P * 8, tickets, int*)
 #undef RES
   if ((rc = h->h_counters.reserve(16))) { delete h; return rc; }
   *out = h;
@@ -1986,7 +2013,7 @@ int gfs_gicp_destroy(GfsGicp* h) {
   if (!h) return GFS_OK;
   DevBuf* d[] = {&h->b_keys, &h->b_minIdx, &h->b_count, &h->b_start, &h->b_cursor, &h->b_rank, &h->b_slotOf, &h->b_members,
                  &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_nFall, &h->b_box, &h->b_pts, &h->b_cov, &h->b_tab, &h->b_rec, &h->b_recf, &h->b_oct, &h->b_knnList, &h->b_knnCnt, &h->b_corr, &h->b_maha, &h->b_partial,
-                 &h->b_partialE, &h->b_state, &h->b_istate, &h->b_counters, &h->b_tgt, &h->b_src, &h->b_n, &h->b_T0, &h->b_res};
+                 &h->b_partialE, &h->b_state, &h->b_istate, &h->b_counters, &h->b_tickets, &h->b_tgt, &h->b_src, &h->b_n, &h->b_T0, &h->b_res};
   for (DevBuf* b : d) b->release();
   h->h_counters.release();
   for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
@@ -2027,11 +2054,13 @@ static int preprocess_clouds(GfsGicp* h, const GicpDev& D, cudaStream_t st, int 
   // grid over the downsampled points (reuses the hash-table storage); group count is not needed
   group_build(h, D, st, 1, clouds, nullptr, nullptr, 0, D.nCells);
   {
-    const long long slots = (long long)clouds * D.hsize;
-    k_cell_sort<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(D, clouds);
+    if (D.octSorted) {
+      const long long slots = (long long)clouds * D.hsize;
+      k_cell_sort<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(D, clouds);
+      h->launches += 1;
+    }
     const long long work = (long long)clouds * std::max(D.hsize, D.nmax);
     k_cell_pack<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(D, clouds);
-    h->launches += 1;
   }
   prof_mark(h, st, ST_GROUP, 11);
   if (h->knnMode == 1 && !h->cellKnn) {
@@ -2077,22 +2106,20 @@ static int optimize_pairs(GfsGicp* h, const GicpDev& D, cudaStream_t st, int pai
     else if (h->nnMode == 5) k_nn_corr2<false, false, true><<<gn, NN_THREADS, 0, st>>>(D);
     else k_nn_corr2<true, false, true><<<gn, NN_THREADS, 0, st>>>(D);
     prof_mark(h, st, ST_NN);
-    k_linearize<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D);
+    k_linearize<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D);   // + the pair's LM begin in its last block
     prof_mark(h, st, ST_LIN);
-    k_lm_begin<<<pairs, LIN_THREADS, 0, st>>>(D);
-    k_error<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D);
     const bool check = round >= nextCheck;
     if (check) GFS_CUDA(cudaMemsetAsync(D.counters, 0, 8, st));
-    k_lm_decide<<<pairs, 32, 0, st>>>(D);
-    h->launches += 5;
+    k_error<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D);       // + the pair's LM decision in its last block
+    h->launches += 3;
     if (check) {
       GFS_CUDA(cudaMemcpyAsync(hc, D.counters, 8, cudaMemcpyDeviceToHost, st));
       GFS_CUDA(gfs::stream_wait(st));
-      prof_mark(h, st, ST_LM, 3);
+      prof_mark(h, st, ST_LM, 1);
       if (hc[1] == 0) break;  // every pair converged / failed / hit max_iterations
       nextCheck = round + checkEvery;
     } else {
-      prof_mark(h, st, ST_LM, 3);
+      prof_mark(h, st, ST_LM, 1);
     }
   }
   k_gicp_result<<<div_up(pairs, 128), 128, 0, st>>>(D, pairs, d_out);
