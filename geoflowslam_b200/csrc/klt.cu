@@ -423,18 +423,35 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
       // Common case (level widths that are multiples of 4, or a reflected window): every staged row has the same
       // misalignment, so a pixel's address is one multiply-add; and a lane's <= 64 products (|diff| <= 8160 =
       // 255 * 32, |d| <= 4080 = 16 * 255: each < 2^25) sum exactly in 32 bits.
+      // Every lane takes ONE contiguous run of the window in raster order (39 pixels of the 35 x 35 window) instead of every
+      // 32nd pixel: the left column of a pixel's 2 x 2 neighbourhood is the right column of the pixel before it, so a step
+      // loads two new bytes instead of four and advances its pointers by one (the sums are exact integers: any order gives
+      // the same bits).
       const uint8_t* wbase = s_win + (aJ == NO_SHIFT ? 0 : (int)aJ);
       int a1 = 0, a2 = 0;
-      int x = lane, y = 0;
-      while (x >= win) { x -= win; y++; }
-      for (int i = lane; i < win * win; i += 32) {
+      const int n = win * win, per = (n + 31) >> 5;
+      int i = lane * per;
+      const int iend = min(i + per, n);
+      if (i < iend) {
+        int y = i / win, x = i - y * win;
         const uint8_t* s0 = wbase + y * pitch + x;
-        const int diff = descale(s0[0] * iw00 + s0[1] * iw01 + s0[pitch] * iw10 + s0[pitch + 1] * iw11, W_BITS - 5) - s_I[i];
-        const short2 d = s_dI[y * (win + 1) + x];
-        a1 += diff * d.x;
-        a2 += diff * d.y;
-        x += 32;
-        while (x >= win) { x -= win; y++; }
+        const short2* dp = s_dI + y * (win + 1) + x;
+        int p00 = s0[0], p10 = s0[pitch];
+        for (; i < iend; i++) {
+          const int p01 = s0[1], p11 = s0[pitch + 1];
+          const int diff = descale(p00 * iw00 + p01 * iw01 + p10 * iw10 + p11 * iw11, W_BITS - 5) - s_I[i];
+          const short2 d = *dp;
+          a1 += diff * d.x;
+          a2 += diff * d.y;
+          if (++x == win) {   // next row: skip the window's extra column, reload the left column
+            x = 0;
+            s0 += pitch - win + 1; dp += 2;
+            p00 = s0[0]; p10 = s0[pitch];
+          } else {
+            s0++; dp++;
+            p00 = p01; p10 = p11;
+          }
+        }
       }
       sb1 = a1; sb2 = a2;
     } else {
