@@ -179,3 +179,46 @@ def test_counts_beyond_stride_are_rejected():
         reg.align_batch(a, np.array([2000], np.int32), a, np.array([10], np.int32), np.eye(4)[None])
     with pytest.raises(GfsError):
         reg.align_batch(a, np.array([10], np.int32), a, np.array([-1], np.int32), np.eye(4)[None])
+
+
+def test_track_mode_edge_cases():
+    """Tracking mode with an empty cloud, a tiny cloud (fewer than 10 points: PredictStateICP refuses such frames, the library
+    must still not misbehave) and a cloud of identical points in the chain: same bytes as the pairwise align, no crash."""
+    from geoflowslam_b200 import RegistrationGICP
+    t, s_, _ = synth.gicp_pair(2060, n_target=4000)
+    tiny = t[:7].copy()
+    same = np.tile(t[:1], (300, 1))
+    chain = [t, np.zeros((0, 4), np.float32), s_, tiny, t, same, s_]
+    stride = max(len(c) for c in chain)
+    T0 = np.eye(4)[None]
+    trk = RegistrationGICP(max_points=stride, max_pairs=1)
+    ref = RegistrationGICP(max_points=stride, max_pairs=1)
+
+    def pack(c):
+        a = np.zeros((1, stride, 4), np.float32); a[0, :len(c)] = c
+        return a, np.array([len(c)], np.int32)
+    assert trk.track_batch(*pack(chain[0])) is None
+    for k in range(1, len(chain)):
+        a, n = pack(chain[k]); pa, pn = pack(chain[k - 1])
+        r = trk.track_batch(a, n, T0)
+        e = ref.align_batch(pa, pn, a, n, T0)
+        assert r.tobytes() == e.tobytes(), "chain step %d" % k
+        assert np.isfinite(r["T"]).all()
+
+
+def test_results_are_run_to_run_reproducible():
+    """Fixed summation orders everywhere (per-warp partials, last-block reductions): two solves of the same batch give the same
+    bytes, also when the batch is processed next to other pairs."""
+    from geoflowslam_b200 import RegistrationGICP
+    pairs = [synth.gicp_pair(2070 + i, n_target=9000) for i in range(3)]
+    tg, nt = _pack([p[0] for p in pairs]); sr, ns = _pack([p[1] for p in pairs])
+    stride = max(tg.shape[1], sr.shape[1])
+    tg = np.pad(tg, ((0, 0), (0, stride - tg.shape[1]), (0, 0))); sr = np.pad(sr, ((0, 0), (0, stride - sr.shape[1]), (0, 0)))
+    T0 = np.tile(np.eye(4), (3, 1, 1))
+    reg = RegistrationGICP(max_points=stride, max_pairs=3)
+    a = reg.align_batch(tg, nt, sr, ns, T0).tobytes()
+    b = reg.align_batch(tg, nt, sr, ns, T0).tobytes()
+    assert a == b
+    one = RegistrationGICP(max_points=stride, max_pairs=1)
+    c = one.align_batch(tg[1:2], nt[1:2], sr[1:2], ns[1:2], T0[1:2]).tobytes()
+    assert c == reg.align_batch(tg, nt, sr, ns, T0)[1:2].tobytes()
