@@ -1,5 +1,6 @@
 """CPU-only checks of host-side logic that ships in libgfs_b200 (no compute kernels are called)."""
 import ctypes as C
+import json
 import re
 import os
 
@@ -87,3 +88,21 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in src and "from oracle" not in src and "libgfs_oracle" not in src, f
+
+
+def test_bench_reference_arm_runs_the_whole_step_on_the_cpu():
+    """bench.py's CPU arm (cpu_baseline / --impl reference) for the headline workload: data of the named shapes, every stage
+    of the step timed per frame, a positive rate.  One sequence, one worker: a few seconds."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    data = bench.make_track_data(1, 1000, 1)
+    assert data["gray"].shape == (bench.RING, 1, 480, 640) and data["depth"].shape == (bench.RING, 1, 480, 640)
+    assert data["depth"].dtype == np.uint16 and data["imu"].shape == (bench.RING, 1, 7, 7)
+    n_valid = int((data["depth"][0, 0, ::2, ::2] > 0).sum())
+    assert 45000 < n_valid < 55000                                   # configs[2]: ~50k-point clouds at stride 2
+    fps, dt, stage = bench.cpu_track_frames_per_sec(data, 1, 1)
+    assert fps > 0 and set(stage) == {"orb_match", "klt", "imu_pose_inertial", "depth_cloud_gicp", "local_inertial_ba"}
+    assert stage["depth_cloud_gicp"] > stage["imu_pose_inertial"] > 0
+    assert bench.TRACK_METRIC == json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
