@@ -1316,7 +1316,10 @@ def run_track(args):
                        "note": "map-dependent inputs (pose-optimiser observations, BA window) are synthetic problems of the named shapes; tests/test_gpu_closed_loop.py chains the stages causally"},
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "gicp_converged_fraction": float(gicp_res["converged"].mean())},
+                    "gicp_converged_fraction": float(gicp_res["converged"].mean()),
+                    "note": "every step: gray + 16-bit depth + IMU rows from pinned host memory (double-buffered on a copy stream: the copy of "
+                            "frame s + 1 overlaps the kernels of frame s), pose / BA problems through the host-pointer C ABI, all results copied to "
+                            "pinned host memory and the stream synchronised before the step returns"},
             "gpu_launches": args.steps * launches}
     print(json.dumps(line))
     if world > 1:
