@@ -25,6 +25,8 @@
 
 #include <dlfcn.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "inertial.cuh"
 
@@ -1206,9 +1208,8 @@ struct Api {
 };
 static Api* api() {
   static Api a;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
     // the copy the process already has (torch's bundled NCCL), else the system one
     void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
     if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
@@ -1223,7 +1224,7 @@ static Api* api() {
       a.groupEnd = (GroupFn)dlsym(lib, "ncclGroupEnd");
       a.errStr = (ErrStrFn)dlsym(lib, "ncclGetErrorString");
     }
-  }
+  });
   return (a.lib && a.getUniqueId && a.commInitRank && a.commDestroy && a.allReduce && a.groupStart && a.groupEnd) ? &a : nullptr;
 }
 }  // namespace ncclrt
