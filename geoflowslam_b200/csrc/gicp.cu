@@ -60,6 +60,8 @@ struct GicpDev {
   uint4* tab;                // [clouds][hsize] kNN grid slot {key lo, key hi, start, count}: one 16-byte probe
   double* rec;               // [clouds][nmax][4] downsampled points in cell order {x, y, z, index bits}
   float4* recf;              // [clouds][nmax] the same records as float32 RELATIVE TO THEIR CELL's origin {x, y, z, index bits}
+  int* nbr;                  // [clouds][nmax][10] the 10 nearest points of every point (itself first), in (distance, index) order
+  double* nbrR2;             // [clouds][nmax] squared distance to the 10th of them (< 0: fewer than 10 found -- no certificate)
   int* knnList;              // [clouds][nmax][16] candidates k_knn_cov_warp hands to k_knn_select_cov
   unsigned char* knnCnt;     // [clouds][nmax] their number (0: the query went to the hand-over list instead)
   uint2* oct;                // [clouds][hsize] per occupied cell: its records are sorted by octant (bit 0 / 1 / 2 = upper half in
@@ -793,6 +795,14 @@ __device__ void cov_from_knn(const Grid& g, const KnnAcc<KNN_K>& acc, double* ou
   out[0] = R[0][0]; out[1] = R[0][1]; out[2] = R[0][2]; out[3] = R[1][1]; out[4] = R[1][2]; out[5] = R[2][2];
 }
 
+// the neighbour list itself is kept too: k_nn_corr3 searches a query's new correspondence among the neighbours of its old one
+__device__ __forceinline__ void store_knn(const GicpDev& D, int c, int i, const KnnAcc<KNN_K>& acc) {
+  int* o = D.nbr + ((size_t)c * D.nmax + i) * KNN_K;
+#pragma unroll
+  for (int k = 0; k < KNN_K; k++) o[k] = acc.id[k];
+  D.nbrR2[(size_t)c * D.nmax + i] = acc.found == KNN_K ? acc.d[KNN_K - 1] : -1.0;
+}
+
 // estimate_local_features<CovarianceSetter>, one thread per query (shell search around the query).
 // use_list = 0: every point of the cloud; use_list = 1: only the queries k_knn_cov_cells handed over
 // (slotOf[] holds their point indices, nFall[] their number).
@@ -836,7 +846,10 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_cov(GicpDev D, int use_l
       warp_brute_knn<KNN_K>(g.pts, nPts, __shfl_sync(0xffffffffu, qx, src), __shfl_sync(0xffffffffu, qy, src),
                             __shfl_sync(0xffffffffu, qz, src), src, acc);
     }
-    if (active) cov_from_knn(g, acc, D.cov + ((size_t)c * D.nmax + i) * 6);
+    if (active) {
+      cov_from_knn(g, acc, D.cov + ((size_t)c * D.nmax + i) * 6);
+      store_knn(D, c, i, acc);
+    }
   }
 }
 
@@ -977,6 +990,7 @@ __global__ void __launch_bounds__(KC_THREADS) k_knn_cov_cells(GicpDev D) {
         acc.push(I[j], __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz)), __dmul_rn(dy, dy)));
       }
       cov_from_knn(g, acc, D.cov + ((size_t)c * D.nmax + pidx) * 6);
+      store_knn(D, c, pidx, acc);
     }
   }
 }
@@ -1193,6 +1207,7 @@ __global__ void __launch_bounds__(128) k_knn_select_cov(GicpDev D) {
       if (4 * t4 + u < cnt) acc.push(id[u], sqdist3(g.pts + (size_t)id[u] * 4, qx, qy, qz));
   }
   cov_from_knn(g, acc, D.cov + ((size_t)c * D.nmax + i) * 6);
+  store_knn(D, c, i, acc);
 }
 
 // ---- block reduction of NV doubles per thread into out[NV] (fixed order: lanes, then warps)
@@ -1500,6 +1515,111 @@ __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr2(GicpDev D) {
     id = nn.id; d = nn.d;
   }
   D.corr[(size_t)p * D.nmax + i] = (id != 0x7fffffff && !(d > max_d2)) ? id : -1;  // DistanceRejector: sq_dist > max_dist_sq
+}
+
+// ---- correspondence search, third generation (GFS_GICP_NN=7, the default): look among the NEIGHBOURS of the old correspondence first.
+// k_knn_cov leaves, for every target point t, its 10 nearest points N(t) (t itself first) and r(t) = the distance to the 10th.  A
+// point outside N(t) is at least r(t) away from t, hence at least r(t) - |q - t| away from a query q.  So for a query whose previous
+// correspondence was t: scan the ten points of N(t); if the best of them is closer than r(t) - |q - t|, it IS the exact nearest
+// target point (ties can only occur inside N(t), where the (distance, index) order decides as everywhere else).  That is eleven
+// independent 32-byte gathers and no hash probe, no cell walk, no data-dependent loop: the lanes of a warp stay together (the ball
+// walk runs at 13 active lanes).  Queries without a certificate -- first round, no previous correspondence, large residuals, a big
+// step of the optimiser -- are COMPACTED inside the block and searched with the ball walk by the first lanes of the block, so
+// the slow path is executed by full warps and only as many of them as needed.  The result is the exact search's, bit for bit.
+__device__ __forceinline__ void nn1_ball_search(const GicpDev& D, const Grid& g, const int* box, const double q[3], int prev, double cap,
+                                                int& id, double& d) {
+  const ShellQuery sq = make_shell_query(D.cell, q[0], q[1], q[2]);
+  Nn1 nn;
+  nn.d = DBL_MAX; nn.id = 0x7fffffff;
+  if (prev >= 0) nn.push(prev, sqdist3(g.pts + (size_t)prev * 4, q[0], q[1], q[2]));
+  visit_ball<true>(g, box, sq, [&]() { return fmin(nn.d, cap); },
+                   [&](int cs_, int cn_, int, int, int, int) { scan_cell_nn1(g, cs_, cn_, q[0], q[1], q[2], nn); });
+  id = nn.id; d = nn.d;
+}
+
+__global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr3(GicpDev D) {
+  __shared__ double s_q[NN_THREADS][3];
+  __shared__ int s_i[NN_THREADS], s_prev[NN_THREADS], s_list[NN_THREADS];
+  __shared__ int s_wcnt[NN_THREADS / 32], s_total;
+  const int p = blockIdx.y;
+  if (!D.istate[p * LM_ISTATE + I_ACTIVE] || D.istate[p * LM_ISTATE + I_NEED]) return;
+  const int iter = D.istate[p * LM_ISTATE + I_OUTER];
+  const int ct = tgt_cloud(D, p), cs = src_cloud(D, p);
+  const int ns = D.nDown[cs];
+  if ((int)(blockIdx.x * NN_THREADS) >= ns) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t = blockIdx.x * NN_THREADS + tid;
+  const bool valid = t < ns;
+  const double* T = D.state + (size_t)p * LM_STATE + S_T;
+  const Grid g = make_grid(D, ct);
+  const double max_d2 = D.max_dist * D.max_dist;
+  const double cap = max_d2 * 1.0000001;
+  int i = 0, prev = -1;
+  double q[3] = {0, 0, 0};
+  bool need = false;
+  if (valid) {
+    double ps[3];
+    i = t;
+    if (D.cellOrder) {
+      const double2* rs = reinterpret_cast<const double2*>(D.rec + ((size_t)cs * D.nmax + t) * 4);
+      const double2 a = __ldg(&rs[0]), b = __ldg(&rs[1]);
+      ps[0] = a.x; ps[1] = a.y; ps[2] = b.x;
+      i = (int)__double_as_longlong(b.y);
+    } else {
+      const double* pp = D.pts + ((size_t)cs * D.nmax + t) * 4;
+      ps[0] = pp[0]; ps[1] = pp[1]; ps[2] = pp[2];
+    }
+    xform(T, ps, q);
+    prev = iter > 0 ? D.corr[(size_t)p * D.nmax + i] : -1;
+    need = true;
+    if (prev >= 0) {
+      const double r2 = __ldg(&D.nbrR2[(size_t)ct * D.nmax + prev]);
+      if (r2 >= 0.0) {
+        const int2* nb = reinterpret_cast<const int2*>(D.nbr + ((size_t)ct * D.nmax + prev) * KNN_K);
+        int ids[KNN_K];
+#pragma unroll
+        for (int k = 0; k < KNN_K / 2; k++) { const int2 v = __ldg(&nb[k]); ids[2 * k] = v.x; ids[2 * k + 1] = v.y; }
+        Nn1 nn;
+        nn.d = DBL_MAX; nn.id = 0x7fffffff;
+        double dprev2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < KNN_K; k++) {
+          const double dd = sqdist3(g.pts + (size_t)ids[k] * 4, q[0], q[1], q[2]);
+          if (ids[k] == prev) dprev2 = dd;
+          nn.push(ids[k], dd);
+        }
+        // prev heads its own list unless other points coincide with it exactly; should it be missing from the list altogether
+        // (ten coincident points: r = 0, no certificate anyway) its distance is measured directly
+        if (ids[0] != prev && dprev2 == 0.0) dprev2 = sqdist3(g.pts + (size_t)prev * 4, q[0], q[1], q[2]);
+        const double bound = sqrt(r2) * (1.0 - 1e-9) - 1e-12 - sqrt(dprev2) * (1.0 + 1e-9);
+        if (bound > 0.0 && sqrt(nn.d) * (1.0 + 1e-9) < bound) {
+          D.corr[(size_t)p * D.nmax + i] = !(nn.d > max_d2) ? nn.id : -1;  // DistanceRejector: sq_dist > max_dist_sq
+          need = false;
+        }
+      }
+    }
+  }
+  // ---- compact the queries that still need the full search: ballot + per-warp offsets
+  const unsigned m = __ballot_sync(0xffffffffu, need);
+  if (lane == 0) s_wcnt[warp] = __popc(m);
+  if (need) { s_q[tid][0] = q[0]; s_q[tid][1] = q[1]; s_q[tid][2] = q[2]; s_i[tid] = i; s_prev[tid] = prev; }
+  __syncthreads();
+  if (tid == 0) {
+    int a = 0;
+    for (int w = 0; w < NN_THREADS / 32; w++) { const int c = s_wcnt[w]; s_wcnt[w] = a; a += c; }
+    s_total = a;
+  }
+  __syncthreads();
+  if (need) s_list[s_wcnt[warp] + __popc(m & ((1u << lane) - 1u))] = tid;
+  __syncthreads();
+  const int total = s_total;
+  if (tid >= total) return;
+  const int src = s_list[tid];
+  const double qq[3] = {s_q[src][0], s_q[src][1], s_q[src][2]};
+  int id;
+  double d;
+  nn1_ball_search(D, g, D.cellBox + ct * 6, qq, s_prev[src], cap, id, d);
+  D.corr[(size_t)p * D.nmax + s_i[src]] = (id != 0x7fffffff && !(d > max_d2)) ? id : -1;
 }
 
 __device__ void lm_begin_block(const GicpDev& D, int p);   // defined below (need lm_trial)
@@ -1854,14 +1974,15 @@ using namespace gfs;
 struct GfsGicp {
   GicpDev dev;
   int maxPairs = 0;
-  DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_nFall, b_box, b_pts, b_cov, b_tab, b_rec, b_recf, b_oct, b_knnList, b_knnCnt,
+  DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_nFall, b_box, b_pts, b_cov, b_tab, b_rec, b_recf, b_oct, b_knnList, b_knnCnt, b_nbr, b_nbrR2,
       b_corr, b_maha, b_partial, b_partialE, b_state, b_istate, b_counters, b_tickets;
   DevBuf b_tgt, b_src, b_n, b_T0, b_res;
   PinnedBuf h_counters;
   int launches = 0;
   bool cellKnn = false;  // GFS_GICP_KNN_CELLS=1: cell-centric 10-NN kernel first (same results)
-  int nnMode = 5;        // GFS_GICP_NN: 0 = k_nn_corr (shell walk), 1 = k_nn_corr2 (ball walk, fp64), 2 = + float32 prefilter, 3 = ball walk over octants
-                         // (fp64), 4 = octants + float32 prefilter, 5 = ball walk with the seven-cell fast path (fp64; default), 6 = 5 + float32 prefilter
+  int nnMode = 7;        // GFS_GICP_NN: 0 = k_nn_corr (shell walk), 1 = k_nn_corr2 (ball walk, fp64), 2 = + float32 prefilter, 3 = ball walk over octants
+                         // (fp64), 4 = octants + float32 prefilter, 5 = ball walk with the seven-cell fast path (fp64), 6 = 5 + float32 prefilter, 7 = neighbours of the old correspondence first,
+                         // certified by the 10-NN radius, ball walk for the compacted rest (default)
   int knnMode = 0;       // GFS_GICP_KNN: 0 = k_knn_cov (thread per query; default, measured fastest), 1 = k_knn_cov_warp (warp per cell, octant
                          // skipping) + k_knn_cov for what it hands over
   int trackCalls = 0;    // gfs_gicp_track_*: calls since the last reset (the new cloud goes to slot trackCalls & 1)
@@ -1993,6 +2114,8 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   RES(b_rec, C * N * 32, rec, double*)
   RES(b_recf, C * N * 16, recf, float4*)
   RES(b_oct, C * H * 8, oct, uint2*)
+  RES(b_nbr, C * N * 40, nbr, int*)
+  RES(b_nbrR2, C * N * 8, nbrR2, double*)
   RES(b_knnList, C * N * 64, knnList, int*)
   RES(b_knnCnt, C * N, knnCnt, unsigned char*)
   RES(b_corr, P * N * 4, corr, int*)
@@ -2012,7 +2135,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
 int gfs_gicp_destroy(GfsGicp* h) {
   if (!h) return GFS_OK;
   DevBuf* d[] = {&h->b_keys, &h->b_minIdx, &h->b_count, &h->b_start, &h->b_cursor, &h->b_rank, &h->b_slotOf, &h->b_members,
-                 &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_nFall, &h->b_box, &h->b_pts, &h->b_cov, &h->b_tab, &h->b_rec, &h->b_recf, &h->b_oct, &h->b_knnList, &h->b_knnCnt, &h->b_corr, &h->b_maha, &h->b_partial,
+                 &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_nFall, &h->b_box, &h->b_pts, &h->b_cov, &h->b_tab, &h->b_rec, &h->b_recf, &h->b_oct, &h->b_knnList, &h->b_knnCnt, &h->b_nbr, &h->b_nbrR2, &h->b_corr, &h->b_maha, &h->b_partial,
                  &h->b_partialE, &h->b_state, &h->b_istate, &h->b_counters, &h->b_tickets, &h->b_tgt, &h->b_src, &h->b_n, &h->b_T0, &h->b_res};
   for (DevBuf* b : d) b->release();
   h->h_counters.release();
@@ -2104,7 +2227,8 @@ static int optimize_pairs(GfsGicp* h, const GicpDev& D, cudaStream_t st, int pai
     else if (h->nnMode == 3) k_nn_corr2<false, true, false><<<gn, NN_THREADS, 0, st>>>(D);
     else if (h->nnMode == 4) k_nn_corr2<true, true, false><<<gn, NN_THREADS, 0, st>>>(D);
     else if (h->nnMode == 5) k_nn_corr2<false, false, true><<<gn, NN_THREADS, 0, st>>>(D);
-    else k_nn_corr2<true, false, true><<<gn, NN_THREADS, 0, st>>>(D);
+    else if (h->nnMode == 6) k_nn_corr2<true, false, true><<<gn, NN_THREADS, 0, st>>>(D);
+    else k_nn_corr3<<<gn, NN_THREADS, 0, st>>>(D);
     prof_mark(h, st, ST_NN);
     k_linearize<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D);   // + the pair's LM begin in its last block
     prof_mark(h, st, ST_LIN);

@@ -106,7 +106,7 @@ def test_search_variants_are_bit_identical(monkeypatch):
     tg = np.pad(tg, ((0, 0), (0, stride - tg.shape[1]), (0, 0))); sr = np.pad(sr, ((0, 0), (0, stride - sr.shape[1]), (0, 0)))
     T0 = np.tile(np.eye(4), (3, 1, 1))
     out = {}
-    variants = ((0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 2, 0), (0, 2, 0), (1, 3, 1), (1, 4, 1), (0, 3, 1), (1, 1, 1), (1, 5, 0), (1, 6, 0), (0, 5, 1))
+    variants = ((0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 2, 0), (0, 2, 0), (1, 3, 1), (1, 4, 1), (0, 3, 1), (1, 1, 1), (1, 5, 0), (1, 6, 0), (0, 5, 1), (1, 7, 0), (0, 7, 0), (1, 7, 1))
     for order, nn, knn in variants:
         monkeypatch.setenv("GFS_GICP_ORDER", str(order)); monkeypatch.setenv("GFS_GICP_NN", str(nn)); monkeypatch.setenv("GFS_GICP_KNN", str(knn))
         reg = RegistrationGICP(max_points=stride, max_pairs=3)
