@@ -60,7 +60,6 @@ struct GicpDev {
   uint4* tab;                // [clouds][hsize] kNN grid slot {key lo, key hi, start, count}: one 16-byte probe
   double* rec;               // [clouds][nmax][4] downsampled points in cell order {x, y, z, index bits}
   float4* recf;              // [clouds][nmax] the same records as float32 RELATIVE TO THEIR CELL's origin {x, y, z, index bits}
-  float* lb;                 // [pairs][nmax] source points WITHOUT a correspondence: lower bound of the distance to the nearest target point
   int* nbr;                  // [clouds][nmax][10] the 10 nearest points of every point (itself first), in (distance, index) order
   double* nbrR2;             // [clouds][nmax] squared distance to the 10th of them (< 0: fewer than 10 found -- no certificate)
   int* knnList;              // [clouds][nmax][16] candidates k_knn_cov_warp hands to k_knn_select_cov
@@ -81,7 +80,7 @@ struct GicpDev {
 };
 
 // per-pair LM state layout (doubles)
-enum { S_T = 0, S_NEWT = 12, S_H = 24, S_B = 45, S_E = 51, S_LAMBDA = 52, S_DELTA = 53, S_TSEARCH = 60, LM_STATE = 72 };  // S_TSEARCH: the T of the pair's last correspondence search
+enum { S_T = 0, S_NEWT = 12, S_H = 24, S_B = 45, S_E = 51, S_LAMBDA = 52, S_DELTA = 53, LM_STATE = 60 };
 // per-pair LM state layout (ints)
 enum { I_ACTIVE = 0, I_NEED = 1, I_CONV = 2, I_ITER = 3, I_TRIAL = 4, I_INL = 5, I_INNER = 6, I_SUCCESS = 7, I_OUTER = 8, LM_ISTATE = 12 };
 // Every pair walks its own LM state machine (optimizer.hpp:97-141) through the launches the host enqueues in "rounds" of
@@ -1538,27 +1537,6 @@ __device__ __forceinline__ void nn1_ball_search(const GicpDev& D, const Grid& g,
   id = nn.id; d = nn.d;
 }
 
-// Queries WITHOUT a correspondence (a quarter of all query-rounds on the bench clouds: the parts of a view the other view does not
-// see) were the most expensive ones -- a ball of the full correspondence radius reaches nearly all 27 cells.  For them lb[] keeps a
-// lower bound of the distance to the nearest target point: the block search below scans the whole 3x3x3 block once (every point
-// within the radius lies in it because cell >= 1.05 radius) and records min(nearest point found, distance to the block's boundary);
-// afterwards the bound shrinks by the query's movement per round (|T q - T_search q|), and as long as it stays above the radius the
-// query still has no correspondence -- no search at all.
-__device__ __forceinline__ void nn1_block_search(const GicpDev& D, const Grid& g, const double q[3], int& id, double& d, double& lbound) {
-  const ShellQuery sq = make_shell_query(D.cell, q[0], q[1], q[2]);
-  Nn1 nn;
-  nn.d = DBL_MAX; nn.id = 0x7fffffff;
-  for (int dz = -1; dz <= 1; dz++)
-    for (int dy = -1; dy <= 1; dy++)
-      for (int dx = -1; dx <= 1; dx++) {
-        int cs_, cn_;
-        if (grid_find(g, sq.cx + dx, sq.cy + dy, sq.cz + dz, cs_, cn_)) scan_cell_nn1(g, cs_, cn_, q[0], q[1], q[2], nn);
-      }
-  id = nn.id; d = nn.d;
-  const double outside = D.cell + sq.margin;  // every point outside the block is farther than this (margin is already shrunk)
-  lbound = fmin(nn.id != 0x7fffffff ? sqrt(nn.d) : DBL_MAX, outside) * (1.0 - 1e-9);
-}
-
 __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr3(GicpDev D) {
   __shared__ double s_q[NN_THREADS][3];
   __shared__ int s_i[NN_THREADS], s_prev[NN_THREADS], s_list[NN_THREADS];
@@ -1576,9 +1554,7 @@ __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr3(GicpDev D) {
   const Grid g = make_grid(D, ct);
   const double max_d2 = D.max_dist * D.max_dist;
   const double cap = max_d2 * 1.0000001;
-  const bool useLb = D.cell >= 1.05 * D.max_dist;  // the 3x3x3 block then holds every point within the radius
-  float* lb = D.lb + (size_t)p * D.nmax;
-  int i = 0, prev = -1;   // prev: >= 0 old correspondence, -1 none (ball search), -2 none (block search)
+  int i = 0, prev = -1;
   double q[3] = {0, 0, 0};
   bool need = false;
   if (valid) {
@@ -1617,24 +1593,13 @@ __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr3(GicpDev D) {
         if (ids[0] != prev && dprev2 == 0.0) dprev2 = sqdist3(g.pts + (size_t)prev * 4, q[0], q[1], q[2]);
         const double bound = sqrt(r2) * (1.0 - 1e-9) - 1e-12 - sqrt(dprev2) * (1.0 + 1e-9);
         if (bound > 0.0 && sqrt(nn.d) * (1.0 + 1e-9) < bound) {
-          const bool rejected = nn.d > max_d2;  // DistanceRejector: sq_dist > max_dist_sq
-          D.corr[(size_t)p * D.nmax + i] = rejected ? -1 : nn.id;
-          if (rejected) lb[i] = __double2float_rd(sqrt(nn.d) * (1.0 - 1e-9));  // the exact nearest point is that far
+          D.corr[(size_t)p * D.nmax + i] = !(nn.d > max_d2) ? nn.id : -1;  // DistanceRejector: sq_dist > max_dist_sq
           need = false;
         }
       }
-    } else if (iter > 0 && useLb) {
-      // no correspondence last round: has the query moved far enough to possibly have one now?
-      const double* Ts = D.state + (size_t)p * LM_STATE + S_TSEARCH;
-      double qo[3];
-      xform(Ts, ps, qo);
-      const double mv = sqrt((q[0] - qo[0]) * (q[0] - qo[0]) + (q[1] - qo[1]) * (q[1] - qo[1]) + (q[2] - qo[2]) * (q[2] - qo[2]));
-      const float lbn = __double2float_rd((double)lb[i] - mv * (1.0 + 1e-9) - 1e-12);
-      if ((double)lbn > D.max_dist * (1.0 + 1e-9)) { lb[i] = lbn; need = false; }  // corr stays -1
-      else prev = -2;
     }
   }
-  // ---- compact the queries that still need a search: ballot + per-warp offsets
+  // ---- compact the queries that still need the full search: ballot + per-warp offsets
   const unsigned m = __ballot_sync(0xffffffffu, need);
   if (lane == 0) s_wcnt[warp] = __popc(m);
   if (need) { s_q[tid][0] = q[0]; s_q[tid][1] = q[1]; s_q[tid][2] = q[2]; s_i[tid] = i; s_prev[tid] = prev; }
@@ -1651,21 +1616,10 @@ __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr3(GicpDev D) {
   if (tid >= total) return;
   const int src = s_list[tid];
   const double qq[3] = {s_q[src][0], s_q[src][1], s_q[src][2]};
-  const int pv = s_prev[src], si = s_i[src];
   int id;
   double d;
-  if (pv == -2) {
-    double lbound;
-    nn1_block_search(D, g, qq, id, d, lbound);
-    const bool found = id != 0x7fffffff && !(d > max_d2);
-    D.corr[(size_t)p * D.nmax + si] = found ? id : -1;
-    if (!found) lb[si] = __double2float_rd(lbound);
-  } else {
-    nn1_ball_search(D, g, D.cellBox + ct * 6, qq, pv, cap, id, d);
-    const bool found = id != 0x7fffffff && !(d > max_d2);
-    D.corr[(size_t)p * D.nmax + si] = found ? id : -1;
-    if (!found) lb[si] = 0.f;  // nothing known beyond "farther than the radius": the next round runs the block search
-  }
+  nn1_ball_search(D, g, D.cellBox + ct * 6, qq, s_prev[src], cap, id, d);
+  D.corr[(size_t)p * D.nmax + s_i[src]] = (id != 0x7fffffff && !(d > max_d2)) ? id : -1;
 }
 
 __device__ void lm_begin_block(const GicpDev& D, int p);   // defined below (need lm_trial)
@@ -1926,7 +1880,6 @@ __device__ void lm_begin_block(const GicpDev& D, int p) {
     is[I_ITER] = iter;
     is[I_TRIAL] = 0;
     is[I_SUCCESS] = 0;
-    for (int k = 0; k < 12; k++) st[S_TSEARCH + k] = st[S_T + k];  // what this round's correspondence search used (k_nn_corr3's movement bound)
     lm_trial(st);
     __threadfence();
     is[I_NEED] = 1;
@@ -2021,7 +1974,7 @@ using namespace gfs;
 struct GfsGicp {
   GicpDev dev;
   int maxPairs = 0;
-  DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_nFall, b_box, b_pts, b_cov, b_tab, b_rec, b_recf, b_oct, b_knnList, b_knnCnt, b_nbr, b_nbrR2, b_lb,
+  DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_nFall, b_box, b_pts, b_cov, b_tab, b_rec, b_recf, b_oct, b_knnList, b_knnCnt, b_nbr, b_nbrR2,
       b_corr, b_maha, b_partial, b_partialE, b_state, b_istate, b_counters, b_tickets;
   DevBuf b_tgt, b_src, b_n, b_T0, b_res;
   PinnedBuf h_counters;
@@ -2161,7 +2114,6 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   RES(b_rec, C * N * 32, rec, double*)
   RES(b_recf, C * N * 16, recf, float4*)
   RES(b_oct, C * H * 8, oct, uint2*)
-  RES(b_lb, P * N * 4, lb, float*)
   RES(b_nbr, C * N * 40, nbr, int*)
   RES(b_nbrR2, C * N * 8, nbrR2, double*)
   RES(b_knnList, C * N * 64, knnList, int*)
@@ -2183,7 +2135,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
 int gfs_gicp_destroy(GfsGicp* h) {
   if (!h) return GFS_OK;
   DevBuf* d[] = {&h->b_keys, &h->b_minIdx, &h->b_count, &h->b_start, &h->b_cursor, &h->b_rank, &h->b_slotOf, &h->b_members,
-                 &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_nFall, &h->b_box, &h->b_pts, &h->b_cov, &h->b_tab, &h->b_rec, &h->b_recf, &h->b_oct, &h->b_knnList, &h->b_knnCnt, &h->b_nbr, &h->b_nbrR2, &h->b_lb, &h->b_corr, &h->b_maha, &h->b_partial,
+                 &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_nFall, &h->b_box, &h->b_pts, &h->b_cov, &h->b_tab, &h->b_rec, &h->b_recf, &h->b_oct, &h->b_knnList, &h->b_knnCnt, &h->b_nbr, &h->b_nbrR2, &h->b_corr, &h->b_maha, &h->b_partial,
                  &h->b_partialE, &h->b_state, &h->b_istate, &h->b_counters, &h->b_tickets, &h->b_tgt, &h->b_src, &h->b_n, &h->b_T0, &h->b_res};
   for (DevBuf* b : d) b->release();
   h->h_counters.release();
