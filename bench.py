@@ -853,7 +853,7 @@ def run_track_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_seq = 2 * max(cores, 8)        # two sequences per core and step: RING frames each, ~3 s of wall per step
+    n_seq = 4 * max(cores, 8)        # four sequences per core and step (RING frames each, ~5 s of wall): enough to amortise the longest sequence
     data = make_track_data(min(n_seq, 16), 1000, min(cores, 16))
     for _ in range(min(args.warmup, 1)):
         cpu_track_frames_per_sec(data, cores, max(cores // 2, 1))
@@ -1276,7 +1276,9 @@ def run_track(args):
 
     cpu = None
     if world == 1 and not args.no_cpu:
-        n_seq = 3 * max(cores, 8)      # ~4 s of wall, ~60 core-seconds: one sequence per core was a +-8 % sample
+        # four sequences per core: with one per core the wall time was the longest sequence's (a GICP pair that runs all 20 iterations),
+        # which understated the CPU arm by 10-15 % (43-47 frames/s at 1 per core, 54 at 3 per core on the same 16-core box)
+        n_seq = 4 * max(cores, 8)
         fps, dt, core_s = cpu_track_frames_per_sec(data, cores, n_seq)
         cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": "%d sequences x %d frames on %d worker threads in %.1f s wall (measured, not extrapolated); core-seconds per frame by stage: %s"
