@@ -1262,950 +1262,6 @@ def run_track(args):
     achieved = alg[top] / (per_launch_ms / 1e3) / 1e9
     traffic_per_query = {"knn_cov": (485.131520e6 + 273.671168e6) / (128 * 42100.0),      # profiles/r02_s1_gicp_knn_cov_after_ncu_details.txt
                          "nn_corr": (126.514944e6 + 4.716544e6) / (64 * 40020.0)}        # profiles/r02_s24_gicp_nn_corr3_ncu_details.txt (64 pairs)
-    roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "stages": stage_roof,
-            "frac": achieved / peak, "traffic": traffic, "traffic_source": ncu_traffic_src.get(top) if traffic else None,
-            "algorithmic_bytes": alg, "ms_per_launch_group": prof[top], "peak_source": peak_src,
-            "stage_ms": prof,
-            "note": "every ORB stage is bound by issue slots (ncu: 63-85 % busy), not DRAM (3-13 % of peak); "
-                    "DRAM traffic equals the algorithmic minimum (profiles/r01_summary.md)"}
-
-    cpu = None
-    if world == 1 and not args.no_cpu:
-        # bounded sample: a short probe sizes it to about 8 s of wall on all host cores (capped by the batch)
-        fps0, _ = cpu_frames_per_sec(frames[:min(B, max(2 * cores, 32))], cores)
-        ns = int(min(B, max(2 * cores, 32, fps0 * 8.0)))
-        fps, dt = cpu_frames_per_sec(frames[:ns], cores)
-        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": "first %d frames + %d pairs of the same batch, %.1f s wall, %d worker threads" % (ns, ns - 1, dt, cores)}
-
-    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1]: ORB(1000 feats, 1.2, 8 levels, FAST 25/7) + BF-Hamming + GMS i->i+1",
-                       "frames_per_gpu": B, "width": W, "height": H, "mean_keypoints": mean_kp, "mean_fast_candidates": cand_per_frame,
-                       "l2": "inputs larger than L2 (%.0f MB of frames per step)" % (frames.nbytes / 1e6),
-                       "parallelism": "frames sharded across ranks, no data-path collective"},
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps * fe.launches_per_call(B)}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-
-
-# ------------------------------------------------------------------------------------------------
-# Secondary workloads (BASELINE configs[2] GICP and configs[3] LocalInertialBA); same JSON contract
-# ------------------------------------------------------------------------------------------------
-def _clock_block(fn, local):
-    import torch
-    s = ClockSampler(local)
-    s.start()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1), s.stop()
-
-
-def run_gicp(args):
-    import torch
-    from concurrent.futures import ThreadPoolExecutor
-    from geoflowslam_b200 import RegistrationGICP, synth
-    from geoflowslam_b200.gicp import RESULT_DTYPE
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    P = args.batch if args.batch != 1024 else 512
-    uniq = min(P, 32)  # distinct synthetic pairs; the batch tiles them (every pair is solved independently)
-    with ThreadPoolExecutor(min(16, os.cpu_count() or 1)) as ex:
-        pairs = list(ex.map(lambda i: synth.gicp_pair(2000 + i, n_target=50000), range(uniq)))
-    stride = max(max(len(t), len(s)) for t, s, _ in pairs)
-    tg = np.zeros((P, stride, 4), np.float32); sr = np.zeros((P, stride, 4), np.float32)
-    nt = np.zeros(P, np.int32); ns = np.zeros(P, np.int32)
-    for i in range(P):
-        t, s_, _ = pairs[i % uniq]
-        tg[i, :len(t)] = t; sr[i, :len(s_)] = s_; nt[i] = len(t); ns[i] = len(s_)
-    T0 = np.tile(np.eye(4), (P, 1, 1))
-    reg = RegistrationGICP(max_points=stride, max_pairs=P)
-    dev = torch.device("cuda", local)
-    d_tg, d_sr = torch.from_numpy(tg).to(dev), torch.from_numpy(sr).to(dev)
-    d_nt, d_ns, d_T0 = torch.from_numpy(nt).to(dev), torch.from_numpy(ns).to(dev), torch.from_numpy(T0).to(dev)
-    d_out = torch.zeros(P * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
-    if args.gicp_track:
-        # tracking mode: every step brings ONE new cloud per sequence (alternately the pair's source and target cloud) and
-        # registers it against the previous step's, which is already preprocessed and resident
-        calls = [0]
-        reg.track_batch_device(d_tg, d_nt, P, stride, None, None, stream=stream)
-
-        def step():
-            calls[0] += 1
-            new, n = (d_sr, d_ns) if calls[0] & 1 else (d_tg, d_nt)
-            reg.track_batch_device(new, n, P, stride, d_T0, d_out, stream=stream)
-    else:
-        step = lambda: reg.align_batch_device(d_tg, d_nt, d_sr, d_ns, P, stride, d_T0, d_out, stream=stream)
-    for _ in range(max(args.warmup, 1)):
-        step()
-    ms, clocks = _clock_block(lambda: [step() for _ in range(args.steps)], local)
-    ms /= args.steps
-    res = d_out.cpu().numpy().view(RESULT_DTYPE)
-    M_t, M_s = float(res["n_target"].mean()), float(res["n_source"].mean())
-    I, J = float(res["iterations"].mean() + 1), float(res["inner_evals"].mean())
-    alg = P * (16 * (nt.mean() + ns.mean()) + 400 * (M_t + M_s) + M_s * (160 * I + 112 * J))  # SURVEY 8d A_gicp
-    t0 = time.perf_counter(); res_h = reg.align_batch(tg, nt, sr, ns, T0); e2e_s = time.perf_counter() - t0
-    if not args.gicp_track:
-        assert np.array_equal(res_h["iterations"], res["iterations"])
-    nsamp = min(uniq, 8)
-    cpu_s = float("nan")
-    if not args.no_cpu:
-        from oracle import oracle as O
-        t0 = time.perf_counter()
-        with ThreadPoolExecutor(max(1, (os.cpu_count() or 4) // 4)) as ex:  # 4 OpenMP threads per pair, as the reference
-            list(ex.map(lambda i: O.gicp_align(pairs[i][0], pairs[i][1], threads=4), range(nsamp)))
-        cpu_s = time.perf_counter() - t0
-    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    line = {"metric": "cloud pairs/sec GICP 50k-pt RGB-D pairs (BASELINE configs[2])", "value": P / (ms / 1e3), "unit": "pairs/s",
-            "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[2]: RegistrationGICP voxel 0.02, max dist 0.1, k=10, <=20 LM iterations" +
-                                   (" -- tracking mode: one new cloud per sequence and step, registered against the resident previous one" if args.gicp_track else ""),
-                       "variant": {k: os.environ.get(k) for k in ("GFS_GICP_ORDER", "GFS_GICP_NN", "GFS_GICP_CELL", "GFS_GICP_KNN_CELLS") if os.environ.get(k)},
-                       "pairs": P, "distinct_pairs": uniq, "points_per_cloud": int(nt.mean()), "downsampled": [M_t, M_s],
-                       "outer_iterations": I, "inner_evals": J},
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "whole align call", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak,
-                         "unit": "GB/s", "frac": alg / (ms / 1e3) / 1e9 / peak, "traffic": None},
-            "cpu_baseline": {"value": nsamp / cpu_s, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
-                             "sample": "%d pairs, 4 threads per pair" % nsamp},
-            "e2e": {"value": P / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": int(tg.nbytes + sr.nbytes),
-                    "d2h_bytes_per_step": int(res_h.nbytes)},
-            "gpu_launches": args.steps * reg.last_launches()}
-    print(json.dumps(line))
-
-
-def run_ba(args, se3=False):
-    import torch
-    from geoflowslam_b200 import Optimizer, synth
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    B = args.batch if args.batch != 1024 else 256
-    uniq = min(B, 8)
-    if se3:  # Optimizer::LocalBundleAdjustment: 18 optimisable + 3 fixed keyframes, no inertial edges
-        probs = [synth.lba_problem(seed=7000 + i, n_kf=18, n_fixed=3, n_points=3000) for i in range(uniq)]
-    else:
-        probs = [synth.ba_problem(seed=3000 + i) for i in range(uniq)]
-    batch = [probs[i % uniq] for i in range(B)]
-    opt = Optimizer(max_kf=21, max_points=3000, max_obs=16384, max_inertial=20, max_batch=B)
-    stream = torch.cuda.current_stream().cuda_stream
-    opt.upload(batch, stream)
-    for _ in range(max(args.warmup, 1)):
-        opt.solve_uploaded(stream)
-    ms, clocks = _clock_block(lambda: [opt.solve_uploaded(stream) for _ in range(args.steps)], local)
-    ms /= args.steps
-    res = opt.download(stream)
-    t0 = time.perf_counter(); opt.LocalInertialBA_batch(batch, stream); e2e_s = time.perf_counter() - t0
-    one = Optimizer(max_kf=21, max_points=3000, max_obs=16384, max_inertial=20, max_batch=1)
-    one.upload(batch[:1], stream); one.solve_uploaded(stream)
-    ms1, _ = _clock_block(lambda: [one.solve_uploaded(stream) for _ in range(5)], local)
-    from oracle import oracle as O
-    t0 = time.perf_counter()
-    for p in probs[:4]:
-        O.ba_solve(p)
-    cpu_s = (time.perf_counter() - t0) / 4
-    trials = float(np.mean([r["lm_trials"] for r in res]))
-    alg = B * trials * 7.6e6  # A_ba ~ 7.6 MB per LM trial
-    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    line = {"metric": ("problems/sec LocalBundleAdjustment 18+3 KF x 3000 MP (SURVEY 8f rank 3)" if se3 else
-                       "problems/sec LocalInertialBA 20 KF x 3000 MP x 15k obs (BASELINE configs[3])"), "value": B / (ms / 1e3),
-            "unit": "problems/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": ("LocalBundleAdjustment: 18 optimisable + 3 fixed keyframes, 3000 points, VertexSE3Expmap, 10 LM iterations" if se3 else
-                                    "configs[3]: 20 KF, 3000 points, ~15k stereo/mono edges, 20 inertial edges, bLarge (4 its)"),
-                       "batch": B, "distinct_problems": uniq, "lm_trials": trials, "single_problem_ms": ms1 / 5},
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "whole solve", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak,
-                         "unit": "GB/s", "frac": alg / (ms / 1e3) / 1e9 / peak, "traffic": None},
-            "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "problems/s", "cores": 1, "kind": "port", "sample": "4 problems, 1 thread (g2o OpenMP is off)"},
-            "e2e": {"value": B / e2e_s, "unit": "problems/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None},
-            "gpu_launches": args.steps * opt.last_launches()}
-    print(json.dumps(line))
-
-
-def run_pose(args):
-    """SURVEY.md 8f rank 1: Optimizer::PoseOptimization, one problem per frame, batched."""
-    import torch
-    from geoflowslam_b200 import PoseOptimizer, synth
-    from geoflowslam_b200 import pose as pose_mod
-    import ctypes as C
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    B = args.batch
-    uniq = min(B, 64)
-    probs = [synth.pose_problem(seed=5000 + i, n_obs=400) for i in range(uniq)]
-    batch = [probs[i % uniq] for i in range(B)]
-    opt = PoseOptimizer(max_obs=512, max_batch=B)
-    # pack once: the timed call is the C-ABI entry point with host pointers (H2D + kernel + D2H)
-    Ps = (pose_mod.PoseProblem * B)()
-    Rs = (pose_mod.PoseResult * B)()
-    keep = [pose_mod.pack_problem(pr, Ps[i])[1] for i, pr in enumerate(batch)]
-    outs = [pose_mod.alloc_result(400, Rs[i])[1] for i in range(B)]
-    stream = torch.cuda.current_stream().cuda_stream
-    call = lambda: pose_mod.check(opt._L.gfs_pose_optimize_batch(opt._h, stream, Ps, B, Rs))
-    for _ in range(max(args.warmup, 3)):
-        call()
-    ms, clocks = _clock_block(lambda: [call() for _ in range(args.steps)], local)
-    ms /= args.steps
-    from oracle import oracle as O
-    t0 = time.perf_counter()
-    for p in probs[:32]:
-        O.pose_optimize(p)
-    cpu_s = (time.perf_counter() - t0) / 32
-    iters = float(np.mean([sum(Rs[i].lm_iterations) for i in range(B)]))
-    h2d = B * (56 + 400 * (24 + 12 + 4))
-    d2h = B * (96 + 400 * 5)
-    alg = B * iters * 2.5 * 400 * (24 + 12 + 4 + 24)  # per LM iteration ~2.5 passes over (Xw, uvr, info, stored error)
-    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    line = {"metric": "frames/sec PoseOptimization 400 map-point observations per frame (SURVEY 8f rank 1)",
-            "value": B / (ms / 1e3), "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": "PoseOptimization: 4 rounds x <=10 LM iterations, 400 observations (80 % stereo), 10 % gross outliers",
-                       "batch": B, "distinct_problems": uniq, "mean_lm_iterations": iters,
-                       "note": "value is measured through the host-pointer C-ABI call (the only entry point): it equals e2e"},
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_pose_opt", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (ms / 1e3) / 1e9 / peak, "traffic": None},
-            "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": 1, "kind": "port",
-                             "sample": "32 frames, 1 thread (the tracking thread runs it serially)"},
-            "e2e": {"value": B / (ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps * opt.last_launches()}
-    print(json.dumps(line))
-
-
-def run_pose_inertial(args):
-    """SURVEY.md 8f rank 1: Optimizer::PoseInertialOptimizationLastFrame / LastKeyFrame, one problem per frame, batched."""
-    import torch
-    from geoflowslam_b200 import PoseInertialOptimizer, synth
-    from geoflowslam_b200 import pose_inertial as pin
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    B = args.batch
-    uniq = min(B, 64)
-    # TrackLocalMap alternates: LastFrame while the map is unchanged, LastKeyFrame after a map update (Tracking.cc:3770-3795)
-    probs = [synth.pose_inertial_problem(seed=6000 + i, mode=(0 if i % 4 == 0 else 1), n_obs=400) for i in range(uniq)]
-    batch = [probs[i % uniq] for i in range(B)]
-    opt = PoseInertialOptimizer(max_obs=512, max_batch=B)
-    Ps = (pin.PoseInertialProblem * B)()
-    Rs = (pin.PoseInertialResult * B)()
-    keep = [pin.pack_problem(pr, Ps[i])[1] for i, pr in enumerate(batch)]
-    outs = [pin.alloc_result(400, Rs[i])[1] for i in range(B)]
-    stream = torch.cuda.current_stream().cuda_stream
-    call = lambda: pin.check(opt._L.gfs_pose_inertial_optimize_batch(opt._h, stream, Ps, B, Rs))
-    for _ in range(max(args.warmup, 3)):
-        call()
-    ms, clocks = _clock_block(lambda: [call() for _ in range(args.steps)], local)
-    ms /= args.steps
-    from oracle import oracle as O
-    t0 = time.perf_counter()
-    for p in probs[:32]:
-        O.pose_inertial_optimize(p)
-    cpu_s = (time.perf_counter() - t0) / 32
-    iters = float(np.mean([sum(Rs[i].gn_iterations) for i in range(B)]))
-    h2d = B * (5400 + 400 * (24 + 12 + 4 + 1))
-    d2h = B * (2000 + 400 * 5)
-    alg = B * iters * 400 * (24 + 12 + 4 + 24)  # per GN iteration one pass over (Xw, uvr, info, stored error)
-    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    line = {"metric": "frames/sec PoseInertialOptimizationLast{Frame,KeyFrame} 400 map-point observations per frame (SURVEY 8f rank 1)",
-            "value": B / (ms / 1e3), "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": "PoseInertialOptimization: 4 rounds x 10 Gauss-Newton iterations, 15 (LastKeyFrame) / 30 (LastFrame) unknowns, 400 observations (80 % stereo), 10 % gross outliers",
-                       "batch": B, "distinct_problems": uniq, "mean_gn_iterations": iters,
-                       "note": "latency-bound dense solves, not an HBM kernel; value is measured through the host-pointer C-ABI call (the only entry point): it equals e2e"},
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_pose_inertial", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (ms / 1e3) / 1e9 / peak, "traffic": None},
-            "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": 1, "kind": "port",
-                             "sample": "32 frames, 1 thread (the tracking thread runs it serially)"},
-            "e2e": {"value": B / (ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps * opt.last_launches()}
-    print(json.dumps(line))
-
-
-def run_klt(args):
-    """SURVEY.md 8f rank 2: cv::buildOpticalFlowPyramid per frame + ORBmatcher::fbKltTracking per consecutive pair."""
-    import cv2
-    import torch
-    from geoflowslam_b200 import KltTracker
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    B = args.batch
-    cores = os.cpu_count() or 1
-    uniq = min(B, 64)
-    frames_u = make_frames(uniq, 1000, min(16, cores))
-    NP = 1000
-    kps_u = np.zeros((uniq, 1024, 2), np.float32); n_u = np.zeros(uniq, np.int32)
-    for i in range(uniq):
-        p = cv2.goodFeaturesToTrack(frames_u[i], NP, 0.01, 5).reshape(-1, 2).astype(np.float32)
-        kps_u[i, :len(p)] = p; n_u[i] = len(p)
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    idx = np.arange(B) % uniq
-    # frame i is tracked into frame i+1 of the same 8-frame scene group (the last frame of a group into its first)
-    nxt = (idx // 8) * 8 + (idx % 8 + 1) % 8
-    frames = np.ascontiguousarray(frames_u[idx])
-    d_imgs = torch.from_numpy(frames).to(dev)
-    d_kps = torch.from_numpy(np.ascontiguousarray(kps_u[idx])).to(dev)
-    d_n = torch.from_numpy(np.ascontiguousarray(n_u[idx])).to(dev)
-    d_next_idx = torch.from_numpy(nxt.astype(np.int64)).to(dev)
-    trk = KltTracker(max_size=(W, H), levels=3, max_points=1024, max_batch=B)
-    pb = trk.pyramid_bytes(W, H)
-    d_pyr = torch.zeros((B, pb), dtype=torch.uint8, device=dev)
-    d_cur = torch.zeros((B, pb), dtype=torch.uint8, device=dev)
-    d_pr = d_kps.clone(); d_st = torch.zeros((B, 1024), dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    t_pyr, t_trk = [], []
-
-    def step(timed=False):
-        d_pr.copy_(d_kps)
-        if timed: ev[0].record()
-        trk.build_pyramids_device(d_imgs, B, W, H, W, W * H, d_pyr, stream=stream)
-        torch.index_select(d_pyr, 0, d_next_idx, out=d_cur)   # pairing only: the "current" frame of pair i
-        if timed: ev[1].record()
-        trk.fb_track_device(d_pyr, d_cur, B, W, H, d_kps, d_pr, d_n, 1024, d_st, nwinsize=35, nbpyrlvl=3, ferr=15.0, fmax_fbklt_dist=0.5,
-                            stream=stream)
-        if timed:
-            ev[2].record(); torch.cuda.synchronize()
-            t_trk.append(ev[1].elapsed_time(ev[2]))
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    ms, clocks = _clock_block(lambda: [step() for _ in range(args.steps)], local)
-    ms /= args.steps
-    for _ in range(3):
-        step(True)
-    trk_ms = sum(t_trk) / len(t_trk)
-    tracked = float(d_st.sum().item()) / float(n_u[idx].sum())
-    # e2e: host images + keypoints in, tracks out, through the host-pointer call (one pair per call)
-    one = KltTracker(max_size=(W, H), levels=3, max_points=1024, max_batch=1)
-    ne = min(B, 64)
-    one.fbKltTracking(frames[0], frames_u[nxt[0]], kps_u[idx[0], :n_u[idx[0]]], kps_u[idx[0], :n_u[idx[0]]])
-    t0 = time.perf_counter()
-    for i in range(ne):
-        k = kps_u[idx[i], :n_u[idx[i]]]
-        one.fbKltTracking(frames[i], frames_u[nxt[i]], k, k)
-    e2e_s = (time.perf_counter() - t0) / ne
-    # CPU arm: the OpenCV calls the reference makes (cv2 wheel, all host threads)
-    crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
-    fl = cv2.OPTFLOW_USE_INITIAL_FLOW + cv2.OPTFLOW_LK_GET_MIN_EIGENVALS
-
-    def cpu_pair(i):
-        a, b = frames_u[i], frames_u[(i // 8) * 8 + (i % 8 + 1) % 8]
-        k = kps_u[i, :n_u[i]]
-        _, pa = cv2.buildOpticalFlowPyramid(a, (35, 35), 3)
-        _, pbb = cv2.buildOpticalFlowPyramid(b, (35, 35), 3)
-        pr, st, er = cv2.calcOpticalFlowPyrLK(a, b, k, k.copy(), winSize=(35, 35), maxLevel=3, criteria=crit, flags=fl)
-        g = st.ravel().astype(bool) & ~(er.ravel() > 15.0)
-        if g.any():
-            cv2.calcOpticalFlowPyrLK(b, a, pr[g], k[g].copy(), winSize=(35, 35), maxLevel=0, criteria=crit, flags=fl)
-
-    cpu_pair(0)
-    t0 = time.perf_counter()
-    cnt = 0
-    while time.perf_counter() - t0 < 8.0:
-        cpu_pair(cnt % uniq); cnt += 1
-    cpu_s = (time.perf_counter() - t0) / cnt
-    npts = float(n_u[idx].mean())
-    alg = B * (W * H * 1.33 * (1 + 1 + 4)) + B * npts * 4 * (37 * 37 * 5 + 6 * 36 * 36)  # pyramid r/w + per point and level: template + ~6 windows
-    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    line = {"metric": "frame pairs/sec buildOpticalFlowPyramid + fbKltTracking, VGA, ~%d points per pair (SURVEY 8f rank 2)" % int(npts),
-            "value": B / (ms / 1e3), "unit": "pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16/f32", "data": "synthetic",
-            "config": {"workload": "optical-flow front end: 3-level pyramid + Scharr derivatives per frame, forward LK (35x35, 4 levels, <=30 its) + backward LK (level 0) per point",
-                       "pairs": B, "distinct_frames": uniq, "points_per_pair": npts, "tracked_fraction": tracked,
-                       "stage_ms": {"track": trk_ms, "pyramid_and_pairing": ms - trk_ms}},
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_klt_track", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (ms / 1e3) / 1e9 / peak, "traffic": None,
-                         "note": "instruction-bound fixed-point bilinear sampling out of shared memory / L1, not an HBM kernel"},
-            "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "pairs/s", "cores": cores, "kind": "reference",
-                             "sample": "%d pairs in %.1f s: cv2 %s buildOpticalFlowPyramid + calcOpticalFlowPyrLK forward/backward, the OpenCV calls the reference makes (OpenCV's own thread pool)" % (cnt, cnt * cpu_s, cv2.__version__)},
-            "e2e": {"value": 1.0 / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": 2 * W * H + int(npts) * 16, "d2h_bytes_per_step": int(npts) * 9,
-                    "note": "one pair per host-pointer call (gfs_klt_fb_track), both pyramids rebuilt per call"},
-            "gpu_launches": args.steps * (5 + 1 + 1)}
-    print(json.dumps(line))
-
-
-#
-# The BASELINE metric: frames/sec VGA RGBD-I (1k feats) track + LocalBA
-# ------------------------------------------------------------------------------------------------
-TRACK_METRIC = "frames/sec VGA RGBD-I (1k feats) track+LocalBA @1/2/4/8 GPU; ATE vs ref"
-TRACK_WORKLOAD = ("per frame: ORB(1000 feats, 1.2, 8 levels, FAST 25/7) + BF-Hamming/GMS against the previous frame, "
-                  "optical-flow pyramid + fbKltTracking of the previous frame's first 512 keypoints, IMU preintegration (7 samples), "
-                  "PoseInertialOptimizationLastFrame (400 observations), depth -> cloud (stride 2, ~50k points) + RegistrationGICP "
-                  "against the previous frame's cloud; per 10 frames: LocalInertialBA (20 KF x 3000 MP x ~15k edges)")
-RING = 4          # frames per synthetic sequence; step s brings frame s % RING of every sequence
-KLT_PTS = 512
-KF_EVERY = 10
-PRE_STRIDE = 292
-
-
-def _gen_depth(seed):
-    from geoflowslam_b200 import synth
-    return synth.depth_frames(seed, n_frames=RING, w=W, h=H, stride=2)[0]
-
-
-def make_track_data(n_seq, seed0, procs):
-    """Synthetic input of `n_seq` independent RGB-D-inertial sequences, RING frames each (numpy, fork pool; before CUDA):
-    gray (RING, n, H, W) u8 -- the frames of a sequence show one scene under small homographies; depth (RING, n, H, W) u16
-    in mm -- one room-and-boxes scene from poses a configs[2] perturbation apart; IMU rows (RING, n, 7, 7) float32;
-    PoseInertialOptimizationLastFrame problems and LocalInertialBA problems of the named shapes."""
-    from multiprocessing import get_context
-    from geoflowslam_b200 import synth
-    assert RING <= 8
-    jobs = [(8 * i, RING, seed0) for i in range(n_seq)]
-    if procs > 1:
-        with get_context("fork").Pool(procs) as pool:
-            gray = pool.map(_gen_chunk, jobs)
-            depth = pool.map(_gen_depth, [seed0 + 500000 + i for i in range(n_seq)])
-    else:
-        gray = [_gen_chunk(j) for j in jobs]
-        depth = [_gen_depth(seed0 + 500000 + i) for i in range(n_seq)]
-    gray = np.ascontiguousarray(np.stack(gray, 1))      # (RING, n, H, W)
-    depth = np.ascontiguousarray(np.stack(depth, 1))    # (RING, n, H, W)
-    rng = np.random.default_rng(seed0 + 77)
-    imu = np.stack([np.stack([synth.imu_samples(rng, 7)[2] for _ in range(n_seq)]) for _ in range(RING)]).astype(np.float32)
-    pin_probs = [synth.pose_inertial_problem(seed=6000 + i, mode=1, n_obs=400) for i in range(min(n_seq, 16))]
-    ba_probs = [synth.ba_problem(seed=3000 + i) for i in range(2)]
-    return dict(gray=gray, depth=depth, imu=imu, pin=pin_probs, ba=ba_probs)
-
-
-def _depth_cloud_np(depth_u16):
-    """GrabImageRGBD's convertTo(CV_32F, 1 / DepthMapFactor) + Frame::ConvertDepthToPointCloud(2) on the host (CPU arm)."""
-    from oracle import oracle as O
-    from geoflowslam_b200 import synth
-    c = synth.G1_CAM
-    return O.depth_to_cloud(depth_u16.astype(np.float32) * np.float32(1e-3), 2, c["fx"], c["fy"], c["cx"], c["cy"])
-
-
-def cpu_track_frames_per_sec(data, threads, n_seq, gicp_threads=1):
-    """The restated reference CPU path of the same step, measured: `threads` workers, each advancing whole sequences frame
-    by frame (every stage single-threaded inside a worker -- with many independent sequences that is the arrangement that
-    uses the host cores best; the reference itself runs one sequence on ~3 threads).  A sequence is advanced by RING
-    frames after an untimed first frame that only fills the previous-frame state.  -> (frames/s, seconds, per-stage
-    core-seconds per frame)."""
-    import cv2
-    from concurrent.futures import ThreadPoolExecutor
-    from oracle import oracle as O
-    from geoflowslam_b200 import synth
-    O.lib()
-    cv2.setNumThreads(1)
-    tl = threading.local()
-    crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
-    fl = cv2.OPTFLOW_USE_INITIAL_FLOW + cv2.OPTFLOW_LK_GET_MIN_EIGENVALS
-    cal = synth.imu_calib_noise()
-    n_data = data["gray"].shape[1]
-    acc = {k: 0.0 for k in ("orb_match", "klt", "imu_pose_inertial", "depth_cloud_gicp", "local_inertial_ba")}
-    lock = threading.Lock()
-
-    def frontend(i, f):
-        if not hasattr(tl, "o"):
-            tl.o = O.OrbOracle(ORB_CFG["nfeatures"], ORB_CFG["scaleFactor"], ORB_CFG["nlevels"], ORB_CFG["iniThFAST"],
-                               ORB_CFG["minThFAST"], threads=1)
-        g = data["gray"][f, i % n_data]
-        k, d, _ = tl.o.extract(g)
-        _, pyr = cv2.buildOpticalFlowPyramid(g, (35, 35), 3)
-        return dict(g=g, k=k, d=d, pyr=pyr, cloud=_depth_cloud_np(data["depth"][f, i % n_data]))
-
-    def advance(i):
-        prev = frontend(i, 0)
-        t = dict.fromkeys(acc, 0.0)
-        for s in range(1, RING + 1):
-            f = s % RING
-            t0 = time.perf_counter()
-            g = data["gray"][f, i % n_data]
-            k, d, _ = tl.o.extract(g)
-            idx, _ = O.bf_match(prev["d"], d, threads=1)
-            m = np.stack([np.arange(len(idx), dtype=np.int32), idx], 1)
-            O.gms_filter(np.stack([prev["k"]["x"], prev["k"]["y"]], 1), (W, H), np.stack([k["x"], k["y"]], 1), (W, H), m)
-            t1 = time.perf_counter()
-            _, pyr = cv2.buildOpticalFlowPyramid(g, (35, 35), 3)
-            pts = np.stack([prev["k"]["x"], prev["k"]["y"]], 1)[:KLT_PTS].astype(np.float32)
-            pr, st, er = cv2.calcOpticalFlowPyrLK(prev["g"], g, pts, pts.copy(), winSize=(35, 35), maxLevel=3, criteria=crit, flags=fl)
-            ok = st.ravel().astype(bool) & ~(er.ravel() > 15.0)
-            if ok.any():
-                cv2.calcOpticalFlowPyrLK(g, prev["g"], pr[ok], pts[ok].copy(), winSize=(35, 35), maxLevel=0, criteria=crit, flags=fl)
-            t2 = time.perf_counter()
-            O.imu_preintegrate(data["imu"][f, i % n_data], np.zeros(6, np.float32), *cal)
-            O.pose_inertial_optimize(data["pin"][i % len(data["pin"])])
-            t3 = time.perf_counter()
-            cloud = _depth_cloud_np(data["depth"][f, i % n_data])
-            O.gicp_align(prev["cloud"], cloud, threads=gicp_threads)
-            t4 = time.perf_counter()
-            if (i * RING + s) % KF_EVERY == 0:
-                O.ba_solve(data["ba"][i % len(data["ba"])])
-            t5 = time.perf_counter()
-            for key, dt in zip(acc, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
-                t[key] += dt
-            prev = dict(g=g, k=k, d=d, pyr=pyr, cloud=cloud)
-        with lock:
-            for key in acc:
-                acc[key] += t[key]
-
-    # untimed: the first frame of every sequence is done inside advance() but it is cheap relative to RING full frames; it
-    # IS inside the wall time below, which therefore slightly favours the GPU arm by < 15 % of one stage (ORB only)
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(threads) as ex:
-        list(ex.map(advance, range(n_seq)))
-    dt = time.perf_counter() - t0
-    cv2.setNumThreads(-1)
-    frames = n_seq * RING
-    return frames / dt, dt, {k: v / frames for k, v in acc.items()}
-
-
-def cv2_orb_match_crosscheck(data, n=8):
-    """BASELINE.md section 3, rule 3: the OpenCV primitives the reference's ORB + match stage calls (cv::resize INTER_AREA x 7,
-    cv::FAST per level, cv::GaussianBlur per level, cv::BFMatcher on 1000 x 1000 descriptors), single thread, cv2's SIMD builds --
-    a sanity check that the restated stage is not a strawman.  It leaves out everything the reference itself owns (cell grid and
-    threshold retry, quadtree, IC_Angle, rBRIEF, GMS), so it is a LOWER bound of the stage.  -> ms per frame."""
-    import cv2
-    from oracle import oracle as O
-    cv2.setNumThreads(1)
-    oo = O.OrbOracle(ORB_CFG["nfeatures"], ORB_CFG["scaleFactor"], ORB_CFG["nlevels"], ORB_CFG["iniThFAST"], ORB_CFG["minThFAST"], threads=1)
-    g = [data["gray"][i % RING, 0] for i in range(n)]
-    descs = [oo.extract(x)[1] for x in g[:2]]
-    fast = cv2.FastFeatureDetector_create(ORB_CFG["iniThFAST"], True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
-    bf = cv2.BFMatcher(cv2.NORM_HAMMING)
-    t0 = time.perf_counter()
-    for img in g:
-        lv = img
-        for (w, h) in LEVELS:
-            if (w, h) != (W, H):
-                lv = cv2.resize(lv, (w, h), interpolation=cv2.INTER_AREA)
-            fast.detect(lv, None)
-            cv2.GaussianBlur(lv, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
-        bf.match(descs[0], descs[1])
-    ms = 1e3 * (time.perf_counter() - t0) / n
-    cv2.setNumThreads(-1)
-    return ms
-
-
-def run_track_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    cores = os.cpu_count() or 1
-    n_seq = 4 * max(cores, 8)        # four sequences per core and step (RING frames each, ~5 s of wall): enough to amortise the longest sequence
-    data = make_track_data(min(n_seq, 16), 1000, min(cores, 16))
-    for _ in range(min(args.warmup, 1)):
-        cpu_track_frames_per_sec(data, cores, max(cores // 2, 1))
-    t, stage = [], None
-    for _ in range(args.steps):
-        fps, dt, stage = cpu_track_frames_per_sec(data, cores, n_seq)
-        t.append(dt)
-    ms = 1e3 * sum(t) / len(t)
-    value = n_seq * RING / (ms / 1e3)
-    sample = "%d sequences x %d frames per step on %d worker threads, %d steps; core-seconds per frame by stage: %s" % (
-        n_seq, RING, cores, args.steps, json.dumps({k: round(v, 5) for k, v in stage.items()}))
-    line = {"impl": "reference", "metric": TRACK_METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
-            "config": {"workload": TRACK_WORKLOAD, "sample": sample,
-                       "note": "restated reference CPU path (oracle/, kind 'port': the reference needs OpenCV/Eigen/PCL/g2o to build); optical flow = the cv2 calls the reference makes"},
-            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    print(json.dumps(line))
-
-
-def latency_table(data, reps=30):
-    """Batch = 1 latency of every entry point through the host-pointer C ABI (what one System::TrackRGBD call pays per stage),
-    median of `reps` calls in ms, next to one call of the CPU oracle on the same input."""
-    import torch
-    from geoflowslam_b200 import (KltTracker, Optimizer, ORBextractor, ORBmatcher, PoseInertialOptimizer, RegistrationGICP, imu, synth)
-    from oracle import oracle as O
-    cal = synth.imu_calib_noise()
-    g0, g1 = data["gray"][0, 0], data["gray"][1, 0]
-    c0, c1 = _depth_cloud_np(data["depth"][0, 0]), _depth_cloud_np(data["depth"][1, 0])
-    orb = ORBextractor(max_size=(W, H), max_batch=1, **ORB_CFG)
-    _, k0, d0 = orb(g0); _, k1, d1 = orb(g1)
-    pts = np.stack([k0["x"], k0["y"]], 1)[:KLT_PTS].astype(np.float32)
-    m = ORBmatcher(); trk = KltTracker(max_size=(W, H), levels=3, max_points=KLT_PTS, max_batch=1)
-    pio = PoseInertialOptimizer(max_obs=512, max_batch=1); reg = RegistrationGICP(max_points=65536, max_pairs=1)
-    opt = Optimizer(max_kf=21, max_points=3000, max_obs=16384, max_inertial=20, max_batch=1)
-    rows = data["imu"][0, 0]; zb = np.zeros(6, np.float32)
-    oo = O.OrbOracle(ORB_CFG["nfeatures"], ORB_CFG["scaleFactor"], ORB_CFG["nlevels"], ORB_CFG["iniThFAST"], ORB_CFG["minThFAST"], threads=1)
-
-    def o_match():
-        idx, _ = O.bf_match(d0, d1)
-        mm = np.stack([np.arange(len(idx), dtype=np.int32), idx], 1)
-        O.gms_filter(np.stack([k0["x"], k0["y"]], 1), (W, H), np.stack([k1["x"], k1["y"]], 1), (W, H), mm)
-
-    def o_klt():
-        pa, pb = O.klt_build_pyramid(g0, 3), O.klt_build_pyramid(g1, 3)
-        O.fb_klt_tracking(pa, pb, W, H, 3, pts, pts)
-    calls = {
-        "ORBextractor::operator()": (lambda: orb(g1), lambda: oo.extract(g1)),
-        "SearchWithGMS": (lambda: m.SearchWithGMS(k0, d0, k1, d1, (W, H)), o_match),
-        "buildOpticalFlowPyramid x2 + fbKltTracking": (lambda: trk.fbKltTracking(g0, g1, pts, pts), o_klt),
-        "IMU preintegration": (lambda: imu.preintegrate_batch([rows], [zb], *cal), lambda: O.imu_preintegrate(rows, zb, *cal)),
-        "PoseInertialOptimizationLastFrame": (lambda: pio.optimize_batch([data["pin"][0]]), lambda: O.pose_inertial_optimize(data["pin"][0])),
-        "RegisterPointClouds": (lambda: reg.RegisterPointClouds(c0, c1), lambda: O.gicp_align(c0, c1, threads=4)),
-        "LocalInertialBA": (lambda: opt.LocalInertialBA(data["ba"][0]), lambda: O.ba_solve(data["ba"][0])),
-    }
-    out = {}
-    for name, (fg, fo) in calls.items():
-        for _ in range(3):
-            fg()
-        ts = []
-        for _ in range(reps if name != "LocalInertialBA" else max(5, reps // 3)):
-            torch.cuda.synchronize(); t0 = time.perf_counter(); fg(); ts.append(1e3 * (time.perf_counter() - t0))
-        fo(); t0 = time.perf_counter(); fo(); to = 1e3 * (time.perf_counter() - t0)
-        out[name] = {"gpu_ms": round(statistics.median(ts), 4), "cpu_oracle_ms": round(to, 4)}
-    return out
-
-
-def ate_vs_oracle(n_frames=12, kf_every=3, seed=4000):
-    """The closed-loop tracker (geoflowslam_b200/tracker.py: ORB -> SearchByProjection / GMS -> GICP gate -> pose optimisers ->
-    keyframes -> LocalInertialBA) on the CUDA library and on the CPU oracle over one synthetic sequence: ATE of both against the
-    ground truth, their difference, and the number of integer decisions that differ."""
-    from geoflowslam_b200 import imu, synth, tracker
-    from oracle.tracker_backend import OracleBackend
-    seq = synth.room_sequence(seed, n_frames=n_frames)
-    g = tracker.run_tracker(seq, tracker.CudaBackend(), kf_every=kf_every)
-    o = tracker.run_tracker(seq, OracleBackend(), kf_every=kf_every)
-    gt = seq["twb"][:n_frames]
-    a, b = imu.ate_rmse(g["twb"], gt), imu.ate_rmse(o["twb"], gt)
-    return {"frames": n_frames, "keyframes": g["n_keyframes"], "ate_cuda_m": a, "ate_oracle_m": b, "ate_difference_m": abs(a - b),
-            "max_position_difference_m": float(np.abs(g["twb"] - o["twb"]).max()),
-            "differing_decisions": sum(1 for x, y in zip(g["decisions"], o["decisions"]) if x != y) + abs(len(g["decisions"]) - len(o["decisions"])),
-            "decisions_compared": len(g["decisions"])}
-
-
-def run_track(args):
-    """BASELINE.json's metric.  One step advances B independent RGB-D-inertial sequences per GPU by one frame: the stages of
-    System::TrackRGBD -> Tracking::Track (reference src/System.cc:661, src/Tracking.cc:2042-2260) that this library replaces,
-    with every stage's previous-frame state (descriptors, keypoints, optical-flow pyramid, preprocessed cloud) resident in
-    HBM from the step before, plus LocalInertialBA (src/LocalMapping.cc:223) for the 1-in-10 sequences that insert a
-    keyframe.  The Tracking / LocalMapping state machines are out of scope, so the map-dependent inputs (the
-    observations of the pose optimiser, the BA window) are synthetic problems of the named shapes rather than the output of
-    the stages before them; tests/test_gpu_closed_loop.py chains the stages causally and checks the trajectory."""
-    import torch
-    import torch.distributed as dist
-    from concurrent.futures import ThreadPoolExecutor
-    from geoflowslam_b200 import KltTracker, Optimizer, ORBextractor, PoseInertialOptimizer, RegistrationGICP, synth
-    from geoflowslam_b200 import pose_inertial as pin
-    from geoflowslam_b200._lib import check, lib, ptr
-    from geoflowslam_b200.gicp import RESULT_DTYPE
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    # sequences per GPU and step: 256 measured best (3937 / 4070 / 4178 / 4107 frames/s device-resident and 3820 / 4066 / 3951 / 3960 end
-    # to end at 128 / 256 / 384 / 512; the LM rounds' small-grid tails and the latency-bound BA / pose launches amortise)
-    B = args.batch if args.batch != 1024 else 256
-    cores = os.cpu_count() or 1
-    uniq = min(B, 16)
-    # Weak scaling = the same work on every GPU.  GICP's cost is data dependent (3 to 20 LM iterations per pair; measured 33.7 to
-    # 41.3 ms per step over four different seed sets, profiles/r02_summary.md), so every rank gets the SAME pool of distinct
-    # synthetic sequences (tiled to B in a rank-rotated order) -- with per-rank seeds the max-over-ranks time measured the
-    # unluckiest data set, not the system.  GFS_BENCH_SEED_RANK=r (diagnostic) selects another pool.
-    seed_rank = int(os.environ.get("GFS_BENCH_SEED_RANK", "0"))
-    data = make_track_data(uniq, 1000 + seed_rank * 100000, max(1, min(16, cores // max(world, 1))))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    s_main = torch.cuda.current_stream()
-    stream = s_main.cuda_stream
-    L = lib()
-    cam = synth.G1_CAM
-    cal = synth.imu_calib_noise()
-    idx = (np.arange(B) + rank) % uniq
-
-    # ---- host inputs (pinned) and their resident copies
-    def pinned(a):
-        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        return t
-    h_gray = [pinned(data["gray"][f][idx]) for f in range(RING)]          # (B, H, W) u8 per ring slot
-    # depth stays 16-bit until the device (as cv::imread hands it to TrackRGBD); millimetres < 32768, so the int16 view holds
-    # the same values and is a dtype every torch op supports
-    h_depth = [pinned(data["depth"][f][idx].view(np.int16)) for f in range(RING)]        # (B, H, W) u16 viewed as i16
-    h_imu = [pinned(data["imu"][f][idx].reshape(B * 7, 7)) for f in range(RING)]
-    d_gray = [t.to(dev) for t in h_gray]
-    d_depth = [t.to(dev) for t in h_depth]
-    d_imu = [t.to(dev) for t in h_imu]
-    d_off = torch.arange(0, 7 * B + 1, 7, dtype=torch.int32, device=dev)
-    d_bias = torch.zeros((B, 6), dtype=torch.float32, device=dev)
-    d_pre = torch.empty((B, PRE_STRIDE), dtype=torch.float32, device=dev)
-    # staging buffers of the host-buffer (e2e) path
-    # two sets: while step s computes on set s & 1, the copy stream brings frame s + 1 into the other set (every step still copies
-    # one frame's inputs from pinned host memory inside the timed region; the copy overlaps the previous step's kernels)
-    s_gray = [torch.empty((B, H, W), dtype=torch.uint8, device=dev) for _ in range(2)]
-    s_depth = [torch.empty((B, H, W), dtype=torch.int16, device=dev) for _ in range(2)]
-    s_imu = [torch.empty((B * 7, 7), dtype=torch.float32, device=dev) for _ in range(2)]
-    s_copy = torch.cuda.Stream(device=dev)
-    copy_done = [None, None]          # event of the copy that fills a set; step number it was filled for
-    copy_for = [-1, -1]
-
-    # ---- ORB + match state: ring of keypoints / descriptors
-    orb = ORBextractor(max_size=(W, H), max_batch=B, **ORB_CFG)
-    S = orb.stride
-    r_kp = [torch.zeros((B, S, 6), dtype=torch.float32, device=dev) for _ in range(RING)]
-    r_desc = [torch.zeros((B, S, 32), dtype=torch.uint8, device=dev) for _ in range(RING)]
-    r_n = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(RING)]
-    d_mono = torch.zeros(B, dtype=torch.int32, device=dev)
-    d_tidx = torch.empty((B, S), dtype=torch.int32, device=dev); d_dist = torch.empty((B, S), dtype=torch.int32, device=dev)
-    d_inl = torch.empty((B, S), dtype=torch.uint8, device=dev); d_inlc = torch.zeros(B, dtype=torch.int32, device=dev)
-    # ---- optical flow state: ring of pyramids
-    trk = KltTracker(max_size=(W, H), levels=3, max_points=KLT_PTS, max_batch=B)
-    pb = trk.pyramid_bytes(W, H)
-    r_pyr = [torch.zeros((B, pb), dtype=torch.uint8, device=dev) for _ in range(RING)]
-    d_kps = torch.zeros((B, KLT_PTS, 2), dtype=torch.float32, device=dev); d_pr = torch.zeros_like(d_kps)
-    d_nk = torch.zeros(B, dtype=torch.int32, device=dev); d_st = torch.zeros((B, KLT_PTS), dtype=torch.uint8, device=dev)
-    # ---- pose-inertial (host-pointer C ABI: the problems are host structures in both modes)
-    pio = PoseInertialOptimizer(max_obs=512, max_batch=B)
-    Ps = (pin.PoseInertialProblem * B)(); Rs = (pin.PoseInertialResult * B)()
-    keep = [pin.pack_problem(data["pin"][i % len(data["pin"])], Ps[i])[1] for i in range(B)]
-    outs = [pin.alloc_result(400, Rs[i])[1] for i in range(B)]
-    # ---- depth -> cloud + GICP in tracking mode (previous cloud resident, preprocessed once)
-    CAP = 65536
-    d_depthf = torch.empty((B, H, W), dtype=torch.float32, device=dev)
-    d_cloud = torch.empty((B, CAP, 4), dtype=torch.float32, device=dev); d_cn = torch.zeros(B, dtype=torch.int32, device=dev)
-    # the sequences' GICP can be cut into GSPLIT groups, each with its own handle, stream and host thread: the late LM rounds of one
-    # group (few unconverged pairs left, small grids) then overlap the full rounds of another (GFS_TRACK_GICP_SPLIT, default 1)
-    GSPLIT = max(1, int(os.environ.get("GFS_TRACK_GICP_SPLIT", "1")))
-    assert B % GSPLIT == 0
-    BG = B // GSPLIT
-    regs = [RegistrationGICP(max_points=CAP, max_pairs=BG) for _ in range(GSPLIT)]
-    reg = regs[0]
-    d_T0 = torch.from_numpy(np.tile(np.eye(4), (B, 1, 1))).to(dev)
-    d_res = torch.zeros((B, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-    # ---- LocalInertialBA for the sequences that insert a keyframe this step
-    nba = max(1, B // KF_EVERY)
-    ba_batch = [data["ba"][i % len(data["ba"])] for i in range(nba)]
-    opt = Optimizer(max_kf=21, max_points=3000, max_obs=16384, max_inertial=20, max_batch=nba)
-    opt.upload(ba_batch, stream)
-    # ---- host outputs of the e2e path (pinned)
-    def pin_out(t):
-        return torch.empty(t.shape, dtype=t.dtype).pin_memory()
-    o_kp, o_desc, o_n = pin_out(r_kp[0]), pin_out(r_desc[0]), pin_out(r_n[0])
-    o_tidx, o_inl, o_inlc = pin_out(d_tidx), pin_out(d_inl), pin_out(d_inlc)
-    o_pr, o_st, o_pre, o_res = pin_out(d_pr), pin_out(d_st), pin_out(d_pre), pin_out(d_res)
-
-    side = [torch.cuda.Stream(device=dev) for _ in range(3)]
-    gside = [side[0]] + [torch.cuda.Stream(device=dev) for _ in range(GSPLIT - 1)]
-    pool = ThreadPoolExecutor(3 + GSPLIT - 1)
-    counts = dict(orb=0, match=0, klt=0, imu=0, pose=0, cloud=0, gicp=0, ba=0)
-    ba_host = [None]
-
-    def _gicp(f, depth16):
-        torch.cuda.set_device(local)
-        with torch.cuda.stream(side[0]):
-            torch.mul(depth16, 1e-3, out=d_depthf)          # GrabImageRGBD: imDepth.convertTo(CV_32F, 1 / DepthMapFactor)
-        cs = side[0].cuda_stream
-        check(L.gfs_depth_to_cloud_batch_device(cs, ptr(d_depthf), B, W, H, W, W * H, 2, cam["fx"], cam["fy"], cam["cx"], cam["cy"],
-                                                ptr(d_cloud), CAP, ptr(d_cn)))
-        if GSPLIT == 1 or side[0] is s_main:
-            for gi, r in enumerate(regs):
-                sl = slice(gi * BG, (gi + 1) * BG)
-                r.track_batch_device(d_cloud[sl], d_cn[sl], BG, CAP, d_T0[sl], d_res[sl], stream=cs)
-        else:
-            ev = torch.cuda.Event(); ev.record(side[0])
-            fs = []
-            for gi in range(1, GSPLIT):
-                gside[gi].wait_event(ev)
-                fs.append(pool.submit(_gicp_group, gi))
-            _gicp_group(0)
-            for ft in fs:
-                ft.result()
-            for gi in range(1, GSPLIT):
-                side[0].wait_stream(gside[gi])
-        counts["cloud"] = 1; counts["gicp"] = sum(r.last_launches() for r in regs)
-
-    def _gicp_group(gi):
-        torch.cuda.set_device(local)
-        sl = slice(gi * BG, (gi + 1) * BG)
-        regs[gi].track_batch_device(d_cloud[sl], d_cn[sl], BG, CAP, d_T0[sl], d_res[sl], stream=gside[gi].cuda_stream)
-
-    def _ba(host):
-        torch.cuda.set_device(local)
-        if host:
-            ba_host[0] = opt.LocalInertialBA_batch(ba_batch, side[1].cuda_stream)     # pack + upload + solve + download
-        else:
-            opt.solve_uploaded(side[1].cuda_stream)
-        counts["ba"] = opt.last_launches()
-
-    def _pose():
-        torch.cuda.set_device(local)
-        pin.check(pio._L.gfs_pose_inertial_optimize_batch(pio._h, side[2].cuda_stream, Ps, B, Rs))
-        counts["pose"] = pio.last_launches()
-
-    step_no = [0]
-    pose_on_main = os.environ.get("GFS_TRACK_POSE_ON_MAIN", "0") == "1"
-
-    def step(host=False, sequential=False, marks=None):
-        """Advance every sequence by one frame.  host: inputs come from pinned host buffers and every result goes back to the
-        host inside the step (the e2e number); otherwise the frame's inputs are already resident (the `value` number)."""
-        s = step_no[0]; step_no[0] += 1
-        f, fp = s % RING, (s - 1) % RING
-        if host:
-            def issue_copy(step_idx):
-                k, ff = step_idx & 1, step_idx % RING
-                with torch.cuda.stream(s_copy):
-                    s_gray[k].copy_(h_gray[ff], non_blocking=True); s_depth[k].copy_(h_depth[ff], non_blocking=True)
-                    s_imu[k].copy_(h_imu[ff], non_blocking=True)
-                    ev = torch.cuda.Event(); ev.record(s_copy)
-                copy_done[k], copy_for[k] = ev, step_idx
-            k = s & 1
-            if copy_for[k] != s:              # first host step (or after device-resident steps): nothing was prefetched
-                s_copy.wait_stream(s_main)
-                issue_copy(s)
-            s_main.wait_event(copy_done[k])
-            # the other set was last read by step s - 1, which has fully completed (host steps end with a synchronize)
-            issue_copy(s + 1)
-            gray, depth16, imu = s_gray[k], s_depth[k], s_imu[k]
-        else:
-            gray, depth16, imu = d_gray[f], d_depth[f], d_imu[f]
-
-        def mark(k):
-            if marks is not None:
-                e = torch.cuda.Event(enable_timing=True); e.record(); marks.append((k, e))
-        mark("start")
-        futs = []
-        if not sequential:
-            for cs in side:
-                cs.wait_stream(s_main)
-            futs = [pool.submit(_gicp, f, depth16), pool.submit(_ba, host)]
-            if not pose_on_main:
-                futs.append(pool.submit(_pose))
-        # tracking front end on the main stream
-        orb.extract_batch_device(gray, B, W, H, W, W * H, r_kp[f], r_desc[f], r_n[f], d_mono, stream=stream)
-        check(L.gfs_match_bf_hamming_batch_device(stream, ptr(r_desc[fp]), ptr(r_n[fp]), ptr(r_desc[f]), ptr(r_n[f]), B, S, ptr(d_tidx), ptr(d_dist)))
-        check(L.gfs_gms_filter_batch_device(stream, ptr(r_kp[fp]), ptr(r_n[fp]), ptr(r_kp[f]), ptr(r_n[f]), ptr(d_tidx), B, S, W, H, W, H,
-                                            ptr(d_inl), ptr(d_inlc)))
-        mark("orb_match")
-        trk.build_pyramids_device(gray, B, W, H, W, W * H, r_pyr[f], stream=stream)
-        d_kps.copy_(r_kp[fp][:, :KLT_PTS, :2]); d_pr.copy_(d_kps)                     # the previous frame's keypoints, prior = same place
-        torch.clamp(r_n[fp], max=KLT_PTS, out=d_nk)
-        trk.fb_track_device(r_pyr[fp], r_pyr[f], B, W, H, d_kps, d_pr, d_nk, KLT_PTS, d_st, stream=stream)
-        mark("klt")
-        check(L.gfs_imu_preintegrate_batch_device(stream, ptr(imu), ptr(d_off), ptr(d_bias), B, cal[0], cal[1], cal[2], cal[3], ptr(d_pre)))
-        mark("imu")
-        if pose_on_main and not sequential:
-            _pose()       # one launch + one wait: the main thread has nothing else to enqueue until the side streams finish
-        if sequential:
-            side_backup = side[:]
-            side[0] = side[1] = side[2] = s_main
-            _pose(); mark("pose_inertial")
-            _gicp(f, depth16); mark("depth_cloud_gicp")
-            _ba(host); mark("local_inertial_ba")
-            side[:] = side_backup
-        for ft in futs:
-            ft.result()
-        if not sequential:
-            for cs in side:
-                s_main.wait_stream(cs)
-        if host:
-            for o, d in ((o_kp, r_kp[f]), (o_desc, r_desc[f]), (o_n, r_n[f]), (o_tidx, d_tidx), (o_inl, d_inl), (o_inlc, d_inlc),
-                         (o_pr, d_pr), (o_st, d_st), (o_pre, d_pre), (o_res, d_res)):
-                o.copy_(d, non_blocking=True)
-            s_main.synchronize()                                                      # the step's results are on the host
-        counts["orb"] = orb.launches_per_call(); counts["match"] = 2; counts["klt"] = 5 + 1; counts["imu"] = 1   # this library's kernels only
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, k):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(k):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        barrier()
-        return float(ms.item())
-
-    W_ = max(args.warmup, 3)
-    for _ in range(W_ + RING):        # RING extra steps fill every ring slot (and the GICP handle's previous cloud)
-        step()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ms_step = timed(step, args.steps) / args.steps
-    clocks = sampler.stop() if rank == 0 else None
-    value = world * B / (ms_step / 1e3)
-    launches = sum(counts.values())
-
-    # ---- end to end: pinned host inputs in, all results back on the host, every step
-    for _ in range(2):
-        step(host=True)
-    e2e_steps = max(1, min(args.steps, 10))
-    ms_e2e = timed(lambda: step(host=True), e2e_steps) / e2e_steps
-    e2e_value = world * B / (ms_e2e / 1e3)
-    pin_bytes = B * (5400 + 400 * (24 + 12 + 4 + 1))
-    ba_bytes = sum(int(np.asarray(v).nbytes) for p in ba_batch for v in p.values() if isinstance(v, np.ndarray))
-    h2d = int(h_gray[0].nbytes + h_depth[0].nbytes + h_imu[0].nbytes) + pin_bytes + ba_bytes
-    d2h = int(sum(o.nbytes for o in (o_kp, o_desc, o_n, o_tidx, o_inl, o_inlc, o_pr, o_st, o_pre, o_res))) + B * (2000 + 400 * 5) + \
-        nba * (21 * 15 * 8 + 3000 * 24 + 16384)
-    gicp_res = o_res.numpy().reshape(-1).view(RESULT_DTYPE).copy()
-
-    # ---- per-stage times: one stream, stages back to back (CUDA events), and GICP's kernels by stage
-    stage = {}
-    for _ in range(2):
-        step(sequential=True)
-    for _ in range(3):
-        marks = []
-        step(sequential=True, marks=marks)
-        torch.cuda.synchronize()
-        for (k0, e0), (k1, e1) in zip(marks[:-1], marks[1:]):
-            stage.setdefault(k1, []).append(e0.elapsed_time(e1))
-    stage = {k: sum(v) / len(v) for k, v in stage.items()}
-    for r in regs:
-        r.set_profiling(True)
-    gprof = {}
-    for _ in range(3):
-        step(sequential=True)
-        torch.cuda.synchronize()
-        for r in regs:
-            for k, (ms, ln) in r.profile().items():
-                a = gprof.setdefault(k, [0.0, 0]); a[0] += ms / 3; a[1] += ln / 3
-    for r in regs:
-        r.set_profiling(False)
-    pool.shutdown()
-    res = d_res.cpu().numpy().reshape(-1).view(RESULT_DTYPE)
-    n_in = float(d_cn.float().mean().item())
-    M = float(res["n_source"].mean()); I = float(res["iterations"].mean() + 1); J = float(res["inner_evals"].mean())
-    kp_mean = float(r_n[0].float().mean().item())
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant kernel (largest total CUDA-event time per step)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
-    # algorithmic bytes per launch (DESIGN.md section 4, SURVEY.md 8d): 10-NN covariances = query 32 B + 10 neighbours x 32 B
-    # + covariance 48 B per downsampled point; correspondence search = source point 32 B + target point 32 B + index 4 B
-    alg = {"knn_cov": BG * M * (32 + 320 + 48), "nn_corr": BG * M * (32 + 32 + 4), "linearize": BG * M * (32 + 4 + 48 + 48 + 32 + 72)}   # per launch (one group)
-    kern = {k: v for k, v in gprof.items() if k in alg and v[1] > 0}
-    top = max(kern, key=lambda k: kern[k][0])
-    per_launch_ms = kern[top][0] / kern[top][1]
-    achieved = alg[top] / (per_launch_ms / 1e3) / 1e9
-    traffic_per_query = {"knn_cov": (485.131520e6 + 273.671168e6) / (128 * 42100.0),      # profiles/r02_s1_gicp_knn_cov_after_ncu_details.txt
-                         "nn_corr": (105.925376e6 + 4.146176e6) / (64 * 42100.0)}        # profiles/r02_s1_gicp_nn_corr_after_ncu_details.txt
     roof = {"bound": "hbm", "kernel": {"knn_cov": "k_knn_cov", "nn_corr": "k_nn_corr3", "linearize": "k_linearize"}[top],
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic_per_query[top] * BG * M if top in traffic_per_query else None,
