@@ -291,47 +291,48 @@ __device__ __forceinline__ unsigned stage_window(const LevelView& L, int x0, int
   const int lane = threadIdx.x & 31, ww = win + 1, pitch = win_pitch(win);
   const bool inside = x0 >= 0 && y0 >= 0 && x0 + ww <= L.w && y0 + ww <= L.h;
   unsigned a0 = NO_SHIFT;
-  // Both copies run over the flattened window, four elements per lane and trip, loads first: the staging is pure memory latency
-  // (it was half of the kernel's stall samples), so what counts is how many independent loads a warp has in flight -- the
-  // row-by-row loops issued one or two per trip, the second with 4 of 32 lanes.
   if (inside) {
     const uint8_t* p0 = L.img + (size_t)y0 * L.w + x0;
     a0 = (unsigned)(reinterpret_cast<size_t>(p0) & 3);
-    const int wpr = pitch / 4, tot = ww * wpr;
-    for (int i0 = lane; i0 < tot; i0 += 128) {
+    const int wpr = pitch / 4;
+    int r = 0, k = lane;
+    while (k >= wpr) { k -= wpr; r++; }
+    const int tot = ww * wpr;
+    for (int i = lane; i < tot; i += 128) {   // four words per lane and trip, loads before stores
       unsigned v[4];
+      int idx[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        const int i = i0 + 32 * u;
-        if (i < tot) {
-          const int r = i / wpr, k = i - r * wpr;
+        idx[u] = (i + 32 * u < tot) ? r * wpr + k : -1;
+        if (idx[u] >= 0) {
           const uint8_t* row = p0 + (size_t)r * L.w;
           const unsigned* src = reinterpret_cast<const unsigned*>(row - (reinterpret_cast<size_t>(row) & 3));
           v[u] = __ldg(src + k);
         }
+        k += 32;
+        while (k >= wpr) { k -= wpr; r++; }
       }
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int i = i0 + 32 * u;
-        if (i < tot) reinterpret_cast<unsigned*>(s_win)[i] = v[u];   // r * wpr + k == i
-      }
+      for (int u = 0; u < 4; u++)
+        if (idx[u] >= 0) reinterpret_cast<unsigned*>(s_win)[idx[u]] = v[u];
     }
   } else {
-    const int tot = ww * ww;
-    for (int i0 = lane; i0 < tot; i0 += 128) {
-      uint8_t v[4];
+    // rows outer, lanes over the columns: the reflected column of a lane is the same for every row
+    const int c0 = lane < ww ? reflect101(x0 + lane, L.w) : 0, c1 = lane + 32 < ww ? reflect101(x0 + lane + 32, L.w) : 0;
+    for (int yb = 0; yb < ww; yb += 4) {   // four rows per trip, loads before stores (memory latency, as above)
+      uint8_t v0[4], v1[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        const int i = i0 + 32 * u;
-        if (i < tot) {
-          const int y = i / ww, x = i - y * ww;
-          v[u] = L.img[(size_t)reflect101(y0 + y, L.h) * L.w + reflect101(x0 + x, L.w)];
-        }
+        const uint8_t* row = L.img + (size_t)reflect101(y0 + min(yb + u, ww - 1), L.h) * L.w;
+        v0[u] = row[c0];
+        v1[u] = row[c1];
       }
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        const int i = i0 + 32 * u;
-        if (i < tot) { const int y = i / ww, x = i - y * ww; s_win[y * pitch + x] = v[u]; }
+        if (yb + u < ww) {
+          if (lane < ww) s_win[(yb + u) * pitch + lane] = v0[u];
+          if (lane + 32 < ww) s_win[(yb + u) * pitch + lane + 32] = v1[u];
+        }
       }
     }
   }
@@ -378,23 +379,27 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
     // the (win+1)^2 derivative window (zero outside the image: derivBorder = BORDER_CONSTANT) goes to shared memory
     // row by row, then is interpolated IN PLACE: output (x, y) needs inputs (x..x+1, y..y+1), which no later output of
     // the raster order reads once this batch of 32 has loaded them
-    const int dw = win + 1, dtot = dw * dw;
-    for (int i0 = lane; i0 < dtot; i0 += 128) {   // flattened, four independent loads per lane in flight (see stage_window)
-      short2 v[4];
+    // four rows per trip, all eight loads (columns lane and lane + 32 of each row) issued before the first store: the copy is pure
+    // memory latency (a quarter of the kernel's stall samples sat on the single load of the row-by-row loop)
+    const int dw = win + 1;
+    const int X0 = ipx + lane, X1 = ipx + lane + 32;
+    const bool c0 = lane < dw && X0 >= 0 && X0 < I.w, c1 = lane + 32 < dw && X1 >= 0 && X1 < I.w;
+    for (int y0 = 0; y0 < dw; y0 += 4) {
+      short2 v0[4], v1[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        const int i = i0 + 32 * u;
-        v[u] = make_short2(0, 0);
-        if (i < dtot) {
-          const int y = i / dw, x = i - y * dw;
-          const int X = ipx + x, Y = ipy + y;
-          if (Y >= 0 && Y < I.h && X >= 0 && X < I.w) v[u] = __ldg(&I.der[(size_t)Y * I.w + X]);
-        }
+        const int Y = ipy + y0 + u;
+        const bool rowIn = y0 + u < dw && Y >= 0 && Y < I.h;
+        const short2* row = I.der + (size_t)(rowIn ? Y : 0) * I.w;
+        v0[u] = (rowIn && c0) ? __ldg(row + X0) : make_short2(0, 0);
+        v1[u] = (rowIn && c1) ? __ldg(row + X1) : make_short2(0, 0);
       }
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        const int i = i0 + 32 * u;
-        if (i < dtot) s_dI[i] = v[u];   // y * dw + x == i
+        if (y0 + u < dw) {
+          if (lane < dw) s_dI[(y0 + u) * dw + lane] = v0[u];
+          if (lane + 32 < dw) s_dI[(y0 + u) * dw + lane + 32] = v1[u];
+        }
       }
     }
     __syncwarp();
