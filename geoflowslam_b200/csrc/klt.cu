@@ -297,43 +297,20 @@ __device__ __forceinline__ unsigned stage_window(const LevelView& L, int x0, int
     const int wpr = pitch / 4;
     int r = 0, k = lane;
     while (k >= wpr) { k -= wpr; r++; }
-    const int tot = ww * wpr;
-    for (int i = lane; i < tot; i += 128) {   // four words per lane and trip, loads before stores
-      unsigned v[4];
-      int idx[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        idx[u] = (i + 32 * u < tot) ? r * wpr + k : -1;
-        if (idx[u] >= 0) {
-          const uint8_t* row = p0 + (size_t)r * L.w;
-          const unsigned* src = reinterpret_cast<const unsigned*>(row - (reinterpret_cast<size_t>(row) & 3));
-          v[u] = __ldg(src + k);
-        }
-        k += 32;
-        while (k >= wpr) { k -= wpr; r++; }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-        if (idx[u] >= 0) reinterpret_cast<unsigned*>(s_win)[idx[u]] = v[u];
+    for (int i = lane; i < ww * wpr; i += 32) {
+      const uint8_t* row = p0 + (size_t)r * L.w;
+      const unsigned* src = reinterpret_cast<const unsigned*>(row - (reinterpret_cast<size_t>(row) & 3));
+      reinterpret_cast<unsigned*>(s_win)[r * wpr + k] = __ldg(src + k);
+      k += 32;
+      while (k >= wpr) { k -= wpr; r++; }
     }
   } else {
     // rows outer, lanes over the columns: the reflected column of a lane is the same for every row
     const int c0 = lane < ww ? reflect101(x0 + lane, L.w) : 0, c1 = lane + 32 < ww ? reflect101(x0 + lane + 32, L.w) : 0;
-    for (int yb = 0; yb < ww; yb += 4) {   // four rows per trip, loads before stores (memory latency, as above)
-      uint8_t v0[4], v1[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const uint8_t* row = L.img + (size_t)reflect101(y0 + min(yb + u, ww - 1), L.h) * L.w;
-        v0[u] = row[c0];
-        v1[u] = row[c1];
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        if (yb + u < ww) {
-          if (lane < ww) s_win[(yb + u) * pitch + lane] = v0[u];
-          if (lane + 32 < ww) s_win[(yb + u) * pitch + lane + 32] = v1[u];
-        }
-      }
+    for (int y = 0; y < ww; y++) {
+      const uint8_t* row = L.img + (size_t)reflect101(y0 + y, L.h) * L.w;
+      if (lane < ww) s_win[y * pitch + lane] = row[c0];
+      if (lane + 32 < ww) s_win[y * pitch + lane + 32] = row[c1];
     }
   }
   __syncwarp();
@@ -379,27 +356,14 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
     // the (win+1)^2 derivative window (zero outside the image: derivBorder = BORDER_CONSTANT) goes to shared memory
     // row by row, then is interpolated IN PLACE: output (x, y) needs inputs (x..x+1, y..y+1), which no later output of
     // the raster order reads once this batch of 32 has loaded them
-    // four rows per trip, all eight loads (columns lane and lane + 32 of each row) issued before the first store: the copy is pure
-    // memory latency (a quarter of the kernel's stall samples sat on the single load of the row-by-row loop)
     const int dw = win + 1;
-    const int X0 = ipx + lane, X1 = ipx + lane + 32;
-    const bool c0 = lane < dw && X0 >= 0 && X0 < I.w, c1 = lane + 32 < dw && X1 >= 0 && X1 < I.w;
-    for (int y0 = 0; y0 < dw; y0 += 4) {
-      short2 v0[4], v1[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int Y = ipy + y0 + u;
-        const bool rowIn = y0 + u < dw && Y >= 0 && Y < I.h;
-        const short2* row = I.der + (size_t)(rowIn ? Y : 0) * I.w;
-        v0[u] = (rowIn && c0) ? __ldg(row + X0) : make_short2(0, 0);
-        v1[u] = (rowIn && c1) ? __ldg(row + X1) : make_short2(0, 0);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        if (y0 + u < dw) {
-          if (lane < dw) s_dI[(y0 + u) * dw + lane] = v0[u];
-          if (lane + 32 < dw) s_dI[(y0 + u) * dw + lane + 32] = v1[u];
-        }
+    for (int y = 0; y < dw; y++) {
+      const int Y = ipy + y;
+      const bool rowIn = Y >= 0 && Y < I.h;
+      const short2* row = I.der + (size_t)(rowIn ? Y : 0) * I.w;
+      for (int x = lane; x < dw; x += 32) {
+        const int X = ipx + x;
+        s_dI[y * dw + x] = (rowIn && X >= 0 && X < I.w) ? row[X] : make_short2(0, 0);
       }
     }
     __syncwarp();
