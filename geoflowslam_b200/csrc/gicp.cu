@@ -40,6 +40,7 @@ struct GicpDev {
   // other way round (track mode alternates, so last call's source is this call's target without being rebuilt).
   int cbase, cstep, swap;
   int inputAll;     // 1: every cloud's raw points come from the `src` array (track mode); 0: even clouds from `tgt`
+  int linPpt;       // source points per thread of k_linearize (GFS_GICP_LIN_PPT, 1..32)
   int cellOrder;    // 1: neighbour-search kernels take their queries in grid-cell order (rec[]), not in point order
   int octSorted;    // 1: k_cell_sort ran (an octant kernel is selected): k_cell_pack takes the cell's members from slotOf[]
   // per cloud (2 * pairs clouds; cloud 2p = target of pair p, 2p+1 = source)
@@ -584,6 +585,8 @@ static const int KNN_LIST = 16;    // candidates kept for the exact selection
 static const int KNN_CELLS = 48;   // occupied cells remembered per query, packed (start << 8 | count)
 static const int KNN_THREADS = 128;
 static const size_t KNN_SMEM = (size_t)KNN_THREADS * (KNN_LIST * 12 + KNN_CELLS * 4);
+static const int KS_LIST = 12, KS_CELLS = 28;   // k_knn_search: 256 bytes of lists per query, 32 KB per CTA (up to 7 CTAs per SM)
+static const size_t KS_SMEM = (size_t)KNN_THREADS * (KS_LIST * 12 + KS_CELLS * 4);
 
 // One flat loop over the records of cells[from..to), four records per trip: their eight 16-byte loads are issued
 // before the first one is used (the loop used to wait out a full L1 / L2 latency per record: 37 % of the kernel's
@@ -621,8 +624,9 @@ __device__ __forceinline__ void walk_cells(const Grid& g, double qx, double qy, 
   }
 }
 
-__device__ bool knn10_two_pass(const Grid& g, const int* box, int nPts, double cell, double qx, double qy, double qz,
-                               double* s_d, int* s_id, unsigned* s_cells, KnnAcc<KNN_K>& acc) {
+template <int LIST = KNN_LIST, int CELLS = KNN_CELLS>
+__device__ __forceinline__ bool knn10_two_pass(const Grid& g, const int* box, int nPts, double cell, double qx, double qy, double qz,
+                                               double* s_d, int* s_id, unsigned* s_cells, KnnAcc<KNN_K>& acc) {
   const ShellQuery q = make_shell_query(cell, qx, qy, qz);
   float top[KNN_K];
 #pragma unroll
@@ -638,7 +642,7 @@ __device__ bool knn10_two_pass(const Grid& g, const int* box, int nPts, double c
       const double lim = (double)top[KNN_K - 1];
       visit_shell(g, box, q, r, [&]() { return lim; },
                   [&](int cs, int cn) {
-                    if (nc < KNN_CELLS && cn < 256 && cs < (1 << 24)) s_cells[nc++ * KNN_THREADS] = ((unsigned)cs << 8) | (unsigned)cn;
+                    if (nc < CELLS && cn < 256 && cs < (1 << 24)) s_cells[nc++ * KNN_THREADS] = ((unsigned)cs << 8) | (unsigned)cn;
                     else overflow = true;
                   }, r == 1 ? cls : 0);
       walk_cells(g, qx, qy, qz, s_cells, from, nc, [&](double dd, int) {
@@ -661,11 +665,11 @@ __device__ bool knn10_two_pass(const Grid& g, const int* box, int nPts, double c
     const double rho = (double)top[KNN_K - 1];
     walk_cells(g, qx, qy, qz, s_cells, 0, nc, [&](double dd, int pi) {
       if (dd <= rho) {
-        if (cnt < KNN_LIST) { s_d[cnt * KNN_THREADS] = dd; s_id[cnt * KNN_THREADS] = pi; }
+        if (cnt < LIST) { s_d[cnt * KNN_THREADS] = dd; s_id[cnt * KNN_THREADS] = pi; }
         cnt++;
       }
     });
-    ok = cnt <= KNN_LIST;
+    ok = cnt <= LIST;
   }
   if (!ok) return grid_knn<KNN_K>(g, box, nPts, cell, qx, qy, qz, -1.0, acc);
   acc.init();
@@ -851,6 +855,59 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_cov(GicpDev D, int use_l
       store_knn(D, c, i, acc);
     }
   }
+}
+
+// ---- the same search, split from the covariance (GFS_GICP_KNN=2).  k_knn_cov holds 128 registers and 48 KB of lists per
+// CTA, so four CTAs (16 warps) share an SM and the search -- a chain of dependent loads -- waits with 37 % of the issue slots
+// used.  The search alone, with lists sized to what a query really needs (<= 27 cells of shells 0 and 1, 10 candidates + ties;
+// anything longer takes the shell-walk fallback as before), fits MINB CTAs; the covariance (the register-heavy 3x3
+// eigen-decomposition) runs afterwards from the stored neighbour lists, one thread per point.  Bit-identical results.
+template <int MINB, int LIST, int CELLS>
+__global__ void __launch_bounds__(KNN_THREADS, MINB) k_knn_search(GicpDev D) {
+  extern __shared__ __align__(16) unsigned char s_knn[];
+  double* s_d = reinterpret_cast<double*>(s_knn);
+  unsigned* s_cells = reinterpret_cast<unsigned*>(s_d + LIST * KNN_THREADS);
+  int* s_id = reinterpret_cast<int*>(s_cells + CELLS * KNN_THREADS);
+  const int c = cloud_of(D, blockIdx.y);
+  const int nPts = D.nDown[c];
+  const Grid g = make_grid(D, c);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((int)(blockIdx.x * blockDim.x) >= nPts) return;
+  const bool active = t < nPts;
+  // queries in grid-cell order (see k_knn_cov)
+  const int r = active ? t : 0;
+  const double2 a = __ldg(&g.rec[2 * (size_t)r]), b = __ldg(&g.rec[2 * (size_t)r + 1]);
+  double qx = a.x, qy = a.y, qz = b.x;
+  const int i = (int)__double_as_longlong(b.y);
+  KnnAcc<KNN_K> acc;
+  bool finished = true;
+  if (active)
+    finished = knn10_two_pass<LIST, CELLS>(g, D.cellBox + c * 6, nPts, D.cell, qx, qy, qz, s_d + threadIdx.x, s_id + threadIdx.x,
+                                           s_cells + threadIdx.x, acc);
+  unsigned need = __ballot_sync(0xffffffffu, active && !finished);
+  while (need) {
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    warp_brute_knn<KNN_K>(g.pts, nPts, __shfl_sync(0xffffffffu, qx, src), __shfl_sync(0xffffffffu, qy, src),
+                          __shfl_sync(0xffffffffu, qz, src), src, acc);
+  }
+  if (active) store_knn(D, c, i, acc);   // missing neighbours (clouds with fewer than K points) keep the id 0x7fffffff
+}
+__global__ void __launch_bounds__(128) k_cov_nbr(GicpDev D) {
+  const int c = cloud_of(D, blockIdx.y);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D.nDown[c]) return;
+  const Grid g = make_grid(D, c);
+  const int2* o = reinterpret_cast<const int2*>(D.nbr + ((size_t)c * D.nmax + i) * KNN_K);
+  KnnAcc<KNN_K> acc;
+  acc.found = 0;
+#pragma unroll
+  for (int k = 0; k < KNN_K / 2; k++) {
+    const int2 v = o[k];
+    acc.id[2 * k] = v.x; acc.id[2 * k + 1] = v.y;
+    acc.found += (v.x != 0x7fffffff) + (v.y != 0x7fffffff);
+  }
+  cov_from_knn(g, acc, D.cov + ((size_t)c * D.nmax + i) * 6);
 }
 
 // ---- cell-centric exact 10-NN + covariance.
@@ -1211,23 +1268,51 @@ __global__ void __launch_bounds__(128) k_knn_select_cov(GicpDev D) {
 }
 
 // ---- block reduction of NV doubles per thread into out[NV] (fixed order: lanes, then warps)
+// Warp sums of NV (<= 32) per-lane values by recursive halving: in the step with offset o a lane keeps one half of its
+// remaining values and hands the other half to lane ^ o, so the whole vector costs 16 + 8 + 4 + 2 + 1 = 31 shuffles of a
+// double instead of 5 per value (145 for the 29 sums of k_linearize, which made the kernel shuffle-bound: one 32-lane
+// shuffle per clock and SM).  Lane l returns the total of v[l] (l < NV); the summation tree is fixed: (l, l^16), ^8, ... ^1.
+template <int NV>
+__device__ __forceinline__ double warp_reduce_vec(const double (&in)[NV]) {
+  static_assert(NV <= 32, "one value per lane");
+  const int lane = threadIdx.x & 31;
+  double v[32];
+#pragma unroll
+  for (int k = 0; k < 32; k++) v[k] = k < NV ? in[k] : 0.0;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int k = 0; k < o; k++) {
+      const double send = upper ? v[k] : v[k + o];
+      const double keep = upper ? v[k + o] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
 template <int NV, int THREADS>
 __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* out) {
   __shared__ double s_red[THREADS / 32][NV];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if constexpr (NV < 7) {  // 5 shuffles per value beat the 31 of the halving scheme
 #pragma unroll
-  for (int k = 0; k < NV; k++) {
-    double x = v[k];
+    for (int k = 0; k < NV; k++) {
+      double x = v[k];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-    if (lane == 0) s_red[warp][k] = x;
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (lane == 0) s_red[warp][k] = x;
+    }
+  } else {
+    const double x = warp_reduce_vec<NV>(v);
+    if (lane < NV) s_red[warp][lane] = x;
   }
   __syncthreads();
   if (threadIdx.x < NV) {
-    double x = 0;
+    double t = 0;
 #pragma unroll
-    for (int w = 0; w < THREADS / 32; w++) x += s_red[w][threadIdx.x];
-    out[threadIdx.x] = x;
+    for (int w = 0; w < THREADS / 32; w++) t += s_red[w][threadIdx.x];
+    out[threadIdx.x] = t;
   }
 }
 
@@ -1647,14 +1732,18 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D) {
   if (!D.istate[p * LM_ISTATE + I_ACTIVE] || D.istate[p * LM_ISTATE + I_NEED]) return;
   const int ct = tgt_cloud(D, p), cs = src_cloud(D, p);
   const int ns = D.nDown[cs];
-  const int nbp = max((ns + LIN_THREADS - 1) / LIN_THREADS, 1);  // participating blocks (block 0 always: an empty cloud still steps)
+  const int PPT = D.linPpt;
+  const int nbp = max((ns + LIN_THREADS * PPT - 1) / (LIN_THREADS * PPT), 1);  // participating blocks (block 0 always: an empty cloud still steps)
   if ((int)blockIdx.x >= nbp) return;
-  const int i = blockIdx.x * LIN_THREADS + threadIdx.x;
   double acc[RED_N];
 #pragma unroll
   for (int k = 0; k < RED_N; k++) acc[k] = 0.0;
-  if (i < ns) {
-    const double* T = D.state + (size_t)p * LM_STATE + S_T;
+  const double* T = D.state + (size_t)p * LM_STATE + S_T;
+  // PPT points per thread, LIN_THREADS apart (coalesced), summed in that order before the warp reduction
+#pragma unroll 1
+  for (int j = 0; j < PPT; j++) {
+    const int i = (blockIdx.x * PPT + j) * LIN_THREADS + threadIdx.x;
+    if (i >= ns) break;
     const double* ps = D.pts + ((size_t)cs * D.nmax + i) * 4;
     double q[3];
     xform(T, ps, q);
@@ -1706,11 +1795,11 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D) {
 #pragma unroll
       for (int a = 0; a < 6; a++)
 #pragma unroll
-        for (int b = a; b < 6; b++) acc[n++] = J[0][a] * MJ[0][b] + J[1][a] * MJ[1][b] + J[2][a] * MJ[2][b];
+        for (int b = a; b < 6; b++) acc[n++] += J[0][a] * MJ[0][b] + J[1][a] * MJ[1][b] + J[2][a] * MJ[2][b];
 #pragma unroll
-      for (int a = 0; a < 6; a++) acc[21 + a] = J[0][a] * Mr[0] + J[1][a] * Mr[1] + J[2][a] * Mr[2];
-      acc[27] = 0.5 * (res[0] * Mr[0] + res[1] * Mr[1] + res[2] * Mr[2]);
-      acc[28] = 1.0;
+      for (int a = 0; a < 6; a++) acc[21 + a] += J[0][a] * Mr[0] + J[1][a] * Mr[1] + J[2][a] * Mr[2];
+      acc[27] += 0.5 * (res[0] * Mr[0] + res[1] * Mr[1] + res[2] * Mr[2]);
+      acc[28] += 1.0;
     }
   }
   // per-warp partial sums (no block barrier: a warp whose lanes all found their neighbour quickly retires
@@ -1718,13 +1807,8 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D) {
   {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* out = D.partial + (((size_t)p * D.nblk + blockIdx.x) * (LIN_THREADS / 32) + warp) * RED_N;
-#pragma unroll
-    for (int k = 0; k < RED_N; k++) {
-      double x = acc[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-      if (lane == 0) out[k] = x;
-    }
+    const double x = warp_reduce_vec<RED_N>(acc);
+    if (lane < RED_N) out[lane] = x;
   }
   if (last_block_of_pair(D, p, 0, nbp)) lm_begin_block(D, p);
 }
@@ -1857,7 +1941,8 @@ __device__ void lm_begin_block(const GicpDev& D, int p) {
   const int iter = is[I_OUTER];
   double* st = D.state + (size_t)p * LM_STATE;
   // fixed-order sum of the per-warp partials: thread t takes partials t, t+128, ...; then lanes, then warps
-  const int nw = max((D.nDown[src_cloud(D, p)] + LIN_THREADS - 1) / LIN_THREADS, 1) * (LIN_THREADS / 32);
+  const int per = LIN_THREADS * D.linPpt;
+  const int nw = max((D.nDown[src_cloud(D, p)] + per - 1) / per, 1) * (LIN_THREADS / 32);
   double acc[RED_N];
 #pragma unroll
   for (int k = 0; k < RED_N; k++) acc[k] = 0.0;
@@ -1983,8 +2068,9 @@ struct GfsGicp {
   int nnMode = 7;        // GFS_GICP_NN: 0 = k_nn_corr (shell walk), 1 = k_nn_corr2 (ball walk, fp64), 2 = + float32 prefilter, 3 = ball walk over octants
                          // (fp64), 4 = octants + float32 prefilter, 5 = ball walk with the seven-cell fast path (fp64), 6 = 5 + float32 prefilter, 7 = neighbours of the old correspondence first,
                          // certified by the 10-NN radius, ball walk for the compacted rest (default)
-  int knnMode = 0;       // GFS_GICP_KNN: 0 = k_knn_cov (thread per query; default, measured fastest), 1 = k_knn_cov_warp (warp per cell, octant
-                         // skipping) + k_knn_cov for what it hands over
+  int knnMode = 2;       // GFS_GICP_KNN: 2 = k_knn_search + k_cov_nbr (search split from the covariance, 6 CTAs per SM; default, measured
+                         // fastest; 3 / 4 / 5 = the same at 7 / 5 / 4 CTAs), 0 = k_knn_cov (thread per query, search + covariance in one
+                         // kernel), 1 = k_knn_cov_warp (warp per cell, octant skipping) + k_knn_cov for what it hands over
   int trackCalls = 0;    // gfs_gicp_track_*: calls since the last reset (the new cloud goes to slot trackCalls & 1)
   int trackSeqs = 0;
   // optional per-stage CUDA-event timing of one call (gfs_gicp_set_profiling): an event after every stage, read back at
@@ -2053,6 +2139,8 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   int rc = gfs_device_check();
   if (rc) return rc;
   GFS_CUDA(cudaFuncSetAttribute(k_knn_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KNN_SMEM));
+  GFS_CUDA(cudaFuncSetAttribute(k_knn_search<6, KS_LIST, KS_CELLS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  GFS_CUDA(cudaFuncSetAttribute(k_knn_search<7, KS_LIST, KS_CELLS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   GFS_CUDA(cudaFuncSetAttribute(k_knn_cov_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KC_SMEM));
   GFS_CUDA(cudaFuncSetAttribute(k_knn_cov_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KW_SMEM));
   GfsGicp* h = new GfsGicp();
@@ -2078,6 +2166,8 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   D.nnBoundA = (float)(1.2 * 2.0 * 1.7320508 * 5.9604645e-8 * (2.0 * D.cell + s.max_correspondence_distance));
   D.cbase = 0; D.cstep = 1; D.swap = 0; D.inputAll = 0;
   D.cellOrder = 1;
+  D.linPpt = 8;
+  if (const char* e = getenv("GFS_GICP_LIN_PPT")) { const int v = atoi(e); D.linPpt = v < 1 ? 1 : (v > 32 ? 32 : v); }
   if (const char* e = getenv("GFS_GICP_ORDER")) D.cellOrder = atoi(e) != 0;  // 0: queries in point order (first generation)
   if (const char* e = getenv("GFS_GICP_NN")) h->nnMode = atoi(e);
   if (const char* e = getenv("GFS_GICP_KNN")) h->knnMode = atoi(e);
@@ -2192,6 +2282,14 @@ static int preprocess_clouds(GfsGicp* h, const GicpDev& D, cudaStream_t st, int 
     k_knn_select_cov<<<dim3(div_up(D.nmax, 128), clouds), 128, 0, st>>>(D);
     k_knn_cov<<<dim3(8, clouds), KNN_THREADS, KNN_SMEM, st>>>(D, 1);
     h->launches += 2;
+  } else if (h->knnMode >= 2 && !h->cellKnn && D.cellOrder) {
+    const dim3 gk(div_up(D.nmax, KNN_THREADS), clouds);
+    if (h->knnMode == 2) k_knn_search<6, KS_LIST, KS_CELLS><<<gk, KNN_THREADS, KS_SMEM, st>>>(D);
+    else if (h->knnMode == 3) k_knn_search<7, KS_LIST, KS_CELLS><<<gk, KNN_THREADS, KS_SMEM, st>>>(D);
+    else if (h->knnMode == 4) k_knn_search<5, KS_LIST, KS_CELLS><<<gk, KNN_THREADS, KS_SMEM, st>>>(D);
+    else k_knn_search<4, KS_LIST, KS_CELLS><<<gk, KNN_THREADS, KS_SMEM, st>>>(D);
+    k_cov_nbr<<<dim3(div_up(D.nmax, 128), clouds), 128, 0, st>>>(D);
+    h->launches += 1;
   } else if (!h->cellKnn) {
     k_knn_cov<<<dim3(div_up(D.nmax, KNN_THREADS), clouds), KNN_THREADS, KNN_SMEM, st>>>(D, 0);
   } else {
@@ -2230,7 +2328,7 @@ static int optimize_pairs(GfsGicp* h, const GicpDev& D, cudaStream_t st, int pai
     else if (h->nnMode == 6) k_nn_corr2<true, false, true><<<gn, NN_THREADS, 0, st>>>(D);
     else k_nn_corr3<<<gn, NN_THREADS, 0, st>>>(D);
     prof_mark(h, st, ST_NN);
-    k_linearize<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D);   // + the pair's LM begin in its last block
+    k_linearize<<<dim3(div_up(D.nblk, D.linPpt), pairs), LIN_THREADS, 0, st>>>(D);   // + the pair's LM begin in its last block
     prof_mark(h, st, ST_LIN);
     const bool check = round >= nextCheck;
     if (check) GFS_CUDA(cudaMemsetAsync(D.counters, 0, 8, st));

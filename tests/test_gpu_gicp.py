@@ -106,7 +106,8 @@ def test_search_variants_are_bit_identical(monkeypatch):
     tg = np.pad(tg, ((0, 0), (0, stride - tg.shape[1]), (0, 0))); sr = np.pad(sr, ((0, 0), (0, stride - sr.shape[1]), (0, 0)))
     T0 = np.tile(np.eye(4), (3, 1, 1))
     out = {}
-    variants = ((0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 2, 0), (0, 2, 0), (1, 3, 1), (1, 4, 1), (0, 3, 1), (1, 1, 1), (1, 5, 0), (1, 6, 0), (0, 5, 1), (1, 7, 0), (0, 7, 0), (1, 7, 1))
+    variants = ((0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 2, 0), (0, 2, 0), (1, 3, 1), (1, 4, 1), (0, 3, 1), (1, 1, 1), (1, 5, 0), (1, 6, 0), (0, 5, 1), (1, 7, 0), (0, 7, 0), (1, 7, 1),
+                (1, 7, 2), (1, 7, 3), (1, 5, 4), (1, 7, 5))
     for order, nn, knn in variants:
         monkeypatch.setenv("GFS_GICP_ORDER", str(order)); monkeypatch.setenv("GFS_GICP_NN", str(nn)); monkeypatch.setenv("GFS_GICP_KNN", str(knn))
         reg = RegistrationGICP(max_points=stride, max_pairs=3)
@@ -132,13 +133,13 @@ def test_dense_and_sparse_clouds_take_the_hand_over_paths(monkeypatch):
     sparse_t, sparse_s = t[::40].copy(), s_[::40].copy()
     for cloud_t, cloud_s, kw in ((t, s_, dict(downsampling_resolution=0.005)), (sparse_t, sparse_s, {})):
         res = {}
-        for knn in (0, 1):
+        for knn in (0, 1, 2, 3):
             monkeypatch.setenv("GFS_GICP_KNN", str(knn))
             reg = RegistrationGICP(max_points=32768, max_pairs=1, **kw)
             r = reg.RegisterPointClouds(cloud_t, cloud_s)
             res[knn] = (r["T"].tobytes(), r["iterations"], r["num_inliers"], reg.cloud(0)[1].tobytes(), reg.cloud(1)[1].tobytes())
             reg.close()
-        assert res[0] == res[1]
+        assert res[0] == res[1] == res[2] == res[3]
 
 
 def test_track_mode_equals_pairwise_align():
