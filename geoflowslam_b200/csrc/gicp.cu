@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 
+#include <type_traits>
 namespace gfs {
 
 static const unsigned long long KEY_EMPTY = 0xffffffffffffffffull;
@@ -43,6 +44,12 @@ struct GicpDev {
   int linPpt;       // source points per thread of k_linearize (GFS_GICP_LIN_PPT, 1..32)
   int cellOrder;    // 1: neighbour-search kernels take their queries in grid-cell order (rec[]), not in point order
   int octSorted;    // 1: k_cell_sort ran (an octant kernel is selected): k_cell_pack takes the cell's members from slotOf[]
+  int dense;        // 1: the k-NN grid is the dense sorted grid (dS / cellBox = its region), 0: the hash grid (tab)
+  int dcap, daxis;  // dense grid: cells per cloud it can hold, per-axis limit applied when a cloud's box would not fit
+  int dstride;      // dcap + 4: entries between two clouds' arrays (a multiple of 4: every array starts 16-byte aligned)
+  unsigned* dS;               // [clouds][dstride] dense grid: first record of every cell of the region, x fastest (an exclusive
+                              // prefix sum of the cell populations: a run of cells xa..xb of one row is records S[xa] .. S[xb + 1])
+  unsigned long long* dSum;   // [clouds][3] sum of the points' cell coordinates (centres the region of an oversized cloud)
   // per cloud (2 * pairs clouds; cloud 2p = target of pair p, 2p+1 = source)
   unsigned long long* keys;  // [clouds][hsize]
   int* minIdx;               // [clouds][hsize]
@@ -398,7 +405,8 @@ __device__ __forceinline__ bool grid_find_slot(const Grid& g, int cx, int cy, in
   }
 }
 // record -> squared distance to the query and the point index
-__device__ __forceinline__ double rec_sqdist(const Grid& g, int r, double qx, double qy, double qz, int& index) {
+template <class G>
+__device__ __forceinline__ double rec_sqdist(const G& g, int r, double qx, double qy, double qz, int& index) {
   const double2 a = __ldg(&g.rec[2 * (size_t)r]), b = __ldg(&g.rec[2 * (size_t)r + 1]);
   index = (int)__double_as_longlong(b.y);
   // Eigen Vector4d::squaredNorm with SSE2 packets: (dx^2 + dz^2) + dy^2
@@ -439,8 +447,8 @@ struct KnnAcc {
   }
 };
 
-template <int K>
-__device__ __forceinline__ void scan_cell(const Grid& g, int s, int n, double qx, double qy, double qz, KnnAcc<K>& acc) {
+template <int K, class G>
+__device__ __forceinline__ void scan_cell(const G& g, int s, int n, double qx, double qy, double qz, KnnAcc<K>& acc) {
   for (int j = 0; j < n; j++) {
     int pi;
     const double d = rec_sqdist(g, s + j, qx, qy, qz, pi);
@@ -516,15 +524,266 @@ __device__ __forceinline__ bool box_covered(const int* box, const ShellQuery& q,
          q.cz + r >= box[5];
 }
 
+// ---- dense sorted grid (GFS_GICP_GRID=1, the default for the default kernels).
+// The hash grid costs a query 27 dependent probes (mix64, a 16-byte slot from a 1 MB table, key compare) for the 27 cells around
+// it, about 60 % of them empty, and a cell's records lie wherever the cell was first seen.  Depth-camera clouds fit a box of a
+// few hundred thousand 0.11 m cells, so the grid can simply be an array over that box: S[cell] = index of the cell's first
+// record, cells numbered x-fastest and the records stored in that order (S is the exclusive prefix sum of the cell
+// populations, k_dense_*).  A lookup is one 4-byte load, and -- the point of sorting -- the cells xa..xb of one row are ONE
+// contiguous run of records S[xa] .. S[xb + 1]: the 27-cell neighbourhood is 9 runs, found with 18 loads from 9 sectors.
+// A cloud whose box exceeds the array (outliers far away) keeps a region of at most `daxis` cells per axis around its mean cell;
+// points AND queries outside are clamped into the region's border cells.  That keeps every bound valid: a border cell then
+// also holds points beyond its outer face, which are farther from any query inside the region than the face the bounds are
+// computed from, and a clamped query sits in the border cell with an offset outside [0, cell) -- its margin is 0 and the gaps to
+// the inner cells are its true distances to their faces.  (Any cell assignment gives the same exact result; only speed differs.)
+struct DGrid {
+  const unsigned* S;
+  const double2* rec;
+  const double* pts;
+  int ox, oy, oz, nx, ny, nz;
+};
+__device__ __forceinline__ DGrid make_dgrid(const GicpDev& D, int c) {
+  DGrid g;
+  g.S = D.dS + (size_t)c * (size_t)D.dstride;
+  g.rec = reinterpret_cast<const double2*>(D.rec + (size_t)c * D.nmax * 4);
+  g.pts = D.pts + (size_t)c * D.nmax * 4;
+  const int* box = D.cellBox + c * 6;
+  g.ox = box[0]; g.oy = box[1]; g.oz = box[2];
+  g.nx = box[3] - box[0] + 1; g.ny = box[4] - box[1] + 1; g.nz = box[5] - box[2] + 1;
+  return g;
+}
+// cell coordinate of a point along one axis, clamped into [lo, hi] (saturating: any finite or infinite input is fine)
+__device__ __forceinline__ int dense_coord(double v, double inv, int lo, int hi) {
+  const double t = fmin(fmax(v * inv, -2.0e6), 2.0e6);
+  const int c = fast_floor_d(t) + (1 << 20);
+  return min(max(c, lo), hi);
+}
+__device__ __forceinline__ ShellQuery make_shell_query(const DGrid& g, double cell, double qx, double qy, double qz) {
+  ShellQuery s;
+  const double inv = 1.0 / cell;
+  const int off = 1 << 20;
+  s.cx = dense_coord(qx, inv, g.ox, g.ox + g.nx - 1); s.cy = dense_coord(qy, inv, g.oy, g.oy + g.ny - 1);
+  s.cz = dense_coord(qz, inv, g.oz, g.oz + g.nz - 1);
+  s.fx = qx - (double)(s.cx - off) * cell; s.fy = qy - (double)(s.cy - off) * cell; s.fz = qz - (double)(s.cz - off) * cell;
+  s.cell = cell;
+  const double m = fmin(fmin(s.fx, cell - s.fx), fmin(fmin(s.fy, cell - s.fy), fmin(s.fz, cell - s.fz)));
+  s.margin = fmax(m, 0.0) * 0.999999;
+  return s;
+}
+__device__ __forceinline__ ShellQuery make_shell_query(const Grid&, double cell, double qx, double qy, double qz) {
+  return make_shell_query(cell, qx, qy, qz);
+}
+// records of the cells xa..xb (inside the region) of row (y, z)
+__device__ __forceinline__ void dense_run(const DGrid& g, int y, int z, int xa, int xb, int& start, int& count) {
+  const unsigned* row = g.S + ((size_t)(z - g.oz) * g.ny + (size_t)(y - g.oy)) * g.nx;
+  const unsigned a = __ldg(row + (xa - g.ox)), b = __ldg(row + (xb - g.ox + 1));
+  start = (int)a; count = (int)(b - a);
+}
+// visit_shell for the dense grid: visit(first record, count) once per ROW of the shell.  rows > 0 (only meaningful for r == 1):
+// only the rows with exactly rows - 1 non-zero offsets in (y, z) -- 1 = the query's own row (its two end cells), 2 = the four
+// rows next to it, 3 = the four diagonal rows -- so that the caller can tighten limit() in between.
+template <class Limit, class Visit>
+__device__ __forceinline__ void visit_shell(const DGrid& g, const int*, const ShellQuery& q, int r, Limit limit, Visit visit, int rows = 0) {
+  const int x0 = max(q.cx - r, g.ox), x1 = min(q.cx + r, g.ox + g.nx - 1);
+  const int y0 = max(q.cy - r, g.oy), y1 = min(q.cy + r, g.oy + g.ny - 1);
+  const int z0 = max(q.cz - r, g.oz), z1 = min(q.cz + r, g.oz + g.nz - 1);
+  for (int z = z0; z <= z1; z++) {
+    const double gz2 = axis_gap2(z - q.cz, q.fz, q.cell);
+    if (gz2 > limit()) continue;
+    for (int y = y0; y <= y1; y++) {
+      if (rows && (z != q.cz) + (y != q.cy) != rows - 1) continue;
+      const double gyz2 = gz2 + axis_gap2(y - q.cy, q.fy, q.cell);
+      if (gyz2 > limit()) continue;
+      const bool face = (z == q.cz - r) || (z == q.cz + r) || (y == q.cy - r) || (y == q.cy + r);
+      int cs, cn;
+      if (face) {
+        // the gap grows with |x - cx|: the cells that survive pruning are one run around cx
+        int xa = x0, xb = x1;
+        while (xa < q.cx && gyz2 + axis_gap2(xa - q.cx, q.fx, q.cell) > limit()) xa++;
+        while (xb > q.cx && gyz2 + axis_gap2(xb - q.cx, q.fx, q.cell) > limit()) xb--;
+        dense_run(g, y, z, xa, xb, cs, cn);
+        if (cn) visit(cs, cn);
+      } else {
+        if (q.cx - r >= x0 && !(gyz2 + axis_gap2(-r, q.fx, q.cell) > limit())) {
+          dense_run(g, y, z, q.cx - r, q.cx - r, cs, cn);
+          if (cn) visit(cs, cn);
+        }
+        if (r > 0 && q.cx + r <= x1 && !(gyz2 + axis_gap2(r, q.fx, q.cell) > limit())) {
+          dense_run(g, y, z, q.cx + r, q.cx + r, cs, cn);
+          if (cn) visit(cs, cn);
+        }
+      }
+    }
+  }
+}
+__device__ __forceinline__ bool box_covered(const DGrid& g, const int*, const ShellQuery& q, int r) {
+  return q.cx - r <= g.ox && q.cx + r >= g.ox + g.nx - 1 && q.cy - r <= g.oy && q.cy + r >= g.oy + g.ny - 1 && q.cz - r <= g.oz &&
+         q.cz + r >= g.oz + g.nz - 1;
+}
+__device__ __forceinline__ bool box_covered(const Grid&, const int* box, const ShellQuery& q, int r) { return box_covered(box, q, r); }
+
+// ---- dense sorted grid: construction (replaces the hash grouping of the downsampled points + k_cell_pack)
+__global__ void k_dense_init(GicpDev D, int clouds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= clouds) return;
+  const int c = cloud_of(D, i);
+  for (int k = 0; k < 3; k++) { D.cellBox[c * 6 + k] = 0x7fffffff; D.cellBox[c * 6 + 3 + k] = -0x7fffffff; D.dSum[c * 3 + k] = 0ull; }
+  D.nFall[c] = 0;
+}
+// bounding box (in cells) and coordinate sums of every cloud
+__global__ void __launch_bounds__(256) k_dense_box(GicpDev D) {
+  const int c = cloud_of(D, blockIdx.y), i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = D.nDown[c];
+  if ((int)(blockIdx.x * blockDim.x) >= n) return;
+  int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {-0x7fffffff, -0x7fffffff, -0x7fffffff};
+  unsigned long long sum[3] = {0ull, 0ull, 0ull};
+  if (i < n) {
+    const double* p = D.pts + ((size_t)c * D.nmax + i) * 4;
+    const double inv = 1.0 / D.cell;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const int v = dense_coord(p[k], inv, 0, (1 << 21) - 1);
+      lo[k] = v; hi[k] = v; sum[k] = (unsigned long long)v;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[k] = min(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+      hi[k] = max(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+      sum[k] += __shfl_xor_sync(0xffffffffu, sum[k], o);
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      atomicMin(&D.cellBox[c * 6 + k], lo[k]);
+      atomicMax(&D.cellBox[c * 6 + 3 + k], hi[k]);
+      atomicAdd(&D.dSum[c * 3 + k], sum[k]);
+    }
+  }
+}
+// one CTA per cloud: fix the region (the box, or `daxis` cells per oversized axis around the mean cell) and clear its counters
+__global__ void __launch_bounds__(1024) k_dense_region(GicpDev D) {
+  __shared__ long long s_vol;
+  const int c = cloud_of(D, blockIdx.x);
+  if (threadIdx.x == 0) {
+    int* box = D.cellBox + c * 6;
+    const int n = D.nDown[c];
+    int lo[3], hi[3];
+    for (int k = 0; k < 3; k++) { lo[k] = n > 0 ? box[k] : 0; hi[k] = n > 0 ? box[3 + k] : 0; }
+    long long vol = 1;
+    for (int k = 0; k < 3; k++) vol *= (long long)(hi[k] - lo[k] + 1);
+    if (vol > (long long)D.dcap) {
+      for (int k = 0; k < 3; k++) {
+        if (hi[k] - lo[k] + 1 <= D.daxis) continue;
+        const int mean = (int)(D.dSum[c * 3 + k] / (unsigned long long)n);
+        const int l = min(max(mean - D.daxis / 2, lo[k]), hi[k] - D.daxis + 1);
+        lo[k] = l; hi[k] = l + D.daxis - 1;
+      }
+      vol = 1;
+      for (int k = 0; k < 3; k++) vol *= (long long)(hi[k] - lo[k] + 1);
+    }
+    for (int k = 0; k < 3; k++) { box[k] = lo[k]; box[3 + k] = hi[k]; }
+    s_vol = vol;
+  }
+  __syncthreads();
+  unsigned* S = D.dS + (size_t)c * (size_t)D.dstride;
+  const long long vol = s_vol;
+  for (long long j = threadIdx.x; j <= vol; j += blockDim.x) S[j] = 0u;
+}
+// population of every cell; a point remembers its cell (slotOf) and its arrival number inside it (members)
+__global__ void __launch_bounds__(256) k_dense_count(GicpDev D) {
+  const int c = cloud_of(D, blockIdx.y), i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D.nDown[c]) return;
+  const int* box = D.cellBox + c * 6;
+  const int ox = box[0], oy = box[1], oz = box[2], nx = box[3] - box[0] + 1, ny = box[4] - box[1] + 1;
+  const double* p = D.pts + ((size_t)c * D.nmax + i) * 4;
+  const double inv = 1.0 / D.cell;
+  const int cx = dense_coord(p[0], inv, ox, box[3]), cy = dense_coord(p[1], inv, oy, box[4]), cz = dense_coord(p[2], inv, oz, box[5]);
+  const int idx = ((cz - oz) * ny + (cy - oy)) * nx + (cx - ox);
+  unsigned* S = D.dS + (size_t)c * (size_t)D.dstride;
+  D.slotOf[(size_t)c * D.nmax + i] = idx;
+  D.members[(size_t)c * D.nmax + i] = (int)atomicAdd(&S[idx], 1u);
+}
+// one CTA per cloud: exclusive prefix sum of the populations, in place, 4096 cells per trip (uint4 per thread); S[vol] = n
+__global__ void __launch_bounds__(1024) k_dense_scan(GicpDev D) {
+  __shared__ unsigned s_w[32];
+  __shared__ unsigned s_carry;
+  const int c = cloud_of(D, blockIdx.x);
+  const int* box = D.cellBox + c * 6;
+  const long long vol = (long long)(box[3] - box[0] + 1) * (box[4] - box[1] + 1) * (box[5] - box[2] + 1);
+  unsigned* S = D.dS + (size_t)c * (size_t)D.dstride;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0u;
+  __syncthreads();
+  for (long long base = 0; base < vol; base += 4096) {
+    const long long j = base + 4 * (long long)tid;
+    unsigned v[4];
+    if (j + 3 < vol) {
+      const uint4 t = *reinterpret_cast<const uint4*>(S + j);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; u++) v[u] = (j + u < vol) ? S[j + u] : 0u;
+    }
+    const unsigned own = v[0] + v[1] + v[2] + v[3];
+    unsigned incl = own;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = s_w[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      s_w[lane] = w;   // inclusive over warps
+    }
+    __syncthreads();
+    unsigned run = s_carry + (warp ? s_w[warp - 1] : 0u) + incl - own;
+    if (j + 3 < vol) {
+      *reinterpret_cast<uint4*>(S + j) = make_uint4(run, run + v[0], run + v[0] + v[1], run + v[0] + v[1] + v[2]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (j + u < vol) S[j + u] = run;
+        run += v[u];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_carry += s_w[31];
+    __syncthreads();
+  }
+  if (tid == 0) { S[vol] = s_carry; D.nCells[c] = 0; }
+}
+// the points again, in cell order {x, y, z, index bits}
+__global__ void __launch_bounds__(256) k_dense_fill(GicpDev D) {
+  const int c = cloud_of(D, blockIdx.y), i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D.nDown[c]) return;
+  const unsigned* S = D.dS + (size_t)c * (size_t)D.dstride;
+  const size_t pos = (size_t)c * D.nmax + S[D.slotOf[(size_t)c * D.nmax + i]] + (unsigned)D.members[(size_t)c * D.nmax + i];
+  const double2* p = reinterpret_cast<const double2*>(D.pts + ((size_t)c * D.nmax + i) * 4);
+  double2* o = reinterpret_cast<double2*>(D.rec + pos * 4);
+  o[0] = p[0];
+  o[1] = make_double2(p[1].x, __longlong_as_double((long long)i));
+}
+
 // Exact k-NN: shells of grid cells around the query until the k-th distance is provably final,
 // brute force over the cloud beyond MAX_SHELL.  If max_r2 >= 0 the search may stop as soon as no
 // unvisited point can be closer than sqrt(max_r2) (bounded 1-NN for correspondences).
 static const int MAX_SHELL = 8;
-template <int K>
-__device__ bool grid_knn(const Grid& g, const int* box, int nPts, double cell, double qx, double qy, double qz,
+template <int K, class G>
+__device__ bool grid_knn(const G& g, const int* box, int nPts, double cell, double qx, double qy, double qz,
                          double max_r2, KnnAcc<K>& acc, bool seeded = false) {
   if (!seeded) acc.init();
-  const ShellQuery q = make_shell_query(cell, qx, qy, qz);
+  const ShellQuery q = make_shell_query(g, cell, qx, qy, qz);
   const double cap = max_r2 >= 0.0 ? max_r2 : DBL_MAX;
   for (int r = 0; r <= MAX_SHELL; r++) {
     visit_shell(g, box, q, r,
@@ -534,7 +793,7 @@ __device__ bool grid_knn(const Grid& g, const int* box, int nPts, double cell, d
     const double b2 = bound * bound;
     if (acc.found == K && acc.d[K - 1] <= b2) return true;
     if (max_r2 >= 0.0 && b2 >= max_r2) return true;
-    if (box_covered(box, q, r)) return true;
+    if (box_covered(g, box, q, r)) return true;
   }
   return false;  // far / sparse query: the caller finishes it by brute force over the cloud
 }
@@ -587,12 +846,14 @@ static const int KNN_THREADS = 128;
 static const size_t KNN_SMEM = (size_t)KNN_THREADS * (KNN_LIST * 12 + KNN_CELLS * 4);
 static const int KS_LIST = 12, KS_CELLS = 28;   // k_knn_search: 256 bytes of lists per query, 32 KB per CTA (up to 7 CTAs per SM)
 static const size_t KS_SMEM = (size_t)KNN_THREADS * (KS_LIST * 12 + KS_CELLS * 4);
+static const int KD_LIST = 12, KD_CELLS = 16;   // dense grid: a list entry is a ROW run (shells 0-1: at most 11), 208 bytes per query
+static const size_t KD_SMEM = (size_t)KNN_THREADS * (KD_LIST * 12 + KD_CELLS * 4);
 
 // One flat loop over the records of cells[from..to), four records per trip: their eight 16-byte loads are issued
 // before the first one is used (the loop used to wait out a full L1 / L2 latency per record: 37 % of the kernel's
 // stall samples).  body(squared distance, point index) is called in record order.
-template <class Body>
-__device__ __forceinline__ void walk_cells(const Grid& g, double qx, double qy, double qz, const unsigned* cells, int from, int to, Body body) {
+template <class G, class Body>
+__device__ __forceinline__ void walk_cells(const G& g, double qx, double qy, double qz, const unsigned* cells, int from, int to, Body body) {
   int ci = from - 1, r = 0, end = 0;
   auto next = [&]() -> int {
     while (r >= end) {
@@ -624,10 +885,10 @@ __device__ __forceinline__ void walk_cells(const Grid& g, double qx, double qy, 
   }
 }
 
-template <int LIST = KNN_LIST, int CELLS = KNN_CELLS>
-__device__ __forceinline__ bool knn10_two_pass(const Grid& g, const int* box, int nPts, double cell, double qx, double qy, double qz,
+template <int LIST = KNN_LIST, int CELLS = KNN_CELLS, class G = Grid>
+__device__ __forceinline__ bool knn10_two_pass(const G& g, const int* box, int nPts, double cell, double qx, double qy, double qz,
                                                double* s_d, int* s_id, unsigned* s_cells, KnnAcc<KNN_K>& acc) {
-  const ShellQuery q = make_shell_query(cell, qx, qy, qz);
+  const ShellQuery q = make_shell_query(g, cell, qx, qy, qz);
   float top[KNN_K];
 #pragma unroll
   for (int i = 0; i < KNN_K; i++) top[i] = FLT_MAX;
@@ -657,7 +918,7 @@ __device__ __forceinline__ bool knn10_two_pass(const Grid& g, const int* box, in
       });
     }
     const double bound = (double)r * cell + q.margin;
-    if ((seen >= KNN_K && (double)top[KNN_K - 1] <= bound * bound) || box_covered(box, q, r)) { ok = true; break; }
+    if ((seen >= KNN_K && (double)top[KNN_K - 1] <= bound * bound) || box_covered(g, box, q, r)) { ok = true; break; }
   }
   ok = ok && !overflow && seen >= KNN_K && top[KNN_K - 1] < FLT_MAX;
   int cnt = 0;
@@ -671,7 +932,7 @@ __device__ __forceinline__ bool knn10_two_pass(const Grid& g, const int* box, in
     });
     ok = cnt <= LIST;
   }
-  if (!ok) return grid_knn<KNN_K>(g, box, nPts, cell, qx, qy, qz, -1.0, acc);
+  if (!ok) return grid_knn<KNN_K, G>(g, box, nPts, cell, qx, qy, qz, -1.0, acc);
   acc.init();
   for (int j = 0; j < cnt; j++) acc.push(s_id[j * KNN_THREADS], s_d[j * KNN_THREADS]);
   return true;
@@ -862,7 +1123,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_cov(GicpDev D, int use_l
 // used.  The search alone, with lists sized to what a query really needs (<= 27 cells of shells 0 and 1, 10 candidates + ties;
 // anything longer takes the shell-walk fallback as before), fits MINB CTAs; the covariance (the register-heavy 3x3
 // eigen-decomposition) runs afterwards from the stored neighbour lists, one thread per point.  Bit-identical results.
-template <int MINB, int LIST, int CELLS>
+template <int MINB, int LIST, int CELLS, bool DENSE>
 __global__ void __launch_bounds__(KNN_THREADS, MINB) k_knn_search(GicpDev D) {
   extern __shared__ __align__(16) unsigned char s_knn[];
   double* s_d = reinterpret_cast<double*>(s_knn);
@@ -870,7 +1131,7 @@ __global__ void __launch_bounds__(KNN_THREADS, MINB) k_knn_search(GicpDev D) {
   int* s_id = reinterpret_cast<int*>(s_cells + CELLS * KNN_THREADS);
   const int c = cloud_of(D, blockIdx.y);
   const int nPts = D.nDown[c];
-  const Grid g = make_grid(D, c);
+  const auto g = [&] { if constexpr (DENSE) return make_dgrid(D, c); else return make_grid(D, c); }();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if ((int)(blockIdx.x * blockDim.x) >= nPts) return;
   const bool active = t < nPts;
@@ -1335,7 +1596,8 @@ struct Nn1 {
     if (dist < d || (dist == d && index < id)) { d = dist; id = index; }
   }
 };
-__device__ __forceinline__ void scan_cell_nn1(const Grid& g, int s, int n, double qx, double qy, double qz, Nn1& nn) {
+template <class G>
+__device__ __forceinline__ void scan_cell_nn1(const G& g, int s, int n, double qx, double qy, double qz, Nn1& nn) {
   for (int j = 0; j < n; j += 4) {
     double2 a[4], b[4];
 #pragma unroll
@@ -1486,6 +1748,70 @@ __device__ __forceinline__ void visit_ball(const Grid& g, const int* box, const 
   }
 }
 
+// visit_ball for the dense grid: visit(first record, count) once per row of the ball's bounding block
+template <bool FAST, class Limit, class Visit>
+__device__ __forceinline__ void visit_ball(const DGrid& g, const ShellQuery& q, Limit limit, Visit visit) {
+  int cs, cn;
+  dense_run(g, q.cy, q.cz, q.cx, q.cx, cs, cn);
+  if (cn) visit(cs, cn);
+  const double lim0 = limit();
+  if (lim0 <= q.margin * q.margin) return;  // the ball stays inside the home cell
+  const double R = sqrt(lim0) * 1.000001 + 1e-12, inv = 1.0 / q.cell;
+  const int xlo = g.ox, xhi = g.ox + g.nx - 1, ylo = g.oy, yhi = g.oy + g.ny - 1, zlo = g.oz, zhi = g.oz + g.nz - 1;
+  if (FAST && 2.0 * R < q.cell) {
+    // the ball reaches at most one neighbour per axis: four rows (own, y-step, z-step, both), in each the home column and / or
+    // the x-step column -- adjacent cells, one run
+    const int sx = (q.fx - R < 0.0) ? -1 : ((q.fx + R >= q.cell) ? 1 : 0), sy = (q.fy - R < 0.0) ? -1 : ((q.fy + R >= q.cell) ? 1 : 0),
+              sz = (q.fz - R < 0.0) ? -1 : ((q.fz + R >= q.cell) ? 1 : 0);
+    const double gx2 = axis_gap2(sx, q.fx, q.cell), gy2 = axis_gap2(sy, q.fy, q.cell), gz2 = axis_gap2(sz, q.fz, q.cell);
+    const bool xin = sx != 0 && q.cx + sx >= xlo && q.cx + sx <= xhi;
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      const bool uy = m & 1, uz = m & 2;
+      if ((uy && !sy) || (uz && !sz)) continue;
+      const double gyz2 = (uy ? gy2 : 0.0) + (uz ? gz2 : 0.0);
+      if (m && gyz2 > limit()) continue;
+      const int y = q.cy + (uy ? sy : 0), z = q.cz + (uz ? sz : 0);
+      if (y < ylo || y > yhi || z < zlo || z > zhi) continue;
+      const bool side = xin && !(gyz2 + gx2 > limit());
+      if (!m && !side) continue;
+      const int xa = m ? (side && sx < 0 ? q.cx - 1 : q.cx) : q.cx + sx, xb = m ? (side && sx > 0 ? q.cx + 1 : q.cx) : q.cx + sx;
+      dense_run(g, y, z, xa, xb, cs, cn);
+      if (cn) visit(cs, cn);
+    }
+    return;
+  }
+  // the ball's bounding block in cells, BOTH ends clamped into the region: a ball that lies beyond the region (a clamped query)
+  // maps to the border cells, which hold everything beyond
+  auto span = [&](int c, double f, int lo_, int hi_, int& a, int& b) {
+    const double lim = 3.0e6;
+    a = min(max(c + fast_floor_d(fmin(fmax((f - R) * inv, -lim), lim)), lo_), hi_);
+    b = min(max(c + fast_floor_d(fmin(fmax((f + R) * inv, -lim), lim)), lo_), hi_);
+  };
+  int x0, x1, y0, y1, z0, z1;
+  span(q.cx, q.fx, xlo, xhi, x0, x1);
+  span(q.cy, q.fy, ylo, yhi, y0, y1);
+  span(q.cz, q.fz, zlo, zhi, z0, z1);
+  for (int z = z0; z <= z1; z++) {
+    const double gz2 = axis_gap2(z - q.cz, q.fz, q.cell);
+    if (gz2 > limit()) continue;
+    for (int y = y0; y <= y1; y++) {
+      const double gyz2 = gz2 + axis_gap2(y - q.cy, q.fy, q.cell);
+      if (gyz2 > limit()) continue;
+      int xa = x0, xb = x1;
+      while (xa < q.cx && gyz2 + axis_gap2(xa - q.cx, q.fx, q.cell) > limit()) xa++;
+      while (xb > q.cx && gyz2 + axis_gap2(xb - q.cx, q.fx, q.cell) > limit()) xb--;
+      if (y == q.cy && z == q.cz) {  // the home cell was visited first: the runs on either side of it
+        if (xa < q.cx) { dense_run(g, y, z, xa, min(q.cx - 1, xb), cs, cn); if (cn) visit(cs, cn); }
+        if (xb > q.cx) { dense_run(g, y, z, max(q.cx + 1, xa), xb, cs, cn); if (cn) visit(cs, cn); }
+      } else {
+        dense_run(g, y, z, xa, xb, cs, cn);
+        if (cn) visit(cs, cn);
+      }
+    }
+  }
+}
+
 // The octants of cell (x, y, z) a ball of squared radius lim around the query can reach, as an 8-bit mask (bit o = octant o of
 // k_cell_sort).  Per axis the lower half [0, cell/2) and the upper half [cell/2, cell) of the cell are tested against
 // [l - R, l + R] (l = query coordinate relative to the cell's origin, R inflated by 1e-6 relative + 1e-9: the octant of a
@@ -1611,18 +1937,23 @@ __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr2(GicpDev D) {
 // walk runs at 13 active lanes).  Queries without a certificate -- first round, no previous correspondence, large residuals, a big
 // step of the optimiser -- are COMPACTED inside the block and searched with the ball walk by the first lanes of the block, so
 // the slow path is executed by full warps and only as many of them as needed.  The result is the exact search's, bit for bit.
-__device__ __forceinline__ void nn1_ball_search(const GicpDev& D, const Grid& g, const int* box, const double q[3], int prev, double cap,
+template <class G>
+__device__ __forceinline__ void nn1_ball_search(const GicpDev& D, const G& g, const int* box, const double q[3], int prev, double cap,
                                                 int& id, double& d) {
-  const ShellQuery sq = make_shell_query(D.cell, q[0], q[1], q[2]);
+  const ShellQuery sq = make_shell_query(g, D.cell, q[0], q[1], q[2]);
   Nn1 nn;
   nn.d = DBL_MAX; nn.id = 0x7fffffff;
   if (prev >= 0) nn.push(prev, sqdist3(g.pts + (size_t)prev * 4, q[0], q[1], q[2]));
-  visit_ball<true>(g, box, sq, [&]() { return fmin(nn.d, cap); },
-                   [&](int cs_, int cn_, int, int, int, int) { scan_cell_nn1(g, cs_, cn_, q[0], q[1], q[2], nn); });
+  if constexpr (std::is_same<G, DGrid>::value)
+    visit_ball<true>(g, sq, [&]() { return fmin(nn.d, cap); }, [&](int cs_, int cn_) { scan_cell_nn1(g, cs_, cn_, q[0], q[1], q[2], nn); });
+  else
+    visit_ball<true>(g, box, sq, [&]() { return fmin(nn.d, cap); },
+                     [&](int cs_, int cn_, int, int, int, int) { scan_cell_nn1(g, cs_, cn_, q[0], q[1], q[2], nn); });
   id = nn.id; d = nn.d;
 }
 
-__global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr3(GicpDev D) {
+template <int MINB, bool DENSE>
+__global__ void __launch_bounds__(NN_THREADS, MINB) k_nn_corr3(GicpDev D) {
   __shared__ double s_q[NN_THREADS][3];
   __shared__ int s_i[NN_THREADS], s_prev[NN_THREADS], s_list[NN_THREADS];
   __shared__ int s_wcnt[NN_THREADS / 32], s_total;
@@ -1636,7 +1967,7 @@ __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr3(GicpDev D) {
   const int t = blockIdx.x * NN_THREADS + tid;
   const bool valid = t < ns;
   const double* T = D.state + (size_t)p * LM_STATE + S_T;
-  const Grid g = make_grid(D, ct);
+  const auto g = [&] { if constexpr (DENSE) return make_dgrid(D, ct); else return make_grid(D, ct); }();
   const double max_d2 = D.max_dist * D.max_dist;
   const double cap = max_d2 * 1.0000001;
   int i = 0, prev = -1;
@@ -2060,17 +2391,18 @@ struct GfsGicp {
   GicpDev dev;
   int maxPairs = 0;
   DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_nFall, b_box, b_pts, b_cov, b_tab, b_rec, b_recf, b_oct, b_knnList, b_knnCnt, b_nbr, b_nbrR2,
-      b_corr, b_maha, b_partial, b_partialE, b_state, b_istate, b_counters, b_tickets;
+      b_corr, b_maha, b_partial, b_partialE, b_state, b_istate, b_counters, b_tickets, b_dS, b_dSum;
   DevBuf b_tgt, b_src, b_n, b_T0, b_res;
   PinnedBuf h_counters;
   int launches = 0;
   bool cellKnn = false;  // GFS_GICP_KNN_CELLS=1: cell-centric 10-NN kernel first (same results)
-  int nnMode = 7;        // GFS_GICP_NN: 0 = k_nn_corr (shell walk), 1 = k_nn_corr2 (ball walk, fp64), 2 = + float32 prefilter, 3 = ball walk over octants
-                         // (fp64), 4 = octants + float32 prefilter, 5 = ball walk with the seven-cell fast path (fp64), 6 = 5 + float32 prefilter, 7 = neighbours of the old correspondence first,
-                         // certified by the 10-NN radius, ball walk for the compacted rest (default)
-  int knnMode = 2;       // GFS_GICP_KNN: 2 = k_knn_search + k_cov_nbr (search split from the covariance, 6 CTAs per SM; default, measured
-                         // fastest; 3 / 4 / 5 = the same at 7 / 5 / 4 CTAs), 0 = k_knn_cov (thread per query, search + covariance in one
-                         // kernel), 1 = k_knn_cov_warp (warp per cell, octant skipping) + k_knn_cov for what it hands over
+  int nnMode = 8;        // GFS_GICP_NN: 0 = k_nn_corr (shell walk), 1 = k_nn_corr2 (ball walk, fp64), 2 = + float32 prefilter, 3 = ball walk over
+                         // octants (fp64), 4 = octants + float32 prefilter, 5 = ball walk with the seven-cell fast path (fp64), 6 = 5 + float32
+                         // prefilter, 7..10 = k_nn_corr3: neighbours of the old correspondence first, certified by the 10-NN radius, ball walk
+                         // for the compacted rest, compiled for 6 / 8 (default) / 7 / 5 CTAs per SM.  0..6 use the hash grid.
+  int knnMode = 3;       // GFS_GICP_KNN: 2..5 = k_knn_search + k_cov_nbr (search split from the covariance) compiled for 6 / 8 (default; 7 on
+                         // the hash grid) / 5 / 4 CTAs per SM, 0 = k_knn_cov (thread per query, search + covariance in one kernel),
+                         // 1 = k_knn_cov_warp (warp per cell, octant skipping) + k_knn_cov for what it hands over.  0 and 1 use the hash grid.
   int trackCalls = 0;    // gfs_gicp_track_*: calls since the last reset (the new cloud goes to slot trackCalls & 1)
   int trackSeqs = 0;
   // optional per-stage CUDA-event timing of one call (gfs_gicp_set_profiling): an event after every stage, read back at
@@ -2139,8 +2471,10 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   int rc = gfs_device_check();
   if (rc) return rc;
   GFS_CUDA(cudaFuncSetAttribute(k_knn_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KNN_SMEM));
-  GFS_CUDA(cudaFuncSetAttribute(k_knn_search<6, KS_LIST, KS_CELLS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  GFS_CUDA(cudaFuncSetAttribute(k_knn_search<7, KS_LIST, KS_CELLS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  GFS_CUDA(cudaFuncSetAttribute(k_knn_search<6, KS_LIST, KS_CELLS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  GFS_CUDA(cudaFuncSetAttribute(k_knn_search<7, KS_LIST, KS_CELLS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  GFS_CUDA(cudaFuncSetAttribute(k_knn_search<6, KD_LIST, KD_CELLS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  GFS_CUDA(cudaFuncSetAttribute(k_knn_search<8, KD_LIST, KD_CELLS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   GFS_CUDA(cudaFuncSetAttribute(k_knn_cov_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KC_SMEM));
   GFS_CUDA(cudaFuncSetAttribute(k_knn_cov_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KW_SMEM));
   GfsGicp* h = new GfsGicp();
@@ -2172,12 +2506,19 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   if (const char* e = getenv("GFS_GICP_NN")) h->nnMode = atoi(e);
   if (const char* e = getenv("GFS_GICP_KNN")) h->knnMode = atoi(e);
   D.octSorted = (h->knnMode == 1 || h->nnMode == 3 || h->nnMode == 4) ? 1 : 0;
+  h->cellKnn = getenv("GFS_GICP_KNN_CELLS") != nullptr;
+  // the dense sorted grid serves the default kernels (k_knn_search, k_nn_corr3); the earlier generations keep the hash grid
+  D.dense = (D.cellOrder && h->knnMode >= 2 && h->nnMode >= 7 && !h->cellKnn) ? 1 : 0;
+  if (const char* e = getenv("GFS_GICP_GRID")) D.dense = D.dense && atoi(e) != 0;
+  D.dcap = 1 << 20;   // 101^3 cells: an 11 m cube at the default 0.11 m cell
+  if (const char* e = getenv("GFS_GICP_DENSE_CAP")) { const int v = atoi(e); if (v >= 64) D.dcap = v; }
+  D.daxis = (int)floor(cbrt((double)D.dcap) + 1e-9);
+  D.dstride = ((D.dcap + 1 + 3) / 4) * 4;
   D.rot_eps = s.rotation_eps;
   D.trans_eps = s.translation_eps;
   D.k = s.num_neighbors;
   D.max_iter = s.max_iterations;
   h->maxPairs = max_pairs;
-  h->cellKnn = getenv("GFS_GICP_KNN_CELLS") != nullptr;
   const size_t C = 2 * (size_t)max_pairs, P = max_pairs, N = max_points, H = hs;
 #define RES(buf, bytes, field, type)            \
   if ((rc = h->buf.reserve(bytes))) {           \
@@ -2216,6 +2557,8 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   RES(b_istate, P * LM_ISTATE * 4, istate, int*)
   RES(b_counters, 16, counters, int*)
   RES(b_tickets, P * 8, tickets, int*)
+  RES(b_dS, (D.dense ? C * (size_t)D.dstride : 4) * 4, dS, unsigned*)
+  RES(b_dSum, C * 3 * 8, dSum, unsigned long long*)
 #undef RES
   if ((rc = h->h_counters.reserve(16))) { delete h; return rc; }
   *out = h;
@@ -2226,7 +2569,7 @@ int gfs_gicp_destroy(GfsGicp* h) {
   if (!h) return GFS_OK;
   DevBuf* d[] = {&h->b_keys, &h->b_minIdx, &h->b_count, &h->b_start, &h->b_cursor, &h->b_rank, &h->b_slotOf, &h->b_members,
                  &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_nFall, &h->b_box, &h->b_pts, &h->b_cov, &h->b_tab, &h->b_rec, &h->b_recf, &h->b_oct, &h->b_knnList, &h->b_knnCnt, &h->b_nbr, &h->b_nbrR2, &h->b_corr, &h->b_maha, &h->b_partial,
-                 &h->b_partialE, &h->b_state, &h->b_istate, &h->b_counters, &h->b_tickets, &h->b_tgt, &h->b_src, &h->b_n, &h->b_T0, &h->b_res};
+                 &h->b_partialE, &h->b_state, &h->b_istate, &h->b_counters, &h->b_tickets, &h->b_dS, &h->b_dSum, &h->b_tgt, &h->b_src, &h->b_n, &h->b_T0, &h->b_res};
   for (DevBuf* b : d) b->release();
   h->h_counters.release();
   for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
@@ -2264,9 +2607,18 @@ static int preprocess_clouds(GfsGicp* h, const GicpDev& D, cudaStream_t st, int 
   prof_begin(h, st);
   group_build(h, D, st, 0, clouds, d_target, d_source, stride, D.nDown);
   k_voxel_mean<<<dim3(div_up(D.nmax, 256), clouds), 256, 0, st>>>(D, d_target, d_source, stride);
-  // grid over the downsampled points (reuses the hash-table storage); group count is not needed
-  group_build(h, D, st, 1, clouds, nullptr, nullptr, 0, D.nCells);
-  {
+  if (D.dense) {
+    const dim3 gp(div_up(D.nmax, 256), clouds);
+    k_dense_init<<<div_up(clouds, 128), 128, 0, st>>>(D, clouds);
+    k_dense_box<<<gp, 256, 0, st>>>(D);
+    k_dense_region<<<clouds, 1024, 0, st>>>(D);
+    k_dense_count<<<gp, 256, 0, st>>>(D);
+    k_dense_scan<<<clouds, 1024, 0, st>>>(D);
+    k_dense_fill<<<gp, 256, 0, st>>>(D);
+    h->launches += 6 - 5;
+  } else {
+    // grid over the downsampled points (reuses the hash-table storage); group count is not needed
+    group_build(h, D, st, 1, clouds, nullptr, nullptr, 0, D.nCells);
     if (D.octSorted) {
       const long long slots = (long long)clouds * D.hsize;
       k_cell_sort<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(D, clouds);
@@ -2284,10 +2636,14 @@ static int preprocess_clouds(GfsGicp* h, const GicpDev& D, cudaStream_t st, int 
     h->launches += 2;
   } else if (h->knnMode >= 2 && !h->cellKnn && D.cellOrder) {
     const dim3 gk(div_up(D.nmax, KNN_THREADS), clouds);
-    if (h->knnMode == 2) k_knn_search<6, KS_LIST, KS_CELLS><<<gk, KNN_THREADS, KS_SMEM, st>>>(D);
-    else if (h->knnMode == 3) k_knn_search<7, KS_LIST, KS_CELLS><<<gk, KNN_THREADS, KS_SMEM, st>>>(D);
-    else if (h->knnMode == 4) k_knn_search<5, KS_LIST, KS_CELLS><<<gk, KNN_THREADS, KS_SMEM, st>>>(D);
-    else k_knn_search<4, KS_LIST, KS_CELLS><<<gk, KNN_THREADS, KS_SMEM, st>>>(D);
+    if (D.dense) {
+      if (h->knnMode == 3) k_knn_search<8, KD_LIST, KD_CELLS, true><<<gk, KNN_THREADS, KD_SMEM, st>>>(D);
+      else if (h->knnMode == 4) k_knn_search<5, KD_LIST, KD_CELLS, true><<<gk, KNN_THREADS, KD_SMEM, st>>>(D);
+      else k_knn_search<6, KD_LIST, KD_CELLS, true><<<gk, KNN_THREADS, KD_SMEM, st>>>(D);
+    } else if (h->knnMode == 2) k_knn_search<6, KS_LIST, KS_CELLS, false><<<gk, KNN_THREADS, KS_SMEM, st>>>(D);
+    else if (h->knnMode == 3) k_knn_search<7, KS_LIST, KS_CELLS, false><<<gk, KNN_THREADS, KS_SMEM, st>>>(D);
+    else if (h->knnMode == 4) k_knn_search<5, KS_LIST, KS_CELLS, false><<<gk, KNN_THREADS, KS_SMEM, st>>>(D);
+    else k_knn_search<4, KS_LIST, KS_CELLS, false><<<gk, KNN_THREADS, KS_SMEM, st>>>(D);
     k_cov_nbr<<<dim3(div_up(D.nmax, 128), clouds), 128, 0, st>>>(D);
     h->launches += 1;
   } else if (!h->cellKnn) {
@@ -2326,7 +2682,15 @@ static int optimize_pairs(GfsGicp* h, const GicpDev& D, cudaStream_t st, int pai
     else if (h->nnMode == 4) k_nn_corr2<true, true, false><<<gn, NN_THREADS, 0, st>>>(D);
     else if (h->nnMode == 5) k_nn_corr2<false, false, true><<<gn, NN_THREADS, 0, st>>>(D);
     else if (h->nnMode == 6) k_nn_corr2<true, false, true><<<gn, NN_THREADS, 0, st>>>(D);
-    else k_nn_corr3<<<gn, NN_THREADS, 0, st>>>(D);
+    else if (D.dense) {
+      if (h->nnMode == 8) k_nn_corr3<8, true><<<gn, NN_THREADS, 0, st>>>(D);
+      else if (h->nnMode == 9) k_nn_corr3<7, true><<<gn, NN_THREADS, 0, st>>>(D);
+      else k_nn_corr3<6, true><<<gn, NN_THREADS, 0, st>>>(D);
+    }
+    else if (h->nnMode == 8) k_nn_corr3<8, false><<<gn, NN_THREADS, 0, st>>>(D);
+    else if (h->nnMode == 9) k_nn_corr3<7, false><<<gn, NN_THREADS, 0, st>>>(D);
+    else if (h->nnMode == 10) k_nn_corr3<5, false><<<gn, NN_THREADS, 0, st>>>(D);
+    else k_nn_corr3<6, false><<<gn, NN_THREADS, 0, st>>>(D);
     prof_mark(h, st, ST_NN);
     k_linearize<<<dim3(div_up(D.nblk, D.linPpt), pairs), LIN_THREADS, 0, st>>>(D);   // + the pair's LM begin in its last block
     prof_mark(h, st, ST_LIN);

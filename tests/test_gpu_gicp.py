@@ -106,23 +106,58 @@ def test_search_variants_are_bit_identical(monkeypatch):
     tg = np.pad(tg, ((0, 0), (0, stride - tg.shape[1]), (0, 0))); sr = np.pad(sr, ((0, 0), (0, stride - sr.shape[1]), (0, 0)))
     T0 = np.tile(np.eye(4), (3, 1, 1))
     out = {}
-    variants = ((0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 2, 0), (0, 2, 0), (1, 3, 1), (1, 4, 1), (0, 3, 1), (1, 1, 1), (1, 5, 0), (1, 6, 0), (0, 5, 1), (1, 7, 0), (0, 7, 0), (1, 7, 1),
-                (1, 7, 2), (1, 7, 3), (1, 5, 4), (1, 7, 5))
-    for order, nn, knn in variants:
+    # (query order, correspondence kernel, 10-NN kernel, grid): grid 1 = the dense sorted grid (only the default kernels use it)
+    variants = ((0, 0, 0, 0), (1, 0, 0, 0), (1, 1, 0, 0), (1, 2, 0, 0), (0, 2, 0, 0), (1, 3, 1, 0), (1, 4, 1, 0), (0, 3, 1, 0), (1, 1, 1, 0),
+                (1, 5, 0, 0), (1, 6, 0, 0), (0, 5, 1, 0), (1, 7, 0, 0), (0, 7, 0, 0), (1, 7, 1, 0),
+                (1, 7, 2, 0), (1, 7, 3, 0), (1, 5, 4, 0), (1, 7, 5, 0), (1, 7, 2, 1), (1, 8, 3, 1), (1, 9, 4, 1))
+    for order, nn, knn, grid in variants:
         monkeypatch.setenv("GFS_GICP_ORDER", str(order)); monkeypatch.setenv("GFS_GICP_NN", str(nn)); monkeypatch.setenv("GFS_GICP_KNN", str(knn))
+        monkeypatch.setenv("GFS_GICP_GRID", str(grid))
         reg = RegistrationGICP(max_points=stride, max_pairs=3)
-        out[(order, nn, knn)] = reg.align_batch(tg, nt, sr, ns, T0).tobytes()
-        out[(order, nn, knn, "cov")] = [reg.cloud(c)[1].tobytes() for c in range(6)]
+        out[(order, nn, knn, grid)] = reg.align_batch(tg, nt, sr, ns, T0).tobytes()
+        out[(order, nn, knn, grid, "cov")] = [reg.cloud(c)[1].tobytes() for c in range(6)]
         if knn == 1:   # the warp-per-cell kernel must do the bulk of the work itself, not hand everything over
             cells, handed = reg.knn_stats(0)
             assert handed < 0.25 * nt[0], (cells, handed)
         reg.close()
-    base = out[(0, 0, 0)]
+    base = out[(0, 0, 0, 0)]
     for k, v in out.items():
-        if len(k) == 3:
-            assert v == base, "variant order=%d nn=%d knn=%d differs from the first-generation search" % k
+        if len(k) == 4:
+            assert v == base, "variant order=%d nn=%d knn=%d grid=%d differs from the first-generation search" % k
         else:
-            assert v == out[(0, 0, 0, "cov")], "covariances of variant order=%d nn=%d knn=%d differ" % k[:3]
+            assert v == out[(0, 0, 0, 0, "cov")], "covariances of variant order=%d nn=%d knn=%d grid=%d differ" % k[:4]
+
+
+def test_dense_grid_with_a_clamped_region(monkeypatch):
+    """Clouds whose bounding box does not fit the dense grid (outliers tens of metres away; a deliberately tiny grid capacity, so
+    that most of the room lies OUTSIDE the 16-cell region and is clamped into its border cells) give the hash grid's bytes:
+    results, covariances, for the pairwise call and for tracking mode."""
+    from geoflowslam_b200 import RegistrationGICP
+    rng = np.random.default_rng(7)
+    clouds = []
+    for k in range(2):
+        t, s_, _ = synth.gicp_pair(2090 + k, n_target=[9000, 4000][k])
+        far_t = np.c_[rng.uniform(-60, 60, (25, 3)), np.ones(25)].astype(np.float32)
+        far_s = np.c_[rng.uniform(-60, 60, (25, 3)), np.ones(25)].astype(np.float32)
+        clouds.append((np.vstack([t, far_t, far_t[:12] + np.float32(0.01)]), np.vstack([s_, far_s, far_t[:5] + np.float32(0.02)])))
+    tg, nt = _pack([c[0] for c in clouds]); sr, ns = _pack([c[1] for c in clouds])
+    stride = max(tg.shape[1], sr.shape[1])
+    tg = np.pad(tg, ((0, 0), (0, stride - tg.shape[1]), (0, 0))); sr = np.pad(sr, ((0, 0), (0, stride - sr.shape[1]), (0, 0)))
+    T0 = np.tile(np.eye(4), (2, 1, 1))
+    res = {}
+    for grid, cap in ((0, None), (1, None), (1, 4096), (1, 64)):
+        monkeypatch.setenv("GFS_GICP_GRID", str(grid))
+        if cap: monkeypatch.setenv("GFS_GICP_DENSE_CAP", str(cap))
+        else: monkeypatch.delenv("GFS_GICP_DENSE_CAP", raising=False)
+        reg = RegistrationGICP(max_points=stride, max_pairs=2)
+        r = reg.align_batch(tg, nt, sr, ns, T0)
+        covs = [reg.cloud(c)[1].tobytes() for c in range(4)]
+        reg.track_reset(); reg.track_batch(tg, nt); q = reg.track_batch(sr, ns, T0)
+        res[(grid, cap)] = (r.tobytes(), covs, q.tobytes())
+        reg.close()
+    for k, v in res.items():
+        assert v == res[(0, None)], "dense grid (capacity %s) differs from the hash grid" % (k[1],)
+    assert res[(0, None)][0] == res[(0, None)][2]
 
 
 def test_dense_and_sparse_clouds_take_the_hand_over_paths(monkeypatch):
