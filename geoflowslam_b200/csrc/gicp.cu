@@ -41,6 +41,7 @@ struct GicpDev {
   // other way round (track mode alternates, so last call's source is this call's target without being rebuilt).
   int cbase, cstep, swap;
   int inputAll;     // 1: every cloud's raw points come from the `src` array (track mode); 0: even clouds from `tgt`
+  int errPpt;       // source points per thread of k_error (GFS_GICP_ERR_PPT, even, 2..32)
   int linPpt;       // source points per thread of k_linearize (GFS_GICP_LIN_PPT, 1..32)
   int cellOrder;    // 1: neighbour-search kernels take their queries in grid-cell order (rec[]), not in point order
   int octSorted;    // 1: k_cell_sort ran (an octant kernel is selected): k_cell_pack takes the cell's members from slotOf[]
@@ -84,6 +85,11 @@ struct GicpDev {
   double* state;             // [pairs][LM_STATE]
   int* istate;               // [pairs][LM_ISTATE]
   int* counters;             // [4]: needTrial, active
+  int* activeList;           // [2][listStride] pairs with work left, written by the decisions of a round the host checks (list
+                             // listWrite), read by the rounds after it (list listRead): the optimiser kernels then launch only as many
+                             // CTA rows as there are unfinished pairs.  Without it the 6 % of pairs that run all 20 iterations kept
+                             // every kernel at full grid size: 16 of 21 rounds spent their time retiring empty CTAs.
+  int listRead, listWrite, listStride;   // -1: none
   int* tickets;              // [pairs][2] blocks of the pair that finished k_linearize / k_error (the last one does the pair's LM step)
 };
 
@@ -98,6 +104,8 @@ enum { I_ACTIVE = 0, I_NEED = 1, I_CONV = 2, I_ITER = 3, I_TRIAL = 4, I_INL = 5,
 // longer steers each trial: it only reads the number of unfinished pairs every few rounds to know when to stop.
 
 __device__ __forceinline__ int cloud_of(const GicpDev& D, int y) { return D.cbase + y * D.cstep; }
+// the pair a CTA row of an optimiser kernel works on: row y itself until the host has seen the first list of unfinished pairs
+__device__ __forceinline__ int pair_of(const GicpDev& D, int y) { return D.listRead < 0 ? y : D.activeList[D.listRead * D.listStride + y]; }
 __device__ __forceinline__ int tgt_cloud(const GicpDev& D, int p) { return 2 * p + D.swap; }
 __device__ __forceinline__ int src_cloud(const GicpDev& D, int p) { return 2 * p + 1 - D.swap; }
 __device__ __forceinline__ const float* raw_points(const GicpDev& D, int c, const float* tgt, const float* src, int stride) {
@@ -1614,7 +1622,7 @@ __device__ __forceinline__ void scan_cell_nn1(const G& g, int s, int n, double q
 }
 static const int NN_THREADS = 128;
 __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr(GicpDev D) {
-  const int p = blockIdx.y;
+  const int p = pair_of(D, blockIdx.y);
   if (!D.istate[p * LM_ISTATE + I_ACTIVE] || D.istate[p * LM_ISTATE + I_NEED]) return;
   const int iter = D.istate[p * LM_ISTATE + I_OUTER];
   const int ct = tgt_cloud(D, p), cs = src_cloud(D, p);
@@ -1849,7 +1857,7 @@ __device__ __forceinline__ void for_octants(const Grid& g, int slot, int cs, int
 
 template <bool F32, bool OCT, bool FAST>
 __global__ void __launch_bounds__(NN_THREADS, 6) k_nn_corr2(GicpDev D) {
-  const int p = blockIdx.y;
+  const int p = pair_of(D, blockIdx.y);
   if (!D.istate[p * LM_ISTATE + I_ACTIVE] || D.istate[p * LM_ISTATE + I_NEED]) return;
   const int iter = D.istate[p * LM_ISTATE + I_OUTER];
   const int ct = tgt_cloud(D, p), cs = src_cloud(D, p);
@@ -1957,7 +1965,7 @@ __global__ void __launch_bounds__(NN_THREADS, MINB) k_nn_corr3(GicpDev D) {
   __shared__ double s_q[NN_THREADS][3];
   __shared__ int s_i[NN_THREADS], s_prev[NN_THREADS], s_list[NN_THREADS];
   __shared__ int s_wcnt[NN_THREADS / 32], s_total;
-  const int p = blockIdx.y;
+  const int p = pair_of(D, blockIdx.y);
   if (!D.istate[p * LM_ISTATE + I_ACTIVE] || D.istate[p * LM_ISTATE + I_NEED]) return;
   const int iter = D.istate[p * LM_ISTATE + I_OUTER];
   const int ct = tgt_cloud(D, p), cs = src_cloud(D, p);
@@ -2058,8 +2066,9 @@ __device__ __forceinline__ bool last_block_of_pair(const GicpDev& D, int p, int 
 
 // GICPFactor::linearize for every source point of every active pair + partial sums; the pair's last block then sums the
 // partials in their fixed order and starts the first lambda trial (what k_lm_begin did in a launch of its own)
-__global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D) {
-  const int p = blockIdx.y;
+template <int MINB>
+__global__ void __launch_bounds__(LIN_THREADS, MINB) k_linearize(GicpDev D) {
+  const int p = pair_of(D, blockIdx.y);
   if (!D.istate[p * LM_ISTATE + I_ACTIVE] || D.istate[p * LM_ISTATE + I_NEED]) return;
   const int ct = tgt_cloud(D, p), cs = src_cloud(D, p);
   const int ns = D.nDown[cs];
@@ -2147,27 +2156,48 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(GicpDev D) {
 // GICPFactor::error with the stored correspondences / Mahalanobis matrices; the pair's last block then decides the trial
 // (what k_lm_decide did in a launch of its own)
 __global__ void __launch_bounds__(LIN_THREADS) k_error(GicpDev D) {
-  const int p = blockIdx.y;
+  const int p = pair_of(D, blockIdx.y);
   if (!D.istate[p * LM_ISTATE + I_NEED]) return;
   const int ct = tgt_cloud(D, p), cs = src_cloud(D, p);
   const int ns = D.nDown[cs];
-  const int nbp = max((ns + LIN_THREADS - 1) / LIN_THREADS, 1);
+  const int per = LIN_THREADS * D.errPpt;
+  const int nbp = max((ns + per - 1) / per, 1);
   if ((int)blockIdx.x >= nbp) return;
-  const int i = blockIdx.x * LIN_THREADS + threadIdx.x;
+  // errPpt points per thread, two per trip: both correspondences, then both gathers are in flight before the first is used
+  // (one point per thread left the kernel waiting out a dependent corr -> target-point chain at 14 % of the issue slots, and a
+  // block of 128 points paid a fence, a ticket and a partial sum for 15 flops per thread)
+  const double* T = D.state + (size_t)p * LM_STATE + S_NEWT;
+  const double* sp = D.pts + (size_t)cs * D.nmax * 4;
+  const double* tp = D.pts + (size_t)ct * D.nmax * 4;
+  const int* corr = D.corr + (size_t)p * D.nmax;
+  const double* maha = D.maha + (size_t)p * D.nmax * 9;
   double acc[1] = {0.0};
-  if (i < ns) {
-    const int tgt = D.corr[(size_t)p * D.nmax + i];
-    if (tgt >= 0) {
-      const double* T = D.state + (size_t)p * LM_STATE + S_NEWT;
-      const double* ps = D.pts + ((size_t)cs * D.nmax + i) * 4;
+#pragma unroll 1
+  for (int j = 0; j < D.errPpt; j += 2) {
+    int i[2], tgt[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      i[u] = (blockIdx.x * D.errPpt + j + u) * LIN_THREADS + threadIdx.x;
+      tgt[u] = (j + u < D.errPpt && i[u] < ns) ? corr[i[u]] : -1;
+    }
+    double ps[2][3], pt[2][3], M[2][9];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      if (tgt[u] < 0) continue;
+#pragma unroll
+      for (int k = 0; k < 3; k++) { ps[u][k] = sp[(size_t)i[u] * 4 + k]; pt[u][k] = tp[(size_t)tgt[u] * 4 + k]; }
+#pragma unroll
+      for (int k = 0; k < 9; k++) M[u][k] = maha[(size_t)i[u] * 9 + k];
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      if (tgt[u] < 0) continue;
       double q[3];
-      xform(T, ps, q);
-      const double* pt = D.pts + ((size_t)ct * D.nmax + tgt) * 4;
-      const double res[3] = {pt[0] - q[0], pt[1] - q[1], pt[2] - q[2]};
-      const double* M = D.maha + ((size_t)p * D.nmax + i) * 9;
+      xform(T, ps[u], q);
+      const double res[3] = {pt[u][0] - q[0], pt[u][1] - q[1], pt[u][2] - q[2]};
       double Mr[3];
-      for (int r = 0; r < 3; r++) Mr[r] = M[3 * r] * res[0] + M[3 * r + 1] * res[1] + M[3 * r + 2] * res[2];
-      acc[0] = 0.5 * (res[0] * Mr[0] + res[1] * Mr[1] + res[2] * Mr[2]);
+      for (int r = 0; r < 3; r++) Mr[r] = M[u][3 * r] * res[0] + M[u][3 * r + 1] * res[1] + M[u][3 * r + 2] * res[2];
+      acc[0] += 0.5 * (res[0] * Mr[0] + res[1] * Mr[1] + res[2] * Mr[2]);
     }
   }
   block_reduce_store<1, LIN_THREADS>(acc, D.partialE + (size_t)p * D.nblk + blockIdx.x);
@@ -2265,7 +2295,7 @@ __device__ void lm_trial(double* st) {
 }
 
 // all LIN_THREADS threads of one block: sum the pair's per-warp partials in block order, start the first trial (:97-112)
-__device__ void lm_begin_block(const GicpDev& D, int p) {
+__device__ __noinline__ void lm_begin_block(const GicpDev& D, int p) {
   __shared__ double s_tot[RED_N];
   const int tid = threadIdx.x;
   int* is = D.istate + p * LM_ISTATE;
@@ -2303,11 +2333,11 @@ __device__ void lm_begin_block(const GicpDev& D, int p) {
 }
 
 // one thread: new_e, accept / reject, next trial or end of the outer iteration (:114-143)
-__device__ void lm_decide_thread(const GicpDev& D, int p) {
+__device__ __noinline__ void lm_decide_thread(const GicpDev& D, int p) {
   int* is = D.istate + p * LM_ISTATE;
   const int iter = is[I_OUTER];
   double* st = D.state + (size_t)p * LM_STATE;
-  const int nb = max((D.nDown[src_cloud(D, p)] + LIN_THREADS - 1) / LIN_THREADS, 1);
+  const int nb = max((D.nDown[src_cloud(D, p)] + LIN_THREADS * D.errPpt - 1) / (LIN_THREADS * D.errPpt), 1);
   // fixed-order sum: lane-strided partial sums are NOT order-preserving, so one thread sums serially
   double new_e = 0;
   for (int b = 0; b < nb; b++) new_e += __ldcg(&D.partialE[(size_t)p * D.nblk + b]);
@@ -2331,7 +2361,8 @@ __device__ void lm_decide_thread(const GicpDev& D, int p) {
     if (!is[I_SUCCESS] || is[I_CONV] || iter + 1 >= D.max_iter) is[I_ACTIVE] = 0;
     else is[I_OUTER] = iter + 1;
   }
-  if (is[I_ACTIVE]) atomicAdd(&D.counters[1], 1);  // pairs with work left (the host reads it every few rounds)
+  if (is[I_ACTIVE] && D.listWrite >= 0)   // pairs with work left (the host reads the number in the rounds it checks)
+    D.activeList[D.listWrite * D.listStride + atomicAdd(&D.counters[1], 1)] = p;
 }
 
 __global__ void k_lm_init(GicpDev D, int pairs, const double* __restrict__ T0) {
@@ -2391,7 +2422,7 @@ struct GfsGicp {
   GicpDev dev;
   int maxPairs = 0;
   DevBuf b_keys, b_minIdx, b_count, b_start, b_cursor, b_rank, b_slotOf, b_members, b_nIn, b_nDown, b_nCells, b_nFall, b_box, b_pts, b_cov, b_tab, b_rec, b_recf, b_oct, b_knnList, b_knnCnt, b_nbr, b_nbrR2,
-      b_corr, b_maha, b_partial, b_partialE, b_state, b_istate, b_counters, b_tickets, b_dS, b_dSum;
+      b_corr, b_maha, b_partial, b_partialE, b_state, b_istate, b_counters, b_tickets, b_dS, b_dSum, b_active;
   DevBuf b_tgt, b_src, b_n, b_T0, b_res;
   PinnedBuf h_counters;
   int launches = 0;
@@ -2403,6 +2434,7 @@ struct GfsGicp {
   int knnMode = 3;       // GFS_GICP_KNN: 2..5 = k_knn_search + k_cov_nbr (search split from the covariance) compiled for 6 / 8 (default; 7 on
                          // the hash grid) / 5 / 4 CTAs per SM, 0 = k_knn_cov (thread per query, search + covariance in one kernel),
                          // 1 = k_knn_cov_warp (warp per cell, octant skipping) + k_knn_cov for what it hands over.  0 and 1 use the hash grid.
+  int linMinb = 3;       // GFS_GICP_LIN_MINB: CTAs per SM k_linearize is compiled for (3 = no register cap, 4 = 128 registers, 5 = 96)
   int trackCalls = 0;    // gfs_gicp_track_*: calls since the last reset (the new cloud goes to slot trackCalls & 1)
   int trackSeqs = 0;
   // optional per-stage CUDA-event timing of one call (gfs_gicp_set_profiling): an event after every stage, read back at
@@ -2499,10 +2531,14 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   D.max_dist = s.max_correspondence_distance;
   D.nnBoundA = (float)(1.2 * 2.0 * 1.7320508 * 5.9604645e-8 * (2.0 * D.cell + s.max_correspondence_distance));
   D.cbase = 0; D.cstep = 1; D.swap = 0; D.inputAll = 0;
+  D.listRead = -1; D.listWrite = -1; D.listStride = max_pairs;
   D.cellOrder = 1;
   D.linPpt = 8;
+  D.errPpt = 8;
+  if (const char* e = getenv("GFS_GICP_ERR_PPT")) { const int v = atoi(e) & ~1; D.errPpt = v < 2 ? 2 : (v > 32 ? 32 : v); }
   if (const char* e = getenv("GFS_GICP_LIN_PPT")) { const int v = atoi(e); D.linPpt = v < 1 ? 1 : (v > 32 ? 32 : v); }
   if (const char* e = getenv("GFS_GICP_ORDER")) D.cellOrder = atoi(e) != 0;  // 0: queries in point order (first generation)
+  if (const char* e = getenv("GFS_GICP_LIN_MINB")) h->linMinb = atoi(e);
   if (const char* e = getenv("GFS_GICP_NN")) h->nnMode = atoi(e);
   if (const char* e = getenv("GFS_GICP_KNN")) h->knnMode = atoi(e);
   D.octSorted = (h->knnMode == 1 || h->nnMode == 3 || h->nnMode == 4) ? 1 : 0;
@@ -2557,6 +2593,7 @@ int gfs_gicp_create(const GfsGicpSetting* setting, int max_points, int max_pairs
   RES(b_istate, P * LM_ISTATE * 4, istate, int*)
   RES(b_counters, 16, counters, int*)
   RES(b_tickets, P * 8, tickets, int*)
+  RES(b_active, 2 * P * 4, activeList, int*)
   RES(b_dS, (D.dense ? C * (size_t)D.dstride : 4) * 4, dS, unsigned*)
   RES(b_dSum, C * 3 * 8, dSum, unsigned long long*)
 #undef RES
@@ -2569,7 +2606,7 @@ int gfs_gicp_destroy(GfsGicp* h) {
   if (!h) return GFS_OK;
   DevBuf* d[] = {&h->b_keys, &h->b_minIdx, &h->b_count, &h->b_start, &h->b_cursor, &h->b_rank, &h->b_slotOf, &h->b_members,
                  &h->b_nIn, &h->b_nDown, &h->b_nCells, &h->b_nFall, &h->b_box, &h->b_pts, &h->b_cov, &h->b_tab, &h->b_rec, &h->b_recf, &h->b_oct, &h->b_knnList, &h->b_knnCnt, &h->b_nbr, &h->b_nbrR2, &h->b_corr, &h->b_maha, &h->b_partial,
-                 &h->b_partialE, &h->b_state, &h->b_istate, &h->b_counters, &h->b_tickets, &h->b_dS, &h->b_dSum, &h->b_tgt, &h->b_src, &h->b_n, &h->b_T0, &h->b_res};
+                 &h->b_partialE, &h->b_state, &h->b_istate, &h->b_counters, &h->b_tickets, &h->b_dS, &h->b_dSum, &h->b_active, &h->b_tgt, &h->b_src, &h->b_n, &h->b_T0, &h->b_res};
   for (DevBuf* b : d) b->release();
   h->h_counters.release();
   for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
@@ -2673,36 +2710,45 @@ static int optimize_pairs(GfsGicp* h, const GicpDev& D, cudaStream_t st, int pai
   static const int checkEvery = [] { const char* e = getenv("GFS_GICP_CHECK_EVERY"); const int v = e ? atoi(e) : 2; return v > 0 ? v : 2; }();
   const int maxRounds = D.max_iter * 10;  // every outer iteration may take up to 10 trials (optimizer.hpp:107)
   int nextCheck = checkEvery == 1 ? 0 : 2;
+  GicpDev L = D;            // per-launch copy: which list of unfinished pairs the kernels read / write
+  L.listRead = -1; L.listWrite = -1; L.listStride = h->maxPairs;
+  int rows = pairs;         // CTA rows = unfinished pairs as of the last check
   for (int round = 0; round < maxRounds; round++) {
-    const dim3 gn(div_up(D.nmax, NN_THREADS), pairs);
-    if (h->nnMode == 0) k_nn_corr<<<gn, NN_THREADS, 0, st>>>(D);
-    else if (h->nnMode == 1) k_nn_corr2<false, false, false><<<gn, NN_THREADS, 0, st>>>(D);
-    else if (h->nnMode == 2) k_nn_corr2<true, false, false><<<gn, NN_THREADS, 0, st>>>(D);
-    else if (h->nnMode == 3) k_nn_corr2<false, true, false><<<gn, NN_THREADS, 0, st>>>(D);
-    else if (h->nnMode == 4) k_nn_corr2<true, true, false><<<gn, NN_THREADS, 0, st>>>(D);
-    else if (h->nnMode == 5) k_nn_corr2<false, false, true><<<gn, NN_THREADS, 0, st>>>(D);
-    else if (h->nnMode == 6) k_nn_corr2<true, false, true><<<gn, NN_THREADS, 0, st>>>(D);
+    const dim3 gn(div_up(D.nmax, NN_THREADS), rows);
+    if (h->nnMode == 0) k_nn_corr<<<gn, NN_THREADS, 0, st>>>(L);
+    else if (h->nnMode == 1) k_nn_corr2<false, false, false><<<gn, NN_THREADS, 0, st>>>(L);
+    else if (h->nnMode == 2) k_nn_corr2<true, false, false><<<gn, NN_THREADS, 0, st>>>(L);
+    else if (h->nnMode == 3) k_nn_corr2<false, true, false><<<gn, NN_THREADS, 0, st>>>(L);
+    else if (h->nnMode == 4) k_nn_corr2<true, true, false><<<gn, NN_THREADS, 0, st>>>(L);
+    else if (h->nnMode == 5) k_nn_corr2<false, false, true><<<gn, NN_THREADS, 0, st>>>(L);
+    else if (h->nnMode == 6) k_nn_corr2<true, false, true><<<gn, NN_THREADS, 0, st>>>(L);
     else if (D.dense) {
-      if (h->nnMode == 8) k_nn_corr3<8, true><<<gn, NN_THREADS, 0, st>>>(D);
-      else if (h->nnMode == 9) k_nn_corr3<7, true><<<gn, NN_THREADS, 0, st>>>(D);
-      else k_nn_corr3<6, true><<<gn, NN_THREADS, 0, st>>>(D);
+      if (h->nnMode == 8) k_nn_corr3<8, true><<<gn, NN_THREADS, 0, st>>>(L);
+      else if (h->nnMode == 9) k_nn_corr3<7, true><<<gn, NN_THREADS, 0, st>>>(L);
+      else k_nn_corr3<6, true><<<gn, NN_THREADS, 0, st>>>(L);
     }
-    else if (h->nnMode == 8) k_nn_corr3<8, false><<<gn, NN_THREADS, 0, st>>>(D);
-    else if (h->nnMode == 9) k_nn_corr3<7, false><<<gn, NN_THREADS, 0, st>>>(D);
-    else if (h->nnMode == 10) k_nn_corr3<5, false><<<gn, NN_THREADS, 0, st>>>(D);
-    else k_nn_corr3<6, false><<<gn, NN_THREADS, 0, st>>>(D);
+    else if (h->nnMode == 8) k_nn_corr3<8, false><<<gn, NN_THREADS, 0, st>>>(L);
+    else if (h->nnMode == 9) k_nn_corr3<7, false><<<gn, NN_THREADS, 0, st>>>(L);
+    else if (h->nnMode == 10) k_nn_corr3<5, false><<<gn, NN_THREADS, 0, st>>>(L);
+    else k_nn_corr3<6, false><<<gn, NN_THREADS, 0, st>>>(L);
     prof_mark(h, st, ST_NN);
-    k_linearize<<<dim3(div_up(D.nblk, D.linPpt), pairs), LIN_THREADS, 0, st>>>(D);   // + the pair's LM begin in its last block
+    const dim3 gl(div_up(D.nblk, D.linPpt), rows);   // + the pair's LM begin in its last block
+    if (h->linMinb == 4) k_linearize<4><<<gl, LIN_THREADS, 0, st>>>(L);
+    else if (h->linMinb == 5) k_linearize<5><<<gl, LIN_THREADS, 0, st>>>(L);
+    else k_linearize<3><<<gl, LIN_THREADS, 0, st>>>(L);
     prof_mark(h, st, ST_LIN);
     const bool check = round >= nextCheck;
     if (check) GFS_CUDA(cudaMemsetAsync(D.counters, 0, 8, st));
-    k_error<<<dim3(D.nblk, pairs), LIN_THREADS, 0, st>>>(D);       // + the pair's LM decision in its last block
+    L.listWrite = check ? (L.listRead < 0 ? 0 : 1 - L.listRead) : -1;
+    k_error<<<dim3(div_up(D.nblk, D.errPpt), rows), LIN_THREADS, 0, st>>>(L);       // + the pair's LM decision in its last block
     h->launches += 3;
     if (check) {
       GFS_CUDA(cudaMemcpyAsync(hc, D.counters, 8, cudaMemcpyDeviceToHost, st));
       GFS_CUDA(gfs::stream_wait(st));
       prof_mark(h, st, ST_LM, 1);
       if (hc[1] == 0) break;  // every pair converged / failed / hit max_iterations
+      rows = hc[1];
+      L.listRead = L.listWrite;
       nextCheck = round + checkEvery;
     } else {
       prof_mark(h, st, ST_LM, 1);
