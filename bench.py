@@ -1260,12 +1260,13 @@ def run_track(args):
     top = max(kern, key=lambda k: kern[k][0])
     per_launch_ms = kern[top][0] / kern[top][1]
     achieved = alg[top] / (per_launch_ms / 1e3) / 1e9
-    traffic_per_query = {"knn_cov": (485.131520e6 + 273.671168e6) / (128 * 42100.0),      # profiles/r02_s1_gicp_knn_cov_after_ncu_details.txt
-                         "nn_corr": (126.514944e6 + 4.716544e6) / (64 * 40020.0)}        # profiles/r02_s24_gicp_nn_corr3_ncu_details.txt (64 pairs)
-    roof = {"bound": "hbm", "kernel": {"knn_cov": "k_knn_cov", "nn_corr": "k_nn_corr3", "linearize": "k_linearize"}[top],
+    traffic_per_query = {"knn_cov": (92.274688e6 + 85.559552e6 + 194.201856e6 + 133.848832e6) / (64 * 40020.0),   # profiles/r02_s35_gicp_knn_search / _cov_nbr _ncu_details.txt (64 clouds)
+                         "nn_corr": (119.439360e6 + 4.440576e6) / (64 * 40020.0),       # profiles/r02_s35_gicp_nn_corr3_ncu_details.txt (64 pairs)
+                         "linearize": (149.452032e6 + 37.468672e6) / (64 * 40020.0)}    # profiles/r02_s35_gicp_linearize_ncu_details.txt (64 pairs)
+    roof = {"bound": "hbm", "kernel": {"knn_cov": "k_knn_search + k_cov_nbr", "nn_corr": "k_nn_corr3", "linearize": "k_linearize"}[top],
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic_per_query[top] * BG * M if top in traffic_per_query else None,
-            "traffic_source": "ncu --set full capture under profiles/ (r02_s1_gicp_knn_cov_after / r02_s24_gicp_nn_corr3 _ncu_details.txt), scaled per query" if top in traffic_per_query else None,
+            "traffic_source": "ncu --set full captures profiles/r02_s35_gicp_*_ncu_details.txt (64 sequences, dense grid), scaled per query" if top in traffic_per_query else None,
             "algorithmic_bytes": alg[top], "ms_per_launch": per_launch_ms, "launches_per_step": kern[top][1], "peak_source": peak_src,
             "gicp_stage_ms_per_step": {k: v[0] for k, v in gprof.items()},
             "gicp_whole": {"algorithmic_bytes": B * (16 * n_in + 400 * M + M * (160 * I + 112 * J)),

@@ -20,6 +20,7 @@
 //                    staged 36x36 derivative window) lives in shared memory, the 36x36 window of the other image is
 //                    staged per iteration (aligned 32-bit words inside the image, reflect-101 bytes at the border),
 //                    the five sums are warp-reduced int64
+#include <climits>
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -357,13 +358,23 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
     // row by row, then is interpolated IN PLACE: output (x, y) needs inputs (x..x+1, y..y+1), which no later output of
     // the raster order reads once this batch of 32 has loaded them
     const int dw = win + 1;
-    for (int y = 0; y < dw; y++) {
-      const int Y = ipy + y;
-      const bool rowIn = Y >= 0 && Y < I.h;
-      const short2* row = I.der + (size_t)(rowIn ? Y : 0) * I.w;
-      for (int x = lane; x < dw; x += 32) {
-        const int X = ipx + x;
-        s_dI[y * dw + x] = (rowIn && X >= 0 && X < I.w) ? row[X] : make_short2(0, 0);
+    {
+      // columns 0..31: one row per trip, every lane its own column (the column test is loop-invariant)
+      const int X = ipx + lane;
+      const bool colIn = lane < dw && X >= 0 && X < I.w;
+      for (int y = 0; y < dw; y++) {
+        const int Y = ipy + y;
+        short2 v = make_short2(0, 0);
+        if (colIn && Y >= 0 && Y < I.h) v = I.der[(size_t)Y * I.w + X];
+        if (lane < dw) s_dI[y * dw + lane] = v;
+      }
+      // the columns beyond 32 (four of them for the 35 x 35 window): flattened over the lanes instead of a second
+      // trip per row with four lanes at work
+      const int rem = dw - 32;
+      for (int i = lane; i < rem * dw; i += 32) {
+        const int y = rem == 4 ? (i >> 2) : i / rem, x = 32 + i - y * rem;
+        const int X2 = ipx + x, Y = ipy + y;
+        s_dI[y * dw + x] = (Y >= 0 && Y < I.h && X2 >= 0 && X2 < I.w) ? I.der[(size_t)Y * I.w + X2] : make_short2(0, 0);
       }
     }
     __syncwarp();
@@ -405,6 +416,8 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
   D = 1.f / D;
   nextx -= halfWin; nexty -= halfWin;
   float pdx = 0, pdy = 0;
+  int stagedX = INT_MIN, stagedY = INT_MIN;   // origin of the J window s_win holds (it held the I window until here)
+  unsigned aJ = NO_SHIFT;
   for (int j = 0; j < maxCount; j++) {
     const int inx = (int)floorf(nextx), iny = (int)floorf(nexty);
     if (inx < -win || inx >= J.w || iny < -win || iny >= J.h) {
@@ -417,7 +430,12 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
     iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS));
     iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
     __syncwarp();
-    const unsigned aJ = stage_window(J, inx, iny, win, s_win);
+    // the window is staged again only when its integer origin moved: once the iteration is down to sub-pixel steps
+    // (most of its trips) the bytes in shared memory are already the ones it needs
+    if (inx != stagedX || iny != stagedY) {
+      aJ = stage_window(J, inx, iny, win, s_win);
+      stagedX = inx; stagedY = iny;
+    }
     long long sb1 = 0, sb2 = 0;
     if (((win * win + 31) >> 5) <= 64 && (aJ == NO_SHIFT || (J.w & 3) == 0)) {
       // Common case (level widths that are multiples of 4, or a reflected window): every staged row has the same
