@@ -19,7 +19,10 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
+
+#include <cuda.h>   // CUtensorMap and its enums only: cuTensorMapEncodeTiled is fetched through the runtime (no libcuda link)
 
 #include "common.cuh"
 #include "gcc_sort.h"
@@ -469,6 +472,16 @@ __device__ __forceinline__ unsigned fast_best16_packed(const unsigned (&q)[16]) 
   return best;
 }
 
+// Tensor maps of the pyramid levels for k_fast_cells2: level l of ALL frames of the batch as one rank-3 tensor (x, y, frame), box
+// = one cell's ROI (roiPitch x roiRows x 1).  A CTA fetches its ROI with ONE cp.async.bulk.tensor.3d (UTMALDG) at the ROI's own
+// coordinates rounded down to a 16-byte column (the tensor path traps on a box whose innermost start is not a multiple of 16
+// bytes -- scripts/probe/tmap_probe3.cu; the box is wide enough for the shift, as with the per-row copies).  mask bit l is
+// clear when level l cannot have a map (base / pitch / frame stride not multiples of 16): the CTA then stages as before.
+struct alignas(64) FastTmaps {
+  CUtensorMap m[MAX_LEVELS];
+  unsigned mask;
+};
+
 // One precomputed record per cell (all levels of a frame): level and ROI of ComputeKeyPointsOctTree's
 // cell loop (:794-808), so the CTA does not search the level table or divide.
 struct FastCell {
@@ -487,13 +500,16 @@ __device__ __forceinline__ void fast_mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity) : "memory");
 }
 
-__global__ void __launch_bounds__(FAST_THREADS) k_fast_cells2(OrbDev P, const FastCell* __restrict__ cellTab,
+__global__ void __launch_bounds__(FAST_THREADS) k_fast_cells2(OrbDev P, const __grid_constant__ FastTmaps tm,
+                                                               const FastCell* __restrict__ cellTab,
                                                                const uint8_t* __restrict__ img0,
                                                                long long img_stride, int pitch0,
                                                                const uint8_t* __restrict__ pyr,
                                                                uint32_t* __restrict__ cellKeys,
                                                                int* __restrict__ cellCount) {
-  extern __shared__ __align__(16) uint8_t sm[];
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  // the tensor-map load wants a 128-byte aligned destination: the dynamic window starts wherever the static variables end
+  uint8_t* sm = sm_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(sm_raw) & 127u)) & 127u);
   __shared__ int s_nCand, s_nCorner, s_nKept;
   __shared__ unsigned s_vm[FAST_THREADS];
   __shared__ __align__(8) unsigned long long s_bar;
@@ -527,9 +543,24 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells2(OrbDev P, const Fa
   // sm[y * RP + shift + x].  Rows whose 16-byte groups are addressable go through the bulk-copy
   // engine (one cp.async.bulk per row, completion on an mbarrier) while the CTA clears the score
   // map; otherwise word / byte loads.
-  const bool bulk = ((pitch & 15) == 0) && ((((size_t)src) & 15) == 0);
+  const bool tmap = (tm.mask >> l) & 1u;
+  const bool bulk = !tmap && ((pitch & 15) == 0) && ((((size_t)src) & 15) == 0);
   int shift;
-  if (bulk) {
+  if (tmap) {
+    shift = iniX & 15;   // the box must start on a 16-byte boundary of the innermost dimension (measured: anything else traps)
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(RP * P.roiRows)) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+              (uint32_t)__cvta_generic_to_shared(sm)),
+          "l"(&tm.m[l]), "r"(iniX - shift), "r"(iniY), "r"(frame), "r"(bar)
+          : "memory");
+    }
+    __syncthreads();   // the barrier's initialisation is visible to the threads that will wait on it
+  } else if (bulk) {
     shift = iniX & 15;
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
     const uint32_t rowBytes = (uint32_t)((shift + rw + 15) & ~15);  // <= RP, stays inside the source row (pitch % 16 == 0)
@@ -584,7 +615,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells2(OrbDev P, const Fa
     s_vm[tid] = vm;
   }
   if (tid == 0) { s_nCorner = 0; s_nCand = 0; s_nKept = 0; }
-  if (bulk) fast_mbar_wait((uint32_t)__cvta_generic_to_shared(&s_bar), 0u);
+  if (bulk || tmap) fast_mbar_wait((uint32_t)__cvta_generic_to_shared(&s_bar), 0u);
   __syncthreads();
 
   const int thMin = P.minTh, thIni = P.iniTh;
@@ -1372,6 +1403,7 @@ struct GfsOrb {
   size_t fastSmem = 0, octSmem = 0, pyrSmem = 0, pyr3Smem = 0;
   bool fastV1 = getenv("GFS_FAST_V1") != nullptr;  // first-generation FAST kernel (A/B runs); same results
   int pyr3Rows = 0, pyr3PitchF = 0;  // k_pyr_level3 shared-memory geometry; pyr3Rows == 0: generic kernel
+  unsigned lastTmapMask = 0;          // levels whose FAST ROIs the last call staged through a tensor map
   DevBuf d_tabs3, d_cellTab;
   // optional per-stage CUDA-event timing (bench roofline): pyramid, fast, octree, blur, orient/desc, pack
   bool profiling = false;
@@ -1385,6 +1417,37 @@ struct GfsOrb {
 };
 
 static inline int cv_round_f(double v) { return (int)std::nearbyint(v); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tmap_encoder() {
+  static EncodeTiledFn fn = [] {
+    if (const char* e = getenv("GFS_ORB_TMAP")) if (atoi(e) == 0) return (EncodeTiledFn) nullptr;   // A/B runs: per-row bulk copies
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return (EncodeTiledFn) nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+// level images of `frames` frames as a rank-3 u8 tensor (x, y, frame) with a roiPitch x roiRows x 1 box; false: no map possible
+static bool encode_level_map(CUtensorMap* m, const uint8_t* base, int w, int hgt, int frames, long long pitch, long long frameStride,
+                             int boxW, int boxH) {
+  EncodeTiledFn enc = tmap_encoder();
+  long long fs = frameStride;
+  if (frames == 1 && (fs < pitch * hgt || (fs & 15))) fs = (pitch * hgt + 15) / 16 * 16;   // a single frame: any valid stride will do
+  if (!enc || (((uintptr_t)base | (uintptr_t)pitch | (uintptr_t)fs) & 15) != 0 || fs < pitch * hgt || pitch < w || boxW > 256 ||
+      boxH > 256 || (boxW & 15))
+    return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)hgt, (cuuint64_t)frames};
+  const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)fs};
+  const cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1u};
+  const cuuint32_t es[3] = {1u, 1u, 1u};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 static void area_tab(int ssize, int dsize, std::vector<AreaEntry>& out) {
   // cv::resize INTER_AREA table (oracle/orb_oracle.cpp area_tab)
@@ -1603,7 +1666,7 @@ static int orb_set_geometry(GfsOrb* h, int w, int ht) {
   GFS_CUDA(cudaMemset(h->d_status.p, 0, 16));
   if ((rc = h->d_pattern.reserve(1024))) return rc;
   GFS_CUDA(cudaMemcpy(h->d_pattern.p, GFS_ORB_PATTERN, 1024, cudaMemcpyHostToDevice));
-  h->fastSmem = (size_t)D.offKept + (size_t)4 * cellCap + 16;
+  h->fastSmem = (size_t)D.offKept + (size_t)4 * cellCap + 16 + 128;   // + the slack k_fast_cells2 uses to align its window to 128 bytes
   const size_t perWarp = align_up(sizeof(OctState) + (size_t)nodeCap * (sizeof(OctNode) + 4 * sizeof(int)), 16);
   h->octSmem = perWarp * OCT_WARPS;
   if (h->octSmem > 200 * 1024) {
@@ -1769,9 +1832,19 @@ static int orb_run_chunk(GfsOrb* h, cudaStream_t st, int slot0, const uint8_t* d
   if (h->fastV1)
     k_fast_cells<<<dim3(D.totalCells, batch), FAST_THREADS, h->fastSmem, st>>>(
         D, d_imgs, (long long)img_stride, pitch, pyr, cellKeys, cellCount);
-  else
+  else {
+    FastTmaps tm;
+    memset(&tm, 0, sizeof(tm));
+    for (int l = 0; l < h->nlevels; l++) {
+      const LevelDev& L = D.lv[l];
+      const bool ok = l == 0 ? encode_level_map(&tm.m[0], d_imgs, L.w, L.h, batch, pitch, (long long)img_stride, D.roiPitch, D.roiRows)
+                             : encode_level_map(&tm.m[l], pyr + L.off, L.w, L.h, batch, L.pitch, D.pyrStride, D.roiPitch, D.roiRows);
+      if (ok) tm.mask |= 1u << l;
+    }
+    h->lastTmapMask = tm.mask;
     k_fast_cells2<<<dim3(D.totalCells, batch), FAST_THREADS, h->fastSmem, st>>>(
-        D, (const FastCell*)h->d_cellTab.p, d_imgs, (long long)img_stride, pitch, pyr, cellKeys, cellCount);
+        D, tm, (const FastCell*)h->d_cellTab.p, d_imgs, (long long)img_stride, pitch, pyr, cellKeys, cellCount);
+  }
   mark(2);
   k_octree<<<div_up(batch * h->nlevels, OCT_WARPS), OCT_WARPS * 32, h->octSmem, st>>>(
       D, batch, cellKeys, cellCount, keysA, keysB, selKeys, selCount, (int*)h->d_status.p);
