@@ -21,6 +21,9 @@
 //                    staged per iteration (aligned 32-bit words inside the image, reflect-101 bytes at the border),
 //                    the five sums are warp-reduced int64
 #include <climits>
+#include <cstdint>
+#include <cstdlib>
+#include <cuda.h>   // CUtensorMap and its enums only (cuTensorMapEncodeTiled is fetched through the runtime)
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -268,13 +271,52 @@ __global__ void __launch_bounds__(256) k_klt_scharr(uint8_t* __restrict__ pyr, P
 }
 
 // ---- LKTrackerInvoker for one point by one warp
-struct LevelView { const uint8_t* img; const short2* der; int w, h; };
-__device__ __forceinline__ LevelView level_view(const uint8_t* frame, const PyrGeom& G, int l) {
+// Tensor maps of the pyramid levels 0..KLT_MAP_LEVELS-1 of both pyramids of a call, images (u8) and derivatives (short2 as u32), each a
+// rank-3 tensor (x, y, frame).  A warp fetches a window with ONE cp.async.bulk.tensor.3d instead of a 36-trip row loop of dependent
+// load -> store pairs (the row loops were 30 % of k_klt_track's samples).  The box starts on a 16-byte column (the hardware traps
+// otherwise, scripts/probe/tmap_probe3.cu), so windows are staged with a column offset: derivative windows 40 x 36 entries (offset
+// 0..3), image windows 64 x 36 bytes (offset 0..15).  Out-of-bounds entries read as zero -- exactly calcScharrDeriv's
+// BORDER_CONSTANT for the derivative window; image windows that leave the image (reflect-101) keep the byte loop.
+static const int KLT_MAP_LEVELS = 5;
+struct alignas(64) KltMaps {
+  CUtensorMap img[2][KLT_MAP_LEVELS], der[2][KLT_MAP_LEVELS];   // [0] = prevPyr, [1] = curPyr
+  unsigned imgMask[2], derMask[2];
+};
+struct LevelView { const uint8_t* img; const short2* der; int w, h; const CUtensorMap *imgMap, *derMap; int frame; };
+__device__ __forceinline__ LevelView level_view(const uint8_t* frame, const PyrGeom& G, int l, const KltMaps& M, int which, int f) {
   LevelView v;
   v.img = frame + G.off[l];
   v.der = reinterpret_cast<const short2*>(frame + G.imgBytes) + G.off[l];
   v.w = G.w[l]; v.h = G.h[l];
+  v.imgMap = (l < KLT_MAP_LEVELS && ((M.imgMask[which] >> l) & 1u)) ? &M.img[which][l] : nullptr;
+  v.derMap = (l < KLT_MAP_LEVELS && ((M.derMask[which] >> l) & 1u)) ? &M.der[which][l] : nullptr;
+  v.frame = f;
   return v;
+}
+// per-warp transaction barrier: lane 0 announces the bytes and issues the loads, every lane waits for the phase
+struct WarpTma { uint32_t bar; uint32_t parity; };
+__device__ __forceinline__ void tma_expect(const WarpTma& t, uint32_t bytes) {
+  // the windows were read / written through the generic proxy until now: order those accesses before the async-proxy writes
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(t.bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load3(const WarpTma& t, const CUtensorMap* map, void* dst, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(dst)),
+               "l"(map), "r"(x), "r"(y), "r"(z), "r"(t.bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_wait(WarpTma& t) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(t.bar), "r"(t.parity) : "memory");
+  t.parity ^= 1u;
 }
 __device__ __forceinline__ int descale(int v, int n) { return (v + (1 << (n - 1))) >> n; }
 __device__ __forceinline__ long long warp_sum_ll(long long v) {
@@ -287,23 +329,34 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 // sits at s_win[y * pitch + ((a0 + y * w) & 3) + x], a0 = the returned low address bits of the first pixel); a
 // window that leaves the image is copied byte by byte with the reflect-101 rule and a0 = NO_SHIFT.
 static const unsigned NO_SHIFT = 0xffffffffu;
-__device__ __forceinline__ int win_pitch(int win) { return (win + 1 + 6) / 4 * 4; }
-__device__ __forceinline__ unsigned stage_window(const LevelView& L, int x0, int y0, int win, uint8_t* s_win) {
+__device__ __host__ __forceinline__ int win_pitch(int win) { return (win + 1 + 15 + 15) / 16 * 16; }   // image window: room for a 0..15 column offset, 16-byte rows
+__device__ __host__ __forceinline__ int der_pitch(int win) { return (win + 1 + 3 + 3) / 4 * 4; }        // derivative window: 0..3 entries of offset, 16-byte rows
+// where pixel (x, y) of a staged window sits: s_win[y * pitch + x + (uniform ? off : (off + y * w) & 3)]
+struct WinRef { unsigned off; bool uniform; };
+// a window inside the image needs no reflection: it can come through the level's tensor map (if it has one)
+__device__ __forceinline__ bool win_tma_ok(const LevelView& L, int x0, int y0, int win) {
+  return L.imgMap != nullptr && x0 >= 0 && y0 >= 0 && x0 + win + 1 <= L.w && y0 + win + 1 <= L.h;
+}
+// the generic-proxy staging: aligned 32-bit words inside the image (every row keeps the source's word alignment), reflect-101 bytes
+// at the border
+__device__ __forceinline__ WinRef stage_window(const LevelView& L, int x0, int y0, int win, uint8_t* s_win) {
   const int lane = threadIdx.x & 31, ww = win + 1, pitch = win_pitch(win);
   const bool inside = x0 >= 0 && y0 >= 0 && x0 + ww <= L.w && y0 + ww <= L.h;
-  unsigned a0 = NO_SHIFT;
+  WinRef ref;
+  ref.off = 0; ref.uniform = true;
   if (inside) {
     const uint8_t* p0 = L.img + (size_t)y0 * L.w + x0;
-    a0 = (unsigned)(reinterpret_cast<size_t>(p0) & 3);
-    const int wpr = pitch / 4;
+    ref.off = (unsigned)(reinterpret_cast<size_t>(p0) & 3);
+    ref.uniform = (L.w & 3) == 0;
+    const int wprS = pitch / 4, nW = (ww + 3 + 3) >> 2;   // words per shared-memory row / words copied per row (covers any alignment)
     int r = 0, k = lane;
-    while (k >= wpr) { k -= wpr; r++; }
-    for (int i = lane; i < ww * wpr; i += 32) {
+    while (k >= nW) { k -= nW; r++; }
+    for (int i = lane; i < ww * nW; i += 32) {
       const uint8_t* row = p0 + (size_t)r * L.w;
       const unsigned* src = reinterpret_cast<const unsigned*>(row - (reinterpret_cast<size_t>(row) & 3));
-      reinterpret_cast<unsigned*>(s_win)[r * wpr + k] = __ldg(src + k);
+      reinterpret_cast<unsigned*>(s_win)[r * wprS + k] = __ldg(src + k);
       k += 32;
-      while (k >= wpr) { k -= wpr; r++; }
+      while (k >= nW) { k -= nW; r++; }
     }
   } else {
     // rows outer, lanes over the columns: the reflected column of a lane is the same for every row
@@ -315,15 +368,15 @@ __device__ __forceinline__ unsigned stage_window(const LevelView& L, int x0, int
     }
   }
   __syncwarp();
-  return a0;
+  return ref;
 }
-__device__ __forceinline__ const uint8_t* win_px(const uint8_t* s_win, int pitch, unsigned a0, int w, int x, int y) {
-  return s_win + y * pitch + x + (a0 == NO_SHIFT ? 0 : (int)((a0 + (unsigned)(y * w)) & 3u));
+__device__ __forceinline__ const uint8_t* win_px(const uint8_t* s_win, int pitch, WinRef ref, int w, int x, int y) {
+  return s_win + y * pitch + x + (ref.uniform ? (int)ref.off : (int)((ref.off + (unsigned)(y * w)) & 3u));
 }
 // One pyramid level.  (nx, ny) in/out as OpenCV's nextPts[ptidx]; status / err updated as the invoker does.
 __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int maxLevel, int win, int maxCount, float eps2,
                          bool useInitial, float px, float py, float& nx, float& ny, int& status, float& err, short* s_I, short2* s_dI,
-                         uint8_t* s_win) {
+                         uint8_t* s_win, WarpTma& T) {
   const int lane = threadIdx.x & 31;
   const float halfWin = (win - 1) * 0.5f;
   const float sc = (float)(1. / (1 << level));
@@ -350,15 +403,25 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
   int iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS));
   int iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
   __syncwarp();
-  const int pitch = win_pitch(win);
-  const unsigned aI = stage_window(I, ipx, ipy, win, s_win);
+  const int pitch = win_pitch(win), DP = der_pitch(win), ww = win + 1;
+  // template side: the image window and the (win+1)^2 derivative window (zero outside the image: derivBorder = BORDER_CONSTANT).
+  // Through the tensor maps both are in flight together (one transaction phase); otherwise row loops.
+  const bool tI = win_tma_ok(I, ipx, ipy, win), tD = I.derMap != nullptr;
+  if ((tI || tD) && lane == 0) {
+    tma_expect(T, (uint32_t)((tI ? pitch * ww : 0) + (tD ? DP * ww * 4 : 0)));
+    if (tI) tma_load3(T, I.imgMap, s_win, ipx & ~15, ipy, I.frame);
+    if (tD) tma_load3(T, I.derMap, s_dI, ipx & ~3, ipy, I.frame);
+  }
+  WinRef aI;
+  aI.off = (unsigned)(ipx & 15); aI.uniform = true;
+  if (!tI) aI = stage_window(I, ipx, ipy, win, s_win);
+  const int dOff = tD ? (ipx & 3) : 0;   // column of the window's first entry inside its staged row
   long long sA11 = 0, sA12 = 0, sA22 = 0;
   {
-    // the (win+1)^2 derivative window (zero outside the image: derivBorder = BORDER_CONSTANT) goes to shared memory
-    // row by row, then is interpolated IN PLACE: output (x, y) needs inputs (x..x+1, y..y+1), which no later output of
-    // the raster order reads once this batch of 32 has loaded them
+    // the derivative window is interpolated IN PLACE: output (x, y) is written to entry (x, y) of the row and needs the inputs at
+    // (dOff + x .. + 1, y .. y + 1), which no later output of the raster order reads once this batch of 32 has loaded them
     const int dw = win + 1;
-    {
+    if (!tD) {
       // columns 0..31: one row per trip, every lane its own column (the column test is loop-invariant)
       const int X = ipx + lane;
       const bool colIn = lane < dw && X >= 0 && X < I.w;
@@ -366,7 +429,7 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
         const int Y = ipy + y;
         short2 v = make_short2(0, 0);
         if (colIn && Y >= 0 && Y < I.h) v = I.der[(size_t)Y * I.w + X];
-        if (lane < dw) s_dI[y * dw + lane] = v;
+        if (lane < dw) s_dI[y * DP + lane] = v;
       }
       // the columns beyond 32 (four of them for the 35 x 35 window): flattened over the lanes instead of a second
       // trip per row with four lanes at work
@@ -374,9 +437,10 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
       for (int i = lane; i < rem * dw; i += 32) {
         const int y = rem == 4 ? (i >> 2) : i / rem, x = 32 + i - y * rem;
         const int X2 = ipx + x, Y = ipy + y;
-        s_dI[y * dw + x] = (Y >= 0 && Y < I.h && X2 >= 0 && X2 < I.w) ? I.der[(size_t)Y * I.w + X2] : make_short2(0, 0);
+        s_dI[y * DP + x] = (Y >= 0 && Y < I.h && X2 >= 0 && X2 < I.w) ? I.der[(size_t)Y * I.w + X2] : make_short2(0, 0);
       }
     }
+    if (tI || tD) tma_wait(T);
     __syncwarp();
     int x = lane, y = 0;
     while (x >= win) { x -= win; y++; }
@@ -386,7 +450,8 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
       const bool valid = i < n;
       int ival = 0, ixval = 0, iyval = 0;
       if (valid) {
-        const short2 d00 = s_dI[y * dw + x], d01 = s_dI[y * dw + x + 1], d10 = s_dI[(y + 1) * dw + x], d11 = s_dI[(y + 1) * dw + x + 1];
+        const short2* dr = s_dI + y * DP + dOff + x;
+        const short2 d00 = dr[0], d01 = dr[1], d10 = dr[DP], d11 = dr[DP + 1];
         const uint8_t* s0 = win_px(s_win, pitch, aI, I.w, x, y);
         const uint8_t* s1 = win_px(s_win, pitch, aI, I.w, x, y + 1);
         ival = descale(s0[0] * iw00 + s0[1] * iw01 + s1[0] * iw10 + s1[1] * iw11, W_BITS - 5);
@@ -397,7 +462,7 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
       __syncwarp();
       if (valid) {
         s_I[i] = (short)ival;
-        s_dI[y * dw + x] = make_short2((short)ixval, (short)iyval);
+        s_dI[y * DP + x] = make_short2((short)ixval, (short)iyval);
       }
       __syncwarp();
       x += 32;
@@ -417,7 +482,8 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
   nextx -= halfWin; nexty -= halfWin;
   float pdx = 0, pdy = 0;
   int stagedX = INT_MIN, stagedY = INT_MIN;   // origin of the J window s_win holds (it held the I window until here)
-  unsigned aJ = NO_SHIFT;
+  WinRef aJ;
+  aJ.off = 0; aJ.uniform = true;
   for (int j = 0; j < maxCount; j++) {
     const int inx = (int)floorf(nextx), iny = (int)floorf(nexty);
     if (inx < -win || inx >= J.w || iny < -win || iny >= J.h) {
@@ -433,11 +499,20 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
     // the window is staged again only when its integer origin moved: once the iteration is down to sub-pixel steps
     // (most of its trips) the bytes in shared memory are already the ones it needs
     if (inx != stagedX || iny != stagedY) {
-      aJ = stage_window(J, inx, iny, win, s_win);
+      if (win_tma_ok(J, inx, iny, win)) {
+        if (lane == 0) {
+          tma_expect(T, (uint32_t)(pitch * ww));
+          tma_load3(T, J.imgMap, s_win, inx & ~15, iny, J.frame);
+        }
+        aJ.off = (unsigned)(inx & 15); aJ.uniform = true;
+        tma_wait(T);
+      } else {
+        aJ = stage_window(J, inx, iny, win, s_win);
+      }
       stagedX = inx; stagedY = iny;
     }
     long long sb1 = 0, sb2 = 0;
-    if (((win * win + 31) >> 5) <= 64 && (aJ == NO_SHIFT || (J.w & 3) == 0)) {
+    if (((win * win + 31) >> 5) <= 64 && aJ.uniform) {
       // Common case (level widths that are multiples of 4, or a reflected window): every staged row has the same
       // misalignment, so a pixel's address is one multiply-add; and a lane's <= 64 products (|diff| <= 8160 =
       // 255 * 32, |d| <= 4080 = 16 * 255: each < 2^25) sum exactly in 32 bits.
@@ -445,7 +520,7 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
       // 32nd pixel: the left column of a pixel's 2 x 2 neighbourhood is the right column of the pixel before it, so a step
       // loads two new bytes instead of four and advances its pointers by one (the sums are exact integers: any order gives
       // the same bits).
-      const uint8_t* wbase = s_win + (aJ == NO_SHIFT ? 0 : (int)aJ);
+      const uint8_t* wbase = s_win + (int)aJ.off;
       int a1 = 0, a2 = 0;
       const int n = win * win, per = (n + 31) >> 5;
       int i = lane * per;
@@ -453,7 +528,7 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
       if (i < iend) {
         int y = i / win, x = i - y * win;
         const uint8_t* s0 = wbase + y * pitch + x;
-        const short2* dp = s_dI + y * (win + 1) + x;
+        const short2* dp = s_dI + y * DP + x;
         int p00 = s0[0], p10 = s0[pitch];
         for (; i < iend; i++) {
           const int p01 = s0[1], p11 = s0[pitch + 1];
@@ -463,7 +538,7 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
           a2 += diff * d.y;
           if (++x == win) {   // next row: skip the window's extra column, reload the left column
             x = 0;
-            s0 += pitch - win + 1; dp += 2;
+            s0 += pitch - win + 1; dp += DP - win + 1;
             p00 = s0[0]; p10 = s0[pitch];
           } else {
             s0++; dp++;
@@ -479,7 +554,7 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
         const uint8_t* s0 = win_px(s_win, pitch, aJ, J.w, x, y);
         const uint8_t* s1 = win_px(s_win, pitch, aJ, J.w, x, y + 1);
         const int diff = descale(s0[0] * iw00 + s0[1] * iw01 + s1[0] * iw10 + s1[1] * iw11, W_BITS - 5) - s_I[i];
-        const short2 d = s_dI[y * (win + 1) + x];
+        const short2 d = s_dI[y * DP + x];
         sb1 += (long long)(diff * d.x);  // |diff| < 2^14, |d| < 2^13: the product fits an int
         sb2 += (long long)(diff * d.y);
         x += 32;
@@ -512,17 +587,30 @@ struct TrackArgs {
 };
 
 // mode fb = 0: cv::calcOpticalFlowPyrLK(prev, cur) with OPTFLOW_LK_GET_MIN_EIGENVALS; fb = 1: ORBmatcher::fbKltTracking
-__global__ void __launch_bounds__(TRACK_WARPS * 32) k_klt_track(TrackArgs A, PyrGeom G) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  const int warp = threadIdx.x >> 5;
+__device__ __host__ __forceinline__ size_t up128(size_t v) { return (v + 127) / 128 * 128; }
+__global__ void __launch_bounds__(TRACK_WARPS * 32) k_klt_track(TrackArgs A, PyrGeom G, const __grid_constant__ KltMaps M) {
+  extern __shared__ __align__(16) unsigned char s_raw0[];
+  __shared__ __align__(8) unsigned long long s_bar[TRACK_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f = blockIdx.y, p = blockIdx.x * TRACK_WARPS + warp;
   if (p >= A.n[f]) return;
   const int win = A.win, ww = win + 1;
-  const size_t perWarp = ((size_t)ww * ww * 4 + (size_t)win * win * 2 + (size_t)ww * win_pitch(win) + 15) / 16 * 16;
-  unsigned char* base = s_raw + perWarp * warp;
+  // per warp: derivative window / template derivatives, image window, template intensities -- each on a 128-byte boundary
+  // (the tensor-map loads want their destination aligned)
+  unsigned char* s_raw = s_raw0 + ((128u - ((uint32_t)__cvta_generic_to_shared(s_raw0) & 127u)) & 127u);
+  const size_t szD = up128((size_t)der_pitch(win) * ww * 4), szW = up128((size_t)win_pitch(win) * ww), szI = up128((size_t)win * win * 2);
+  unsigned char* base = s_raw + (szD + szW + szI) * warp;
   short2* s_dI = reinterpret_cast<short2*>(base);
-  uint8_t* s_win = base + (size_t)ww * ww * 4;                         // word-aligned: staged with 32-bit stores
-  short* s_I = reinterpret_cast<short*>(s_win + (size_t)ww * win_pitch(win));
+  uint8_t* s_win = base + szD;
+  short* s_I = reinterpret_cast<short*>(base + szD + szW);
+  WarpTma T;
+  T.bar = (uint32_t)__cvta_generic_to_shared(&s_bar[warp]);
+  T.parity = 0u;
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(T.bar), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
   const uint8_t* P = A.prevPyr + (size_t)f * G.frameBytes;
   const uint8_t* C = A.curPyr + (size_t)f * G.frameBytes;
   const size_t o = (size_t)f * A.stride + p;
@@ -532,9 +620,8 @@ __global__ void __launch_bounds__(TRACK_WARPS * 32) k_klt_track(TrackArgs A, Pyr
   float err = 0;
   const int maxLevel = min(A.maxLevel, G.levels);
   for (int l = maxLevel; l >= 0; l--)
-    lk_level(level_view(P, G, l), level_view(C, G, l), l, maxLevel, win, A.maxCount, A.eps2, A.useInitial != 0, kx, ky, nx, ny, status, err,
-             s_I, s_dI, s_win);
-  const int lane = threadIdx.x & 31;
+    lk_level(level_view(P, G, l, M, 0, f), level_view(C, G, l, M, 1, f), l, maxLevel, win, A.maxCount, A.eps2, A.useInitial != 0, kx, ky, nx,
+             ny, status, err, s_I, s_dI, s_win, T);
   if (!A.fb) {
     if (lane == 0) { A.next[2 * o] = nx; A.next[2 * o + 1] = ny; A.status[o] = (uint8_t)status; if (A.err) A.err[o] = err; }
     return;
@@ -544,7 +631,8 @@ __global__ void __launch_bounds__(TRACK_WARPS * 32) k_klt_track(TrackArgs A, Pyr
   if (ok) {
     float bx = kx, by = ky, err2 = 0;
     int st2 = 1;
-    lk_level(level_view(C, G, 0), level_view(P, G, 0), 0, 0, win, A.maxCount, A.eps2, true, nx, ny, bx, by, st2, err2, s_I, s_dI, s_win);
+    lk_level(level_view(C, G, 0, M, 1, f), level_view(P, G, 0, M, 0, f), 0, 0, win, A.maxCount, A.eps2, true, nx, ny, bx, by, st2, err2, s_I, s_dI,
+             s_win, T);
     const double ddx = (double)kx - (double)bx, ddy = (double)ky - (double)by;
     ok = st2 != 0 && !(sqrt(ddx * ddx + ddy * ddy) > (double)A.fbDist);
   }
@@ -627,12 +715,53 @@ int gfs_klt_build_pyramid_batch_device(GfsKlt* h, void* stream, const uint8_t* d
   return GFS_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tmap_encoder() {
+  static EncodeTiledFn fn = [] {
+    if (const char* e = getenv("GFS_KLT_TMAP")) if (atoi(e) == 0) return (EncodeTiledFn) nullptr;   // A/B runs: row loops only
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return (EncodeTiledFn) nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+// one pyramid level of `frames` frames as a rank-3 tensor (x, y, frame) of `esize`-byte entries; false: no map possible
+static bool encode_level_map(CUtensorMap* m, const void* base, int esize, int w, int hgt, int frames, size_t frameStride, int boxW, int boxH) {
+  EncodeTiledFn enc = tmap_encoder();
+  const size_t pitch = (size_t)w * esize;
+  if (!enc || (((uintptr_t)base | pitch | frameStride) & 15) != 0 || frameStride < pitch * hgt || boxW > 256 || boxH > 256 ||
+      ((boxW * esize) & 15))
+    return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)hgt, (cuuint64_t)frames};
+  const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frameStride};
+  const cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1u};
+  const cuuint32_t es[3] = {1u, 1u, 1u};
+  return enc(m, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int launch_track(GfsKlt* h, cudaStream_t st, const TrackArgs& A, const PyrGeom& g, int batch, int maxPts) {
   const int win = A.win, ww = win + 1;
-  const size_t perWarp = align_up((size_t)ww * ww * 4 + (size_t)win * win * 2 + (size_t)ww * ((ww + 6) / 4 * 4), 16);
-  const size_t smem = perWarp * TRACK_WARPS;
+  const size_t perWarp = up128((size_t)der_pitch(win) * ww * 4) + up128((size_t)win_pitch(win) * ww) + up128((size_t)win * win * 2);
+  const size_t smem = perWarp * TRACK_WARPS + 128;   // + the slack the kernel uses to align its window to 128 bytes
   if (smem > 48 * 1024) GFS_CUDA(cudaFuncSetAttribute(k_klt_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_klt_track<<<dim3(div_up(maxPts, TRACK_WARPS), batch), TRACK_WARPS * 32, smem, st>>>(A, g);
+  KltMaps M;
+  memset(&M, 0, sizeof(M));
+  for (int which = 0; which < 2; which++) {
+    const uint8_t* pyr = which ? A.curPyr : A.prevPyr;
+    for (int l = 0; l <= g.levels && l < KLT_MAP_LEVELS; l++) {
+      if (encode_level_map(&M.img[which][l], pyr + g.off[l], 1, g.w[l], g.h[l], batch, g.frameBytes, win_pitch(win), ww))
+        M.imgMask[which] |= 1u << l;
+      if (encode_level_map(&M.der[which][l], pyr + g.imgBytes + (size_t)4 * g.off[l], 4, g.w[l], g.h[l], batch, g.frameBytes, der_pitch(win), ww))
+        M.derMask[which] |= 1u << l;
+    }
+  }
+  k_klt_track<<<dim3(div_up(maxPts, TRACK_WARPS), batch), TRACK_WARPS * 32, smem, st>>>(A, g, M);
   h->launches++;
   GFS_CUDA(cudaGetLastError());
   return GFS_OK;
