@@ -1183,7 +1183,7 @@ def run_track(args):
         if host:
             o_res.copy_(d_res, non_blocking=True)                                     # GICP results (the pose / BA calls return theirs)
             s_main.synchronize()                                                      # the step's results are on the host
-        counts["orb"] = orb.launches_per_call(); counts["match"] = 2; counts["klt"] = 5 + 1; counts["imu"] = 1   # this library's kernels only
+        counts["orb"] = orb.launches_per_call(); counts["match"] = 2; counts["klt"] = 6 + 1; counts["imu"] = 1   # this library's kernels only
 
     def barrier():
         if world > 1:

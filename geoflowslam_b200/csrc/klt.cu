@@ -44,8 +44,15 @@ struct PyrGeom {
   int npix;                   // total pixels over all levels
   int tilesX[MAX_LEVELS + 1], tileBase[MAX_LEVELS + 2];  // 128x32 tiles of k_klt_scharr: per-level grid width and first block
   size_t imgBytes;            // npix rounded up to 16: the derivatives start there
-  size_t frameBytes;          // imgBytes + 4 * npix
+  size_t derEnd;              // imgBytes + 4 * npix rounded up to 16: the padded level copies start there
+  // every level once more with a reflect-101 border of KLT_PAD_X / KLT_PAD_Y pixels (what cv::buildOpticalFlowPyramid's
+  // copyMakeBorder produces), row pitch a multiple of 16 bytes: a tracking window that leaves the image is then an ordinary
+  // box of the padded copy, and EVERY image window can come through the tensor-map path
+  int padW[MAX_LEVELS + 1], padH[MAX_LEVELS + 1];
+  size_t padOff[MAX_LEVELS + 1];   // byte offset inside the frame
+  size_t frameBytes;
 };
+static const int KLT_PAD_X = 48, KLT_PAD_Y = 40;   // >= the largest window the padded path serves (win + 1 <= 36 ... 40)
 
 static PyrGeom make_geom(int w, int h, int levels) {
   PyrGeom g;
@@ -66,7 +73,15 @@ static PyrGeom make_geom(int w, int h, int levels) {
   }
   g.tileBase[levels + 1] = tb;
   g.imgBytes = align_up((size_t)off, 16);
-  g.frameBytes = align_up(g.imgBytes + (size_t)4 * off, 16);
+  g.derEnd = align_up(g.imgBytes + (size_t)4 * off, 16);
+  size_t po = g.derEnd;
+  for (int l = 0; l <= levels; l++) {
+    g.padW[l] = (int)align_up((size_t)g.w[l] + 2 * KLT_PAD_X, 16);
+    g.padH[l] = g.h[l] + 2 * KLT_PAD_Y;
+    g.padOff[l] = po;
+    po += (size_t)g.padW[l] * g.padH[l];
+  }
+  g.frameBytes = align_up(po, 16);
   return g;
 }
 
@@ -212,6 +227,27 @@ __global__ void __launch_bounds__(PD_TX * PD_TY) k_klt_pyr_down(uint8_t* __restr
 // pixels and writes them as one 16-byte store when the level's geometry allows it.  HBM-bound: 1 byte read + 4 bytes
 // written per pixel.
 static const int SC_TX = 128, SC_TY = 32;
+// the padded copies of all levels: 16 bytes of a row per thread
+__global__ void __launch_bounds__(256) k_klt_pad_level(uint8_t* __restrict__ pyr, PyrGeom G) {
+  const int l = blockIdx.z;   // one launch for all levels: the grid is sized for level 0, the CTAs beyond a level's size retire
+  const int w = G.w[l], h = G.h[l], pw = G.padW[l], ph = G.padH[l];
+  const int groups = pw / 16;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups * ph) return;
+  const int y = i / groups, gx = (i - y * groups) * 16;
+  const uint8_t* src = pyr + (size_t)blockIdx.y * G.frameBytes + G.off[l] + (size_t)reflect101(y - KLT_PAD_Y, h) * w;
+  uint8_t* dst = pyr + (size_t)blockIdx.y * G.frameBytes + G.padOff[l] + (size_t)y * pw + gx;
+  unsigned v[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    unsigned word = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) word |= (unsigned)src[reflect101(gx + 4 * k + b - KLT_PAD_X, w)] << (8 * b);
+    v[k] = word;
+  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
+}
+
 __global__ void __launch_bounds__(256) k_klt_scharr(uint8_t* __restrict__ pyr, PyrGeom G) {
   __shared__ __align__(16) uint8_t s_t[SC_TY + 2][SC_TX + 8];  // column c of the tile at [.][c + 4]: words stay aligned
   int b = blockIdx.x, l = 0;
@@ -333,9 +369,9 @@ __device__ __host__ __forceinline__ int win_pitch(int win) { return (win + 1 + 1
 __device__ __host__ __forceinline__ int der_pitch(int win) { return (win + 1 + 3 + 3) / 4 * 4; }        // derivative window: 0..3 entries of offset, 16-byte rows
 // where pixel (x, y) of a staged window sits: s_win[y * pitch + x + (uniform ? off : (off + y * w) & 3)]
 struct WinRef { unsigned off; bool uniform; };
-// a window inside the image needs no reflection: it can come through the level's tensor map (if it has one)
+// the image maps describe the PADDED level copies (reflect-101 border): any window within the border is a plain box of them
 __device__ __forceinline__ bool win_tma_ok(const LevelView& L, int x0, int y0, int win) {
-  return L.imgMap != nullptr && x0 >= 0 && y0 >= 0 && x0 + win + 1 <= L.w && y0 + win + 1 <= L.h;
+  return L.imgMap != nullptr && x0 >= -KLT_PAD_X && y0 >= -KLT_PAD_Y && x0 + win + 1 <= L.w + KLT_PAD_X && y0 + win + 1 <= L.h + KLT_PAD_Y;
 }
 // the generic-proxy staging: aligned 32-bit words inside the image (every row keeps the source's word alignment), reflect-101 bytes
 // at the border
@@ -409,11 +445,11 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
   const bool tI = win_tma_ok(I, ipx, ipy, win), tD = I.derMap != nullptr;
   if ((tI || tD) && lane == 0) {
     tma_expect(T, (uint32_t)((tI ? pitch * ww : 0) + (tD ? DP * ww * 4 : 0)));
-    if (tI) tma_load3(T, I.imgMap, s_win, ipx & ~15, ipy, I.frame);
+    if (tI) tma_load3(T, I.imgMap, s_win, (ipx + KLT_PAD_X) & ~15, ipy + KLT_PAD_Y, I.frame);
     if (tD) tma_load3(T, I.derMap, s_dI, ipx & ~3, ipy, I.frame);
   }
   WinRef aI;
-  aI.off = (unsigned)(ipx & 15); aI.uniform = true;
+  aI.off = (unsigned)((ipx + KLT_PAD_X) & 15); aI.uniform = true;
   if (!tI) aI = stage_window(I, ipx, ipy, win, s_win);
   const int dOff = tD ? (ipx & 3) : 0;   // column of the window's first entry inside its staged row
   long long sA11 = 0, sA12 = 0, sA22 = 0;
@@ -502,9 +538,9 @@ __device__ void lk_level(const LevelView& I, const LevelView& J, int level, int 
       if (win_tma_ok(J, inx, iny, win)) {
         if (lane == 0) {
           tma_expect(T, (uint32_t)(pitch * ww));
-          tma_load3(T, J.imgMap, s_win, inx & ~15, iny, J.frame);
+          tma_load3(T, J.imgMap, s_win, (inx + KLT_PAD_X) & ~15, iny + KLT_PAD_Y, J.frame);
         }
-        aJ.off = (unsigned)(inx & 15); aJ.uniform = true;
+        aJ.off = (unsigned)((inx + KLT_PAD_X) & 15); aJ.uniform = true;
         tma_wait(T);
       } else {
         aJ = stage_window(J, inx, iny, win, s_win);
@@ -711,6 +747,8 @@ int gfs_klt_build_pyramid_batch_device(GfsKlt* h, void* stream, const uint8_t* d
   }
   k_klt_scharr<<<dim3(g.tileBase[g.levels + 1], batch), 256, 0, st>>>(d_pyr, g);
   h->launches++;
+  k_klt_pad_level<<<dim3(div_up(g.padW[0] / 16 * g.padH[0], 256), batch, g.levels + 1), 256, 0, st>>>(d_pyr, g);
+  h->launches++;
   GFS_CUDA(cudaGetLastError());
   return GFS_OK;
 }
@@ -755,7 +793,8 @@ static int launch_track(GfsKlt* h, cudaStream_t st, const TrackArgs& A, const Py
   for (int which = 0; which < 2; which++) {
     const uint8_t* pyr = which ? A.curPyr : A.prevPyr;
     for (int l = 0; l <= g.levels && l < KLT_MAP_LEVELS; l++) {
-      if (encode_level_map(&M.img[which][l], pyr + g.off[l], 1, g.w[l], g.h[l], batch, g.frameBytes, win_pitch(win), ww))
+      if (ww <= std::min(KLT_PAD_X, KLT_PAD_Y) &&
+          encode_level_map(&M.img[which][l], pyr + g.padOff[l], 1, g.padW[l], g.padH[l], batch, g.frameBytes, win_pitch(win), ww))
         M.imgMask[which] |= 1u << l;
       if (encode_level_map(&M.der[which][l], pyr + g.imgBytes + (size_t)4 * g.off[l], 4, g.w[l], g.h[l], batch, g.frameBytes, der_pitch(win), ww))
         M.derMask[which] |= 1u << l;

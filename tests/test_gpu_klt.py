@@ -92,7 +92,7 @@ def test_fb_klt_tracking_matches_oracle_bitwise():
         pr_o, st_o = O.fb_klt_tracking(pa, pb, 640, 480, 3, pts, pts)
         assert np.array_equal(st_g, st_o) and np.array_equal(pr_g, pr_o)
         assert st_g.sum() > 0.5 * len(pts)
-    assert trk.last_launches() == 11  # two pyramids (copy + 3 pyrDown + 1 Scharr each) + ONE tracking launch
+    assert trk.last_launches() == 13  # two pyramids (copy + 3 pyrDown + 1 Scharr + 1 padded copies each) + ONE tracking launch
     pr_e, st_e = trk.fbKltTracking(fr[0], fr[1], np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32))
     assert len(pr_e) == 0 and len(st_e) == 0
 
