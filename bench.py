@@ -958,9 +958,10 @@ def run_track(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    # sequences per GPU and step: 256 measured best (3937 / 4070 / 4178 / 4107 frames/s device-resident and 3820 / 4066 / 3951 / 3960 end
-    # to end at 128 / 256 / 384 / 512; the LM rounds' small-grid tails and the latency-bound BA / pose launches amortise)
-    B = args.batch if args.batch != 1024 else 256
+    # sequences per GPU and step: 512 (end of round 2: 6591 / 6707 / 6755 frames/s device-resident and 6175 / 6486 / 6591 end to end at
+    # 256 / 384 / 512 -- the LM rounds' small-grid tails, the latency-bound BA / pose launches and the end-of-step synchronisation of
+    # the host-buffer path amortise; mid-round, with the slower kernels, 256 had been the best: 4070 / 4178 / 4107 and 4066 / 3951 / 3960)
+    B = args.batch if args.batch != 1024 else 512
     cores = os.cpu_count() or 1
     uniq = min(B, 16)
     # Weak scaling = the same work on every GPU.  GICP's cost is data dependent (3 to 20 LM iterations per pair; measured 33.7 to
