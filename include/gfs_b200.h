@@ -445,8 +445,11 @@ int gfs_pose_inertial_last_launches(const GfsPoseInertial* h);
  * ORBmatcher.cc:2399,2463) is NOT part of this entry point.
  * A frame's pyramid is one caller-owned device block of gfs_klt_pyramid_bytes() bytes: the images of levels
  * 0..levels tightly packed (level l is ((w+1)/2, (h+1)/2) of level l-1), then, 16-byte aligned, the int16
- * (dI/dx, dI/dy) Scharr derivatives in the same order -- what mImGray holds, without the winSize border (reads
- * outside the image follow the border rules of the padded OpenCV pyramid: reflect-101 image, zero derivative).
+ * (dI/dx, dI/dy) Scharr derivatives in the same order, then every level once more with the reflect-101 border
+ * cv::buildOpticalFlowPyramid's copyMakeBorder gives mImGray (48 x 40 pixels, row pitch a multiple of 16 bytes; the
+ * tracker fetches its windows from these copies with tensor-map TMA loads).  Reads outside the image follow the
+ * border rules of the padded OpenCV pyramid: reflect-101 image, zero derivative.  gfs_klt_pyramid_layout describes
+ * the first two parts (the ones with an OpenCV counterpart a caller may want to read).
  * ------------------------------------------------------------------------------------------------ */
 typedef struct GfsKlt GfsKlt;
 int gfs_klt_create(int max_w, int max_h, int levels, int max_points, int max_batch, GfsKlt** out);
