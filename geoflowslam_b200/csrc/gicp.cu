@@ -2104,15 +2104,21 @@ __global__ void __launch_bounds__(LIN_THREADS, MINB) k_linearize(GicpDev D) {
   for (int k = 0; k < RED_N; k++) acc[k] = 0.0;
   const double* T = D.state + (size_t)p * LM_STATE + S_T;
   // PPT points per thread, LIN_THREADS apart (coalesced), summed in that order before the warp reduction
+  // the correspondence of the NEXT point is fetched one trip ahead: a trip's gathers (target point, target covariance) then start
+  // at once instead of after the index load they depend on
+  const int* corr = D.corr + (size_t)p * D.nmax;
+  const int i0 = blockIdx.x * PPT * LIN_THREADS + threadIdx.x;
+  int tgtNext = i0 < ns ? corr[i0] : -1;
 #pragma unroll 1
   for (int j = 0; j < PPT; j++) {
-    const int i = (blockIdx.x * PPT + j) * LIN_THREADS + threadIdx.x;
+    const int i = i0 + j * LIN_THREADS;
     if (i >= ns) break;
+    const int tgt = tgtNext;
+    tgtNext = (j + 1 < PPT && i + LIN_THREADS < ns) ? corr[i + LIN_THREADS] : -1;
     const double* ps = D.pts + ((size_t)cs * D.nmax + i) * 4;
     double q[3];
     xform(T, ps, q);
     const Grid g = make_grid(D, ct);
-    const int tgt = D.corr[(size_t)p * D.nmax + i];
     if (tgt >= 0) {
       const double* cS = D.cov + ((size_t)cs * D.nmax + i) * 6;
       const double* cT = D.cov + ((size_t)ct * D.nmax + tgt) * 6;
